@@ -1,0 +1,591 @@
+"""Top-level config: JSON / HJSON / dict / base64 -> typed ``DeepSpeedConfig``.
+
+Parity target: reference ``runtime/config.py:707 DeepSpeedConfig`` (+ ``constants.py``).  All
+reference top-level keys listed in SURVEY.md 5.6 are accepted.  Unlike the reference (which
+mixes ``get_scalar_param`` getters with pydantic blocks), every block here is a pydantic model;
+the flat attribute names the reference engine reads (``fp16_enabled``, ``zero_optimization_stage``,
+``gradient_clipping`` ...) are exported as properties so ported user code keeps working.
+"""
+import base64
+import copy
+import json
+import os
+from typing import Any, Dict, List, Optional, Union
+
+import hjson
+from pydantic import Field
+
+from deepspeed_b200.comm.config import CommsConfig
+from deepspeed_b200.runtime.config_utils import (DeepSpeedConfigModel, ScientificNotationEncoder,
+                                                 dict_raise_error_on_duplicate_keys)
+from deepspeed_b200.runtime.zero.config import ZeroStageEnum, get_zero_config
+from deepspeed_b200.utils.logging import logger
+
+TORCH_ADAM_PARAM = "torch_adam"
+ADAM_W_MODE = "adam_w_mode"
+ADAM_W_MODE_DEFAULT = True
+
+ADAGRAD_OPTIMIZER = "adagrad"
+ADAM_OPTIMIZER = "adam"
+ADAMW_OPTIMIZER = "adamw"
+LAMB_OPTIMIZER = "lamb"
+ONEBIT_ADAM_OPTIMIZER = "onebitadam"
+ZERO_ONE_ADAM_OPTIMIZER = "zerooneadam"
+ONEBIT_LAMB_OPTIMIZER = "onebitlamb"
+MUADAM_OPTIMIZER = "muadam"
+MUADAMW_OPTIMIZER = "muadamw"
+MUSGD_OPTIMIZER = "musgd"
+LION_OPTIMIZER = "lion"
+SGD_OPTIMIZER = "sgd"
+DEEPSPEED_OPTIMIZERS = [
+    ADAGRAD_OPTIMIZER, ADAM_OPTIMIZER, ADAMW_OPTIMIZER, LAMB_OPTIMIZER, ONEBIT_ADAM_OPTIMIZER, ONEBIT_LAMB_OPTIMIZER,
+    ZERO_ONE_ADAM_OPTIMIZER, MUADAM_OPTIMIZER, MUADAMW_OPTIMIZER, MUSGD_OPTIMIZER, LION_OPTIMIZER, SGD_OPTIMIZER
+]
+
+ROUTE_TRAIN = "train"
+ROUTE_EVAL = "eval"
+ROUTE_PREDICT = "predict"
+ROUTE_ENCODE = "encode"
+
+
+class DeepSpeedConfigError(Exception):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# blocks
+# ------------------------------------------------------------------------------------------------
+class FP16Config(DeepSpeedConfigModel):
+    enabled: bool = False
+    auto_cast: bool = False
+    loss_scale: float = Field(0.0, ge=0)  # 0 == dynamic
+    initial_scale_power: int = Field(16, ge=0)
+    loss_scale_window: int = Field(1000, ge=0)
+    hysteresis: int = Field(2, ge=0)
+    consecutive_hysteresis: bool = False
+    min_loss_scale: float = Field(1.0, ge=0)
+    fp16_master_weights_and_grads: bool = False
+
+    @property
+    def dynamic_loss_scale(self):
+        return self.loss_scale == 0
+
+
+class BF16Config(DeepSpeedConfigModel):
+    enabled: bool = False
+    immediate_grad_update: bool = False
+    check_grad_overflow: bool = False
+
+
+class AMPConfig(DeepSpeedConfigModel):
+    model_config = dict(DeepSpeedConfigModel.model_config, extra="allow")
+    enabled: bool = False
+
+
+class DataTypesConfig(DeepSpeedConfigModel):
+    grad_accum_dtype: Optional[str] = None
+
+
+class OptimizerConfig(DeepSpeedConfigModel):
+    type: Optional[str] = None
+    params: Dict[str, Any] = {}
+    legacy_fusion: bool = False
+
+
+class SchedulerConfig(DeepSpeedConfigModel):
+    type: Optional[str] = None
+    params: Dict[str, Any] = {}
+
+
+class ActivationCheckpointingConfig(DeepSpeedConfigModel):
+    partition_activations: bool = False
+    contiguous_memory_optimization: bool = False
+    cpu_checkpointing: bool = False
+    number_checkpoints: Optional[int] = None
+    synchronize_checkpoint_boundary: bool = False
+    profile: bool = False
+
+
+class AIOConfig(DeepSpeedConfigModel):
+    block_size: int = 1048576
+    queue_depth: int = 8
+    intra_op_parallelism: int = Field(1, alias="thread_count")
+    single_submit: bool = False
+    overlap_events: bool = True
+    use_gds: bool = False
+
+
+class PipelineConfig(DeepSpeedConfigModel):
+    stages: Union[str, int] = "auto"
+    partition: str = "best"
+    seed_layers: bool = False
+    activation_checkpoint_interval: int = 0
+    pipe_partitioned: bool = True
+    grad_partitioned: bool = True
+    use_reentrant: bool = True
+
+
+class TensorParallelTPConfig(DeepSpeedConfigModel):
+    tp_size: int = 1
+    tp_grain_size: int = 1
+    mpu: Any = None
+    tp_group: Any = None
+
+
+class TensorParallelConfig(DeepSpeedConfigModel):
+    autotp_size: int = 0
+    tp: TensorParallelTPConfig = TensorParallelTPConfig()
+    tp_overlap_comm: bool = False
+    injection_policy_tuple: Optional[tuple] = None
+    keep_module_on_host: bool = False
+    replace_with_kernel_inject: bool = False
+
+
+class FlopsProfilerConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    recompute_fwd_factor: float = Field(0.0, ge=0.0)
+    profile_step: int = Field(1, ge=1)
+    module_depth: int = -1
+    top_modules: int = 1
+    detailed: bool = True
+    output_file: Optional[str] = None
+
+
+class TensorBoardConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    output_path: str = ""
+    job_name: str = "DeepSpeedJobName"
+
+
+class WandbConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    group: Optional[str] = None
+    team: Optional[str] = None
+    project: str = "deepspeed"
+
+
+class CSVConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    output_path: str = ""
+    job_name: str = "DeepSpeedJobName"
+
+
+class CometConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    samples_log_interval: int = 100
+    project: Optional[str] = None
+    workspace: Optional[str] = None
+    api_key: Optional[str] = None
+    experiment_name: Optional[str] = None
+    experiment_key: Optional[str] = None
+    online: Optional[bool] = None
+    mode: Optional[str] = None
+
+
+class MonitorConfig:
+
+    def __init__(self, d):
+        self.tensorboard = TensorBoardConfig(**d.get("tensorboard", {}))
+        self.wandb = WandbConfig(**d.get("wandb", {}))
+        self.csv_monitor = CSVConfig(**d.get("csv_monitor", {}))
+        self.comet = CometConfig(**d.get("comet", {}))
+
+    @property
+    def enabled(self):
+        return self.tensorboard.enabled or self.wandb.enabled or self.csv_monitor.enabled or self.comet.enabled
+
+
+class CheckpointParallelWriteConfig(DeepSpeedConfigModel):
+    pipeline_stage: bool = False
+
+
+class CheckpointConfig(DeepSpeedConfigModel):
+    tag_validation: str = "Warn"
+    load_universal: bool = False
+    use_node_local_storage: bool = False
+    parallel_write: CheckpointParallelWriteConfig = CheckpointParallelWriteConfig()
+    writer: Optional[Dict[str, Any]] = None  # async (FastPersist-style) writer selection
+
+
+class ThroughputTimerConfig(DeepSpeedConfigModel):
+    enabled: bool = True
+    synchronized: bool = True
+
+
+class TimersConfig(DeepSpeedConfigModel):
+    throughput: ThroughputTimerConfig = ThroughputTimerConfig()
+
+
+class HybridEngineConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    max_out_tokens: int = 512
+    inference_tp_size: int = 1
+    release_inference_cache: bool = False
+    pin_parameters: bool = True
+    tp_gather_partition_size: int = 8
+
+
+class NebulaConfig(DeepSpeedConfigModel):
+    enabled: bool = False
+    persistent_storage_path: Optional[str] = None
+    persistent_time_interval: int = 100
+    num_of_version_in_retention: int = 2
+    enable_nebula_load: bool = True
+    load_path: Optional[str] = None
+
+
+class CompileConfig(DeepSpeedConfigModel):
+    deepcompile: bool = False
+    free_activation: bool = False
+    offload_activation: bool = False
+    offload_opt_states: bool = False
+    double_buffer: bool = True
+    symmetric_memory: bool = False
+    debug_log: bool = False
+    offload_parameters: bool = False
+    sync_before_reduce: bool = False
+    sync_after_reduce: bool = False
+    sync_before_allgather: bool = False
+    sync_after_allgather: bool = False
+
+
+class CUDAGraphConfig(DeepSpeedConfigModel):
+    """B200-native addition: capture the optimizer step / small-model step in a CUDA graph."""
+    enabled: bool = False
+    capture_optimizer_step: bool = True
+    capture_full_step: bool = False
+    warmup_steps: int = 3
+
+
+# ------------------------------------------------------------------------------------------------
+# top level
+# ------------------------------------------------------------------------------------------------
+_PASSTHROUGH_DICT_BLOCKS = ("compression_training", "data_efficiency", "curriculum_learning", "progressive_layer_drop",
+                            "eigenvalue", "quantize_training", "sparse_attention", "weight_quantization", "autotuning",
+                            "elasticity", "moe", "zenflow")
+
+
+def _load_config_source(config: Union[str, dict, os.PathLike]) -> dict:
+    if isinstance(config, dict):
+        return copy.deepcopy(config)
+    if isinstance(config, (str, os.PathLike)) and os.path.exists(config):
+        with open(config, "r") as f:
+            return hjson.load(f, object_pairs_hook=dict_raise_error_on_duplicate_keys)
+    if isinstance(config, str):
+        try:
+            decoded = base64.urlsafe_b64decode(config).decode("utf-8")
+            return hjson.loads(decoded, object_pairs_hook=dict_raise_error_on_duplicate_keys)
+        except Exception:
+            pass
+        try:
+            return hjson.loads(config, object_pairs_hook=dict_raise_error_on_duplicate_keys)
+        except Exception:
+            pass
+    raise ValueError(f"Expected a string path to an existing deepspeed config, a dict, or a base64/json string. "
+                     f"Received: {config!r}")
+
+
+class DeepSpeedConfig:
+
+    def __init__(self, config: Union[str, dict], mpu=None, mesh_device=None):
+        self._param_dict = _load_config_source(config)
+        self.mesh_device = mesh_device
+        try:
+            from deepspeed_b200 import comm as dist
+            self.global_rank = dist.get_rank()
+            if mpu is not None:
+                if hasattr(mpu, "get_data_parallel_world_size"):
+                    self.world_size = mpu.get_data_parallel_world_size()
+                else:
+                    self.world_size = dist.get_world_size() // mpu.get_model_parallel_world_size()
+            elif mesh_device is not None:
+                self.world_size = dist.get_world_size(mesh_device.get_group(mesh_dim="data_parallel"))
+            else:
+                sp = int(self._param_dict.get("sequence_parallel_size", 1))
+                tp = int(self._param_dict.get("tensor_parallel", {}).get("autotp_size", 0)) or 1
+                pp = self._param_dict.get("pipeline", {}).get("stages", 1)
+                pp = 1 if not isinstance(pp, int) else pp
+                self.world_size = max(dist.get_world_size() // (sp * tp * max(pp, 1)), 1)
+                if "data_parallel_size" in self._param_dict:
+                    self.world_size = int(self._param_dict["data_parallel_size"])
+        except Exception:
+            self.global_rank = 0
+            self.world_size = 1
+        # elasticity may rewrite the batch parameters before they are parsed
+        self.elasticity_enabled = False
+        self._apply_elasticity()
+        self._initialize_params(self._param_dict)
+        self._configure_train_batch_size()
+        self._do_sanity_check()
+
+    # ---- elasticity --------------------------------------------------------------------
+    def _apply_elasticity(self):
+        pd = self._param_dict
+        el = pd.get("elasticity", {})
+        if not el or not el.get("enabled", False):
+            return
+        from deepspeed_b200.elasticity import compute_elastic_config, ensure_immutable_elastic_config
+        from deepspeed_b200.elasticity.constants import (IGNORE_NON_ELASTIC_BATCH_INFO,
+                                                         IGNORE_NON_ELASTIC_BATCH_INFO_DEFAULT)
+        from deepspeed_b200 import __version__
+        self.elasticity_enabled = True
+        ensure_immutable_elastic_config(runtime_elastic_config_dict=el)
+        final_batch, valid_gpus, micro = compute_elastic_config(ds_config=pd,
+                                                                target_deepspeed_version=__version__,
+                                                                world_size=self.world_size)
+        if not el.get(IGNORE_NON_ELASTIC_BATCH_INFO, IGNORE_NON_ELASTIC_BATCH_INFO_DEFAULT):
+            clash = [k for k in ("train_batch_size", "train_micro_batch_size_per_gpu", "gradient_accumulation_steps")
+                     if k in pd]
+            if clash:
+                raise DeepSpeedConfigError(
+                    f"One or more batch related parameters were found in your ds_config ({clash}). These parameters "
+                    f"*will not be used* since elastic training is enabled, which takes control of these parameters. "
+                    f"If you want to suppress this error (the parameters will be silently ignored) please set "
+                    f"'{IGNORE_NON_ELASTIC_BATCH_INFO}': true in your elasticity config.")
+        gas = final_batch // (micro * self.world_size)
+        logger.info(f"elasticity: train_batch_size={final_batch} micro_batch={micro} gas={gas} valid_gpus={valid_gpus}")
+        pd["train_batch_size"] = final_batch
+        pd["train_micro_batch_size_per_gpu"] = micro
+        pd["gradient_accumulation_steps"] = gas
+
+    # ---- parsing -----------------------------------------------------------------------
+    def _initialize_params(self, pd: dict):
+        g = pd.get
+        self.train_batch_size = g("train_batch_size", None)
+        self.train_micro_batch_size_per_gpu = g("train_micro_batch_size_per_gpu", None)
+        self.gradient_accumulation_steps = g("gradient_accumulation_steps", None)
+        self.steps_per_print = g("steps_per_print", None)
+        self.dump_state = g("dump_state", False)
+        self.disable_allgather = g("disable_allgather", False)
+        self.communication_data_type = _dtype_from_str(g("communication_data_type", None))
+        self.seq_parallel_communication_data_type = _dtype_from_str(g("seq_parallel_communication_data_type", "fp32"))
+        self.prescale_gradients = g("prescale_gradients", False)
+        self.gradient_predivide_factor = g("gradient_predivide_factor", 1.0)
+        self.sparse_gradients_enabled = g("sparse_gradients", False)
+        self.gradient_clipping = g("gradient_clipping", 0.0)
+        self.graph_harvesting = g("graph_harvesting", False)
+        self.wall_clock_breakdown = g("wall_clock_breakdown", False)
+        self.memory_breakdown = g("memory_breakdown", False)
+        self.dataloader_drop_last = g("dataloader_drop_last", False)
+        self.zero_allow_untested_optimizer = g("zero_allow_untested_optimizer", False)
+        self.zero_force_ds_cpu_optimizer = g("zero_force_ds_cpu_optimizer", True)
+        self.sequence_parallel_size = g("sequence_parallel_size", 1)
+        self.data_parallel_size = g("data_parallel_size", None)
+        self.use_data_before_expert_parallel_ = g("use_data_before_expert_parallelism", False)
+        self.vocabulary_size = g("vocabulary_size", 1e9)
+
+        self.zero_config = get_zero_config(pd)
+        self.zero_optimization_stage = int(self.zero_config.stage)
+        self.zero_enabled = self.zero_optimization_stage > 0
+        self.mics_shard_size = self.zero_config.mics_shard_size
+        self.mics_hierarchial_params_gather = self.zero_config.mics_hierarchical_params_gather
+
+        self.fp16_config = FP16Config(**g("fp16", {}))
+        bf = g("bf16", g("bfloat16", {}))
+        self.bf16_config = BF16Config(**bf)
+        self.amp_config = AMPConfig(**g("amp", {}))
+        self.data_types_config = DataTypesConfig(**g("data_types", {}))
+        self.optimizer_config = OptimizerConfig(**g("optimizer", {})) if g("optimizer") else OptimizerConfig()
+        self.scheduler_config = SchedulerConfig(**g("scheduler", {})) if g("scheduler") else SchedulerConfig()
+        self.activation_checkpointing_config = ActivationCheckpointingConfig(**g("activation_checkpointing", {}))
+        self.aio_config = AIOConfig(**g("aio", {}))
+        self.pipeline_config = PipelineConfig(**g("pipeline", {}))
+        self.pipeline = self.pipeline_config.model_dump()
+        self.tensor_parallel_config = TensorParallelConfig(**g("tensor_parallel", {}))
+        self.flops_profiler_config = FlopsProfilerConfig(**g("flops_profiler", {}))
+        self.monitor_config = MonitorConfig(pd)
+        self.comms_config = CommsConfig(pd)
+        self.checkpoint_config = CheckpointConfig(**g("checkpoint", {}))
+        self.timers_config = TimersConfig(**g("timers", {}))
+        self.hybrid_engine = HybridEngineConfig(**g("hybrid_engine", {}))
+        self.nebula_config = NebulaConfig(**g("nebula", {}))
+        self.compile_config = CompileConfig(**g("compile", {}))
+        self.cuda_graph_config = CUDAGraphConfig(**g("cuda_graph", {}))
+
+        for k in _PASSTHROUGH_DICT_BLOCKS:
+            setattr(self, f"{k}_params", copy.deepcopy(g(k, {})))
+        self.curriculum_enabled_legacy = bool(self.curriculum_learning_params.get("enabled", False))
+        self.curriculum_params_legacy = self.curriculum_learning_params
+        self.pld_enabled = bool(self.progressive_layer_drop_params.get("enabled", False))
+        self.pld_params = self.progressive_layer_drop_params if self.pld_enabled else False
+        ev = self.eigenvalue_params
+        self.eigenvalue_enabled = bool(ev.get("enabled", False))
+        self.eigenvalue_verbose = ev.get("verbose", False)
+        self.eigenvalue_max_iter = ev.get("max_iter", 100)
+        self.eigenvalue_tol = ev.get("tol", 1e-2)
+        self.eigenvalue_stability = ev.get("stability", 1e-6)
+        self.eigenvalue_gas_boundary_resolution = ev.get("gas_boundary_resolution", 1)
+        self.eigenvalue_layer_name = ev.get("layer_name", "bert.encoder.layer")
+        self.eigenvalue_layer_num = ev.get("layer_num", 0)
+        self.sparse_attention = self.sparse_attention_params or None
+        self.compression_config = self.compression_training_params
+        self.data_efficiency_enabled = bool(self.data_efficiency_params.get("enabled", False))
+        self.data_efficiency_config = self.data_efficiency_params
+        self.autotuning_config = self.autotuning_params
+        self.weight_quantization_config = self.weight_quantization_params or None
+
+        ckpt = self.checkpoint_config
+        self.checkpoint_tag_validation_enabled = ckpt.tag_validation.upper() != "IGNORE"
+        self.checkpoint_tag_validation_fail = ckpt.tag_validation.upper() == "FAIL"
+        if ckpt.tag_validation.upper() not in ("WARN", "IGNORE", "FAIL"):
+            raise DeepSpeedConfigError(f"Checkpoint config contains invalid tag_validation value of "
+                                       f"{ckpt.tag_validation}, expecting one of ['WARN', 'IGNORE', 'FAIL']")
+        self.load_universal_checkpoint = ckpt.load_universal
+        self.use_node_local_storage = ckpt.use_node_local_storage
+
+    # ---- flat aliases the reference engine exposes ---------------------------------------
+    @property
+    def fp16_enabled(self):
+        return self.fp16_config.enabled
+
+    @property
+    def fp16_auto_cast(self):
+        return self.fp16_config.auto_cast
+
+    @property
+    def fp16_master_weights_and_gradients(self):
+        return self.fp16_config.fp16_master_weights_and_grads
+
+    @property
+    def bfloat16_enabled(self):
+        return self.bf16_config.enabled
+
+    @property
+    def bfloat16_immediate_grad_update(self):
+        return self.bf16_config.immediate_grad_update
+
+    @property
+    def amp_enabled(self):
+        return self.amp_config.enabled
+
+    @property
+    def amp_params(self):
+        d = self.amp_config.model_dump()
+        d.update(self.amp_config.model_extra or {})
+        d.pop("enabled", None)
+        return d
+
+    @property
+    def loss_scale(self):
+        return self.fp16_config.loss_scale
+
+    @property
+    def initial_dynamic_scale(self):
+        return 2**self.fp16_config.initial_scale_power
+
+    @property
+    def dynamic_loss_scale_args(self):
+        c = self.fp16_config
+        if not c.enabled:
+            return None
+        return {
+            "init_scale": 2**c.initial_scale_power,
+            "scale_window": c.loss_scale_window,
+            "delayed_shift": c.hysteresis,
+            "consecutive_hysteresis": c.consecutive_hysteresis,
+            "min_scale": c.min_loss_scale,
+        }
+
+    @property
+    def grad_accum_dtype(self):
+        return self.data_types_config.grad_accum_dtype
+
+    @property
+    def optimizer_name(self):
+        t = self.optimizer_config.type
+        if t is None:
+            return None
+        return t.lower() if t.lower() in DEEPSPEED_OPTIMIZERS else t
+
+    @property
+    def optimizer_params(self):
+        return copy.deepcopy(self.optimizer_config.params) if self.optimizer_config.type else None
+
+    @property
+    def optimizer_legacy_fusion(self):
+        return self.optimizer_config.legacy_fusion
+
+    @property
+    def scheduler_name(self):
+        return self.scheduler_config.type
+
+    @property
+    def scheduler_params(self):
+        return copy.deepcopy(self.scheduler_config.params) if self.scheduler_config.type else None
+
+    # ---- batch triad (reference: config.py:936 _set_batch_related_parameters) ------------
+    def _configure_train_batch_size(self):
+        self._set_batch_related_parameters()
+        self._batch_assertion()
+
+    def _set_batch_related_parameters(self):
+        tb, mb, gas = self.train_batch_size, self.train_micro_batch_size_per_gpu, self.gradient_accumulation_steps
+        ws = self.world_size
+        if tb is not None and mb is not None and gas is not None:
+            return
+        if tb is not None and mb is not None:
+            gas = tb // mb // ws
+        elif tb is not None and gas is not None:
+            mb = tb // ws // gas
+        elif mb is not None and gas is not None:
+            tb = mb * gas * ws
+        elif tb is not None:
+            gas = 1
+            mb = tb // ws
+        elif mb is not None:
+            gas = 1
+            tb = mb * ws
+        else:
+            raise DeepSpeedConfigError("Either train_batch_size or train_micro_batch_size_per_gpu needs to be provided")
+        self.train_batch_size, self.train_micro_batch_size_per_gpu, self.gradient_accumulation_steps = tb, mb, gas
+
+    def _batch_assertion(self):
+        tb, mb, gas = self.train_batch_size, self.train_micro_batch_size_per_gpu, self.gradient_accumulation_steps
+        assert tb > 0, f"Train batch size: {tb} has to be greater than 0"
+        assert mb > 0, f"Micro batch size per gpu: {mb} has to be greater than 0"
+        assert gas > 0, f"Gradient accumulation steps: {gas} has to be greater than 0"
+        assert tb == mb * gas * self.world_size, (
+            f"Check batch related parameters. train_batch_size is not equal to micro_batch_per_gpu * gradient_acc_step"
+            f" * world_size {tb} != {mb} * {gas} * {self.world_size}")
+
+    def _do_sanity_check(self):
+        if self.fp16_enabled and self.bfloat16_enabled:
+            raise DeepSpeedConfigError("bf16 and fp16 modes cannot be simultaneously enabled")
+        if self.fp16_master_weights_and_gradients:
+            assert self.zero_enabled and self.zero_optimization_stage in (1, 2, 3), \
+                "fp16_master_weights_and_grads is only supported with ZeRO"
+        assert self.zero_optimization_stage <= ZeroStageEnum.max_stage, \
+            f"DeepSpeedConfig: Maximum supported ZeRO stage is {int(ZeroStageEnum.max_stage)}"
+        if self.steps_per_print is None:
+            self.steps_per_print = 10
+
+    # ---- output ------------------------------------------------------------------------
+    def print_user_config(self):
+        logger.info("  json = {}".format(
+            json.dumps(self._param_dict, sort_keys=True, indent=4, cls=ScientificNotationEncoder,
+                       separators=(",", ":"))))
+
+    def print(self, name):
+        logger.info(f"{name}:")
+        for arg in sorted(vars(self)):
+            if arg != "_param_dict":
+                logger.info(f"  {arg} {'.' * max(1, 29 - len(arg))} {getattr(self, arg)}")
+        self.print_user_config()
+
+
+def _dtype_from_str(s):
+    import torch
+    if s is None:
+        return None
+    table = {
+        "fp32": torch.float32,
+        "float32": torch.float32,
+        "fp16": torch.float16,
+        "float16": torch.float16,
+        "half": torch.float16,
+        "bf16": torch.bfloat16,
+        "bfloat16": torch.bfloat16,
+    }
+    if s not in table:
+        raise ValueError(f"Invalid communication_data_type. Supported data types: {sorted(table)}. Got: {s}")
+    return table[s]

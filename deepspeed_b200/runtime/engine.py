@@ -1,0 +1,620 @@
+"""``DeepSpeedEngine`` -- wraps a module for mixed-precision, ZeRO-sharded data-parallel training.
+
+Parity target: reference ``runtime/engine.py:184`` (forward / backward / step, optimizer + scheduler
+selection, gradient accumulation, dtype casting, timers, monitor, checkpoint save/load, 16-bit
+model export, ``no_sync``).  Architectural difference: every optimizer path (plain DP, bf16, fp16,
+ZeRO-1/2/3, offload) goes through ONE class, :class:`ZeroShardedOptimizer`, parameterised by
+stage; the engine therefore has no allreduce-bucket fallback code of its own.
+"""
+import contextlib
+import os
+import re
+from typing import Optional
+
+import torch
+from torch import nn
+
+from deepspeed_b200 import comm as dist
+from deepspeed_b200.accelerator import get_accelerator
+from deepspeed_b200.monitor.monitor import MonitorMaster
+from deepspeed_b200.runtime import lr_schedules
+from deepspeed_b200.runtime.checkpointing import CheckpointMixin
+from deepspeed_b200.runtime.config import (ADAGRAD_OPTIMIZER, ADAM_OPTIMIZER, ADAMW_OPTIMIZER, DeepSpeedConfig,
+                                           LAMB_OPTIMIZER, LION_OPTIMIZER, ONEBIT_ADAM_OPTIMIZER,
+                                           ONEBIT_LAMB_OPTIMIZER, SGD_OPTIMIZER, ZERO_ONE_ADAM_OPTIMIZER)
+from deepspeed_b200.runtime.dataloader import DeepSpeedDataLoader
+from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer
+from deepspeed_b200.utils import groups
+from deepspeed_b200.utils.logging import log_dist, logger
+from deepspeed_b200.utils.nvtx import instrument_w_nvtx
+from deepspeed_b200.utils.timer import (BACKWARD_GLOBAL_TIMER, BACKWARD_MICRO_TIMER, FORWARD_GLOBAL_TIMER,
+                                        FORWARD_MICRO_TIMER, NoopTimer, STEP_GLOBAL_TIMER, STEP_MICRO_TIMER,
+                                        SynchronizedWallClockTimer, ThroughputTimer)
+
+MEMORY_OPT_ALLREDUCE_SIZE = 500000000
+DeepSpeedOptimizerCallable = object
+DeepSpeedSchedulerCallable = object
+
+
+class DeepSpeedEngine(CheckpointMixin, nn.Module):
+
+    def __init__(self, args=None, model=None, optimizer=None, model_parameters=None, training_data=None,
+                 lr_scheduler=None, mpu=None, dist_init_required=None, collate_fn=None, config=None,
+                 config_class: Optional[DeepSpeedConfig] = None, mesh_device=None, dont_change_device=False):
+        super().__init__()
+        self.dont_change_device = dont_change_device
+        self.client_optimizer = optimizer
+        self.client_lr_scheduler = lr_scheduler
+        self.training_data = training_data
+        self.collate_fn = collate_fn
+        self.mpu = mpu
+        self.mesh_device = mesh_device
+        self.global_steps = 0
+        self.global_samples = 0
+        self.micro_steps = 0
+        self.skipped_steps = 0
+        self.gradient_average = True
+        self.warn_unscaled_loss = True
+        self.loaded_checkpoint_mp_world_size = None
+        self.loaded_checkpoint_dp_world_size = None
+        self.enable_backward_allreduce = True
+        self.losses = None
+        self._is_gradient_accumulation_boundary = None
+        self.scale_wrt_gas = None
+        self.accel = get_accelerator()
+
+        dist.init_distributed(dist_init_required=dist_init_required)
+        self._config = config_class if config_class is not None else DeepSpeedConfig(config, mpu,
+                                                                                      mesh_device=mesh_device)
+        self._set_distributed_vars(args)
+        dist.configure(self._config)
+        self.monitor = MonitorMaster(self._config.monitor_config)
+
+        self._configure_parallel_groups()
+        self.module = model
+        self._configure_distributed_model(model)
+        self.timers = SynchronizedWallClockTimer() if self.wall_clock_breakdown() else NoopTimer()
+        self.tput_timer = ThroughputTimer(self._config.timers_config.throughput,
+                                          batch_size=self.train_batch_size(),
+                                          steps_per_output=self.steps_per_print(),
+                                          monitor_memory=False)
+        self.training_dataloader = self.deepspeed_io(training_data) if training_data is not None else None
+
+        # ---- optimizer -------------------------------------------------------------------------
+        self.optimizer = None
+        self.basic_optimizer = None
+        self.lr_scheduler = None
+        has_opt = optimizer is not None or self._config.optimizer_name is not None
+        if model_parameters is None and has_opt:
+            model_parameters = [p for p in self.module.parameters() if p.requires_grad]
+        if has_opt:
+            self._configure_optimizer(optimizer, model_parameters)
+            self._configure_lr_scheduler(lr_scheduler)
+        elif self.zero_optimization_stage() == 3:
+            # ZeRO-Inference: parameter sharding + fetch hooks without an optimizer
+            self._configure_zero_inference()
+        self._configure_aux()
+        if self.global_rank == 0 and self._config.dump_state:
+            self._config.print("DeepSpeedEngine configuration")
+
+    # =========================================================================================
+    # setup
+    # =========================================================================================
+    def _set_distributed_vars(self, args):
+        self.local_rank = int(os.environ.get("LOCAL_RANK", getattr(args, "local_rank", 0) or 0))
+        self.world_size = dist.get_world_size()
+        self.global_rank = dist.get_rank()
+        if self.accel.device_name() == "cuda" and not self.dont_change_device:
+            self.accel.set_device(self.local_rank % max(self.accel.device_count(), 1))
+            self.device = torch.device("cuda", self.accel.current_device())
+        else:
+            self.device = torch.device("cpu") if self.accel.device_name() == "cpu" else torch.device(
+                "cuda", torch.cuda.current_device())
+
+    def _configure_parallel_groups(self):
+        sp = int(self._config.sequence_parallel_size or 1)
+        tp = int(self._config.tensor_parallel_config.autotp_size or 0) or 1
+        if self.mpu is not None:
+            groups.initialize(mpu=self.mpu)
+        elif self.mesh_device is not None:
+            groups.mesh_device = self.mesh_device
+        elif sp * tp > 1 and groups.ranks_of("dp") is None:
+            groups.initialize(tp_size=tp, sp_size=sp)
+        self.seq_parallel_group = groups._get_sequence_parallel_group() if sp > 1 else None
+        self.sequence_parallel_size = sp
+        self.data_parallel_group = groups._get_data_parallel_group()
+        # ZeRO shards over seq x data when Ulysses is on (reference engine.py:1655)
+        self.seq_data_parallel_group = groups._get_sequence_data_parallel_group() if sp > 1 else self.data_parallel_group
+        self.dp_world_size = groups._get_data_parallel_world_size()
+        self.seq_dp_world_size = groups._get_sequence_data_parallel_world_size() if sp > 1 else self.dp_world_size
+        self.mp_world_size = groups._get_model_parallel_world_size()
+
+    def _model_dtype(self):
+        if self._config.fp16_enabled:
+            return torch.float16
+        if self._config.bfloat16_enabled:
+            return torch.bfloat16
+        return torch.float32
+
+    def get_data_types(self):
+        model_dtype = self._model_dtype()
+        gad = self._config.grad_accum_dtype
+        if gad is None:
+            grad_accum_dtype = torch.float32 if (model_dtype == torch.bfloat16
+                                                 and not self.zero_optimization()) else model_dtype
+        else:
+            grad_accum_dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[gad]
+        return model_dtype, grad_accum_dtype
+
+    def _configure_distributed_model(self, model):
+        dtype = self._model_dtype()
+        from deepspeed_b200.runtime.zero.partition_parameters import is_zero_param
+        sharded_already = any(is_zero_param(p) for p in model.parameters())
+        if not sharded_already:
+            if dtype != torch.float32 and not self._config.amp_enabled:
+                model.to(dtype)
+            if not self.dont_change_device:
+                model.to(self.device)
+        # MoE discovery: create expert groups before the optimizer partitions parameters
+        self.has_moe_layers = False
+        self.num_experts = []
+        try:
+            from deepspeed_b200.moe.layer import MoE
+            for m in model.modules():
+                if isinstance(m, MoE):
+                    self.has_moe_layers = True
+                    self.num_experts.append(m.num_experts)
+                    m.set_deepspeed_parallelism(self._config.use_data_before_expert_parallel_)
+        except ImportError:
+            pass
+
+    def _build_loss_scale_config(self):
+        c = self._config
+        if not c.fp16_enabled:
+            return {"dynamic": False, "static_loss_scale": 1.0}
+        if c.loss_scale == 0:
+            return {"dynamic": True, "dynamic_args": c.dynamic_loss_scale_args}
+        return {"dynamic": False, "static_loss_scale": c.loss_scale}
+
+    def _configure_optimizer(self, client_optimizer, model_parameters):
+        c = self._config
+        name = c.optimizer_name
+        opt_params = c.optimizer_params or {}
+        param_groups = None
+        if client_optimizer is not None and not isinstance(client_optimizer, torch.optim.Optimizer):
+            if callable(client_optimizer):  # optimizer factory callable (reference DeepSpeedOptimizerCallable)
+                client_optimizer = client_optimizer(model_parameters)
+            else:
+                raise TypeError("optimizer must be a torch.optim.Optimizer or a callable returning one")
+        if client_optimizer is None:
+            if name in (ONEBIT_ADAM_OPTIMIZER, ZERO_ONE_ADAM_OPTIMIZER, ONEBIT_LAMB_OPTIMIZER):
+                from deepspeed_b200.runtime.fp16.onebit import build_onebit_optimizer
+                client_optimizer = build_onebit_optimizer(name, model_parameters, opt_params, self)
+                name = None
+            elif name not in (ADAM_OPTIMIZER, ADAMW_OPTIMIZER, LION_OPTIMIZER, ADAGRAD_OPTIMIZER, SGD_OPTIMIZER,
+                              LAMB_OPTIMIZER, "muadam", "muadamw", "musgd"):
+                # any torch.optim class by name
+                cls = getattr(torch.optim, name, None)
+                if cls is None:
+                    raise ValueError(f"unknown optimizer type {name!r}")
+                client_optimizer = cls(model_parameters, **opt_params)
+                name = None
+            else:
+                pl = list(model_parameters)
+                param_groups = pl if (pl and isinstance(pl[0], dict)) else [{"params": pl}]
+        self.basic_optimizer = client_optimizer
+        model_dtype, gad = self.get_data_types()
+        stage = self.zero_optimization_stage()
+        if stage > 0 and client_optimizer is not None and not c.zero_allow_untested_optimizer:
+            from deepspeed_b200.runtime.zero.utils import is_zero_supported_optimizer
+            assert is_zero_supported_optimizer(client_optimizer), (
+                f"{type(client_optimizer).__name__} is not a ZeRO-tested optimizer; set "
+                f"'zero_allow_untested_optimizer': true to use it anyway")
+        self.optimizer = ZeroShardedOptimizer(self.module,
+                                              stage,
+                                              client_optimizer=client_optimizer,
+                                              optimizer_name=name,
+                                              optimizer_params=opt_params,
+                                              param_groups=param_groups,
+                                              zero_config=c.zero_config,
+                                              dp_group=self.seq_data_parallel_group,
+                                              model_dtype=model_dtype,
+                                              grad_accum_dtype=gad,
+                                              gradient_accumulation_steps=self.gradient_accumulation_steps(),
+                                              gradient_clipping=self.gradient_clipping(),
+                                              loss_scale_config=self._build_loss_scale_config(),
+                                              communication_data_type=c.communication_data_type,
+                                              prescale_gradients=c.prescale_gradients,
+                                              gradient_predivide_factor=c.gradient_predivide_factor,
+                                              device=self.device,
+                                              mpu=self.mpu,
+                                              timers=self.timers)
+
+    def _configure_zero_inference(self):
+        self.optimizer = ZeroShardedOptimizer(self.module, 3, optimizer_name="sgd", optimizer_params={"lr": 0.0},
+                                              param_groups=[{"params": []}], zero_config=self._config.zero_config,
+                                              dp_group=self.seq_data_parallel_group, model_dtype=self._model_dtype(),
+                                              device=self.device)
+        self._zero_inference = True
+
+    def _configure_lr_scheduler(self, client_lr_scheduler):
+        c = self._config
+        if client_lr_scheduler is not None:
+            if callable(client_lr_scheduler) and not hasattr(client_lr_scheduler, "step"):
+                self.lr_scheduler = client_lr_scheduler(self.optimizer)
+            else:
+                self.lr_scheduler = client_lr_scheduler
+                # a client scheduler built on the client optimizer must drive OUR param groups
+                if hasattr(self.lr_scheduler, "optimizer") and self.lr_scheduler.optimizer is self.client_optimizer:
+                    self.lr_scheduler.optimizer = self.optimizer
+        elif c.scheduler_name is not None:
+            cls = lr_schedules.get_lr_schedule_class(c.scheduler_name)
+            if cls is None:
+                cls = getattr(torch.optim.lr_scheduler, c.scheduler_name, None)
+                assert cls is not None, f"DeepSpeed does not recognize LR scheduler {c.scheduler_name}"
+            self.lr_scheduler = cls(self.optimizer, **(c.scheduler_params or {}))
+        log_dist(f"DeepSpeed LR Scheduler = {type(self.lr_scheduler).__name__ if self.lr_scheduler else None}",
+                 ranks=[0])
+
+    def _configure_aux(self):
+        c = self._config
+        self.flops_profiler = None
+        if c.flops_profiler_config.enabled:
+            from deepspeed_b200.profiling.flops_profiler import FlopsProfiler
+            self.flops_profiler = FlopsProfiler(self.module, self)
+        self.progressive_layer_drop = None
+        if c.pld_enabled:
+            from deepspeed_b200.runtime.progressive_layer_drop import ProgressiveLayerDrop
+            self.progressive_layer_drop = ProgressiveLayerDrop(theta=c.pld_params.get("theta", 0.5),
+                                                               gamma=c.pld_params.get("gamma", 0.001))
+        self.curriculum_scheduler_legacy = None
+        if c.curriculum_enabled_legacy:
+            from deepspeed_b200.runtime.data_pipeline.curriculum_scheduler import CurriculumScheduler
+            self.curriculum_scheduler_legacy = CurriculumScheduler(c.curriculum_params_legacy)
+        self.eigenvalue = None
+        if c.eigenvalue_enabled:
+            from deepspeed_b200.runtime.eigenvalue import Eigenvalue
+            self.eigenvalue = Eigenvalue(verbose=c.eigenvalue_verbose, max_iter=c.eigenvalue_max_iter,
+                                         tol=c.eigenvalue_tol, stability=c.eigenvalue_stability,
+                                         gas_boundary_resolution=c.eigenvalue_gas_boundary_resolution,
+                                         layer_name=c.eigenvalue_layer_name, layer_num=c.eigenvalue_layer_num)
+        self.quantizer = None
+        self._configure_checkpointing()
+
+    # =========================================================================================
+    # accessors (reference names)
+    # =========================================================================================
+    def train_batch_size(self):
+        return self._config.train_batch_size
+
+    def train_micro_batch_size_per_gpu(self):
+        return self._config.train_micro_batch_size_per_gpu
+
+    def gradient_accumulation_steps(self):
+        return self._config.gradient_accumulation_steps
+
+    def set_train_batch_size(self, train_batch_size):
+        mb = self.train_micro_batch_size_per_gpu() * self.dp_world_size
+        if train_batch_size % mb != 0:
+            raise ValueError("Train batch size must be divisible by micro-batch data parallelism")
+        self._config.gradient_accumulation_steps = train_batch_size // mb
+        self._config.train_batch_size = train_batch_size
+        if self.optimizer is not None:
+            self.optimizer.gas = self._config.gradient_accumulation_steps
+
+    def set_train_micro_batch_size(self, micro_batch_size):
+        self._config.train_batch_size = micro_batch_size * self.gradient_accumulation_steps() * self.dp_world_size
+        self._config.train_micro_batch_size_per_gpu = micro_batch_size
+
+    def steps_per_print(self):
+        return self._config.steps_per_print
+
+    def wall_clock_breakdown(self):
+        return self._config.wall_clock_breakdown
+
+    def memory_breakdown(self):
+        return self._config.memory_breakdown
+
+    def gradient_clipping(self):
+        return self._config.gradient_clipping
+
+    def zero_optimization(self):
+        return self._config.zero_enabled
+
+    def zero_optimization_stage(self):
+        return self._config.zero_optimization_stage
+
+    def zero_optimization_partition_gradients(self):
+        return self.zero_optimization_stage() >= 2
+
+    def zero_optimization_partition_weights(self):
+        return self.zero_optimization_stage() >= 3
+
+    def fp16_enabled(self):
+        return self._config.fp16_enabled
+
+    def bfloat16_enabled(self):
+        return self._config.bfloat16_enabled
+
+    def amp_enabled(self):
+        return self._config.amp_enabled
+
+    def dynamic_loss_scale(self):
+        return self._config.fp16_enabled and self._config.loss_scale == 0
+
+    def loss_scale(self):
+        return self._config.loss_scale
+
+    def optimizer_name(self):
+        return self.client_optimizer.__class__.__name__ if self.client_optimizer else self._config.optimizer_name
+
+    def scheduler_name(self):
+        return self._config.scheduler_name
+
+    def get_lr(self):
+        return [g["lr"] for g in self.optimizer.param_groups]
+
+    def get_type(self):
+        return [g.get("type", None) for g in self.optimizer.param_groups]
+
+    def get_mom(self):
+        return [g.get("betas", g.get("momentum")) for g in self.optimizer.param_groups]
+
+    def get_global_grad_norm(self):
+        return self.optimizer.get_global_grad_norm() if self.optimizer is not None else None
+
+    @property
+    def config(self):
+        return self._config._param_dict
+
+    def get_batch_info(self):
+        return self.train_batch_size(), self.train_micro_batch_size_per_gpu(), self.gradient_accumulation_steps()
+
+    def is_first_weights_partition_group(self):
+        return self.global_rank == 0 or self.zero_optimization_stage() >= 1
+
+    def was_step_applied(self) -> bool:
+        return self._step_applied
+
+    # =========================================================================================
+    # data
+    # =========================================================================================
+    def deepspeed_io(self, dataset, batch_size=None, route="train", pin_memory=True, data_sampler=None,
+                     collate_fn=None, num_local_io_workers=None):
+        if not isinstance(dataset, torch.utils.data.Dataset):
+            raise ValueError("Training data must be a torch Dataset")
+        if batch_size is None:
+            batch_size = self.train_micro_batch_size_per_gpu()
+        if collate_fn is None:
+            collate_fn = self.collate_fn
+        return DeepSpeedDataLoader(dataset=dataset, batch_size=batch_size, pin_memory=pin_memory,
+                                   collate_fn=collate_fn, local_rank=self.local_rank, tput_timer=self.tput_timer,
+                                   num_local_io_workers=num_local_io_workers, data_sampler=data_sampler,
+                                   data_parallel_world_size=self.dp_world_size,
+                                   data_parallel_rank=groups._get_data_parallel_rank(),
+                                   dataloader_drop_last=self._config.dataloader_drop_last)
+
+    # =========================================================================================
+    # train / eval
+    # =========================================================================================
+    def train(self, mode=True):
+        self.warn_unscaled_loss = True
+        self.module.train(mode)
+        return self
+
+    def eval(self):
+        self.warn_unscaled_loss = True
+        self.module.train(False)
+        return self
+
+    def _cast_inputs(self, args, kwargs):
+        if not (self._config.fp16_auto_cast and self.fp16_enabled()):
+            return args, kwargs
+
+        def cast(x):
+            return x.half() if torch.is_tensor(x) and torch.is_floating_point(x) else x
+
+        return tuple(cast(a) for a in args), {k: cast(v) for k, v in kwargs.items()}
+
+    @instrument_w_nvtx
+    def forward(self, *inputs, **kwargs):
+        if self.flops_profiler is not None and self.global_steps == self._config.flops_profiler_config.profile_step \
+                and self.global_rank == 0 and self.module.training:
+            self.flops_profiler.start_profile(ignore_list=None)
+        if self.module.training:
+            if self.progressive_layer_drop is not None:
+                kwargs.update(self.progressive_layer_drop.get_state())
+            if self.curriculum_scheduler_legacy is not None:
+                self.curriculum_scheduler_legacy.update_difficulty(self.global_steps + 1)
+                if self._config.curriculum_params_legacy.get("curriculum_type") == "seqlen":
+                    kwargs["curriculum_seqlen"] = self.curriculum_scheduler_legacy.get_current_difficulty()
+        self.timers(FORWARD_MICRO_TIMER).start()
+        self.timers(FORWARD_GLOBAL_TIMER).start()
+        if self.module.training:
+            self.tput_timer.start()
+        inputs, kwargs = self._cast_inputs(inputs, kwargs)
+        loss = self.module(*inputs, **kwargs)
+        self.timers(FORWARD_MICRO_TIMER).stop()
+        self.timers(FORWARD_GLOBAL_TIMER).stop()
+        if self.flops_profiler is not None and self.flops_profiler.started:
+            self.flops_profiler.stop_profile()
+        return loss
+
+    __call__ = nn.Module.__call__
+
+    def is_gradient_accumulation_boundary(self):
+        if self._is_gradient_accumulation_boundary is None:
+            return (self.micro_steps + 1) % self.gradient_accumulation_steps() == 0
+        return self._is_gradient_accumulation_boundary
+
+    def set_gradient_accumulation_boundary(self, is_boundary):
+        self._is_gradient_accumulation_boundary = is_boundary
+        if self.optimizer is not None:
+            self.optimizer._forced_boundary = is_boundary
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Skip gradient reduction inside the context (reference engine.py:2065); illegal with
+        ZeRO >= 2 because gradients are partitioned as they are produced."""
+        assert not self.zero_optimization_partition_gradients(), \
+            f"no_sync context manager is incompatible with gradient partitioning logic of ZeRO stage " \
+            f"{self.zero_optimization_stage()}"
+        assert not getattr(self, "inside_no_sync_ctxt", False), "no_sync context manager reentry is unsupported"
+        self.inside_no_sync_ctxt = True
+        try:
+            yield
+        finally:
+            self.inside_no_sync_ctxt = False
+
+    @instrument_w_nvtx
+    def backward(self, loss, retain_graph=False, scale_wrt_gas=True):
+        assert self.optimizer is not None, "must provide optimizer during init in order to use backward"
+        self.timers(BACKWARD_MICRO_TIMER).start()
+        self.timers(BACKWARD_GLOBAL_TIMER).start()
+        gas = self.gradient_accumulation_steps()
+        if gas > 1 and scale_wrt_gas:
+            loss = loss / gas
+        if self.monitor.enabled and self.is_gradient_accumulation_boundary():
+            self._last_loss_for_monitor = loss.detach()
+        self.optimizer.backward(loss, retain_graph=retain_graph)
+        self.timers(BACKWARD_MICRO_TIMER).stop()
+        self.timers(BACKWARD_GLOBAL_TIMER).stop()
+        return loss
+
+    def zero_grad(self):
+        for p in self.module.parameters():
+            p.grad = None
+
+    def clip_fp32_gradients(self):
+        pass  # clipping is fused into the sharded optimizer step
+
+    def _take_model_step(self, lr_kwargs=None):
+        self.optimizer.step()
+        overflow = getattr(self.optimizer, "overflow", False)
+        self._step_applied = not overflow
+        if overflow:
+            self.skipped_steps += 1
+        elif self.lr_scheduler is not None:
+            try:
+                self.lr_scheduler.step(**(lr_kwargs or {}))
+            except TypeError:
+                self.lr_scheduler.step()
+        self.global_steps += 1
+        self.global_samples += self.train_batch_size()
+
+    @instrument_w_nvtx
+    def step(self, lr_kwargs=None):
+        assert self.optimizer is not None, "must provide optimizer during init in order to use step"
+        self.timers(STEP_MICRO_TIMER).start()
+        self.timers(STEP_GLOBAL_TIMER).start()
+        self._step_applied = False
+        boundary = self.is_gradient_accumulation_boundary()
+        if boundary:
+            if self.progressive_layer_drop is not None:
+                self.progressive_layer_drop.update_state(self.global_steps)
+            self._take_model_step(lr_kwargs)
+            if self.monitor.enabled and self.global_rank == 0:
+                ev = [("Train/Samples/lr", self.get_lr()[0], self.global_samples)]
+                if getattr(self, "_last_loss_for_monitor", None) is not None:
+                    ev.append(("Train/Samples/train_loss", float(self._last_loss_for_monitor), self.global_samples))
+                if self.fp16_enabled():
+                    ev.append(("Train/Samples/loss_scale", self.optimizer.cur_scale, self.global_samples))
+                self.monitor.write_events(ev)
+        self.tput_timer.stop(global_step=boundary)
+        self.timers(STEP_MICRO_TIMER).stop()
+        self.timers(STEP_GLOBAL_TIMER).stop()
+        if boundary and self.wall_clock_breakdown() and self.global_steps % self.steps_per_print() == 0:
+            self.timers.log([FORWARD_GLOBAL_TIMER, BACKWARD_GLOBAL_TIMER, STEP_GLOBAL_TIMER],
+                            memory_breakdown=self.memory_breakdown())
+        if boundary and self.flops_profiler is not None and self.flops_profiler.has_result() and \
+                self.global_steps == self._config.flops_profiler_config.profile_step + 1:
+            fc = self._config.flops_profiler_config
+            self.flops_profiler.print_model_profile(profile_step=fc.profile_step, module_depth=fc.module_depth,
+                                                    top_modules=fc.top_modules, detailed=fc.detailed,
+                                                    output_file=fc.output_file)
+            self.flops_profiler.end_profile()
+        if boundary and self.global_steps % self.steps_per_print() == 0:
+            self._report_progress(self.global_steps)
+        self.micro_steps += 1
+
+    def _report_progress(self, step):
+        lr = self.get_lr()
+        log_dist(f"step={step}, skipped={self.skipped_steps}, lr={lr}, mom={self.get_mom()}", ranks=[0])
+
+    # ---- convenience: one full optimizer step over GAS micro-batches -----------------------------
+    def train_batch(self, data_iter=None, loss_fn=None):
+        """Run forward/backward for ``gradient_accumulation_steps`` micro batches and step.
+        (For non-pipeline engines; mirrors ``PipelineEngine.train_batch`` ergonomics.)"""
+        if data_iter is None:
+            assert self.training_dataloader is not None
+            if not hasattr(self, "_train_iter"):
+                from deepspeed_b200.runtime.dataloader import RepeatingLoader
+                self._train_iter = iter(RepeatingLoader(self.training_dataloader))
+            data_iter = self._train_iter
+        total = None
+        for _ in range(self.gradient_accumulation_steps()):
+            batch = next(data_iter)
+            batch = _to_device(batch, self.device)
+            if isinstance(batch, dict):
+                out = self(**batch)
+            elif isinstance(batch, (tuple, list)):
+                out = self(*batch)
+            else:
+                out = self(batch)
+            loss = loss_fn(out, batch) if loss_fn is not None else (out[0] if isinstance(out, (tuple, list)) else
+                                                                    getattr(out, "loss", out))
+            self.backward(loss)
+            self.step()
+            total = loss.detach() if total is None else total + loss.detach()
+        return total / self.gradient_accumulation_steps()
+
+    # ---- misc reference API ------------------------------------------------------------------------
+    def module_state_dict(self, destination=None, prefix="", keep_vars=False, exclude_frozen_parameters=False):
+        sd = self.module.state_dict(destination=destination, prefix=prefix, keep_vars=keep_vars)
+        if exclude_frozen_parameters:
+            for n, p in self.module.named_parameters():
+                if not p.requires_grad and n in sd:
+                    del sd[n]
+        return sd
+
+    def load_module_state_dict(self, checkpoint, strict=True, custom_load_fn=None, fetch_z3_params=False):
+        sd = checkpoint["module"] if "module" in checkpoint else checkpoint
+        if custom_load_fn:
+            custom_load_fn(src=sd, dst=self.module)
+        else:
+            self.module.load_state_dict(sd, strict=strict)
+
+    def get_sequence_parallel_group(self):
+        return self.seq_parallel_group
+
+    def destroy(self):
+        if self.optimizer is not None and hasattr(self.optimizer, "destroy"):
+            self.optimizer.destroy()
+
+    def offload_states(self, include=None, device="cpu", pin_memory=True, non_blocking=False):
+        from deepspeed_b200.runtime.zero.offload_states import offload_states
+        offload_states(self.optimizer, include, device, pin_memory, non_blocking)
+
+    def reload_states(self, non_blocking=False):
+        from deepspeed_b200.runtime.zero.offload_states import reload_states
+        reload_states(self.optimizer, non_blocking)
+
+    def compile(self, backend=None, compile_kwargs=None, schedule=None):
+        """The reference wraps ``torch.compile``; on B200 the hot path is hand-written CUDA plus CUDA
+        graphs, so this only records the request (kept for API compatibility)."""
+        self._is_compiled = True
+        log_dist("engine.compile(): no-op -- deepspeed_b200 uses native sm_100a kernels + CUDA graphs", ranks=[0])
+
+    @property
+    def is_compiled(self):
+        return getattr(self, "_is_compiled", False)
+
+
+def _to_device(batch, device):
+    if torch.is_tensor(batch):
+        return batch.to(device, non_blocking=True)
+    if isinstance(batch, dict):
+        return {k: _to_device(v, device) for k, v in batch.items()}
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(_to_device(v, device) for v in batch)
+    return batch

@@ -1,0 +1,1105 @@
+"""ZeRO stages 0-3 as ONE sharded-state engine over a static unit plan.
+
+Capability parity with the reference ``runtime/zero/stage_1_and_2.py`` (P5), ``stage3.py`` (P6),
+``partition_parameters.py`` (P7), ``partitioned_param_coordinator.py`` (P8),
+``parameter_offload.py`` (P9), ``bf16_optimizer.py`` (P13) and ``fp16/fused_optimizer.py`` (P14),
+but a different architecture:
+
+* **Static plan** (``units.py``): unit-flat buffers sharded contiguously across the DP group, so
+  all-gather / reduce-scatter are zero-copy on both ends.
+* **Rank-local arenas**: one flat tensor each for the low-precision shard, the fp32 master, every
+  optimizer state and (when needed) the accumulated gradient shard.  The optimizer step is a few
+  fused-kernel launches over arena segments, not a Python loop over parameters.
+* **Stage is a parameter, not a class**: stage 0 = no sharding (all-reduce), stage 1/2 = sharded
+  optimizer state + reduce-scatter'd gradients with persistently gathered parameters, stage 3 =
+  transient parameters gathered per unit with prefetch.
+* **Streams**: gathers run on ``ag_stream``, reductions (+ fused accumulate / Adam) on
+  ``rs_stream``; buffers come from fixed rotating pools so no allocator/stream hazards exist.
+* **Collective back-ends**: NCCL through ``deepspeed_b200.comm`` (baseline / multi-node / host),
+  or the in-kernel NVLink peer-memory path from ``deepspeed_b200.comm.symm`` when the symmetric
+  arena is available (``b200_fused_collectives``).
+* **No host syncs in the step** for bf16: grad-norm, clip coefficient and overflow flag live on
+  the device and are consumed by the fused optimizer kernel directly.
+"""
+import math
+import weakref
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from deepspeed_b200 import comm as dist
+from deepspeed_b200.accelerator import get_accelerator
+from deepspeed_b200.ops.kernels import flat_ops
+from deepspeed_b200.runtime.fp16.loss_scaler import CreateLossScaler
+from deepspeed_b200.runtime.zero.flat_optimizers import (FlatOptimizer, TorchOptimizerAdapter, build_flat_optimizer)
+from deepspeed_b200.runtime.zero.units import (Segment, Unit, arena_segments, build_units, param_fragments)
+from deepspeed_b200.utils.logging import logger, log_dist
+from deepspeed_b200.utils.nvtx import instrument_w_nvtx
+
+NOT_GATHERED, INFLIGHT, GATHERED = 0, 1, 2
+
+
+class _Slot:
+    """One buffer of a rotating pool plus the event that marks it reusable."""
+
+    def __init__(self, buf):
+        self.buf = buf
+        self.free_event = None  # recorded on the stream that last read/wrote it
+        self.owner = None
+
+
+class _UnitRT:
+    """Runtime (mutable) companion of a plan :class:`Unit`."""
+
+    def __init__(self, unit: Unit):
+        self.u = unit
+        self.state = NOT_GATHERED
+        self.full: Optional[torch.Tensor] = None
+        self.slot: Optional[_Slot] = None
+        self.gather_event = None
+        self.grad_slot: Optional[_Slot] = None
+        self.grad_full: Optional[torch.Tensor] = None
+        self.pending = 0
+        self.n_trainable = 0
+        self.reduced_this_micro = False
+        self.dense_grads = False  # set by model integrations that write every gradient view
+        self.in_use = 0
+
+
+class ZeroShardedOptimizer:
+    """Sharded model-state manager + optimizer.  See module docstring."""
+
+    def __init__(self,
+                 module: nn.Module,
+                 stage: int,
+                 *,
+                 client_optimizer=None,
+                 optimizer_name: Optional[str] = None,
+                 optimizer_params: Optional[dict] = None,
+                 param_groups: Optional[List[dict]] = None,
+                 zero_config=None,
+                 dp_group=None,
+                 model_dtype=torch.bfloat16,
+                 grad_accum_dtype=None,
+                 gradient_accumulation_steps: int = 1,
+                 gradient_clipping: float = 0.0,
+                 loss_scale_config: Optional[dict] = None,
+                 communication_data_type=None,
+                 prescale_gradients=False,
+                 gradient_predivide_factor=1.0,
+                 device=None,
+                 mpu=None,
+                 broadcast_init=True,
+                 timers=None):
+        from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
+        self.module = module
+        self.stage = int(stage)
+        self.zc = zero_config or DeepSpeedZeroConfig(stage=self.stage)
+        self.dp_group = dp_group
+        self.dp_world = dist.get_world_size(dp_group)
+        self.dp_rank = dist.get_rank(dp_group)
+        self.shard_world = self.dp_world if self.stage >= 1 else 1
+        self.shard_rank = self.dp_rank if self.stage >= 1 else 0
+        self.accel = get_accelerator()
+        self.device = torch.device(device if device is not None else self.accel.current_device_name())
+        self.on_cuda = self.device.type == "cuda"
+        self.model_dtype = model_dtype
+        self.master_dtype = torch.float32
+        self.gas = max(1, int(gradient_accumulation_steps))
+        self.clip = float(gradient_clipping or 0.0)
+        self.grad_accum_dtype = grad_accum_dtype or model_dtype
+        self.comm_dtype = communication_data_type or model_dtype
+        self.prescale = prescale_gradients
+        self.predivide = float(gradient_predivide_factor)
+        self.mpu = mpu
+        self.timers = timers
+        self.micro_step = 0
+        self.global_step = 0
+        self.overflow = False
+        self.skipped_steps = 0
+        self._global_grad_norm = None
+        self.custom_loss_scaler = False
+        self.external_loss_scale = None
+
+        # ---- offload tiers -------------------------------------------------------------
+        oo = self.zc.offload_optimizer
+        op = self.zc.offload_param
+        self.offload_optimizer = bool(oo and str(getattr(oo.device, "value", oo.device)) != "none")
+        self.offload_param = bool(op and str(getattr(op.device, "value", op.device)) != "none") and self.stage == 3
+        self.offload_pin = bool(oo.pin_memory) if oo else False
+        self.offload_ratio = float(oo.ratio) if oo else 1.0
+
+        # ---- loss scaling ----------------------------------------------------------------
+        lsc = loss_scale_config or {}
+        self.loss_scaler = CreateLossScaler(dtype=model_dtype,
+                                            static_loss_scale=lsc.get("static_loss_scale", 1.0),
+                                            dynamic_scaling=lsc.get("dynamic", False),
+                                            dynamic_loss_args=lsc.get("dynamic_args"))
+        self.dynamic_loss_scale = self.loss_scaler.dynamic
+
+        # ---- param groups ------------------------------------------------------------------
+        self.client_optimizer = client_optimizer
+        self.flat_opt: FlatOptimizer = build_flat_optimizer(optimizer_name, optimizer_params, client_optimizer)
+        self.param_groups = self._make_param_groups(client_optimizer, param_groups, optimizer_params)
+        p2g = {}
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                p2g[id(p)] = gi
+        for p in module.parameters():
+            if id(p) not in p2g:
+                p2g[id(p)] = -1  # frozen / unmanaged: sharded but never stepped
+        self.group_steps = [0 for _ in self.param_groups]
+
+        # ---- plan ------------------------------------------------------------------------------
+        thresh = int(self.zc.param_persistence_threshold) if self.stage == 3 else 0
+        self.units: List[Unit] = build_units(module, self.shard_world, p2g, persistence_threshold=0)
+        self.rts: List[_UnitRT] = [_UnitRT(u) for u in self.units]
+        self.unit_of_param: Dict[int, _UnitRT] = {}
+        self.slot_of_param = {}
+        for rt in self.rts:
+            for s in rt.u.slots:
+                self.unit_of_param[id(s.param)] = rt
+                self.slot_of_param[id(s.param)] = s
+            rt.n_trainable = sum(1 for s in rt.u.slots if s.param.requires_grad)
+            # whole-unit persistence (small units stay gathered, like the reference's
+            # param_persistence_threshold but at unit granularity)
+            rt.u.persistent = self.stage < 3 or self.shard_world == 1 or rt.u.raw_numel <= thresh
+        self.arena_numel = sum(u.shard_numel for u in self.units)
+        self.segments: List[Segment] = arena_segments(self.units, self.shard_rank)
+        # pieces = segments split at unit boundaries: (unit_rt, group, start, end)
+        self.pieces = []
+        for rt in self.rts:
+            a, b = rt.u.arena_offset, rt.u.arena_offset + rt.u.shard_numel
+            for seg in self.segments:
+                s0, e0 = max(seg.start, a), min(seg.end, b)
+                if s0 < e0:
+                    self.pieces.append((rt, seg.group, s0, e0))
+        self.max_full = max(u.full_numel for u in self.units)
+
+        # ---- streams ---------------------------------------------------------------------------
+        overlap = bool(self.zc.overlap_comm) and self.on_cuda
+        self.ag_stream = torch.cuda.Stream() if overlap else None
+        self.rs_stream = torch.cuda.Stream() if overlap else None
+        self.prefetch_depth = max(0, int(self.zc.b200_unit_prefetch))
+
+        # ---- fusion policy ------------------------------------------------------------------------
+        fib = self.zc.b200_fused_optimizer_in_backward
+        can_fuse = (self.flat_opt.fused and not getattr(self.flat_opt, "per_tensor", False) and self.clip == 0.0
+                    and self.gas == 1 and not self.dynamic_loss_scale and not self.offload_optimizer)
+        self.fused_in_backward = bool(can_fuse if fib is None else (fib and can_fuse))
+
+        self._allocate(broadcast_init)
+        self._register_hooks()
+        self.stats = flat_ops.GradStats(self.device if not self.offload_optimizer else "cpu")
+        self._dev_stats = flat_ops.GradStats(self.device) if self.offload_optimizer else self.stats
+        self._trace: List[int] = []
+        self._trace_done = False
+        self._order_pos: Dict[int, int] = {}
+        self._in_backward = False
+        self._symm = None
+        self._maybe_enable_symm()
+        log_dist(
+            f"ZeroShardedOptimizer: stage={self.stage} units={len(self.units)} arena={self.arena_numel:,} elems/rank "
+            f"shard_world={self.shard_world} fused_in_backward={self.fused_in_backward} "
+            f"offload_opt={self.offload_optimizer} symm={'on' if self._symm else 'off'}",
+            ranks=[0])
+
+    # =========================================================================================
+    # construction
+    # =========================================================================================
+    def _make_param_groups(self, client_optimizer, param_groups, defaults):
+        if client_optimizer is not None:
+            groups = []
+            for g in client_optimizer.param_groups:
+                ng = {k: v for k, v in g.items() if k != "params"}
+                ng["params"] = [p for p in g["params"]]
+                groups.append(ng)
+            return groups
+        if param_groups is None:
+            param_groups = [{"params": [p for p in self.module.parameters() if p.requires_grad]}]
+        elif len(param_groups) and not isinstance(param_groups[0], dict):
+            param_groups = [{"params": list(param_groups)}]
+        out = []
+        base = dict(self.flat_opt.defaults)
+        for g in param_groups:
+            ng = dict(base)
+            ng.update({k: v for k, v in g.items() if k != "params"})
+            ng["params"] = [p for p in g["params"] if p.requires_grad]
+            ng.setdefault("lr", base.get("lr", 1e-3))
+            out.append(ng)
+        return out
+
+    def _empty(self, n, dtype, device=None, pin=False):
+        dev = device or self.device
+        t = torch.empty(n, dtype=dtype, device=dev)
+        if pin and torch.device(dev).type == "cpu" and torch.cuda.is_available():
+            t = t.pin_memory()
+        return t
+
+    def _allocate(self, broadcast_init):
+        dev = self.device
+        lp = self.model_dtype
+        S3 = self.stage == 3 and self.shard_world > 1
+        self.transient = S3
+        # ---- low-precision storage ------------------------------------------------------------
+        if S3:
+            lp_dev = "cpu" if self.offload_param else dev
+            self.lp_arena = self._empty(self.arena_numel, lp, lp_dev, pin=True)
+            n_slots = 2 + self.prefetch_depth
+            self.param_pool = [_Slot(self._symm_or_empty(self.max_full, lp)) for _ in range(n_slots)]
+            self.full_arena = None
+        else:
+            total_full = sum(u.full_numel for u in self.units)
+            self.full_arena = self._symm_or_empty(total_full, lp)
+            self.full_arena.zero_()
+            self.param_pool = []
+            self.lp_arena = None  # shards are views of full_arena
+        self.grad_pool = [_Slot(self._symm_or_empty(self.max_full, self.comm_dtype)) for _ in range(2)]
+        self._rs_tmp = [self._empty(max(u.shard_numel for u in self.units), self.comm_dtype) for _ in range(2)] \
+            if self.shard_world > 1 else []
+
+        # ---- materialise parameter data ---------------------------------------------------------
+        foff = 0
+        src_rank = dist.get_global_rank(self.dp_group, 0) if self.dp_group is not None else 0
+        for rt in self.rts:
+            u = rt.u
+            if S3:
+                tmp = torch.zeros(u.full_numel, dtype=lp, device=dev)
+                self._pack_unit(u, tmp)
+                if broadcast_init and self.dp_world > 1:
+                    dist.broadcast(tmp, src=src_rank, group=self.dp_group)
+                lo, hi = u.shard_range(self.shard_rank)
+                self._lp_shard(u).copy_(tmp[lo:hi])
+                if u.persistent:
+                    rt.full = tmp
+                    rt.state = GATHERED
+                    self._point_params(rt, tmp)
+                else:
+                    self._detach_params(rt)
+                    del tmp
+            else:
+                full = self.full_arena[foff:foff + u.full_numel]
+                self._pack_unit(u, full)
+                rt.full = full
+                rt.state = GATHERED
+                self._point_params(rt, full)
+                foff += u.full_numel
+        if not S3 and broadcast_init and self.dp_world > 1:
+            dist.broadcast(self.full_arena, src=src_rank, group=self.dp_group)
+
+        # ---- master + optimizer state ---------------------------------------------------------------
+        st_dev = "cpu" if self.offload_optimizer else dev
+        if lp == torch.float32 and not self.offload_optimizer:
+            self.master = None  # fp32 training: the lp shard *is* the master
+        else:
+            self.master = self._empty(self.arena_numel, self.master_dtype, st_dev, pin=True)
+            for rt in self.rts:
+                a = rt.u.arena_offset
+                self.master[a:a + rt.u.shard_numel].copy_(self._lp_shard(rt.u))
+        self.flat_opt.init_state(self.arena_numel, st_dev, torch.float32, pin=True)
+        if isinstance(self.flat_opt, TorchOptimizerAdapter):
+            self.flat_opt.bind([(g, s0, e0, self._piece_master(rt, s0, e0)) for (rt, g, s0, e0) in self.pieces],
+                               len(self.param_groups))
+        # accumulated gradient shard: only allocated when the fused-in-backward path is off
+        self.grad_arena = None
+        if not self.fused_in_backward:
+            gdt = torch.float32 if (self.offload_optimizer or not self.flat_opt.fused) else self.grad_accum_dtype
+            self.grad_arena = self._empty(self.arena_numel, gdt, st_dev, pin=True)
+            self.grad_arena.zero_()
+        self._lp_stage = self._empty(max(u.shard_numel for u in self.units), lp, "cpu", pin=True) \
+            if self.offload_optimizer else None
+
+    def _symm_or_empty(self, n, dtype):
+        """Allocate from the symmetric (peer-mapped) arena when available, else a plain tensor."""
+        from deepspeed_b200.comm import symm
+        t = symm.maybe_alloc(n, dtype, self.device, self.dp_group) if (self.on_cuda and self.shard_world > 1
+                                                                       and self._want_symm()) else None
+        return t if t is not None else torch.empty(n, dtype=dtype, device=self.device)
+
+    def _want_symm(self):
+        f = self.zc.b200_fused_collectives
+        if f is False:
+            return False
+        from deepspeed_b200.comm import symm
+        return symm.is_supported(self.dp_group, explicit=bool(f))
+
+    def _maybe_enable_symm(self):
+        if not (self.on_cuda and self.shard_world > 1 and self._want_symm()):
+            return
+        from deepspeed_b200.comm import symm
+        self._symm = symm.get_context(self.dp_group)
+
+    def _piece_master(self, rt, s0, e0):
+        """fp32 (or native-precision) master slice for arena range [s0, e0) inside unit ``rt``."""
+        if self.master is not None:
+            return self.master[s0:e0]
+        a = rt.u.arena_offset
+        return self._lp_shard(rt.u)[s0 - a:e0 - a]
+
+    def _piece_lp(self, rt, s0, e0):
+        a = rt.u.arena_offset
+        return self._lp_shard(rt.u)[s0 - a:e0 - a]
+
+    def _lp_shard(self, u: Unit) -> torch.Tensor:
+        if self.lp_arena is not None:
+            return self.lp_arena[u.arena_offset:u.arena_offset + u.shard_numel]
+        rt = self.rts[u.index]
+        lo, hi = u.shard_range(self.shard_rank)
+        return rt.full[lo:hi]
+
+    @torch.no_grad()
+    def _pack_unit(self, u: Unit, flat: torch.Tensor):
+        """Copy current parameter values into the unit's flat layout."""
+        for s in u.slots:
+            p = s.param
+            src = getattr(p, "ds_full_data", None)
+            if src is None:
+                src = p.data
+            if src.numel() != s.numel:
+                from deepspeed_b200.runtime.zero.partition_parameters import materialize_full
+                src = materialize_full(p)
+            flat[s.offset:s.offset + s.numel].copy_(src.reshape(-1))
+
+    def _point_params(self, rt: _UnitRT, full: torch.Tensor):
+        for s in rt.u.slots:
+            s.param.data = full[s.offset:s.offset + s.numel].view(s.shape)
+            s.param.ds_status = "AVAILABLE"
+
+    def _detach_params(self, rt: _UnitRT):
+        for s in rt.u.slots:
+            p = s.param
+            p.ds_shape = s.shape
+            p.ds_numel = s.numel
+            p.data = torch.empty(0, dtype=p.dtype, device=self.device)
+            p.ds_status = "NOT_AVAILABLE"
+
+    # =========================================================================================
+    # hooks
+    # =========================================================================================
+    def _register_hooks(self):
+        self._hook_handles = []
+        for rt in self.rts:
+            for s in rt.u.slots:
+                p = s.param
+                p.ds_unit_index = rt.u.index
+                p._ds_zero = weakref.ref(self)
+                if p.requires_grad:
+                    self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_grad_hook(rt, s)))
+            m = rt.u.module
+            if m is None or not self.transient or rt.u.persistent:
+                continue
+            self._hook_handles.append(m.register_forward_pre_hook(self._make_pre_fwd(rt)))
+            self._hook_handles.append(m.register_forward_hook(self._make_post_fwd(rt)))
+            self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
+
+    def _make_pre_fwd(self, rt):
+
+        def hook(module, args):
+            self.fetch_unit(rt, forward=not self._in_backward)
+
+        return hook
+
+    def _make_post_fwd(self, rt):
+
+        def hook(module, args, output):
+            if self._in_backward:
+                return  # recompute inside backward: released by the gradient path
+            if torch.is_grad_enabled() and rt.u.index == self._last_forward_unit():
+                return  # its backward is next: keep it
+            self.release_unit(rt)
+
+        return hook
+
+    def _make_pre_bwd(self, rt):
+
+        def hook(module, grad_output):
+            self._in_backward = True
+            self.fetch_unit(rt, forward=False)
+
+        return hook
+
+    def _last_forward_unit(self):
+        if self._trace_done and self._trace:
+            return self._trace[-1]
+        return self.units[-1].index
+
+    def _make_grad_hook(self, rt, slot):
+
+        def hook(p):
+            g = p.grad
+            if g is None:
+                return
+            self._in_backward = True
+            view = self._grad_view(rt, slot)
+            if getattr(slot, "_written", False):
+                view.add_(g.reshape(-1))
+            else:
+                view.copy_(g.reshape(-1))
+                slot._written = True
+            p.grad = None
+            self._param_grad_ready(rt)
+
+        return hook
+
+    # ---- gradient buffers ------------------------------------------------------------------------
+    def _acquire_grad_buf(self, rt: _UnitRT):
+        if rt.grad_full is not None:
+            return
+        # round-robin over the pool; wait until the previous reduce that used the slot is done
+        slot = self.grad_pool[rt.u.index % len(self.grad_pool)]
+        if slot.owner is not None and slot.owner is not rt and slot.owner.grad_full is not None:
+            # previous owner still accumulating (out-of-order graph): fall back to a private buffer
+            slot = _Slot(torch.empty(self.max_full, dtype=self.comm_dtype, device=self.device))
+        if slot.free_event is not None and self.on_cuda:
+            torch.cuda.current_stream().wait_event(slot.free_event)
+        slot.owner = rt
+        rt.grad_slot = slot
+        rt.grad_full = slot.buf[:rt.u.full_numel]
+        if not rt.dense_grads:
+            rt.grad_full.zero_()
+        rt.pending = rt.n_trainable
+        for s in rt.u.slots:
+            s._written = False
+
+    def _grad_view(self, rt: _UnitRT, slot) -> torch.Tensor:
+        self._acquire_grad_buf(rt)
+        return rt.grad_full[slot.offset:slot.offset + slot.numel]
+
+    def grad_view_for(self, p: nn.Parameter) -> torch.Tensor:
+        """Public: the flat-gradient view a custom autograd function should write ``p``'s gradient
+        into (then call :meth:`mark_grad_ready`).  Avoids AccumulateGrad + copy entirely."""
+        rt = self.unit_of_param[id(p)]
+        s = self.slot_of_param[id(p)]
+        return self._grad_view(rt, s).view(s.shape)
+
+    def grad_is_fresh(self, p: nn.Parameter) -> bool:
+        return not getattr(self.slot_of_param[id(p)], "_written", False)
+
+    def mark_grad_ready(self, p: nn.Parameter):
+        self._in_backward = True
+        s = self.slot_of_param[id(p)]
+        s._written = True
+        self._param_grad_ready(self.unit_of_param[id(p)])
+
+    def _param_grad_ready(self, rt: _UnitRT):
+        rt.pending -= 1
+        if rt.pending == 0:
+            self._reduce_unit(rt)
+
+    # =========================================================================================
+    # gather / release (stage 3)
+    # =========================================================================================
+    def _position(self, rt):
+        return self._order_pos.get(rt.u.index, rt.u.index)
+
+    @instrument_w_nvtx
+    def fetch_unit(self, rt: _UnitRT, forward=True, prefetch=True):
+        """Make ``rt``'s parameters available on the compute stream; kick off prefetches."""
+        if not self.transient or rt.u.persistent:
+            return
+        if forward and not self._trace_done:
+            self._trace.append(rt.u.index)
+        if rt.state == NOT_GATHERED:
+            self._launch_gather(rt)
+        if rt.state == INFLIGHT:
+            if rt.gather_event is not None and self.on_cuda:
+                torch.cuda.current_stream().wait_event(rt.gather_event)
+            rt.state = GATHERED
+        rt.in_use += 1
+        if prefetch and self.prefetch_depth > 0:
+            for nxt in self._upcoming(rt, forward):
+                if nxt.state == NOT_GATHERED and not nxt.u.persistent:
+                    self._launch_gather(nxt)
+
+    def _upcoming(self, rt, forward):
+        order = self._trace if (self._trace_done and self._trace) else [u.index for u in self.units]
+        try:
+            pos = order.index(rt.u.index) if forward else len(order) - 1 - order[::-1].index(rt.u.index)
+        except ValueError:
+            return []
+        out = []
+        step = 1 if forward else -1
+        for k in range(1, self.prefetch_depth + 1):
+            q = pos + step * k
+            if 0 <= q < len(order):
+                out.append(self.rts[order[q]])
+        return out
+
+    def _launch_gather(self, rt: _UnitRT):
+        u = rt.u
+        slot = self.param_pool[u.index % len(self.param_pool)]
+        if slot.owner is not None and slot.owner is not rt and slot.owner.state != NOT_GATHERED:
+            if slot.owner.in_use > 0 or slot.owner.state == GATHERED:
+                # occupant still live (irregular graph): use a private buffer rather than corrupt it
+                slot = _Slot(self._symm_or_empty(self.max_full, self.model_dtype))
+        stream = self.ag_stream
+        cur = torch.cuda.current_stream() if self.on_cuda else None
+        if stream is not None:
+            if slot.free_event is not None:
+                stream.wait_event(slot.free_event)
+            if getattr(self, "_step_event", None) is not None:
+                stream.wait_event(self._step_event)
+        elif slot.free_event is not None and self.on_cuda:
+            cur.wait_event(slot.free_event)
+        full = slot.buf[:u.full_numel]
+        shard = self._lp_shard(u)
+        ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
+        with ctx:
+            if self.offload_param:
+                lo, hi = u.shard_range(self.shard_rank)
+                full[lo:hi].copy_(shard, non_blocking=True)
+                shard = full[lo:hi]
+            self._all_gather(full, shard, u)
+            if self.on_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                rt.gather_event = ev
+        slot.owner = rt
+        rt.slot = slot
+        rt.full = full
+        rt.state = INFLIGHT
+        self._point_params(rt, full)
+
+    def _all_gather(self, full, shard, u: Unit):
+        if self._symm is not None and self._symm.owns(full) and self._symm.owns(shard):
+            self._symm.all_gather(full, shard, u.shard_numel)
+            return
+        w = dist.all_gather_into_tensor(full, shard, group=self.dp_group, async_op=self.on_cuda)
+        if w is not None and hasattr(w, "wait"):
+            w.wait()
+
+    @instrument_w_nvtx
+    def release_unit(self, rt: _UnitRT):
+        if not self.transient or rt.u.persistent or rt.state == NOT_GATHERED:
+            return
+        rt.in_use = max(0, rt.in_use - 1)
+        if rt.in_use > 0:
+            return
+        if self.on_cuda and rt.slot is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            rt.slot.free_event = ev
+        self._detach_params(rt)
+        rt.full = None
+        rt.state = NOT_GATHERED
+        rt.gather_event = None
+
+    def gather_all(self):
+        """Gather every unit (used by state-dict export / GatheredParameters on the whole model)."""
+        for rt in self.rts:
+            if self.transient and not rt.u.persistent and rt.state == NOT_GATHERED:
+                buf = torch.empty(rt.u.full_numel, dtype=self.model_dtype, device=self.device)
+                shard = self._lp_shard(rt.u)
+                if self.offload_param:
+                    lo, hi = rt.u.shard_range(self.shard_rank)
+                    buf[lo:hi].copy_(shard)
+                    shard = buf[lo:hi]
+                dist.all_gather_into_tensor(buf, shard, group=self.dp_group)
+                rt.full = buf
+                rt.slot = None
+                rt.state = GATHERED
+                rt.in_use += 1
+                self._point_params(rt, buf)
+
+    def release_all(self):
+        for rt in self.rts:
+            if self.transient and not rt.u.persistent and rt.state != NOT_GATHERED:
+                rt.in_use = 0
+                self._detach_params(rt)
+                rt.full = None
+                rt.state = NOT_GATHERED
+
+    # =========================================================================================
+    # gradient reduction
+    # =========================================================================================
+    def is_gradient_accumulation_boundary(self):
+        return (self.micro_step + 1) % self.gas == 0
+
+    @instrument_w_nvtx
+    def _reduce_unit(self, rt: _UnitRT):
+        u = rt.u
+        full_g = rt.grad_full
+        cur = torch.cuda.current_stream() if self.on_cuda else None
+        stream = self.rs_stream
+        if stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            stream.wait_event(ev)
+        ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
+        with ctx:
+            scale = 1.0
+            if self.dp_world > 1:
+                if self.prescale and self.predivide != 1.0:
+                    full_g.mul_(1.0 / self.predivide)
+                    scale = self.predivide / self.dp_world
+                else:
+                    scale = 1.0 / self.dp_world
+            if self.shard_world > 1:
+                lo, hi = u.shard_range(self.shard_rank)
+                if self._symm is not None and self._symm.owns(full_g):
+                    shard_g = self._symm_reduce(rt, full_g, scale)
+                    scale = None  # consumed inside the fused kernel
+                else:
+                    shard_g = self._rs_tmp[u.index % 2][:u.shard_numel]
+                    w = dist.reduce_scatter_tensor(shard_g, full_g, group=self.dp_group, async_op=self.on_cuda)
+                    if w is not None and hasattr(w, "wait"):
+                        w.wait()
+            else:
+                if self.dp_world > 1:  # stage 0: plain data parallel
+                    w = dist.all_reduce(full_g, group=self.dp_group, async_op=self.on_cuda)
+                    if w is not None and hasattr(w, "wait"):
+                        w.wait()
+                shard_g = full_g
+            if scale is not None:
+                self._consume_shard_grad(rt, shard_g, scale)
+            if self.on_cuda:
+                ev2 = torch.cuda.Event()
+                ev2.record()
+                rt.grad_slot.free_event = ev2
+        rt.grad_full = None
+        rt.grad_slot.owner = None if rt.grad_slot.owner is rt else rt.grad_slot.owner
+        rt.reduced_this_micro = True
+        if self.transient and not u.persistent:
+            self.release_unit(rt)
+
+    def _consume_shard_grad(self, rt: _UnitRT, shard_g: torch.Tensor, scale: float):
+        """Either run the fused optimizer now (boundary, no clipping) or accumulate into the arena."""
+        u = rt.u
+        a, b = u.arena_offset, u.arena_offset + u.shard_numel
+        if self.fused_in_backward and self.is_gradient_accumulation_boundary():
+            self._step_range(a, b, shard_g, grad_offset=a, grad_scale=scale)
+            return
+        first = (self.micro_step % self.gas) == 0
+        dst = self.grad_arena[a:b]
+        if dst.device != shard_g.device:  # optimizer offload: D2H through the pinned arena
+            if first:
+                tmp = shard_g.float().mul_(scale)
+                dst.copy_(tmp, non_blocking=True)
+            else:
+                dst.add_(shard_g.float().mul_(scale).cpu())
+            return
+        flat_ops.scale_cast(shard_g, dst, scale=scale, accumulate=not first)
+
+    def _symm_reduce(self, rt: _UnitRT, full_g, scale):
+        """In-kernel reduce-scatter over NVLink peer memory, fused with scale + (Adam | accumulate)."""
+        u = rt.u
+        a, b = u.arena_offset, u.arena_offset + u.shard_numel
+        boundary = self.is_gradient_accumulation_boundary()
+        if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()):
+            self._symm.reduce_scatter_adam(self, rt, full_g, scale)
+        else:
+            first = (self.micro_step % self.gas) == 0
+            self._symm.reduce_scatter_accumulate(full_g, self.grad_arena[a:b], u.shard_numel, scale,
+                                                 accumulate=not first)
+        return None
+
+    def end_backward(self):
+        """Flush units whose gradients are partially populated (unused parameters) and close the
+        micro step.  Called by the engine after ``loss.backward()`` returns."""
+        for rt in self.rts:
+            if rt.grad_full is not None and rt.pending > 0:
+                rt.pending = 0
+                self._reduce_unit(rt)
+        if self.grad_arena is not None and (self.micro_step % self.gas) == 0:
+            # units that produced no gradient at all this micro step must not keep stale values
+            for rt in self.rts:
+                if not rt.reduced_this_micro and rt.n_trainable:
+                    a = rt.u.arena_offset
+                    self.grad_arena[a:a + rt.u.shard_numel].zero_()
+        for rt in self.rts:
+            rt.reduced_this_micro = False
+        if self.transient:
+            for rt in self.rts:
+                if not rt.u.persistent and rt.state != NOT_GATHERED and rt.grad_full is None:
+                    rt.in_use = 0
+                    self.release_unit(rt)
+        self._in_backward = False
+        if not self._trace_done and self._trace:
+            self._trace_done = True
+            # keep first occurrence order
+            seen, order = set(), []
+            for i in self._trace:
+                if i not in seen:
+                    seen.add(i)
+                    order.append(i)
+            self._trace = order
+        self.micro_step += 1
+
+    # =========================================================================================
+    # backward / step API (reference-compatible)
+    # =========================================================================================
+    @property
+    def loss_scale(self):
+        if self.custom_loss_scaler:
+            return self.external_loss_scale
+        return self.loss_scaler.cur_scale
+
+    cur_scale = loss_scale
+
+    def backward(self, loss, retain_graph=False):
+        self._in_backward = True
+        if self.custom_loss_scaler:
+            (loss * self.external_loss_scale).backward(retain_graph=retain_graph)
+        else:
+            self.loss_scaler.backward(loss.float(), retain_graph=retain_graph)
+        self.end_backward()
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.module.parameters():
+            p.grad = None
+
+    def _group_hyper(self, gi):
+        return self.param_groups[gi]
+
+    def _step_range(self, a, b, grad, grad_offset, grad_scale, d_gscale=None, d_skip=None):
+        """Run the flat optimizer over arena range [a, b).  ``grad`` holds arena coordinates
+        ``[grad_offset, ...)``."""
+        write_lp = self.master is not None and not self.offload_optimizer
+        for (rt, gi, s0, e0) in self.pieces:
+            s1, e1 = max(s0, a), min(e0, b)
+            if s1 >= e1 or gi < 0:
+                continue
+            p = self._piece_master(rt, s1, e1)
+            g = grad[s1 - grad_offset:e1 - grad_offset]
+            out = self._piece_lp(rt, s1, e1) if write_lp else None
+            self.flat_opt.step_segment(s1, e1, p, g, out, self.param_groups[gi], self._peek_step(gi),
+                                       grad_scale=grad_scale, d_gscale=d_gscale, d_skip=d_skip)
+
+    def _peek_step(self, gi):
+        # group_steps is advanced once per global step in step(); during fused-in-backward calls the
+        # upcoming value is used.
+        return self.group_steps[gi] + 1
+
+    @instrument_w_nvtx
+    def step(self, closure=None):
+        """Optimizer step at a gradient-accumulation boundary."""
+        if self.on_cuda and self.rs_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.rs_stream)
+        self.overflow = False
+        if self.fused_in_backward:
+            # parameters were already updated unit-by-unit inside backward
+            for gi in range(len(self.group_steps)):
+                self.group_steps[gi] += 1
+            self._post_step()
+            return
+        inv_scale = 1.0 / float(self.loss_scale)
+        need_norm = self.clip > 0.0 or self.dynamic_loss_scale or self.model_dtype == torch.float16
+        stats = self.stats
+        d_gscale = d_skip = None
+        if need_norm:
+            stats.reset()
+            stats.accumulate(self.grad_arena)
+            self._allreduce_stats(stats)
+            stats.finalize(inv_loss_scale=inv_scale, max_norm=self.clip)
+            d_gscale, d_skip = stats.gscale, stats.skip
+            self._global_grad_norm = stats.norm
+            if self.dynamic_loss_scale or self.model_dtype == torch.float16:
+                self.overflow = bool(int(stats.skip.item()))  # fp16 needs the host to adapt the scale
+                self.loss_scaler.update_scale(self.overflow)
+                if self.overflow:
+                    self.skipped_steps += 1
+                    log_dist(f"[deepspeed_b200] OVERFLOW! Skipping step. Attempted loss scale: "
+                             f"{self.loss_scale * (self.loss_scaler.scale_factor if self.dynamic_loss_scale else 1)}"
+                             f", reducing to {self.loss_scale}", ranks=[0])
+                    self._post_step(skipped=True)
+                    return
+        gscale = 1.0 if need_norm else inv_scale
+        if isinstance(self.flat_opt, TorchOptimizerAdapter):
+            g32 = self.grad_arena
+            if need_norm:
+                g32.mul_(stats.gscale.to(g32.device))
+            elif gscale != 1.0:
+                g32.mul_(gscale)
+            self.flat_opt.step_all(g32)
+            self._master_to_lp(0, self.arena_numel)
+        elif getattr(self.flat_opt, "per_tensor", False):
+            self._step_per_tensor(gscale, d_gscale, d_skip)
+        else:
+            self._step_range(0, self.arena_numel, self.grad_arena, 0, gscale, d_gscale, d_skip)
+            if self.offload_optimizer:
+                self._master_to_lp(0, self.arena_numel)
+        for gi in range(len(self.group_steps)):
+            self.group_steps[gi] += 1
+        self._post_step()
+
+    def _step_per_tensor(self, gscale, d_gscale, d_skip):
+        for rt in self.rts:
+            for sl in rt.u.slots:
+                if sl.group < 0:
+                    continue
+                for (r, p0, a0, ln) in param_fragments(rt.u, sl, self.shard_world):
+                    if r != self.shard_rank:
+                        continue
+                    self.flat_opt.step_segment(a0, a0 + ln, self._piece_master(rt, a0, a0 + ln),
+                                               self.grad_arena[a0:a0 + ln], None, self.param_groups[sl.group],
+                                               self.group_steps[sl.group] + 1, grad_scale=gscale, d_gscale=d_gscale,
+                                               d_skip=d_skip)
+        self._master_to_lp(0, self.arena_numel)
+
+    def _master_to_lp(self, a, b):
+        """fp32 master -> low-precision shard (H2D when the optimizer lives on the host)."""
+        if self.master is None:
+            return
+        for rt in self.rts:
+            u = rt.u
+            s, e = max(a, u.arena_offset), min(b, u.arena_offset + u.shard_numel)
+            if s >= e:
+                continue
+            dst = self._lp_shard(u)[s - u.arena_offset:e - u.arena_offset]
+            src = self.master[s:e]
+            if src.device != dst.device:
+                dst.copy_(src.to(dst.dtype), non_blocking=True)
+            else:
+                flat_ops.scale_cast(src, dst)
+
+    def _allreduce_stats(self, stats):
+        if self.shard_world > 1:
+            t = stats.sumsq if stats.sumsq.device == self.device else stats.sumsq.to(self.device)
+            f = stats.found_inf if stats.found_inf.device == self.device else stats.found_inf.to(self.device)
+            dist.all_reduce(t, group=self.dp_group)
+            dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.dp_group)
+            if t is not stats.sumsq:
+                stats.sumsq.copy_(t)
+                stats.found_inf.copy_(f)
+        if self.mpu is not None and hasattr(self.mpu, "get_model_parallel_group"):
+            mp = self.mpu.get_model_parallel_group()
+            if dist.get_world_size(mp) > 1:
+                dist.all_reduce(stats.sumsq, group=mp)
+                dist.all_reduce(stats.found_inf, op=dist.ReduceOp.MAX, group=mp)
+
+    def _post_step(self, skipped=False):
+        """Make the updated low-precision parameters visible: stage<=2 all-gathers each unit in
+        place; stage 3 invalidates gathered copies (persistent units are re-gathered)."""
+        if self.on_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._step_event = ev
+        if not skipped and self.shard_world > 1:
+            if not self.transient:
+                for rt in self.rts:
+                    lo, hi = rt.u.shard_range(self.shard_rank)
+                    self._all_gather(rt.full, rt.full[lo:hi], rt.u)
+            else:
+                for rt in self.rts:
+                    if rt.u.persistent:
+                        lo, hi = rt.u.shard_range(self.shard_rank)
+                        rt.full[lo:hi].copy_(self._lp_shard(rt.u))
+                        self._all_gather(rt.full, rt.full[lo:hi], rt.u)
+        if self._symm is not None:
+            self._symm.barrier()
+        self.global_step += 1
+
+
+    # =========================================================================================
+    # GatheredParameters / external-parameter support
+    # =========================================================================================
+    def param_is_gathered(self, p) -> bool:
+        rt = self.unit_of_param[id(p)]
+        return (not self.transient) or rt.u.persistent or rt.state != NOT_GATHERED
+
+    def gather_param_temp(self, p):
+        """Gather the unit owning ``p`` into a private buffer (outside the rotating pool)."""
+        rt = self.unit_of_param[id(p)]
+        if rt.state == NOT_GATHERED:
+            buf = torch.empty(rt.u.full_numel, dtype=self.model_dtype, device=self.device)
+            shard = self._lp_shard(rt.u)
+            if shard.device != buf.device:
+                lo, hi = rt.u.shard_range(self.shard_rank)
+                buf[lo:hi].copy_(shard)
+                shard = buf[lo:hi]
+            dist.all_gather_into_tensor(buf, shard, group=self.dp_group)
+            rt.full, rt.slot, rt.state = buf, None, GATHERED
+            self._point_params(rt, buf)
+        rt.in_use += 1
+
+    def release_param_temp(self, p, write_back_from=None):
+        rt = self.unit_of_param[id(p)]
+        if write_back_from is not None:
+            self.sync_param_from_full(p, write_back_from)
+        rt.in_use = max(0, rt.in_use - 1)
+        if rt.in_use == 0 and self.transient and not rt.u.persistent:
+            self._detach_params(rt)
+            rt.full, rt.state, rt.gather_event = None, NOT_GATHERED, None
+
+    @torch.no_grad()
+    def sync_param_from_full(self, p, src_rank=0):
+        """Propagate an in-place edit of a gathered parameter: broadcast from ``src_rank`` then refresh
+        this rank's low-precision shard and fp32 master."""
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        full = rt.full[s.offset:s.offset + s.numel]
+        if self.dp_world > 1:
+            src = dist.get_global_rank(self.dp_group, src_rank) if self.dp_group is not None else src_rank
+            dist.broadcast(full, src=src, group=self.dp_group)
+        for (r, p0, a0, ln) in param_fragments(rt.u, s, self.shard_world):
+            if r != self.shard_rank:
+                continue
+            piece = full[p0:p0 + ln]
+            if self.lp_arena is not None:
+                self.lp_arena[a0:a0 + ln].copy_(piece)
+            if self.master is not None:
+                self.master[a0:a0 + ln].copy_(piece)
+
+    def get_full_lp_param(self, p):
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        if rt.state != NOT_GATHERED and rt.full is not None:
+            return rt.full[s.offset:s.offset + s.numel].view(s.shape)
+        arena = self._lp_arena_as_flat()
+        return self._gather_arena_piece(arena, rt, s).to(self.model_dtype)
+
+    def add_external_dependency(self, module: nn.Module, parameter: nn.Parameter):
+        rt = self.unit_of_param.get(id(parameter))
+        if rt is None or not self.transient or rt.u.persistent:
+            return
+
+        def pre(mod, args):
+            self.fetch_unit(rt, forward=False, prefetch=False)
+
+        def post(mod, args, out):
+            if not torch.is_grad_enabled():
+                self.release_unit(rt)
+
+        self._hook_handles.append(module.register_forward_pre_hook(pre))
+        self._hook_handles.append(module.register_forward_hook(post))
+        self._hook_handles.append(module.register_full_backward_pre_hook(lambda m, g: self.fetch_unit(rt, False, False)))
+
+    def destroy(self):
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles.clear()
+
+    # =========================================================================================
+    # introspection helpers (tensor_fragment API, checkpointing)
+    # =========================================================================================
+    def get_global_grad_norm(self):
+        n = self._global_grad_norm
+        return None if n is None else float(n.item())
+
+    def _gather_arena_piece(self, arena: torch.Tensor, rt: _UnitRT, slot) -> torch.Tensor:
+        """Reassemble one parameter's fp32 values from every rank's arena (debug / checkpoint API)."""
+        u = rt.u
+        a = u.arena_offset
+        shard = arena[a:a + u.shard_numel].to(self.device, torch.float32)
+        if self.shard_world > 1:
+            full = torch.empty(u.full_numel, dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(full, shard.contiguous(), group=self.dp_group)
+        else:
+            full = shard
+        return full[slot.offset:slot.offset + slot.numel].view(slot.shape).clone()
+
+    def get_full_hp_param(self, p):
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        if self.master is None:
+            return self._gather_arena_piece(self._lp_arena_as_flat(), rt, s)
+        return self._gather_arena_piece(self.master, rt, s)
+
+    def get_full_hp_grad(self, p):
+        if self.grad_arena is None:
+            return None
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        return self._gather_arena_piece(self.grad_arena, rt, s)
+
+    def get_full_optimizer_state(self, p, key):
+        st = self.flat_opt.state_tensors()
+        if isinstance(self.flat_opt, TorchOptimizerAdapter):
+            return None
+        if key not in st:
+            return None
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        return self._gather_arena_piece(st[key], rt, s)
+
+    def _lp_arena_as_flat(self):
+        if self.lp_arena is not None:
+            return self.lp_arena
+        return torch.cat([self._lp_shard(u) for u in self.units])
+
+    def set_full_hp_param(self, value, p):
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        self._scatter_into_arena(self.master, rt, s, value)
+        # keep the low-precision copy coherent
+        for (r, p0, a0, ln) in param_fragments(rt.u, s, self.shard_world):
+            if r == self.shard_rank:
+                dst = self._lp_shard(rt.u)[a0 - rt.u.arena_offset:a0 - rt.u.arena_offset + ln]
+                dst.copy_(value.reshape(-1)[p0:p0 + ln].to(dst.device, dst.dtype))
+        if rt.state == GATHERED and rt.full is not None:
+            rt.full[s.offset:s.offset + s.numel].copy_(value.reshape(-1).to(rt.full.device, rt.full.dtype))
+
+    def set_full_optimizer_state(self, value, p, key):
+        st = self.flat_opt.state_tensors()
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        self._scatter_into_arena(st[key], rt, s, value)
+
+    def _scatter_into_arena(self, arena, rt, s, value):
+        if arena is None:
+            return
+        flat = value.reshape(-1)
+        for (r, p0, a0, ln) in param_fragments(rt.u, s, self.shard_world):
+            if r == self.shard_rank:
+                arena[a0:a0 + ln].copy_(flat[p0:p0 + ln].to(arena.device, arena.dtype))
+
+    # ---- state dict ---------------------------------------------------------------------------------
+    def state_dict(self):
+        sd = {
+            "zero_stage": self.stage,
+            "loss_scaler": self.loss_scaler.state_dict(),
+            "dynamic_loss_scale": self.dynamic_loss_scale,
+            "overflow": self.overflow,
+            "partition_count": self.shard_world,
+            "group_steps": list(self.group_steps),
+            "global_step": self.global_step,
+            "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+            "fp32_flat": (self.master if self.master is not None else self._lp_arena_as_flat()).detach().cpu().clone(),
+            "arena_numel": self.arena_numel,
+            "unit_layout": [(u.name, u.full_numel, u.shard_numel, u.arena_offset) for u in self.units],
+        }
+        if isinstance(self.flat_opt, TorchOptimizerAdapter):
+            sd["base_optimizer_state"] = self.flat_opt.optimizer.state_dict()
+        else:
+            sd["flat_state"] = {k: v.detach().cpu().clone() for k, v in self.flat_opt.state_tensors().items()}
+        return sd
+
+    def load_state_dict(self, sd, load_optimizer_states=True, load_from_fp32_weights=True):
+        assert sd["partition_count"] == self.shard_world, (
+            f"checkpoint was saved with {sd['partition_count']} shards but this run has {self.shard_world}; "
+            f"use the universal checkpoint path to reshape")
+        self.loss_scaler.load_state_dict(sd["loss_scaler"])
+        self.group_steps = list(sd.get("group_steps", self.group_steps))
+        self.global_step = sd.get("global_step", 0)
+        for g, saved in zip(self.param_groups, sd.get("param_groups", [])):
+            g.update(saved)
+        if load_from_fp32_weights:
+            src = sd["fp32_flat"]
+            if self.master is not None:
+                self.master.copy_(src.to(self.master.device, self.master.dtype))
+            else:
+                for rt in self.rts:
+                    a0 = rt.u.arena_offset
+                    sh = self._lp_shard(rt.u)
+                    sh.copy_(src[a0:a0 + rt.u.shard_numel].to(sh.device, sh.dtype))
+            self._refresh_lp_from_master()
+        if load_optimizer_states:
+            if isinstance(self.flat_opt, TorchOptimizerAdapter) and "base_optimizer_state" in sd:
+                self.flat_opt.optimizer.load_state_dict(sd["base_optimizer_state"])
+            elif "flat_state" in sd:
+                for k, v in sd["flat_state"].items():
+                    self.flat_opt.state_tensors()[k].copy_(v)
+
+    def _refresh_lp_from_master(self):
+        if self.master is not None:
+            self._master_to_lp(0, self.arena_numel)
+        self._post_step(skipped=False)
+        self.global_step -= 1
+
+
+def _adam_cls():
+    from deepspeed_b200.runtime.zero.flat_optimizers import FlatAdam
+    return FlatAdam
+
+
+class _nullctx:
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

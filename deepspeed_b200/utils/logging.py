@@ -1,0 +1,102 @@
+"""Rank-aware logging helpers.
+
+Parity target: reference ``deepspeed/utils/logging.py`` (``logger``, ``log_dist``,
+``print_json_dist``, ``warning_once``).  Implementation is independent: a single
+module-level logger whose handler tags every record with the rank read lazily from
+the environment / torch.distributed.
+"""
+import functools
+import json
+import logging
+import os
+import sys
+
+_LEVELS = {
+    "debug": logging.DEBUG,
+    "info": logging.INFO,
+    "warning": logging.WARNING,
+    "error": logging.ERROR,
+    "critical": logging.CRITICAL,
+}
+
+
+def _current_rank() -> int:
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank()
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0"))
+
+
+class _RankFilter(logging.Filter):
+
+    def filter(self, record):
+        record.rank = _current_rank()
+        return True
+
+
+def _build_logger(name="deepspeed_b200", level=logging.INFO):
+    lg = logging.getLogger(name)
+    if getattr(lg, "_dsb200_configured", False):
+        return lg
+    lg.setLevel(_LEVELS.get(os.environ.get("DSB200_LOG_LEVEL", "").lower(), level))
+    lg.propagate = False
+    h = logging.StreamHandler(stream=sys.stdout)
+    h.setFormatter(
+        logging.Formatter("[%(asctime)s] [%(levelname)s] [rank %(rank)s] [%(filename)s:%(lineno)d] %(message)s"))
+    h.addFilter(_RankFilter())
+    lg.addHandler(h)
+    lg._dsb200_configured = True
+    return lg
+
+
+logger = _build_logger()
+
+
+def should_log(ranks=None) -> bool:
+    """True when this process' rank is in ``ranks`` (``None``/``[-1]`` = everyone)."""
+    if ranks is None:
+        return True
+    ranks = list(ranks)
+    if -1 in ranks:
+        return True
+    return _current_rank() in ranks
+
+
+def log_dist(message, ranks=None, level=logging.INFO):
+    """Log ``message`` only on the listed ranks (reference: utils/logging.py log_dist)."""
+    if should_log(ranks if ranks is not None else [0]):
+        logger.log(level, message, stacklevel=2)
+
+
+def print_json_dist(message: dict, ranks=None, path=None):
+    """Dump a dict as json on the listed ranks (used by the autotuner metric hand-off)."""
+    if should_log(ranks if ranks is not None else [0]):
+        message = dict(message)
+        message["rank"] = _current_rank()
+        if path is None:
+            print(json.dumps(message), flush=True)
+        else:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            with open(path, "w") as f:
+                json.dump(message, f)
+                f.flush()
+
+
+@functools.lru_cache(None)
+def warning_once(msg: str):
+    logger.warning(msg, stacklevel=2)
+
+
+def get_log_level_from_string(s: str) -> int:
+    if s.lower() not in _LEVELS:
+        raise ValueError(f"unknown log level {s!r}; choose from {sorted(_LEVELS)}")
+    return _LEVELS[s.lower()]
+
+
+def set_log_level(level):
+    if isinstance(level, str):
+        level = get_log_level_from_string(level)
+    logger.setLevel(level)

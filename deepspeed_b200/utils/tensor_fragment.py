@@ -1,0 +1,129 @@
+"""Safe accessors for sharded high-precision state.
+
+Parity target: reference ``utils/tensor_fragment.py:132-299`` (``safe_get_full_fp32_param``,
+``safe_get_full_grad``, ``safe_get_full_optimizer_state`` and their ``set`` / ``local`` variants).
+The reference attaches a ``tensor_fragment`` object to every parameter; here the mapping lives in the
+static unit plan (``runtime/zero/units.py param_fragments``) and the optimizer exposes gather /
+scatter helpers on top of it, so these functions are thin dispatchers.  Every ``full`` accessor is a
+collective: all ranks of the DP group must call it.
+"""
+import torch
+
+
+def _zo(param):
+    ref = getattr(param, "_ds_zero", None)
+    return ref() if ref is not None else None
+
+
+def safe_get_full_fp32_param(param):
+    zo = _zo(param)
+    if zo is None:
+        return param.detach().float()
+    return zo.get_full_hp_param(param)
+
+
+def safe_set_full_fp32_param(param, value):
+    zo = _zo(param)
+    if zo is None:
+        with torch.no_grad():
+            param.copy_(value.to(param.dtype))
+        return
+    zo.set_full_hp_param(value, param)
+
+
+def safe_get_full_optimizer_state(param, optim_state_key):
+    zo = _zo(param)
+    if zo is None:
+        return None
+    return zo.get_full_optimizer_state(param, optim_state_key)
+
+
+def safe_set_full_optimizer_state(param, value, optim_state_key):
+    zo = _zo(param)
+    if zo is not None:
+        zo.set_full_optimizer_state(value, param, optim_state_key)
+
+
+def safe_get_full_grad(param):
+    zo = _zo(param)
+    if zo is None:
+        return None if param.grad is None else param.grad.detach().float()
+    return zo.get_full_hp_grad(param)
+
+
+def safe_set_full_grad(param, value):
+    zo = _zo(param)
+    if zo is None:
+        param.grad = value.to(param.dtype)
+        return
+    rt, s = zo.unit_of_param[id(param)], zo.slot_of_param[id(param)]
+    zo._scatter_into_arena(zo.grad_arena, rt, s, value)
+
+
+# ---- local (this rank's fragment) API: ZeRO-3 style ------------------------------------------------
+def _local_view(zo, param, arena):
+    from deepspeed_b200.runtime.zero.units import param_fragments
+    if arena is None:
+        return None
+    rt, s = zo.unit_of_param[id(param)], zo.slot_of_param[id(param)]
+    for (r, p0, a0, ln) in param_fragments(rt.u, s, zo.shard_world):
+        if r == zo.shard_rank:
+            return arena[a0:a0 + ln]
+    return arena[0:0]
+
+
+def safe_get_local_fp32_param(param):
+    zo = _zo(param)
+    if zo is None:
+        return param.detach().float().view(-1)
+    arena = zo.master if zo.master is not None else zo._lp_arena_as_flat()
+    return _local_view(zo, param, arena).float()
+
+
+def safe_set_local_fp32_param(param, value):
+    zo = _zo(param)
+    if zo is None:
+        with torch.no_grad():
+            param.view(-1).copy_(value)
+        return
+    v = _local_view(zo, param, zo.master if zo.master is not None else zo._lp_arena_as_flat())
+    v.copy_(value.to(v.device, v.dtype).view(-1))
+    if zo.master is not None and zo.lp_arena is not None:
+        _local_view(zo, param, zo.lp_arena).copy_(value.view(-1))
+
+
+def safe_get_local_grad(param):
+    zo = _zo(param)
+    if zo is None:
+        return None if param.grad is None else param.grad.view(-1).float()
+    v = _local_view(zo, param, zo.grad_arena)
+    return None if v is None else v.float()
+
+
+def safe_set_local_grad(param, value):
+    zo = _zo(param)
+    if zo is None:
+        param.grad = value.view_as(param).to(param.dtype)
+        return
+    v = _local_view(zo, param, zo.grad_arena)
+    if v is not None:
+        v.copy_(value.to(v.device, v.dtype).view(-1))
+
+
+def safe_get_local_optimizer_state(param, optim_state_key):
+    zo = _zo(param)
+    if zo is None:
+        return None
+    st = zo.flat_opt.state_tensors()
+    if optim_state_key not in st:
+        return None
+    return _local_view(zo, param, st[optim_state_key]).float()
+
+
+def safe_set_local_optimizer_state(param, value, optim_state_key):
+    zo = _zo(param)
+    if zo is None:
+        return
+    st = zo.flat_opt.state_tensors()
+    v = _local_view(zo, param, st[optim_state_key])
+    v.copy_(value.to(v.device, v.dtype).view(-1))
