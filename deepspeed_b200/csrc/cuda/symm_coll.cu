@@ -1,0 +1,3 @@
+// placeholder -- replaced by the real implementation in a later commit of this round
+#include "dsb_common.cuh"
+DSB_EXPORT int dsb_symm_coll_version() { return 0; }

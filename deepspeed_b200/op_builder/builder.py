@@ -44,6 +44,12 @@ def nvcc_path() -> Optional[str]:
     return cand if cand and os.path.exists(cand) else None
 
 
+def cxx_path() -> str:
+    """Host C++ compiler.  ``$CXX`` is deliberately NOT honoured blindly: some images export a wrapper
+    without OpenMP specs; ``DSB200_CXX`` overrides, else the first ``g++`` on PATH."""
+    return os.environ.get("DSB200_CXX") or shutil.which("g++") or "g++"
+
+
 def cuda_home() -> str:
     n = nvcc_path()
     return str(Path(n).resolve().parent.parent) if n else os.environ.get("CUDA_HOME", "/usr/local/cuda")
@@ -126,7 +132,7 @@ class OpBuilder:
                 raise BuildError("nvcc not found; cannot build CUDA sources")
         else:
             flags = CXX_FLAGS + _simd_flags() + self.EXTRA_CXX + incs
-            tool = os.environ.get("CXX", "g++")
+            tool = cxx_path()
         key = _hash([src] + _headers(), flags)
         obj = OBJ_DIR / f"{self.NAME}-{src.stem}-{key}.o"
         if obj.exists():
@@ -155,7 +161,7 @@ class OpBuilder:
             cmd = [nvcc_path(), "-shared"] + ARCH_FLAGS + ["-Xcompiler", "-fPIC", "-o", str(tmp)] + \
                 [str(o) for o in objs] + ["-lcudart"] + self.LINK_LIBS
         else:
-            cmd = [os.environ.get("CXX", "g++"), "-shared", "-fPIC", "-fopenmp", "-o", str(tmp)] + \
+            cmd = [cxx_path(), "-shared", "-fPIC", "-fopenmp", "-o", str(tmp)] + \
                 [str(o) for o in objs] + self.LINK_LIBS
         _run(cmd)
         os.replace(tmp, out)

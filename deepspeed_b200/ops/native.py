@@ -61,7 +61,12 @@ def stream(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+launch_count = 0  # native entry points invoked since import (each launches >= 1 kernel)
+
+
 def check(rc: int, what: str):
+    global launch_count
+    launch_count += 1
     if rc == 0:
         return
     if rc == -1:

@@ -433,6 +433,10 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         if self.module.training:
             self.tput_timer.start()
         inputs, kwargs = self._cast_inputs(inputs, kwargs)
+        if self.optimizer is not None and hasattr(self.module, "ds_loss_multiplier"):
+            # lets fused loss heads fold the upcoming backward scale into their in-forward gradients
+            gas = self.gradient_accumulation_steps()
+            self.module.ds_loss_multiplier = float(self.optimizer.loss_scale) / (gas if gas > 1 else 1)
         loss = self.module(*inputs, **kwargs)
         self.timers(FORWARD_MICRO_TIMER).stop()
         self.timers(FORWARD_GLOBAL_TIMER).stop()

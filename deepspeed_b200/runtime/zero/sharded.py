@@ -64,7 +64,9 @@ class _UnitRT:
         self.n_trainable = 0
         self.reduced_this_micro = False
         self.dense_grads = False  # set by model integrations that write every gradient view
-        self.in_use = 0
+        self.temp_refs = 0  # GatheredParameters / external users holding the unit
+        self.home = None  # buffer used by this iteration's forward gather (backward MUST reuse it)
+        self.consumed = False  # a module hook actually used the gathered copy (vs. a speculative prefetch)
 
 
 class ZeroShardedOptimizer:
@@ -146,6 +148,10 @@ class ZeroShardedOptimizer:
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 p2g[id(p)] = gi
+        if isinstance(self.flat_opt, TorchOptimizerAdapter):
+            # the client optimizer reads ITS group dicts at step time: expose those very objects so LR
+            # schedulers (which mutate ``optimizer.param_groups[i]["lr"]``) reach it
+            self.param_groups = client_optimizer.param_groups
         for p in module.parameters():
             if id(p) not in p2g:
                 p2g[id(p)] = -1  # frozen / unmanaged: sharded but never stepped
@@ -506,7 +512,7 @@ class ZeroShardedOptimizer:
             if rt.gather_event is not None and self.on_cuda:
                 torch.cuda.current_stream().wait_event(rt.gather_event)
             rt.state = GATHERED
-        rt.in_use += 1
+        rt.consumed = True
         if prefetch and self.prefetch_depth > 0:
             for nxt in self._upcoming(rt, forward):
                 if nxt.state == NOT_GATHERED and not nxt.u.persistent:
@@ -528,11 +534,24 @@ class ZeroShardedOptimizer:
 
     def _launch_gather(self, rt: _UnitRT):
         u = rt.u
-        slot = self.param_pool[u.index % len(self.param_pool)]
-        if slot.owner is not None and slot.owner is not rt and slot.owner.state != NOT_GATHERED:
-            if slot.owner.in_use > 0 or slot.owner.state == GATHERED:
-                # occupant still live (irregular graph): use a private buffer rather than corrupt it
-                slot = _Slot(self._symm_or_empty(self.max_full, self.model_dtype))
+        # Autograd may hold *views* of the gathered weights saved during forward, so the backward
+        # re-gather must land in the very same memory: ``rt.home`` remembers the forward buffer.
+        slot = rt.home if rt.home is not None else self.param_pool[u.index % len(self.param_pool)]
+        occ = slot.owner
+        if occ is not None and occ is not rt and occ.state != NOT_GATHERED and not occ.consumed \
+                and occ.temp_refs == 0:
+            # speculative prefetch that nobody used (e.g. a module skipped by this forward): evict it
+            self._detach_params(occ)
+            occ.full, occ.state, occ.gather_event, occ.home = None, NOT_GATHERED, None, None
+        if occ is not None and occ is not rt and occ.state != NOT_GATHERED:
+            if rt.home is not None:
+                raise RuntimeError(
+                    f"ZeRO-3 unit '{u.name}' must be re-gathered into the buffer it used in forward, but that "
+                    f"buffer still holds live unit '{occ.u.name}'.  Increase zero_optimization.b200_unit_prefetch "
+                    f"(pool size) or mark the enclosing module as a z3 leaf module.")
+            slot = _Slot(self._symm_or_empty(self.max_full, self.model_dtype))  # irregular graph: private buffer
+        if self._in_backward is False or rt.home is None:
+            rt.home = slot
         stream = self.ag_stream
         cur = torch.cuda.current_stream() if self.on_cuda else None
         if stream is not None:
@@ -559,6 +578,7 @@ class ZeroShardedOptimizer:
         rt.slot = slot
         rt.full = full
         rt.state = INFLIGHT
+        rt.consumed = False
         self._point_params(rt, full)
 
     def _all_gather(self, full, shard, u: Unit):
@@ -571,10 +591,7 @@ class ZeroShardedOptimizer:
 
     @instrument_w_nvtx
     def release_unit(self, rt: _UnitRT):
-        if not self.transient or rt.u.persistent or rt.state == NOT_GATHERED:
-            return
-        rt.in_use = max(0, rt.in_use - 1)
-        if rt.in_use > 0:
+        if not self.transient or rt.u.persistent or rt.state == NOT_GATHERED or rt.temp_refs > 0:
             return
         if self.on_cuda and rt.slot is not None:
             ev = torch.cuda.Event()
@@ -599,13 +616,13 @@ class ZeroShardedOptimizer:
                 rt.full = buf
                 rt.slot = None
                 rt.state = GATHERED
-                rt.in_use += 1
+                rt.temp_refs += 1
                 self._point_params(rt, buf)
 
     def release_all(self):
         for rt in self.rts:
             if self.transient and not rt.u.persistent and rt.state != NOT_GATHERED:
-                rt.in_use = 0
+                rt.temp_refs = 0
                 self._detach_params(rt)
                 rt.full = None
                 rt.state = NOT_GATHERED
@@ -712,8 +729,8 @@ class ZeroShardedOptimizer:
         if self.transient:
             for rt in self.rts:
                 if not rt.u.persistent and rt.state != NOT_GATHERED and rt.grad_full is None:
-                    rt.in_use = 0
                     self.release_unit(rt)
+                rt.home = None
         self._in_backward = False
         if not self._trace_done and self._trace:
             self._trace_done = True
@@ -911,14 +928,14 @@ class ZeroShardedOptimizer:
             dist.all_gather_into_tensor(buf, shard, group=self.dp_group)
             rt.full, rt.slot, rt.state = buf, None, GATHERED
             self._point_params(rt, buf)
-        rt.in_use += 1
+        rt.temp_refs += 1
 
     def release_param_temp(self, p, write_back_from=None):
         rt = self.unit_of_param[id(p)]
         if write_back_from is not None:
             self.sync_param_from_full(p, write_back_from)
-        rt.in_use = max(0, rt.in_use - 1)
-        if rt.in_use == 0 and self.transient and not rt.u.persistent:
+        rt.temp_refs = max(0, rt.temp_refs - 1)
+        if rt.temp_refs == 0 and self.transient and not rt.u.persistent and not self._in_backward:
             self._detach_params(rt)
             rt.full, rt.state, rt.gather_event = None, NOT_GATHERED, None
 
