@@ -579,7 +579,9 @@ DSB_EXPORT int dsb_norm_fwd(const void* x, const void* residual, const void* w, 
 
 DSB_EXPORT int dsb_norm_bwd_grid(int rows)
 {
-    const int cap = kSmCountB200 * 2;
+    // HBM-bound: as many resident CTAs as the register budget allows (~6 per SM at 128 threads);
+    // more CTAs = more dw partial rows, so stop there.
+    const int cap = kSmCountB200 * 6;
     return rows < cap ? rows : cap;
 }
 

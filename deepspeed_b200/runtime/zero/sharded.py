@@ -168,6 +168,7 @@ class ZeroShardedOptimizer:
                 self.unit_of_param[id(s.param)] = rt
                 self.slot_of_param[id(s.param)] = s
             rt.n_trainable = sum(1 for s in rt.u.slots if s.param.requires_grad)
+            rt.layout_sig = (rt.u.full_numel, tuple((s.offset, s.numel) for s in rt.u.slots))
             # whole-unit persistence (small units stay gathered, like the reference's
             # param_persistence_threshold but at unit granularity)
             rt.u.persistent = self.stage < 3 or self.shard_world == 1 or rt.u.raw_numel <= thresh
@@ -250,8 +251,10 @@ class ZeroShardedOptimizer:
         self.transient = S3
         # ---- low-precision storage ------------------------------------------------------------
         if S3:
-            lp_dev = "cpu" if self.offload_param else dev
-            self.lp_arena = self._empty(self.arena_numel, lp, lp_dev, pin=True)
+            if self.offload_param:
+                self.lp_arena = self._empty(self.arena_numel, lp, "cpu", pin=True)
+            else:
+                self.lp_arena = self._symm_or_empty(self.arena_numel, lp)  # peers gather straight from it
             n_slots = 2 + self.prefetch_depth
             self.param_pool = [_Slot(self._symm_or_empty(self.max_full, lp)) for _ in range(n_slots)]
             self.full_arena = None
@@ -462,8 +465,13 @@ class ZeroShardedOptimizer:
         slot.owner = rt
         rt.grad_slot = slot
         rt.grad_full = slot.buf[:rt.u.full_numel]
-        if not rt.dense_grads:
+        # No blanket memset: every parameter slot is either written before the reduce or zeroed in the
+        # flush path (unused parameters).  Only the alignment gaps must be zero, and they already are
+        # when the buffer last held a unit with the same layout (all transformer blocks share one).
+        sig = rt.layout_sig
+        if getattr(slot, "layout_sig", None) != sig:
             rt.grad_full.zero_()
+            slot.layout_sig = sig
         rt.pending = rt.n_trainable
         for s in rt.u.slots:
             s._written = False
@@ -655,8 +663,11 @@ class ZeroShardedOptimizer:
             if self.shard_world > 1:
                 lo, hi = u.shard_range(self.shard_rank)
                 if self._symm is not None and self._symm.owns(full_g):
-                    shard_g = self._symm_reduce(rt, full_g, scale)
-                    scale = None  # consumed inside the fused kernel
+                    res = self._symm_reduce(rt, full_g, scale)
+                    if res is None:
+                        scale = None  # consumed inside the fused kernel
+                    else:
+                        shard_g, scale = res
                 else:
                     shard_g = self._rs_tmp[u.index % 2][:u.shard_numel]
                     w = dist.reduce_scatter_tensor(shard_g, full_g, group=self.dp_group, async_op=self.on_cuda)
@@ -699,23 +710,31 @@ class ZeroShardedOptimizer:
         flat_ops.scale_cast(shard_g, dst, scale=scale, accumulate=not first)
 
     def _symm_reduce(self, rt: _UnitRT, full_g, scale):
-        """In-kernel reduce-scatter over NVLink peer memory, fused with scale + (Adam | accumulate)."""
+        """In-kernel reduce-scatter over NVLink peer memory, fused with scale + (Adam | accumulate).
+        Returns ``None`` when the kernel consumed the gradient, else ``(shard_grad, remaining_scale)``."""
         u = rt.u
         a, b = u.arena_offset, u.arena_offset + u.shard_numel
         boundary = self.is_gradient_accumulation_boundary()
-        if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()):
+        if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()) and self.master is not None:
             self._symm.reduce_scatter_adam(self, rt, full_g, scale)
-        else:
+            return None
+        if self.grad_arena is not None and self.grad_arena.is_cuda and not self.fused_in_backward:
             first = (self.micro_step % self.gas) == 0
             self._symm.reduce_scatter_accumulate(full_g, self.grad_arena[a:b], u.shard_numel, scale,
                                                  accumulate=not first)
-        return None
+            return None
+        tmp = self._rs_tmp[u.index % 2][:u.shard_numel]
+        self._symm.reduce_scatter_accumulate(full_g, tmp, u.shard_numel, scale, accumulate=False)
+        return tmp, 1.0
 
     def end_backward(self):
         """Flush units whose gradients are partially populated (unused parameters) and close the
         micro step.  Called by the engine after ``loss.backward()`` returns."""
         for rt in self.rts:
             if rt.grad_full is not None and rt.pending > 0:
+                for sl in rt.u.slots:  # parameters that received no gradient this micro step
+                    if not getattr(sl, "_written", False):
+                        rt.grad_full[sl.offset:sl.offset + sl.numel].zero_()
                 rt.pending = 0
                 self._reduce_unit(rt)
         if self.grad_arena is not None and (self.micro_step % self.gas) == 0:
@@ -888,25 +907,28 @@ class ZeroShardedOptimizer:
     def _post_step(self, skipped=False):
         """Make the updated low-precision parameters visible: stage<=2 all-gathers each unit in
         place; stage 3 invalidates gathered copies (persistent units are re-gathered)."""
-        if self.on_cuda:
-            ev = torch.cuda.Event()
-            ev.record()
-            self._step_event = ev
+        if self._symm is not None:
+            self._symm.barrier()  # every rank's shard is final before any peer reads it
+        gathered = False
         if not skipped and self.shard_world > 1:
             if not self.transient:
                 for rt in self.rts:
                     lo, hi = rt.u.shard_range(self.shard_rank)
                     self._all_gather(rt.full, rt.full[lo:hi], rt.u)
+                    gathered = True
             else:
                 for rt in self.rts:
                     if rt.u.persistent:
                         lo, hi = rt.u.shard_range(self.shard_rank)
                         rt.full[lo:hi].copy_(self._lp_shard(rt.u))
                         self._all_gather(rt.full, rt.full[lo:hi], rt.u)
-        if self._symm is not None:
-            self._symm.barrier()
+        if self._symm is not None and gathered:
+            self._symm.barrier()  # peers are done reading our in-place shard before the next update
+        if self.on_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._step_event = ev
         self.global_step += 1
-
 
     # =========================================================================================
     # GatheredParameters / external-parameter support

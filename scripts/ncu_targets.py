@@ -1,0 +1,50 @@
+"""Small standalone launches of the framework's hot kernels, for `ncu --set full` captures.
+Usage: python scripts/ncu_targets.py adam|rmsnorm|swiglu|xent|rope"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from deepspeed_b200.ops.kernels import flat_ops, transformer_ops as T
+
+which = sys.argv[1] if len(sys.argv) > 1 else "adam"
+d = "cuda"
+torch.manual_seed(0)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=d)
+if which == "adam":
+    n = 256 * 1024 * 1024
+    p = torch.randn(n, device=d)
+    g = torch.randn(n, device=d, dtype=torch.bfloat16)
+    m, v = torch.zeros(n, device=d), torch.zeros(n, device=d)
+    out = torch.empty(n, device=d, dtype=torch.bfloat16)
+    for step in range(1, 6):
+        flush.zero_()
+        flat_ops.adam_flat(p, g, m, v, out, lr=1e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.1, step=step)
+elif which == "rmsnorm":
+    x = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16, requires_grad=True)
+    w = torch.ones(4096, device=d, dtype=torch.bfloat16, requires_grad=True)
+    for _ in range(5):
+        flush.zero_()
+        y, s = T.rms_norm(x, w, 1e-5, residual=r)
+        (y.sum() + s.sum()).backward()
+elif which == "swiglu":
+    gu = torch.randn(8192, 2 * 14336, device=d, dtype=torch.bfloat16, requires_grad=True)
+    for _ in range(5):
+        flush.zero_()
+        T.gated_act(gu, "silu").sum().backward()
+elif which == "xent":
+    lg = torch.randn(2048, 128256, device=d, dtype=torch.bfloat16)
+    lab = torch.randint(0, 128256, (2048, ), device=d)
+    for _ in range(5):
+        flush.zero_()
+        T.softmax_xent_fwd_bwd(lg.clone(), lab, 1.0)
+elif which == "rope":
+    table = T.RotaryTable(128, 8192, 500000.0, d)
+    qkv = torch.randn(8192, 6144, device=d, dtype=torch.bfloat16)
+    for _ in range(5):
+        flush.zero_()
+        T.rope_qk_inplace(qkv, 32, 8, 128, table, None, 4096)
+torch.cuda.synchronize()
+print("done", which)

@@ -1,0 +1,101 @@
+"""Multi-GPU tier: symmetric-memory arena + in-kernel NVLink collectives vs NCCL / torch references."""
+import os
+
+import pytest
+import torch
+
+from tests.common import run_distributed
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _collectives():
+    import torch.distributed as dist
+    from deepspeed_b200.comm import symm
+    from deepspeed_b200.ops.kernels import flat_ops
+    r, w = dist.get_rank(), dist.get_world_size()
+    assert symm.is_supported(None, explicit=True), "symmetric memory unavailable on this box"
+    ctx = symm.get_context(None)
+    S = 1 << 20
+    torch.manual_seed(100 + r)
+    # ---- all-gather ------------------------------------------------------------------------------
+    shard = ctx.alloc(S, torch.bfloat16)
+    full = ctx.alloc(S * w, torch.bfloat16)
+    shard.copy_(torch.randn(S, device="cuda"))
+    torch.cuda.synchronize(); dist.barrier()
+    ctx.all_gather(full, shard, S)
+    ref = torch.empty(S * w, dtype=torch.bfloat16, device="cuda")
+    dist.all_gather_into_tensor(ref, shard)
+    assert torch.equal(full, ref)
+    # ---- reduce-scatter + accumulate ----------------------------------------------------------------
+    g = ctx.alloc(S * w, torch.bfloat16)
+    g.copy_(torch.randn(S * w, device="cuda"))
+    torch.cuda.synchronize(); dist.barrier()
+    gf = g.float()
+    dist.all_reduce(gf)
+    want = gf[r * S:(r + 1) * S] * (1.0 / w)
+    for ddt in (torch.float32, torch.bfloat16):
+        dst = torch.ones(S, dtype=ddt, device="cuda")
+        ctx.reduce_scatter_accumulate(g, dst, S, 1.0 / w, accumulate=False)
+        tol = 1e-5 if ddt == torch.float32 else 2e-2
+        assert (dst.float() - want).abs().max() < tol * max(1.0, want.abs().max().item()), ddt
+        ctx.reduce_scatter_accumulate(g, dst, S, 1.0 / w, accumulate=True)
+        assert (dst.float() - 2 * want).abs().max() < 2 * tol * max(1.0, want.abs().max().item()), ddt
+    # ---- barrier + one-shot all-reduce ----------------------------------------------------------------
+    ctx.barrier()
+    t = ctx.alloc(4096, torch.float32)
+    t.copy_(torch.full((4096, ), float(r + 1), device="cuda"))
+    torch.cuda.synchronize(); dist.barrier()
+    assert ctx.all_reduce_(t)
+    assert torch.allclose(t, torch.full_like(t, w * (w + 1) / 2))
+    torch.cuda.synchronize()
+
+
+def test_symm_collectives_2gpu():
+    _need(2)
+    run_distributed(_collectives, 2, backend="nccl")
+
+
+def _engine_parity(fused):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.models.llama import LlamaForCausalLM, llama_config
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    cfg = llama_config("tiny", hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2,
+                       vocab_size=1024, num_hidden_layers=3)
+    outs = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        with torch.device("cuda"):
+            model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+        conf = {"train_micro_batch_size_per_gpu": 2, "bf16": {"enabled": True},
+                "optimizer": {"type": "AdamW", "params": {"lr": 1e-3, "weight_decay": 0.1}},
+                "gradient_clipping": 0.0 if fused else 1.0,
+                "zero_optimization": {"stage": 3, "stage3_param_persistence_threshold": 0, "b200_fused_collectives": mode}}
+        eng, _, _, _ = ds.initialize(model=model, config=conf)
+        assert (eng.optimizer._symm is not None) == mode
+        g = torch.Generator().manual_seed(7)
+        losses = []
+        for _ in range(4):
+            ids = torch.randint(0, cfg.vocab_size, (2 * w, 64), generator=g)[r * 2:(r + 1) * 2].cuda()
+            loss = eng(ids, labels=ids)
+            eng.backward(loss)
+            eng.step()
+            losses.append(loss.item())
+        outs[mode] = (losses, [safe_get_full_fp32_param(p).clone() for p in model.parameters()])
+        eng.destroy()
+    la, lb = outs[False][0], outs[True][0]
+    assert all(abs(a - b) < 2e-2 for a, b in zip(la, lb)), (la, lb)
+    worst = max((a - b).abs().max().item() for a, b in zip(outs[False][1], outs[True][1]))
+    assert worst < 5e-3, worst  # 4 Adam steps at lr 1e-3: only reduction-order noise allowed
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_zero3_symm_matches_nccl_2gpu(fused):
+    _need(2)
+    run_distributed(_engine_parity, 2, args=(fused, ), backend="nccl")
