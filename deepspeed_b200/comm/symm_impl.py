@@ -164,6 +164,8 @@ class SymmContext:
         self.segments: List[_Segment] = []
         self.epochs = [1] * self.lib.dsb_symm_channels()
         self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "32"))
+        self.ag_ctas = int(os.environ.get("DSB200_SYMM_AG_CTAS", str(self.ctas)))
+        self.ag_mode = os.environ.get("DSB200_SYMM_AG", "ce").lower()  # "ce" (DMA engines) | "kernel" (SM pull)
         # signal pads live in their own small segment (never multicast-bound)
         self._pad_seg = _Segment(self, self._round(max(self.lib.dsb_symm_pad_bytes(), 4096)), want_mc=False)
         self._pad_seg.tensor.zero_()
@@ -227,8 +229,14 @@ class SymmContext:
         every rank.  No internal barrier: callers order it after the optimizer-step barrier."""
         shards, _ = self._peers(shard)
         nbytes = shard_numel * shard.element_size()
+        if self.ag_mode == "ce":
+            # copy-engine DMA straight from the peers' shards: no SMs taken from the GEMMs it overlaps with
+            rc = self.lib.dsb_symm_all_gather_ce(shards, N.ptr(full), ctypes.c_int64(nbytes), self.rank, self.world,
+                                                 N.stream())
+            N.check(rc, "symm_all_gather_ce")
+            return
         rc = self.lib.dsb_symm_all_gather(shards, N.ptr(full), ctypes.c_int64(nbytes), self._pads, self.rank, self.world,
-                                          CH_AG, ctypes.c_uint32(0), 0, self.ctas, N.stream())
+                                          CH_AG, ctypes.c_uint32(0), 0, self.ag_ctas, N.stream())
         N.check(rc, "symm_all_gather")
 
     def _sumsq_buf(self):

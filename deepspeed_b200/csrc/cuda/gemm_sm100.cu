@@ -1,3 +1,515 @@
-// placeholder -- replaced by the real implementation in a later commit of this round
+// Hand-written sm_100a GEMM: C[M,N] (bf16) = A[M,K] (bf16, K-major) x B[N,K]^T (bf16, K-major), fp32 accumulate.
+//
+//   * operands staged global -> shared by TMA (cp.async.bulk.tensor, 128-byte swizzle), 4-stage mbarrier ring
+//   * tcgen05.mma (cta_group::1, kind::f16, M=128 N=256 K=16) issued by ONE elected thread, accumulators
+//     in TMEM (2 x 256 columns: the epilogue of tile i overlaps the main loop of tile i+1)
+//   * warp-specialised persistent CTAs (one per SM): warp0 = TMA producer, warp1 = MMA issuer,
+//     warp2 = TMEM allocator, warps4-7 = epilogue (tcgen05.ld -> bf16 -> swizzled smem -> TMA store)
+//   * OPTIONAL fused all-gather: when `ag` is given, the weight matrix B is being assembled in local
+//     memory from the other ranks' ZeRO shards *by this same kernel*: `ag.comm_ctas` CTAs pull the
+//     peers' shard bytes over NVLink (peer-mapped addresses) chunk by chunk and publish a per-chunk
+//     ready flag (st.release.gpu); the TMA producer of each MMA CTA acquires the flag of the chunk(s)
+//     backing a B tile before loading it, and tiles are visited starting with the locally owned rows,
+//     so transfer and math overlap tile by tile with no NCCL call.
+//
+// The reference has no tensor-core GEMM of its own for training (cuBLAS via csrc/transformer/
+// cublas_wrappers.cu:65 or torch.matmul); this kernel is the framework's native path.
+#include <cuda.h>
 #include "dsb_common.cuh"
-DSB_EXPORT int dsb_gemm_sm100_version() { return 0; }
+
+namespace dsb {
+namespace gemm {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int CCHUNK = 64;  // epilogue column chunk (64 bf16 = 128 B = one swizzle row)
+constexpr int kThreads = 256;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
+constexpr uint32_t C_BUF_BYTES = BM * CCHUNK * 2;  // 16 KiB
+constexpr uint32_t SMEM_A = 0;
+constexpr uint32_t SMEM_B = SMEM_A + STAGES * A_STAGE_BYTES;
+constexpr uint32_t SMEM_C = SMEM_B + STAGES * B_STAGE_BYTES;
+constexpr uint32_t SMEM_BAR = SMEM_C + 2 * C_BUF_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread `lane` receives row `lane`, registers = consecutive columns.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// K-major, 128B-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);          // start address
+    d |= static_cast<uint64_t>(1) << 16;                              // LBO (unused for swizzled K-major) = 1
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                      // SBO = 1024 B
+    d |= static_cast<uint64_t>(1) << 46;                              // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
+    return d;
+}
+
+// c=F32, a=b=BF16, both K-major, N=256, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+// ---- fused all-gather descriptor ------------------------------------------------------------------------
+struct AgParams {
+    // B (= this unit's gathered weights) lives in `local_full`; rank p's shard is `shard_bytes` long and is
+    // found at peers[p] (peer-mapped VA).  Chunk c covers bytes [c*chunk_bytes, (c+1)*chunk_bytes) of the
+    // unit's flat buffer; flags[c] becomes `epoch` once the chunk is resident in local_full.
+    const void* peers[8];
+    void* local_full;
+    uint32_t* flags;
+    int64_t shard_bytes;
+    int64_t chunk_bytes;
+    int64_t b_offset_bytes;  // byte offset of B's first element inside the unit flat buffer
+    int n_chunks;
+    int world;
+    int rank;
+    int comm_ctas;  // trailing CTAs of the grid that do the gathering
+    uint32_t epoch;
+    int enabled;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Gather role: CTA `ci` of `nc` copies chunks ci, ci+nc, ... in the order "own shard first, then rank+1, ...".
+__device__ void ag_gather_role(const AgParams& ag, int ci, int nc)
+{
+    const int chunks_per_shard = static_cast<int>(ag.shard_bytes / ag.chunk_bytes);
+    for (int j = ci; j < ag.n_chunks; j += nc) {
+        // visit order: shards rotated so that every rank starts pulling from a different peer
+        const int k = j / chunks_per_shard;
+        const int within = j - k * chunks_per_shard;
+        const int peer = (ag.rank + k) % ag.world;
+        const int chunk = peer * chunks_per_shard + within;
+        const int64_t off = static_cast<int64_t>(within) * ag.chunk_bytes;
+        const char* src = static_cast<const char*>(ag.peers[peer]) + off;
+        char* dst = static_cast<char*>(ag.local_full) + static_cast<int64_t>(peer) * ag.shard_bytes + off;
+        const int64_t nvec = ag.chunk_bytes >> 4;
+        if (peer == ag.rank) {
+            for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) st_plain(dst + (i << 4), ld_plain(src + (i << 4)));
+        } else {
+            constexpr int kU = 4;
+            int64_t i = threadIdx.x;
+            for (; i + (kU - 1) * blockDim.x < nvec; i += kU * blockDim.x) {
+                Vec16 v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) v[u] = ld_peer(src + ((i + u * blockDim.x) << 4));
+#pragma unroll
+                for (int u = 0; u < kU; ++u) st_plain(dst + ((i + u * blockDim.x) << 4), v[u]);
+            }
+            for (; i < nvec; i += blockDim.x) st_plain(dst + (i << 4), ld_peer(src + (i << 4)));
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu_u32(ag.flags + chunk, ag.epoch);
+    }
+}
+
+// Wait until every chunk overlapping B rows [n0, n0+rows) is resident.
+__device__ __forceinline__ void ag_wait_rows(const AgParams& ag, int n0, int rows, int K)
+{
+    const int64_t lo = ag.b_offset_bytes + static_cast<int64_t>(n0) * K * 2;
+    const int64_t hi = lo + static_cast<int64_t>(rows) * K * 2;
+    int c0 = static_cast<int>(lo / ag.chunk_bytes);
+    int c1 = static_cast<int>((hi - 1) / ag.chunk_bytes);
+    if (c1 >= ag.n_chunks) c1 = ag.n_chunks - 1;
+    for (int c = c0; c <= c1; ++c) {
+        while (ld_acquire_gpu_u32(ag.flags + c) != ag.epoch) __nanosleep(64);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, int M, int N, int K, const AgParams ag)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment required by SWIZZLE_128B
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_base = sbase + SMEM_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8 * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8 * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8 * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8 * (2 * STAGES + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int mma_ctas = ag.enabled ? static_cast<int>(gridDim.x) - ag.comm_ctas : static_cast<int>(gridDim.x);
+
+    if (ag.enabled && static_cast<int>(blockIdx.x) >= mma_ctas) {
+        ag_gather_role(ag, static_cast<int>(blockIdx.x) - mma_ctas, ag.comm_ctas);
+        return;
+    }
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m = (M + BM - 1) / BM;
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (K + BK - 1) / BK;
+    // With the fused gather, n-blocks are visited starting at the locally owned rows.
+    int n_rot = 0;
+    if (ag.enabled) {
+        const int64_t own_lo = static_cast<int64_t>(ag.rank) * ag.shard_bytes - ag.b_offset_bytes;
+        int64_t row = own_lo > 0 ? (own_lo + static_cast<int64_t>(K) * 2 - 1) / (static_cast<int64_t>(K) * 2) : 0;
+        n_rot = static_cast<int>((row + BN - 1) / BN) % num_n;
+    }
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += mma_ctas) {
+                const int m_blk = tile % num_m;
+                const int n_blk = (tile / num_m + n_rot) % num_n;
+                if (ag.enabled) ag_wait_rows(ag, n_blk * BN, (N - n_blk * BN) < BN ? (N - n_blk * BN) : BN, K);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_2d(sbase + SMEM_A + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m_blk * BM);
+                    tma_load_2d(sbase + SMEM_B + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n_blk * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += mma_ctas, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = make_desc_kmajor_sw128(sbase + SMEM_A + stage * A_STAGE_BYTES);
+                    const uint64_t db = make_desc_kmajor_sw128(sbase + SMEM_B + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row
+                        umma_bf16(tmem_d, da + static_cast<uint64_t>((k * UMMA_K * 2) >> 4),
+                                  db + static_cast<uint64_t>((k * UMMA_K * 2) >> 4), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;  // TMEM lane group == warp_id % 4
+        const int etid = threadIdx.x - 128;
+        const int row = ew * 32 + lane;  // row inside the 128-row tile
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += mma_ctas, ++it) {
+            const int m_blk = tile % num_m;
+            const int n_blk = (tile / num_m + n_rot) % num_n;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / CCHUNK; ++c) {
+                const int buf = c & 1;
+                if (etid == 0) tma_store_wait_read<1>();  // the store that last used `buf` has drained
+                epi_bar_sync();
+                uint32_t r[64];
+                tmem_ld_32x32(taddr + c * CCHUNK, r);
+                tmem_ld_32x32(taddr + c * CCHUNK + 32, r + 32);
+                tmem_ld_wait();
+                if (c == BN / CCHUNK - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                uint8_t* crow = smem + SMEM_C + buf * C_BUF_BYTES + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j * 8 + e]);
+                    const Vec16 v = Elem<__nv_bfloat16>::pack(f);
+                    const uint32_t dst = smem_u32(crow + ((j ^ (row & 7)) << 4));  // 128B swizzle
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                                 "r"(v.w[3])
+                                 : "memory");
+                }
+                fence_async_smem();
+                epi_bar_sync();
+                if (etid == 0) {
+                    tma_store_2d(&map_c, sbase + SMEM_C + buf * C_BUF_BYTES, n_blk * BN + c * CCHUNK, m_blk * BM);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (etid == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// Row-major [rows, cols] bf16 matrix with leading dimension `ld` (elements); box = [box_rows, box_cols].
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                    uint32_t box_cols)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -3;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 100;
+}
+
+}  // namespace gemm
+}  // namespace dsb
+
+using namespace dsb::gemm;
+
+static int g_sm_count = 0;
+static bool g_attr_set = false;
+
+static int launch(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc, const AgParams& ag,
+                  int sms, cudaStream_t stream)
+{
+    if (K % 8 || lda % 8 || ldb % 8 || ldc % 8) return -2;
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return -2;
+    CUtensorMap ma, mb, mc;
+    int rc;
+    if ((rc = make_map(&ma, a, M, K, lda, BM, BK))) return rc;
+    if ((rc = make_map(&mb, b, N, K, ldb, BN, BK))) return rc;
+    if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        g_attr_set = true;
+    }
+    int grid = sms > 0 ? sms : g_sm_count;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    int mma = ag.enabled ? grid - ag.comm_ctas : grid;
+    if (mma < 1) return -2;
+    if (mma > tiles) {
+        mma = tiles;
+        grid = ag.enabled ? mma + ag.comm_ctas : mma;
+    }
+    gemm_nt_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(ma, mb, mc, M, N, K, ag);
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+// C[M,N] = A[M,K] @ B[N,K]^T   (bf16 in/out, fp32 accumulate).  sms <= 0 -> all SMs.
+DSB_EXPORT int dsb_gemm_nt_bf16(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                int sms, cudaStream_t stream)
+{
+    AgParams ag;
+    memset(&ag, 0, sizeof(ag));
+    return launch(a, b, c, M, N, K, lda, ldb, ldc, ag, sms, stream);
+}
+
+// Fused all-gather + GEMM.  `b` points at B inside `local_full` (the unit's gathered buffer); the kernel
+// fills local_full from peers[] (each `shard_bytes` long) while multiplying.  `flags` holds n_chunks words.
+DSB_EXPORT int dsb_gemm_nt_bf16_allgather(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb,
+                                          int ldc, void* const* peers, void* local_full, uint32_t* flags,
+                                          int64_t shard_bytes, int64_t chunk_bytes, int64_t b_offset_bytes, int world,
+                                          int rank, int comm_ctas, uint32_t epoch, int sms, cudaStream_t stream)
+{
+    if (world > 8 || chunk_bytes <= 0 || shard_bytes % chunk_bytes || chunk_bytes % 16) return -2;
+    AgParams ag;
+    memset(&ag, 0, sizeof(ag));
+    for (int i = 0; i < world; ++i) ag.peers[i] = peers[i];
+    ag.local_full = local_full;
+    ag.flags = flags;
+    ag.shard_bytes = shard_bytes;
+    ag.chunk_bytes = chunk_bytes;
+    ag.b_offset_bytes = b_offset_bytes;
+    ag.n_chunks = static_cast<int>(shard_bytes / chunk_bytes) * world;
+    ag.world = world;
+    ag.rank = rank;
+    ag.comm_ctas = comm_ctas;
+    ag.epoch = epoch;
+    ag.enabled = 1;
+    return launch(a, b, c, M, N, K, lda, ldb, ldc, ag, sms, stream);
+}
+
+DSB_EXPORT int dsb_gemm_tile_m() { return BM; }
+DSB_EXPORT int dsb_gemm_tile_n() { return BN; }
+DSB_EXPORT int dsb_gemm_tile_k() { return BK; }

@@ -428,3 +428,22 @@ DSB_EXPORT int dsb_exchange_fds(const char* prefix, int rank, int world, int my_
     if (send_err) return send_err;
     return recv_err;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// copy-engine all-gather: (world-1) asynchronous peer->local DMA copies on `stream`, zero SM footprint.
+// shards[p] = peer p's shard address (peer-mapped VA); own shard copied only if it is not already in place.
+// ------------------------------------------------------------------------------------------------------
+DSB_EXPORT int dsb_symm_all_gather_ce(void* const* shards, void* full, int64_t shard_bytes, int rank, int world,
+                                      cudaStream_t stream)
+{
+    char* out = static_cast<char*>(full);
+    for (int k = 1; k <= world; ++k) {
+        const int peer = (rank + k) % world;  // start with rank+1: spreads load over the links
+        char* dst = out + static_cast<int64_t>(peer) * shard_bytes;
+        if (dst == shards[peer]) continue;  // in-place (stage <= 2): own shard already there
+        cudaError_t e = cudaMemcpyAsync(dst, shards[peer], static_cast<size_t>(shard_bytes), cudaMemcpyDeviceToDevice,
+                                        stream);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return 0;
+}

@@ -124,6 +124,20 @@ class FlatLinear(nn.Module):
         return flat_linear(x, self.weight, self.bias)
 
 
+class LMHead(FlatLinear):
+    """Output projection.  ``forward(h)`` -> logits; ``forward(h, labels)`` -> mean cross entropy computed
+    chunk-wise without materialising the logits.  Being a module call (not a bare use of ``weight``) keeps
+    the ZeRO-3 fetch hooks in the loop; its backward needs no weights (dW/dh are produced in forward)."""
+    ds_skip_backward_fetch = True
+
+    def forward(self, h, labels=None, chunk=2048, assumed_scale=1.0):
+        if labels is None:
+            return flat_linear(h, self.weight, self.bias)
+        from deepspeed_b200.ops.linear import chunked_linear_xent
+        return chunked_linear_xent(h.reshape(-1, h.shape[-1]), self.weight, labels.reshape(-1), chunk=chunk,
+                                   assumed_scale=assumed_scale)
+
+
 class LlamaAttention(nn.Module):
 
     def __init__(self, cfg: LlamaConfig):
@@ -182,6 +196,7 @@ class LlamaModel(nn.Module):
         super().__init__()
         self.cfg = cfg
         self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size)
+        self.embed_tokens.ds_skip_backward_fetch = True  # embedding backward is an index-add: no weights needed
         self.layers = nn.ModuleList([LlamaDecoderLayer(cfg, i) for i in range(cfg.num_hidden_layers)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self._rope = None
@@ -215,7 +230,7 @@ class LlamaForCausalLM(nn.Module):
         super().__init__()
         self.cfg = cfg
         self.model = LlamaModel(cfg)
-        self.lm_head = FlatLinear(cfg.hidden_size, cfg.vocab_size)
+        self.lm_head = LMHead(cfg.hidden_size, cfg.vocab_size)
         if cfg.tie_word_embeddings:
             self.lm_head.weight = self.model.embed_tokens.weight
         self.ds_loss_multiplier = 1.0  # set by the engine: loss_scale / grad_accum_steps
@@ -236,9 +251,7 @@ class LlamaForCausalLM(nn.Module):
             return self.lm_head(h)
         if shift_labels:
             labels = torch.cat([labels[:, 1:], torch.full_like(labels[:, :1], -100)], dim=1)
-        from deepspeed_b200.ops.linear import chunked_linear_xent
-        return chunked_linear_xent(h.view(-1, h.shape[-1]), self.lm_head.weight, labels.reshape(-1),
-                                   chunk=self.cfg.loss_chunk_tokens, assumed_scale=self.ds_loss_multiplier)
+        return self.lm_head(h, labels=labels, chunk=self.cfg.loss_chunk_tokens, assumed_scale=self.ds_loss_multiplier)
 
     # ---- HF checkpoint interop ---------------------------------------------------------------------
     @staticmethod

@@ -1,0 +1,75 @@
+"""Python face of ``csrc/cuda/gemm_sm100.cu`` -- the hand-written tcgen05 / TMEM / TMA GEMM."""
+import ctypes
+
+import torch
+
+from deepspeed_b200.ops import native as N
+
+_checked = None
+
+
+def supports(a, b, nt=True) -> bool:
+    """bf16, 2-D, K-major operands (``a`` [M,K], ``b`` [N,K] when ``nt``), K % 8 == 0, 16-byte aligned rows."""
+    if not nt:
+        return False  # NN / TN use the library path until the MN-major descriptors land
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2:
+        return False
+    if a.stride(1) != 1 or b.stride(1) != 1 or a.shape[1] != b.shape[1]:
+        return False
+    K = a.shape[1]
+    if K % 8 or a.stride(0) % 8 or b.stride(0) % 8 or a.data_ptr() % 16 or b.data_ptr() % 16:
+        return False
+    return a.shape[0] >= 128 and b.shape[0] >= 256 and K >= 64
+
+
+def matmul_nt(a, b, out=None, sms=0):
+    """``a [M,K] @ b[N,K]^T -> [M,N]`` bf16."""
+    M, K = a.shape
+    Nn = b.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.bfloat16, device=a.device)
+    rc = N.cuda().dsb_gemm_nt_bf16(N.ptr(a), N.ptr(b), N.ptr(out), M, Nn, K, a.stride(0), b.stride(0), out.stride(0), sms,
+                                   N.stream())
+    N.check(rc, "gemm_nt_bf16")
+    return out
+
+
+def matmul_nn(a, b):
+    raise NotImplementedError("MN-major B operand: use the cuBLAS backend")
+
+
+def matmul_nt_allgather(a, b_view, local_full, peers, flags, shard_bytes, chunk_bytes, b_offset_bytes, world, rank, epoch,
+                        comm_ctas=16, out=None, sms=0):
+    """Fused all-gather + GEMM (see kernel header).  ``b_view`` is the [N,K] view of the weight inside
+    ``local_full`` (the unit's gathered buffer, being filled by this very kernel)."""
+    M, K = a.shape
+    Nn = b_view.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.bfloat16, device=a.device)
+    arr = (ctypes.c_void_p * world)(*[ctypes.c_void_p(p) for p in peers])
+    rc = N.cuda().dsb_gemm_nt_bf16_allgather(N.ptr(a), N.ptr(b_view), N.ptr(out), M, Nn, K, a.stride(0), b_view.stride(0),
+                                             out.stride(0), arr, N.ptr(local_full), N.ptr(flags),
+                                             ctypes.c_int64(shard_bytes), ctypes.c_int64(chunk_bytes),
+                                             ctypes.c_int64(b_offset_bytes), world, rank, comm_ctas,
+                                             ctypes.c_uint32(epoch), sms, N.stream())
+    N.check(rc, "gemm_nt_bf16_allgather")
+    return out
+
+
+def self_check() -> bool:
+    """One-time numerical self test against torch.matmul on this device."""
+    global _checked
+    if _checked is not None:
+        return _checked
+    try:
+        torch.manual_seed(0)
+        a = torch.randn(384, 320, device="cuda", dtype=torch.bfloat16)
+        b = torch.randn(768, 320, device="cuda", dtype=torch.bfloat16)
+        c = matmul_nt(a, b)
+        ref = (a.float() @ b.float().t())
+        torch.cuda.synchronize()
+        err = (c.float() - ref).abs().max().item()
+        _checked = bool(err < 0.05 * ref.abs().max().item() + 0.5) and bool(torch.isfinite(c).all())
+    except Exception:
+        _checked = False
+    return _checked

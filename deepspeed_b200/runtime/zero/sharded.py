@@ -67,6 +67,7 @@ class _UnitRT:
         self.temp_refs = 0  # GatheredParameters / external users holding the unit
         self.home = None  # buffer used by this iteration's forward gather (backward MUST reuse it)
         self.consumed = False  # a module hook actually used the gathered copy (vs. a speculative prefetch)
+        self.skip_bwd_fetch = False  # module's backward does not read its weights (embedding, fused LM head)
 
 
 class ZeroShardedOptimizer:
@@ -380,7 +381,13 @@ class ZeroShardedOptimizer:
             p = s.param
             p.ds_shape = s.shape
             p.ds_numel = s.numel
-            p.data = torch.empty(0, dtype=p.dtype, device=self.device)
+            if rt.skip_bwd_fetch:
+                # Units whose backward never reads the weights are not re-gathered, but autograd still
+                # validates incoming gradients against the parameter's *shape*: keep the logical shape
+                # with a stride-0 one-element placeholder (no memory).
+                p.data = torch.empty(1, dtype=p.dtype, device=self.device).expand(s.shape)
+            else:
+                p.data = torch.empty(0, dtype=p.dtype, device=self.device)
             p.ds_status = "NOT_AVAILABLE"
 
     # =========================================================================================
@@ -400,7 +407,9 @@ class ZeroShardedOptimizer:
                 continue
             self._hook_handles.append(m.register_forward_pre_hook(self._make_pre_fwd(rt)))
             self._hook_handles.append(m.register_forward_hook(self._make_post_fwd(rt)))
-            self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
+            rt.skip_bwd_fetch = bool(getattr(m, "ds_skip_backward_fetch", False))
+            if not rt.skip_bwd_fetch:
+                self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
 
     def _make_pre_fwd(self, rt):
 
@@ -414,7 +423,7 @@ class ZeroShardedOptimizer:
         def hook(module, args, output):
             if self._in_backward:
                 return  # recompute inside backward: released by the gradient path
-            if torch.is_grad_enabled() and rt.u.index == self._last_forward_unit():
+            if torch.is_grad_enabled() and rt.u.index == self._last_forward_unit() and not rt.skip_bwd_fetch:
                 return  # its backward is next: keep it
             self.release_unit(rt)
 
@@ -523,7 +532,7 @@ class ZeroShardedOptimizer:
         rt.consumed = True
         if prefetch and self.prefetch_depth > 0:
             for nxt in self._upcoming(rt, forward):
-                if nxt.state == NOT_GATHERED and not nxt.u.persistent:
+                if nxt.state == NOT_GATHERED and not nxt.u.persistent and (forward or not nxt.skip_bwd_fetch):
                     self._launch_gather(nxt)
 
     def _upcoming(self, rt, forward):

@@ -1,0 +1,40 @@
+"""tcgen05 GEMM vs cuBLAS on the Llama-3-8B forward shapes (CUDA events, L2 flushed between iterations)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from deepspeed_b200.ops.kernels import gemm_sm100
+
+shapes = [(8192, 6144, 4096, "qkv"), (8192, 4096, 4096, "o"), (8192, 28672, 4096, "gate_up"), (8192, 4096, 14336, "down"),
+          (2048, 128256, 4096, "lm_head_chunk")]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+rows = []
+for M, N, K, name in shapes:
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+    def t(fn, iters=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    ok = gemm_sm100.self_check()
+    t_lib = t(lambda: torch.matmul(a, b.t(), out=out))
+    t_own = t(lambda: gemm_sm100.matmul_nt(a, b, out=out)) if ok else float("nan")
+    fl = 2.0 * M * N * K
+    rows.append({"shape": name, "M": M, "N": N, "K": K, "cublas_ms": t_lib, "sm100_ms": t_own,
+                 "cublas_tflops": fl / t_lib / 1e9, "sm100_tflops": fl / t_own / 1e9 if ok else None})
+    print(rows[-1], flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(rows, open("gpurun_out/gemm_bench.json", "w"), indent=1)

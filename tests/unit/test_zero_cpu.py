@@ -198,3 +198,39 @@ def _unused_parameter_and_frozen():
 
 def test_unused_and_frozen_parameters():
     run_distributed(_unused_parameter_and_frozen, 2)
+
+
+def _llama_transient_units(stage, ckpt):
+    """Tiny Llama with every unit transient (threshold 0): exercises the LM-head / embedding fetch paths,
+    the direct flat-gradient writes and recompute-in-backward under ZeRO-3."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.models.llama import LlamaForCausalLM, llama_config
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    torch.manual_seed(0)
+    cfg = llama_config("tiny", checkpoint_layers=ckpt)
+    m = LlamaForCausalLM(cfg)
+    ref = LlamaForCausalLM(cfg)
+    ref.load_state_dict(m.state_dict())
+    conf = {"train_micro_batch_size_per_gpu": 2, "optimizer": {"type": "AdamW", "params": {"lr": 1e-3, "weight_decay": 0.1}},
+            "zero_optimization": {"stage": stage, "stage3_param_persistence_threshold": 0}}
+    eng, _, _, _ = ds.initialize(model=m, config=conf)
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3, weight_decay=0.1)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        ids = torch.randint(0, cfg.vocab_size, (2 * w, 32), generator=g)
+        loss = eng(ids[r * 2:(r + 1) * 2], labels=ids[r * 2:(r + 1) * 2])
+        eng.backward(loss)
+        eng.step()
+        rl = sum(ref(ids[k * 2:(k + 1) * 2], labels=ids[k * 2:(k + 1) * 2]) for k in range(w)) / w
+        rl.backward()
+        ropt.step()
+        ropt.zero_grad()
+    worst = max((safe_get_full_fp32_param(p).cpu() - q).abs().max().item()
+                for p, q in zip(m.parameters(), ref.parameters()))
+    assert worst < 5e-5, worst
+
+
+@pytest.mark.parametrize("ckpt", [0, 2])
+def test_llama_zero3_all_units_transient(ckpt):
+    run_distributed(_llama_transient_units, 2, (3, ckpt))
