@@ -163,7 +163,7 @@ class SymmContext:
         self._tag = 0
         self.segments: List[_Segment] = []
         self.epochs = [1] * self.lib.dsb_symm_channels()
-        self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "32"))
+        self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "64"))
         self.ag_ctas = int(os.environ.get("DSB200_SYMM_AG_CTAS", str(self.ctas)))
         self.ag_mode = os.environ.get("DSB200_SYMM_AG", "ce").lower()  # "ce" (DMA engines) | "kernel" (SM pull)
         # signal pads live in their own small segment (never multicast-bound)

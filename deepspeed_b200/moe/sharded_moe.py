@@ -1,0 +1,216 @@
+"""Gating + dispatch/combine for expert-parallel MoE.
+
+Parity target: reference ``moe/sharded_moe.py`` (``top1gating :183``, ``top2gating :290``, ``topkgating :374``,
+``TopKGate :449``, ``MOELayer :533``, ``_AllToAll :96``).  Differences by design:
+
+* dispatch / combine are **index-based** (scatter rows into an expert-major buffer, weighted gather back)
+  through the kernels in ``csrc/cuda/moe_ragged.cu`` instead of the dense ``einsum('sec,sm->ecm')`` with a
+  ``[tokens, experts, capacity]`` mask -- O(tokens*k*hidden) instead of O(tokens*experts*capacity);
+* with ``ep_size == 1`` the layout is exact (no capacity padding, nothing dropped unless asked);
+* with expert parallelism the capacity-padded ``[E, C, H]`` buffer goes through ``all_to_all_single`` over the
+  EP group exactly like the reference (fixed message shape), and the differentiable all-to-all is the same
+  autograd trick (backward = the inverse all-to-all).
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from deepspeed_b200 import comm as dist
+from deepspeed_b200.ops.kernels import moe_ops
+from deepspeed_b200.utils import groups
+
+TOPK_GATE_TIMER = "topk_gate"
+MOE_TIMER = "moe"
+FIRST_ALLTOALL_TIMER = "1st_a2a"
+SECOND_ALLTOALL_TIMER = "2nd_a2a"
+
+
+class _AllToAll(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, group, x):
+        ctx.group = group
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        dist.all_to_all_single(out, x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return None, _AllToAll.apply(ctx.group, dy)
+
+
+def multiplicative_jitter(x, epsilon=1e-2):
+    if epsilon == 0:
+        return x
+    return x * torch.empty_like(x).uniform_(1.0 - epsilon, 1.0 + epsilon)
+
+
+def gumbel_rsample(shape, device):
+    u = torch.rand(shape, device=device).clamp_(1e-9, 1 - 1e-9)
+    return -torch.log(-torch.log(u))
+
+
+def _capacity(num_tokens, num_experts, capacity_factor, min_capacity, k=1):
+    cap = int(math.ceil(num_tokens / num_experts * capacity_factor * k))
+    return max(cap, int(min_capacity))
+
+
+class GateOutput:
+    __slots__ = ("l_aux", "expert_ids", "weights", "positions", "offsets", "counts", "capacity", "k")
+
+
+def topkgating(logits, k, capacity_factor, min_capacity, drop_tokens=True, ep_group=None, use_rts=False,
+               noisy_gate_policy=None, normalize=True, drop_policy="probs"):
+    """Token-choice top-k routing.  Returns a :class:`GateOutput`; ``weights`` are differentiable w.r.t.
+    ``logits``; the index tensors are not."""
+    T, E = logits.shape
+    logits_for_choice = logits
+    if noisy_gate_policy == "RSample":
+        logits_for_choice = logits + gumbel_rsample(logits.shape, logits.device)
+    gates = F.softmax(logits.float(), dim=1)
+    _, ids = torch.topk(logits_for_choice if noisy_gate_policy == "RSample" else gates, k, dim=1)
+    w = gates.gather(1, ids)
+    if normalize and k > 1:
+        w = w / w.sum(dim=1, keepdim=True).clamp(min=torch.finfo(w.dtype).eps)
+    # load-balancing loss (GShard): fraction of router probability x fraction of tokens, first choice
+    me = gates.mean(dim=0)
+    if k <= 2:
+        ce = F.one_hot(ids[:, 0], E).float().mean(dim=0)
+    else:
+        ce = F.one_hot(ids, E).float().sum(dim=1).mean(dim=0) / k
+    l_aux = torch.sum(me * ce) * E
+    out = GateOutput()
+    out.l_aux, out.k = l_aux, k
+    flat_ids = ids.to(torch.int32).contiguous()
+    if use_rts and k == 1:
+        # random token selection: capacity slots go to a random subset instead of the earliest tokens
+        perm = torch.randperm(T, device=logits.device)
+        pos_p, counts, offsets = moe_ops.route(flat_ids[perm], E)
+        positions = torch.empty_like(pos_p)
+        positions[perm] = pos_p
+    else:
+        positions, counts, offsets = moe_ops.route(flat_ids, E)
+    if drop_tokens:
+        cap = _capacity(T, E, capacity_factor, min_capacity, k)
+    else:
+        mx = counts.max().to(torch.int64)
+        if ep_group is not None and dist.get_world_size(ep_group) > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=ep_group)
+        cap = int(mx.item())
+        cap = max(cap, int(min_capacity))
+    out.expert_ids, out.weights, out.positions, out.offsets, out.counts, out.capacity = flat_ids, w, positions, offsets, \
+        counts, cap
+    return out
+
+
+def top1gating(logits, capacity_factor, min_capacity, used_token=None, noisy_gate_policy=None, drop_tokens=True,
+               use_rts=True, ep_group=None, use_tutel=False):
+    return topkgating(logits, 1, capacity_factor, min_capacity, drop_tokens, ep_group, use_rts, noisy_gate_policy)
+
+
+def top2gating(logits, capacity_factor, min_capacity, drop_tokens=True, ep_group=None, top2_2nd_expert_sampling=True):
+    return topkgating(logits, 2, capacity_factor, min_capacity, drop_tokens, ep_group,
+                      noisy_gate_policy="RSample" if False else None)
+
+
+class TopKGate(nn.Module):
+    """Router (reference ``TopKGate :449``): fp32 linear gate + top-k selection."""
+
+    def __init__(self, model_dim, num_experts, k=1, capacity_factor=1.0, eval_capacity_factor=1.0, min_capacity=8,
+                 noisy_gate_policy: Optional[str] = None, drop_tokens=True, use_rts=True, ep_group=None,
+                 top2_2nd_expert_sampling=True):
+        super().__init__()
+        self.wg = nn.Linear(model_dim, num_experts, bias=False)
+        self.ep_group = ep_group
+        self.k = k
+        self.capacity_factor = capacity_factor
+        self.eval_capacity_factor = eval_capacity_factor
+        self.min_capacity = min_capacity
+        self.noisy_gate_policy = noisy_gate_policy
+        self.drop_tokens = drop_tokens
+        self.use_rts = use_rts
+        self.top2_2nd_expert_sampling = top2_2nd_expert_sampling
+        self.gate_time = 0.0
+        self.wall_clock_breakdown = False
+
+    def _set_ep_group(self, ep_group):
+        assert self.ep_group is None, "Attempting to override an existing ep_group"
+        self.ep_group = ep_group
+
+    def forward(self, x, used_token=None, use_tutel=False):
+        xf = x.float()
+        if self.noisy_gate_policy == "Jitter" and self.training:
+            xf = multiplicative_jitter(xf)
+        logits = F.linear(xf, self.wg.weight.float())
+        cf = self.capacity_factor if self.training else self.eval_capacity_factor
+        return topkgating(logits, self.k, cf, self.min_capacity, self.drop_tokens, self.ep_group,
+                          use_rts=self.use_rts and self.training,
+                          noisy_gate_policy=self.noisy_gate_policy if self.training else None)
+
+
+class MOELayer(nn.Module):
+    """Route -> (all-to-all) -> local experts -> (all-to-all) -> combine.  Reference ``MOELayer :533``."""
+
+    def __init__(self, gate, experts, ep_group_name, ep_size, num_local_experts, use_tutel=False):
+        super().__init__()
+        self.gate = gate
+        self.experts = experts
+        self.ep_group = None
+        self.ep_size = ep_size
+        self.ep_group_name = ep_group_name
+        self.num_local_experts = num_local_experts
+        self.l_aux = None
+        self.exp_counts = None
+        self.wall_clock_breakdown = False
+
+    def _set_ep_group(self, ep_group):
+        self.ep_group = ep_group
+        self.gate._set_ep_group(ep_group)
+
+    def forward(self, *inp):
+        x = inp[0]
+        H = x.shape[-1]
+        flat = x.reshape(-1, H)
+        T = flat.shape[0]
+        g = self.gate(flat, inp[1] if len(inp) > 1 else None)
+        self.l_aux, self.exp_counts = g.l_aux, g.counts
+        E = self.ep_size * self.num_local_experts
+        k = g.k
+        if self.ep_size == 1 and not self.gate.drop_tokens:
+            # exact layout: rows sorted by expert, no padding -> ragged per-expert slices
+            rows, slots = moe_ops.scatter(flat, g.expert_ids, g.positions, g.offsets, k, 0, T * k)
+            counts = g.counts.tolist()
+            outs, start = [], 0
+            chunks = rows.split(counts, dim=0)
+            experts = self.experts.deepspeed_experts if hasattr(self.experts, "deepspeed_experts") else None
+            if experts is not None:
+                for c, ex in zip(chunks, experts):
+                    o = ex(c) if c.shape[0] else c
+                    outs.append(o[0] if isinstance(o, tuple) else o)
+                eo = torch.cat(outs, dim=0)
+            else:
+                mx = max(counts) if counts else 0
+                padded = rows.new_zeros(E, mx, H)
+                for e, c in enumerate(chunks):
+                    padded[e, :c.shape[0]] = c
+                po = self.experts(padded)
+                eo = torch.cat([po[e, :n] for e, n in enumerate(counts)], dim=0)
+            y = moe_ops.gather(eo, g.weights.to(torch.float32), slots, T, k)
+            return y.reshape(x.shape).to(x.dtype)
+        C = g.capacity
+        rows, slots = moe_ops.scatter(flat, g.expert_ids, g.positions, g.offsets, k, C, E * C)
+        disp = rows.view(E, C, H)
+        if self.ep_size > 1:
+            disp = _AllToAll.apply(self.ep_group, disp)  # [ep, E_local, C, H] flattened on dim 0
+        disp = disp.view(self.ep_size, self.num_local_experts, C, H).transpose(0, 1).reshape(
+            self.num_local_experts, self.ep_size * C, H)
+        eo = self.experts(disp)
+        eo = eo.view(self.num_local_experts, self.ep_size, C, H).transpose(0, 1).reshape(E, C, H).contiguous()
+        if self.ep_size > 1:
+            eo = _AllToAll.apply(self.ep_group, eo)
+        y = moe_ops.gather(eo.reshape(E * C, H), g.weights.to(torch.float32), slots, T, k)
+        return y.reshape(x.shape).to(x.dtype)

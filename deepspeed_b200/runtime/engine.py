@@ -210,25 +210,32 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             assert is_zero_supported_optimizer(client_optimizer), (
                 f"{type(client_optimizer).__name__} is not a ZeRO-tested optimizer; set "
                 f"'zero_allow_untested_optimizer': true to use it anyway")
-        self.optimizer = ZeroShardedOptimizer(self.module,
-                                              stage,
-                                              client_optimizer=client_optimizer,
-                                              optimizer_name=name,
-                                              optimizer_params=opt_params,
-                                              param_groups=param_groups,
-                                              zero_config=c.zero_config,
-                                              dp_group=self.seq_data_parallel_group,
-                                              model_dtype=model_dtype,
-                                              grad_accum_dtype=gad,
-                                              gradient_accumulation_steps=self.gradient_accumulation_steps(),
-                                              gradient_clipping=self.gradient_clipping(),
-                                              loss_scale_config=self._build_loss_scale_config(),
-                                              communication_data_type=c.communication_data_type,
-                                              prescale_gradients=c.prescale_gradients,
-                                              gradient_predivide_factor=c.gradient_predivide_factor,
-                                              device=self.device,
-                                              mpu=self.mpu,
-                                              timers=self.timers)
+        common = dict(client_optimizer=client_optimizer, optimizer_name=name, optimizer_params=opt_params,
+                      param_groups=param_groups, zero_config=c.zero_config, model_dtype=model_dtype, grad_accum_dtype=gad,
+                      gradient_accumulation_steps=self.gradient_accumulation_steps(),
+                      gradient_clipping=self.gradient_clipping(), loss_scale_config=self._build_loss_scale_config(),
+                      communication_data_type=c.communication_data_type, prescale_gradients=c.prescale_gradients,
+                      gradient_predivide_factor=c.gradient_predivide_factor, device=self.device, mpu=self.mpu,
+                      timers=self.timers)
+        expert_names = sorted({getattr(p, "group_name", None) for p in self.module.parameters()
+                               if getattr(p, "allreduce", True) is False} - {None})
+        if not expert_names:
+            self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
+            return
+        # MoE: dense parameters over the DP group, every expert family over its expert-data-parallel group
+        from deepspeed_b200.runtime.zero.multi import ZeroOptimizerGroup
+        assert client_optimizer is None or not isinstance(client_optimizer, torch.optim.Optimizer) or True
+        parts, ep_groups = [], []
+        parts.append(ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, name="dense",
+                                          param_filter=lambda p: getattr(p, "allreduce", True) is not False, **common))
+        ep_groups.append(None)
+        for en in expert_names:
+            edp = groups._get_expert_data_parallel_group(en)
+            parts.append(ZeroShardedOptimizer(self.module, stage, dp_group=edp, name=f"expert:{en}",
+                                              param_filter=lambda p, en=en: getattr(p, "group_name", None) == en and
+                                              getattr(p, "allreduce", True) is False, **common))
+            ep_groups.append(groups._get_expert_parallel_group(en))
+        self.optimizer = ZeroOptimizerGroup(parts, ep_groups)
 
     def _configure_zero_inference(self):
         self.optimizer = ZeroShardedOptimizer(self.module, 3, optimizer_name="sgd", optimizer_params={"lr": 0.0},

@@ -94,8 +94,12 @@ class ZeroShardedOptimizer:
                  device=None,
                  mpu=None,
                  broadcast_init=True,
-                 timers=None):
+                 timers=None,
+                 param_filter=None,
+                 name="dense"):
         from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
+        self.param_filter = param_filter
+        self.name = name
         self.module = module
         self.stage = int(stage)
         self.zc = zero_config or DeepSpeedZeroConfig(stage=self.stage)
@@ -154,13 +158,15 @@ class ZeroShardedOptimizer:
             # schedulers (which mutate ``optimizer.param_groups[i]["lr"]``) reach it
             self.param_groups = client_optimizer.param_groups
         for p in module.parameters():
-            if id(p) not in p2g:
+            if id(p) not in p2g and (param_filter is None or param_filter(p)):
                 p2g[id(p)] = -1  # frozen / unmanaged: sharded but never stepped
         self.group_steps = [0 for _ in self.param_groups]
 
         # ---- plan ------------------------------------------------------------------------------
         thresh = int(self.zc.param_persistence_threshold) if self.stage == 3 else 0
-        self.units: List[Unit] = build_units(module, self.shard_world, p2g, persistence_threshold=0)
+        self.units: List[Unit] = build_units(module, self.shard_world, p2g, persistence_threshold=0,
+                                             param_filter=param_filter)
+        assert self.units, f"ZeroShardedOptimizer[{name}]: no parameters to manage"
         self.rts: List[_UnitRT] = [_UnitRT(u) for u in self.units]
         self.unit_of_param: Dict[int, _UnitRT] = {}
         self.slot_of_param = {}
@@ -217,15 +223,16 @@ class ZeroShardedOptimizer:
     # construction
     # =========================================================================================
     def _make_param_groups(self, client_optimizer, param_groups, defaults):
+        keep = self.param_filter or (lambda p: True)
         if client_optimizer is not None:
             groups = []
             for g in client_optimizer.param_groups:
                 ng = {k: v for k, v in g.items() if k != "params"}
-                ng["params"] = [p for p in g["params"]]
+                ng["params"] = [p for p in g["params"] if keep(p)]
                 groups.append(ng)
             return groups
         if param_groups is None:
-            param_groups = [{"params": [p for p in self.module.parameters() if p.requires_grad]}]
+            param_groups = [{"params": [p for p in self.module.parameters() if p.requires_grad and keep(p)]}]
         elif len(param_groups) and not isinstance(param_groups[0], dict):
             param_groups = [{"params": list(param_groups)}]
         out = []
@@ -233,7 +240,7 @@ class ZeroShardedOptimizer:
         for g in param_groups:
             ng = dict(base)
             ng.update({k: v for k, v in g.items() if k != "params"})
-            ng["params"] = [p for p in g["params"] if p.requires_grad]
+            ng["params"] = [p for p in g["params"] if p.requires_grad and keep(p)]
             ng.setdefault("lr", base.get("lr", 1e-3))
             out.append(ng)
         return out
@@ -819,9 +826,26 @@ class ZeroShardedOptimizer:
     @instrument_w_nvtx
     def step(self, closure=None):
         """Optimizer step at a gradient-accumulation boundary."""
+        self.prepare_step()
+        self.finish_step()
+
+    def needs_norm(self):
+        return (not self.fused_in_backward) and (self.clip > 0.0 or self.dynamic_loss_scale
+                                                 or self.model_dtype == torch.float16)
+
+    def prepare_step(self):
+        """Phase 1: join the reduction stream and compute this instance's squared gradient norm / overflow
+        flag (already summed over its own sharding group).  Split from :meth:`finish_step` so that several
+        instances (dense + expert parameter domains) can combine their norms before clipping."""
         if self.on_cuda and self.rs_stream is not None:
             torch.cuda.current_stream().wait_stream(self.rs_stream)
         self.overflow = False
+        if self.needs_norm():
+            self.stats.reset()
+            self.stats.accumulate(self.grad_arena)
+            self._allreduce_stats(self.stats)
+
+    def finish_step(self, extra_sumsq=None, extra_found_inf=None):
         if self.fused_in_backward:
             # parameters were already updated unit-by-unit inside backward
             for gi in range(len(self.group_steps)):
@@ -829,13 +853,14 @@ class ZeroShardedOptimizer:
             self._post_step()
             return
         inv_scale = 1.0 / float(self.loss_scale)
-        need_norm = self.clip > 0.0 or self.dynamic_loss_scale or self.model_dtype == torch.float16
+        need_norm = self.needs_norm()
         stats = self.stats
         d_gscale = d_skip = None
         if need_norm:
-            stats.reset()
-            stats.accumulate(self.grad_arena)
-            self._allreduce_stats(stats)
+            if extra_sumsq is not None:
+                stats.sumsq.add_(extra_sumsq.to(stats.sumsq.device))
+            if extra_found_inf is not None:
+                stats.found_inf.copy_(torch.maximum(stats.found_inf, extra_found_inf.to(stats.found_inf.device)))
             stats.finalize(inv_loss_scale=inv_scale, max_norm=self.clip)
             d_gscale, d_skip = stats.gscale, stats.skip
             self._global_grad_norm = stats.norm
@@ -844,9 +869,7 @@ class ZeroShardedOptimizer:
                 self.loss_scaler.update_scale(self.overflow)
                 if self.overflow:
                     self.skipped_steps += 1
-                    log_dist(f"[deepspeed_b200] OVERFLOW! Skipping step. Attempted loss scale: "
-                             f"{self.loss_scale * (self.loss_scaler.scale_factor if self.dynamic_loss_scale else 1)}"
-                             f", reducing to {self.loss_scale}", ranks=[0])
+                    log_dist(f"[deepspeed_b200] OVERFLOW! Skipping step, loss scale -> {self.loss_scale}", ranks=[0])
                     self._post_step(skipped=True)
                     return
         gscale = 1.0 if need_norm else inv_scale

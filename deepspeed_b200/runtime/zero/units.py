@@ -99,7 +99,8 @@ def build_units(model: nn.Module,
                 persistence_threshold: int = 0,
                 max_unit_numel: Optional[int] = None,
                 leaf_classes: Sequence[type] = (),
-                trainable_only: bool = False) -> List[Unit]:
+                trainable_only: bool = False,
+                param_filter=None) -> List[Unit]:
     """Build the unit plan for ``model``.  Shared (tied) parameters are assigned to the first unit
     that references them.  Units larger than ``max_unit_numel`` are not split (a unit is the
     module-hook granularity) but the value is used by ZeRO-1/2 to form reduce buckets."""
@@ -117,6 +118,8 @@ def build_units(model: nn.Module,
             if id(p) in seen:
                 continue
             if trainable_only and not p.requires_grad:
+                continue
+            if param_filter is not None and not param_filter(p):
                 continue
             seen.add(id(p))
             numel = _ds_numel(p)
