@@ -1,0 +1,318 @@
+"""Runtime helpers: gradient-norm / clipping, partitioning, memory reporting.
+
+Parity target: reference ``runtime/utils.py`` (``clip_grad_norm_ :315``, ``get_global_norm_of_tensors :826``,
+``partition_uniform``, ``partition_balanced :583``, ``see_memory_usage :771``, ``CheckOverflow :181``,
+``PartitionedTensor :624``, ``all_gather_dp_groups :965``, ``align_dense_tensors``).
+"""
+import gc
+import math
+from bisect import bisect_left
+from typing import List
+
+import psutil
+import torch
+
+from deepspeed_b200 import comm as dist
+from deepspeed_b200.utils.logging import logger
+
+
+def noop_decorator(func):
+    return func
+
+
+def ensure_directory_exists(filename):
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
+
+
+def set_random_seed(seed):
+    import random
+    import numpy
+    random.seed(seed)
+    numpy.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def is_model_parallel_parameter(p) -> bool:
+    return (hasattr(p, "model_parallel") and p.model_parallel) or (hasattr(p, "tensor_model_parallel")
+                                                                   and p.tensor_model_parallel)
+
+
+def get_grad_norm(parameters, norm_type=2, mpu=None):
+    """Global norm of ``p.grad`` over ``parameters`` (model-parallel aware: replicated params counted once)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    parameters = [p for p in parameters if p.grad is not None]
+    if not parameters:
+        return 0.0
+    dev = parameters[0].grad.device
+    if norm_type == math.inf:
+        total = torch.stack([p.grad.detach().abs().max().float() for p in parameters]).max()
+        if mpu is not None:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX, group=mpu.get_model_parallel_group())
+        return float(total)
+    total = torch.zeros((), dtype=torch.float32, device=dev)
+    tp_rank = mpu.get_model_parallel_rank() if mpu is not None else 0
+    for p in parameters:
+        if mpu is not None and tp_rank > 0 and not is_model_parallel_parameter(p):
+            continue
+        total += p.grad.detach().float().norm(norm_type)**norm_type
+    if mpu is not None:
+        dist.all_reduce(total, group=mpu.get_model_parallel_group())
+    total = float(total)**(1.0 / norm_type)
+    if total in (float("inf"), -float("inf")) or total != total:
+        total = -1
+    return total
+
+
+def get_global_norm(norm_list):
+    return math.sqrt(sum(n**2 for n in norm_list))
+
+
+def get_global_norm_of_tensors(input_tensors, norm_type=2, mpu=None, use_graph=False, moe_ep_group=None):
+    tensors = [t for t in input_tensors if t is not None]
+    if not tensors:
+        return torch.zeros((), dtype=torch.float32)
+    dev = tensors[0].device
+    if norm_type == math.inf:
+        total = torch.stack([t.detach().abs().max().float() for t in tensors]).max()
+        op = dist.ReduceOp.MAX
+    else:
+        total = sum((t.detach().float().norm(norm_type)**norm_type for t in tensors), torch.zeros((), device=dev))
+        op = dist.ReduceOp.SUM
+    for grp in ([mpu.get_model_parallel_group()] if mpu is not None else []) + ([moe_ep_group] if moe_ep_group else []):
+        dist.all_reduce(total, op=op, group=grp)
+    if norm_type != math.inf:
+        total = total**(1.0 / norm_type)
+    return total
+
+
+def clip_grad_norm_(parameters, max_norm, norm_type=2, mpu=None):
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    parameters = [p for p in parameters if p.grad is not None]
+    total = get_grad_norm(parameters, norm_type, mpu)
+    if total < 0:
+        return total
+    coef = max_norm / (total + 1e-6)
+    if coef < 1:
+        for p in parameters:
+            p.grad.detach().mul_(coef)
+    return total
+
+
+def clip_tensors_by_global_norm(input_tensors, max_norm=1.0, global_norm=None, mpu=None, eps=1e-6, use_graph=False):
+    if global_norm is None:
+        global_norm = get_global_norm_of_tensors(input_tensors, mpu=mpu)
+    coef = max_norm / (float(global_norm) + eps)
+    if coef < 1:
+        for t in input_tensors:
+            t.detach().mul_(coef)
+    return global_norm
+
+
+class CheckOverflow:
+    """inf/nan scan over parameter gradients with cross-rank agreement."""
+
+    def __init__(self, param_groups=None, mpu=None, zero_reduce_scatter=False, deepspeed=None):
+        self.mpu = mpu
+        self.params = [p for g in (param_groups or []) for p in g]
+        self.zero_reduce_scatter = zero_reduce_scatter
+        self.deepspeed = deepspeed
+
+    @staticmethod
+    def _has_inf_or_nan(x):
+        s = float(x.float().sum())
+        return s in (float("inf"), -float("inf")) or s != s
+
+    def has_overflow_serial(self, params):
+        return any(p.grad is not None and self._has_inf_or_nan(p.grad.data) for p in params)
+
+    def has_overflow(self, params, has_moe_params=None):
+        local = self.has_overflow_serial(params)
+        dev = "cuda" if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([float(local)], device=dev)
+        if dist.is_initialized():
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item())
+
+    def check(self, param_groups=None):
+        params = [p for g in (param_groups or []) for p in g] if param_groups is not None else self.params
+        return self.has_overflow(params)
+
+
+# ---- partitioning ------------------------------------------------------------------------------------------------
+def prefix_sum_inc(weights):
+    out = list(weights)
+    for i in range(1, len(out)):
+        out[i] += out[i - 1]
+    return out
+
+
+def partition_uniform(num_items, num_parts):
+    """``num_parts + 1`` boundaries splitting ``num_items`` as evenly as possible (earlier parts get the extra)."""
+    parts = [0] * (num_parts + 1)
+    if num_items <= num_parts:
+        for p in range(num_parts + 1):
+            parts[p] = min(p, num_items)
+        return parts
+    chunk, rem = divmod(num_items, num_parts)
+    for p in range(num_parts):
+        parts[p + 1] = parts[p] + chunk + (1 if p < rem else 0)
+    return parts
+
+
+def _feasible(prefix, num_parts, limit):
+    """Greedy: can the items be covered by ``num_parts`` contiguous parts each weighing <= limit?"""
+    parts = [0]
+    start_w = 0
+    n = len(prefix)
+    idx = 0
+    for _ in range(num_parts):
+        # furthest end whose weight <= limit
+        end = bisect_left(prefix, start_w + limit + 1e-9, lo=idx)
+        if end < n and prefix[end] <= start_w + limit + 1e-9:
+            end += 1
+        if end == idx:
+            return None
+        parts.append(end)
+        if end >= n:
+            break
+        start_w = prefix[end - 1]
+        idx = end
+    if parts[-1] < n:
+        return None
+    while len(parts) < num_parts + 1:
+        parts.append(n)
+    return parts
+
+
+def partition_balanced(weights, num_parts):
+    """Contiguous partition minimising the heaviest part (binary search over the bottleneck weight)."""
+    n = len(weights)
+    if n <= num_parts:
+        return partition_uniform(n, num_parts)
+    prefix = prefix_sum_inc([float(w) for w in weights])
+    lo, hi = max(weights), prefix[-1]
+    best = _feasible(prefix, num_parts, hi)
+    for _ in range(64):
+        if hi - lo < 1e-6 * max(1.0, hi):
+            break
+        mid = (lo + hi) / 2
+        got = _feasible(prefix, num_parts, mid)
+        if got is not None:
+            best, hi = got, mid
+        else:
+            lo = mid
+    return best
+
+
+class PartitionedTensor:
+    """A tensor split evenly across a process group with meta to reassemble (reference :624)."""
+
+    def __init__(self, tensor, group, partition_meta=None):
+        self.group = group
+        self.num_parts = dist.get_world_size(group=group)
+        self.rank = dist.get_rank(group=group)
+        self.orig_size = list(tensor.size())
+        self.orig_device = tensor.device
+        self.local_data, self.partition = self._partition_tensor(tensor)
+
+    @classmethod
+    def from_meta(cls, meta, local_part, group, device=None):
+        meta = meta.tolist()
+        obj = cls.__new__(cls)
+        obj.group = group
+        obj.num_parts = dist.get_world_size(group=group)
+        obj.rank = dist.get_rank(group=group)
+        ndim = meta[0]
+        obj.orig_size = meta[1:1 + ndim]
+        obj.partition = meta[2 + ndim:]
+        obj.orig_device = device or local_part.device
+        obj.local_data = local_part
+        return obj
+
+    def _partition_tensor(self, tensor):
+        partition = partition_uniform(tensor.numel(), self.num_parts)
+        s, e = partition[self.rank], partition[self.rank + 1]
+        return tensor.detach().contiguous().view(-1)[s:e].clone(), partition
+
+    def full(self, device=None):
+        device = device or self.orig_device
+        numel = self.partition[-1]
+        flat = torch.zeros(numel, dtype=self.local_data.dtype, device=device)
+        maxp = max(self.partition[i + 1] - self.partition[i] for i in range(self.num_parts))
+        buf = torch.zeros(maxp, dtype=self.local_data.dtype, device=device)
+        buf[:self.local_data.numel()] = self.local_data
+        gathered = [torch.zeros_like(buf) for _ in range(self.num_parts)]
+        dist.all_gather(gathered, buf, group=self.group)
+        for r in range(self.num_parts):
+            s, e = self.partition[r], self.partition[r + 1]
+            flat[s:e] = gathered[r][:e - s]
+        return flat.view(self.orig_size)
+
+    def to_meta(self):
+        meta = [len(self.orig_size)] + list(self.orig_size) + [self.num_parts] + list(self.partition)
+        return torch.tensor(meta, dtype=torch.long, device=self.local_data.device)
+
+    def data(self):
+        return self.local_data
+
+    def local_size(self):
+        return self.local_data.size()
+
+
+def align_dense_tensors(tensor_list, alignment):
+    num = sum(t.numel() for t in tensor_list)
+    rem = num % alignment
+    if rem:
+        pad = torch.zeros(alignment - rem, device=tensor_list[0].device, dtype=tensor_list[0].dtype)
+        return list(tensor_list) + [pad]
+    return list(tensor_list)
+
+
+def all_gather_dp_groups(groups_flat, partitioned_param_groups, dp_process_group, start_alignment_factor=None,
+                         allgather_bucket_size=None):
+    for group_id, parts in enumerate(partitioned_param_groups):
+        pid = dist.get_rank(group=dp_process_group[group_id])
+        dist.all_gather_into_tensor(groups_flat[group_id], parts[pid], group=dp_process_group[group_id])
+
+
+memory_status_last = [0.0]
+
+
+def see_memory_usage(message, force=False):
+    if not force:
+        return
+    if dist.is_initialized() and dist.get_rank() != 0:
+        return
+    gc.collect()
+    gb = 1024**3
+    if torch.cuda.is_available():
+        logger.info(f"{message} | MA {torch.cuda.memory_allocated() / gb:.2f} GB  Max_MA "
+                    f"{torch.cuda.max_memory_allocated() / gb:.2f} GB  CA {torch.cuda.memory_reserved() / gb:.2f} GB")
+        torch.cuda.reset_peak_memory_stats()
+    vm = psutil.virtual_memory()
+    logger.info(f"CPU Virtual Memory:  used = {(vm.total - vm.available) / gb:.2f} GB, percent = {vm.percent}%")
+
+
+def call_to_str(base, *args, **kwargs):
+    parts = [repr(a) for a in args] + [f"{k}={v!r}" for k, v in kwargs.items()]
+    return f"{base}({', '.join(parts)})"
+
+
+def get_only_unique_item(items):
+    s = set(items)
+    if len(s) != 1:
+        raise RuntimeError(f"expected there to be only one unique element in {items}")
+    return next(iter(s))
+
+
+def required_torch_version(min_version=None, max_version=None):
+    from packaging import version as pv
+    v = pv.parse(torch.__version__.split("+")[0])
+    if min_version is not None and v < pv.parse(str(min_version)):
+        return False
+    if max_version is not None and v > pv.parse(str(max_version)):
+        return False
+    return True

@@ -1,0 +1,145 @@
+"""Pipeline parallelism on the host tier: schedule / topology unit tests + 2-stage and (pp=2, dp=2) training
+parity against a single-process run (strategy: reference tests/unit/runtime/pipe/*)."""
+import copy
+
+import pytest
+import torch
+from torch import nn
+
+from tests.common import run_distributed
+
+
+def test_topology_rank_math():
+    from deepspeed_b200.runtime.pipe.topology import PipeDataParallelTopology, PipeModelDataParallelTopology, ProcessTopology
+    t = ProcessTopology(axes=["a", "b"], dims=[2, 3])
+    assert t.world_size() == 6 and t.get_rank(a=1, b=2) == 5 and t.get_coord(4).a == 1 and t.get_coord(4).b == 1
+    assert t.get_axis_comm_lists("a") == [[0, 3], [1, 4], [2, 5]]
+    assert t.get_axis_comm_lists("b") == [[0, 1, 2], [3, 4, 5]]
+    assert t.filter_match(a=0) == [0, 1, 2] and t.get_axis_list("b", 1) == [1, 4]
+    t3 = PipeModelDataParallelTopology(num_pp=2, num_mp=2, num_dp=2)
+    assert t3.get_rank(pipe=1, data=0, model=1) == 5
+    assert t3.get_rank_repr(5) == "model_01"
+    assert PipeDataParallelTopology(2, 2).get_axis_comm_lists("data") == [[0, 1], [2, 3]]
+
+
+@pytest.mark.parametrize("stages,micro", [(1, 1), (2, 4), (4, 4), (4, 8), (3, 2)])
+def test_train_schedule_is_consistent(stages, micro):
+    from deepspeed_b200.runtime.pipe import schedule as S
+    streams = [[c for step in S.TrainSchedule(micro, stages, s) for c in step] for s in range(stages)]
+    for s, cmds in enumerate(streams):
+        fw = [c.buffer_id for c in cmds if isinstance(c, S.ForwardPass)]
+        bw = [c.buffer_id for c in cmds if isinstance(c, S.BackwardPass)]
+        assert len(fw) == micro and len(bw) == micro
+        assert isinstance(cmds[-1], S.OptimizerStep)
+        # live activations never exceed the buffer count
+        live, peak = 0, 0
+        for c in cmds:
+            if isinstance(c, S.ForwardPass):
+                live += 1
+            elif isinstance(c, S.BackwardPass):
+                live -= 1
+            peak = max(peak, live)
+        assert peak <= S.TrainSchedule(micro, stages, s).num_pipe_buffers()
+        n_send = sum(isinstance(c, S.SendActivation) for c in cmds)
+        n_recv = sum(isinstance(c, S.RecvGrad) for c in cmds)
+        assert n_send == (micro if s < stages - 1 else 0) and n_recv == n_send
+    # simulate blocking rendezvous on every link with the executor's exchange fusion: must run to completion
+    ops = []
+    for s, cmds in enumerate(streams):
+        seq = []
+        for c in S.fuse_exchanges(cmds):
+            if isinstance(c, S.SendActivation):
+                seq.append(("send", s + 1, "act"))
+            elif isinstance(c, S.RecvActivation):
+                seq.append(("recv", s - 1, "act"))
+            elif isinstance(c, S.SendGrad):
+                seq.append(("send", s - 1, "grad"))
+            elif isinstance(c, S.RecvGrad):
+                seq.append(("recv", s + 1, "grad"))
+            elif isinstance(c, S.SendActivationRecvGrad):
+                seq.append(("xchg", s + 1, "act", "grad"))
+            elif isinstance(c, S.SendGradRecvActivation):
+                seq.append(("xchg", s - 1, "grad", "act"))
+        ops.append(seq)
+    # every op is a set of sub-ops (an exchange posts its send and its recv together); a stage advances
+    # when all sub-ops of its current op have been matched by the neighbour's *current* op
+    def subops(op):
+        if op[0] == "xchg":
+            return [("send", op[1], op[2]), ("recv", op[1], op[3])]
+        return [op]
+
+    ptr = [0] * stages
+    pending = [subops(ops[s][0]) if ops[s] else [] for s in range(stages)]
+    progressed = True
+    while progressed:
+        progressed = False
+        for s in range(stages - 1):
+            for a in list(pending[s]):
+                for b in list(pending[s + 1]):
+                    if a[1] == s + 1 and b[1] == s and a[2] == b[2] and {a[0], b[0]} == {"send", "recv"}:
+                        pending[s].remove(a)
+                        pending[s + 1].remove(b)
+                        progressed = True
+                        break
+        for s in range(stages):
+            while ptr[s] < len(ops[s]) and not pending[s]:
+                ptr[s] += 1
+                pending[s] = subops(ops[s][ptr[s]]) if ptr[s] < len(ops[s]) else []
+                progressed = True
+    assert all(ptr[s] >= len(ops[s]) for s in range(stages)), f"pipeline would dead-lock: {ptr} vs {[len(o) for o in ops]}"
+
+
+class _Blk(nn.Module):
+
+    def __init__(self, d):
+        super().__init__()
+        self.l = nn.Linear(d, d)
+
+    def forward(self, x):
+        return torch.tanh(self.l(x))
+
+
+def _pipe_train(num_stages):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.pipe import LayerSpec, PipelineModule
+    torch.manual_seed(0)
+    d, L, micro, mbs = 16, 4, 4, 2
+    ref_layers = [_Blk(d) for _ in range(L)]
+    ref = nn.Sequential(*copy.deepcopy(ref_layers))
+    w = torch.distributed.get_world_size()
+    dp = w // num_stages
+    model = PipelineModule(layers=copy.deepcopy(ref_layers), num_stages=num_stages, loss_fn=nn.MSELoss(),
+                           partition_method="uniform")
+    cfg = {"train_micro_batch_size_per_gpu": mbs, "gradient_accumulation_steps": micro,
+           "optimizer": {"type": "SGD", "params": {"lr": 0.1}}, "zero_optimization": {"stage": 0}}
+    eng, _, _, _ = ds.initialize(model=model, config=cfg)
+    dp_rank = eng.grid.get_data_parallel_id()
+    g = torch.Generator().manual_seed(5)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    for it in range(3):
+        xs = torch.randn(dp, micro, mbs, d, generator=g)
+        ys = torch.randn(dp, micro, mbs, d, generator=g)
+        data = iter([(xs[dp_rank, m], ys[dp_rank, m]) for m in range(micro)])
+        loss = eng.train_batch(data_iter=data)
+        total = 0.0
+        for r in range(dp):
+            for m in range(micro):
+                l = nn.functional.mse_loss(ref(xs[r, m]), ys[r, m]) / (micro * dp)
+                l.backward()
+                total += l.item()
+        ropt.step()
+        ropt.zero_grad()
+        assert abs(loss.item() - total) < 1e-5, (loss.item(), total)
+    # compare the layers this stage owns
+    for idx in range(model._local_start, model._local_stop):
+        mine = dict(model.named_parameters())[f"{idx}.l.weight"]
+        from deepspeed_b200.utils import safe_get_full_fp32_param
+        assert (safe_get_full_fp32_param(mine).cpu() - ref[idx].l.weight).abs().max() < 1e-5
+
+
+def test_pipeline_two_stages_matches_sequential():
+    run_distributed(_pipe_train, 2, (2, ))
+
+
+def test_pipeline_pp2_dp2_matches_sequential():
+    run_distributed(_pipe_train, 4, (2, ), timeout=300)
