@@ -1,0 +1,71 @@
+"""Weight-only quantized linears for inference (reference ``inference/quantization/layers.py``,
+``inference/v2/modules/implementations/linear/quantized_linear.py`` (FP6 ``wf6af16``), ``ops/fp_quantizer``).
+
+Weights are stored group-quantised (int8/int4 via ``quant.cu`` or FP8/FP6 via ``fp_quantize``); at run time the
+weight is dequantised tile-wise into bf16 and fed to the tensor-core GEMM.  For decode-sized inputs (few rows)
+the op is bandwidth bound on the *weight* bytes, so 8-/6-bit storage is the win; the dequant kernel streams the
+packed bytes once.
+"""
+import torch
+import torch.nn.functional as F
+
+from deepspeed_b200.ops.quantizer import quantizer as Q
+
+
+class QuantizedWeight:
+    """Packed weight + group params.  ``mode``: int8 | int4 | fp8 | fp6"""
+
+    def __init__(self, q, params, shape, mode, group_size, dtype):
+        self.q, self.params, self.shape, self.mode, self.group_size, self.dtype = q, params, tuple(shape), mode, group_size, dtype
+
+    @property
+    def is_cuda(self):
+        return self.q.is_cuda
+
+    def dequantize(self):
+        n = self.shape[0] * self.shape[1]
+        groups = n // self.group_size
+        if self.mode in ("int8", "int4"):
+            return Q.dequantize(self.q, self.params, groups, 8 if self.mode == "int8" else 4, Q.Symmetric,
+                                dtype=self.dtype).view(self.shape)
+        from deepspeed_b200.ops.fp_quantizer.quantize import FP_Quantize
+        fq = FP_Quantize(group_size=self.group_size)
+        fq.orig_shape, fq.orig_dtype = self.shape, self.dtype
+        bits, man = (8, 3) if self.mode == "fp8" else (6, 2)
+        return fq.dequantize(self.q, q_bits=bits, q_mantisa_bits=man, scale=self.params).view(self.shape).to(self.dtype)
+
+
+def quantize_weight(w, mode="int8", group_size=128):
+    n = w.numel()
+    while n % group_size:
+        group_size //= 2
+    groups = n // group_size
+    if mode in ("int8", "int4"):
+        q, params = Q.quantize(w.contiguous(), groups, 8 if mode == "int8" else 4, Q.Symmetric)
+        return QuantizedWeight(q, params, w.shape, mode, group_size, w.dtype)
+    if mode in ("fp8", "fp6", "wf6af16"):
+        from deepspeed_b200.ops.fp_quantizer.quantize import FP_Quantize
+        fq = FP_Quantize(group_size=group_size)
+        bits, man = (8, 3) if mode == "fp8" else (6, 2)
+        q, scale = fq.quantize(w.contiguous(), q_bits=bits, q_mantisa_bits=man, return_meta_tensor=True)
+        return QuantizedWeight(q, scale, w.shape, "fp8" if mode == "fp8" else "fp6", group_size, w.dtype)
+    raise ValueError(f"unknown quantization mode {mode}")
+
+
+def maybe_quantized_linear(x, w, b=None):
+    if isinstance(w, QuantizedWeight):
+        w = w.dequantize()
+    return F.linear(x, w, b)
+
+
+class QuantizedLinear(torch.nn.Module):
+    """Drop-in for nn.Linear holding a QuantizedWeight (reference ``QuantizedLinear``)."""
+
+    def __init__(self, linear: torch.nn.Linear, mode="int8", group_size=128):
+        super().__init__()
+        self.qw = quantize_weight(linear.weight.data, mode, group_size)
+        self.bias = linear.bias
+        self.in_features, self.out_features = linear.in_features, linear.out_features
+
+    def forward(self, x):
+        return maybe_quantized_linear(x, self.qw, self.bias)

@@ -1,0 +1,113 @@
+"""Host-side builder of the ragged batch metadata (reference ``ragged/ragged_wrapper.py:31``).
+
+All metadata is staged in ONE pinned host buffer and moved with a single async H2D copy into a persistent
+device buffer (so the decode step is CUDA-graph friendly: the graph reads fixed addresses):
+
+    input_ids [T] | seq_of [T] | pos_of [T] | last_tok [S] | block_table [S, max_blocks]
+"""
+import torch
+
+from deepspeed_b200.accelerator import get_accelerator
+from ..config_v2 import DSStateManagerConfig
+
+
+class RaggedBatchWrapper:
+
+    def __init__(self, config: DSStateManagerConfig, max_blocks_per_seq: int = 64, device=None):
+        self._config = config
+        T, S, MB = config.max_ragged_batch_size, config.max_ragged_sequence_count, max_blocks_per_seq
+        self._max_T, self._max_S, self._max_blocks = T, S, MB
+        self.device = device if device is not None else get_accelerator().current_device_name()
+        total = 3 * T + S + S * MB
+        pin = torch.cuda.is_available()
+        self._host = torch.zeros(total, dtype=torch.int32, pin_memory=pin)
+        self._dev = torch.zeros(total, dtype=torch.int32, device=self.device)
+        o = 0
+        self._views = {}
+        for name, n in (("ids", T), ("seq_of", T), ("pos_of", T), ("last_tok", S), ("block_table", S * MB)):
+            self._views[name] = (o, n)
+            o += n
+        self.clear()
+
+    def _h(self, name):
+        o, n = self._views[name]
+        return self._host[o:o + n]
+
+    def _d(self, name):
+        o, n = self._views[name]
+        return self._dev[o:o + n]
+
+    def clear(self) -> None:
+        self._n_tokens = 0
+        self._n_seqs = 0
+        self._seq_tokens = []
+        self._seq_seen = []
+        self._is_finalized = False
+
+    def insert_sequence(self, seq_descriptor, tokens: torch.Tensor, do_checks=True) -> None:
+        n = tokens.numel()
+        if do_checks:
+            if self._n_seqs + 1 > self._max_S:
+                raise RuntimeError(f"Ragged batch is full: {self._n_seqs} sequences")
+            if self._n_tokens + n > self._max_T:
+                raise RuntimeError(f"Ragged batch is full: {self._n_tokens} + {n} tokens > {self._max_T}")
+        s, t0 = self._n_seqs, self._n_tokens
+        self._h("ids")[t0:t0 + n] = tokens.to(torch.int32).reshape(-1)
+        self._h("seq_of")[t0:t0 + n] = s
+        self._h("pos_of")[t0:t0 + n] = torch.arange(seq_descriptor.seen_tokens, seq_descriptor.seen_tokens + n,
+                                                   dtype=torch.int32)
+        self._h("last_tok")[s] = t0 + n - 1
+        nb = seq_descriptor.cur_allocated_blocks
+        bt = self._h("block_table").view(self._max_S, self._max_blocks)
+        bt[s, :nb] = seq_descriptor.kv_cache_ids(0)[:nb]
+        self._seq_tokens.append(n)
+        self._seq_seen.append(seq_descriptor.seen_tokens)
+        self._n_seqs += 1
+        self._n_tokens += n
+
+    def finalize(self, padding: bool = False) -> None:
+        """One H2D copy of the used prefix of every region (regions are contiguous so a single copy of the whole
+        staging buffer is cheaper than five small ones at these sizes)."""
+        self._dev.copy_(self._host, non_blocking=True)
+        self._is_finalized = True
+
+    # --- views consumed by the model ---
+    def input_ids(self, padded_tokens=None):
+        return self._d("ids")[:padded_tokens or self._n_tokens]
+
+    def seq_of(self, padded_tokens=None):
+        return self._d("seq_of")[:padded_tokens or self._n_tokens]
+
+    def pos_of(self, padded_tokens=None):
+        return self._d("pos_of")[:padded_tokens or self._n_tokens]
+
+    def last_token_index(self, padded_seqs=None):
+        return self._d("last_tok")[:padded_seqs or self._n_seqs]
+
+    def block_table(self):
+        return self._d("block_table").view(self._max_S, self._max_blocks)
+
+    @property
+    def seq_layout(self):
+        """Host list of (token_start, n_tokens, seen_tokens) per sequence — used to pick dense prefill."""
+        out, t = [], 0
+        for n, seen in zip(self._seq_tokens, self._seq_seen):
+            out.append((t, n, seen))
+            t += n
+        return out
+
+    @property
+    def current_tokens(self) -> int:
+        return self._n_tokens
+
+    @property
+    def current_sequences(self) -> int:
+        return self._n_seqs
+
+    @property
+    def tensor_toks(self):
+        return self._n_tokens
+
+    @property
+    def is_pure_decode(self) -> bool:
+        return self._n_seqs == self._n_tokens and self._n_seqs > 0

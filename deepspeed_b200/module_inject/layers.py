@@ -1,0 +1,210 @@
+"""Tensor-parallel linear layers.
+
+Parity target: reference ``module_inject/layers.py`` (``RowParallel :65``, ``ColumnParallel :97``,
+``LinearAllreduce :300``, ``LinearLayer :370``, ``LmHeadLinearAllreduce``, fused-QKV / gate-up aware column
+splits, uneven shard sizes, ``GatherReplacedLayerParams :238``).  Forward of a row-parallel layer ends in an
+all-reduce, backward of a column-parallel layer's input gradient does; both go through
+``deepspeed_b200.comm.inference_all_reduce`` which uses the one-shot NVLS kernel for small symmetric tensors.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from deepspeed_b200 import comm as dist
+
+
+def shard_sizes(total, world, granularity=1):
+    """Sizes of ``world`` contiguous shards of ``total`` in units of ``granularity`` (first shards larger)."""
+    assert total % granularity == 0
+    units = total // granularity
+    base, rem = divmod(units, world)
+    return [(base + (1 if r < rem else 0)) * granularity for r in range(world)]
+
+
+def shard_bounds(total, world, rank, granularity=1):
+    sizes = shard_sizes(total, world, granularity)
+    start = sum(sizes[:rank])
+    return start, start + sizes[rank]
+
+
+class RowParallel(torch.autograd.Function):
+    """Identity forward / all-reduce... inverse of ColumnParallel: all-reduce in forward, identity in backward."""
+
+    @staticmethod
+    def symbolic(graph, input):
+        return input
+
+    @staticmethod
+    def forward(ctx, group, input, is_inference_mode=False):
+        ctx.group = group
+        if group is None or dist.get_world_size(group) == 1:
+            return input
+        input = input.contiguous()
+        if is_inference_mode:
+            dist.inference_all_reduce(input, group=group)
+        else:
+            dist.all_reduce(input, group=group)
+        return input
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return None, grad_output, None
+
+
+class ColumnParallel(torch.autograd.Function):
+    """Identity in forward, all-reduce of the input gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, group, input):
+        ctx.group = group
+        return input
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.group is None or dist.get_world_size(ctx.group) == 1:
+            return None, grad_output
+        grad_output = grad_output.contiguous()
+        dist.all_reduce(grad_output, group=ctx.group)
+        return None, grad_output
+
+
+class TensorParallel_Layer(nn.Module):
+    keep_module_on_host = False
+
+    def __init__(self, mp_group, name=None):
+        super().__init__()
+        self.mp_group = mp_group
+        self.tp_world_size = dist.get_world_size(mp_group) if mp_group is not None else 1
+        self.tp_index = dist.get_rank(mp_group) if mp_group is not None else 0
+        self.name = name
+        self.support_training = False
+
+    def is_training_mode(self):
+        return self.training
+
+    def _mark(self, *params):
+        for p in params:
+            if p is not None:
+                p.tensor_model_parallel = True
+                p.model_parallel = True
+                p.ds_tp_world = self.tp_world_size
+
+
+class LinearLayer(TensorParallel_Layer):
+    """Column-parallel: each rank owns ``out/P`` output features (``weight`` rows)."""
+
+    def __init__(self, module: nn.Module = None, mp_group=None, skip_partition=False, weight=None, bias=None,
+                 granularity=1, fused_parts=1, **kwargs):
+        super().__init__(mp_group, kwargs.get("name"))
+        w = module.weight if module is not None else weight
+        b = module.bias if module is not None and getattr(module, "bias", None) is not None else bias
+        self.support_training = True
+        if skip_partition or self.tp_world_size == 1:
+            self.weight, self.bias = nn.Parameter(w.data), (nn.Parameter(b.data) if b is not None else None)
+        else:
+            self.weight = nn.Parameter(_split_rows(w.data, self.tp_world_size, self.tp_index, fused_parts, granularity))
+            self.bias = nn.Parameter(_split_rows(b.data, self.tp_world_size, self.tp_index, fused_parts,
+                                                 granularity)) if b is not None else None
+        self._mark(self.weight, self.bias)
+
+    def forward(self, input):
+        x = ColumnParallel.apply(self.mp_group, input) if self.training else input
+        return F.linear(x, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f"in={self.weight.shape[1]}, out_local={self.weight.shape[0]}, tp={self.tp_world_size}"
+
+
+def _split_rows(t, world, rank, fused_parts=1, granularity=1):
+    """Shard dim 0.  ``fused_parts`` > 1: the tensor is a concatenation (q|k|v or gate|up) and every part is
+    sharded separately so each rank gets matching slices of all parts."""
+    if fused_parts == 1:
+        s, e = shard_bounds(t.shape[0], world, rank, granularity)
+        return t[s:e].clone()
+    parts = t.chunk(fused_parts, dim=0) if not isinstance(fused_parts, (list, tuple)) else torch.split(t, list(fused_parts), 0)
+    outs = []
+    for p in parts:
+        s, e = shard_bounds(p.shape[0], world, rank, granularity)
+        outs.append(p[s:e])
+    return torch.cat(outs, dim=0).clone()
+
+
+class LinearAllreduce(TensorParallel_Layer):
+    """Row-parallel: each rank owns ``in/P`` input features (``weight`` columns); outputs are summed."""
+
+    def __init__(self, module: nn.Module = None, mp_group=None, weight=None, bias=None, granularity=1, **kwargs):
+        super().__init__(mp_group, kwargs.get("name"))
+        w = module.weight if module is not None else weight
+        b = module.bias if module is not None and getattr(module, "bias", None) is not None else bias
+        self.support_training = True
+        if self.tp_world_size == 1:
+            self.weight = nn.Parameter(w.data)
+        else:
+            s, e = shard_bounds(w.shape[1], self.tp_world_size, self.tp_index, granularity)
+            self.weight = nn.Parameter(w.data[:, s:e].clone())
+        self.bias = nn.Parameter(b.data) if b is not None else None  # replicated, added after the reduce
+        self._mark(self.weight)
+
+    def forward(self, input):
+        out = torch.matmul(input, self.weight.transpose(-1, -2))
+        out = RowParallel.apply(self.mp_group, out, not self.training)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+class LmHeadLinearAllreduce(LinearAllreduce):
+    """LM head whose *input* (hidden) dimension is sharded: slices the incoming hidden states itself."""
+
+    def forward(self, input):
+        s, e = shard_bounds(input.shape[-1], self.tp_world_size, self.tp_index)
+        if self.training:  # every rank only produces the gradient of its own slice of the hidden states
+            input = ColumnParallel.apply(self.mp_group, input)
+        out = torch.matmul(input[..., s:e], self.weight.transpose(-1, -2))
+        out = RowParallel.apply(self.mp_group, out, not self.training)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+
+class GatherReplacedLayerParams:
+    """Context manager: temporarily reassemble the full weight of TP layers (for export / inspection)."""
+
+    def __init__(self, params, module, enabled=True):
+        self.enabled = enabled
+        self.module = module
+        self.params = params if isinstance(params, (list, tuple)) else [params]
+        self._saved = []
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        for m in self.module.modules():
+            if isinstance(m, LinearLayer) and m.tp_world_size > 1:
+                self._saved.append((m, "weight", m.weight.data))
+                m.weight.data = _gather_dim(m.weight.data, m.mp_group, 0)
+            elif isinstance(m, LinearAllreduce) and m.tp_world_size > 1:
+                self._saved.append((m, "weight", m.weight.data))
+                m.weight.data = _gather_dim(m.weight.data, m.mp_group, 1)
+        return self
+
+    def __exit__(self, *exc):
+        for m, name, data in self._saved:
+            getattr(m, name).data = data
+        self._saved.clear()
+        return False
+
+
+def _gather_dim(t, group, dim):
+    world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device), group=group)
+    outs = []
+    for s in sizes:
+        shp = list(t.shape)
+        shp[dim] = int(s.item())
+        outs.append(torch.empty(shp, dtype=t.dtype, device=t.device))
+    dist.all_gather(outs, t.contiguous(), group=group) if len({tuple(o.shape) for o in outs}) == 1 else \
+        [dist.broadcast(o if i != dist.get_rank(group) else o.copy_(t), src=dist.get_global_rank(group, i) if group else i,
+                        group=group) for i, o in enumerate(outs)]
+    return torch.cat(outs, dim=dim)
