@@ -1,0 +1,6 @@
+from .constants import *  # noqa: F401,F403
+from .deepspeed_checkpoint import DeepSpeedCheckpoint  # noqa: F401
+from .universal_checkpoint import load_universal_into_engine, load_hp_checkpoint_state  # noqa: F401
+from .ds_to_universal import convert_to_universal  # noqa: F401
+from .utils import (get_model_ckpt_name_for_rank, get_zero_ckpt_name_for_rank, get_layer_ckpt_name_for_rank,  # noqa: F401
+                    clone_tensors_for_torch_save)

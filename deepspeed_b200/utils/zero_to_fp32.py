@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Consolidate a ZeRO (stage 1/2/3) checkpoint written by deepspeed_b200 into a plain fp32 ``state_dict``.
+
+This script is copied next to every checkpoint (like the reference's ``utils/zero_to_fp32.py``) and depends on
+``torch`` only.  Usage::
+
+    python zero_to_fp32.py <checkpoint_dir> <output_dir> [--tag TAG] [--max_shard_size 5GB] [--safe_serialization]
+
+API parity: ``get_fp32_state_dict_from_zero_checkpoint``, ``convert_zero_checkpoint_to_fp32_state_dict``,
+``load_state_dict_from_zero_checkpoint``.
+
+Layout read (see ``runtime/checkpointing.py``): every DP rank's ``*_optim_states.pt`` holds ``fp32_flat`` — its
+slice of each *unit* (unit u occupies ``[arena_offset, arena_offset+shard_numel)``); the unit's full flat
+buffer is the rank-order concatenation of those slices and ``ds_b200_layout`` in the model-states file lists
+each parameter's ``(name, offset, numel, shape)`` inside it.
+"""
+import argparse
+import glob
+import json
+import os
+import re
+from collections import OrderedDict
+
+import torch
+
+
+def _natural(s):
+    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+
+
+def _resolve_tag(checkpoint_dir, tag):
+    if tag is None:
+        latest = os.path.join(checkpoint_dir, "latest")
+        if not os.path.isfile(latest):
+            raise ValueError(f"Unable to find 'latest' file at {latest}")
+        with open(latest) as f:
+            tag = f.read().strip()
+    d = os.path.join(checkpoint_dir, tag)
+    if not os.path.isdir(d):
+        raise FileNotFoundError(f"Directory '{d}' doesn't exist")
+    return d
+
+
+def _load(path):
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def _files(ds_dir, pattern):
+    fs = sorted(glob.glob(os.path.join(ds_dir, pattern)), key=_natural)
+    if not fs:
+        raise FileNotFoundError(f"can't find {pattern} files in directory '{ds_dir}'")
+    return fs
+
+
+def _model_state(ds_dir):
+    cands = sorted(glob.glob(os.path.join(ds_dir, "*_model_states.pt")), key=_natural)
+    cands = [c for c in cands if "expert_" not in os.path.basename(c)]
+    if not cands:
+        raise FileNotFoundError(f"no *_model_states.pt under {ds_dir}")
+    return _load(cands[0])
+
+
+def get_optim_shards(ds_dir):
+    files = _files(ds_dir, "*_optim_states.pt")
+    # one file per DP rank (mp_rank_00 only: TP-sharded checkpoints are consolidated per mp rank)
+    by_mp = {}
+    for f in files:
+        m = re.search(r"zero_pp_rank_(\d+)_mp_rank_(\d+)_optim_states", os.path.basename(f))
+        by_mp.setdefault(int(m.group(2)), []).append((int(m.group(1)), f))
+    return {mp: [f for _, f in sorted(v)] for mp, v in by_mp.items()}
+
+
+def _unit_flats(layout, shards, key="fp32_flat", sub=None):
+    """Yield (unit_dict, full_flat_fp32) by concatenating every rank's slice."""
+    for u in layout["units"]:
+        a, n = u["arena_offset"], u["shard_numel"]
+        parts = []
+        for sd in shards:
+            src = sd[key] if sub is None else sd[key][sub]
+            parts.append(src[a:a + n].float())
+        yield u, torch.cat(parts)
+
+
+def get_fp32_state_dict_from_zero_checkpoint(checkpoint_dir, tag=None, exclude_frozen_parameters=False, lazy_mode=False):
+    ds_dir = _resolve_tag(checkpoint_dir, tag)
+    ms = _model_state(ds_dir)
+    layout = ms.get("ds_b200_layout")
+    if layout is None:
+        raise ValueError("checkpoint has no ds_b200_layout: not a deepspeed_b200 ZeRO checkpoint")
+    shards = [_load(f)["optimizer_state_dict"] for f in get_optim_shards(ds_dir)[0]]
+    world = shards[0]["partition_count"]
+    if len(shards) != world:
+        raise ValueError(f"Expected {world} of '*_optim_states.pt' under '{ds_dir}' but found {len(shards)} files")
+    print(f"Detected checkpoint of type zero stage {shards[0]['zero_stage']}, world_size: {world}")
+    frozen = set((ms.get("frozen_param_shapes") or {}).keys())
+    out = OrderedDict()
+    buffers = set(ms.get("buffer_names") or [])
+    for k, v in ms["module"].items():
+        if k in buffers:
+            out[k] = v.float() if v.is_floating_point() else v
+    for u, flat in _unit_flats(layout, shards):
+        for (name, off, numel, shape, group) in u["slots"]:
+            if exclude_frozen_parameters and name in frozen:
+                continue
+            out[name] = flat[off:off + numel].view(*shape).clone()
+    # parameters that are not managed by ZeRO (stage<=2 keeps none outside; ZeRO-3 external) fall back to module
+    for k, v in ms["module"].items():
+        if k not in out and v.numel() > 0:
+            out[k] = v.float() if v.is_floating_point() else v
+    for alias, canon in (ms.get("shared_params") or {}).items():
+        if canon in out:
+            out[alias] = out[canon]
+    return out
+
+
+def _parse_size(s):
+    if isinstance(s, int):
+        return s
+    m = re.match(r"^(\d+(?:\.\d+)?)\s*([KMGT]?B)$", s.strip().upper())
+    if not m:
+        raise ValueError(f"bad size {s}")
+    return int(float(m.group(1)) * {"B": 1, "KB": 10**3, "MB": 10**6, "GB": 10**9, "TB": 10**12}[m.group(2)])
+
+
+def convert_zero_checkpoint_to_fp32_state_dict(checkpoint_dir, output_dir, max_shard_size="5GB", safe_serialization=False,
+                                               tag=None, exclude_frozen_parameters=False):
+    sd = get_fp32_state_dict_from_zero_checkpoint(checkpoint_dir, tag, exclude_frozen_parameters)
+    os.makedirs(output_dir, exist_ok=True)
+    limit = _parse_size(max_shard_size)
+    shards, cur, cur_bytes = [], OrderedDict(), 0
+    for k, v in sd.items():
+        b = v.numel() * v.element_size()
+        if cur and cur_bytes + b > limit:
+            shards.append(cur)
+            cur, cur_bytes = OrderedDict(), 0
+        cur[k] = v
+        cur_bytes += b
+    shards.append(cur)
+    ext = "safetensors" if safe_serialization else "bin"
+    base = "model" if safe_serialization else "pytorch_model"
+    index = {"metadata": {"total_size": sum(v.numel() * v.element_size() for v in sd.values())}, "weight_map": {}}
+    for i, sh in enumerate(shards):
+        fn = f"{base}.{ext}" if len(shards) == 1 else f"{base}-{i + 1:05d}-of-{len(shards):05d}.{ext}"
+        path = os.path.join(output_dir, fn)
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file({k: v.contiguous().clone() for k, v in sh.items()}, path, metadata={"format": "pt"})
+        else:
+            torch.save(sh, path)
+        for k in sh:
+            index["weight_map"][k] = fn
+    if len(shards) > 1:
+        with open(os.path.join(output_dir, f"{base}.{ext}.index.json"), "w") as f:
+            json.dump(index, f, indent=2, sort_keys=True)
+    print(f"Saved fp32 state dict ({len(sd)} tensors, {len(shards)} shard(s)) to {output_dir}")
+
+
+def load_state_dict_from_zero_checkpoint(model, checkpoint_dir, tag=None):
+    sd = get_fp32_state_dict_from_zero_checkpoint(checkpoint_dir, tag)
+    model = model.cpu()
+    model.load_state_dict(sd, strict=False)
+    return model
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("checkpoint_dir", type=str, help="path to the checkpoint folder, e.g. path/checkpoint-12")
+    ap.add_argument("output_dir", type=str, help="directory for the consolidated fp32 weights")
+    ap.add_argument("--max_shard_size", type=str, default="5GB")
+    ap.add_argument("--safe_serialization", default=False, action="store_true")
+    ap.add_argument("-t", "--tag", type=str, default=None)
+    ap.add_argument("--exclude_frozen_parameters", action="store_true")
+    ap.add_argument("-d", "--debug", action="store_true")
+    a = ap.parse_args()
+    convert_zero_checkpoint_to_fp32_state_dict(a.checkpoint_dir, a.output_dir, a.max_shard_size, a.safe_serialization, a.tag,
+                                               a.exclude_frozen_parameters)
