@@ -22,6 +22,7 @@ from deepspeed_b200.ops.kernels import moe_ops as M
 from .arch import ArchSpec
 
 DENSE_PREFILL_MIN = 32
+MOE_DENSE_MAX_TOKENS = 64
 
 
 def _act(x, name):
@@ -153,6 +154,17 @@ class RaggedTransformer:
         Tn = x.shape[0]
         logits = F.linear(x, lw.gate_w)
         ids, w, counts = M.top_k_gating(logits, sp.top_k, normalize=sp.norm_topk)
+        capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+        if capturing or Tn <= MOE_DENSE_MAX_TOKENS:
+            # decode-sized batch: every expert's weights get streamed once anyway (weight-bandwidth bound), so run
+            # all experts on all rows and mask — no host sync, static shapes, CUDA-graph capturable.
+            out = torch.zeros(Tn, x.shape[1], dtype=torch.float32, device=x.device)
+            for e in range(sp.num_experts):
+                we = (w * (ids == e)).sum(-1, keepdim=True)
+                ye = F.linear(T.gated_act(F.linear(x, lw.experts_up[e]), sp.act), lw.experts_down[e])
+                out.addcmul_(ye.float(), we)
+            out = out.to(x.dtype)
+            return self._moe_shared(lw, x, out)
         positions, counts2, offsets = M.route(ids, sp.num_experts)
         rows = Tn * sp.top_k
         xs, slots = M.scatter(x, ids, positions, offsets, sp.top_k, 0, rows)
@@ -164,6 +176,10 @@ class RaggedTransformer:
                 h = T.gated_act(F.linear(xs[s:t], lw.experts_up[e]), sp.act)
                 ys[s:t] = F.linear(h, lw.experts_down[e])
         out = M.gather(ys, w, slots, Tn, sp.top_k)
+        return self._moe_shared(lw, x, out)
+
+    def _moe_shared(self, lw, x, out):
+        sp = self.spec
         if lw.shared_up is not None:
             sh = F.linear(T.gated_act(F.linear(x, lw.shared_up), sp.act), lw.shared_down)
             if lw.shared_gate is not None:

@@ -216,7 +216,7 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
                       gradient_clipping=self.gradient_clipping(), loss_scale_config=self._build_loss_scale_config(),
                       communication_data_type=c.communication_data_type, prescale_gradients=c.prescale_gradients,
                       gradient_predivide_factor=c.gradient_predivide_factor, device=self.device, mpu=self.mpu,
-                      timers=self.timers)
+                      timers=self.timers, aio_config=getattr(c, "aio_config", None))
         expert_names = sorted({getattr(p, "group_name", None) for p in self.module.parameters()
                                if getattr(p, "allreduce", True) is False} - {None})
         if not expert_names:

@@ -1,0 +1,109 @@
+"""NVMe tier for ZeRO-3 parameter shards (reference ``partitioned_param_swapper.py:36
+AsyncPartitionedParameterSwapper``): each unit's low-precision shard has a swap file; ``swap_in`` brings a set
+of shards into pinned buffers ahead of the all-gather, ``swap_out_and_release`` writes them back."""
+import os
+from enum import Enum
+
+import torch
+
+from .utils import _pinned
+
+
+class PartitionedParamStatus(Enum):
+    AVAILABLE = 1
+    NOT_AVAILABLE = 2
+    INFLIGHT = 3
+
+
+class AsyncPartitionedParameterSwapper:
+
+    def __init__(self, ds_config_or_offload, model_dtype, aio_config=None, base_folder=None, rank=0):
+        from .aio_config import make_handle
+        oc = ds_config_or_offload
+        self.dtype = model_dtype
+        self.folder = os.path.join(base_folder or str(getattr(oc, "nvme_path", "/tmp")), "zero_stage_3",
+                                   f"{str(model_dtype).split('.')[-1]}params", f"rank{rank}")
+        os.makedirs(self.folder, exist_ok=True)
+        self.aio_read = make_handle(aio_config or {})
+        self.aio_write = make_handle(aio_config or {})
+        self.buffer_elems = int(getattr(oc, "buffer_size", 1 << 27) or (1 << 27))
+        self.buffer_count = int(getattr(oc, "buffer_count", 5) or 5)
+        self._pool = [_pinned(self.buffer_elems, model_dtype) for _ in range(self.buffer_count)]
+        self._free = list(range(self.buffer_count))
+        self._resident = {}   # id -> (buf idx, numel)
+        self._inflight = set()
+        self._status = {}
+        self._numel = {}
+        self.pending_writes = 0
+
+    def _path(self, pid):
+        return os.path.join(self.folder, f"{pid}_param.tensor.swp")
+
+    def available_swap_in_buffers(self):
+        return len(self._free)
+
+    def swappable_tensor(self, param=None, numel=None):
+        n = numel if numel is not None else param.numel()
+        return n * self.dtype.itemsize >= 1024 and n <= self.buffer_elems
+
+    def get_buffer(self, pid, numel):
+        """Pinned tensor for ``pid`` (allocated on first use)."""
+        if pid in self._resident:
+            i, n = self._resident[pid]
+            return self._pool[i][:n]
+        if not self._free:
+            raise RuntimeError("parameter swap buffers exhausted; raise offload_param.buffer_count")
+        i = self._free.pop()
+        self._resident[pid] = (i, numel)
+        self._numel[pid] = numel
+        return self._pool[i][:numel]
+
+    def swap_out_and_release(self, pids, tensors=None, async_op=False, force_buffer_release=False):
+        for k, pid in enumerate(pids):
+            buf = self.get_buffer(pid, self._numel.get(pid, tensors[k].numel() if tensors else 0))
+            if tensors is not None:
+                buf.copy_(tensors[k].reshape(-1))
+            self.aio_write.async_pwrite(buf, self._path(pid))
+            self.pending_writes += 1
+            self._status[pid] = PartitionedParamStatus.NOT_AVAILABLE
+        if not async_op:
+            self.synchronize_writes()
+            for pid in pids:
+                self._release(pid)
+
+    def _release(self, pid):
+        ent = self._resident.pop(pid, None)
+        if ent is not None:
+            self._free.append(ent[0])
+
+    def synchronize_writes(self):
+        if self.pending_writes:
+            self.aio_write.wait()
+            self.pending_writes = 0
+
+    def swap_in(self, pids, async_op=True):
+        out = []
+        for pid in pids:
+            buf = self.get_buffer(pid, self._numel[pid])
+            self.aio_read.async_pread(buf, self._path(pid))
+            self._inflight.add(pid)
+            self._status[pid] = PartitionedParamStatus.INFLIGHT
+            out.append(buf)
+        if not async_op:
+            self.synchronize_reads()
+        return out
+
+    def synchronize_reads(self):
+        if self._inflight:
+            self.aio_read.wait()
+            for pid in self._inflight:
+                self._status[pid] = PartitionedParamStatus.AVAILABLE
+            self._inflight.clear()
+
+    def release(self, pids):
+        for pid in pids:
+            self._release(pid)
+            self._status[pid] = PartitionedParamStatus.NOT_AVAILABLE
+
+    def status(self, pid):
+        return self._status.get(pid, PartitionedParamStatus.NOT_AVAILABLE)

@@ -41,6 +41,7 @@ class DeepSpeedZeroOffloadOptimizerConfig(DeepSpeedConfigModel):
     pipeline_write: bool = False
     fast_init: bool = False
     ratio: float = Field(1.0, ge=0.0, le=1.0)  # Twin-Flow: fraction of optimizer state on the host
+    b200_swap_window: int = Field(pp_int(1 << 26), ge=1)  # NVMe tier: elements per pinned streaming window
 
     @model_validator(mode="after")
     def _set_pipeline(self):

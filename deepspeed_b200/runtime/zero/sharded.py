@@ -96,7 +96,9 @@ class ZeroShardedOptimizer:
                  broadcast_init=True,
                  timers=None,
                  param_filter=None,
-                 name="dense"):
+                 name="dense",
+                 aio_config=None):
+        self.aio_config = aio_config
         from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
         self.param_filter = param_filter
         self.name = name
@@ -136,6 +138,8 @@ class ZeroShardedOptimizer:
         self.offload_param = bool(op and str(getattr(op.device, "value", op.device)) != "none") and self.stage == 3
         self.offload_pin = bool(oo.pin_memory) if oo else False
         self.offload_ratio = float(oo.ratio) if oo else 1.0
+        self.offload_nvme = self.offload_optimizer and str(getattr(oo.device, "value", oo.device)) == "nvme"
+        self.state_swapper = None
 
         # ---- loss scaling ----------------------------------------------------------------
         lsc = loss_scale_config or {}
@@ -314,7 +318,15 @@ class ZeroShardedOptimizer:
             for rt in self.rts:
                 a = rt.u.arena_offset
                 self.master[a:a + rt.u.shard_numel].copy_(self._lp_shard(rt.u))
-        self.flat_opt.init_state(self.arena_numel, st_dev, torch.float32, pin=True)
+        if self.offload_nvme and not isinstance(self.flat_opt, TorchOptimizerAdapter):
+            # NVMe tier: optimizer moments live in per-rank swap files and stream through pinned windows
+            from deepspeed_b200.runtime.swap_tensor import FlatStateSwapper
+            oo = self.zc.offload_optimizer
+            self.state_swapper = FlatStateSwapper(oo, self.aio_config or {}, str(oo.nvme_path or "/tmp"),
+                                                  dist.get_rank())
+            self.state_swapper.wrap(self.flat_opt, self.arena_numel)
+        else:
+            self.flat_opt.init_state(self.arena_numel, st_dev, torch.float32, pin=True)
         if isinstance(self.flat_opt, TorchOptimizerAdapter):
             self.flat_opt.bind([(g, s0, e0, self._piece_master(rt, s0, e0)) for (rt, g, s0, e0) in self.pieces],
                                len(self.param_groups))
@@ -808,15 +820,27 @@ class ZeroShardedOptimizer:
         """Run the flat optimizer over arena range [a, b).  ``grad`` holds arena coordinates
         ``[grad_offset, ...)``."""
         write_lp = self.master is not None and not self.offload_optimizer
+        work = []
+        win = self.state_swapper.window_elems if self.state_swapper is not None else None
         for (rt, gi, s0, e0) in self.pieces:
             s1, e1 = max(s0, a), min(e0, b)
             if s1 >= e1 or gi < 0:
                 continue
+            if win is None:
+                work.append((rt, gi, s1, e1))
+            else:  # NVMe tier: never touch more than one swap window of state at a time
+                for c in range(s1, e1, win):
+                    work.append((rt, gi, c, min(c + win, e1)))
+        for i, (rt, gi, s1, e1) in enumerate(work):
+            if self.state_swapper is not None and i + 1 < len(work):
+                self.state_swapper.prefetch(self.flat_opt, work[i + 1][2], work[i + 1][3])
             p = self._piece_master(rt, s1, e1)
             g = grad[s1 - grad_offset:e1 - grad_offset]
             out = self._piece_lp(rt, s1, e1) if write_lp else None
             self.flat_opt.step_segment(s1, e1, p, g, out, self.param_groups[gi], self._peek_step(gi),
                                        grad_scale=grad_scale, d_gscale=d_gscale, d_skip=d_skip)
+        if self.state_swapper is not None:
+            self.state_swapper.flush(self.flat_opt)
 
     def _peek_step(self, gi):
         # group_steps is advanced once per global step in step(); during fused-in-backward calls the

@@ -107,3 +107,9 @@ def test_from_b200_llama_and_quantized():
     eq = build_engine_from_model(m, ec)
     gq = eq.put([0], [ids])[0]
     assert torch.nn.functional.cosine_similarity(gq, got, dim=0) > 0.99
+
+
+def test_mixtral_routed_path(monkeypatch):
+    from deepspeed_b200.inference.v2.model_implementations import ragged_transformer as RT
+    monkeypatch.setattr(RT, "MOE_DENSE_MAX_TOKENS", 0)
+    test_family_parity("mixtral")
