@@ -221,6 +221,7 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
                                if getattr(p, "allreduce", True) is False} - {None})
         if not expert_names:
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
+            self.optimizer.grad_allreduce_enabled = lambda: self.enable_backward_allreduce
             return
         # MoE: dense parameters over the DP group, every expert family over its expert-data-parallel group
         from deepspeed_b200.runtime.zero.multi import ZeroOptimizerGroup

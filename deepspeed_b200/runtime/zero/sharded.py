@@ -138,6 +138,7 @@ class ZeroShardedOptimizer:
         self.offload_param = bool(op and str(getattr(op.device, "value", op.device)) != "none") and self.stage == 3
         self.offload_pin = bool(oo.pin_memory) if oo else False
         self.offload_ratio = float(oo.ratio) if oo else 1.0
+        self.grad_allreduce_enabled = lambda: True
         self.offload_nvme = self.offload_optimizer and str(getattr(oo.device, "value", oo.device)) == "nvme"
         self.state_swapper = None
 
@@ -703,9 +704,12 @@ class ZeroShardedOptimizer:
                         w.wait()
             else:
                 if self.dp_world > 1:  # stage 0: plain data parallel
-                    w = dist.all_reduce(full_g, group=self.dp_group, async_op=self.on_cuda)
-                    if w is not None and hasattr(w, "wait"):
-                        w.wait()
+                    if self.grad_allreduce_enabled():
+                        w = dist.all_reduce(full_g, group=self.dp_group, async_op=self.on_cuda)
+                        if w is not None and hasattr(w, "wait"):
+                            w.wait()
+                    else:  # a communication-compressing optimizer (1-bit family) exchanges momentum itself
+                        scale = 1.0
                 shard_g = full_g
             if scale is not None:
                 self._consume_shard_grad(rt, shard_g, scale)
