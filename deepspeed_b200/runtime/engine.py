@@ -220,6 +220,14 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         expert_names = sorted({getattr(p, "group_name", None) for p in self.module.parameters()
                                if getattr(p, "allreduce", True) is False} - {None})
         if not expert_names:
+            mics = int(getattr(c.zero_config, "mics_shard_size", -1) or -1)
+            if mics > 0 and stage == 3 and mics < dist.get_world_size(self.seq_data_parallel_group):
+                from deepspeed_b200.runtime.zero.mics import create_mics_comm_groups
+                mg = create_mics_comm_groups(mics, self.seq_data_parallel_group)
+                self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=mg.param_shard_group,
+                                                      replica_group=mg.param_repli_group, **common)
+                self.optimizer.grad_allreduce_enabled = lambda: self.enable_backward_allreduce
+                return
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
             self.optimizer.grad_allreduce_enabled = lambda: self.enable_backward_allreduce
             return

@@ -1,0 +1,87 @@
+"""MiCS: shard model states inside a *sub-group* of the data-parallel world and replicate across sub-groups.
+
+Parity target: reference ``runtime/zero/mics.py`` (``MiCS_Init :64``, ``MiCS_Optimizer :361``) and
+``mics_utils.py`` (group construction).  In this framework MiCS is the same ``ZeroShardedOptimizer`` with two
+communicators: ``dp_group`` = the shard group (all-gather / reduce-scatter scope) and ``replica_group`` = ranks
+holding the same shard index (gradient all-reduce scope) — i.e. exactly the hierarchical communication of the
+paper, with the intra-group collectives riding NVSwitch.
+"""
+from dataclasses import dataclass
+from typing import List
+
+from deepspeed_b200 import comm as dist
+from deepspeed_b200.runtime.zero.partition_parameters import Init
+
+
+@dataclass
+class MiCS_CommGroups:
+    param_shard_group: object = None
+    param_shard_size: int = -1
+    param_shard_rank: int = -1
+    param_repli_group: object = None
+    param_repli_size: int = -1
+    param_repli_rank: int = -1
+    param_intra_node_group: object = None
+    param_inter_node_shard_group: object = None
+    shard_ranks: List[List[int]] = None
+    repli_ranks: List[List[int]] = None
+
+
+def mics_rank_layout(world_ranks: List[int], shard_size: int):
+    """-> (shard groups, replica groups) as lists of global ranks."""
+    n = len(world_ranks)
+    assert n % shard_size == 0, f"DP world {n} is not divisible by mics_shard_size {shard_size}"
+    shard = [world_ranks[i:i + shard_size] for i in range(0, n, shard_size)]
+    repli = [[g[i] for g in shard] for i in range(shard_size)]
+    return shard, repli
+
+
+_cache = {}
+
+
+def create_mics_comm_groups(shard_size, dp_group=None, hierarchical_allgather=False, mpu=None) -> MiCS_CommGroups:
+    key = (shard_size, id(dp_group))
+    if key in _cache:
+        return _cache[key]
+    world = dist.get_world_size(dp_group)
+    ranks = [dist.get_global_rank(dp_group, i) for i in range(world)] if dp_group is not None else list(range(world))
+    shard, repli = mics_rank_layout(ranks, shard_size)
+    me = dist.get_rank()
+    g = MiCS_CommGroups(shard_ranks=shard, repli_ranks=repli)
+    for rs in shard:
+        h = dist.new_group(rs)
+        if me in rs:
+            g.param_shard_group, g.param_shard_size, g.param_shard_rank = h, len(rs), rs.index(me)
+    for rs in repli:
+        h = dist.new_group(rs)
+        if me in rs:
+            g.param_repli_group, g.param_repli_size, g.param_repli_rank = h, len(rs), rs.index(me)
+    _cache[key] = g
+    return g
+
+
+class MiCS_Init(Init):
+    """``zero.Init`` whose partitioning scope is the MiCS shard group (parameters are sharded ``mics_shard_size``
+    ways instead of over the whole DP world)."""
+
+    def __init__(self, module=None, data_parallel_group=None, sequence_data_parallel_group=None, mem_efficient_linear=True,
+                 remote_device=None, pin_memory=False, config_dict_or_path=None, config=None, enabled=True, dtype=None,
+                 mpu=None):
+        cfg = config_dict_or_path if config_dict_or_path is not None else config
+        shard = -1
+        if isinstance(cfg, dict):
+            shard = cfg.get("zero_optimization", {}).get("mics_shard_size", -1)
+        self.mics_comm_groups = None
+        if enabled and shard and shard > 0 and dist.is_initialized():
+            self.mics_comm_groups = create_mics_comm_groups(shard, data_parallel_group, mpu=mpu)
+            data_parallel_group = self.mics_comm_groups.param_shard_group
+        super().__init__(module=module, data_parallel_group=data_parallel_group, mem_efficient_linear=mem_efficient_linear,
+                         remote_device=remote_device, pin_memory=pin_memory, config_dict_or_path=config_dict_or_path,
+                         config=config, enabled=enabled, dtype=dtype, mpu=mpu)
+
+
+def MiCS_Optimizer(module, *, shard_size, dp_group=None, **kw):
+    """Factory: the ZeRO-3 optimizer over (shard group, replica group)."""
+    from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer
+    g = create_mics_comm_groups(shard_size, dp_group)
+    return ZeroShardedOptimizer(module, 3, dp_group=g.param_shard_group, replica_group=g.param_repli_group, **kw)

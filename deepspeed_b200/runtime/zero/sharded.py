@@ -97,8 +97,10 @@ class ZeroShardedOptimizer:
                  timers=None,
                  param_filter=None,
                  name="dense",
-                 aio_config=None):
+                 aio_config=None,
+                 replica_group=None):
         self.aio_config = aio_config
+        self.replica_group = replica_group  # MiCS: model-state replicas across shard groups
         from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
         self.param_filter = param_filter
         self.name = name
@@ -139,6 +141,19 @@ class ZeroShardedOptimizer:
         self.offload_pin = bool(oo.pin_memory) if oo else False
         self.offload_ratio = float(oo.ratio) if oo else 1.0
         self.grad_allreduce_enabled = lambda: True
+        self.replica_world = dist.get_world_size(replica_group) if replica_group is not None else 1
+        # ---- ZeRO++ -----------------------------------------------------------------------
+        self.qwz = bool(getattr(self.zc, "zero_quantized_weights", False)) and self.stage == 3 and self.shard_world > 1
+        self.qgz = bool(getattr(self.zc, "zero_quantized_gradients", False)) and self.shard_world > 1
+        self.loco = getattr(self.zc, "zeropp_loco_param", None) if self.qgz else None
+        hpz = int(getattr(self.zc, "zero_hpz_partition_size", 1) or 1)
+        self.hpz = hpz if (hpz > 1 and self.stage == 3 and self.shard_world > hpz and self.shard_world % hpz == 0) else 1
+        self.hpz_group = None
+        if self.hpz > 1:
+            from deepspeed_b200.utils import groups as _g
+            if not _g._zero_param_parallel_is_initialized():
+                _g._create_zero_param_parallel_group(self.hpz)
+            self.hpz_group = _g._get_zero_param_intra_parallel_group()
         self.offload_nvme = self.offload_optimizer and str(getattr(oo.device, "value", oo.device)) == "nvme"
         self.state_swapper = None
 
@@ -291,6 +306,8 @@ class ZeroShardedOptimizer:
                 self._pack_unit(u, tmp)
                 if broadcast_init and self.dp_world > 1:
                     dist.broadcast(tmp, src=src_rank, group=self.dp_group)
+                if broadcast_init and self.replica_world > 1:  # MiCS: replicas start from replica 0's values
+                    dist.broadcast(tmp, src=dist.get_global_rank(self.replica_group, 0), group=self.replica_group)
                 lo, hi = u.shard_range(self.shard_rank)
                 self._lp_shard(u).copy_(tmp[lo:hi])
                 if u.persistent:
@@ -309,6 +326,8 @@ class ZeroShardedOptimizer:
                 foff += u.full_numel
         if not S3 and broadcast_init and self.dp_world > 1:
             dist.broadcast(self.full_arena, src=src_rank, group=self.dp_group)
+        if not S3 and broadcast_init and self.replica_world > 1:
+            dist.broadcast(self.full_arena, src=dist.get_global_rank(self.replica_group, 0), group=self.replica_group)
 
         # ---- master + optimizer state ---------------------------------------------------------------
         st_dev = "cpu" if self.offload_optimizer else dev
@@ -349,7 +368,7 @@ class ZeroShardedOptimizer:
 
     def _want_symm(self):
         f = self.zc.b200_fused_collectives
-        if f is False:
+        if f is False or self.replica_world > 1 or self.qwz or self.qgz or self.hpz > 1:
             return False
         from deepspeed_b200.comm import symm
         return symm.is_supported(self.dp_group, explicit=bool(f))
@@ -606,7 +625,7 @@ class ZeroShardedOptimizer:
                 lo, hi = u.shard_range(self.shard_rank)
                 full[lo:hi].copy_(shard, non_blocking=True)
                 shard = full[lo:hi]
-            self._all_gather(full, shard, u)
+            self._all_gather(full, shard, u, rt=rt)
             if self.on_cuda:
                 ev = torch.cuda.Event()
                 ev.record()
@@ -618,13 +637,64 @@ class ZeroShardedOptimizer:
         rt.consumed = False
         self._point_params(rt, full)
 
-    def _all_gather(self, full, shard, u: Unit):
+    def _all_gather(self, full, shard, u: Unit, rt=None):
+        if rt is not None and self.hpz > 1:
+            if self._hpz_gather(full, rt):
+                return
+        if self.qwz:
+            self._quantized_gather(full, shard, u)
+            if rt is not None and self.hpz > 1:
+                self._hpz_save(full, rt)
+            return
+        if rt is not None and self.hpz > 1:
+            w = dist.all_gather_into_tensor(full, shard, group=self.dp_group, async_op=self.on_cuda)
+            if w is not None and hasattr(w, "wait"):
+                w.wait()
+            self._hpz_save(full, rt)
+            return
         if self._symm is not None and self._symm.owns(full) and self._symm.owns(shard):
             self._symm.all_gather(full, shard, u.shard_numel)
             return
         w = dist.all_gather_into_tensor(full, shard, group=self.dp_group, async_op=self.on_cuda)
         if w is not None and hasattr(w, "wait"):
             w.wait()
+
+    # ---- ZeRO++ helpers -------------------------------------------------------------------------
+    def _quantized_gather(self, full, shard, u: Unit):
+        """qwZ: all-gather int8 block-quantised shards (+ fp32 scales) and dequantise into ``full``; this rank's
+        own range keeps its exact values (reference ``partition_parameters.py`` quantised all-gather)."""
+        from deepspeed_b200.ops.quantizer import quantizer as Q
+        n = u.shard_numel
+        g = max(1, n // 2048)
+        while n % g:
+            g -= 1
+        q, params = Q.quantize(shard.contiguous(), g, 8, Q.Symmetric)
+        qs = torch.empty(self.shard_world * q.numel(), dtype=q.dtype, device=q.device)
+        ps = torch.empty(self.shard_world * params.numel(), dtype=params.dtype, device=params.device)
+        dist.all_gather_into_tensor(qs, q.reshape(-1), group=self.dp_group)
+        dist.all_gather_into_tensor(ps, params.reshape(-1), group=self.dp_group)
+        deq = Q.dequantize(qs, ps, g * self.shard_world, 8, Q.Symmetric, dtype=full.dtype)
+        full.copy_(deq.reshape(-1)[:full.numel()])
+        lo, hi = u.shard_range(self.shard_rank)
+        full[lo:hi].copy_(shard)
+
+    def _hpz_save(self, full, rt):
+        """hpZ: keep this rank's slice of the freshly gathered unit as the *secondary* shard."""
+        k = full.numel() // self.hpz
+        hr = dist.get_rank(self.hpz_group)
+        if getattr(rt, "sec", None) is None:
+            rt.sec = torch.empty(k, dtype=full.dtype, device=full.device)
+        rt.sec.copy_(full[hr * k:(hr + 1) * k])
+        rt.sec_valid = True
+
+    def _hpz_gather(self, full, rt) -> bool:
+        """Backward re-gather inside the small (NVLink-local) group from the secondary shards."""
+        if not (self._in_backward and getattr(rt, "sec_valid", False)):
+            return False
+        w = dist.all_gather_into_tensor(full, rt.sec, group=self.hpz_group, async_op=self.on_cuda)
+        if w is not None and hasattr(w, "wait"):
+            w.wait()
+        return True
 
     @instrument_w_nvtx
     def release_unit(self, rt: _UnitRT):
@@ -683,7 +753,7 @@ class ZeroShardedOptimizer:
         ctx = torch.cuda.stream(stream) if stream is not None else _nullctx()
         with ctx:
             scale = 1.0
-            if self.dp_world > 1:
+            if self.dp_world > 1 or self.replica_world > 1:
                 if self.prescale and self.predivide != 1.0:
                     full_g.mul_(1.0 / self.predivide)
                     scale = self.predivide / self.dp_world
@@ -697,11 +767,24 @@ class ZeroShardedOptimizer:
                         scale = None  # consumed inside the fused kernel
                     else:
                         shard_g, scale = res
+                elif self.qgz:
+                    from deepspeed_b200.runtime.comm.coalesced_collectives import all_to_all_quant_reduce
+                    red = all_to_all_quant_reduce([full_g], {"local": self.dp_group})[0]  # already the shard-group mean
+                    shard_g = self._rs_tmp[u.index % 2][:u.shard_numel]
+                    shard_g.zero_()
+                    shard_g[:red.numel()].copy_(red)
+                    scale = scale * self.shard_world
                 else:
                     shard_g = self._rs_tmp[u.index % 2][:u.shard_numel]
                     w = dist.reduce_scatter_tensor(shard_g, full_g, group=self.dp_group, async_op=self.on_cuda)
                     if w is not None and hasattr(w, "wait"):
                         w.wait()
+                if self.replica_world > 1 and scale is not None:
+                    # MiCS: sum the partial results of the model-state replicas (hierarchical all-reduce)
+                    w = dist.all_reduce(shard_g, group=self.replica_group, async_op=self.on_cuda)
+                    if w is not None and hasattr(w, "wait"):
+                        w.wait()
+                    scale = scale / self.replica_world
             else:
                 if self.dp_world > 1:  # stage 0: plain data parallel
                     if self.grad_allreduce_enabled():
@@ -984,6 +1067,9 @@ class ZeroShardedOptimizer:
                         self._all_gather(rt.full, rt.full[lo:hi], rt.u)
         if self._symm is not None and gathered:
             self._symm.barrier()  # peers are done reading our in-place shard before the next update
+        if self.hpz > 1:
+            for rt in self.rts:
+                rt.sec_valid = False
         if self.on_cuda:
             ev = torch.cuda.Event()
             ev.record()
