@@ -1,0 +1,132 @@
+"""Offline data analysis for curriculum learning: compute per-sample metrics (map) and merge them into
+``index_to_metric`` / ``index_to_sample`` indexed datasets (reduce).  Reference
+``data_sampling/data_analyzer.py`` (``DataAnalyzer :22``, ``DistributedDataAnalyzer :455``)."""
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .indexed_dataset import MMapIndexedDataset, MMapIndexedDatasetBuilder
+
+
+class DataAnalyzer:
+
+    def __init__(self, dataset, num_workers=1, worker_id=0, num_threads=1, num_threads_reduce=1, specific_threads=(),
+                 batch_size=1, metric_names=(), metric_functions=(), metric_types=(), metric_dtypes=(), save_path="./",
+                 collate_fn=None, custom_map_init=None, custom_map_update=None, custom_map_finalize=None,
+                 custom_reduce=None, sample_indices=None):
+        self.dataset = dataset
+        self.num_workers, self.worker_id = num_workers, worker_id
+        self.batch_size = batch_size
+        self.metric_names, self.metric_functions = list(metric_names), list(metric_functions)
+        self.metric_types, self.metric_dtypes = list(metric_types), list(metric_dtypes)
+        self.save_path = save_path
+        self.collate_fn = collate_fn
+        self.sample_indices = sample_indices
+
+    def _my_range(self):
+        n = len(self.dataset) if self.sample_indices is None else len(self.sample_indices)
+        per = (n + self.num_workers - 1) // self.num_workers
+        return self.worker_id * per, min(n, (self.worker_id + 1) * per)
+
+    def _wdir(self, name):
+        d = os.path.join(self.save_path, name, f"worker{self.worker_id}")
+        os.makedirs(d, exist_ok=True)
+        return d
+
+    def run_map(self):
+        lo, hi = self._my_range()
+        results = {n: [] for n in self.metric_names}
+        accum = {}
+        for s in range(lo, hi, self.batch_size):
+            idx = list(range(s, min(s + self.batch_size, hi)))
+            if self.sample_indices is not None:
+                idx = [self.sample_indices[i] for i in idx]
+            batch = [self.dataset[i] for i in idx]
+            batch = self.collate_fn(batch) if self.collate_fn else torch.utils.data.default_collate(batch)
+            for name, fn, kind in zip(self.metric_names, self.metric_functions, self.metric_types):
+                v = fn(batch)
+                if kind == "single_value_per_sample":
+                    results[name].extend(zip(idx, np.asarray(v).reshape(-1).tolist()))
+                elif kind == "accumulate_value_over_samples":
+                    accum[name] = v if name not in accum else accum[name] + v
+                else:
+                    raise ValueError(f"unknown metric type {kind}")
+        for name, dt in zip(self.metric_names, self.metric_dtypes):
+            d = self._wdir(name)
+            if name in accum:
+                np.save(os.path.join(d, "accumulate.npy"), np.asarray(accum[name]))
+            else:
+                arr = np.asarray(results[name], dtype=np.int64).reshape(-1, 2)
+                np.save(os.path.join(d, "sample_to_metric.npy"), arr)
+
+    def run_reduce(self):
+        for name, kind, dt in zip(self.metric_names, self.metric_types, self.metric_dtypes):
+            base = os.path.join(self.save_path, name)
+            if kind == "accumulate_value_over_samples":
+                total = None
+                for w in range(self.num_workers):
+                    a = np.load(os.path.join(base, f"worker{w}", "accumulate.npy"))
+                    total = a if total is None else total + a
+                b = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_metric_value.bin"), dtype=dt)
+                b.add_item(np.asarray(total).reshape(-1))
+                b.end_document()
+                b.finalize(os.path.join(base, f"{name}_metric_value.idx"))
+                continue
+            pairs = np.concatenate([np.load(os.path.join(base, f"worker{w}", "sample_to_metric.npy"))
+                                    for w in range(self.num_workers)])
+            pairs = pairs[np.argsort(pairs[:, 0], kind="stable")]
+            s2m = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_sample_to_metric.bin"), dtype=dt)
+            for v in pairs[:, 1]:
+                s2m.add_item(np.asarray([v]))
+            s2m.end_document()
+            s2m.finalize(os.path.join(base, f"{name}_sample_to_metric.idx"))
+            groups = defaultdict(list)
+            for i, v in pairs:
+                groups[int(v)].append(int(i))
+            values = sorted(groups)
+            i2s = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_sample.bin"), dtype=np.int64)
+            i2m = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_metric.bin"), dtype=dt)
+            for v in values:
+                i2s.add_item(np.asarray(groups[v], dtype=np.int64))
+                i2m.add_item(np.asarray([v]))
+            i2s.end_document(), i2m.end_document()
+            i2s.finalize(os.path.join(base, f"{name}_index_to_sample.idx"))
+            i2m.finalize(os.path.join(base, f"{name}_index_to_metric.idx"))
+            # percentile merged view used by percentile-based difficulty
+            merged = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_sample_percentile_merged.bin"),
+                                               dtype=np.int64)
+            order = np.concatenate([np.asarray(groups[v], dtype=np.int64) for v in values]) if values else np.zeros(0, np.int64)
+            for chunk in np.array_split(order, 100):
+                merged.add_item(chunk)
+            merged.end_document()
+            merged.finalize(os.path.join(base, f"{name}_index_to_sample_percentile_merged.idx"))
+
+    def run_map_reduce(self, comm_group=None):
+        self.run_map()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier(group=comm_group)
+        if self.worker_id == 0:
+            self.run_reduce()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier(group=comm_group)
+
+
+class DistributedDataAnalyzer(DataAnalyzer):
+    """One worker per rank of the process group (reference :455): map locally, rank 0 reduces."""
+
+    def __init__(self, dataset, num_workers=1, num_threads=1, worker_id=0, batch_size=1, metric_names=(),
+                 metric_functions=(), metric_types=(), save_path="./", collate_fn=None, device="cpu", comm_group=None,
+                 sample_indices=None, metric_dtypes=()):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            num_workers = torch.distributed.get_world_size(comm_group)
+            worker_id = torch.distributed.get_rank(comm_group)
+        super().__init__(dataset, num_workers=num_workers, worker_id=worker_id, batch_size=batch_size,
+                         metric_names=metric_names, metric_functions=metric_functions, metric_types=metric_types,
+                         metric_dtypes=metric_dtypes or [np.int64] * len(metric_names), save_path=save_path,
+                         collate_fn=collate_fn, sample_indices=sample_indices)
+        self.comm_group = comm_group
+
+    def run_map_reduce(self):
+        super().run_map_reduce(self.comm_group)
