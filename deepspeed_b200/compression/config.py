@@ -1,0 +1,58 @@
+"""Normalise the ``compression_training`` block: every technique gets ``shared_parameters`` (with defaults) and
+``different_groups`` (each with ``params`` / ``modules`` / ``related_modules``).  Reference ``compression/config.py``."""
+import copy
+
+from . import constants as C
+
+_SHARED_DEFAULTS = {
+    C.WEIGHT_QUANTIZATION: {C.TECHNIQUE_ENABLED: False, C.WEIGHT_QUANTIZE_KERNEL: False, C.TECHNIQUE_SCHEDULE_OFFSET: 0,
+                            C.WEIGHT_QUANTIZE_GROUPS: 1, C.WEIGHT_QUANTIZE_VERBOSE: False,
+                            C.WEIGHT_QUANTIZE_TYPE: C.WEIGHT_QUANTIZE_SYMMETRIC,
+                            C.WEIGHT_QUANTIZE_IN_FORWARD_ENABLED: False,
+                            C.WEIGHT_QUANTIZE_ROUNDING: C.WEIGHT_QUANTIZE_NEAREST_ROUNDING,
+                            C.WEIGHT_QUANTIZE_FP16_MIXED_QUANTIZE: {C.TECHNIQUE_ENABLED: False,
+                                                                    C.WEIGHT_QUANTIZE_CHANGE_RATIO: 0.001}},
+    C.ACTIVATION_QUANTIZATION: {C.TECHNIQUE_ENABLED: False, C.ACTIVATION_QUANTIZE_TYPE: "symmetric",
+                                C.ACTIVATION_QUANTIZE_RANGE: C.ACTIVATION_QUANTIZE_RANGE_DYNAMIC,
+                                C.TECHNIQUE_SCHEDULE_OFFSET: 1000},
+    C.SPARSE_PRUNING: {C.TECHNIQUE_ENABLED: False, C.SPARSE_PRUNING_METHOD: C.SPARSE_PRUNING_METHOD_L1,
+                       C.TECHNIQUE_SCHEDULE_OFFSET: 1000},
+    C.ROW_PRUNING: {C.TECHNIQUE_ENABLED: False, C.ROW_PRUNING_METHOD: "l1", C.TECHNIQUE_SCHEDULE_OFFSET: 1000},
+    C.HEAD_PRUNING: {C.TECHNIQUE_ENABLED: False, C.HEAD_PRUNING_METHOD: "topk", C.TECHNIQUE_SCHEDULE_OFFSET: 1000},
+    C.CHANNEL_PRUNING: {C.TECHNIQUE_ENABLED: False, C.CHANNEL_PRUNING_METHOD: "l1", C.TECHNIQUE_SCHEDULE_OFFSET: 1000},
+}
+
+
+def _technique(block, name):
+    sub = copy.deepcopy(block.get(name, {}))
+    shared = copy.deepcopy(_SHARED_DEFAULTS[name])
+    shared.update(sub.get(C.SHARED_PARAMETERS, {}))
+    if name == C.HEAD_PRUNING and shared[C.TECHNIQUE_ENABLED]:
+        assert C.HEAD_PRUNING_NUM_HEADS in shared, "head_pruning requires shared_parameters.num_heads"
+    groups = {}
+    for gname, g in sub.get(C.DIFFERENT_GROUPS, {}).items():
+        assert C.DIFFERENT_GROUPS_PARAMETERS in g, f"group {gname} of {name} needs 'params'"
+        groups[gname] = {
+            C.DIFFERENT_GROUPS_PARAMETERS: dict(g[C.DIFFERENT_GROUPS_PARAMETERS]),
+            C.DIFFERENT_GROUPS_MODULE_SCOPE: g.get(C.DIFFERENT_GROUPS_MODULE_SCOPE, [C.DIFFERENT_GROUPS_MODULE_SCOPE_DEFAULT]),
+            C.DIFFERENT_GROUPS_RELATED_MODULE_SCOPE: g.get(C.DIFFERENT_GROUPS_RELATED_MODULE_SCOPE,
+                                                           C.DIFFERENT_GROUPS_RELATED_MODULE_SCOPE_DEFAULT),
+        }
+        p = groups[gname][C.DIFFERENT_GROUPS_PARAMETERS]
+        if name == C.WEIGHT_QUANTIZATION:
+            assert C.WEIGHT_QUANTIZE_START_BITS in p and C.WEIGHT_QUANTIZE_TARGET_BITS in p
+            p.setdefault(C.WEIGHT_QUANTIZATION_PERIOD, 1)
+        elif name == C.ACTIVATION_QUANTIZATION:
+            assert C.ACTIVATION_QUANTIZE_BITS in p
+        else:
+            assert "dense_ratio" in p, f"{name} group {gname} requires dense_ratio"
+    return {C.SHARED_PARAMETERS: shared, C.DIFFERENT_GROUPS: groups}
+
+
+def get_compression_config(param_dict):
+    block = param_dict.get(C.COMPRESSION_TRAINING, {})
+    out = {t: _technique(block, t) for t in C.TECHNIQUES}
+    lr = copy.deepcopy(block.get(C.LAYER_REDUCTION, {}))
+    lr.setdefault(C.LAYER_REDUCTION_ENABLED, False)
+    out[C.LAYER_REDUCTION] = lr
+    return out
