@@ -274,60 +274,71 @@ class InferenceEngine(nn.Module):
             if "num_beams" in kwargs and kwargs["num_beams"] > 1 and self._config.replace_with_kernel_inject:
                 raise NotImplementedError("beam search is not supported with kernel injection")
             return self.module.generate(*inputs, **kwargs)
-        input_ids = kwargs.get("input_ids", inputs[0] if inputs else None)
-        if kwargs.get("num_beams", 1) > 1:
-            raise NotImplementedError("DeepSpeed-B200 kernel-injected generate supports greedy / sampling only")
-        max_new = kwargs.get("max_new_tokens")
-        if max_new is None:
-            max_new = kwargs.get("max_length", input_ids.shape[1] + 20) - input_ids.shape[1]
-        if input_ids.shape[1] + max_new > self._config.max_out_tokens:
-            raise RuntimeError(f"Input with size {input_ids.shape[1]} + {max_new} new tokens exceeds max_out_tokens "
-                               f"{self._config.max_out_tokens}; raise `max_tokens` in the inference config")
-        do_sample = kwargs.get("do_sample", False)
-        temperature, top_k, top_p = kwargs.get("temperature", 1.0), kwargs.get("top_k", 0), kwargs.get("top_p", 1.0)
-        eos = kwargs.get("eos_token_id", getattr(getattr(self.module, "config", None), "eos_token_id", None))
-        eos = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
-        pad = kwargs.get("pad_token_id", next(iter(eos)) if eos else 0)
-        B = input_ids.shape[0]
-        mask = kwargs.get("attention_mask")
-        uids = self._next_uids(B)
-        seqs = [input_ids[b][mask[b].bool()] if mask is not None else input_ids[b] for b in range(B)]
-        logits = self._ragged.put(uids, [s.cpu() for s in seqs])
-        done = [False] * B
-        new_tokens = [[] for _ in range(B)]
-        for step in range(max_new):
-            nxt = _sample(logits, do_sample, temperature, top_k, top_p)
-            live_u, live_t = [], []
-            nxt_host = nxt.tolist()
-            k = 0
-            for b in range(B):
-                if done[b]:
-                    continue
-                tok = nxt_host[k]
-                k += 1
-                new_tokens[b].append(tok)
-                if tok in eos:
-                    done[b] = True
-                else:
-                    live_u.append(uids[b])
-                    live_t.append(torch.tensor([tok]))
-            if not live_u or step == max_new - 1:
-                break
-            logits = self._ragged.put(live_u, live_t)
-        for u in uids:
-            self._ragged.flush(u)
-        L = max(len(t) for t in new_tokens)
-        out = torch.full((B, input_ids.shape[1] + L), pad, dtype=input_ids.dtype, device=input_ids.device)
-        out[:, :input_ids.shape[1]] = input_ids
-        for b in range(B):
-            out[b, input_ids.shape[1]:input_ids.shape[1] + len(new_tokens[b])] = torch.tensor(new_tokens[b],
-                                                                                             dtype=input_ids.dtype)
+        input_ids = kwargs.pop("input_ids", inputs[0] if inputs else None)
+        eos_default = getattr(getattr(self.module, "config", None), "eos_token_id", None)
+        out, self._uid = ragged_generate(self._ragged, input_ids, self._uid, self._config.max_out_tokens,
+                                         eos_default=eos_default, **kwargs)
         return out
 
     def destroy(self):
         self._ragged = None
         self._cuda_graphs = None
         InferenceEngine.inference_mp_group = None
+
+
+
+@torch.no_grad()
+def ragged_generate(ragged, input_ids, uid0, max_out_tokens, eos_default=None, **kwargs):
+    """Greedy / sampling generation on a ragged engine; returns (tokens [B, S+new], next free uid)."""
+    if kwargs.get("num_beams", 1) > 1:
+        raise NotImplementedError("DeepSpeed-B200 kernel-injected generate supports greedy / sampling only")
+    max_new = kwargs.get("max_new_tokens")
+    if max_new is None:
+        max_new = kwargs.get("max_length", input_ids.shape[1] + 20) - input_ids.shape[1]
+    if input_ids.shape[1] + max_new > max_out_tokens:
+        raise RuntimeError(f"Input with size {input_ids.shape[1]} + {max_new} new tokens exceeds max_out_tokens "
+                           f"{max_out_tokens}; raise `max_tokens` in the inference config")
+    do_sample = kwargs.get("do_sample", False)
+    temperature, top_k, top_p = kwargs.get("temperature", 1.0), kwargs.get("top_k", 0), kwargs.get("top_p", 1.0)
+    eos = kwargs.get("eos_token_id", eos_default)
+    eos = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
+    pad = kwargs.get("pad_token_id", next(iter(eos)) if eos else 0)
+    B = input_ids.shape[0]
+    mask = kwargs.get("attention_mask")
+    uids = list(range(uid0, uid0 + B))
+    seqs = [input_ids[b][mask[b].bool()] if mask is not None else input_ids[b] for b in range(B)]
+    logits = ragged.put(uids, [s.cpu() for s in seqs])
+    done = [False] * B
+    new_tokens = [[] for _ in range(B)]
+    for step in range(max_new):
+        nxt = _sample(logits, do_sample, temperature, top_k, top_p)
+        live_u, live_t = [], []
+        nxt_host = nxt.tolist()
+        k = 0
+        for b in range(B):
+            if done[b]:
+                continue
+            tok = nxt_host[k]
+            k += 1
+            new_tokens[b].append(tok)
+            if tok in eos:
+                done[b] = True
+            else:
+                live_u.append(uids[b])
+                live_t.append(torch.tensor([tok]))
+        if not live_u or step == max_new - 1:
+            break
+        logits = ragged.put(live_u, live_t)
+    for u in uids:
+        ragged.flush(u)
+    L = max(len(t) for t in new_tokens)
+    out = torch.full((B, input_ids.shape[1] + L), pad, dtype=input_ids.dtype, device=input_ids.device)
+    out[:, :input_ids.shape[1]] = input_ids
+    for b in range(B):
+        out[b, input_ids.shape[1]:input_ids.shape[1] + len(new_tokens[b])] = torch.tensor(new_tokens[b],
+                                                                                         dtype=input_ids.dtype)
+    return out, uid0 + B
+
 
 
 def _policy_names(injection_dict):
