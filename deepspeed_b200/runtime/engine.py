@@ -272,8 +272,51 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         log_dist(f"DeepSpeed LR Scheduler = {type(self.lr_scheduler).__name__ if self.lr_scheduler else None}",
                  ranks=[0])
 
+    def _autotuning_setup(self):
+        """Autotuning experiments run the user script unchanged; the engine measures and exits
+        (reference ``engine.py`` autotuning hooks: model-info dump, ``metric_path`` write, early exit)."""
+        at = self._config.autotuning_config or {}
+        self._at = at if at.get("enabled") else None
+        if not self._at:
+            return
+        import json
+        info = {"num_params": sum(getattr(p, "ds_numel", p.numel()) for p in self.module.parameters()),
+                "trainable_num_params": sum(getattr(p, "ds_numel", p.numel()) for p in self.module.parameters()
+                                            if p.requires_grad)}
+        if self.global_rank == 0 and at.get("model_info_path"):
+            with open(at["model_info_path"], "w") as f:
+                json.dump(info, f)
+        if (at.get("model_info") or {}).get("profile"):
+            dist.barrier()
+            raise SystemExit(0)
+        self._at_t0 = None
+
+    def _autotuning_step(self):
+        at = self._at
+        if not at:
+            return
+        import json
+        import time
+        start, end = int(at.get("start_profile_step", 3)), int(at.get("end_profile_step", 5))
+        if self.global_steps == start:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            self._at_t0 = time.time()
+        elif self.global_steps >= end and self._at_t0 is not None:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            dt = (time.time() - self._at_t0) / max(1, end - start)
+            m = {"latency": dt * 1e3, "throughput": self.train_batch_size() / dt, "flops": 0.0,
+                 "max_mem_gb": (torch.cuda.max_memory_allocated() / 2**30) if torch.cuda.is_available() else 0.0}
+            if self.global_rank == 0 and at.get("metric_path"):
+                with open(at["metric_path"], "w") as f:
+                    json.dump(m, f)
+            dist.barrier()
+            raise SystemExit(0)
+
     def _configure_aux(self):
         c = self._config
+        self._autotuning_setup()
         self.flops_profiler = None
         if c.flops_profiler_config.enabled:
             from deepspeed_b200.profiling.flops_profiler import FlopsProfiler
@@ -543,6 +586,8 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         self.tput_timer.stop(global_step=boundary)
         self.timers(STEP_MICRO_TIMER).stop()
         self.timers(STEP_GLOBAL_TIMER).stop()
+        if boundary and getattr(self, "_at", None):
+            self._autotuning_step()
         if boundary and self.wall_clock_breakdown() and self.global_steps % self.steps_per_print() == 0:
             self.timers.log([FORWARD_GLOBAL_TIMER, BACKWARD_GLOBAL_TIMER, STEP_GLOBAL_TIMER],
                             memory_breakdown=self.memory_breakdown())
