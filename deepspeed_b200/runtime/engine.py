@@ -226,10 +226,10 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
                 mg = create_mics_comm_groups(mics, self.seq_data_parallel_group)
                 self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=mg.param_shard_group,
                                                       replica_group=mg.param_repli_group, **common)
-                self.optimizer.grad_allreduce_enabled = lambda: self.enable_backward_allreduce
+                self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
                 return
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
-            self.optimizer.grad_allreduce_enabled = lambda: self.enable_backward_allreduce
+            self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
             return
         # MoE: dense parameters over the DP group, every expert family over its expert-data-parallel group
         from deepspeed_b200.runtime.zero.multi import ZeroOptimizerGroup
@@ -271,6 +271,12 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             self.lr_scheduler = cls(self.optimizer, **(c.scheduler_params or {}))
         log_dist(f"DeepSpeed LR Scheduler = {type(self.lr_scheduler).__name__ if self.lr_scheduler else None}",
                  ranks=[0])
+
+    def _dense_grad_allreduce_enabled(self):
+        # the pipeline engine keeps its own switch (1-bit optimizers toggle whichever applies)
+        if hasattr(self, "pipeline_enable_backward_allreduce"):
+            return self.pipeline_enable_backward_allreduce
+        return self.enable_backward_allreduce
 
     def _autotuning_setup(self):
         """Autotuning experiments run the user script unchanged; the engine measures and exits
