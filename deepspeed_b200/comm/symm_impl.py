@@ -239,6 +239,26 @@ class SymmContext:
                                           CH_AG, ctypes.c_uint32(0), 0, self.ag_ctas, N.stream())
         N.check(rc, "symm_all_gather")
 
+    def all_gather_matmul(self, a, full, shard, shard_numel, w_offset, n_rows, k, chunk_bytes=1 << 20, comm_ctas=16):
+        """``a [M,K] @ W^T`` where ``W [n_rows, K]`` lives ``w_offset`` elements into the gathered unit buffer
+        ``full`` — ONE kernel that pulls every rank's shard over NVLink (trailing ``comm_ctas`` CTAs, chunk flags
+        with release/acquire) while the tcgen05 tiles of rows that already arrived are being multiplied.
+        Returns ``(out [M, n_rows])``; on return-to-stream the whole unit is resident in ``full``."""
+        from deepspeed_b200.ops.kernels import gemm_sm100
+        shards, _ = self._peers(shard)
+        nbytes = shard_numel * shard.element_size()
+        while nbytes % chunk_bytes:
+            chunk_bytes //= 2
+        n_chunks = (nbytes // chunk_bytes) * self.world
+        if getattr(self, "_agmm_flags", None) is None or self._agmm_flags.numel() < n_chunks:
+            self._agmm_flags = torch.zeros(max(n_chunks, 4096), dtype=torch.int32, device="cuda")
+            self._agmm_epoch = 0
+        self._agmm_epoch = (self._agmm_epoch + 1) & 0x7fffffff or 1
+        w_view = full[w_offset:w_offset + n_rows * k].view(n_rows, k)
+        return gemm_sm100.matmul_nt_allgather(a, w_view, full, [int(x or 0) for x in shards], self._agmm_flags, nbytes,
+                                              chunk_bytes, w_offset * full.element_size(), self.world, self.rank,
+                                              self._agmm_epoch, comm_ctas=comm_ctas)
+
     def _sumsq_buf(self):
         if self._partials is None:
             self._partials = torch.zeros(max(self.ctas, 256), dtype=torch.float32, device="cuda")

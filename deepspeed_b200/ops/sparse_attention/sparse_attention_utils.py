@@ -74,3 +74,20 @@ class SparseAttentionUtils:
     @staticmethod
     def unpad_sequence_output(pad_len, sequence_output):
         return sequence_output[:, :-pad_len] if pad_len > 0 else sequence_output
+
+
+def sdd_segment(layout, max_width=4):
+    """Cover each head's non-zero blocks with maximal square segments (native ``dsb_sdd_segment``; reference
+    ``csrc/sparse_attention/utils.cpp`` N15).  Returns int32 rows ``[head, row, col, width]``."""
+    import ctypes
+    from deepspeed_b200.ops import native as N
+    lay = layout.to(torch.int32).contiguous()
+    H, M, Nn = lay.shape
+    cap = int(lay.sum().item()) + 1
+    out = torch.empty(cap, 4, dtype=torch.int32)
+    lib = N.cpu()
+    lib.dsb_sdd_segment.restype = ctypes.c_int64
+    n = lib.dsb_sdd_segment(ctypes.c_void_p(lay.data_ptr()), H, M, Nn, max_width, ctypes.c_void_p(out.data_ptr()),
+                            ctypes.c_int64(cap))
+    assert n >= 0
+    return out[:n]

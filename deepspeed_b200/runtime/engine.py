@@ -332,6 +332,35 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             from deepspeed_b200.runtime.progressive_layer_drop import ProgressiveLayerDrop
             self.progressive_layer_drop = ProgressiveLayerDrop(theta=c.pld_params.get("theta", 0.5),
                                                                gamma=c.pld_params.get("gamma", 0.001))
+        self.random_ltd_scheduler = None
+        self.compression_scheduler = None
+        self.data_post_process_func = None
+        de = c.data_efficiency_config if c.data_efficiency_enabled else None
+        if de:
+            from deepspeed_b200.runtime.data_pipeline.config import get_data_efficiency_config
+            from deepspeed_b200.runtime.data_pipeline import constants as DC
+            self._de = get_data_efficiency_config({"data_efficiency": de})
+            ltd = self._de[DC.DATA_ROUTING][DC.RANDOM_LTD]
+            if self._de[DC.DATA_ROUTING][DC.DATA_ROUTING_ENABLED] and ltd.get(DC.RANDOM_LTD_ENABLED):
+                from deepspeed_b200.runtime.data_pipeline.data_routing import RandomLayerTokenDrop, RandomLTDScheduler
+                ltd = dict(ltd)
+                ltd.setdefault(DC.RANDOM_LTD_GLOBAL_BATCH_SIZE, self.train_batch_size())
+                ltd.setdefault(DC.RANDOM_LTD_MICRO_BATCH_SIZE, self.train_micro_batch_size_per_gpu())
+                self.random_ltd_scheduler = RandomLTDScheduler(ltd)
+                lid = 0
+                for m in self.module.modules():
+                    if isinstance(m, RandomLayerTokenDrop):
+                        m.init_config(ltd, self.random_ltd_scheduler, lid)
+                        lid += 1
+        else:
+            self._de = None
+        if (c._param_dict.get("compression_training") or {}):
+            from deepspeed_b200.compression import compression_scheduler
+            from deepspeed_b200.compression.config import get_compression_config
+            cc = get_compression_config(c._param_dict)
+            if any(cc[t]["shared_parameters"]["enabled"] for t in cc if t != "layer_reduction"):
+                self.compression_scheduler = compression_scheduler(self.module, cc)
+                self.compression_scheduler.step(step_zero_check=True)
         self.curriculum_scheduler_legacy = None
         if c.curriculum_enabled_legacy:
             from deepspeed_b200.runtime.data_pipeline.curriculum_scheduler import CurriculumScheduler
@@ -452,6 +481,15 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             batch_size = self.train_micro_batch_size_per_gpu()
         if collate_fn is None:
             collate_fn = self.collate_fn
+        if data_sampler is None and route == "train" and getattr(self, "_de", None):
+            from deepspeed_b200.runtime.data_pipeline import constants as DC
+            ds_cfg = self._de[DC.DATA_SAMPLING]
+            if ds_cfg.get(DC.DATA_SAMPLING_ENABLED):
+                from deepspeed_b200.runtime.data_pipeline.data_sampling import DeepSpeedDataSampler
+                data_sampler = DeepSpeedDataSampler(self._de, len(dataset), self.train_micro_batch_size_per_gpu(),
+                                                    groups._get_data_parallel_rank(), self.dp_world_size,
+                                                    self.seq_data_parallel_group, self.gradient_accumulation_steps(),
+                                                    self.global_rank, drop_last=self._config.dataloader_drop_last)
         return DeepSpeedDataLoader(dataset=dataset, batch_size=batch_size, pin_memory=pin_memory,
                                    collate_fn=collate_fn, local_rank=self.local_rank, tput_timer=self.tput_timer,
                                    num_local_io_workers=num_local_io_workers, data_sampler=data_sampler,
@@ -582,6 +620,10 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             if self.progressive_layer_drop is not None:
                 self.progressive_layer_drop.update_state(self.global_steps)
             self._take_model_step(lr_kwargs)
+            if self.random_ltd_scheduler is not None:
+                self.random_ltd_scheduler.update_seq(self.global_steps)
+            if self.compression_scheduler is not None:
+                self.compression_scheduler.step()
             if self.monitor.enabled and self.global_rank == 0:
                 ev = [("Train/Samples/lr", self.get_lr()[0], self.global_samples)]
                 if getattr(self, "_last_loss_for_monitor", None) is not None:
@@ -657,6 +699,54 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
 
     def get_sequence_parallel_group(self):
         return self.seq_parallel_group
+
+    # ---- reference API surface kept for drop-in compatibility ------------------------------------------------
+    def allreduce_gradients(self, bucket_size=None):
+        """Gradients are reduced unit-by-unit inside backward by the sharded optimizer; an explicit call only has
+        to drain the reduction stream (reference ``engine.py:2048``)."""
+        if self.optimizer is not None and getattr(self.optimizer, "rs_stream", None) is not None:
+            torch.cuda.current_stream().wait_stream(self.optimizer.rs_stream)
+
+    def sparse_allreduce(self, sparse_tensor, dp_group=None):
+        from deepspeed_b200.runtime.sparse_tensor import sparse_allreduce
+        return sparse_allreduce(sparse_tensor, dp_group or self.seq_data_parallel_group)
+
+    def set_custom_curriculum_learning_schedule(self, schedule_func_dict):
+        if self.training_dataloader is not None and getattr(self.training_dataloader, "data_sampler", None) is not None \
+                and hasattr(self.training_dataloader.data_sampler, "set_custom_curriculum_learning_schedule"):
+            self.training_dataloader.data_sampler.set_custom_curriculum_learning_schedule(schedule_func_dict)
+        elif self.curriculum_scheduler_legacy is not None:
+            fn = schedule_func_dict if callable(schedule_func_dict) else next(iter(schedule_func_dict.values()))
+            self.curriculum_scheduler_legacy.set_custom_get_difficulty(fn)
+
+    def set_data_post_process_func(self, post_process_func):
+        self.data_post_process_func = post_process_func
+        if self.training_dataloader is not None:
+            self.training_dataloader.post_process_func = post_process_func
+
+    def get_data_parallel_rank(self):
+        return groups._get_data_parallel_rank()
+
+    def empty_partition_cache(self):
+        """Release every transiently gathered ZeRO-3 unit (reference ``engine.py`` / ``stage3.py``)."""
+        zo = self.optimizer
+        if zo is not None and getattr(zo, "transient", False):
+            for rt in zo.rts:
+                zo.release_unit(rt)
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+    def dump_state(self):
+        if self.global_rank != 0:
+            return
+        c = self._config
+        for k in ("train_batch_size", "train_micro_batch_size_per_gpu", "gradient_accumulation_steps", "zero_config",
+                  "optimizer_name", "optimizer_params", "scheduler_name", "bfloat16_enabled", "fp16_enabled",
+                  "gradient_clipping"):
+            logger.info(f"  {k} {'.' * (40 - len(k))} {getattr(c, k, None)}")
+
+    def random_ltd_initialize(self):
+        return self.random_ltd_scheduler
 
     def destroy(self):
         if self.optimizer is not None and hasattr(self.optimizer, "destroy"):

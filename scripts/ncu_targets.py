@@ -46,5 +46,24 @@ elif which == "rope":
     for _ in range(5):
         flush.zero_()
         T.rope_qk_inplace(qkv, 32, 8, 128, table, None, 4096)
+elif which == "gemm":
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    a = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16)
+    b = torch.randn(14336 * 2, 4096, device=d, dtype=torch.bfloat16)
+    for _ in range(3):
+        flush.zero_()
+        gemm_sm100.matmul_nt(a, b)
+elif which == "paged":
+    from deepspeed_b200.ops.kernels import ragged_ops as R
+    hq, hkv, dd, bs, seqs, ctx = 32, 8, 128, 128, 64, 2048
+    qkv = torch.randn(seqs, (hq + 2 * hkv) * dd, device=d, dtype=torch.bfloat16)
+    nb = ctx // bs
+    cache = torch.randn(seqs * nb, bs, 2, hkv, dd, device=d, dtype=torch.bfloat16)
+    bt = torch.arange(seqs * nb, device=d, dtype=torch.int32).view(seqs, nb)
+    seq_of = torch.arange(seqs, device=d, dtype=torch.int32)
+    pos_of = torch.full((seqs, ), ctx - 1, device=d, dtype=torch.int32)
+    for _ in range(3):
+        flush.zero_()
+        R.paged_attention(qkv, cache, seq_of, pos_of, bt, hq, hkv, dd, bs)
 torch.cuda.synchronize()
 print("done", which)

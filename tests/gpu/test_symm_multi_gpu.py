@@ -104,3 +104,56 @@ def _engine_parity(fused):
 def test_zero3_symm_matches_nccl_2gpu(fused):
     _need(2)
     run_distributed(_engine_parity, 2, args=(fused, ), backend="nccl")
+
+
+def _ag_gemm():
+    import torch.distributed as dist
+    from deepspeed_b200.comm import symm
+    r, w = dist.get_rank(), dist.get_world_size()
+    assert symm.is_supported(None, explicit=True)
+    ctx = symm.get_context(None)
+    K, rows_a, rows_b = 1024, 2048, 1024          # unit = [W_a (2048xK) | W_b (1024xK)], sharded over ranks
+    S = (rows_a + rows_b) * K // w
+    torch.manual_seed(5)
+    unit = torch.randn((rows_a + rows_b) * K, device="cuda").bfloat16()     # same on every rank (same seed)
+    shard = ctx.alloc(S, torch.bfloat16)
+    full = ctx.alloc(S * w, torch.bfloat16)
+    shard.copy_(unit[r * S:(r + 1) * S])
+    x = torch.randn(512, K, device="cuda", dtype=torch.bfloat16)
+    for it in range(3):                              # epochs advance; stale data must never be consumed
+        full.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        y = ctx.all_gather_matmul(x, full, shard, S, rows_a * K, rows_b, K)   # multiply by W_b while gathering the unit
+        torch.cuda.synchronize()
+        assert torch.equal(full, unit), "fused kernel did not leave the whole unit resident"
+        ref = x.float() @ unit[rows_a * K:].view(rows_b, K).float().t()
+        assert (y.float() - ref).abs().max() < 0.05 * ref.abs().max() + 0.5
+        dist.barrier()
+    # timing vs all-gather followed by the same GEMM
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    def fused():
+        return ctx.all_gather_matmul(x, full, shard, S, rows_a * K, rows_b, K)
+    def split():
+        ctx.all_gather(full, shard, S)
+        return gemm_sm100.matmul_nt(x, full[rows_a * K:].view(rows_b, K))
+    out = {}
+    for name, fn in (("fused", fused), ("split", split)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / 10], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = t.item()
+    if r == 0:
+        print(f"AG+GEMM fused {out['fused']:.3f} ms vs split {out['split']:.3f} ms (max over ranks)")
+
+
+def test_fused_allgather_gemm_2gpu():
+    _need(2)
+    run_distributed(_ag_gemm, 2, backend="nccl")
