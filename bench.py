@@ -218,6 +218,20 @@ def run_b200(args):
     launches = native.launch_count - l0
     t_e2e = timed_loop(torch, ds.comm, world, args.steps, step_e2e)
     clocks = sampler.stop() if rank == 0 else None
+    # exposed (non-overlapped) communication: 2 extra, untimed-for-throughput steps with every compute-stream
+    # wait on a collective bracketed by CUDA events (the bracket holds no kernels => elapsed == stall)
+    exposed = None
+    if world > 1 and hasattr(engine.optimizer, "measure_exposed"):
+        engine.optimizer.measure_exposed(True)
+        for i in range(2):
+            step_dev(i)
+        ex = engine.optimizer.exposed_ms()
+        engine.optimizer.measure_exposed(False)
+        t = torch.tensor([ex["all_gather"] / 2, ex["reduce"] / 2], device="cuda")
+        ds.comm.all_reduce(t, op=ds.comm.ReduceOp.MAX)
+        exposed = {"all_gather_ms_per_step": float(t[0]), "reduce_scatter_adam_ms_per_step": float(t[1]),
+                   "total_ms_per_step": float(t[0] + t[1]), "how": "CUDA-event brackets around compute-stream waits, "
+                   "max over ranks, mean of 2 steps"}
     tokens_per_step = B * S * world
     if rank == 0:
         val = tokens_per_step * args.steps / t_dev
@@ -268,6 +282,7 @@ def run_b200(args):
             },
             "gpu_launches": launches,
             "max_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
+            "exposed_comm": exposed,
         }
         print(json.dumps(out), flush=True)
 

@@ -509,7 +509,7 @@ class ZeroShardedOptimizer:
             # previous owner still accumulating (out-of-order graph): fall back to a private buffer
             slot = _Slot(torch.empty(self.max_full, dtype=self.comm_dtype, device=self.device))
         if slot.free_event is not None and self.on_cuda:
-            torch.cuda.current_stream().wait_event(slot.free_event)
+            self._stall_wait("reduce", lambda: torch.cuda.current_stream().wait_event(slot.free_event))
         slot.owner = rt
         rt.grad_slot = slot
         rt.grad_full = slot.buf[:rt.u.full_numel]
@@ -566,13 +566,42 @@ class ZeroShardedOptimizer:
             self._launch_gather(rt)
         if rt.state == INFLIGHT:
             if rt.gather_event is not None and self.on_cuda:
-                torch.cuda.current_stream().wait_event(rt.gather_event)
+                self._stall_wait("all_gather", lambda: torch.cuda.current_stream().wait_event(rt.gather_event))
             rt.state = GATHERED
         rt.consumed = True
         if prefetch and self.prefetch_depth > 0:
             for nxt in self._upcoming(rt, forward):
                 if nxt.state == NOT_GATHERED and not nxt.u.persistent and (forward or not nxt.skip_bwd_fetch):
                     self._launch_gather(nxt)
+
+    # ---- exposed-communication accounting (bench / profiling aid) -----------------------------------
+    def measure_exposed(self, on=True):
+        """While on, every point where the COMPUTE stream has to wait for a collective (a gather that did not
+        finish in time, the reduction stream at the end of backward, a buffer still in use by a reduce) is bracketed
+        with CUDA events; the bracket contains no kernels, so its elapsed time is exactly the stall."""
+        self._exposed = [] if on else None
+
+    def _stall_wait(self, what, wait_fn):
+        if getattr(self, "_exposed", None) is None or not self.on_cuda:
+            wait_fn()
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        wait_fn()
+        b.record()
+        self._exposed.append((what, a, b))
+
+    def exposed_ms(self):
+        """-> {"all_gather": ms, "reduce": ms, "total": ms} since measure_exposed(True); synchronises."""
+        if not getattr(self, "_exposed", None):
+            return {"all_gather": 0.0, "reduce": 0.0, "total": 0.0}
+        torch.cuda.synchronize()
+        out = {"all_gather": 0.0, "reduce": 0.0}
+        for what, a, b in self._exposed:
+            out[what] += a.elapsed_time(b)
+        out["total"] = out["all_gather"] + out["reduce"]
+        self._exposed = []
+        return out
 
     def _upcoming(self, rt, forward):
         order = self._trace if (self._trace_done and self._trace) else [u.index for u in self.units]
@@ -949,7 +978,7 @@ class ZeroShardedOptimizer:
         flag (already summed over its own sharding group).  Split from :meth:`finish_step` so that several
         instances (dense + expert parameter domains) can combine their norms before clipping."""
         if self.on_cuda and self.rs_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.rs_stream)
+            self._stall_wait("reduce", lambda: torch.cuda.current_stream().wait_stream(self.rs_stream))
         self.overflow = False
         if self.needs_norm():
             self.stats.reset()
