@@ -89,6 +89,180 @@ paged_attention_kernel(const T* __restrict__ q, const T* __restrict__ cache, T* 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Decode-optimised variant ("flash decoding" shape): one CTA per (token, KV head, KV split).
+//   * GQA sharing: the REP = hq/hkv query heads that read the same KV head are processed together, so K/V bytes are
+//     fetched once per KV head instead of once per query head.
+//   * memory-level parallelism: every lane keeps U=4 independent 16-byte K loads and 4 V loads in flight; a warp
+//     load instruction covers 32/LPK whole keys (LPK = D/8 lanes per key), i.e. 512 contiguous-row bytes.
+//   * split-KV: long contexts are cut into `nsplit` ranges so small decode batches still fill 148 SMs; partial
+//     (m, l, acc) triples go to a workspace and a tiny merge kernel combines them.
+// The per-key dot product is reduced over only LPK lanes; the running max is shared by the whole warp so all lanes
+// rescale identically.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T, int D, int REP>
+__global__ void __launch_bounds__(128)
+paged_decode_kernel(const T* __restrict__ q, const T* __restrict__ cache, T* __restrict__ out, float* __restrict__ ws_acc,
+                    float* __restrict__ ws_ml, const int32_t* __restrict__ seq_of, const int32_t* __restrict__ pos_of,
+                    const int32_t* __restrict__ block_table, int hq, int hkv, int q_stride, int block_size, int max_blocks,
+                    float scale, int nsplit)
+{
+    constexpr int LPK = D / 8;     // lanes per key (8 bf16/half elements per 16-byte vector)
+    constexpr int KPW = 32 / LPK;  // keys per warp-wide load
+    constexpr int U = 4;
+    constexpr int kW = 4;
+    __shared__ float sm_m[kW][REP], sm_l[kW][REP];
+    __shared__ float sm_acc[kW][REP][D];
+    const int t = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane / LPK, dl = lane % LPK;
+    const int kv_len = pos_of[t] + 1;
+    const int seq = seq_of[t];
+    const int per = (kv_len + nsplit - 1) / nsplit;
+    const int k0 = sp * per;
+    const int k1 = min(kv_len, k0 + per);
+    float qf[REP][8], acc[REP][8], m[REP], l[REP];
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+        const T* qrow = q + static_cast<int64_t>(t) * q_stride + static_cast<int64_t>(kvh * REP + r) * D + dl * 8;
+        Elem<T>::unpack(ld_plain(qrow), qf[r]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            qf[r][e] *= scale;
+            acc[r][e] = 0.f;
+        }
+        m[r] = -INFINITY;
+        l[r] = 0.f;
+    }
+    const int32_t* bt = block_table + static_cast<int64_t>(seq) * max_blocks;
+    const int64_t tok_stride = static_cast<int64_t>(2) * hkv * D;
+    for (int base = k0 + warp * KPW * U; base < k1; base += kW * KPW * U) {
+        Vec16 kx[U], vx[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = base + u * KPW + sub;
+            ok[u] = j < k1;
+            const int jj = ok[u] ? j : k0;  // always a valid address
+            const int blk = bt[jj / block_size];
+            const T* row = cache + (static_cast<int64_t>(blk) * block_size + (jj % block_size)) * tok_stride +
+                           static_cast<int64_t>(kvh) * D + dl * 8;
+            kx[u] = ld_stream(row);
+            vx[u] = ld_stream(row + static_cast<int64_t>(hkv) * D);
+        }
+        float s[REP][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float kf[8];
+            Elem<T>::unpack(kx[u], kf);
+#pragma unroll
+            for (int r = 0; r < REP; ++r) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d = fmaf(qf[r][e], kf[e], d);
+#pragma unroll
+                for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                s[r][u] = ok[u] ? d : -INFINITY;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < REP; ++r) {
+            float mx = s[r][0];
+#pragma unroll
+            for (int u = 1; u < U; ++u) mx = fmaxf(mx, s[r][u]);
+#pragma unroll
+            for (int o = LPK; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float mn = fmaxf(m[r], mx);
+            const float alpha = (m[r] == -INFINITY) ? 0.f : __expf(m[r] - mn);
+            m[r] = mn;
+            l[r] *= alpha;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][e] *= alpha;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float vf[8];
+            Elem<T>::unpack(vx[u], vf);
+#pragma unroll
+            for (int r = 0; r < REP; ++r) {
+                const float p = (ok[u] && m[r] != -INFINITY) ? __expf(s[r][u] - m[r]) : 0.f;
+                l[r] += p;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(p, vf[e], acc[r][e]);
+            }
+        }
+    }
+    // lanes with the same `dl` but different `sub` saw different keys under the same running max: add them up
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+#pragma unroll
+        for (int o = LPK; o < 32; o <<= 1) {
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[r][e] += __shfl_xor_sync(0xffffffffu, acc[r][e], o);
+        }
+        if (lane == 0) {
+            sm_m[warp][r] = m[r];
+            sm_l[warp][r] = l[r];
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sm_acc[warp][r][dl * 8 + e] = acc[r][e];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < REP * D; i += blockDim.x) {
+        const int r = i / D, e = i % D;
+        float gm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) gm = fmaxf(gm, sm_m[w][r]);
+        float gl = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
+            const float f = (sm_m[w][r] == -INFINITY) ? 0.f : __expf(sm_m[w][r] - gm);
+            gl = fmaf(sm_l[w][r], f, gl);
+            o = fmaf(sm_acc[w][r][e], f, o);
+        }
+        const int h = kvh * REP + r;
+        if (nsplit == 1) {
+            out[static_cast<int64_t>(t) * hq * D + static_cast<int64_t>(h) * D + e] = Elem<T>::from_f(gl > 0.f ? o / gl : 0.f);
+        } else {
+            const int64_t slot = (static_cast<int64_t>(t) * hq + h) * nsplit + sp;
+            ws_acc[slot * D + e] = o;
+            if (e == 0) {
+                ws_ml[slot * 2] = gm;
+                ws_ml[slot * 2 + 1] = gl;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+paged_decode_merge_kernel(const float* __restrict__ ws_acc, const float* __restrict__ ws_ml, T* __restrict__ out, int hq,
+                          int d, int nsplit)
+{
+    const int t = blockIdx.x, h = blockIdx.y;
+    const int64_t base = (static_cast<int64_t>(t) * hq + h) * nsplit;
+    float gm = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) gm = fmaxf(gm, ws_ml[(base + s) * 2]);
+    float gl = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+        const float mm = ws_ml[(base + s) * 2];
+        gl += (mm == -INFINITY) ? 0.f : ws_ml[(base + s) * 2 + 1] * __expf(mm - gm);
+    }
+    const float inv = gl > 0.f ? 1.f / gl : 0.f;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+        float o = 0.f;
+        for (int s = 0; s < nsplit; ++s) {
+            const float mm = ws_ml[(base + s) * 2];
+            if (mm != -INFINITY) o = fmaf(ws_acc[(base + s) * d + e], __expf(mm - gm), o);
+        }
+        out[static_cast<int64_t>(t) * hq * d + static_cast<int64_t>(h) * d + e] = Elem<T>::from_f(o * inv);
+    }
+}
+
 }  // namespace pattn
 }  // namespace dsb
 
@@ -117,6 +291,57 @@ DSB_EXPORT int dsb_paged_attention(const void* q, const void* cache, void* out, 
             block_size, max_blocks, scale);
     else
         return -1;
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+
+// Decode-optimised entry: eligible when dtype is bf16/fp16, d in {64,128,256} and hq/hkv in {1,2,4,8}.
+// ws_acc: float [tokens*hq*nsplit*d], ws_ml: float [tokens*hq*nsplit*2] (unused when nsplit == 1).
+// Returns -3 when the shape is not eligible (caller falls back to dsb_paged_attention).
+#define DSB_PD_LAUNCH(TT, DD, RR)                                                                                        \
+    pattn::paged_decode_kernel<TT, DD, RR><<<grid, 128, 0, stream>>>((const TT*)q, (const TT*)cache, (TT*)out, ws_acc,   \
+                                                                     ws_ml, seq_of, pos_of, block_table, hq, hkv, q_stride, \
+                                                                     block_size, max_blocks, scale, nsplit)
+#define DSB_PD_REP(TT, DD)                          \
+    switch (rep) {                                   \
+        case 1: DSB_PD_LAUNCH(TT, DD, 1); break;     \
+        case 2: DSB_PD_LAUNCH(TT, DD, 2); break;     \
+        case 4: DSB_PD_LAUNCH(TT, DD, 4); break;     \
+        case 8: DSB_PD_LAUNCH(TT, DD, 8); break;     \
+        default: return -3;                          \
+    }
+#define DSB_PD_D(TT)                                 \
+    switch (d) {                                     \
+        case 64: DSB_PD_REP(TT, 64) break;           \
+        case 128: DSB_PD_REP(TT, 128) break;         \
+        case 256: DSB_PD_REP(TT, 256) break;         \
+        default: return -3;                          \
+    }
+
+DSB_EXPORT int dsb_paged_decode(const void* q, const void* cache, void* out, float* ws_acc, float* ws_ml,
+                                const int32_t* seq_of, const int32_t* pos_of, const int32_t* block_table, int tokens, int hq,
+                                int hkv, int d, int q_stride, int block_size, int max_blocks, float scale, int nsplit,
+                                int dtype, cudaStream_t stream)
+{
+    if (tokens <= 0) return 0;
+    if (hq % hkv || nsplit < 1 || q_stride % 8) return -3;
+    const int rep = hq / hkv;
+    if (dtype != kBF16 && dtype != kF16) return -3;
+    dim3 grid(tokens, hkv, nsplit);
+    if (dtype == kBF16) {
+        DSB_PD_D(__nv_bfloat16)
+    } else {
+        DSB_PD_D(__half)
+    }
+    if (nsplit > 1) {
+        dim3 g2(tokens, hq);
+        if (dtype == kBF16)
+            pattn::paged_decode_merge_kernel<__nv_bfloat16><<<g2, 128, 0, stream>>>(ws_acc, ws_ml, (__nv_bfloat16*)out, hq, d,
+                                                                                  nsplit);
+        else
+            pattn::paged_decode_merge_kernel<__half><<<g2, 128, 0, stream>>>(ws_acc, ws_ml, (__half*)out, hq, d, nsplit);
+    }
     DSB_CHECK_LAUNCH();
     return 0;
 }

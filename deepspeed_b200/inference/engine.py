@@ -115,9 +115,10 @@ class InferenceEngine(nn.Module):
         ec = RaggedInferenceEngineConfig(state_manager={"max_context": max_ctx, "max_ragged_batch_size":
                                                         max(4 * max_ctx, 2048), "max_ragged_sequence_count": 256},
                                          cuda_graph_decode=cfg.enable_cuda_graph)
-        if not self.device.type == "cuda":
-            ec.state_manager.memory_config.mode = type(ec.state_manager.memory_config.mode)("allocate")
-            ec.state_manager.memory_config.size = 64
+        # v1 API serves at most 256 concurrent sequences of max_out_tokens: size the KV pool for exactly that instead
+        # of claiming all free HBM (the v2 factory default)
+        ec.state_manager.memory_config.mode = "allocate"
+        ec.state_manager.memory_config.size = 64 if self.device.type != "cuda" else max(64, 256 * ((max_ctx + 127) // 128))
         rank = dist.get_rank(self.mp_group) if self.mp_group is not None else 0
         quant = "int8" if self.dtype == torch.int8 else None
         dtype = torch.float16 if self.dtype == torch.int8 else self.dtype

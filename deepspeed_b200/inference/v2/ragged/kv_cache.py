@@ -36,7 +36,8 @@ class BlockedKVCache:
             layers, heads, d = c.cache_shape
             per_block.append(layers * c.block_size * 2 * heads * d * _DT[c.cache_dtype].itemsize)
         total_per_block = sum(per_block)
-        if memory_config.mode == AllocationMode.RESERVE:
+        mode = getattr(memory_config.mode, "value", memory_config.mode)
+        if mode == AllocationMode.RESERVE.value:
             if str(device).startswith("cuda") and torch.cuda.is_available():
                 free, _ = torch.cuda.mem_get_info()
                 usable = max(free - memory_config.size, total_per_block)

@@ -7,10 +7,29 @@ identical semantics so the scheduler / state-manager logic is testable without a
 """
 import ctypes
 import math
+import os
 
 import torch
 
 from deepspeed_b200.ops import native as N
+
+
+_ws = {}
+
+
+def _decode_ws(device, n_acc, n_ml):
+    """Persistent fp32 workspace for split-KV partials (persistent so CUDA-graph replays see stable addresses)."""
+    ent = _ws.get(device)
+    if ent is None or ent[0].numel() < n_acc or ent[1].numel() < n_ml:
+        ent = (torch.empty(max(n_acc, 1 << 22), dtype=torch.float32, device=device),
+               torch.empty(max(n_ml, 1 << 16), dtype=torch.float32, device=device))
+        _ws[device] = ent
+    return ent
+
+
+def _decode_eligible(qkv, hq, hkv, d):
+    return (qkv.dtype in (torch.bfloat16, torch.float16) and d in (64, 128, 256) and hq % hkv == 0
+            and hq // hkv in (1, 2, 4, 8) and qkv.shape[1] % 8 == 0)
 
 
 def _p(t):
@@ -72,6 +91,22 @@ def paged_attention(qkv, cache, seq_of, pos_of, block_table, hq, hkv, d, block_s
     max_blocks = block_table.shape[1]
     if qkv.is_cuda:
         out = torch.empty(T, hq * d, dtype=qkv.dtype, device=qkv.device)
+        if _decode_eligible(qkv, hq, hkv, d) and os.environ.get("DSB200_PAGED_V1", "0") != "1":
+            # split the KV range so (tokens x kv_heads x splits) covers the 148 SMs a few times over; the split count
+            # depends only on static shapes (graph-capturable: no device->host read of the positions)
+            max_ctx = max_blocks * block_size
+            nsplit = 1
+            ctas = T * hkv
+            while ctas * nsplit < 592 and nsplit < 32 and max_ctx // (nsplit * 2) >= 256:
+                nsplit *= 2
+            ws_acc, ws_ml = _decode_ws(qkv.device, T * hq * nsplit * d, T * hq * nsplit * 2) if nsplit > 1 else (None, None)
+            rc = N.cuda().dsb_paged_decode(_p(qkv), _p(cache), _p(out), _p(ws_acc), _p(ws_ml), _p(seq_of), _p(pos_of),
+                                           _p(block_table), T, hq, hkv, d, qkv.shape[1], block_size, max_blocks,
+                                           ctypes.c_float(scale), nsplit, N.dt(qkv), N.stream())
+            if rc == 0:
+                return out
+            if rc != -3:
+                N.check(rc, "paged_decode")
         rc = N.cuda().dsb_paged_attention(_p(qkv), _p(cache), _p(out), _p(seq_of), _p(pos_of), _p(block_table), T, hq, hkv, d,
                                           qkv.shape[1], block_size, max_blocks, ctypes.c_float(scale), N.dt(qkv),
                                           N.stream())

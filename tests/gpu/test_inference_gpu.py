@@ -38,6 +38,25 @@ def test_kv_append_and_paged_attention(dtype):
     torch.testing.assert_close(o_d.cpu().float(), o_h.float(), atol=tol, rtol=tol)
 
 
+@pytest.mark.parametrize("hq,hkv,d", [(32, 8, 128), (8, 8, 64), (16, 2, 128), (14, 2, 64)])
+def test_paged_decode_split_kv_long_context(hq, hkv, d):
+    """Decode-shaped batch (1 token per sequence, long contexts): the split-KV / GQA-shared kernel (or the generic
+    fallback for the 14/2 head ratio) must match the plain fp32 definition."""
+    from deepspeed_b200.ops.kernels import ragged_ops as R
+    torch.manual_seed(0)
+    bs, seqs, nb = 128, 5, 12
+    ctx = [1500, 17, 1024, 129, 1536]
+    qkv = (torch.randn(seqs, (hq + 2 * hkv) * d) * 0.5).bfloat16()
+    cache = (torch.randn(seqs * nb, bs, 2, hkv, d) * 0.5).bfloat16()
+    bt = torch.randperm(seqs * nb).to(torch.int32).view(seqs, nb)
+    seq_of = torch.arange(seqs, dtype=torch.int32)
+    pos_of = torch.tensor([c - 1 for c in ctx], dtype=torch.int32)
+    ref = R.paged_attention(qkv.float(), cache.float(), seq_of, pos_of, bt, hq, hkv, d, bs)
+    dev = "cuda"
+    got = R.paged_attention(qkv.to(dev), cache.to(dev), seq_of.to(dev), pos_of.to(dev), bt.to(dev), hq, hkv, d, bs)
+    torch.testing.assert_close(got.float().cpu(), ref, atol=2e-2, rtol=2e-2)
+
+
 def test_embed_and_row_gather():
     from deepspeed_b200.ops.kernels import ragged_ops as R
     wte = torch.randn(100, 64).bfloat16()
