@@ -403,6 +403,244 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ==================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA *pair* on one TPC computes a 256x256 tile.  Each CTA stages its own 128 rows of A
+// and HALF of the B tile (128 of the 256 N rows), so the L2->SM operand traffic per flop drops by a third versus the
+// 1-CTA kernel (32 KiB instead of 48 KiB per CTA per k-block); the leader CTA's elected thread issues
+// tcgen05.mma.cta_group::2 (M=256) which reads both CTAs' shared memory and writes each CTA's half of the accumulator
+// into that CTA's TMEM.  Barrier protocol:
+//   full[s]   (leader only, count 2): each CTA's producer does a *remote* arrive.expect_tx(own bytes) on it and both
+//             CTAs' TMA loads (cp.async.bulk.tensor...cta_group::2) complete_tx on it (peer bit of the address cleared)
+//   empty[s]  (both CTAs): tcgen05.commit.cta_group::2 ... multicast::cluster mask 0b11 from the leader's MMA thread
+//   tfull[a]  (both CTAs): multicast commit after the last k-block -> each CTA's epilogue drains its own TMEM half
+//   tempty[a] (leader only, count 8): remote arrives from the 4 epilogue warps of each CTA
+// ==================================================================================================================
+constexpr int STAGES2 = 6;
+constexpr uint32_t B2_STAGE_BYTES = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the B tile
+constexpr uint32_t SMEM2_A = 0;
+constexpr uint32_t SMEM2_B = SMEM2_A + STAGES2 * A_STAGE_BYTES;
+constexpr uint32_t SMEM2_C = SMEM2_B + STAGES2 * B2_STAGE_BYTES;
+constexpr uint32_t SMEM2_BAR = SMEM2_C + 2 * C_BUF_BYTES;
+constexpr uint32_t SMEM2_TOTAL = SMEM2_BAR + 256 + 1024;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | (((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_leader(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar & kPeerMask), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint32_t bar)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accum)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, int M, int N, int K)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_base = sbase + SMEM2_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8 * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8 * (STAGES2 + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8 * (2 * STAGES2 + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8 * (2 * STAGES2 + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM2_BAR + 8 * (2 * STAGES2 + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_pairs = static_cast<int>(gridDim.x) >> 1;
+    const int pair = static_cast<int>(blockIdx.x) >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 2);   // one arrive.expect_tx per CTA of the pair (only the leader's copy is used)
+            mbar_init(empty_bar(s), 1);  // multicast commit from the leader's MMA thread
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
+    const int num_n = (N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                const int m_blk = tile % num_m;
+                const int n_blk = tile / num_m;
+                const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+                const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx_leader(full_bar(stage), A_STAGE_BYTES + B2_STAGE_BYTES);
+                    tma_load_2d_2sm(sbase + SMEM2_A + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
+                    tma_load_2d_2sm(sbase + SMEM2_B + stage * B2_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = make_desc_kmajor_sw128(sbase + SMEM2_A + stage * A_STAGE_BYTES);
+                    const uint64_t db = make_desc_kmajor_sw128(sbase + SMEM2_B + stage * B2_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16_2cta(tmem_d, da + static_cast<uint64_t>((k * UMMA_K * 2) >> 4),
+                                       db + static_cast<uint64_t>((k * UMMA_K * 2) >> 4), kIdesc2,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit2(empty_bar(stage));
+                    if (++stage == STAGES2) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit2(tfull_bar(as));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int ew = warp - 4;
+        const int etid = threadIdx.x - 128;
+        const int row = ew * 32 + lane;
+        int it = 0;
+        for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
+            const int m_blk = tile % num_m;
+            const int n_blk = tile / num_m;
+            const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / CCHUNK; ++c) {
+                const int buf = c & 1;
+                if (etid == 0) tma_store_wait_read<1>();
+                epi_bar_sync();
+                uint32_t r[64];
+                tmem_ld_32x32(taddr + c * CCHUNK, r);
+                tmem_ld_32x32(taddr + c * CCHUNK + 32, r + 32);
+                tmem_ld_wait();
+                if (c == BN / CCHUNK - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+                }
+                uint8_t* crow = smem + SMEM2_C + buf * C_BUF_BYTES + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j * 8 + e]);
+                    const Vec16 v = Elem<__nv_bfloat16>::pack(f);
+                    const uint32_t dst = smem_u32(crow + ((j ^ (row & 7)) << 4));
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                                 "r"(v.w[3])
+                                 : "memory");
+                }
+                fence_async_smem();
+                epi_bar_sync();
+                if (etid == 0 && m0 < M) {
+                    tma_store_2d(&map_c, sbase + SMEM2_C + buf * C_BUF_BYTES, n_blk * BN + c * CCHUNK, m0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (etid == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer may still be reading our smem / arriving on our barriers until here
+    if (warp == 2) tmem_dealloc2(tmem_base, TMEM_COLS);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -472,6 +710,36 @@ static int launch(const void* a, const void* b, void* c, int M, int N, int K, in
         grid = ag.enabled ? mma + ag.comm_ctas : mma;
     }
     gemm_nt_kernel<<<grid, kThreads, SMEM_TOTAL, stream>>>(ma, mb, mc, M, N, K, ag);
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+static bool g_attr2_set = false;
+
+// 2-CTA (cta_group::2) variant: 256x256 tiles per CTA pair.
+DSB_EXPORT int dsb_gemm_nt_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                     int sms, cudaStream_t stream)
+{
+    if (K % 8 || lda % 8 || ldb % 8 || ldc % 8) return -2;
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return -2;
+    CUtensorMap ma, mb, mc;
+    int rc;
+    if ((rc = make_map(&ma, a, M, K, lda, BM, BK))) return rc;
+    if ((rc = make_map(&mb, b, N, K, ldb, BN / 2, BK))) return rc;
+    if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
+    if (!g_attr2_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        g_attr2_set = true;
+    }
+    int grid = (sms > 0 ? sms : g_sm_count) & ~1;
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    if (grid / 2 > tiles) grid = tiles * 2;
+    if (grid < 2) return -2;
+    gemm_nt_2cta_kernel<<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K);
     DSB_CHECK_LAUNCH();
     return 0;
 }

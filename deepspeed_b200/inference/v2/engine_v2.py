@@ -42,7 +42,9 @@ class InferenceEngineV2:
         return self._model
 
     def put(self, batch_uids: Iterable[int], batch_tokens: Iterable[torch.Tensor], do_checks: bool = True) -> torch.Tensor:
-        batch_uids, batch_tokens = list(batch_uids), [torch.as_tensor(t).reshape(-1) for t in batch_tokens]
+        batch_uids = list(batch_uids)
+        batch_tokens = [t if (isinstance(t, torch.Tensor) and t.dim() == 1 and t.device.type == "cpu") else
+                        torch.as_tensor(t).reshape(-1).cpu() for t in batch_tokens]
         if do_checks:
             res = self.can_schedule(batch_uids, [t.numel() for t in batch_tokens])
             if res != SchedulingResult.Success:
@@ -101,7 +103,7 @@ class InferenceEngineV2:
         uids, lengths = list(uids), list(lengths)
         smc = self._config.state_manager
         cur_seqs = self._state_manager.n_tracked_sequences
-        free = int(self._state_manager.free_blocks[0])
+        free = self._state_manager.free_block_count(0)
         if len(uids) > smc.max_ragged_sequence_count:
             return SchedulingResult.BatchSequenceLimitExceeded
         batch_len = 0

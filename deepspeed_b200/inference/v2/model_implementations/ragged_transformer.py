@@ -89,7 +89,10 @@ class RaggedTransformer:
         return (bs - seq.seen_tokens % bs) % bs
 
     def maybe_allocate_kv(self, seq, n_new_tokens: int) -> None:
-        _, n_blocks = self.get_kv_requirements(seq, n_new_tokens, int(self._state_manager.free_blocks[0]))
+        bs = self._state_manager.kv_block_size
+        if (seq.seen_tokens + n_new_tokens + bs - 1) // bs <= seq.cur_allocated_blocks:
+            return  # fast path (almost every decode step): the current last block still has room
+        _, n_blocks = self.get_kv_requirements(seq, n_new_tokens, self._state_manager.free_block_count(0))
         if n_blocks > 0:
             seq.extend_kv_cache(self._state_manager.allocate_blocks(n_blocks))
 

@@ -18,19 +18,20 @@ class BlockedAllocator:
         self._head = 0
         self._free = num_blocks
         self._allocated = torch.zeros(num_blocks, dtype=torch.bool)
+        self._next_np, self._alloc_np = self._next.numpy(), self._allocated.numpy()
 
     def allocate(self, num_blocks: int) -> torch.Tensor:
         if num_blocks > self._free:
             raise ValueError(f"Not enough free blocks in the KV-cache to allocate {num_blocks} blocks")
-        out = torch.empty(num_blocks, dtype=torch.int32)
-        nxt, head = self._next, self._head
-        for i in range(num_blocks):
-            out[i] = head
-            self._allocated[head] = True
+        nxt, alloc, head = self._next_np, self._alloc_np, self._head
+        ids = []
+        for _ in range(num_blocks):
+            ids.append(head)
+            alloc[head] = True
             head = int(nxt[head])
         self._head = head
         self._free -= num_blocks
-        return out
+        return torch.tensor(ids, dtype=torch.int32)
 
     def free(self, blocks: Union[Iterable[int], int, torch.Tensor]) -> None:
         if isinstance(blocks, int):
@@ -38,15 +39,16 @@ class BlockedAllocator:
         elif isinstance(blocks, torch.Tensor):
             blocks = blocks.tolist()
         blocks = list(blocks)
+        alloc, nxt = self._alloc_np, self._next_np
         for b in blocks:
             if b < 0 or b >= self._num_blocks:
                 raise ValueError(f"Invalid block {b} provided to free")
-            if not self._allocated[b]:
+            if not alloc[b]:
                 raise ValueError(f"Block {b} is already free")
         for b in blocks:
-            self._next[b] = self._head
+            nxt[b] = self._head
             self._head = b
-            self._allocated[b] = False
+            alloc[b] = False
             self._free += 1
 
     @property

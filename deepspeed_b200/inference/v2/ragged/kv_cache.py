@@ -82,6 +82,9 @@ class BlockedKVCache:
     def get_cache(self, cache_id: int, cache_group: int = 0) -> torch.Tensor:
         return self._caches[cache_group][cache_id]
 
+    def free_block_count(self, cache_group: int = 0) -> int:
+        return self._allocators[cache_group].free_blocks
+
     @property
     def free_blocks(self) -> torch.Tensor:
         return torch.tensor([a.free_blocks for a in self._allocators], dtype=torch.int32)

@@ -86,6 +86,9 @@ class DSStateManager:
     def n_kv_cache_groups(self) -> int:
         return self._kv_cache.num_caches
 
+    def free_block_count(self, cache_group: int = 0) -> int:
+        return self._kv_cache.free_block_count(cache_group)
+
     @property
     def free_blocks(self) -> torch.Tensor:
         return self._kv_cache.free_blocks

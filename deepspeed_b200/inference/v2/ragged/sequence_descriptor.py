@@ -34,6 +34,7 @@ class DSSequenceDescriptor(BaseSequenceDescriptor):
     def __init__(self, tracking_id: int, kv_cache_ids: Tuple[torch.Tensor, ...], max_context: int = -1):
         self._tracking_id = tracking_id
         self._kv_cache_ids = kv_cache_ids          # per cache group: int32 [max_blocks] host tensors
+        self._kv_np = tuple(t.numpy() for t in kv_cache_ids)  # same memory, cheap host-side access
         self._blocks_per = [0 for _ in kv_cache_ids]
         self._seen_tokens = 0
         self._in_flight_tokens = 0
@@ -66,6 +67,9 @@ class DSSequenceDescriptor(BaseSequenceDescriptor):
     def kv_cache_ids(self, cache_group: int = 0) -> torch.Tensor:
         return self._kv_cache_ids[cache_group]
 
+    def kv_ids_np(self, cache_group: int = 0):
+        return self._kv_np[cache_group]
+
     def all_block_ids(self, cache_group: int = 0) -> torch.Tensor:
         return self._kv_cache_ids[cache_group][:self._blocks_per[cache_group]]
 
@@ -82,7 +86,7 @@ class DSSequenceDescriptor(BaseSequenceDescriptor):
         ids = new_ids[0] if len(new_ids) == 1 else torch.cat(list(new_ids))
         n = ids.numel()
         s = self._blocks_per[cache_group]
-        self._kv_cache_ids[cache_group][s:s + n] = ids
+        self._kv_np[cache_group][s:s + n] = ids.numpy() if ids.device.type == "cpu" else ids.cpu().numpy()
         self._blocks_per[cache_group] += n
 
     def free_kv_cache(self, free_ids, cache_group: int = 0) -> None:

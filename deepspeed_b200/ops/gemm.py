@@ -52,7 +52,7 @@ def _pick(a, b):
     choice = _tuned.get(key)
     if choice is not None:
         return choice
-    if _backend == "sm100" or torch.cuda.is_current_stream_capturing():
+    if torch.cuda.is_current_stream_capturing():
         return "sm100"
     from deepspeed_b200.ops.kernels import gemm_sm100
     out = torch.empty(a.shape[0], b.shape[0], dtype=a.dtype, device=a.device)
@@ -67,11 +67,39 @@ def _pick(a, b):
         e.synchronize()
         return s.elapsed_time(e)
 
-    t_own = t(lambda: gemm_sm100.matmul_nt(a, b, out=out))
-    t_lib = t(lambda: torch.matmul(a, b.t(), out=out))
-    choice = "sm100" if t_own <= t_lib else "cublas"
+    cands = {"sm100": t(lambda: gemm_sm100.matmul_nt(a, b, out=out)),
+             "cublas": t(lambda: torch.matmul(a, b.t(), out=out))}
+    if _two_cta_ok():
+        cands["sm100_2cta"] = t(lambda: gemm_sm100.matmul_nt_2cta(a, b, out=out))
+    if _backend == "sm100":
+        cands.pop("cublas")
+    choice = min(cands, key=cands.get)
     _tuned[key] = choice
     return choice
+
+
+_2cta_ok = None
+
+
+def _two_cta_ok():
+    """One-time numerical self check of the CTA-pair kernel (disabled with DSB200_GEMM_2CTA=0)."""
+    global _2cta_ok
+    if _2cta_ok is None:
+        if os.environ.get("DSB200_GEMM_2CTA", "1") == "0":
+            _2cta_ok = False
+            return False
+        try:
+            from deepspeed_b200.ops.kernels import gemm_sm100
+            g = torch.Generator(device="cuda").manual_seed(0)
+            a = torch.randn(640, 320, device="cuda", generator=g).bfloat16()
+            b = torch.randn(768, 320, device="cuda", generator=g).bfloat16()
+            c = gemm_sm100.matmul_nt_2cta(a, b)
+            ref = a.float() @ b.float().t()
+            torch.cuda.synchronize()
+            _2cta_ok = bool((c.float() - ref).abs().max() < 0.05 * ref.abs().max() + 0.5) and bool(torch.isfinite(c).all())
+        except Exception:
+            _2cta_ok = False
+    return _2cta_ok
 
 
 def tuning_table():
@@ -80,10 +108,12 @@ def tuning_table():
 
 def matmul_nt(a, b):
     """a [M, K] @ b[N, K]^T."""
-    if _sm100_usable(a, b, True) and _pick(a, b) == "sm100":
-        from deepspeed_b200.ops.kernels import gemm_sm100
-        _report(a.shape[0] * a.shape[1] * b.shape[0])
-        return gemm_sm100.matmul_nt(a, b)
+    if _sm100_usable(a, b, True):
+        choice = _pick(a, b)
+        if choice != "cublas":
+            from deepspeed_b200.ops.kernels import gemm_sm100
+            _report(a.shape[0] * a.shape[1] * b.shape[0])
+            return gemm_sm100.matmul_nt_2cta(a, b) if choice == "sm100_2cta" else gemm_sm100.matmul_nt(a, b)
     return torch.matmul(a, b.t())
 
 

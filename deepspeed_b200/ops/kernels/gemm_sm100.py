@@ -34,6 +34,18 @@ def matmul_nt(a, b, out=None, sms=0):
     return out
 
 
+def matmul_nt_2cta(a, b, out=None, sms=0):
+    """Same contract as :func:`matmul_nt`, CTA-pair kernel (``tcgen05.mma.cta_group::2``, 256x256 tiles)."""
+    M, K = a.shape
+    Nn = b.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.bfloat16, device=a.device)
+    rc = N.cuda().dsb_gemm_nt_bf16_2cta(N.ptr(a), N.ptr(b), N.ptr(out), M, Nn, K, a.stride(0), b.stride(0), out.stride(0),
+                                        sms, N.stream())
+    N.check(rc, "gemm_nt_bf16_2cta")
+    return out
+
+
 def matmul_nn(a, b):
     raise NotImplementedError("MN-major B operand: use the cuBLAS backend")
 

@@ -32,9 +32,15 @@ for M, N, K, name in shapes:
     ok = gemm_sm100.self_check()
     t_lib = t(lambda: torch.matmul(a, b.t(), out=out))
     t_own = t(lambda: gemm_sm100.matmul_nt(a, b, out=out)) if ok else float("nan")
+    try:
+        t_2cta = t(lambda: gemm_sm100.matmul_nt_2cta(a, b, out=out))
+        ok2 = bool((out.float() - torch.matmul(a, b.t()).float()).abs().max() < 0.05 * out.float().abs().max() + 0.5)
+    except Exception as ex:
+        t_2cta, ok2 = float("nan"), False
     fl = 2.0 * M * N * K
     rows.append({"shape": name, "M": M, "N": N, "K": K, "cublas_ms": t_lib, "sm100_ms": t_own,
-                 "cublas_tflops": fl / t_lib / 1e9, "sm100_tflops": fl / t_own / 1e9 if ok else None})
+                 "cublas_tflops": fl / t_lib / 1e9, "sm100_tflops": fl / t_own / 1e9 if ok else None,
+                 "sm100_2cta_ms": t_2cta, "sm100_2cta_tflops": fl / t_2cta / 1e9 if ok2 else None, "2cta_correct": ok2})
     print(rows[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/gemm_bench.json", "w"), indent=1)

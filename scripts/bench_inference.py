@@ -28,6 +28,11 @@ eng = build_engine_from_model(model, {"state_manager": {"max_context": a.prompt 
                                                         "memory_config": {"mode": "reserve", "size": 8_000_000_000}}})
 del model
 torch.cuda.empty_cache()
+# warm-up: cuBLAS heuristics, cuDNN SDPA plan, first-touch of the KV pool
+eng.put([10**6], [torch.randint(0, cfg.vocab_size, (a.prompt, ))])
+eng.put([10**6], [torch.randint(0, cfg.vocab_size, (1, ))])
+eng.flush(10**6)
+torch.cuda.synchronize()
 uids = list(range(a.batch))
 prompts = [torch.randint(0, cfg.vocab_size, (a.prompt, )) for _ in uids]
 # prefill in ragged batches of <= 8192 tokens
