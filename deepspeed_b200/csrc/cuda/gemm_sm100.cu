@@ -425,6 +425,21 @@ constexpr uint32_t SMEM2_BAR = SMEM2_C + 2 * C_BUF_BYTES;
 constexpr uint32_t SMEM2_TOTAL = SMEM2_BAR + 256 + 1024;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA of the pair
 constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | (((2 * BM) >> 4) << 24);
+// MN-major operand (the matrix is stored [k, mn] row-major, i.e. mn is the contiguous dimension).  A stage holds the
+// [128 mn x 64 k] tile as TWO TMA boxes of [64 k rows x 64 mn] (128-byte swizzled rows, 8 KiB each):
+//   canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> LBO = 8192 B between the two 64-wide mn atoms,
+//   SBO = 1024 B between groups of 8 k rows; one UMMA_K=16 step advances the start address by 2048 B.
+constexpr uint32_t MN_BOX_BYTES = 64 * 64 * 2;
+__device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+    d |= static_cast<uint64_t>(MN_BOX_BYTES >> 4) << 16;  // LBO
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;          // SBO
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
@@ -482,8 +497,9 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         : "memory");
 }
 
+template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, int M, int N, int K)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -543,8 +559,20 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx_leader(full_bar(stage), A_STAGE_BYTES + B2_STAGE_BYTES);
-                    tma_load_2d_2sm(sbase + SMEM2_A + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
-                    tma_load_2d_2sm(sbase + SMEM2_B + stage * B2_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+                    const uint32_t sa = sbase + SMEM2_A + stage * A_STAGE_BYTES;
+                    const uint32_t sb = sbase + SMEM2_B + stage * B2_STAGE_BYTES;
+                    if constexpr (A_MN) {
+                        tma_load_2d_2sm(sa, &map_a, full_bar(stage), m0, kb * BK);
+                        tma_load_2d_2sm(sa + MN_BOX_BYTES, &map_a, full_bar(stage), m0 + 64, kb * BK);
+                    } else {
+                        tma_load_2d_2sm(sa, &map_a, full_bar(stage), kb * BK, m0);
+                    }
+                    if constexpr (B_MN) {
+                        tma_load_2d_2sm(sb, &map_b, full_bar(stage), n0, kb * BK);
+                        tma_load_2d_2sm(sb + MN_BOX_BYTES, &map_b, full_bar(stage), n0 + 64, kb * BK);
+                    } else {
+                        tma_load_2d_2sm(sb, &map_b, full_bar(stage), kb * BK, n0);
+                    }
                     if (++stage == STAGES2) {
                         stage = 0;
                         phase ^= 1;
@@ -567,13 +595,17 @@ gemm_nt_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t da = make_desc_kmajor_sw128(sbase + SMEM2_A + stage * A_STAGE_BYTES);
-                    const uint64_t db = make_desc_kmajor_sw128(sbase + SMEM2_B + stage * B2_STAGE_BYTES);
+                    const uint32_t sa = sbase + SMEM2_A + stage * A_STAGE_BYTES;
+                    const uint32_t sb = sbase + SMEM2_B + stage * B2_STAGE_BYTES;
+                    const uint64_t da = A_MN ? make_desc_mnmajor_sw128(sa) : make_desc_kmajor_sw128(sa);
+                    const uint64_t db = B_MN ? make_desc_mnmajor_sw128(sb) : make_desc_kmajor_sw128(sb);
+                    // per UMMA_K (16 elements of k): K-major advances 32 B inside the swizzle row, MN-major 16 k-rows = 2 KiB
+                    constexpr uint64_t ka = A_MN ? (2048 >> 4) : ((UMMA_K * 2) >> 4);
+                    constexpr uint64_t kbs = B_MN ? (2048 >> 4) : ((UMMA_K * 2) >> 4);
+                    constexpr uint32_t idesc = kIdesc2 | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16_2cta(tmem_d, da + static_cast<uint64_t>((k * UMMA_K * 2) >> 4),
-                                       db + static_cast<uint64_t>((k * UMMA_K * 2) >> 4), kIdesc2,
-                                       (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16_2cta(tmem_d, da + ka * k, db + kbs * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit2(empty_bar(stage));
                     if (++stage == STAGES2) {
@@ -716,20 +748,45 @@ static int launch(const void* a, const void* b, void* c, int M, int N, int K, in
 
 static bool g_attr2_set = false;
 
-// 2-CTA (cta_group::2) variant: 256x256 tiles per CTA pair.
-DSB_EXPORT int dsb_gemm_nt_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
-                                     int sms, cudaStream_t stream)
+template <bool A_MN, bool B_MN>
+static int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int M, int N, int K, int grid,
+                       cudaStream_t stream)
 {
-    if (K % 8 || lda % 8 || ldb % 8 || ldc % 8) return -2;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM2_TOTAL);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        attr = true;
+    }
+    gemm_2cta_kernel<A_MN, B_MN><<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K);
+    return 0;
+}
+
+// 2-CTA (cta_group::2) GEMM, 256x256 tiles per CTA pair:  C[M,N] = op(A) x op(B), bf16 in/out, fp32 accumulate.
+//   a_mn == 0: A is stored [M, K] row-major (K-major)      a_mn == 1: A is stored [K, M] row-major (MN-major)
+//   b_mn == 0: B is stored [N, K] row-major (K-major)      b_mn == 1: B is stored [K, N] row-major (MN-major)
+// so (0,0) = "NT" (y = x W^T), (0,1) = "NN" (dx = dy W), (1,1) = "TN" (dW = dy^T x).  lda/ldb are row strides in elements.
+DSB_EXPORT int dsb_gemm_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int sms, cudaStream_t stream)
+{
+    if (lda % 8 || ldb % 8 || ldc % 8) return -2;
+    if ((a_mn ? M : K) % 8 || (b_mn ? N : K) % 8) return -2;
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return -2;
     CUtensorMap ma, mb, mc;
     int rc;
-    if ((rc = make_map(&ma, a, M, K, lda, BM, BK))) return rc;
-    if ((rc = make_map(&mb, b, N, K, ldb, BN / 2, BK))) return rc;
+    if (a_mn) {
+        if ((rc = make_map(&ma, a, K, M, lda, 64, 64))) return rc;  // rows = k, cols = mn; box [64 k x 64 mn]
+    } else if ((rc = make_map(&ma, a, M, K, lda, BM, BK))) {
+        return rc;
+    }
+    if (b_mn) {
+        if ((rc = make_map(&mb, b, K, N, ldb, 64, 64))) return rc;
+    } else if ((rc = make_map(&mb, b, N, K, ldb, BN / 2, BK))) {
+        return rc;
+    }
     if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
     if (!g_attr2_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
-        if (e != cudaSuccess) return static_cast<int>(e);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -739,9 +796,23 @@ DSB_EXPORT int dsb_gemm_nt_bf16_2cta(const void* a, const void* b, void* c, int 
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
     if (grid / 2 > tiles) grid = tiles * 2;
     if (grid < 2) return -2;
-    gemm_nt_2cta_kernel<<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K);
+    if (a_mn && b_mn)
+        rc = launch_2cta<true, true>(ma, mb, mc, M, N, K, grid, stream);
+    else if (a_mn)
+        rc = launch_2cta<true, false>(ma, mb, mc, M, N, K, grid, stream);
+    else if (b_mn)
+        rc = launch_2cta<false, true>(ma, mb, mc, M, N, K, grid, stream);
+    else
+        rc = launch_2cta<false, false>(ma, mb, mc, M, N, K, grid, stream);
+    if (rc) return rc;
     DSB_CHECK_LAUNCH();
     return 0;
+}
+
+DSB_EXPORT int dsb_gemm_nt_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                     int sms, cudaStream_t stream)
+{
+    return dsb_gemm_bf16_2cta(a, b, c, M, N, K, lda, ldb, ldc, 0, 0, sms, stream);
 }
 
 // C[M,N] = A[M,K] @ B[N,K]^T   (bf16 in/out, fp32 accumulate).  sms <= 0 -> all SMs.

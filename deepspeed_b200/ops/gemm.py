@@ -117,13 +117,69 @@ def matmul_nt(a, b):
     return torch.matmul(a, b.t())
 
 
-def matmul_nn(a, b):
-    """a [M, K] @ b[K, N]."""
-    if _sm100_usable(a, b, False):
+def _pick_kind(kind, a, b, out, lib_fn, own_fn):
+    """Autotune NN / TN problems (backward GEMMs) between cuBLAS and the CTA-pair tcgen05 kernel."""
+    key = (kind, ) + tuple(a.shape) + tuple(b.shape)
+    choice = _tuned.get(key)
+    if choice is not None:
+        return choice
+    if torch.cuda.is_current_stream_capturing():
+        return "cublas"
+    scratch = torch.empty_like(out)
+
+    def t(fn):
+        fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(3):
+            fn()
+        e.record()
+        e.synchronize()
+        return s.elapsed_time(e)
+
+    t_lib = t(lambda: lib_fn(scratch))
+    try:
+        t_own = t(lambda: own_fn(scratch))
+        ref = lib_fn(torch.empty_like(out)).float()
+        good = bool((scratch.float() - ref).abs().max() <= 0.05 * ref.abs().max() + 0.5)
+    except Exception:
+        t_own, good = float("inf"), False
+    choice = "sm100_2cta" if (good and t_own < t_lib and _backend != "cublas") else "cublas"
+    _tuned[key] = choice
+    return choice
+
+
+def _own_ok(a, b, out):
+    if _backend == "cublas" or not a.is_cuda or not _two_cta_ok():
+        return False
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    return gemm_sm100.supports_2cta(a, b, False, False, out)
+
+
+def matmul_nn(a, b, out=None):
+    """a [M, K] @ b[K, N]  (dX = dY @ W)."""
+    if out is None:
+        out = torch.empty(a.shape[0], b.shape[1], dtype=a.dtype, device=a.device)
+    if _own_ok(a, b, out):
         from deepspeed_b200.ops.kernels import gemm_sm100
-        _report(a.shape[0] * a.shape[1] * b.shape[1])
-        return gemm_sm100.matmul_nn(a, b)
-    return torch.matmul(a, b)
+        if _pick_kind("nn", a, b, out, lambda o: torch.mm(a, b, out=o), lambda o: gemm_sm100.matmul_nn(a, b, out=o)) \
+                == "sm100_2cta":
+            _report(a.shape[0] * a.shape[1] * b.shape[1])
+            return gemm_sm100.matmul_nn(a, b, out=out)
+    return torch.mm(a, b, out=out)
+
+
+def matmul_tn(a, b, out=None):
+    """a[K, M]^T @ b[K, N]  (dW = dY^T @ X), optionally straight into ``out`` (a flat-gradient view)."""
+    if out is None:
+        out = torch.empty(a.shape[1], b.shape[1], dtype=a.dtype, device=a.device)
+    if _own_ok(a, b, out):
+        from deepspeed_b200.ops.kernels import gemm_sm100
+        if _pick_kind("tn", a, b, out, lambda o: torch.mm(a.t(), b, out=o), lambda o: gemm_sm100.matmul_tn(a, b, out=o)) \
+                == "sm100_2cta":
+            _report(a.shape[0] * a.shape[1] * b.shape[1])
+            return gemm_sm100.matmul_tn(a, b, out=out)
+    return torch.mm(a.t(), b, out=out)
 
 
 def _report(macs):

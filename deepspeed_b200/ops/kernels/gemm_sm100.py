@@ -46,8 +46,36 @@ def matmul_nt_2cta(a, b, out=None, sms=0):
     return out
 
 
-def matmul_nn(a, b):
-    raise NotImplementedError("MN-major B operand: use the cuBLAS backend")
+def matmul_2cta(a, b, a_mn: bool, b_mn: bool, out=None, sms=0):
+    """CTA-pair kernel with selectable operand majorness.
+
+    ``a_mn=False``: ``a`` is [M, K];  ``a_mn=True``: ``a`` is [K, M] (the kernel multiplies by its transpose).
+    ``b_mn=False``: ``b`` is [N, K];  ``b_mn=True``: ``b`` is [K, N].
+    Result ``[M, N]`` bf16.  Rows may be strided (views of larger buffers)."""
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    Nn = b.shape[1] if b_mn else b.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.bfloat16, device=a.device)
+    rc = N.cuda().dsb_gemm_bf16_2cta(N.ptr(a), N.ptr(b), N.ptr(out), M, Nn, K, a.stride(0), b.stride(0), out.stride(0),
+                                     int(a_mn), int(b_mn), sms, N.stream())
+    N.check(rc, "gemm_bf16_2cta")
+    return out
+
+
+def supports_2cta(a, b, a_mn, b_mn, out=None) -> bool:
+    ok = lambda t: (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0
+                    and t.data_ptr() % 16 == 0 and t.shape[1] % 8 == 0)
+    return ok(a) and ok(b) and (out is None or ok(out))
+
+
+def matmul_nn(a, b, out=None):
+    """a [M, K] @ b [K, N]."""
+    return matmul_2cta(a, b, False, True, out=out)
+
+
+def matmul_tn(a, b, out=None):
+    """a[K, M]^T @ b[K, N]."""
+    return matmul_2cta(a, b, True, True, out=out)
 
 
 def matmul_nt_allgather(a, b_view, local_full, peers, flags, shard_bytes, chunk_bytes, b_offset_bytes, world, rank, epoch,

@@ -59,7 +59,8 @@ class _FlatLinearFn(torch.autograd.Function):
                 gv = zo.grad_view_for(w)
                 if gv.dtype == dy2.dtype:
                     if zo.grad_is_fresh(w):
-                        torch.mm(dy2.t(), x2, out=gv)
+                        from deepspeed_b200.ops import gemm
+                        gemm.matmul_tn(dy2, x2, out=gv)
                     else:
                         gv.addmm_(dy2.t(), x2)
                 else:
@@ -107,10 +108,12 @@ class _ChunkedLinearXent(torch.autograd.Function):
             loss_rows, grad = softmax_xent_fwd_bwd(logits, labels[s:e].contiguous(), 1.0, inv_n, ignore_index, True)
             total = total + loss_rows.sum()
             if need_dh:
-                torch.mm(grad, weight, out=dh[s:e])
+                from deepspeed_b200.ops import gemm
+                gemm.matmul_nn(grad, weight, out=dh[s:e])
             if need_dw:
                 if first:
-                    torch.mm(grad.t(), hc, out=dw_tmp)
+                    from deepspeed_b200.ops import gemm
+                    gemm.matmul_tn(grad, hc, out=dw_tmp)
                 else:
                     dw_tmp.addmm_(grad.t(), hc)
             first = False

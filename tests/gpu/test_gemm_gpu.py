@@ -53,3 +53,43 @@ def test_gemm_2cta_matches_fp32(shape):
     for _ in range(3):
         c2 = gemm_sm100.matmul_nt_2cta(a, b)
     assert torch.equal(c, c2)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 384, 192), (1000, 520, 264), (8192, 4096, 6144), (4096, 14336, 8192)])
+def test_gemm_2cta_nn_tn_match_cublas(shape):
+    """MN-major operands: NN (dX = dY W) and TN (dW = dY^T X), incl. strided views and writes into a larger buffer."""
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b_kn = torch.randn(K, N, device="cuda", dtype=torch.bfloat16)
+    c = gemm_sm100.matmul_nn(a, b_kn)
+    ref = torch.mm(a, b_kn)
+    scale = ref.float().abs().max().item()
+    assert (c.float() - ref.float()).abs().max().item() < 2e-2 * scale + 1e-2
+    a_km = torch.randn(K, M, device="cuda", dtype=torch.bfloat16)
+    big = torch.zeros(M + 8, N + 16, device="cuda", dtype=torch.bfloat16)
+    out = big[:M, 8:8 + N] if N % 8 == 0 else None
+    c2 = gemm_sm100.matmul_tn(a_km, b_kn, out=out)
+    ref2 = torch.mm(a_km.t(), b_kn)
+    scale2 = ref2.float().abs().max().item()
+    assert (c2.float() - ref2.float()).abs().max().item() < 2e-2 * scale2 + 1e-2
+    if out is not None:
+        assert float(big[M:].abs().max()) == 0.0 and float(big[:, :8].abs().max()) == 0.0
+
+
+def test_flat_linear_backward_uses_native_gemm_and_matches_autograd():
+    from deepspeed_b200.ops import gemm
+    from deepspeed_b200.ops.linear import flat_linear
+    torch.manual_seed(0)
+    x = torch.randn(4, 512, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = torch.randn(2048, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = flat_linear(x, w)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr, wr = x.detach().clone().requires_grad_(True), w.detach().clone().requires_grad_(True)
+    torch.nn.functional.linear(xr, wr).backward(g)
+    for got, ref in ((x.grad, xr.grad), (w.grad, wr.grad)):
+        s = ref.float().abs().max().item()
+        assert (got.float() - ref.float()).abs().max().item() < 2e-2 * s + 1e-2
+    assert any(k[0] in ("nn", "tn") for k in gemm.tuning_table() if isinstance(k[0], str))
