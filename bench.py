@@ -267,6 +267,7 @@ def run_b200(args):
                 "fused_in_backward_optimizer": bool(engine.optimizer.fused_in_backward),
                 "collectives": "nvlink-peer-kernels" if engine.optimizer._symm is not None else "nccl",
                 "gemm_backend": __import__("deepspeed_b200.ops.gemm", fromlist=["x"]).get_backend(),
+                "gemm_autotune_choices": _gemm_choice_summary(),
                 "l2": "working set (>=100 GB of parameter/optimizer state streamed per step) >> 126 MB L2",
             },
             "model_tflops_per_gpu": flops / 1e12,
@@ -285,6 +286,16 @@ def run_b200(args):
             "exposed_comm": exposed,
         }
         print(json.dumps(out), flush=True)
+
+
+def _gemm_choice_summary():
+    """How many distinct GEMM problems the per-shape autotuner gave to each implementation."""
+    from deepspeed_b200.ops import gemm
+    out = {}
+    for k, v in gemm.tuning_table().items():
+        kind = k[0] if isinstance(k[0], str) else "nt"
+        out[f"{kind}:{v}"] = out.get(f"{kind}:{v}", 0) + 1
+    return out
 
 
 def run_reference(args):
