@@ -171,6 +171,22 @@ class MOELayer(nn.Module):
         self.ep_group = ep_group
         self.gate._set_ep_group(ep_group)
 
+    def _symm_state(self, flat):
+        """Symmetric-memory exchange state when usable: EP over >1 GPUs of one NVLink domain, 16-bit/32-bit rows,
+        grouped experts that take the [E_local, rows, H] layout (``DSB200_MOE_SYMM=0`` forces the NCCL path)."""
+        import os
+        if self.ep_size <= 1 or not flat.is_cuda or os.environ.get("DSB200_MOE_SYMM", "1") == "0":
+            return None
+        if self.gate.k > 8 or not self.gate.drop_tokens:
+            return None
+        if getattr(self, "_symm", False) is False:
+            try:
+                from deepspeed_b200.moe.symm_ep import SymmEP
+                self._symm = SymmEP.get(self.ep_group)
+            except Exception:
+                self._symm = None
+        return self._symm
+
     def forward(self, *inp):
         x = inp[0]
         H = x.shape[-1]
@@ -202,6 +218,15 @@ class MOELayer(nn.Module):
             y = moe_ops.gather(eo, g.weights.to(torch.float32), slots, T, k)
             return y.reshape(x.shape).to(x.dtype)
         C = g.capacity
+        st = self._symm_state(flat)
+        if st is not None:
+            # fused path: permutation kernels write / read the peers' symmetric buffers directly (no NCCL all-to-all)
+            from deepspeed_b200.moe import symm_ep
+            disp = symm_ep.dispatch(st, flat, g.expert_ids, g.positions, k, C, self.num_local_experts)
+            eo = self.experts(disp)
+            eo = eo[0] if isinstance(eo, tuple) else eo
+            y = symm_ep.combine(st, eo, g.weights, g.expert_ids, g.positions, k, C, self.num_local_experts, T)
+            return y.reshape(x.shape).to(x.dtype)
         rows, slots = moe_ops.scatter(flat, g.expert_ids, g.positions, g.offsets, k, C, E * C)
         disp = rows.view(E, C, H)
         if self.ep_size > 1:

@@ -27,6 +27,7 @@ class CudaKernelsBuilder(CUDAOpBuilder):
         "cuda/symm_coll.cu",
         "cuda/gemm_sm100.cu",
         "cuda/attention.cu",
+        "cuda/moe_symm.cu",
         "cuda/symm_mem.cpp",
     ]
     LINK_LIBS = ["-ldl", "-lpthread"]
