@@ -173,24 +173,30 @@ def _moe_symm_vs_nccl():
     H, I, E = 256, 512, 4
     results = {}
     for kind in ("grouped", "modules"):
-        torch.manual_seed(0)
-        if kind == "grouped":
-            expert = GroupedSwiGLUExperts(E // w, H, I)
-        else:
-            expert = nn.Sequential(nn.Linear(H, I), nn.GELU(), nn.Linear(I, H))
-        base = MoE(H, expert, num_experts=E, ep_size=w, k=2, capacity_factor=1.25, min_capacity=4, use_rts=False).cuda().bfloat16()
-        base.set_deepspeed_parallelism()
-        # different expert weights per rank (they are different experts), same gate everywhere
-        with torch.no_grad():
-            for n, p in base.named_parameters():
-                if "experts" in n:
-                    p.add_(0.01 * (r + 1) * torch.randn_like(p))
+
+        def make():
+            torch.manual_seed(0)
+            if kind == "grouped":
+                expert = GroupedSwiGLUExperts(E // w, H, I)
+            else:
+                expert = nn.Sequential(nn.Linear(H, I), nn.GELU(), nn.Linear(I, H))
+            mm = MoE(H, expert, num_experts=E, ep_size=w, k=2, capacity_factor=1.25, min_capacity=4, use_rts=False)
+            mm = mm.cuda().bfloat16()
+            mm.set_deepspeed_parallelism()
+            # different expert weights per rank (they are different experts), same gate everywhere
+            g = torch.Generator(device="cuda").manual_seed(100 + r)
+            with torch.no_grad():
+                for n, p in mm.named_parameters():
+                    if "experts" in n:
+                        p.add_(0.01 * torch.randn(p.shape, device="cuda", generator=g).to(p.dtype))
+            return mm
+
+        base = make()
         x0 = torch.randn(3, 96, H, generator=torch.Generator().manual_seed(10 + r)).cuda().bfloat16()
         outs = {}
         for mode in ("0", "1"):
             os.environ["DSB200_MOE_SYMM"] = mode
-            m = copy.deepcopy(base)
-            m.deepspeed_moe._set_ep_group(base.deepspeed_moe.ep_group)
+            m = make()
             m.deepspeed_moe._symm = False
             x = x0.clone().requires_grad_(True)
             y, l_aux, _ = m(x)
