@@ -597,8 +597,13 @@ class ZeroShardedOptimizer:
             return {"all_gather": 0.0, "reduce": 0.0, "total": 0.0}
         torch.cuda.synchronize()
         out = {"all_gather": 0.0, "reduce": 0.0}
-        for what, a, b in self._exposed:
-            out[what] += a.elapsed_time(b)
+        import os
+        dbg = os.environ.get("DSB200_EXPOSED_DEBUG")
+        for i, (what, a, b) in enumerate(self._exposed):
+            ms = a.elapsed_time(b)
+            out[what] += ms
+            if dbg and ms > 0.05:
+                print(f"[exposed] #{i} {what} {ms:.3f} ms", flush=True)
         out["total"] = out["all_gather"] + out["reduce"]
         self._exposed = []
         return out

@@ -129,13 +129,27 @@ def _ag_gemm():
         ref = x.float() @ unit[rows_a * K:].view(rows_b, K).float().t()
         assert (y.float() - ref).abs().max() < 0.05 * ref.abs().max() + 0.5
         dist.barrier()
-    # timing vs all-gather followed by the same GEMM
+    # timing at a Llama-3-8B-layer-like size: the unit is [other weights (18432 x 4096) | W_qkv (6144 x 4096)] = 201 MB and
+    # the consumer GEMM is x[8192, 4096] @ W_qkv^T -- all-gather followed by the GEMM vs the single fused kernel
     from deepspeed_b200.ops.kernels import gemm_sm100
+    K2, ra2, rb2 = 4096, 18432, 6144
+    S2 = (ra2 + rb2) * K2 // w
+    shard2 = ctx.alloc(S2, torch.bfloat16)
+    full2 = ctx.alloc(S2 * w, torch.bfloat16)
+    shard2.copy_(torch.randn(S2, device="cuda"))
+    x2 = torch.randn(8192, K2, device="cuda", dtype=torch.bfloat16)
+    torch.cuda.synchronize(); dist.barrier()
+
     def fused():
-        return ctx.all_gather_matmul(x, full, shard, S, rows_a * K, rows_b, K)
+        return ctx.all_gather_matmul(x2, full2, shard2, S2, ra2 * K2, rb2, K2)
+
     def split():
-        ctx.all_gather(full, shard, S)
-        return gemm_sm100.matmul_nt(x, full[rows_a * K:].view(rows_b, K))
+        ctx.all_gather(full2, shard2, S2)
+        return gemm_sm100.matmul_nt(x2, full2[ra2 * K2:].view(rb2, K2))
+
+    y_f, y_s = fused(), split()
+    torch.cuda.synchronize()
+    assert (y_f.float() - y_s.float()).abs().max() < 0.05 * y_s.float().abs().max() + 0.5
     out = {}
     for name, fn in (("fused", fused), ("split", split)):
         for _ in range(3):
@@ -151,7 +165,9 @@ def _ag_gemm():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[name] = t.item()
     if r == 0:
-        print(f"AG+GEMM fused {out['fused']:.3f} ms vs split {out['split']:.3f} ms (max over ranks)")
+        gb = S2 * w * 2 / 1e9
+        print(f"AG+GEMM (unit {gb:.2f} GB, GEMM 8192x6144x4096): fused {out['fused']:.3f} ms vs all-gather+GEMM "
+              f"{out['split']:.3f} ms (max over ranks)")
 
 
 def test_fused_allgather_gemm_2gpu():
