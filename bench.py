@@ -222,6 +222,9 @@ def run_b200(args):
     # wait on a collective bracketed by CUDA events (the bracket holds no kernels => elapsed == stall)
     exposed = None
     if world > 1 and hasattr(engine.optimizer, "measure_exposed"):
+        step_dev(0)  # settle: absorbs the rank skew left by the timing epilogue (host-side all-reduce of the timings)
+        torch.cuda.synchronize()
+        ds.comm.barrier()
         engine.optimizer.measure_exposed(True)
         for i in range(2):
             step_dev(i)

@@ -51,6 +51,38 @@ def _collectives():
         assert (dst.float() - want).abs().max() < tol * max(1.0, want.abs().max().item()), ddt
         ctx.reduce_scatter_accumulate(g, dst, S, 1.0 / w, accumulate=True)
         assert (dst.float() - 2 * want).abs().max() < 2 * tol * max(1.0, want.abs().max().item()), ddt
+    # ---- bandwidth of the two ZeRO-3 collectives at Llama-3-8B layer size (218 M bf16 elements per unit) --------
+    big = 218_112_000 // w // 8 * 8
+    sh = ctx.alloc(big, torch.bfloat16)
+    fu = ctx.alloc(big * w, torch.bfloat16)
+    dst32 = torch.zeros(big, dtype=torch.float32, device="cuda")
+
+    def timeit(fn, n=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record(); torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) / n], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    os.environ["DSB200_NVLS_RS"] = "1"
+    t_ag = timeit(lambda: ctx.all_gather(fu, sh, big))
+    t_rs = timeit(lambda: ctx.reduce_scatter_accumulate(fu, dst32, big, 1.0 / w, accumulate=False))
+    ref_full = torch.empty(big * w, dtype=torch.bfloat16, device="cuda")
+    ref_sh = torch.empty(big, dtype=torch.bfloat16, device="cuda")
+    t_ag_nccl = timeit(lambda: dist.all_gather_into_tensor(ref_full, sh))
+    t_rs_nccl = timeit(lambda: dist.reduce_scatter_tensor(ref_sh, fu))
+    if r == 0:
+        recv = big * (w - 1) * 2 / 1e9
+        print(f"unit all-gather  ({recv:.2f} GB received/rank): copy-engine {t_ag:.3f} ms = {recv / t_ag * 1e3:.0f} GB/s | "
+              f"NCCL {t_ag_nccl:.3f} ms = {recv / t_ag_nccl * 1e3:.0f} GB/s")
+        print(f"unit reduce-scatter ({recv:.2f} GB pulled/rank): fused kernel {t_rs:.3f} ms = {recv / t_rs * 1e3:.0f} GB/s | "
+              f"NCCL {t_rs_nccl:.3f} ms = {recv / t_rs_nccl * 1e3:.0f} GB/s")
     # ---- barrier + one-shot all-reduce ----------------------------------------------------------------
     ctx.barrier()
     t = ctx.alloc(4096, torch.float32)
