@@ -141,6 +141,8 @@ class ZeroShardedOptimizer:
         self.offload_pin = bool(oo.pin_memory) if oo else False
         self.offload_ratio = float(oo.ratio) if oo else 1.0
         self.grad_allreduce_enabled = lambda: True
+        from deepspeed_b200.runtime.zero.partitioned_param_profiler import PartitionedParameterProfiler
+        self.param_profiler = PartitionedParameterProfiler() if PartitionedParameterProfiler.enabled() else None
         self.replica_world = dist.get_world_size(replica_group) if replica_group is not None else 1
         # ---- ZeRO++ -----------------------------------------------------------------------
         self.qwz = bool(getattr(self.zc, "zero_quantized_weights", False)) and self.stage == 3 and self.shard_world > 1
@@ -562,8 +564,13 @@ class ZeroShardedOptimizer:
             return
         if forward and not self._trace_done:
             self._trace.append(rt.u.index)
+        prof = self.param_profiler
         if rt.state == NOT_GATHERED:
+            if prof is not None:
+                prof.count("fetch_miss", rt.u.full_numel)   # not prefetched: the gather is issued on demand
             self._launch_gather(rt)
+        elif prof is not None:
+            prof.count("fetch_hit", rt.u.full_numel)
         if rt.state == INFLIGHT:
             if rt.gather_event is not None and self.on_cuda:
                 self._stall_wait("all_gather", lambda: torch.cuda.current_stream().wait_event(rt.gather_event))
@@ -909,6 +916,11 @@ class ZeroShardedOptimizer:
                     seen.add(i)
                     order.append(i)
             self._trace = order
+            if self.shard_world > 1:
+                # every rank must walk the units in the same order or the prefetched collectives would mismatch
+                # (reference coordinator.py:237 assert_ints_same_as_other_ranks)
+                from deepspeed_b200.runtime.zero.utils import assert_ints_same_as_other_ranks
+                assert_ints_same_as_other_ranks(order, self.dp_group)
         self.micro_step += 1
 
     # =========================================================================================
