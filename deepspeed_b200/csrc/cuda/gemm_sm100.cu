@@ -189,9 +189,34 @@ __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v)
 }
 
 // Gather role: CTA `ci` of `nc` copies chunks ci, ci+nc, ... in the order "own shard first, then rank+1, ...".
-__device__ void ag_gather_role(const AgParams& ag, int ci, int nc)
+// The copy is done by the TMA engine, not by SM load/store instructions: one elected thread streams each chunk through a
+// ring of 3 x 64 KiB shared-memory buffers with  cp.async.bulk (peer global -> smem, mbarrier complete_tx)  followed by
+// cp.async.bulk (smem -> local global, bulk_group);  192 KiB in flight per CTA hides the NVLink round trip, so a dozen
+// gather CTAs saturate the links while leaving their SMs' issue slots idle.
+constexpr uint32_t AG_PIECE = 64 * 1024;
+constexpr int AG_BUFS = 3;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
 {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+
+__device__ void ag_gather_role(const AgParams& ag, int ci, int nc, uint8_t* smem)
+{
+    if (threadIdx.x != 0) return;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + AG_BUFS * AG_PIECE;  // AG_BUFS mbarriers after the ring
+    for (int b = 0; b < AG_BUFS; ++b) mbar_init(bar0 + 8 * b, 1);
+    fence_barrier_init();
     const int chunks_per_shard = static_cast<int>(ag.shard_bytes / ag.chunk_bytes);
+    uint32_t issued = 0;           // pieces issued so far (ring position = issued % AG_BUFS)
     for (int j = ci; j < ag.n_chunks; j += nc) {
         // visit order: shards rotated so that every rank starts pulling from a different peer
         const int k = j / chunks_per_shard;
@@ -201,24 +226,36 @@ __device__ void ag_gather_role(const AgParams& ag, int ci, int nc)
         const int64_t off = static_cast<int64_t>(within) * ag.chunk_bytes;
         const char* src = static_cast<const char*>(ag.peers[peer]) + off;
         char* dst = static_cast<char*>(ag.local_full) + static_cast<int64_t>(peer) * ag.shard_bytes + off;
-        const int64_t nvec = ag.chunk_bytes >> 4;
-        if (peer == ag.rank) {
-            for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) st_plain(dst + (i << 4), ld_plain(src + (i << 4)));
-        } else {
-            constexpr int kU = 4;
-            int64_t i = threadIdx.x;
-            for (; i + (kU - 1) * blockDim.x < nvec; i += kU * blockDim.x) {
-                Vec16 v[kU];
-#pragma unroll
-                for (int u = 0; u < kU; ++u) v[u] = ld_peer(src + ((i + u * blockDim.x) << 4));
-#pragma unroll
-                for (int u = 0; u < kU; ++u) st_plain(dst + ((i + u * blockDim.x) << 4), v[u]);
+        const int n_pieces = static_cast<int>((ag.chunk_bytes + AG_PIECE - 1) / AG_PIECE);
+        // software pipeline inside the chunk: loads run AG_BUFS-1 pieces ahead of the stores
+        int loaded = 0, stored = 0;
+        uint32_t first = issued;
+        while (stored < n_pieces) {
+            while (loaded < n_pieces && loaded - stored < AG_BUFS) {
+                const uint32_t slot = (first + loaded) % AG_BUFS;
+                // the store that last read this slot must have finished reading shared memory
+                if (first + loaded >= static_cast<uint32_t>(AG_BUFS)) tma_store_wait_read<0>();
+                const int64_t po = static_cast<int64_t>(loaded) * AG_PIECE;
+                const int64_t rem = ag.chunk_bytes - po;
+                const uint32_t bytes = static_cast<uint32_t>(rem < static_cast<int64_t>(AG_PIECE) ? rem : AG_PIECE);
+                mbar_expect_tx(bar0 + 8 * slot, bytes);
+                bulk_g2s(sbase + slot * AG_PIECE, src + po, bytes, bar0 + 8 * slot);
+                ++loaded;
             }
-            for (; i < nvec; i += blockDim.x) st_plain(dst + (i << 4), ld_peer(src + (i << 4)));
+            const uint32_t n = first + stored;
+            const uint32_t slot = n % AG_BUFS;
+            mbar_wait(bar0 + 8 * slot, (n / AG_BUFS) & 1);
+            const int64_t po = static_cast<int64_t>(stored) * AG_PIECE;
+            const int64_t rem2 = ag.chunk_bytes - po;
+            const uint32_t bytes = static_cast<uint32_t>(rem2 < static_cast<int64_t>(AG_PIECE) ? rem2 : AG_PIECE);
+            bulk_s2g(dst + po, sbase + slot * AG_PIECE, bytes);
+            tma_store_commit();
+            ++stored;
         }
+        issued = first + n_pieces;
+        tma_store_wait_all();  // the chunk's bytes are written before the flag is published
         __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_gpu_u32(ag.flags + chunk, ag.epoch);
+        st_release_gpu_u32(ag.flags + chunk, ag.epoch);
     }
 }
 
@@ -233,6 +270,8 @@ __device__ __forceinline__ void ag_wait_rows(const AgParams& ag, int n0, int row
     for (int c = c0; c <= c1; ++c) {
         while (ld_acquire_gpu_u32(ag.flags + c) != ag.epoch) __nanosleep(64);
     }
+    // the chunk was written through the async proxy (bulk copies) and is about to be read through it (TMA loads)
+    asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -255,7 +294,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int mma_ctas = ag.enabled ? static_cast<int>(gridDim.x) - ag.comm_ctas : static_cast<int>(gridDim.x);
 
     if (ag.enabled && static_cast<int>(blockIdx.x) >= mma_ctas) {
-        ag_gather_role(ag, static_cast<int>(blockIdx.x) - mma_ctas, ag.comm_ctas);
+        ag_gather_role(ag, static_cast<int>(blockIdx.x) - mma_ctas, ag.comm_ctas, smem);
         return;
     }
 
