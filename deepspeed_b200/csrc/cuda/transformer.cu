@@ -107,41 +107,51 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
                 float* __restrict__ db_part, int rows, int hidden)
 {
     __shared__ float scratch[64];
+    extern __shared__ __align__(16) uint8_t w_smem_raw[];  // the weight vector, staged once per block
+    T* w_s = reinterpret_cast<T*>(w_smem_raw);
     constexpr int kPer = Elem<T>::kPerVec;
     const int nvec = hidden / kPer;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st_plain(w_s + v * kPer, ld_plain(w + v * kPer));
+    __syncthreads();
     float dw_acc[kMaxVecPerThread][kPer];
     float db_acc[kMaxVecPerThread][kPer];
-    float wf[kMaxVecPerThread][kPer];
 #pragma unroll
     for (int k = 0; k < kMaxVecPerThread; ++k) {
-        const int v = threadIdx.x + k * blockDim.x;
 #pragma unroll
         for (int e = 0; e < kPer; ++e) {
             dw_acc[k][e] = 0.f;
             db_acc[k][e] = 0.f;
-            wf[k][e] = 0.f;
         }
-        if (v < nvec) Elem<T>::unpack(ld_plain(w + v * kPer), wf[k]);
     }
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int64_t base = static_cast<int64_t>(row) * hidden;
         const float rstd = rstd_in[row];
         const float mean = kLN ? mean_in[row] : 0.f;
-        Vec16 cx[kMaxVecPerThread], cdy[kMaxVecPerThread];
-        float s1 = 0.f, s2 = 0.f;  // sum(g), sum(g * xhat)   with g = dy * w
+        // issue every global load of the row up front (x, dy and the residual-branch gradient): 12 x 16 B in flight
+        // per thread instead of 8 followed by a dependent 4 after the block reduction
+        Vec16 cx[kMaxVecPerThread], cdy[kMaxVecPerThread], cres[kMaxVecPerThread];
 #pragma unroll
         for (int k = 0; k < kMaxVecPerThread; ++k) {
             const int v = threadIdx.x + k * blockDim.x;
             if (v < nvec) {
                 cx[k] = ld_stream(x + base + v * kPer);
                 cdy[k] = ld_stream(dy + base + v * kPer);
-                float xf[kPer], df[kPer];
+                if (dres) cres[k] = ld_stream(dres + base + v * kPer);
+            }
+        }
+        float s1 = 0.f, s2 = 0.f;  // sum(g), sum(g * xhat)   with g = dy * w
+#pragma unroll
+        for (int k = 0; k < kMaxVecPerThread; ++k) {
+            const int v = threadIdx.x + k * blockDim.x;
+            if (v < nvec) {
+                float xf[kPer], df[kPer], wf[kPer];
                 Elem<T>::unpack(cx[k], xf);
                 Elem<T>::unpack(cdy[k], df);
+                Elem<T>::unpack(ld_plain(w_s + v * kPer), wf);
 #pragma unroll
                 for (int e = 0; e < kPer; ++e) {
                     const float xhat = (xf[e] - mean) * rstd;
-                    const float g = df[e] * wf[k][e];
+                    const float g = df[e] * wf[e];
                     s1 += g;
                     s2 = fmaf(g, xhat, s2);
                     dw_acc[k][e] = fmaf(df[e], xhat, dw_acc[k][e]);
@@ -161,18 +171,19 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
         for (int k = 0; k < kMaxVecPerThread; ++k) {
             const int v = threadIdx.x + k * blockDim.x;
             if (v < nvec) {
-                float xf[kPer], df[kPer], o[kPer];
+                float xf[kPer], df[kPer], wf[kPer], o[kPer];
                 Elem<T>::unpack(cx[k], xf);
                 Elem<T>::unpack(cdy[k], df);
+                Elem<T>::unpack(ld_plain(w_s + v * kPer), wf);
 #pragma unroll
                 for (int e = 0; e < kPer; ++e) {
                     const float xhat = (xf[e] - mean) * rstd;
-                    const float g = df[e] * wf[k][e];
+                    const float g = df[e] * wf[e];
                     o[e] = rstd * (g - m1 - xhat * m2);
                 }
                 if (dres) {
                     float r[kPer];
-                    Elem<T>::unpack(ld_stream(dres + base + v * kPer), r);
+                    Elem<T>::unpack(cres[k], r);
 #pragma unroll
                     for (int e = 0; e < kPer; ++e) o[e] += r[e];
                 }
@@ -579,9 +590,9 @@ DSB_EXPORT int dsb_norm_fwd(const void* x, const void* residual, const void* w, 
 
 DSB_EXPORT int dsb_norm_bwd_grid(int rows)
 {
-    // HBM-bound: as many resident CTAs as the register budget allows (~6 per SM at 128 threads);
-    // more CTAs = more dw partial rows, so stop there.
-    const int cap = kSmCountB200 * 6;
+    // HBM-bound persistent kernel: exactly one wave of resident CTAs (4 per SM at 128 threads x ~120 registers); more
+    // CTAs only add a second, half-empty wave and more dw partial rows for the column-sum pass.
+    const int cap = kSmCountB200 * 4;
     return rows < cap ? rows : cap;
 }
 
@@ -599,11 +610,11 @@ DSB_EXPORT int dsb_norm_bwd(const void* dy, const void* x, const void* w, const 
     const int grid = dsb_norm_bwd_grid(rows);
     DISPATCH_T(dtype, T, {
         if (kind == 0)
-            norm_bwd_kernel<T, false><<<grid, threads, 0, stream>>>((const T*)dy, (const T*)x, (const T*)w, mean,
+            norm_bwd_kernel<T, false><<<grid, threads, hidden * sizeof(T), stream>>>((const T*)dy, (const T*)x, (const T*)w, mean,
                                                                      rstd, (const T*)dres, (T*)dx, dw_part, db_part,
                                                                      rows, hidden);
         else
-            norm_bwd_kernel<T, true><<<grid, threads, 0, stream>>>((const T*)dy, (const T*)x, (const T*)w, mean,
+            norm_bwd_kernel<T, true><<<grid, threads, hidden * sizeof(T), stream>>>((const T*)dy, (const T*)x, (const T*)w, mean,
                                                                     rstd, (const T*)dres, (T*)dx, dw_part, db_part,
                                                                     rows, hidden);
     })

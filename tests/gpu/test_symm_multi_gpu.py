@@ -172,8 +172,10 @@ def _ag_gemm():
     x2 = torch.randn(8192, K2, device="cuda", dtype=torch.bfloat16)
     torch.cuda.synchronize(); dist.barrier()
 
+    comm = [int(os.environ.get("DSB200_AG_GEMM_CTAS", "16"))]
+
     def fused():
-        return ctx.all_gather_matmul(x2, full2, shard2, S2, ra2 * K2, rb2, K2)
+        return ctx.all_gather_matmul(x2, full2, shard2, S2, ra2 * K2, rb2, K2, comm_ctas=comm[0])
 
     def split():
         ctx.all_gather(full2, shard2, S2)
@@ -183,7 +185,9 @@ def _ag_gemm():
     torch.cuda.synchronize()
     assert (y_f.float() - y_s.float()).abs().max() < 0.05 * y_s.float().abs().max() + 0.5
     out = {}
-    for name, fn in (("fused", fused), ("split", split)):
+    variants = [("split", split, 16)] + [(f"fused/{c}ctas", fused, c) for c in (8, 16, 24, 32)]
+    for name, fn, c in variants:
+        comm[0] = c
         for _ in range(3):
             fn()
         torch.cuda.synchronize(); dist.barrier()
@@ -197,6 +201,8 @@ def _ag_gemm():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[name] = t.item()
     if r == 0:
+        print("AG+GEMM sweep: " + ", ".join(f"{k} {v:.3f} ms" for k, v in out.items()))
+        out["fused"] = min(v for k, v in out.items() if k.startswith("fused"))
         gb = S2 * w * 2 / 1e9
         print(f"AG+GEMM (unit {gb:.2f} GB, GEMM 8192x6144x4096): fused {out['fused']:.3f} ms vs all-gather+GEMM "
               f"{out['split']:.3f} ms (max over ranks)")
