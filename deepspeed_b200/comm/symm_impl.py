@@ -239,7 +239,7 @@ class SymmContext:
                                           CH_AG, ctypes.c_uint32(0), 0, self.ag_ctas, N.stream())
         N.check(rc, "symm_all_gather")
 
-    def all_gather_matmul(self, a, full, shard, shard_numel, w_offset, n_rows, k, chunk_bytes=1 << 20, comm_ctas=16):
+    def all_gather_matmul(self, a, full, shard, shard_numel, w_offset, n_rows, k, chunk_bytes=1 << 20, comm_ctas=32):
         """``a [M,K] @ W^T`` where ``W [n_rows, K]`` lives ``w_offset`` elements into the gathered unit buffer
         ``full`` — ONE kernel that pulls every rank's shard over NVLink (trailing ``comm_ctas`` CTAs, chunk flags
         with release/acquire) while the tcgen05 tiles of rows that already arrived are being multiplied.

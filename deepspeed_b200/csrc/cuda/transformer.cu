@@ -111,7 +111,8 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
     T* w_s = reinterpret_cast<T*>(w_smem_raw);
     constexpr int kPer = Elem<T>::kPerVec;
     const int nvec = hidden / kPer;
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) st_plain(w_s + v * kPer, ld_plain(w + v * kPer));
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x)
+        *reinterpret_cast<Vec16*>(w_s + v * kPer) = ld_plain(w + v * kPer);  // generic store: w_s is shared memory
     __syncthreads();
     float dw_acc[kMaxVecPerThread][kPer];
     float db_acc[kMaxVecPerThread][kPer];
@@ -147,7 +148,7 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
                 float xf[kPer], df[kPer], wf[kPer];
                 Elem<T>::unpack(cx[k], xf);
                 Elem<T>::unpack(cdy[k], df);
-                Elem<T>::unpack(ld_plain(w_s + v * kPer), wf);
+                Elem<T>::unpack(*reinterpret_cast<const Vec16*>(w_s + v * kPer), wf);
 #pragma unroll
                 for (int e = 0; e < kPer; ++e) {
                     const float xhat = (xf[e] - mean) * rstd;
@@ -174,7 +175,7 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
                 float xf[kPer], df[kPer], wf[kPer], o[kPer];
                 Elem<T>::unpack(cx[k], xf);
                 Elem<T>::unpack(cdy[k], df);
-                Elem<T>::unpack(ld_plain(w_s + v * kPer), wf);
+                Elem<T>::unpack(*reinterpret_cast<const Vec16*>(w_s + v * kPer), wf);
 #pragma unroll
                 for (int e = 0; e < kPer; ++e) {
                     const float xhat = (xf[e] - mean) * rstd;
