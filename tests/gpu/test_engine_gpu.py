@@ -94,3 +94,84 @@ def test_checkpoint_roundtrip_gpu(tmp_path):
     e2.backward(l2); e2.step()
     l1b, l2b = e1(ids, labels=ids).item(), e2(ids, labels=ids).item()
     assert abs(l1b - l2b) < 2e-3
+
+
+@pytest.mark.parametrize("tier", ["cpu", "nvme"])
+def test_offload_tiers_match_device_optimizer(tier, tmp_path):
+    """ZeRO-3 with the optimizer state on the host (pinned memory, AVX Adam) or on NVMe-backed swap files streams through
+    the same math as the on-device fused Adam (config #4 of BASELINE.json at toy size)."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.models.llama import LlamaForCausalLM, llama_config
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    cfg = llama_config("tiny", hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=2,
+                       vocab_size=1024, num_hidden_layers=2)
+    ids = torch.randint(0, cfg.vocab_size, (2, 64), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    results = {}
+    for mode in ("device", tier):
+        torch.manual_seed(0)
+        with torch.device("cuda"):
+            model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+        zo = {"stage": 3, "stage3_param_persistence_threshold": 0}
+        conf = {"train_micro_batch_size_per_gpu": 2, "bf16": {"enabled": True}, "gradient_clipping": 1.0,
+                "optimizer": {"type": "AdamW", "params": {"lr": 1e-3, "weight_decay": 0.1}}, "zero_optimization": zo}
+        if mode == "cpu":
+            zo["offload_optimizer"] = {"device": "cpu", "pin_memory": True}
+        elif mode == "nvme":
+            zo["offload_optimizer"] = {"device": "nvme", "nvme_path": str(tmp_path), "b200_swap_window": 100_000,
+                                       "pipeline_read": True, "pipeline_write": True}
+            conf["aio"] = {"block_size": 1 << 20, "queue_depth": 8}
+        eng, *_ = ds.initialize(model=model, config=conf)
+        losses = []
+        for _ in range(4):
+            loss = eng(ids, labels=ids)
+            eng.backward(loss)
+            eng.step()
+            losses.append(loss.item())
+        results[mode] = (losses, [safe_get_full_fp32_param(p).float().cpu() for p in model.parameters()])
+        eng.destroy()
+    la, lb = results["device"][0], results[tier][0]
+    assert all(abs(a - b) < 2e-2 for a, b in zip(la, lb)), (la, lb)
+    worst = max((a - b).abs().max().item() for a, b in zip(results["device"][1], results[tier][1]))
+    assert worst < 5e-3, worst
+
+
+def test_mixtral_moe_and_phi3_zero2_train():
+    import deepspeed_b200 as ds
+    from deepspeed_b200.models.llama import LlamaForCausalLM, llama_config
+    from deepspeed_b200.models.mixtral import MixtralConfig, MixtralForCausalLM
+    torch.manual_seed(0)
+    mcfg = MixtralConfig(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                         num_key_value_heads=2, num_local_experts=4, num_experts_per_tok=2, max_position_embeddings=256)
+    with torch.device("cuda"):
+        moe = MixtralForCausalLM(mcfg).to(torch.bfloat16)
+    eng, *_ = ds.initialize(model=moe, config={"train_micro_batch_size_per_gpu": 2, "bf16": {"enabled": True},
+                                               "optimizer": {"type": "AdamW", "params": {"lr": 2e-3}},
+                                               "zero_optimization": {"stage": 2}})
+    ids = torch.randint(0, 512, (2, 64), device="cuda")
+    first = last = None
+    for _ in range(8):
+        out = eng(ids, labels=ids)
+        loss = out[0] if isinstance(out, tuple) else out
+        eng.backward(loss)
+        eng.step()
+        first = first if first is not None else loss.item()
+        last = loss.item()
+    assert last < first - 0.3, (first, last)
+    eng.destroy()
+    # Phi-3-mini shaped (MHA, fused qkv/gate_up) under ZeRO-2 with gradient accumulation
+    cfg = llama_config("phi3-mini", hidden_size=256, intermediate_size=512, num_attention_heads=4, num_key_value_heads=4,
+                       vocab_size=1024, num_hidden_layers=2)
+    with torch.device("cuda"):
+        phi = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    eng, *_ = ds.initialize(model=phi, config={"train_micro_batch_size_per_gpu": 2, "gradient_accumulation_steps": 2,
+                                               "bf16": {"enabled": True}, "gradient_clipping": 1.0,
+                                               "optimizer": {"type": "AdamW", "params": {"lr": 2e-3}},
+                                               "zero_optimization": {"stage": 2}})
+    ids = torch.randint(0, 1024, (2, 64), device="cuda")
+    losses = []
+    for _ in range(12):
+        loss = eng(ids, labels=ids)
+        eng.backward(loss)
+        eng.step()
+        losses.append(loss.item())
+    assert eng.global_steps == 6 and losses[-1] < losses[0] - 0.3, losses
