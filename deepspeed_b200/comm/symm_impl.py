@@ -163,7 +163,10 @@ class SymmContext:
         self._tag = 0
         self.segments: List[_Segment] = []
         self.epochs = [1] * self.lib.dsb_symm_channels()
-        self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "64"))
+        # CTAs given to the fused reduce-scatter(+Adam) kernels: each rank reduces and steps 1/world of every unit, so small
+        # worlds need more CTAs per kernel to keep up with backward (measured on Llama-3-8B: 2 GPUs 394.8 ms @64 -> 390.1 ms
+        # @128; 8 GPUs prefer 64, which leaves more SM issue slots to the concurrent GEMMs)
+        self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "128" if self.world <= 2 else "64"))
         self.ag_ctas = int(os.environ.get("DSB200_SYMM_AG_CTAS", str(self.ctas)))
         self.ag_mode = os.environ.get("DSB200_SYMM_AG", "ce").lower()  # "ce" (DMA engines) | "kernel" (SM pull)
         # signal pads live in their own small segment (never multicast-bound)
