@@ -53,6 +53,13 @@ elif which == "gemm":
     for _ in range(3):
         flush.zero_()
         gemm_sm100.matmul_nt(a, b)
+elif which == "gemm2cta":
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    a = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16)
+    b = torch.randn(6144, 4096, device=d, dtype=torch.bfloat16)
+    for _ in range(3):
+        flush.zero_()
+        gemm_sm100.matmul_nt_2cta(a, b)
 elif which == "paged":
     from deepspeed_b200.ops.kernels import ragged_ops as R
     hq, hkv, dd, bs, seqs, ctx = 32, 8, 128, 128, 64, 2048
