@@ -1,0 +1,124 @@
+"""Activation checkpointing, comm facade + comms logger, monitors, dataloaders, timers (host tier)."""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+from tests.common import run_distributed
+
+
+def test_activation_checkpointing_matches_plain_and_rng():
+    from deepspeed_b200.runtime.activation_checkpointing import checkpointing as ck
+    ck.reset()
+    ck.configure(None, partition_activations=False, checkpoint_in_cpu=False)
+    torch.manual_seed(0)
+    lin1, lin2 = nn.Linear(16, 32), nn.Linear(32, 16)
+    drop = nn.Dropout(0.3)
+
+    def block(x, scale):
+        return lin2(drop(torch.relu(lin1(x)))) * scale
+
+    x = torch.randn(4, 16, requires_grad=True)
+    torch.manual_seed(5)
+    y = ck.checkpoint(block, x, 2.0)
+    y.sum().backward()
+    g_ck, gw_ck = x.grad.clone(), lin1.weight.grad.clone()
+    x.grad = None
+    lin1.weight.grad = None
+    lin2.weight.grad = None
+    torch.manual_seed(5)
+    y2 = block(x, 2.0)
+    y2.sum().backward()
+    torch.testing.assert_close(y, y2)            # same dropout mask: RNG state is captured and replayed
+    torch.testing.assert_close(g_ck, x.grad)
+    torch.testing.assert_close(gw_ck, lin1.weight.grad)
+    # CPU checkpointing + non-tensor / multiple outputs
+    ck.configure(None, checkpoint_in_cpu=True)
+
+    def two(x):
+        return x * 2, x.sum()
+
+    a, b = ck.checkpoint(two, x)
+    (a.sum() + b).backward()
+    assert ck.is_configured()
+    ck.reset()
+
+
+def _comm_worker():
+    import deepspeed_b200.comm as dist
+    dist.configure(enabled=True, prof_all=True, verbose=False)
+    r, w = dist.get_rank(), dist.get_world_size()
+    t = torch.full((8, ), float(r + 1))
+    dist.all_reduce(t)
+    assert torch.all(t == sum(range(1, w + 1)))
+    out = torch.empty(8 * w)
+    dist.all_gather_into_tensor(out, torch.full((8, ), float(r)))
+    assert torch.equal(out, torch.arange(w).float().repeat_interleave(8))
+    rs = torch.empty(4)
+    dist.reduce_scatter_tensor(rs, torch.arange(4 * w).float())
+    assert torch.equal(rs, torch.arange(4 * w).float()[r * 4:(r + 1) * 4] * w)
+    a2a = torch.empty(2 * w)
+    dist.all_to_all_single(a2a, torch.arange(2 * w).float() + 100 * r)
+    assert a2a.view(w, 2)[:, 0].tolist() == [100 * s + 2 * r for s in range(w)]
+    b = torch.tensor([float(r)])
+    dist.broadcast(b, src=1)
+    assert b.item() == 1.0
+    objs = [None] * w
+    dist.all_gather_object(objs, {"rank": r})
+    assert [o["rank"] for o in objs] == list(range(w))
+    dist.barrier()
+    dist.monitored_barrier()
+    lg = dist.comms_logger
+    assert lg is not None and any("all_reduce" in k for k in lg.comms_dict), list(lg.comms_dict)
+    dist.log_summary()
+    os.environ["DSB200_COMM_ALL_REDUCE_OFF"] = "1"
+    z = torch.ones(2)
+    dist.all_reduce(z)                      # kill switch: op becomes a no-op
+    assert torch.all(z == 1)
+    del os.environ["DSB200_COMM_ALL_REDUCE_OFF"]
+
+
+def test_comm_facade_and_logger_ws2():
+    run_distributed(_comm_worker, 2)
+
+
+def test_csv_monitor_and_master(tmp_path):
+    from deepspeed_b200.monitor.monitor import MonitorMaster
+    from deepspeed_b200.runtime.config import DeepSpeedConfig
+    cfg = DeepSpeedConfig({"train_batch_size": 1, "csv_monitor": {"enabled": True, "output_path": str(tmp_path),
+                                                                  "job_name": "job"}})
+    mon = MonitorMaster(cfg.monitor_config)
+    assert mon.enabled
+    mon.write_events([("Train/Samples/lr", 0.1, 1), ("Train/Samples/train_loss", 2.5, 1)])
+    mon.write_events([("Train/Samples/lr", 0.05, 2)])
+    txt = (tmp_path / "job" / "Train_Samples_lr.csv").read_text().strip().splitlines()
+    assert txt[0] == "step,lr" and txt[1:] == ["1,0.1", "2,0.05"]
+
+
+def test_dataloaders():
+    from deepspeed_b200.runtime.dataloader import DeepSpeedDataLoader, RepeatingLoader
+    ds = torch.utils.data.TensorDataset(torch.arange(10).float())
+    dl = DeepSpeedDataLoader(ds, batch_size=4, pin_memory=False, local_rank=0, tput_timer=None,
+                             data_parallel_world_size=2, data_parallel_rank=1, dataloader_drop_last=True)
+    batches = list(dl)
+    assert len(batches) == 1 and batches[0][0].numel() == 4          # 5 samples on this rank, drop_last
+    rep = RepeatingLoader([1, 2, 3])
+    it = iter(rep)
+    assert [next(it) for _ in range(7)] == [1, 2, 3, 1, 2, 3, 1]
+
+
+def test_timers_and_throughput():
+    from deepspeed_b200.utils.timer import SynchronizedWallClockTimer, ThroughputTimer
+    t = SynchronizedWallClockTimer()
+    t("fwd").start()
+    sum(range(10000))
+    t("fwd").stop()
+    assert t("fwd").elapsed(reset=False) >= 0 and "fwd" in t.get_timers()
+    means = t.get_mean(["fwd"], reset=True)
+    assert "fwd" in means
+    tp = ThroughputTimer(batch_size=8, start_step=1)
+    for _ in range(4):
+        tp.start()
+        tp.stop(global_step=True)
+    assert tp.global_step_count == 4 and tp.avg_samples_per_sec() > 0
