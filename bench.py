@@ -246,7 +246,9 @@ def run_b200(args):
             pass
         flops = cfg.flops_per_token(S) * val / world
         out = {
-            "metric": "tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B ZeRO-3 bf16 training",
+            "metric": ("tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B ZeRO-3 bf16 training"
+                       if (args.model == "llama3-8b" and args.zero_stage == 3) else
+                       f"tokens/sec (whole job, device-timed, max over ranks) {args.model} ZeRO-{args.zero_stage} bf16 training"),
             "value": val,
             "unit": "tokens/s",
             "n_gpus": world,
