@@ -305,3 +305,40 @@ def _moe_symm_vs_nccl():
 def test_moe_symm_dispatch_combine_2gpu():
     _need(2)
     run_distributed(_moe_symm_vs_nccl, 2, backend="nccl")
+
+
+def _ragged_tp2():
+    """Tensor-parallel ragged inference on 2 GPUs (weights sharded by head / intermediate dim, row-parallel outputs summed
+    with the NVLink one-shot all-reduce) against the unsharded HF model."""
+    import torch.distributed as dist
+    from transformers import AutoConfig, AutoModelForCausalLM
+    from deepspeed_b200.inference.v2 import build_hf_engine
+    cfg = AutoConfig.for_model("llama", vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=8,
+                               num_key_value_heads=4, intermediate_size=512, max_position_embeddings=512)
+    torch.manual_seed(0)
+    m = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).cuda().eval()
+    e = build_hf_engine(m, {"tensor_parallel": {"tp_size": 2}, "state_manager": {
+        "max_context": 512, "max_ragged_batch_size": 512, "max_ragged_sequence_count": 8,
+        "memory_config": {"mode": "allocate", "size": 32}}})
+    g = torch.Generator().manual_seed(3)
+    p0, p1 = torch.randint(0, 512, (70, ), generator=g), torch.randint(0, 512, (9, ), generator=g)
+    lg = e.put([0, 1], [p0, p1])
+    with torch.no_grad():
+        r0, r1 = m(p0[None].cuda()).logits[0, -1], m(p1[None].cuda()).logits[0, -1]
+    for a, b in ((lg[0], r0), (lg[1], r1)):
+        assert torch.nn.functional.cosine_similarity(a.float(), b.float(), dim=0) > 0.995
+    cur = p0
+    for _ in range(3):                      # graphed decode steps with the all-reduce inside the graph
+        n0, n1 = lg[0].argmax().reshape(1).cpu(), lg[1].argmax().reshape(1).cpu()
+        cur = torch.cat([cur, n0])
+        lg = e.put([0, 1], [n0, n1])
+    with torch.no_grad():
+        r0 = m(cur[None].cuda()).logits[0, -1]
+    assert torch.nn.functional.cosine_similarity(lg[0].float(), r0.float(), dim=0) > 0.99
+    dist.barrier()
+
+
+def test_ragged_inference_tp2_gpu():
+    _need(2)
+    pytest.importorskip("transformers")
+    run_distributed(_ragged_tp2, 2, backend="nccl")
