@@ -8,3 +8,26 @@ from deepspeed_b200.ops.kernels.moe_ops import top_k_gating, scatter as moe_scat
 from deepspeed_b200.ops.kernels.transformer_ops import (rms_norm, layer_norm, gated_act as gated_activation,  # noqa: F401
                                                         bias_act as bias_activation)
 from deepspeed_b200.ops.gemm import matmul_nt as blas_linear  # noqa: F401
+
+
+def mixed_gemm(x, qweight, bias=None):
+    """Weight-only-quantised GEMM (reference cutlass ``mixed_gemm``): ``qweight`` is a ``QuantizedWeight`` (int8/int4/fp8/fp6);
+    it is dequantised group-wise into bf16 and multiplied on the tensor cores."""
+    from deepspeed_b200.inference.quantization.layers import maybe_quantized_linear
+    return maybe_quantized_linear(x, qweight, bias)
+
+
+def moe_gemm(x_sorted, expert_weights, offsets, out=None):
+    """Grouped GEMM over expert-sorted rows (reference cutlass ``moe_gemm``): ``x_sorted`` [rows, K] with expert e owning
+    rows ``offsets[e]:offsets[e+1]``, ``expert_weights`` [E, N, K] (or a list).  One tensor-core GEMM per non-empty expert."""
+    import torch
+    off = offsets.tolist() if torch.is_tensor(offsets) else list(offsets)
+    E = len(off) - 1
+    n_out = expert_weights[0].shape[0]
+    if out is None:
+        out = torch.empty(x_sorted.shape[0], n_out, dtype=x_sorted.dtype, device=x_sorted.device)
+    for e in range(E):
+        s, t = off[e], off[e + 1]
+        if t > s:
+            torch.mm(x_sorted[s:t], expert_weights[e].t(), out=out[s:t])
+    return out

@@ -99,3 +99,37 @@ class DeepSpeedCPUAdam(torch.optim.Optimizer):
                                        eps=group["eps"], weight_decay=group["weight_decay"], step=st["step"],
                                        adamw=self.adam_w_mode, bias_correction=group["bias_correction"])
         return loss
+
+
+# ---- binding-level API of the reference op (``csrc/adam/cpu_adam.cpp``: create_adam / adam_update / destroy_adam) ----------
+_registry = {}
+
+
+def create_adam(optimizer_id, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, adamw_mode=True,
+                should_log=False):
+    _registry[optimizer_id] = dict(lr=alpha, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, adamw=adamw_mode)
+    return 0
+
+
+def adam_update(optimizer_id, step, lr, beta1, beta2, epsilon, weight_decay, bias_correction, params, grads, exp_avg,
+                exp_avg_sq):
+    cfg = _registry[optimizer_id]
+    cpu_adam_flat(params.view(-1), grads.view(-1), exp_avg.view(-1), exp_avg_sq.view(-1), None, lr=lr, beta1=beta1,
+                  beta2=beta2, eps=epsilon, weight_decay=weight_decay, step=step, adamw=cfg["adamw"],
+                  bias_correction=bool(bias_correction))
+    return 0
+
+
+def adam_update_copy(optimizer_id, step, lr, beta1, beta2, epsilon, weight_decay, bias_correction, params, grads, exp_avg,
+                     exp_avg_sq, device_params):
+    cfg = _registry[optimizer_id]
+    lp = torch.empty(params.numel(), dtype=device_params.dtype)
+    cpu_adam_flat(params.view(-1), grads.view(-1), exp_avg.view(-1), exp_avg_sq.view(-1), lp, lr=lr, beta1=beta1, beta2=beta2,
+                  eps=epsilon, weight_decay=weight_decay, step=step, adamw=cfg["adamw"], bias_correction=bool(bias_correction))
+    device_params.copy_(lp.view_as(device_params), non_blocking=True)
+    return 0
+
+
+def destroy_adam(optimizer_id):
+    _registry.pop(optimizer_id, None)
+    return 0

@@ -197,3 +197,13 @@ class Quantizer:
     def dequantize(self, q, params, dtype=torch.bfloat16):
         groups = params.shape[0]
         return dequantize(q, params, groups, self.q_bits, self.q_type, dtype)
+
+
+def loco_swizzle_quant(x, err, groups, num_bits=8, q_type=Symmetric, pipeline_size=1, nodes=1, devices_per_node=1, err_beta=0.8):
+    """LoCo variant of :func:`swizzle_quant`: quantise ``x + err`` and fold the new quantisation error back into ``err``
+    (exponential average) so it is re-injected next step (reference ``loco_swizzle_quant``)."""
+    comp = x.float() + err
+    q, params = swizzle_quant(comp.to(x.dtype), groups, num_bits, q_type, pipeline_size, nodes, devices_per_node)
+    deq = fake_quantize(comp.to(x.dtype).contiguous().view(-1), groups, num_bits, q_type).view_as(comp).float()
+    err.mul_(err_beta).add_(comp - deq, alpha=1 - err_beta)
+    return q, params

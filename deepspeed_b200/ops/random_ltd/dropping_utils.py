@@ -70,3 +70,13 @@ class ScatterTokens(torch.autograd.Function):
         if not ctx.batch_first:
             full, part = full.transpose(0, 1), part.transpose(0, 1)
         return full, part, None, None
+
+
+def mask_gather_gpt(attn_mask, reserved_length):
+    """Causal masks only need their top-left corner (reference ``mask_gather_gpt``)."""
+    return attn_mask[:, :, :reserved_length, :reserved_length]
+
+
+def mask_gather_bert(attn_mask, sorted_indices):
+    """Slice a full [B,1,S,S] mask down to the kept tokens (reference ``mask_gather_bert``)."""
+    return K.mask_gather(attn_mask, sorted_indices)

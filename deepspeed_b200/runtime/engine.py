@@ -707,6 +707,46 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         if self.optimizer is not None and getattr(self.optimizer, "rs_stream", None) is not None:
             torch.cuda.current_stream().wait_stream(self.optimizer.rs_stream)
 
+    def allreduce_bucket(self, bucket, dp_group=None, dp_world_size=None):
+        """Average one list of same-dtype tensors over the DP group with a single flattened collective."""
+        from deepspeed_b200.ops.flatten import flatten, unflatten
+        group = dp_group or self.seq_data_parallel_group
+        world = dp_world_size or dist.get_world_size(group)
+        flat = flatten(bucket)
+        if self._config.prescale_gradients and self._config.gradient_predivide_factor != 1.0:
+            flat.mul_(1.0 / self._config.gradient_predivide_factor)
+            dist.all_reduce(flat, group=group)
+            flat.mul_(self._config.gradient_predivide_factor / world)
+        else:
+            dist.all_reduce(flat, group=group)
+            flat.mul_(1.0 / world)
+        return flat
+
+    def allreduce_and_copy(self, small_bucket, dp_group=None, dp_world_size=None):
+        from deepspeed_b200.ops.flatten import unflatten
+        flat = self.allreduce_bucket(small_bucket, dp_group, dp_world_size)
+        for buf, synced in zip(small_bucket, unflatten(flat, small_bucket)):
+            buf.copy_(synced)
+
+    def buffered_allreduce_fallback(self, grads=None, elements_per_buffer=500000000):
+        """Explicit DP all-reduce of ``.grad`` tensors in dtype-homogeneous buckets (reference ``engine.py:2611``); only
+        needed for parameters that are not managed by the sharded optimizer (it reduces its own)."""
+        if grads is None:
+            grads = [p.grad for p in self.module.parameters() if p.grad is not None and not hasattr(p, "_ds_zero")]
+        by_dtype = {}
+        for g in grads:
+            by_dtype.setdefault(g.dtype, []).append(g)
+        for gs in by_dtype.values():
+            bucket, n = [], 0
+            for g in gs:
+                if n + g.numel() > elements_per_buffer and bucket:
+                    self.allreduce_and_copy(bucket)
+                    bucket, n = [], 0
+                bucket.append(g)
+                n += g.numel()
+            if bucket:
+                self.allreduce_and_copy(bucket)
+
     def sparse_allreduce(self, sparse_tensor, dp_group=None):
         from deepspeed_b200.runtime.sparse_tensor import sparse_allreduce
         return sparse_allreduce(sparse_tensor, dp_group or self.seq_data_parallel_group)

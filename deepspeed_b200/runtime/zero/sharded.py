@@ -1315,6 +1315,23 @@ class ZeroShardedOptimizer:
                 for k, v in sd["flat_state"].items():
                     self.flat_opt.state_tensors()[k].copy_(v)
 
+    # ---- names used by the reference's BF16_Optimizer / coordinator (API compatibility) ------------------------
+    def update_lp_params(self):
+        """fp32 master -> low-precision parameters (+ all-gather for sharded stages)."""
+        self._refresh_lp_from_master()
+
+    def update_hp_grads(self, clear_lp_grads=False):
+        """Gradients are accumulated into the fp32/bf16 shard arena as they are reduced; nothing to fold here."""
+        if clear_lp_grads:
+            self.zero_grad()
+
+    def reset_step(self):
+        """Forget the recorded unit order (the module graph changed): it is re-traced on the next iteration."""
+        self._trace, self._trace_done = [], False
+
+    def clear_lp_grads(self):
+        self.zero_grad()
+
     def _refresh_lp_from_master(self):
         if self.master is not None:
             self._master_to_lp(0, self.arena_numel)

@@ -127,3 +127,16 @@ def safe_set_local_optimizer_state(param, value, optim_state_key):
     st = zo.flat_opt.state_tensors()
     v = _local_view(zo, param, st[optim_state_key])
     v.copy_(value.to(v.device, v.dtype).view(-1))
+
+
+def get_hp_fragment_mapping(lp_param, lp_start=None, flat_hp_partition=None, gradient_dict=None, offload_gradient_dict=None,
+                            use_offload=False, param_group_index=0, partition_start=None, partition_size=None):
+    """Where does ``lp_param`` live in this rank's flat fp32 partition?  Returns a list of
+    ``(param_start, arena_start, length)`` triples (reference ``tensor_fragment.py:312`` returns one ``tensor_fragment``
+    because its partitions are per param group; here a parameter may straddle two ranks' shards of its unit)."""
+    from deepspeed_b200.runtime.zero.units import param_fragments
+    zo = _zo(lp_param)
+    if zo is None:
+        return []
+    rt, slot = zo.unit_of_param[id(lp_param)], zo.slot_of_param[id(lp_param)]
+    return [(p0, a0, ln) for (r, p0, a0, ln) in param_fragments(rt.u, slot, zo.shard_world) if r == zo.shard_rank]
