@@ -54,8 +54,33 @@ def quantize_weight(w, mode="int8", group_size=128):
 
 def maybe_quantized_linear(x, w, b=None):
     if isinstance(w, QuantizedWeight):
+        y = _wq_gemv(x, w, b)
+        if y is not None:
+            return y
         w = w.dequantize()
     return F.linear(x, w, b)
+
+
+def _wq_gemv(x, qw: "QuantizedWeight", b):
+    """Decode-sized inputs: fused in-register dequantisation + GEMV (``csrc/cuda/wq_gemm.cu``); None -> not eligible."""
+    import ctypes
+    if not (x.is_cuda and qw.mode in ("int8", "int4") and x.dtype in (torch.bfloat16, torch.float16)):
+        return None
+    x2 = x.reshape(-1, x.shape[-1])
+    M, K = x2.shape
+    N = qw.shape[0]
+    if M > 16 or K != qw.shape[1]:
+        return None
+    from deepspeed_b200.ops import native as NV
+    x2 = x2.contiguous()
+    out = torch.empty(M, N, dtype=x.dtype, device=x.device)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    rc = NV.cuda().dsb_wq_gemv(p(x2), p(qw.q), p(qw.params), p(b.to(x.dtype).contiguous() if b is not None else None), p(out),
+                               M, N, K, 8 if qw.mode == "int8" else 4, qw.group_size, NV.dt(x2), NV.stream())
+    if rc == -3:
+        return None
+    NV.check(rc, "wq_gemv")
+    return out.view(*x.shape[:-1], N)
 
 
 class QuantizedLinear(torch.nn.Module):

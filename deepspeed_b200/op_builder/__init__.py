@@ -28,6 +28,7 @@ class CudaKernelsBuilder(CUDAOpBuilder):
         "cuda/gemm_sm100.cu",
         "cuda/attention.cu",
         "cuda/moe_symm.cu",
+        "cuda/wq_gemm.cu",
         "cuda/symm_mem.cpp",
     ]
     LINK_LIBS = ["-ldl", "-lpthread"]

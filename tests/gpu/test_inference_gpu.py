@@ -117,3 +117,41 @@ def test_v1_kernel_inject_generate():
     ids = torch.randint(0, 512, (2, 12)).cuda()
     out = eng.generate(ids, max_new_tokens=8)
     assert out.shape == (2, 20) and torch.equal(out[:, :12], ids)
+
+
+@pytest.mark.parametrize("mode", ["int8", "int4"])
+@pytest.mark.parametrize("M", [1, 5, 16, 40])
+def test_weight_only_quantized_linear(mode, M):
+    """Decode-sized inputs take the fused dequant+GEMV kernel, larger ones dequantise + tensor cores; both must equal the
+    plain definition x @ dequant(W)^T."""
+    from deepspeed_b200.inference.quantization.layers import maybe_quantized_linear, quantize_weight, _wq_gemv
+    torch.manual_seed(0)
+    N, K = 1536, 2048
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda").bfloat16()
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    qw = quantize_weight(w, mode, group_size=128)
+    ref = torch.nn.functional.linear(x.float(), qw.dequantize().float(), b.float())
+    got = maybe_quantized_linear(x, qw, b)
+    assert (_wq_gemv(x, qw, b) is not None) == (M <= 16)
+    torch.testing.assert_close(got.float(), ref, atol=3e-2 * ref.abs().max().item(), rtol=3e-2)
+
+
+def test_quantized_engine_decode_gpu():
+    transformers = pytest.importorskip("transformers")
+    from transformers import AutoConfig, AutoModelForCausalLM
+    from deepspeed_b200.inference.v2 import build_hf_engine
+    cfg = AutoConfig.for_model("llama", vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=4,
+                               num_key_value_heads=2, intermediate_size=512, max_position_embeddings=512)
+    torch.manual_seed(0)
+    m = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).cuda().eval()
+    sm = {"max_context": 512, "max_ragged_batch_size": 512, "max_ragged_sequence_count": 16,
+          "memory_config": {"mode": "allocate", "size": 32}}
+    ref = build_hf_engine(m, {"state_manager": sm})
+    q8 = build_hf_engine(m, {"state_manager": sm, "quantization": {"quantization_mode": "int8"}})
+    p = torch.randint(0, 512, (40, ))
+    a, b = ref.put([0], [p])[0], q8.put([0], [p])[0]
+    assert torch.nn.functional.cosine_similarity(a.float(), b.float(), dim=0) > 0.99
+    n = a.argmax().reshape(1).cpu()
+    a2, b2 = ref.put([0], [n])[0], q8.put([0], [n])[0]     # decode step: the GEMV kernel inside a CUDA graph
+    assert torch.nn.functional.cosine_similarity(a2.float(), b2.float(), dim=0) > 0.99
