@@ -69,7 +69,7 @@ def _wq_gemv(x, qw: "QuantizedWeight", b):
     x2 = x.reshape(-1, x.shape[-1])
     M, K = x2.shape
     N = qw.shape[0]
-    if M > 16 or K != qw.shape[1]:
+    if M > 32 or K != qw.shape[1]:
         return None
     from deepspeed_b200.ops import native as NV
     x2 = x2.contiguous()

@@ -72,5 +72,15 @@ elif which == "paged":
     for _ in range(3):
         flush.zero_()
         R.paged_attention(qkv, cache, seq_of, pos_of, bt, hq, hkv, dd, bs)
+elif which == "wq":
+    from deepspeed_b200.inference.quantization.layers import maybe_quantized_linear, quantize_weight
+    N, K, M = 28672, 4096, 8
+    w = (torch.randn(N, K, device=d) * 0.05).bfloat16()
+    x = torch.randn(M, K, device=d).bfloat16()
+    for mode in ("int8", "int4"):
+        qw = quantize_weight(w, mode, 128)
+        for _ in range(2):
+            flush.zero_()
+            maybe_quantized_linear(x, qw)
 torch.cuda.synchronize()
 print("done", which)
