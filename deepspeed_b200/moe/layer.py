@@ -42,6 +42,7 @@ class MoE(nn.Module):
                      None if noisy_gate_policy == "None" else noisy_gate_policy, drop_tokens, use_rts, None,
                      top2_2nd_expert_sampling), experts, self.expert_group_name, self.ep_size, self.num_local_experts,
             use_tutel=use_tutel)
+        self.deepspeed_moe.expert_tp = enable_expert_tensor_parallelism
         if self.use_residual:
             import copy
             self.mlp = copy.deepcopy(expert)

@@ -218,7 +218,12 @@ class MOELayer(nn.Module):
             y = moe_ops.gather(eo, g.weights.to(torch.float32), slots, T, k)
             return y.reshape(x.shape).to(x.dtype)
         C = g.capacity
-        st = self._symm_state(flat)
+        # TP > 1 with replicated (non-TP) experts: every TP rank routed the same tokens, so each keeps 1/tp of every
+        # expert's capacity rows through the exchange + experts and the slices are re-assembled afterwards
+        # (reference sharded_moe.py MOELayer.forward: drop_tokens / gather_tokens).
+        from deepspeed_b200.moe.mappings import _tp, drop_tokens, gather_tokens
+        tp = 1 if getattr(self, "expert_tp", False) else _tp()[0]
+        st = self._symm_state(flat) if tp == 1 else None
         if st is not None:
             # fused path: permutation kernels write / read the peers' symmetric buffers directly (no NCCL all-to-all)
             from deepspeed_b200.moe import symm_ep
@@ -229,6 +234,12 @@ class MOELayer(nn.Module):
             return y.reshape(x.shape).to(x.dtype)
         rows, slots = moe_ops.scatter(flat, g.expert_ids, g.positions, g.offsets, k, C, E * C)
         disp = rows.view(E, C, H)
+        C_full = C
+        if tp > 1:
+            if C % tp:
+                disp = torch.nn.functional.pad(disp, (0, 0, 0, tp - C % tp))
+            disp = drop_tokens(disp, dim=1).contiguous()
+            C = disp.shape[1]
         if self.ep_size > 1:
             disp = _AllToAll.apply(self.ep_group, disp)  # [ep, E_local, C, H] flattened on dim 0
         disp = disp.view(self.ep_size, self.num_local_experts, C, H).transpose(0, 1).reshape(
@@ -237,5 +248,8 @@ class MOELayer(nn.Module):
         eo = eo.view(self.num_local_experts, self.ep_size, C, H).transpose(0, 1).reshape(E, C, H).contiguous()
         if self.ep_size > 1:
             eo = _AllToAll.apply(self.ep_group, eo)
+        if tp > 1:
+            eo = gather_tokens(eo, dim=1)[:, :C_full].contiguous()
+            C = C_full
         y = moe_ops.gather(eo.reshape(E * C, H), g.weights.to(torch.float32), slots, T, k)
         return y.reshape(x.shape).to(x.dtype)

@@ -94,3 +94,41 @@ def test_zero_to_fp32_and_universal_reshape(tmp_path):
     from deepspeed_b200.checkpoint import convert_to_universal
     convert_to_universal(os.path.join(d, "t3"), os.path.join(d, "t3_universal"))
     run_distributed(_universal_resume_worker, 1, (d, 2))
+
+
+def test_reshape_2d_and_3d_maps():
+    from deepspeed_b200.checkpoint import get_mpu_ranks, model_3d_desc, reshape_meg_2d_parallel
+    g = reshape_meg_2d_parallel(old_pp_degree=2, old_tp_degree=4, new_pp_degree=1, new_tp_degree=2)
+    # source rank = pp*4 + tp; tp 4->2 merges (0,1),(2,3); pp 2->1 stacks the stages
+    assert g.get_data(0, 0) == [0, 1, 4, 5] and g.get_data(0, 1) == [2, 3, 6, 7]
+    maps = model_3d_desc(pp_degree=1, tp_degree=2, dp_degree=4).reshape(model_3d_desc(1, 1, 2))
+    assert len(maps) == 2
+    assert sorted(maps[0].get_data(0, 0) + maps[1].get_data(0, 0)) == list(range(8))
+    ok, errs = model_3d_desc(1, 1, 2).can_reshape(model_3d_desc(1, 2, 2))
+    assert not ok and "TP" in errs[0]
+    tp, pp, dp = get_mpu_ranks(tp_size=2, pp_size=4, dp_size=2)
+    assert tp[0] == [0, 1] and dp[0] == [0, 2] and pp[0] == [0, 4, 8, 12] and pp[1] == [1, 5, 9, 13]
+
+
+def test_zero_checkpoint_merge(tmp_path):
+    import torch
+    from deepspeed_b200.checkpoint import ZeROCheckpoint, model_3d_desc
+    from deepspeed_b200.checkpoint.constants import (BASE_OPTIMIZER_STATE, GROUP_PADDINGS, OPTIMIZER_STATE_DICT,
+                                                     PARTITION_COUNT)
+    d = tmp_path / "global_step1"
+    d.mkdir()
+    torch.save({}, d / "mp_rank_00_model_states.pt")
+    for dp in range(4):
+        pad = 2 if dp == 3 else 0
+        flat = torch.arange(dp * 6, dp * 6 + 6, dtype=torch.float32)
+        sd = {OPTIMIZER_STATE_DICT: {BASE_OPTIMIZER_STATE: {"state": {0: {"exp_avg": flat.clone(), "step": 5}}},
+                                     GROUP_PADDINGS: [pad], PARTITION_COUNT: [4]}}
+        torch.save(sd, d / f"zero_pp_rank_{dp}_mp_rank_00_optim_states.pt")
+    z = ZeROCheckpoint(str(d))
+    assert (z.get_src_dp_degree(), z.get_src_tp_degree(), z.get_src_pp_degree()) == (4, 1, 1)
+    z.reshape(model_3d_desc(1, 1, 2))
+    a = z.get_state_for_rank(0, 0, 0)[OPTIMIZER_STATE_DICT]
+    b = z.get_state_for_rank(0, 0, 1)[OPTIMIZER_STATE_DICT]
+    assert a[BASE_OPTIMIZER_STATE]["state"][0]["exp_avg"].tolist() == list(map(float, range(12)))
+    assert b[BASE_OPTIMIZER_STATE]["state"][0]["exp_avg"].tolist() == list(map(float, range(12, 22)))  # padding stripped
+    assert a[PARTITION_COUNT] == [2] and b[GROUP_PADDINGS] == [0]

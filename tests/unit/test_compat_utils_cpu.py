@@ -1,0 +1,96 @@
+"""Small compatibility utilities: bwc accessors, numa binding maths, MoE token mappings under TP, torch gates."""
+import pytest
+import torch
+
+from tests.common import run_distributed
+
+
+def test_bwc_accessors_handle_all_spellings():
+    from deepspeed_b200.utils import bwc
+
+    class New:
+        get_tensor_model_parallel_rank = staticmethod(lambda: 3)
+        get_tensor_model_parallel_world_size = staticmethod(lambda: 4)
+        get_pipeline_model_parallel_world_size = staticmethod(lambda: 2)
+
+    class Old:
+        get_model_parallel_rank = staticmethod(lambda: 1)
+        get_slice_parallel_world_size = staticmethod(lambda: 8)
+        get_pipe_parallel_world_size = staticmethod(lambda: 5)
+
+    assert bwc.bwc_tensor_model_parallel_rank(New) == 3 and bwc.bwc_tensor_model_parallel_world_size(New) == 4
+    assert bwc.bwc_pipeline_parallel_world_size(New) == 2
+    assert bwc.bwc_tensor_model_parallel_rank(Old) == 1 and bwc.bwc_tensor_model_parallel_world_size(Old) == 8
+    assert bwc.bwc_pipeline_parallel_world_size(Old) == 5
+    assert bwc.bwc_tensor_model_parallel_world_size(None) == 1
+
+
+def test_numa_ranges_and_binding(monkeypatch):
+    from deepspeed_b200.utils import numa
+    assert numa.parse_range("4") == [4] and numa.parse_range("2-5") == [2, 3, 4, 5]
+    assert numa.parse_range_list("0-2,5,7-8") == [0, 1, 2, 5, 7, 8]
+    with pytest.raises(ValueError):
+        numa.parse_range_list("3-1")
+    with pytest.raises(ValueError):
+        numa.parse_range_list("0-4,3")
+    monkeypatch.setattr(numa, "get_numa_cores", lambda: [list(range(0, 8)), list(range(8, 16))])
+    monkeypatch.delenv("KMP_AFFINITY", raising=False)
+    n, cmd = numa.get_numactl_cmd("", 4, 3)
+    assert n == 4 and cmd == ["numactl", "-m", "1", "-C", "12-15"]
+    n, cmd = numa.get_numactl_cmd("0-3,8-11", 2, 1)
+    assert n == 4 and cmd == ["numactl", "-m", "1", "-C", "8-11"]
+    monkeypatch.setenv("KMP_AFFINITY", "x")
+    with pytest.raises(ValueError):
+        numa.get_numactl_cmd("", 1, 0)
+
+
+def test_torch_gates_and_types():
+    from deepspeed_b200.utils.torch import register_grad_hook, required_torch_version
+    from deepspeed_b200.utils.types import GATED_ACTIVATION_TYPES, ActivationFuncType
+    from deepspeed_b200.utils.config import get_timers_config
+    assert required_torch_version(min_version=1.8) and not required_torch_version(max_version=1.8)
+    p = torch.nn.Parameter(torch.ones(3))
+    seen = []
+    register_grad_hook(p, lambda q: seen.append(q.grad.clone()))
+    (p * 2).sum().backward()
+    assert seen and torch.equal(seen[0], torch.full((3, ), 2.0))
+    assert ActivationFuncType.GATED_SILU in GATED_ACTIVATION_TYPES
+    assert get_timers_config({"timers": {"throughput": {"enabled": False}}}).enabled is False
+    assert get_timers_config({}).synchronized is True
+
+
+def _tp_moe():
+    import torch.distributed as td
+    import deepspeed_b200 as ds
+    from deepspeed_b200.moe.layer import MoE
+    from deepspeed_b200.moe.mappings import drop_tokens, gather_tokens
+    from deepspeed_b200.utils import groups
+    r = td.get_rank()
+    groups.initialize(tp_size=2)  # both ranks form one TP group, dp = 1
+    x = torch.arange(24, dtype=torch.float32).reshape(2, 4, 3).requires_grad_(True)
+    d = drop_tokens(x, dim=1)
+    assert d.shape == (2, 2, 3) and torch.equal(d, x[:, 2 * r:2 * r + 2])
+    g = gather_tokens(d, dim=1)
+    assert torch.equal(g, x)
+    g.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))  # gather bwd = drop, drop bwd = gather -> every element once
+    # a MoE block under TP=2 with replicated experts must match the single-process result
+    torch.manual_seed(0)
+    expert = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 8))
+    moe = MoE(8, expert, num_experts=2, ep_size=1, k=1, capacity_factor=2.0, min_capacity=4, use_rts=False)
+    moe.set_deepspeed_parallelism()
+    torch.manual_seed(1)
+    inp = torch.randn(6, 8)
+    y, _, _ = moe(inp)
+    groups_tp = groups._get_model_parallel_world_size()
+    assert groups_tp == 2
+    # reference result: same layer evaluated with the mappings disabled (expert_tp=True keeps all tokens on every rank)
+    moe.deepspeed_moe.expert_tp = True
+    y_ref, _, _ = moe(inp)
+    assert torch.allclose(y, y_ref, atol=1e-6)
+    y.sum().backward()
+    assert all(p.grad is not None for p in moe.parameters())
+
+
+def test_moe_token_mappings_under_tp():
+    run_distributed(_tp_moe, 2)
