@@ -30,33 +30,9 @@ def load_hp_checkpoint_state(folder, key, full_shape, tp_rank=0, tp_world_size=1
     return t
 
 
-def load_universal_into_engine(engine, load_dir, tag, load_optimizer_states=True):
-    folder = os.path.join(load_dir, str(tag))
-    if not os.path.isdir(os.path.join(folder, "zero")):
-        lu = os.path.join(load_dir, "latest_universal")
-        if os.path.isfile(lu):
-            with open(lu) as f:
-                folder = os.path.join(load_dir, f.read().strip())
-    zero_dir = os.path.join(folder, "zero")
-    if not os.path.isdir(zero_dir):
-        raise FileNotFoundError(f"{folder} is not a universal checkpoint (no zero/ directory); run ds_to_universal")
-    ms = torch.load(os.path.join(folder, "mp_rank_00_model_states.pt"), map_location="cpu", weights_only=False)
-    zo = engine.optimizer
-    # buffers + scheduler + counters
-    bufs = {k: v for k, v in ms["module"].items() if k in set(ms.get("buffer_names", []))}
-    if bufs:
-        engine.module.load_state_dict(bufs, strict=False)
-    engine.global_steps = ms.get("global_steps", 0)
-    engine.global_samples = ms.get("global_samples", 0)
-    engine.skipped_steps = ms.get("skipped_steps", 0)
-    if engine.lr_scheduler is not None and ms.get("lr_scheduler") is not None:
-        engine.lr_scheduler.load_state_dict(ms["lr_scheduler"])
-    if zo is None or not hasattr(zo, "units"):
-        sd = {}
-        for name in os.listdir(zero_dir):
-            sd[name] = torch.load(os.path.join(zero_dir, name, "fp32.pt"), map_location="cpu", weights_only=False)["param"]
-        engine.module.load_state_dict(sd, strict=False)
-        return folder, {}
+def load_universal_into_optimizer(zo, zero_dir, load_optimizer_states=True, refresh=True):
+    """Copy this rank's fragments of every parameter's fp32 weight (+ optimizer moments) from the per-parameter folders of a
+    universal checkpoint into the sharded optimizer's arenas.  Returns the number of parameters touched."""
     rank = zo.shard_rank
     states = zo.flat_opt.state_tensors() if hasattr(zo.flat_opt, "state_tensors") else {}
     loaded = 0
@@ -87,6 +63,41 @@ def load_universal_into_engine(engine, load_dir, tag, load_optimizer_states=True
                     for k, t in extra.items():
                         states[k][astart:astart + length].copy_(t[pstart:pstart + length])
                 loaded += 1
+        if refresh:
+            zo._refresh_lp_from_master()
+    return loaded
+
+
+def load_universal_into_engine(engine, load_dir, tag, load_optimizer_states=True):
+    folder = os.path.join(load_dir, str(tag))
+    if not os.path.isdir(os.path.join(folder, "zero")):
+        lu = os.path.join(load_dir, "latest_universal")
+        if os.path.isfile(lu):
+            with open(lu) as f:
+                folder = os.path.join(load_dir, f.read().strip())
+    zero_dir = os.path.join(folder, "zero")
+    if not os.path.isdir(zero_dir):
+        raise FileNotFoundError(f"{folder} is not a universal checkpoint (no zero/ directory); run ds_to_universal")
+    ms = torch.load(os.path.join(folder, "mp_rank_00_model_states.pt"), map_location="cpu", weights_only=False)
+    zo = engine.optimizer
+    # buffers + scheduler + counters
+    bufs = {k: v for k, v in ms["module"].items() if k in set(ms.get("buffer_names", []))}
+    if bufs:
+        engine.module.load_state_dict(bufs, strict=False)
+    engine.global_steps = ms.get("global_steps", 0)
+    engine.global_samples = ms.get("global_samples", 0)
+    engine.skipped_steps = ms.get("skipped_steps", 0)
+    if engine.lr_scheduler is not None and ms.get("lr_scheduler") is not None:
+        engine.lr_scheduler.load_state_dict(ms["lr_scheduler"])
+    if zo is None or not hasattr(zo, "units"):
+        sd = {}
+        for name in os.listdir(zero_dir):
+            sd[name] = torch.load(os.path.join(zero_dir, name, "fp32.pt"), map_location="cpu", weights_only=False)["param"]
+        engine.module.load_state_dict(sd, strict=False)
+        return folder, {}
+    loaded = load_universal_into_optimizer(zo, zero_dir, load_optimizer_states, refresh=False)
+    rank = zo.shard_rank
+    with torch.no_grad():
         meta = ms.get("optimizer_meta") or {}
         if load_optimizer_states and meta:
             if meta.get("group_steps") is not None:

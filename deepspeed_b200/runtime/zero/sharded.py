@@ -31,6 +31,7 @@ from torch import nn
 from deepspeed_b200 import comm as dist
 from deepspeed_b200.accelerator import get_accelerator
 from deepspeed_b200.ops.kernels import flat_ops
+from deepspeed_b200.runtime.base_optimizer import ZeROOptimizer
 from deepspeed_b200.runtime.fp16.loss_scaler import CreateLossScaler
 from deepspeed_b200.runtime.zero.flat_optimizers import (FlatOptimizer, TorchOptimizerAdapter, build_flat_optimizer)
 from deepspeed_b200.runtime.zero.units import (Segment, Unit, arena_segments, build_units, param_fragments)
@@ -70,7 +71,7 @@ class _UnitRT:
         self.skip_bwd_fetch = False  # module's backward does not read its weights (embedding, fused LM head)
 
 
-class ZeroShardedOptimizer:
+class ZeroShardedOptimizer(ZeROOptimizer):
     """Sharded model-state manager + optimizer.  See module docstring."""
 
     def __init__(self,

@@ -1,0 +1,51 @@
+"""ZeRO stage 3 optimizer under the reference's class name and constructor
+(reference ``runtime/zero/stage3.py:DeepSpeedZeroOptimizer_Stage3``); the implementation is
+``sharded.ZeroShardedOptimizer`` with ``stage=3``."""
+import sys
+
+import torch
+
+from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
+from deepspeed_b200.runtime.zero.mem_estimator import (  # noqa: F401  (the reference defines these here)
+    estimate_zero3_model_states_mem_needs, estimate_zero3_model_states_mem_needs_all_cold,
+    estimate_zero3_model_states_mem_needs_all_live)
+from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer
+
+
+class DeepSpeedZeroOptimizer_Stage3(ZeroShardedOptimizer):
+
+    def __init__(self, module, init_optimizer, timers=None, ds_config=None, static_loss_scale=1.0, dynamic_loss_scale=False,
+                 dynamic_loss_args=None, verbose=True, contiguous_gradients=True, reduce_bucket_size=500000000,
+                 prefetch_bucket_size=50000000, max_reuse_distance=1000000000, max_live_parameters=1000000000,
+                 param_persistence_threshold=100000, model_persistence_threshold=sys.maxsize, dp_process_group=None,
+                 reduce_scatter=True, overlap_comm=False, offload_optimizer_config=None, offload_param_config=None,
+                 sub_group_size=1000000000000, offload_ratio=0.0, mpu=None, clip_grad=0.0,
+                 gradient_accumulation_dtype=torch.float32, communication_data_type=torch.float16, postscale_gradients=True,
+                 gradient_predivide_factor=1.0, gradient_accumulation_steps=1, elastic_checkpoint=False, aio_config=None,
+                 all2all_process_group=None, zero_hpz_partition_size=1, zero_quantized_weights=False,
+                 zero_quantized_nontrainable_weights=False, zero_module_granularity_threshold=0, zeropp_loco_param=None,
+                 log_trace_cache_warnings=False, device=None):
+        extra = {}
+        if offload_optimizer_config:
+            extra["offload_optimizer"] = offload_optimizer_config
+        if offload_param_config:
+            extra["offload_param"] = offload_param_config
+        zc = DeepSpeedZeroConfig(stage=3, contiguous_gradients=contiguous_gradients, reduce_bucket_size=reduce_bucket_size,
+                                 stage3_prefetch_bucket_size=prefetch_bucket_size, stage3_max_reuse_distance=max_reuse_distance,
+                                 stage3_max_live_parameters=max_live_parameters,
+                                 stage3_param_persistence_threshold=param_persistence_threshold,
+                                 stage3_model_persistence_threshold=min(model_persistence_threshold, 2**62),
+                                 reduce_scatter=reduce_scatter, overlap_comm=overlap_comm, sub_group_size=min(sub_group_size, 2**62),
+                                 zero_hpz_partition_size=zero_hpz_partition_size, zero_quantized_weights=zero_quantized_weights,
+                                 zero_quantized_nontrainable_weights=zero_quantized_nontrainable_weights, **extra)
+        mdt = next((p.dtype for p in module.parameters()), torch.float32)
+        super().__init__(module, 3, client_optimizer=init_optimizer, zero_config=zc, dp_group=dp_process_group, model_dtype=mdt,
+                         grad_accum_dtype=gradient_accumulation_dtype if gradient_accumulation_dtype != torch.float32 else None,
+                         gradient_accumulation_steps=gradient_accumulation_steps, gradient_clipping=clip_grad,
+                         loss_scale_config={"static_loss_scale": static_loss_scale, "dynamic": dynamic_loss_scale,
+                                            "dynamic_args": dynamic_loss_args},
+                         communication_data_type=communication_data_type if communication_data_type != torch.float16 or
+                         mdt == torch.float16 else None, prescale_gradients=not postscale_gradients,
+                         gradient_predivide_factor=gradient_predivide_factor, mpu=mpu, timers=timers, aio_config=aio_config,
+                         device=device)
+        self.elastic_checkpoint = elastic_checkpoint

@@ -122,3 +122,28 @@ def test_timers_and_throughput():
         tp.start()
         tp.stop(global_step=True)
     assert tp.global_step_count == 4 and tp.avg_samples_per_sec() > 0
+
+
+def test_contiguous_memory_allocator_defragments():
+    import torch
+    from deepspeed_b200.runtime.zero.contiguous_memory_allocator import ContiguousMemoryAllocator
+    a = ContiguousMemoryAllocator(64, torch.float32, "cpu")
+    ts = [a.allocate_tensor(16) for _ in range(4)]
+    for i, t in enumerate(ts):
+        t.fill_(float(i + 1))
+    p = torch.nn.Parameter(torch.empty(0))
+    a.assign_to_param(ts[3], p, 12, (3, 4))
+    assert p.shape == (3, 4) and float(p.sum()) == 48.0
+    a.release_tensor(ts[0])
+    a.release_tensor(ts[2])
+    assert a.total_free == 32 and a.largest_contiguous == 16
+    big = a.allocate_tensor(32)  # needs compaction: two 16-element holes
+    assert big.numel() == 32 and a.total_free == 0 and a.max_allocated == 64
+    # survivors kept their contents and their identity; the param view followed its block
+    assert float(ts[1].sum()) == 32.0 and float(ts[3].sum()) == 64.0 and float(p.sum()) == 48.0
+    big.zero_()
+    assert float(ts[1].sum()) == 32.0 and float(p.sum()) == 48.0
+    ts[3].fill_(7.0)
+    assert float(p.sum()) == 84.0  # still aliases the block
+    a.release_tensor(ts[3])
+    assert p.numel() == 0 and a.total_free == 16
