@@ -30,6 +30,7 @@ DEFAULT_MASTER_PORT = "29500"
 comms_logger = CommsLogger()
 _mesh_device = None
 _initialized_here = False
+cdb = None  # object-style backend (comm/torch.py:TorchBackend), created by init_distributed
 
 
 def _off(op: str) -> bool:
@@ -149,12 +150,15 @@ def init_distributed(dist_backend: Optional[str] = None,
 
     ``dist_backend`` defaults to the accelerator's backend (``nccl`` on B200, ``gloo`` on host).
     """
-    global _initialized_here
+    global _initialized_here, cdb
     if config is not None:
         configure(config)
     if dist_init_required is False:
         return
     if dist.is_initialized():
+        if cdb is None:
+            from .torch import TorchBackend
+            cdb = TorchBackend(dist.get_backend())
         return
     from deepspeed_b200.accelerator import get_accelerator
     accel = get_accelerator()
@@ -187,6 +191,8 @@ def init_distributed(dist_backend: Optional[str] = None,
         dist.init_process_group(backend=backend, timeout=timeout, init_method=init_method, rank=rank,
                                 world_size=world_size)
     _initialized_here = True
+    from .torch import TorchBackend
+    cdb = TorchBackend(backend)
 
 
 def destroy_process_group(group=None):

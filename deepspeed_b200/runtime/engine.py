@@ -223,9 +223,11 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             mics = int(getattr(c.zero_config, "mics_shard_size", -1) or -1)
             if mics > 0 and stage == 3 and mics < dist.get_world_size(self.seq_data_parallel_group):
                 from deepspeed_b200.runtime.zero.mics import create_mics_comm_groups
-                mg = create_mics_comm_groups(mics, self.seq_data_parallel_group)
+                mg = create_mics_comm_groups(mics, self.seq_data_parallel_group,
+                                             hierarchical_allgather=bool(c.zero_config.mics_hierarchical_params_gather))
                 self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=mg.param_shard_group,
                                                       replica_group=mg.param_repli_group, **common)
+                self.optimizer.mics_groups = mg  # two-hop parameter gathers when the shard group spans nodes
                 self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
                 return
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)

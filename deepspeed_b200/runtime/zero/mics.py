@@ -39,8 +39,55 @@ def mics_rank_layout(world_ranks: List[int], shard_size: int):
 _cache = {}
 
 
-def create_mics_comm_groups(shard_size, dp_group=None, hierarchical_allgather=False, mpu=None) -> MiCS_CommGroups:
-    key = (shard_size, id(dp_group))
+def hierarchy_layout(shard_group: List[int], ndev_per_node: int):
+    """Split one shard group that spans nodes into (intra-node groups, inter-node groups): intra = consecutive runs of
+    ``ndev_per_node`` ranks; inter = ranks with the same local index across the nodes."""
+    assert len(shard_group) % ndev_per_node == 0
+    intra = [shard_group[i:i + ndev_per_node] for i in range(0, len(shard_group), ndev_per_node)]
+    inter = [[g[i] for g in intra] for i in range(ndev_per_node)]
+    return intra, inter
+
+
+def _generate_mics_config(world_size, ndev_per_node, shard_size, pp_size=1):
+    """Rank lists of a MiCS layout: ``{"shard_groups", "replicate_groups", "span_nodes"}`` (reference
+    ``mics_utils._generate_mics_config``); with pipeline parallelism each stage owns a contiguous block of ranks."""
+    assert world_size % pp_size == 0
+    per_stage = world_size // pp_size
+    assert per_stage % shard_size == 0, f"dp size {per_stage} is not divisible by the MiCS shard size {shard_size}"
+    shard, repli = [], []
+    for st in range(pp_size):
+        s, r = mics_rank_layout(list(range(st * per_stage, (st + 1) * per_stage)), shard_size)
+        shard += s
+        repli += r
+    return {"shard_groups": shard, "replicate_groups": repli, "span_nodes": max(1, shard_size // ndev_per_node)}
+
+
+def scale_tensors(tensors, scale):
+    for t in tensors:
+        t.div_(scale)
+
+
+def hierarchical_all_gather(output, shard, groups: "MiCS_CommGroups"):
+    """All-gather ``shard`` over a shard group spanning nodes in two hops (reference ``MiCS_AllGatherCoalescedHandle`` /
+    ``_hierarchical_all_gather_params``): first across nodes between same-local-index ranks (small messages on the slow
+    fabric, all local ranks in parallel), then inside the node over NVLink.  ``output`` is ordered by shard rank."""
+    import torch
+    inter, intra = groups.param_inter_node_shard_group, groups.param_intra_node_group
+    if inter is None or intra is None:
+        return dist.all_gather_into_tensor(output, shard, group=groups.param_shard_group)
+    n_nodes, n_local = dist.get_world_size(inter), dist.get_world_size(intra)
+    n = shard.numel()
+    stage1 = torch.empty(n_nodes * n, dtype=shard.dtype, device=shard.device)  # [node][n] for my local index
+    dist.all_gather_into_tensor(stage1, shard.contiguous().view(-1), group=inter)
+    stage2 = torch.empty(n_local * n_nodes * n, dtype=shard.dtype, device=shard.device)  # [local][node][n]
+    dist.all_gather_into_tensor(stage2, stage1, group=intra)
+    # shard rank = node * n_local + local
+    output.view(n_nodes, n_local, n).copy_(stage2.view(n_local, n_nodes, n).transpose(0, 1))
+    return None
+
+
+def create_mics_comm_groups(shard_size, dp_group=None, hierarchical_allgather=False, mpu=None, ndev_per_node=None) -> MiCS_CommGroups:
+    key = (shard_size, id(dp_group), bool(hierarchical_allgather), ndev_per_node)
     if key in _cache:
         return _cache[key]
     world = dist.get_world_size(dp_group)
@@ -56,6 +103,21 @@ def create_mics_comm_groups(shard_size, dp_group=None, hierarchical_allgather=Fa
         h = dist.new_group(rs)
         if me in rs:
             g.param_repli_group, g.param_repli_size, g.param_repli_rank = h, len(rs), rs.index(me)
+    if hierarchical_allgather:
+        import os
+        import torch
+        per_node = ndev_per_node or int(os.environ.get("LOCAL_WORLD_SIZE", 0)) or max(1, torch.cuda.device_count())
+        if shard_size > per_node and shard_size % per_node == 0:  # only when a shard group really spans nodes
+            for rs in shard:
+                intra, inter = hierarchy_layout(rs, per_node)
+                for sub in intra:
+                    h = dist.new_group(sub)
+                    if me in sub:
+                        g.param_intra_node_group = h
+                for sub in inter:
+                    h = dist.new_group(sub)
+                    if me in sub:
+                        g.param_inter_node_shard_group = h
     _cache[key] = g
     return g
 

@@ -697,6 +697,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         if self._symm is not None and self._symm.owns(full) and self._symm.owns(shard):
             self._symm.all_gather(full, shard, u.shard_numel)
             return
+        mg = getattr(self, "mics_groups", None)
+        if mg is not None and mg.param_inter_node_shard_group is not None:
+            from deepspeed_b200.runtime.zero.mics import hierarchical_all_gather
+            hierarchical_all_gather(full, shard, mg)
+            return
         w = dist.all_gather_into_tensor(full, shard, group=self.dp_group, async_op=self.on_cuda)
         if w is not None and hasattr(w, "wait"):
             w.wait()

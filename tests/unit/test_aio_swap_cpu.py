@@ -110,3 +110,27 @@ def test_nvme_offload_matches_cpu_offload(tmp_path):
     sa, sb = torch.load(a), torch.load(b)
     for k in sa:
         torch.testing.assert_close(sa[k], sb[k], atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["partitioned", "pipelined"])
+def test_named_optimizer_swappers(tmp_path, kind):
+    """The two reference swapper classes drive the same flat NVMe-backed state, with and without read-ahead."""
+    from types import SimpleNamespace
+    from deepspeed_b200.runtime.swap_tensor.partitioned_optimizer_swapper import PartitionedOptimizerSwapper
+    from deepspeed_b200.runtime.swap_tensor.pipelined_optimizer_swapper import PipelinedOptimizerSwapper
+    cls = PartitionedOptimizerSwapper if kind == "partitioned" else PipelinedOptimizerSwapper
+    sw = cls(SimpleNamespace(b200_swap_window=1000, buffer_count=4), {"block_size": 65536, "queue_depth": 4}, str(tmp_path))
+    assert sw.pipeline == (kind == "pipelined")
+    flat = SimpleNamespace(state_names=["exp_avg", "exp_avg_sq"], state={})
+    sw.wrap(flat, 3500)
+    ref = torch.zeros(3500)
+    for s in range(0, 3500, 1000):
+        e = min(s + 1000, 3500)
+        nxt = (e, min(e + 1000, 3500)) if e < 3500 else None
+        win = sw.swap_in_optimizer_state(flat, s, e, nxt) if kind == "pipelined" else sw.swap_in_optimizer_state(flat, s, e)
+        win["exp_avg"].add_(1.5)
+        win["exp_avg_sq"].add_(torch.arange(s, e, dtype=torch.float32))
+        ref[s:e] = torch.arange(s, e, dtype=torch.float32)
+    sw.swap_out_optimizer_state(flat, async_swap=False)
+    assert torch.equal(flat.state["exp_avg"].detach(), torch.full((3500, ), 1.5))
+    assert torch.equal(flat.state["exp_avg_sq"].detach(), ref)

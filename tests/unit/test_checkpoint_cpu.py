@@ -132,3 +132,27 @@ def test_zero_checkpoint_merge(tmp_path):
     assert a[BASE_OPTIMIZER_STATE]["state"][0]["exp_avg"].tolist() == list(map(float, range(12)))
     assert b[BASE_OPTIMIZER_STATE]["state"][0]["exp_avg"].tolist() == list(map(float, range(12, 22)))  # padding stripped
     assert a[PARTITION_COUNT] == [2] and b[GROUP_PADDINGS] == [0]
+
+
+def test_nebula_tiered_engine(tmp_path):
+    import os
+    import torch
+    from deepspeed_b200.nebula.config import DeepSpeedNebulaConfig
+    from deepspeed_b200.runtime.checkpoint_engine import NebulaCheckpointEngine
+    fast, slow = tmp_path / "fast", tmp_path / "slow"
+    cfg = DeepSpeedNebulaConfig({"nebula": {"enabled": True, "persistent_storage_path": str(slow),
+                                            "persistent_time_interval": 0, "num_of_version_in_retention": 2}})
+    eng = NebulaCheckpointEngine(cfg)
+    for step in range(4):
+        tag = f"global_step{step}"
+        os.makedirs(fast / tag)
+        eng.create(tag)
+        eng.save({"w": torch.full((3, ), float(step))}, str(fast / tag / "mp_rank_00_model_states.pt"))
+        eng.commit(tag)
+        eng.wait_persisted()
+    kept = sorted(d for d in os.listdir(slow) if os.path.isdir(slow / d))
+    assert kept == ["global_step2", "global_step3"] and (slow / "latest").read_text() == "global_step3"
+    # the fast tier lost a version: load falls back to the persistent copy
+    os.remove(fast / "global_step3" / "mp_rank_00_model_states.pt")
+    sd = eng.load(str(fast / "global_step3" / "mp_rank_00_model_states.pt"))
+    assert sd["w"].tolist() == [3.0, 3.0, 3.0]

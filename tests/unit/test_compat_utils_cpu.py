@@ -94,3 +94,31 @@ def _tp_moe():
 
 def test_moe_token_mappings_under_tp():
     run_distributed(_tp_moe, 2)
+
+
+def _cdb():
+    import deepspeed_b200.comm as dist
+    from deepspeed_b200.comm import comm as C
+    from deepspeed_b200.comm.torch import TorchBackend, all_reduce_comm_off
+    from deepspeed_b200.comm.utils import get_msg_size_from_args, get_world_size_from_launcher
+    dist.init_distributed("gloo")
+    cdb = C.cdb
+    assert isinstance(cdb, TorchBackend) and cdb.get_world_size() == 2
+    t = torch.ones(4) * (cdb.get_rank() + 1)
+    cdb.all_reduce(t, op=dist.ReduceOp.SUM)
+    assert torch.equal(t, torch.full((4, ), 3.0))
+    out = torch.empty(8)
+    cdb.all_gather_into_tensor(out, torch.full((4, ), float(cdb.get_rank())))
+    assert out.tolist() == [0.0] * 4 + [1.0] * 4
+    all_reduce_comm_off(True)
+    u = torch.ones(2)
+    cdb.all_reduce(u).wait()
+    assert torch.equal(u, torch.ones(2))  # switched off: untouched
+    all_reduce_comm_off(False)
+    assert get_msg_size_from_args(cdb.all_reduce, torch.zeros(10)) == 40
+    assert get_msg_size_from_args(cdb.reduce_scatter, torch.zeros(2), [torch.zeros(3), torch.zeros(5)]) == 32
+    assert get_world_size_from_launcher() == 2
+
+
+def test_object_style_backend():
+    run_distributed(_cdb, 2)

@@ -63,3 +63,25 @@ def _quantized():
 
 def test_qwz_qgz():
     run_distributed(_quantized, 2)
+
+
+def _mics_hier():
+    import torch
+    import torch.distributed as td
+    from deepspeed_b200.runtime.zero.mics_utils import (_generate_mics_config, create_mics_comm_groups,
+                                                        hierarchical_all_gather)
+    r = td.get_rank()
+    cfg = _generate_mics_config(world_size=8, ndev_per_node=2, shard_size=4)
+    assert cfg["shard_groups"] == [[0, 1, 2, 3], [4, 5, 6, 7]] and cfg["replicate_groups"][1] == [1, 5] and cfg["span_nodes"] == 2
+    # 4 ranks = one shard group over two 2-GPU "nodes"
+    g = create_mics_comm_groups(4, hierarchical_allgather=True, ndev_per_node=2)
+    assert g.param_intra_node_group is not None and g.param_inter_node_shard_group is not None
+    assert td.get_world_size(g.param_intra_node_group) == 2 and td.get_world_size(g.param_inter_node_shard_group) == 2
+    shard = torch.full((3, ), float(r))
+    out = torch.empty(12)
+    hierarchical_all_gather(out, shard, g)
+    assert out.tolist() == [float(i) for i in range(4) for _ in range(3)]
+
+
+def test_mics_hierarchical_all_gather():
+    run_distributed(_mics_hier, 4)
