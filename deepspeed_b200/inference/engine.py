@@ -123,6 +123,22 @@ class InferenceEngine(nn.Module):
         quant = "int8" if self.dtype == torch.int8 else None
         dtype = torch.float16 if self.dtype == torch.int8 else self.dtype
         hf_cfg = getattr(self.module, "config", None)
+        from .v2.model_implementations.arch import SUPPORTED_MODEL_TYPES
+        layerwise = os.environ.get("DSB200_LAYERWISE_INJECTION", "0") == "1"
+        if hf_cfg is not None and hasattr(hf_cfg, "model_type") and (hf_cfg.model_type not in SUPPORTED_MODEL_TYPES or layerwise):
+            # encoders (BERT, DistilBERT, RoBERTa, CLIP), BLOOM / GPT-Neo and anything else the ragged engine has no
+            # architecture entry for: per-layer fused kernels through the policy / container registry, the rest of the
+            # Hugging Face model (embeddings, pooler, heads, generate loop) stays as is
+            from deepspeed_b200.module_inject.replace_module import replace_transformer_layer
+            sd = None
+            if isinstance(cfg.checkpoint, str) and os.path.isdir(cfg.checkpoint):
+                from .v2.engine_factory import HuggingFaceCheckpointEngine
+                eng = HuggingFaceCheckpointEngine(cfg.checkpoint)
+                sd = dict(eng.parameters())
+            self.module.to(dtype)
+            replace_transformer_layer(None, self.module, checkpoint_dict=sd, config=cfg)
+            self.module.to(self.device)
+            return
         if hf_cfg is not None and hasattr(hf_cfg, "model_type"):
             spec = arch_from_hf_config(hf_cfg)
             model = RaggedTransformer(spec, self.mp_group, self.mp_world_size, rank, dtype, self.device)

@@ -12,13 +12,51 @@ from torch import nn
 from .auto_tp import AutoTP
 
 
+def _inject_layers(model, config, mp_group=None, mp_size=1, device=None):
+    """Swap every transformer layer a policy recognises for its fused counterpart; returns the number replaced."""
+    from .replace_policy import policy_for, policy_to_ds_container
+    from .policy import TransformerPolicy
+    TransformerPolicy.hf_model_config = getattr(model, "config", None)
+    count = 0
+
+    def walk(parent):
+        nonlocal count
+        for name, child in list(parent.named_children()):
+            pol_cls = policy_for(child)
+            if pol_cls is None:
+                walk(child)
+                continue
+            policy = pol_cls(child, inference=True)
+            cont = policy_to_ds_container[pol_cls](policy=policy, config=config, model_config=TransformerPolicy.hf_model_config,
+                                                   layer_id=count, child=child)
+            cont.set_tensor_parallel_config(mp_size, mp_group)
+            setattr(parent, name, cont.build(device=device))
+            count += 1
+
+    walk(model)
+    return count
+
+
 def replace_transformer_layer(orig_layer_impl, model, checkpoint_dict=None, config=None, model_config=None):
+    """``config.replace_with_kernel_inject``: per-layer fused kernels through the policy/container registry; otherwise
+    AutoTP sharding.  Optional post-init weight quantisation in both cases."""
     tp = config.tensor_parallel.tp_size if config is not None else 1
+    group = None
     if tp > 1:
         from deepspeed_b200.utils import groups
         if groups.ranks_of("tp") is None:
             groups._init_tp_mesh_device(tensor_model_parallel_size=tp)
-        AutoTP(model, mp_group=groups.get_tensor_model_parallel_group(), mp_size=tp).replace()
+        group = groups.get_tensor_model_parallel_group()
+    if config is not None and getattr(config, "replace_with_kernel_inject", False):
+        n = _inject_layers(model, config, mp_group=group, mp_size=tp)
+        if checkpoint_dict is not None:
+            from .load_checkpoint import load_model_with_checkpoint
+            load_model_with_checkpoint(model, checkpoint_dict, mp_group=group, mp_size=tp)
+        if n == 0:
+            raise ValueError("replace_with_kernel_inject: no injection policy matches this model; use AutoTP "
+                             "(replace_with_kernel_inject=False) or provide an injection_policy")
+    elif tp > 1:
+        AutoTP(model, mp_group=group, mp_size=tp).replace()
     if config is not None and config.quant.enabled and config.quant.weight.post_init_quant:
         from deepspeed_b200.inference.quantization import _init_group_wise_weight_quantization
         _init_group_wise_weight_quantization(model, {"weight_quantization": {"post_init_quant":
@@ -68,4 +106,38 @@ def generic_injection(module, dtype=None, enable_cuda_graph=True):
 
 
 def revert_transformer_layer(orig_layer_impl, model, config, preln=False):
-    raise NotImplementedError("revert is not supported: keep a reference to the original module instead")
+    """Inverse of kernel injection: rebuild ``orig_layer_impl(config)`` layers and copy the fused weights back in the
+    family's original layout.  Supported for the families whose policy can be written to (HF BERT-style encoders);
+    other families should keep a reference to the original module."""
+    from .containers.base import InjectedLayer
+    from .replace_policy import policy_for
+    n = 0
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if not isinstance(child, InjectedLayer):
+                continue
+            new = orig_layer_impl(config)
+            pol_cls = policy_for(new)
+            if pol_cls is None:
+                raise NotImplementedError(f"no policy can write into {type(new).__name__}")
+            pol = pol_cls(new)
+            f = child.fused
+            qkvw, qkvb, ow, ob = pol.attention()
+            w1, b1, w2, b2 = pol.mlp()
+            anw, anb, inw, inb = pol.layernorm()
+            import torch
+            with torch.no_grad():
+                # q/k/v are separate parameters in the original layer: the policy's packed view is a copy, so write
+                # through the original modules
+                a = new.attention
+                for lin, (wt, bt) in zip((a.self.query, a.self.key, a.self.value),
+                                         zip(f.attn_qkvw.chunk(3, 0), f.attn_qkvb.chunk(3, 0))):
+                    lin.weight.copy_(wt)
+                    lin.bias.copy_(bt)
+                for dst, src in ((ow, f.attn_ow), (ob, f.attn_ob), (w1, f.inter_w), (b1, f.inter_b), (w2, f.output_w),
+                                 (b2, f.output_b), (anw, f.attn_nw), (anb, f.attn_nb), (inw, f.norm_w), (inb, f.norm_b)):
+                    if dst is not None:
+                        dst.copy_(src)
+            setattr(parent, name, new.to(f.attn_ow.device, f.attn_ow.dtype))
+            n += 1
+    return model

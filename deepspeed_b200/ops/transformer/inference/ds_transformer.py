@@ -19,6 +19,8 @@ from .config import DeepSpeedInferenceConfig
 
 def _act(x, name):
     name = str(name).lower()
+    if "quick" in name:
+        return x * torch.sigmoid(1.702 * x)
     if "relu" in name:
         return F.relu(x)
     if "silu" in name or "swish" in name:
@@ -51,7 +53,8 @@ class DeepSpeedTransformerInference(nn.Module):
         self.attn_qkvw, self.attn_qkvb = p(qkv_out, h), p(qkv_out)
         self.attn_ow, self.attn_ob = p(h, self.heads * self.d), p(h)
         self.attn_nw, self.attn_nb = p(h), p(h)             # post-attention norm
-        self.inter_w, self.inter_b = p(c.intermediate_size // tp, h), p(c.intermediate_size // tp)
+        inter_rows = (2 if _is_gated(c.mlp_act_func_type) else 1) * (c.intermediate_size // tp)
+        self.inter_w, self.inter_b = p(inter_rows, h), p(inter_rows)
         self.output_w, self.output_b = p(h, c.intermediate_size // tp), p(h)
         self.cache = None
         self.seen = 0
@@ -82,7 +85,7 @@ class DeepSpeedTransformerInference(nn.Module):
             if self.rope.cos.device != x.device:
                 self.rope.to(x.device)
             pos = torch.arange(self.seen, self.seen + S, device=x.device)
-            q, k = _rope(q, k, self.rope, pos, c.rotary_dim)
+            q, k = (_rope if c.rotate_half or not c.rotate_every_two else _rope_interleaved)(q, k, self.rope, pos, c.rotary_dim)
         if self.cache is None or self.cache.shape[0] < B or self.cache.device != x.device:
             self.cache = torch.zeros(B, 2, hkv, c.max_out_tokens, d, dtype=x.dtype, device=x.device)
         if self.seen + S > c.max_out_tokens:
@@ -92,11 +95,31 @@ class DeepSpeedTransformerInference(nn.Module):
         total = self.seen + S
         kk, vv = self.cache[:B, 0, :, :total], self.cache[:B, 1, :, :total]
         scale = 1.0 / math.sqrt(d) if c.scale_attention else 1.0
-        causal = c.triangular_masking and S > 1 and self.seen == 0 and attn_mask is None
+        window = c.window_size if c.local_attention else 0
+        use_alibi = bool(c.bigscience_bloom)
         mask = attn_mask
-        if mask is None and c.triangular_masking and S > 1 and self.seen > 0:
-            i = torch.arange(S, device=x.device)[:, None] + self.seen
-            mask = (torch.arange(total, device=x.device)[None, :] <= i)
+        if mask is not None and mask.dim() == 2:  # [B, total] padding mask (1 = keep)
+            mask = mask[:, None, None, :].bool() if mask.dtype != torch.bool else mask[:, None, None, :]
+        if mask is not None and mask.shape[-1] != total:
+            mask = mask[..., -total:] if mask.shape[-1] > total else None
+        causal = c.triangular_masking and S > 1 and self.seen == 0 and mask is None and not window and not use_alibi
+        need_struct = c.triangular_masking and (S > 1 or window or use_alibi) and not causal
+        if need_struct or use_alibi:
+            qi = torch.arange(S, device=x.device)[:, None] + self.seen
+            kj = torch.arange(total, device=x.device)[None, :]
+            keep = (kj <= qi) if c.triangular_masking else torch.ones(S, total, dtype=torch.bool, device=x.device)
+            if window:
+                keep = keep & (qi - kj < window)
+            bias = torch.zeros(1, 1, S, total, dtype=torch.float32, device=x.device).masked_fill(~keep, float("-inf"))
+            if use_alibi:
+                if getattr(self, "_slopes", None) is None or self._slopes.device != x.device:
+                    full = alibi_slopes(c.heads, x.device)
+                    r = dist.get_rank(self.mp_group) if (self.mp_group is not None and c.mp_size > 1) else 0
+                    self._slopes = full[r * hq:(r + 1) * hq]
+                bias = bias + self._slopes.view(1, hq, 1, 1) * kj.to(torch.float32).view(1, 1, 1, total)
+            if mask is not None:
+                bias = bias.masked_fill(~mask, float("-inf")) if mask.dtype == torch.bool else bias + mask.float()
+            mask = bias.to(q.dtype)
         o = F.scaled_dot_product_attention(q.transpose(1, 2), kk, vv, attn_mask=mask, is_causal=causal, scale=scale,
                                            enable_gqa=hq != hkv)
         self.seen = total
@@ -122,16 +145,56 @@ class DeepSpeedTransformerInference(nn.Module):
             else:
                 residual = self._norm(residual + a + self.attn_ob, self.norm_w, self.norm_b)
                 f_in = residual
-            m = F.linear(_act(F.linear(f_in, self.inter_w, self.inter_b), c.mlp_act_func_type), self.output_w)
+            m = F.linear(_mlp_act(F.linear(f_in, self.inter_w, self.inter_b), c.mlp_act_func_type), self.output_w)
             out = residual + self._reduce(m) + self.output_b
             if not c.pre_layer_norm:
                 out = self._norm(out, self.attn_nw, self.attn_nb)
         else:  # parallel attention + MLP (GPT-J / NeoX style)
-            m = F.linear(_act(F.linear(a_in, self.inter_w, self.inter_b), c.mlp_act_func_type), self.output_w)
+            m_in = self._norm(x, self.attn_nw, self.attn_nb) if getattr(c, "parallel_mlp_own_norm", False) else a_in
+            m = F.linear(_mlp_act(F.linear(m_in, self.inter_w, self.inter_b), c.mlp_act_func_type), self.output_w)
             out = residual + a + self.attn_ob + self._reduce(m) + self.output_b
         if c.return_single_tuple:
             return (out, )
         return (out, None) if c.return_tuple else out
+
+
+def _is_gated(name):
+    return "gated" in str(name).lower() or str(name) in ("3", "4", "ActivationFuncType.GATED_GELU", "ActivationFuncType.GATED_SILU")
+
+
+def _mlp_act(h, name):
+    """Activation of the first MLP GEMM's output; gated variants hold [gate; up] stacked on the feature dim."""
+    if _is_gated(name):
+        gate, up = h.chunk(2, dim=-1)
+        return _act(gate, "silu" if "silu" in str(name).lower() or str(name).endswith("4") else "gelu") * up
+    return _act(h, name)
+
+
+def alibi_slopes(n_heads, device=None):
+    """Per-head ALiBi slopes (geometric sequence; the closest power of two first, then the interleaved remainder)."""
+    def pow2(n):
+        start = 2.0**(-(2.0**-(math.log2(n) - 3)))
+        return [start * (start**i) for i in range(n)]
+    if math.log2(n_heads).is_integer():
+        sl = pow2(n_heads)
+    else:
+        c = 2**math.floor(math.log2(n_heads))
+        sl = pow2(c) + pow2(2 * c)[0::2][:n_heads - c]
+    return torch.tensor(sl, dtype=torch.float32, device=device)
+
+
+def _rope_interleaved(q, k, table, pos, rot_dim):
+    """GPT-J style rotary: pairs are (0,1), (2,3), ... instead of (i, i + rot_dim/2)."""
+    cos = table.cos[pos][None, :, None, :].to(torch.float32)
+    sin = table.sin[pos][None, :, None, :].to(torch.float32)
+
+    def rot(t):
+        tf = t.float()
+        a, b = tf[..., 0:rot_dim:2], tf[..., 1:rot_dim:2]
+        r = torch.stack([a * cos - b * sin, b * cos + a * sin], dim=-1).flatten(-2)
+        return torch.cat([r, tf[..., rot_dim:]], -1).to(t.dtype)
+
+    return rot(q), rot(k)
 
 
 def _rope(q, k, table, pos, rot_dim):
