@@ -1,0 +1,14 @@
+"""``BiasReluOp`` (reference ``ops/transformer/inference/op_binding/bias_relu.py``): ``relu(activation + bias)``."""
+import torch
+import torch.nn.functional as F
+
+from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
+from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
+
+from .base import BaseOp
+
+
+class BiasReluOp(BaseOp):
+
+    def forward(self, activation: torch.Tensor, bias: torch.Tensor):
+        return T.bias_act(activation, bias, act="relu")

@@ -70,3 +70,88 @@ def test_inference_layer_kv_cache_decode_matches_full():
         o, _ = l(x[:, t:t + 1], use_cache=True)
         outs.append(o)
     torch.testing.assert_close(torch.cat(outs, 1), full, atol=1e-5, rtol=1e-4)
+
+
+def test_op_bindings_compose_into_the_fused_layer():
+    """DeepSpeedSelfAttention + DeepSpeedMLP built from the op bindings == the monolithic fused layer."""
+    import torch
+    from deepspeed_b200.ops.transformer.inference.config import DeepSpeedInferenceConfig
+    from deepspeed_b200.ops.transformer.inference.ds_attention import DeepSpeedSelfAttention
+    from deepspeed_b200.ops.transformer.inference.ds_mlp import DeepSpeedMLP
+    from deepspeed_b200.ops.transformer.inference.ds_transformer import DeepSpeedTransformerInference
+    from deepspeed_b200.ops.transformer.inference.op_binding import WorkspaceOp
+    torch.manual_seed(0)
+    cfg = DeepSpeedInferenceConfig(hidden_size=32, intermediate_size=64, heads=4, dtype=torch.float32, pre_layer_norm=True,
+                                   max_out_tokens=32, mlp_act_func_type="gelu")
+    layer = DeepSpeedTransformerInference(cfg)
+    for p in layer.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    attn, mlp = DeepSpeedSelfAttention(cfg), DeepSpeedMLP(cfg)
+    with torch.no_grad():
+        attn.attn_qkvw.copy_(layer.attn_qkvw), attn.attn_qkvb.copy_(layer.attn_qkvb)
+        attn.attn_ow.copy_(layer.attn_ow), attn.attn_ob.copy_(layer.attn_ob)
+        mlp.attn_nw.copy_(layer.attn_nw), mlp.attn_nb.copy_(layer.attn_nb)
+        mlp.inter_w.copy_(layer.inter_w), mlp.inter_b.copy_(layer.inter_b)
+        mlp.output_w.copy_(layer.output_w), mlp.output_b.copy_(layer.output_b)
+    x = torch.randn(2, 6, 32)
+    ref = layer(x)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    WorkspaceOp(cfg).release_workspace()
+    a, k, v, _, _ = attn(x, norm_w=layer.norm_w, norm_b=layer.norm_b)
+    out = mlp(a, x, bias=attn.attn_ob)
+    assert k.shape == (2, 4, 6, 8) and torch.allclose(out, ref, atol=1e-5), (out - ref).abs().max()
+    # incremental step reuses the workspace cache
+    step_ref = layer(x[:, -1:] * 0.5, use_cache=True)
+    step_ref = step_ref[0] if isinstance(step_ref, tuple) else step_ref
+    a2, k2, _, _, _ = attn(x[:, -1:] * 0.5, norm_w=layer.norm_w, norm_b=layer.norm_b, layer_past=True)
+    assert k2.shape[2] == 7 and torch.allclose(mlp(a2, x[:, -1:] * 0.5, bias=attn.attn_ob), step_ref, atol=1e-5)
+
+
+def test_diffusers_block_and_attention():
+    import torch
+    from types import SimpleNamespace
+    from torch import nn
+    from deepspeed_b200.ops.transformer.inference.bias_add import nhwc_bias_add
+    from deepspeed_b200.ops.transformer.inference.diffusers_attention import DeepSpeedDiffusersAttention
+    from deepspeed_b200.ops.transformer.inference.diffusers_transformer_block import DeepSpeedDiffusersTransformerBlock
+    torch.manual_seed(0)
+    cfg = SimpleNamespace(hidden_size=16, heads=4, dtype=torch.float32)
+    att = DeepSpeedDiffusersAttention(cfg)
+    for p in att.parameters():
+        nn.init.normal_(p, std=0.2)
+    x, ctx = torch.randn(2, 5, 16), torch.randn(2, 3, 16)
+    q, k, v = torch.nn.functional.linear(x, att.attn_qkvw, att.attn_qkvb).chunk(3, -1)
+    sp = lambda t: t.reshape(2, -1, 4, 4).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(2, 5, 16)
+    assert torch.allclose(att(x), torch.nn.functional.linear(ref, att.attn_ow, att.attn_ob), atol=1e-5)
+    assert att(x, ctx).shape == (2, 5, 16)
+
+    class GEGLU(nn.Module):
+
+        def __init__(self):
+            super().__init__()
+            self.proj = nn.Linear(16, 64)
+
+        def forward(self, h):
+            a, g = self.proj(h).chunk(2, dim=-1)
+            return a * torch.nn.functional.gelu(g)
+
+    class Block(nn.Module):
+
+        def __init__(self):
+            super().__init__()
+            self.norm1, self.norm2, self.norm3 = nn.LayerNorm(16), nn.LayerNorm(16), nn.LayerNorm(16)
+            self.attn1, self.attn2 = nn.Linear(16, 16), nn.Linear(16, 16)
+            self.ff = SimpleNamespace(net=nn.ModuleList([GEGLU(), nn.Dropout(0.0), nn.Linear(32, 16)]))
+
+        def forward(self, x):
+            x = x + self.attn1(self.norm1(x))
+            x = x + self.attn2(self.norm2(x))
+            h = self.norm3(x)
+            return x + self.ff.net[2](self.ff.net[0](h))
+
+    blk = Block()
+    fused = DeepSpeedDiffusersTransformerBlock(blk)
+    assert torch.allclose(fused(x), blk(x), atol=1e-5)
+    a = torch.randn(1, 3, 3, 4)  # [N, H, W, C]
+    assert torch.allclose(nhwc_bias_add(a, torch.ones(4)), a + 1)
