@@ -1,0 +1,35 @@
+"""Pre-RMSNorm block (reference ``modules/implementations/pre_norm/cuda_pre_rms.py``)."""
+from typing import Any, Dict
+
+import torch
+
+from ....inference_utils import DtypeEnum, NormTypeEnum
+from ....kernels.core_ops import CUDARMSNorm, CUDARMSPreNorm
+from ...configs import DSNormConfig
+from ...interfaces import DSPreNormBase, DSPreNormRegistry
+
+
+@DSPreNormRegistry.register_module
+class DSPreRMSCUDAModule(DSPreNormBase):
+
+    @staticmethod
+    def name() -> str:
+        return "cuda_pre_rms"
+
+    @staticmethod
+    def supports_config(config: DSNormConfig) -> bool:
+        return NormTypeEnum(config.type) == NormTypeEnum.RMSNorm and len({config.residual_dtype, config.input_dtype,
+                                                                          config.output_dtype}) == 1
+
+    def __init__(self, config: DSNormConfig, implementation_config: Dict[str, Any] = None) -> None:
+        super().__init__(config, implementation_config)
+        dt = DtypeEnum(config.residual_dtype).value
+        self.rms, self.pre_rms = CUDARMSNorm(config.channels, dt, config.eps), CUDARMSPreNorm(config.channels, dt, config.eps)
+
+    def forward(self, residual, hidden_in, gamma, beta=None):
+        hidden = torch.empty_like(residual)
+        if hidden_in is None:
+            self.rms(hidden, residual, gamma)
+        else:
+            self.pre_rms(residual, hidden, residual, hidden_in, gamma)
+        return residual, hidden

@@ -55,6 +55,16 @@ def _build_logger(name="deepspeed_b200", level=logging.INFO):
 logger = _build_logger()
 
 
+class LoggerFactory:
+    """Reference-compatible factory (``utils/logging.py:LoggerFactory``)."""
+
+    @staticmethod
+    def create_logger(name=None, level=logging.INFO):
+        if name is None:
+            raise ValueError("name for logger cannot be None")
+        return _build_logger(name, level)
+
+
 def should_log(ranks=None) -> bool:
     """True when this process' rank is in ``ranks`` (``None``/``[-1]`` = everyone)."""
     if ranks is None:
