@@ -1,0 +1,24 @@
+"""Policy for Qwen2 (llama layout with QKV biases) (reference ``model_implementations/qwen_v2/policy.py``)."""
+from ..inference_policy_base import ContainerMap, InferenceV2Policy
+from .container import Qwen2NonTransformerContainer, Qwen2TransformerContainer
+from .model import Qwen2InferenceModel
+
+
+class Qwen2Policy(InferenceV2Policy):
+    model_type = "qwen2"
+
+    def instantiate_model(self, engine_config, mp_group=None) -> Qwen2InferenceModel:
+        import torch
+        from deepspeed_b200 import comm as dist
+        tp = getattr(getattr(engine_config, "tensor_parallel", None), "tp_size", 1) if engine_config is not None else 1
+        rank = dist.get_rank(mp_group) if (mp_group is not None and tp > 1) else 0
+        return Qwen2InferenceModel.from_hf_config(self._model_config, mp_group, tp, rank)
+
+    def build_container_map(self, model=None) -> ContainerMap:
+        """Declarative checkpoint map: one transformer container per layer + the non-transformer container."""
+        model = model if model is not None else self.instantiate_model(None)
+        cmap = ContainerMap()
+        cmap.set_transformer_params(["model.layers"], [Qwen2TransformerContainer(model) for _ in range(model.num_layers)])
+        cmap.set_non_transformer_params(Qwen2NonTransformerContainer(model))
+        cmap.set_unmapped_params([])
+        return cmap

@@ -65,6 +65,27 @@ class RaggedTransformer:
         self._state_manager = None
         self.all_logits = False  # v1 `forward` wants every position's logits
 
+    def flat_tensors(self):
+        """name -> tensor for every weight this rank holds (quantised weights contribute their codes and scales); the
+        contract ``flat_model_helpers`` serialises / restores through."""
+        out = {}
+
+        def add(name, v):
+            if torch.is_tensor(v):
+                out[name] = v
+            elif hasattr(v, "q") and hasattr(v, "params"):  # QuantizedWeight
+                out[name + ".q"], out[name + ".scales"] = v.q, v.params
+            elif isinstance(v, (list, tuple)):
+                for i, x in enumerate(v):
+                    add(f"{name}.{i}", x)
+
+        for k in ("embed_w", "pos_w", "final_ln_w", "final_ln_b", "lm_head_w", "lm_head_b"):
+            add(k, getattr(self, k))
+        for i, lw in enumerate(self.layers):
+            for sname in lw.__slots__:
+                add(f"layers.{i}.{sname}", getattr(lw, sname, None))
+        return out
+
     # ------------------------------------------------------------------ engine-facing API
     def kv_cache_config(self, block_size=128, max_context=8192):
         from ..config_v2 import KVCacheConfig
