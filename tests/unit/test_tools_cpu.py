@@ -64,3 +64,40 @@ def test_env_report_runs(capsys):
     main()
     out = capsys.readouterr().out
     assert "fused_adam" in out and "torch version" in out
+
+
+def test_nvme_tooling_sweep_logs_and_param_generation(tmp_path):
+    """reference-dialect ds_io args, a 2-point sweep with config-encoded log names, log parsing, best-config selection."""
+    import pytest
+    from deepspeed_b200.nvme import ds_aio_args, parse_nvme_stats, perf_generate_param, perf_run_sweep
+    from deepspeed_b200.nvme.ds_aio_job import Job, run_job
+    from deepspeed_b200.nvme.test_ds_aio import ds_io_main
+    from deepspeed_b200.nvme.test_ds_aio_utils import get_block_size_and_count, refine_integer_value
+    from deepspeed_b200.nvme.validate_async_io import main as validate
+    assert refine_integer_value("4K") == 4096 and refine_integer_value("2m") == 2 << 20 and refine_integer_value("17") == 17
+    assert get_block_size_and_count(3 << 20) == (1 << 20, 3)
+    io = tmp_path / "io"
+    io.mkdir()
+    args = ds_aio_args.get_validated_args(["--folder", str(io), "--io_size", "1M", "--block_size", "128K", "--loops", "1", "--read"])
+    assert args.io_size == 1 << 20 and args.mapping_list == [(0, str(io))]
+    with pytest.raises(SystemExit):
+        ds_aio_args.get_validated_args(["--io_size", "1M"])
+    assert ds_io_main(["--folder", str(io), "--io_size", "1M", "--block_size", "128K", "--loops", "1"]) > 0  # write
+    assert ds_io_main(["--folder", str(io), "--io_size", "1M", "--block_size", "128K", "--loops", "1", "--read"]) > 0
+    cfg = tmp_path / "sweep.json"
+    cfg.write_text('{"block_size": ["128K", "256K"], "queue_depth": [4], "io_parallel": [1], "single_submit": [false]}')
+    sargs = perf_run_sweep.parse_sweep_arguments(["--nvme_dir", str(io), "--sweep_config", str(cfg), "--io_size", "1M", "--log_dir",
+                                                  str(tmp_path / "logs")])
+    assert perf_run_sweep.validate_arguments(sargs)
+    log_dir = perf_run_sweep.sweep_main(sargs)
+    rlogs = sorted(p.name for p in (tmp_path / "logs" / "_aio_bench_read_logs").iterdir())
+    assert rlogs == ["read_block_overlap_t1_p1_d4_bs128K.txt", "read_block_overlap_t1_p1_d4_bs256K.txt"]
+    res, keys = parse_nvme_stats.get_sorted_results(str(tmp_path / "logs" / "_aio_bench_read_logs"), "read_speed")
+    assert len(res) == 2 and all(v > 0 for v in res.values())
+    assert parse_nvme_stats.get_thread_count("x/read_block_overlap_t8_p2_d4_bs1M.txt") == 16
+    param = perf_generate_param.generate_main(log_dir)
+    assert param["queue_depth"] == 4 and param["block_size"] in (128 << 10, 256 << 10) and param["single_submit"] == "false"
+    out = tmp_path / "job.txt"
+    run_job(Job(["echo", "hello"], str(out)))
+    assert out.read_text().strip() == "hello"
+    assert validate() is True
