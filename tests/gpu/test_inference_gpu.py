@@ -171,3 +171,31 @@ def test_graphed_wrappers_replay_on_gpu():
         out = g(x, s)
         torch.testing.assert_close(out, ref, atol=2e-3, rtol=2e-3)
     assert g.captures == 2 and g.replays == 5
+
+
+def test_layerwise_kernel_injection_bf16_gpu():
+    """Policy/container injection on the device (bf16): logits stay close to the Hugging Face model, generate() agrees."""
+    import copy
+    from types import SimpleNamespace
+    transformers = pytest.importorskip("transformers")
+    from transformers import AutoConfig, AutoModelForCausalLM
+    from deepspeed_b200.module_inject.containers.base import InjectedLayer
+    from deepspeed_b200.module_inject.replace_module import replace_transformer_layer
+    cfg = AutoConfig.for_model("llama", vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=8,
+                               num_key_value_heads=4, intermediate_size=512, max_position_embeddings=256)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    model = AutoModelForCausalLM.from_config(cfg).to(torch.bfloat16).cuda().eval()
+    icfg = SimpleNamespace(replace_with_kernel_inject=True, dtype=torch.bfloat16, max_out_tokens=128,
+                           tensor_parallel=SimpleNamespace(tp_size=1),
+                           quant=SimpleNamespace(enabled=False, weight=SimpleNamespace(post_init_quant=None)))
+    inj = replace_transformer_layer(None, copy.deepcopy(model), config=icfg).cuda()
+    assert sum(isinstance(m, InjectedLayer) for m in inj.modules()) == 2
+    ids = torch.randint(0, 512, (2, 24), device="cuda")
+    with torch.no_grad():
+        a, b = model(ids).logits.float(), inj(ids).logits.float()
+    assert torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0) > 0.999
+    with torch.no_grad():
+        g1 = model.generate(ids[:, :8], max_new_tokens=6, do_sample=False, pad_token_id=0)
+        g2 = inj.generate(ids[:, :8], max_new_tokens=6, do_sample=False, pad_token_id=0)
+    assert (g1 == g2).float().mean() > 0.9
