@@ -444,6 +444,178 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 
 // ==================================================================================================================
+// Grouped (MoE) variant: C[rows, N] = A[rows, K] x W[e][N, K]^T where the rows of A are sorted by expert and expert e owns
+// rows offsets[e] .. offsets[e+1].  One persistent launch covers every expert: the tile list is built on the device from
+// `offsets` (no host synchronisation, CUDA-graph capturable), m-tiles of an expert start at its first row (so a tile never
+// mixes two experts' weights) and the rows of a tail tile that belong to the next expert are computed and discarded by
+// the epilogue, which therefore writes global memory directly (predicated 16-byte stores of full 128-byte row segments)
+// instead of using a TMA store.  Same TMA -> tcgen05 -> TMEM pipeline as gemm_nt_kernel.
+// Reference role: inference/v2/kernels/cutlass_ops/moe_gemm (CUTLASS grouped GEMM).
+// ==================================================================================================================
+constexpr int kMaxGroups = 256;
+constexpr uint32_t SMEM_GRP = SMEM_BAR + 256;                        // int tile_prefix[kMaxGroups + 1]
+constexpr uint32_t SMEM_GRP_TOTAL = SMEM_GRP + (kMaxGroups + 1) * 4 + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_grouped_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       __nv_bfloat16* __restrict__ C, const int* __restrict__ offsets, int E, int N, int K, int ldc)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_base = sbase + SMEM_BAR;
+    auto full_bar = [&](int s) { return bar_base + 8 * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8 * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8 * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8 * (2 * STAGES + 2 + s); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * STAGES + 4));
+    int* tile_prefix = reinterpret_cast<int*>(smem + SMEM_GRP);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_n = (N + BN - 1) / BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 3 && lane == 0) {
+        int acc = 0;
+        tile_prefix[0] = 0;
+        for (int e = 0; e < E; ++e) {
+            const int cnt = offsets[e + 1] - offsets[e];
+            acc += ((cnt + BM - 1) / BM) * num_n;
+            tile_prefix[e + 1] = acc;
+        }
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int num_tiles = tile_prefix[E];
+    const int num_k = (K + BK - 1) / BK;
+
+    // tile id -> (expert, first row of the m-tile, rows of the expert left from there, n block); `e` only moves forward
+    auto locate = [&](int tile, int& e, int& row0, int& rows_left, int& n_blk) {
+        while (tile >= tile_prefix[e + 1]) ++e;
+        const int lo = offsets[e], cnt = offsets[e + 1] - lo;
+        const int num_m = (cnt + BM - 1) / BM;
+        const int local = tile - tile_prefix[e];
+        const int m_blk = local % num_m;
+        n_blk = local / num_m;
+        row0 = lo + m_blk * BM;
+        rows_left = cnt - m_blk * BM;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0, e = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int row0, rows_left, n_blk;
+                locate(tile, e, row0, rows_left, n_blk);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_2d(sbase + SMEM_A + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, row0);
+                    tma_load_2d(sbase + SMEM_B + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, e * N + n_blk * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(tempty_bar(as), aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = make_desc_kmajor_sw128(sbase + SMEM_A + stage * A_STAGE_BYTES);
+                    const uint64_t db = make_desc_kmajor_sw128(sbase + SMEM_B + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16(tmem_d, da + static_cast<uint64_t>((k * UMMA_K * 2) >> 4),
+                                  db + static_cast<uint64_t>((k * UMMA_K * 2) >> 4), kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tfull_bar(as));
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        int it = 0, e = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int row0, rows_left, n_blk;
+            locate(tile, e, row0, rows_left, n_blk);
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+            const bool row_ok = row < rows_left;
+            __nv_bfloat16* crow = C + static_cast<int64_t>(row0 + row) * ldc + n_blk * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / CCHUNK; ++c) {
+                uint32_t r[64];
+                tmem_ld_32x32(taddr + c * CCHUNK, r);
+                tmem_ld_32x32(taddr + c * CCHUNK + 32, r + 32);
+                tmem_ld_wait();
+                if (c == BN / CCHUNK - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = n_blk * BN + c * CCHUNK + j * 8;
+                        if (col < N) {  // N % 8 == 0: a vector of 8 is entirely inside or outside
+                            float f[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(r[j * 8 + q]);
+                            *reinterpret_cast<Vec16*>(crow + c * CCHUNK + j * 8) = Elem<__nv_bfloat16>::pack(f);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+
+// ==================================================================================================================
 // 2-CTA variant (cta_group::2): a CTA *pair* on one TPC computes a 256x256 tile.  Each CTA stages its own 128 rows of A
 // and HALF of the B tile (128 of the 256 N rows), so the L2->SM operand traffic per flop drops by a third versus the
 // 1-CTA kernel (32 KiB instead of 48 KiB per CTA per k-block); the leader CTA's elected thread issues
@@ -886,6 +1058,38 @@ DSB_EXPORT int dsb_gemm_nt_bf16_allgather(const void* a, const void* b, void* c,
     ag.epoch = epoch;
     ag.enabled = 1;
     return launch(a, b, c, M, N, K, lda, ldb, ldc, ag, sms, stream);
+}
+
+// Grouped GEMM for expert-sorted rows: c[r, :] = a[r, :] @ w[e]^T for offsets[e] <= r < offsets[e+1].
+// a [rows, K] (lda), w [E, N, K] contiguous, c [rows, N] (ldc), offsets int32 [E+1] ON THE DEVICE.
+static bool g_attr_grp_set = false;
+DSB_EXPORT int dsb_gemm_grouped_nt_bf16(const void* a, const void* w, void* c, const int* offsets, int rows, int E, int N, int K,
+                                        int lda, int ldc, int sms, cudaStream_t stream)
+{
+    if (rows <= 0 || E <= 0) return 0;
+    if (E > kMaxGroups || K % 8 || N % 8 || lda % 8 || ldc % 8) return -3;
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(c)) & 15) return -3;
+    CUtensorMap ma, mb;
+    int rc;
+    if ((rc = make_map(&ma, a, rows, K, lda, BM, BK))) return rc;
+    if ((rc = make_map(&mb, w, static_cast<uint64_t>(E) * N, K, K, BN, BK))) return rc;
+    if (!g_attr_grp_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_grouped_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_GRP_TOTAL);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        if (!g_sm_count) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        }
+        g_attr_grp_set = true;
+    }
+    int grid = sms > 0 ? sms : g_sm_count;
+    // upper bound of the tile count (each expert adds at most one partial m-tile) so tiny problems do not launch idle CTAs
+    const int64_t max_tiles = (static_cast<int64_t>(rows + BM - 1) / BM + E) * ((N + BN - 1) / BN);
+    if (grid > max_tiles) grid = static_cast<int>(max_tiles);
+    gemm_grouped_nt_kernel<<<grid, kThreads, SMEM_GRP_TOTAL, stream>>>(ma, mb, static_cast<__nv_bfloat16*>(c), offsets, E, N, K, ldc);
+    DSB_CHECK_LAUNCH();
+    return 0;
 }
 
 DSB_EXPORT int dsb_gemm_tile_m() { return BM; }

@@ -19,8 +19,15 @@ def mixed_gemm(x, qweight, bias=None):
 
 def moe_gemm(x_sorted, expert_weights, offsets, out=None):
     """Grouped GEMM over expert-sorted rows (reference cutlass ``moe_gemm``): ``x_sorted`` [rows, K] with expert e owning
-    rows ``offsets[e]:offsets[e+1]``, ``expert_weights`` [E, N, K] (or a list).  One tensor-core GEMM per non-empty expert."""
+    rows ``offsets[e]:offsets[e+1]``, ``expert_weights`` [E, N, K] (or a list).  On the device with bf16 stacked weights
+    this is ONE persistent tcgen05 launch driven by the device-resident offsets (``gemm_grouped_nt_kernel``); otherwise
+    one GEMM per non-empty expert."""
     import torch
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    if torch.is_tensor(offsets) and gemm_sm100.supports_grouped(x_sorted, expert_weights, offsets.to(torch.int32)
+                                                                if offsets.dtype != torch.int32 else offsets):
+        return gemm_sm100.grouped_matmul_nt(x_sorted, expert_weights, offsets if offsets.dtype == torch.int32 else
+                                            offsets.to(torch.int32), out=out)
     off = offsets.tolist() if torch.is_tensor(offsets) else list(offsets)
     E = len(off) - 1
     n_out = expert_weights[0].shape[0]

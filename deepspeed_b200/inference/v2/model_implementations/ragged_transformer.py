@@ -12,6 +12,8 @@ are long enough go through the dense flash path (cuDNN SDPA) after their K/V wer
 import math
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -179,6 +181,18 @@ class RaggedTransformer:
         logits = F.linear(x, lw.gate_w)
         ids, w, counts = M.top_k_gating(logits, sp.top_k, normalize=sp.norm_topk)
         capturing = x.is_cuda and torch.cuda.is_current_stream_capturing()
+        if (x.is_cuda and x.dtype == torch.bfloat16 and torch.is_tensor(lw.experts_up) and torch.is_tensor(lw.experts_down)
+                and lw.experts_up.dtype == torch.bfloat16 and os.environ.get("DSB200_MOE_GROUPED", "1") != "0"):
+            # device-driven grouped GEMM: one persistent tcgen05 launch per projection streams only the experts that
+            # received tokens; offsets never leave the device, so prefill and (graph-captured) decode share this path
+            from deepspeed_b200.inference.v2.kernels import moe_gemm
+            positions, _, offsets = M.route(ids, sp.num_experts, counts=counts)
+            rows = Tn * sp.top_k
+            xs, slots = M.scatter(x, ids, positions, offsets, sp.top_k, 0, rows)
+            h = T.gated_act(moe_gemm(xs, lw.experts_up, offsets), sp.act)
+            ys = moe_gemm(h, lw.experts_down, offsets)
+            out = M.gather(ys, w, slots, Tn, sp.top_k)
+            return self._moe_shared(lw, x, out)
         if capturing or Tn <= MOE_DENSE_MAX_TOKENS:
             # decode-sized batch: every expert's weights get streamed once anyway (weight-bandwidth bound), so run
             # all experts on all rows and mask — no host sync, static shapes, CUDA-graph capturable.

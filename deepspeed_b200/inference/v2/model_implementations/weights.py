@@ -48,7 +48,15 @@ def _finish(model: RaggedTransformer, quant_mode=None):
         for s in lw.__slots__:
             v = getattr(lw, s)
             if isinstance(v, list):
-                setattr(lw, s, [put(x) for x in v])
+                if s in ("experts_up", "experts_down") and v and not quant_mode and len({tuple(x.shape) for x in v}) == 1:
+                    # stacked [E, N, K]: the layout the grouped (MoE) GEMM kernel consumes; still indexable per expert.
+                    # Filled expert by expert so the host never holds a second full copy.
+                    stacked = torch.empty(len(v), *v[0].shape, dtype=model.dtype, device=model.device)
+                    for i, x in enumerate(v):
+                        stacked[i].copy_(x)
+                    setattr(lw, s, stacked)
+                else:
+                    setattr(lw, s, [put(x) for x in v])
             elif v is not None:
                 setattr(lw, s, put(v))
         if quant_mode:

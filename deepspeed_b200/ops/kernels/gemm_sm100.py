@@ -34,6 +34,28 @@ def matmul_nt(a, b, out=None, sms=0):
     return out
 
 
+def supports_grouped(x, w, offsets) -> bool:
+    """bf16 rows [R, K] (row stride % 8), stacked weights [E, N, K] contiguous, int32 device offsets [E + 1]."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and torch.is_tensor(w) and w.dtype == torch.bfloat16 and w.dim() == 3
+            and w.is_contiguous() and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == w.shape[2] and x.shape[1] % 8 == 0
+            and w.shape[1] % 8 == 0 and x.stride(0) % 8 == 0 and w.shape[0] <= 256 and torch.is_tensor(offsets)
+            and offsets.is_cuda and offsets.dtype == torch.int32 and x.data_ptr() % 16 == 0 and w.data_ptr() % 16 == 0
+            and x.shape[1] >= 64)
+
+
+def grouped_matmul_nt(x, w, offsets, out=None, sms=0):
+    """Grouped (MoE) GEMM: ``out[r] = x[r] @ w[e]^T`` for ``offsets[e] <= r < offsets[e+1]`` in ONE persistent tcgen05
+    launch; ``offsets`` stays on the device (no host sync, CUDA-graph capturable)."""
+    R, K = x.shape
+    E, Nn, _ = w.shape
+    if out is None:
+        out = torch.empty(R, Nn, dtype=torch.bfloat16, device=x.device)
+    rc = N.cuda().dsb_gemm_grouped_nt_bf16(N.ptr(x), N.ptr(w), N.ptr(out), N.ptr(offsets), R, E, Nn, K, x.stride(0), out.stride(0),
+                                           sms, N.stream())
+    N.check(rc, "gemm_grouped_nt_bf16")
+    return out
+
+
 def matmul_nt_2cta(a, b, out=None, sms=0):
     """Same contract as :func:`matmul_nt`, CTA-pair kernel (``tcgen05.mma.cta_group::2``, 256x256 tiles)."""
     M, K = a.shape

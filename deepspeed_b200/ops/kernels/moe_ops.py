@@ -35,13 +35,15 @@ def top_k_gating(logits, k, normalize=True):
     return ids.to(torch.int32), w, counts
 
 
-def route(expert_ids, num_experts):
-    """positions [T*k] (slot inside the expert, token-major order), counts [E], offsets [E+1]."""
+def route(expert_ids, num_experts, counts=None):
+    """positions [T*k] (slot inside the expert, token-major order), counts [E], offsets [E+1].  Passing the ``counts`` the
+    gating kernel already produced avoids ``torch.bincount`` (which synchronises and cannot be graph-captured)."""
     flat = expert_ids.reshape(-1).to(torch.int32).contiguous()
     n = flat.numel()
     dev = flat.device
     if flat.is_cuda:
-        counts = torch.bincount(flat, minlength=num_experts).to(torch.int32)
+        if counts is None:
+            counts = torch.bincount(flat, minlength=num_experts).to(torch.int32)
         positions = torch.empty(n, dtype=torch.int32, device=dev)
         offsets = torch.empty(num_experts + 1, dtype=torch.int32, device=dev)
         rc = N.cuda().dsb_moe_assign_positions(_p(flat), _p(counts), _p(positions), _p(offsets), n, num_experts,

@@ -93,3 +93,24 @@ def test_flat_linear_backward_uses_native_gemm_and_matches_autograd():
         s = ref.float().abs().max().item()
         assert (got.float() - ref.float()).abs().max().item() < 2e-2 * s + 1e-2
     assert any(k[0] in ("nn", "tn") for k in gemm.tuning_table() if isinstance(k[0], str))
+
+
+@pytest.mark.parametrize("counts", [[300, 0, 17, 128, 1, 513], [0, 0, 5, 0], [256, 256]])
+@pytest.mark.parametrize("N,K", [(512, 256), (328, 192)])
+def test_grouped_gemm_matches_per_expert_loop(counts, N, K):
+    """Device-driven grouped tcgen05 GEMM (MoE): ragged expert extents incl. empty experts, N not a tile multiple."""
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    torch.manual_seed(0)
+    E, rows = len(counts), sum(counts)
+    x = (torch.randn(rows, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(E, N, K, device="cuda") * 0.1).bfloat16()
+    off = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device="cuda")
+    assert gemm_sm100.supports_grouped(x, w, off)
+    out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    gemm_sm100.grouped_matmul_nt(x, w, off, out=out)
+    s = 0
+    for e, c in enumerate(counts):
+        ref = x[s:s + c].float() @ w[e].float().t()
+        torch.testing.assert_close(out[s:s + c].float(), ref, atol=2e-2 * max(1.0, ref.abs().max().item()) if c else 0, rtol=2e-2)
+        s += c
+    assert torch.isfinite(out.float()).all()
