@@ -21,6 +21,15 @@ class MoEGEMM(DSKernelBase):
     def __call__(self, ordered_output, ordered_input, weights, cumsum_rows, biases=None) -> None:
         """``weights`` [E, out, in]; expert e owns rows ``cumsum_rows[e-1]:cumsum_rows[e]`` of the sorted input."""
         from ... import moe_gemm
+        if torch.is_tensor(cumsum_rows) and cumsum_rows.is_cuda and biases is None and torch.is_tensor(weights):
+            # device-resident offsets -> single grouped tcgen05 launch, no host synchronisation
+            off = torch.cat([cumsum_rows.new_zeros(1), cumsum_rows]).to(torch.int32)
+            moe_gemm(ordered_input, weights, off, out=ordered_output)
+            if self.act_fn == ActivationFuncType.GELU:
+                ordered_output.copy_(torch.nn.functional.gelu(ordered_output))
+            elif self.act_fn == ActivationFuncType.ReLU:
+                ordered_output.relu_()
+            return ordered_output
         ends = cumsum_rows.tolist() if torch.is_tensor(cumsum_rows) else list(cumsum_rows)
         offsets = [0] + [int(e) for e in ends]
         moe_gemm(ordered_input, weights, offsets, out=ordered_output)
