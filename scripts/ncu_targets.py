@@ -72,6 +72,16 @@ elif which == "paged":
     for _ in range(3):
         flush.zero_()
         R.paged_attention(qkv, cache, seq_of, pos_of, bt, hq, hkv, dd, bs)
+elif which == "grouped":
+    from deepspeed_b200.ops.kernels import gemm_sm100
+    E, N, K = 8, 28672, 4096  # Mixtral gate+up projection
+    w = (torch.randn(E, N, K, device=d) * 0.02).bfloat16()
+    for rows_per in (2, 512):  # decode-like (weight streaming) and prefill-like (tensor-core bound)
+        x = (torch.randn(E * rows_per, K, device=d) * 0.5).bfloat16()
+        off = (torch.arange(E + 1, device=d, dtype=torch.int32) * rows_per)
+        for _ in range(2):
+            flush.zero_()
+            gemm_sm100.grouped_matmul_nt(x, w, off)
 elif which == "wq":
     from deepspeed_b200.inference.quantization.layers import maybe_quantized_linear, quantize_weight
     N, K, M = 28672, 4096, 8
