@@ -97,7 +97,10 @@ def paged_attention(qkv, cache, seq_of, pos_of, block_table, hq, hkv, d, block_s
             max_ctx = max_blocks * block_size
             nsplit = 1
             ctas = T * hkv
-            while ctas * nsplit < 592 and nsplit < 32 and max_ctx // (nsplit * 2) >= 256:
+            # the tensor-core kernel runs 2 CTAs per SM: one full wave (296 CTAs) is enough, every extra KV split costs a
+            # partial-result round trip (measured: 118 us at 296 vs 130 us at 592 for 64 seqs x 2048 ctx)
+            target = int(os.environ.get("DSB200_PAGED_CTA_TARGET", "296" if os.environ.get("DSB200_PAGED_DECODE_MMA", "1") != "0" else "592"))
+            while ctas * nsplit < target and nsplit < 32 and max_ctx // (nsplit * 2) >= 256:
                 nsplit *= 2
             ws_acc, ws_ml = _decode_ws(qkv.device, T * hq * nsplit * d, T * hq * nsplit * 2) if nsplit > 1 else (None, None)
             rc = N.cuda().dsb_paged_decode(_p(qkv), _p(cache), _p(out), _p(ws_acc), _p(ws_ml), _p(seq_of), _p(pos_of),
