@@ -221,3 +221,66 @@ def _bert_engine():
     with torch.no_grad():
         out = eng(ids).last_hidden_state
     assert (out - ref).abs().max() < 2e-4
+
+
+def _tp_inject(family):
+    """tp=2 layer-wise injection: every rank holds half the heads / MLP columns; the all-reduced result equals the HF model."""
+    import torch.distributed as td
+    from deepspeed_b200.utils import groups
+    torch.manual_seed(0)
+    cfg = AutoConfig.for_model(family, **CAUSAL[family])
+    cfg._attn_implementation = "eager"
+    model = AutoModelForCausalLM.from_config(cfg).eval()
+    ids = torch.randint(0, 100, (2, 9))
+    with torch.no_grad():
+        ref = model(ids).logits
+    icfg = _cfg()
+    icfg.tensor_parallel = SimpleNamespace(tp_size=2)
+    inj = replace_transformer_layer(None, copy.deepcopy(model), config=icfg)
+    layers = [m for m in inj.modules() if isinstance(m, InjectedLayer)]
+    assert len(layers) == 2
+    f = layers[0].fused
+    full = [m for m in model.modules() if type(m).__name__.endswith(("DecoderLayer", "Block"))][0]
+    assert f.attn_qkvw.shape[0] < sum(p.shape[0] for n, p in full.named_parameters() if any(k in n for k in ("q_proj.weight", "k_proj.weight",
+                                      "v_proj.weight", "c_attn.weight"))) or family == "gpt2"
+    with torch.no_grad():
+        out = inj(ids).logits
+    assert (out - ref).abs().max() < 3e-4, (out - ref).abs().max()
+    # checkpoint-driven loading applies the same slicing
+    from deepspeed_b200.module_inject.load_checkpoint import load_model_with_checkpoint
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        for l in layers:
+            for p in l.fused.parameters():
+                p.normal_()
+    load_model_with_checkpoint(inj, sd, mp_group=groups.get_tensor_model_parallel_group(), mp_size=2)
+    with torch.no_grad():
+        assert (inj(ids).logits - ref).abs().max() < 3e-4
+
+
+@pytest.mark.parametrize("family", ["llama", "gpt2", "opt"])
+def test_layerwise_injection_tensor_parallel(family):
+    from tests.common import run_distributed
+    run_distributed(_tp_inject, 2, (family, ))
+
+
+def test_module_quantize_and_training_inject():
+    from transformers.models.bert.modeling_bert import BertLayer
+    from deepspeed_b200.module_inject.inject import module_inject
+    from deepspeed_b200.module_inject.module_quantize import quantize_transformer_layer
+    torch.manual_seed(0)
+    cfg = AutoConfig.for_model("bert", **ENCODERS["bert"])
+    cfg._attn_implementation = "eager"
+    model = AutoModel.from_config(cfg).eval()
+    q = quantize_transformer_layer(BertLayer, copy.deepcopy(model))
+    lin = q.encoder.layer[0].intermediate.dense
+    assert lin.weight.dtype == torch.int8 and hasattr(lin.weight, "scale")
+    ref_w = model.encoder.layer[0].intermediate.dense.weight
+    assert (lin.weight.float() * lin.weight.scale - ref_w).abs().max() <= lin.weight.scale * 0.51
+    # training-time injection: fused training layer with the HF weights copied in
+    tr = module_inject(BertLayer, copy.deepcopy(model), cfg, micro_batch_size=2, max_seq_length=16, seed=1, preln=False, fp16=False)
+    from deepspeed_b200.ops.transformer import DeepSpeedTransformerLayer
+    new = tr.encoder.layer[0]
+    assert isinstance(new, DeepSpeedTransformerLayer)
+    a = model.encoder.layer[0].attention
+    assert torch.equal(new.attn_qkvw[:32], a.self.query.weight) and torch.equal(new.output_w, model.encoder.layer[0].output.dense.weight)
