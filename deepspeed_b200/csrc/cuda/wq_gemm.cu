@@ -15,6 +15,8 @@
 // into its own fp32 tile and the group scale is applied to that tile in fp32 -- scaling before the rounding to bf16 would
 // cost an instruction per weight and lose bits.  Partial sums of the 8 warps are reduced through shared memory.
 // (mma.sync on purpose: at M <= 64 a tcgen05 tile would be >75% padding and the kernel is bound by the weight stream.)
+#include <cuda_fp8.h>
+#include <type_traits>
 #include "dsb_common.cuh"
 
 namespace dsb {
@@ -92,7 +94,21 @@ __device__ __forceinline__ float dq8(const Vec16& pk, int e)
     return __uint_as_float(__byte_perm(pk.w[e >> 2] ^ 0x80808080u, 0x4B000000u, 0x7650 | (e & 3))) - (8388608.f + 128.f);
 }
 
-template <typename T, int BITS, int NT, int MT>
+// two e4m3 codes (the low / high half of a packet word) -> one packed fragment register; e4m3 values are exact in bf16
+template <typename T>
+__device__ __forceinline__ uint32_t fp8x2_frag(uint32_t word, int hi)
+{
+    const __nv_fp8x2_storage_t two = static_cast<__nv_fp8x2_storage_t>(hi ? (word >> 16) : (word & 0xffffu));
+    const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2(two, __NV_E4M3);
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+        return *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+        return Frag<T>::pack(f.x, f.y);
+    }
+}
+
+template <typename T, int BITS, int NT, int MT, bool FP8 = false>
 __global__ void __launch_bounds__(kWarps * 32)
 wq_mma_kernel(const T* __restrict__ x, const int8_t* __restrict__ wq, const float* __restrict__ scales,
               const T* __restrict__ bias, T* __restrict__ out, int M, int N, int K, int group_size, int S)
@@ -203,8 +219,14 @@ wq_mma_kernel(const T* __restrict__ x, const int8_t* __restrict__ wq, const floa
                     const int j = 2 * jp + h;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        const uint32_t b0 = Frag<T>::pack(dq8(cur[nt], 4 * j), dq8(cur[nt], 4 * j + 1));
-                        const uint32_t b1 = Frag<T>::pack(dq8(cur[nt], 4 * j + 2), dq8(cur[nt], 4 * j + 3));
+                        uint32_t b0, b1;
+                        if constexpr (FP8) {
+                            b0 = fp8x2_frag<T>(cur[nt].w[j], 0);
+                            b1 = fp8x2_frag<T>(cur[nt].w[j], 1);
+                        } else {
+                            b0 = Frag<T>::pack(dq8(cur[nt], 4 * j), dq8(cur[nt], 4 * j + 1));
+                            b1 = Frag<T>::pack(dq8(cur[nt], 4 * j + 2), dq8(cur[nt], 4 * j + 3));
+                        }
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) Frag<T>::mma(tmp[mt][nt], a[h][mt], b0, b1);
                     }
@@ -271,14 +293,14 @@ wq_mma_kernel(const T* __restrict__ x, const int8_t* __restrict__ wq, const floa
     }
 }
 
-template <typename T, int BITS>
+template <typename T, int BITS, bool FP8 = false>
 void launch(const void* x, const void* wq, const float* scales, const void* bias, void* out, int M, int N, int K, int gs,
             cudaStream_t stream)
 {
     constexpr int kSmemBudget = 80 * 1024;  // two CTAs per SM and ~90 KB of L1 left for the activations
 #define WQ_GO(NT, MT)                                                                                                   \
     do {                                                                                                                \
-        auto kern = wq_mma_kernel<T, BITS, NT, MT>;                                                                     \
+        auto kern = wq_mma_kernel<T, BITS, NT, MT, FP8>;                                                                  \
         const int stage = NT * 512 + ((M + 7) / 8) * (BITS == 8 ? 2 : 4) * 512 + 128;                                   \
         int S = kSmemBudget / (kWarps * stage);                                                                         \
         S = S < 2 ? 2 : (S > 4 ? 4 : S);                                                                                \
@@ -325,6 +347,23 @@ DSB_EXPORT int dsb_wq_gemv(const void* x, const void* wq, const float* scales, c
         if (bits == 8) wq::launch<__half, 8>(x, wq, scales, bias, out, M, N, K, group_size, stream);
         else wq::launch<__half, 4>(x, wq, scales, bias, out, M, N, K, group_size, stream);
     }
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+// FP8 (e4m3 codes + one fp32 scale per group) weights: same kernel, the codes are converted with the hardware
+// fp8x2 -> f16x2 instruction on their way into the fragments.
+DSB_EXPORT int dsb_wq_gemv_fp8(const void* x, const void* wq, const float* scales, const void* bias, void* out, int M, int N, int K,
+                               int group_size, int dtype, cudaStream_t stream)
+{
+    if (M <= 0 || N <= 0) return 0;
+    if (M > 32 || K % 64 || group_size % 64 || K % group_size) return -3;
+    if (dtype == kBF16)
+        wq::launch<__nv_bfloat16, 8, true>(x, wq, scales, bias, out, M, N, K, group_size, stream);
+    else if (dtype == kF16)
+        wq::launch<__half, 8, true>(x, wq, scales, bias, out, M, N, K, group_size, stream);
+    else
+        return -3;
     DSB_CHECK_LAUNCH();
     return 0;
 }

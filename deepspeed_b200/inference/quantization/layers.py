@@ -30,7 +30,7 @@ class QuantizedWeight:
                                 dtype=self.dtype).view(self.shape)
         from deepspeed_b200.ops.fp_quantizer.quantize import FP_Quantize
         fq = FP_Quantize(group_size=self.group_size)
-        fq.orig_shape, fq.orig_dtype = self.shape, self.dtype
+        fq.orig_shape, fq.orig_dtype = torch.Size(self.shape), self.dtype
         bits, man = (8, 3) if self.mode == "fp8" else (6, 2)
         return fq.dequantize(self.q, q_bits=bits, q_mantisa_bits=man, scale=self.params).view(self.shape).to(self.dtype)
 
@@ -64,7 +64,7 @@ def maybe_quantized_linear(x, w, b=None):
 def _wq_gemv(x, qw: "QuantizedWeight", b):
     """Decode-sized inputs: fused in-register dequantisation + GEMV (``csrc/cuda/wq_gemm.cu``); None -> not eligible."""
     import ctypes
-    if not (x.is_cuda and qw.mode in ("int8", "int4") and x.dtype in (torch.bfloat16, torch.float16)):
+    if not (x.is_cuda and qw.mode in ("int8", "int4", "fp8") and x.dtype in (torch.bfloat16, torch.float16)):
         return None
     x2 = x.reshape(-1, x.shape[-1])
     M, K = x2.shape
@@ -75,8 +75,12 @@ def _wq_gemv(x, qw: "QuantizedWeight", b):
     x2 = x2.contiguous()
     out = torch.empty(M, N, dtype=x.dtype, device=x.device)
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
-    rc = NV.cuda().dsb_wq_gemv(p(x2), p(qw.q), p(qw.params), p(b.to(x.dtype).contiguous() if b is not None else None), p(out),
-                               M, N, K, 8 if qw.mode == "int8" else 4, qw.group_size, NV.dt(x2), NV.stream())
+    bias = b.to(x.dtype).contiguous() if b is not None else None
+    if qw.mode == "fp8":
+        rc = NV.cuda().dsb_wq_gemv_fp8(p(x2), p(qw.q), p(qw.params), p(bias), p(out), M, N, K, qw.group_size, NV.dt(x2), NV.stream())
+    else:
+        rc = NV.cuda().dsb_wq_gemv(p(x2), p(qw.q), p(qw.params), p(bias), p(out), M, N, K, 8 if qw.mode == "int8" else 4,
+                                   qw.group_size, NV.dt(x2), NV.stream())
     if rc == -3:
         return None
     NV.check(rc, "wq_gemv")

@@ -119,7 +119,7 @@ def test_v1_kernel_inject_generate():
     assert out.shape == (2, 20) and torch.equal(out[:, :12], ids)
 
 
-@pytest.mark.parametrize("mode", ["int8", "int4"])
+@pytest.mark.parametrize("mode", ["int8", "int4", "fp8"])
 @pytest.mark.parametrize("M", [1, 5, 16, 27, 32, 100])
 def test_weight_only_quantized_linear(mode, M):
     """Decode-sized inputs take the fused dequant+GEMV kernel, larger ones dequantise + tensor cores; both must equal the

@@ -105,3 +105,16 @@ def _qctx():
 def test_quantization_context_shards_packed_weights():
     from tests.common import run_distributed
     run_distributed(_qctx, 2)
+
+
+@pytest.mark.parametrize("mode,tol", [("int8", 0.02), ("int4", 0.2), ("fp8", 0.08), ("fp6", 0.2)])
+def test_weight_only_quantized_linear_all_formats_host(mode, tol):
+    from deepspeed_b200.inference.quantization.layers import maybe_quantized_linear, quantize_weight
+    torch.manual_seed(0)
+    w = torch.randn(32, 128) * 0.1
+    x = torch.randn(3, 128)
+    qw = quantize_weight(w, mode, group_size=64)
+    deq = qw.dequantize()
+    assert deq.shape == w.shape and (deq - w).abs().max() < tol * w.abs().max()
+    y = maybe_quantized_linear(x, qw)
+    assert torch.allclose(y, x @ deq.t(), atol=1e-5)
