@@ -1,5 +1,6 @@
 """Checkpoint-name mapping for Falcon (parallel attention/MLP, multi-query or grouped fused QKV) (reference ``model_implementations/falcon/container.py``)."""
 from ..common_parameters import *  # noqa: F401,F403
+from .. import param_maps as P
 from ..layer_container_base import LayerContainer
 
 
@@ -12,14 +13,8 @@ class FalconTransformerContainer(LayerContainer):
     ln_attn_gamma: NormParameter
     ln_attn_beta: NormParameter
 
-    PARAM_MAPPING = {
-        "self_attention.query_key_value.weight": "qkv_w.params",
-        "self_attention.dense.weight": "attn_out_w.params",
-        "mlp.dense_h_to_4h.weight": "mlp_1_w.params",
-        "mlp.dense_4h_to_h.weight": "mlp_2_w.params",
-        "input_layernorm.weight": "ln_attn_gamma.params",
-        "input_layernorm.bias": "ln_attn_beta.params",
-    }
+    PARAM_MAPPING = {**P.fused_qkv("self_attention.query_key_value"), **P.attn_out("self_attention.dense"),
+                     **P.plain_mlp("mlp.dense_h_to_4h", "mlp.dense_4h_to_h"), **P.norm("input_layernorm", "ln_attn_gamma", "ln_attn_beta")}
 
 
 class FalconNonTransformerContainer(LayerContainer):
@@ -29,9 +24,4 @@ class FalconNonTransformerContainer(LayerContainer):
     final_norm_w: NormParameter
     final_norm_b: NormParameter
 
-    PARAM_MAPPING = {
-        "transformer.word_embeddings.weight": "word_emb.params",
-        "transformer.ln_f.weight": "final_norm_w.params",
-        "transformer.ln_f.bias": "final_norm_b.params",
-        "lm_head.weight": "word_unembed.params",
-    }
+    PARAM_MAPPING = P.embeddings("transformer.word_embeddings", "transformer.ln_f", "lm_head", final_norm_bias=True)

@@ -1,5 +1,6 @@
 """Checkpoint-name mapping for Mistral (llama layout, sliding-window capable) (reference ``model_implementations/mistral/container.py``)."""
 from ..common_parameters import *  # noqa: F401,F403
+from .. import param_maps as P
 from ..layer_container_base import LayerContainer
 
 
@@ -12,17 +13,8 @@ class MistralTransformerContainer(LayerContainer):
     attn_norm_gamma: NormParameter
     mlp_norm_gamma: NormParameter
 
-    PARAM_MAPPING = {
-        "self_attn.q_proj.weight": "qkv_w.q_params",
-        "self_attn.k_proj.weight": "qkv_w.k_params",
-        "self_attn.v_proj.weight": "qkv_w.v_params",
-        "self_attn.o_proj.weight": "attn_out_w.params",
-        "mlp.gate_proj.weight": "mlp_1_w.gate_params",
-        "mlp.up_proj.weight": "mlp_1_w.up_params",
-        "mlp.down_proj.weight": "mlp_2_w.params",
-        "input_layernorm.weight": "attn_norm_gamma.params",
-        "post_attention_layernorm.weight": "mlp_norm_gamma.params",
-    }
+    PARAM_MAPPING = {**P.split_qkv("self_attn"), **P.attn_out("self_attn.o_proj"), **P.gated_mlp("mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"),
+                     **P.norm("input_layernorm", "attn_norm_gamma"), **P.norm("post_attention_layernorm", "mlp_norm_gamma")}
 
 
 class MistralNonTransformerContainer(LayerContainer):
@@ -31,8 +23,4 @@ class MistralNonTransformerContainer(LayerContainer):
     word_unembed: UnembedParameter
     final_norm: NormParameter
 
-    PARAM_MAPPING = {
-        "model.embed_tokens.weight": "word_emb.params",
-        "model.norm.weight": "final_norm.params",
-        "lm_head.weight": "word_unembed.params",
-    }
+    PARAM_MAPPING = P.embeddings("model.embed_tokens", "model.norm", "lm_head")

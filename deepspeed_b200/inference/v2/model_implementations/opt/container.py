@@ -1,5 +1,6 @@
 """Checkpoint-name mapping for OPT (LayerNorm, learned positions offset by 2, ReLU) (reference ``model_implementations/opt/container.py``)."""
 from ..common_parameters import *  # noqa: F401,F403
+from .. import param_maps as P
 from ..layer_container_base import LayerContainer
 
 
@@ -18,24 +19,9 @@ class OPTTransformerContainer(LayerContainer):
     mlp_norm_gamma: NormParameter
     mlp_norm_beta: NormParameter
 
-    PARAM_MAPPING = {
-        "self_attn.q_proj.weight": "qkv_w.q_params",
-        "self_attn.k_proj.weight": "qkv_w.k_params",
-        "self_attn.v_proj.weight": "qkv_w.v_params",
-        "self_attn.q_proj.bias": "qkv_b.q_params",
-        "self_attn.k_proj.bias": "qkv_b.k_params",
-        "self_attn.v_proj.bias": "qkv_b.v_params",
-        "self_attn.out_proj.weight": "attn_out_w.params",
-        "self_attn.out_proj.bias": "attn_out_b.params",
-        "fc1.weight": "mlp_1_w.params",
-        "fc1.bias": "mlp_1_b.params",
-        "fc2.weight": "mlp_2_w.params",
-        "fc2.bias": "mlp_2_b.params",
-        "self_attn_layer_norm.weight": "attn_norm_gamma.params",
-        "self_attn_layer_norm.bias": "attn_norm_beta.params",
-        "final_layer_norm.weight": "mlp_norm_gamma.params",
-        "final_layer_norm.bias": "mlp_norm_beta.params",
-    }
+    PARAM_MAPPING = {**P.split_qkv("self_attn", bias=True), **P.attn_out("self_attn.out_proj", bias=True), **P.plain_mlp("fc1", "fc2", bias=True),
+                     **P.norm("self_attn_layer_norm", "attn_norm_gamma", "attn_norm_beta"),
+                     **P.norm("final_layer_norm", "mlp_norm_gamma", "mlp_norm_beta")}
 
 
 class OPTNonTransformerContainer(LayerContainer):
@@ -46,9 +32,5 @@ class OPTNonTransformerContainer(LayerContainer):
     final_norm_w: NormParameter
     final_norm_b: NormParameter
 
-    PARAM_MAPPING = {
-        "model.decoder.embed_tokens.weight": ["word_emb.params", "word_unembed.params"],
-        "model.decoder.embed_positions.weight": "word_emb_pos.params",
-        "model.decoder.final_layer_norm.weight": "final_norm_w.params",
-        "model.decoder.final_layer_norm.bias": "final_norm_b.params",
-    }
+    PARAM_MAPPING = {**P.embeddings("model.decoder.embed_tokens", "model.decoder.final_layer_norm", final_norm_bias=True, tie=True),
+                     "model.decoder.embed_positions.weight": "word_emb_pos.params"}

@@ -1,5 +1,6 @@
 """Checkpoint-name mapping for Phi-3 (fused qkv_proj and gate_up_proj) (reference ``model_implementations/phi3/container.py``)."""
 from ..common_parameters import *  # noqa: F401,F403
+from .. import param_maps as P
 from ..layer_container_base import LayerContainer
 
 
@@ -12,14 +13,9 @@ class Phi3TransformerContainer(LayerContainer):
     attn_norm_gamma: NormParameter
     mlp_norm_gamma: NormParameter
 
-    PARAM_MAPPING = {
-        "self_attn.qkv_proj.weight": "qkv_w.params",
-        "self_attn.o_proj.weight": "attn_out_w.params",
-        "mlp.gate_up_proj.weight": "mlp_1_w.params",
-        "mlp.down_proj.weight": "mlp_2_w.params",
-        "input_layernorm.weight": "attn_norm_gamma.params",
-        "post_attention_layernorm.weight": "mlp_norm_gamma.params",
-    }
+    PARAM_MAPPING = {**P.fused_qkv("self_attn.qkv_proj"), **P.attn_out("self_attn.o_proj"),
+                     **P.plain_mlp("mlp.gate_up_proj", "mlp.down_proj"),
+                     **P.norm("input_layernorm", "attn_norm_gamma"), **P.norm("post_attention_layernorm", "mlp_norm_gamma")}
 
 
 class Phi3NonTransformerContainer(LayerContainer):
@@ -28,8 +24,4 @@ class Phi3NonTransformerContainer(LayerContainer):
     word_unembed: UnembedParameter
     final_norm: NormParameter
 
-    PARAM_MAPPING = {
-        "model.embed_tokens.weight": "word_emb.params",
-        "model.norm.weight": "final_norm.params",
-        "lm_head.weight": "word_unembed.params",
-    }
+    PARAM_MAPPING = P.embeddings("model.embed_tokens", "model.norm", "lm_head")

@@ -1,5 +1,6 @@
 """Checkpoint-name mapping for Qwen-1 (fused c_attn with biases, w1/w2 gated MLP) (reference ``model_implementations/qwen/container.py``)."""
 from ..common_parameters import *  # noqa: F401,F403
+from .. import param_maps as P
 from ..layer_container_base import LayerContainer
 
 
@@ -13,16 +14,8 @@ class QwenTransformerContainer(LayerContainer):
     attn_norm_gamma: NormParameter
     mlp_norm_gamma: NormParameter
 
-    PARAM_MAPPING = {
-        "attn.c_attn.weight": "qkv_w.params",
-        "attn.c_attn.bias": "qkv_b.params",
-        "attn.c_proj.weight": "attn_out_w.params",
-        "mlp.w2.weight": "mlp_1_w.gate_params",
-        "mlp.w1.weight": "mlp_1_w.up_params",
-        "mlp.c_proj.weight": "mlp_2_w.params",
-        "ln_1.weight": "attn_norm_gamma.params",
-        "ln_2.weight": "mlp_norm_gamma.params",
-    }
+    PARAM_MAPPING = {**P.fused_qkv("attn.c_attn", bias=True), **P.attn_out("attn.c_proj"), **P.gated_mlp("mlp.w2", "mlp.w1", "mlp.c_proj"),
+                     **P.norm("ln_1", "attn_norm_gamma"), **P.norm("ln_2", "mlp_norm_gamma")}
 
 
 class QwenNonTransformerContainer(LayerContainer):
@@ -31,8 +24,4 @@ class QwenNonTransformerContainer(LayerContainer):
     word_unembed: UnembedParameter
     final_norm: NormParameter
 
-    PARAM_MAPPING = {
-        "transformer.wte.weight": "word_emb.params",
-        "transformer.ln_f.weight": "final_norm.params",
-        "lm_head.weight": "word_unembed.params",
-    }
+    PARAM_MAPPING = P.embeddings("transformer.wte", "transformer.ln_f", "lm_head")

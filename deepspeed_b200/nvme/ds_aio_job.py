@@ -1,12 +1,16 @@
 """Shell job wrapper used by the sweep (reference ``nvme/ds_aio_job.py``)."""
+import contextlib
 import subprocess
+from dataclasses import dataclass
+from typing import List, Optional
 
 
+@dataclass
 class Job:
-
-    def __init__(self, cmd_line, output_file=None, work_dir=None):
-        self.cmd_line, self.output_file, self.work_dir = cmd_line, output_file, work_dir
-        self.output_fd = None
+    cmd_line: List[str]
+    output_file: Optional[str] = None
+    work_dir: Optional[str] = None
+    output_fd = None
 
     def cmd(self):
         return self.cmd_line
@@ -19,8 +23,20 @@ class Job:
     def get_cwd(self):
         return self.work_dir
 
+    @contextlib.contextmanager
+    def redirected(self):
+        """Open the log file for the duration of the run (stdout and stderr share it)."""
+        self.output_fd = open(self.output_file, "w") if self.output_file else None
+        try:
+            yield self.output_fd
+        finally:
+            if self.output_fd is not None:
+                self.output_fd.close()
+                self.output_fd = None
+
+    # reference-style explicit open / close
     def open_output_file(self):
-        if self.output_file is not None:
+        if self.output_file:
             self.output_fd = open(self.output_file, "w")
 
     def close_output_file(self):
@@ -30,13 +46,10 @@ class Job:
 
 
 def run_job(job, verbose=False):
-    args = " ".join(job.cmd())
+    line = " ".join(job.cmd())
     if verbose:
-        print(f"args = {args}")
-    job.open_output_file()
-    try:
-        proc = subprocess.run(args=args, shell=True, stdout=job.get_stdout(), stderr=job.get_stderr(), cwd=job.get_cwd())
-    finally:
-        job.close_output_file()
-    assert proc.returncode == 0, f"'{args}' failed with exit code {proc.returncode}"
-    return proc.returncode
+        print(f"args = {line}")
+    with job.redirected() as fd:
+        rc = subprocess.run(line, shell=True, stdout=fd, stderr=fd, cwd=job.get_cwd()).returncode
+    assert rc == 0, f"'{line}' failed with exit code {rc}"
+    return rc

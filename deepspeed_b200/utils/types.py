@@ -1,20 +1,8 @@
 """Small enums shared by the inference stacks (reference ``utils/types.py``)."""
 from enum import IntEnum
 
+# values are part of the kernel ABI (passed as ints): keep the numbering
+ActivationFuncType = IntEnum("ActivationFuncType", ["UNKNOWN", "GELU", "ReLU", "GATED_GELU", "GATED_SILU"], start=0)
+NormType = IntEnum("NormType", ["UNKNOWN", "LayerNorm", "GroupNorm", "RMSNorm"], start=0)
 
-class ActivationFuncType(IntEnum):
-    UNKNOWN = 0
-    GELU = 1
-    ReLU = 2
-    GATED_GELU = 3
-    GATED_SILU = 4
-
-
-GATED_ACTIVATION_TYPES = [ActivationFuncType.GATED_GELU, ActivationFuncType.GATED_SILU]
-
-
-class NormType(IntEnum):
-    UNKNOWN = 0
-    LayerNorm = 1
-    GroupNorm = 2
-    RMSNorm = 3
+GATED_ACTIVATION_TYPES = [a for a in ActivationFuncType if a.name.startswith("GATED_")]
