@@ -147,3 +147,27 @@ def test_contiguous_memory_allocator_defragments():
     assert float(p.sum()) == 84.0  # still aliases the block
     a.release_tensor(ts[3])
     assert p.numel() == 0 and a.total_free == 16
+
+
+def test_weight_quantization_megatron_state_dict():
+    import torch
+    from deepspeed_b200.runtime.weight_quantizer import WeightQuantization
+    torch.manual_seed(0)
+    sd = {}
+    for l in range(2):
+        sd[f"l{l}.attention.query_key_value.weight"] = torch.randn(96, 32)
+        sd[f"l{l}.attention.dense.weight"] = torch.randn(32, 32)
+        sd[f"l{l}.mlp.dense_h_to_4h.weight"] = torch.randn(128, 32)
+        sd[f"l{l}.mlp.dense_4h_to_h.weight"] = torch.randn(32, 128)
+        sd[f"l{l}.ln.weight"] = torch.randn(32)
+    ref = {k: v.clone() for k, v in sd.items()}
+    wq = WeightQuantization(mlp_extra_grouping=True)
+    out, scales = wq.sd_quantize_megatron(sd, 8, 4)
+    assert out["l0.ln.weight"].dtype == torch.float32 and out["l0.attention.dense.weight"].dtype == torch.int8
+    assert scales.shape == (2, 4, 8)  # layers x [qkv, dense, h4h, 4hh] x widest row (MLP rows use 2x groups)
+    inv = scales[0, 1, :4]  # attention.dense of layer 0: 4 groups
+    deq = (out["l0.attention.dense.weight"].float().reshape(4, -1) * inv[:, None]).reshape(32, 32)
+    assert (deq - ref["l0.attention.dense.weight"]).abs().max() < 0.05
+    halves = wq.merge_scales_split(2)
+    assert len(halves) == 2 and halves[0].shape == (2, 4, 4)
+    assert wq.is_qkv(ref["l0.attention.query_key_value.weight"]) and wq.is_mlp(ref["l0.mlp.dense_h_to_4h.weight"])
