@@ -284,3 +284,45 @@ def test_module_quantize_and_training_inject():
     assert isinstance(new, DeepSpeedTransformerLayer)
     a = model.encoder.layer[0].attention
     assert torch.equal(new.attn_qkvw[:32], a.self.query.weight) and torch.equal(new.output_w, model.encoder.layer[0].output.dense.weight)
+
+
+@pytest.mark.parametrize("family", ["gpt2", "bloom", "gpt_neox", "opt"])
+def test_checkpoint_loading_per_family(family):
+    """load_model_with_checkpoint understands each family's checkpoint layout (Conv1D transposes, per-head fused QKV, ...)."""
+    from deepspeed_b200.module_inject.load_checkpoint import load_model_with_checkpoint
+    torch.manual_seed(0)
+    cfg = AutoConfig.for_model(family, **CAUSAL[family])
+    cfg._attn_implementation = "eager"
+    model = AutoModelForCausalLM.from_config(cfg).eval()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    inj = replace_transformer_layer(None, copy.deepcopy(model), config=_cfg())
+    with torch.no_grad():
+        for m in inj.modules():
+            if isinstance(m, InjectedLayer):
+                for p in m.fused.parameters():
+                    p.normal_()
+    assert load_model_with_checkpoint(inj, sd) >= 2
+    ids = torch.randint(0, 100, (2, 7))
+    with torch.no_grad():
+        assert (inj(ids).logits - model(ids).logits).abs().max() < 3e-4
+
+
+def test_alibi_helpers_and_fused_qkv_layouts():
+    from deepspeed_b200.module_inject.auto_tp_model_utils import build_bloom_alibi_tensor, get_alibi_mask
+    from deepspeed_b200.module_inject.fusedqkv_utils import fused_type_of, prepare_tp_fused_qkvw, require_tp_fused_qkvw
+    from transformers.models.bloom.modeling_bloom import build_alibi_tensor
+    mask = torch.ones(2, 6, dtype=torch.long)
+    mask[1, :2] = 0
+    ours = build_bloom_alibi_tensor(mask, 4, torch.float32)
+    ref = build_alibi_tensor(mask, 4, torch.float32)
+    assert ours.shape == ref.shape and torch.allclose(ours, ref, atol=1e-6)
+    from types import SimpleNamespace
+    m = get_alibi_mask(SimpleNamespace(n_head=4), torch.zeros(1), 5)
+    assert m.shape == (4, 5, 5) and torch.isinf(m[0, 0, 1]) and m[0, 1, 0] < 0 and m[0, 2, 2] == 0
+    assert fused_type_of("BloomBlock") == "bloomtype" and require_tp_fused_qkvw("h.0.self_attention.query_key_value", 2)
+    assert not require_tp_fused_qkvw("h.0.mlp.fc1", 2)
+    # codegen: 4 groups of [q | v | k]; each rank takes its slice of every block of every group
+    w = torch.arange(48.).reshape(48, 1)
+    a, b = (prepare_tp_fused_qkvw("codegentype", w, 2, r).flatten() for r in range(2))
+    assert a.numel() == 24 and sorted(torch.cat([a, b]).tolist()) == list(map(float, range(48)))
+    assert a[:2].tolist() == [0.0, 1.0] and b[:2].tolist() == [2.0, 3.0]
