@@ -168,3 +168,49 @@ def tp_model_init(model, tp_size, dtype, config=None, **kwargs):
     """Shard ``model`` for tensor-parallel *training* (AutoTP).  Reference :369."""
     from .module_inject.auto_tp import tp_model_init as _impl
     return _impl(model, tp_size, dtype, config=config, **kwargs)
+
+
+# ---- reference top-level names ----------------------------------------------------------------------------------------
+from typing import Callable, Iterable, Union  # noqa: E402
+
+import torch as _torch  # noqa: E402
+
+from .constants import TORCH_DISTRIBUTED_DEFAULT_PORT  # noqa: E402,F401
+from .runtime.lr_schedules import add_tuning_arguments  # noqa: E402,F401
+from .runtime.compiler import is_compile_supported  # noqa: E402,F401
+
+ADAM_OPTIMIZER, LAMB_OPTIMIZER = "adam", "lamb"
+DeepSpeedOptimizerCallable = Callable[[Union[Iterable[_torch.nn.Parameter], dict]], _torch.optim.Optimizer]
+DeepSpeedSchedulerCallable = Callable[[_torch.optim.Optimizer], object]
+version = __version__
+
+
+def set_autotp_mode(training=False):
+    """Select whether AutoTP builds training (autograd-aware) or inference tensor-parallel layers."""
+    from .module_inject import layers as _l
+    _l.AUTOTP_TRAINING_MODE = bool(training)
+
+
+def __getattr_compat(name):
+    if name in ("git_hash", "git_branch"):
+        from . import git_version_info as g
+        return getattr(g, name)
+    if name in ("replace_transformer_layer", "revert_transformer_layer"):
+        from .module_inject import replace_module as r
+        return getattr(r, name)
+    if name == "domino":
+        from .runtime import domino as d
+        return d
+    raise AttributeError(name)
+
+
+_orig_getattr = globals().get("__getattr__")
+
+
+def __getattr__(name):  # noqa: F811
+    try:
+        return __getattr_compat(name)
+    except AttributeError:
+        if _orig_getattr is not None:
+            return _orig_getattr(name)
+        raise AttributeError(f"module 'deepspeed_b200' has no attribute {name!r}")

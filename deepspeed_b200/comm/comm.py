@@ -528,3 +528,72 @@ def batch_isend_irecv(p2p_op_list):
 
 
 P2POp = dist.P2POp if dist.is_available() else None
+
+
+# ---- launcher-environment helpers + backend selection (reference ``comm/comm.py``) --------------------------------------
+from datetime import timedelta  # noqa: E402,F401
+
+from deepspeed_b200.constants import TORCH_DISTRIBUTED_DEFAULT_PORT, default_pg_timeout  # noqa: E402,F401
+
+nccl_backend = mpi_backend = ccl_backend = hccl_backend = None  # only the torch backend object (``cdb``) exists here
+mpi_discovery = _mpi_discovery
+
+
+def in_aml():
+    """Azure ML job?"""
+    return "AZUREML_EXPERIMENT_ID" in os.environ
+
+
+def in_aws_sm():
+    """AWS SageMaker job?"""
+    return "SM_TRAINING_ENV" in os.environ
+
+
+def in_dlts():
+    """DLTS cluster job?"""
+    return "DLTS_JOB_ID" in os.environ
+
+
+def patch_aml_env_for_torch_nccl_backend(master_port=6105, verbose=True):
+    """Derive RANK / WORLD_SIZE / MASTER_* from the Azure ML (OpenMPI) environment."""
+    os.environ["RANK"] = os.environ["OMPI_COMM_WORLD_RANK"]
+    os.environ["WORLD_SIZE"] = os.environ["OMPI_COMM_WORLD_SIZE"]
+    if int(os.environ["WORLD_SIZE"]) == int(os.environ.get("OMPI_COMM_WORLD_LOCAL_SIZE", os.environ["WORLD_SIZE"])):
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")  # single node
+    else:
+        os.environ["MASTER_ADDR"] = os.environ["AZ_BATCH_MASTER_NODE"].split(":")[0]
+    os.environ.setdefault("MASTER_PORT", str(master_port))
+    os.environ["LOCAL_RANK"] = os.environ.get("OMPI_COMM_WORLD_LOCAL_RANK", "0")
+    if verbose:
+        logger.info(f"AML env: rank={os.environ['RANK']} world={os.environ['WORLD_SIZE']} master={os.environ['MASTER_ADDR']}:"
+                    f"{os.environ['MASTER_PORT']}")
+
+
+def patch_aws_sm_env_for_torch_nccl_backend(verbose=True):
+    """SageMaker launches through MPI: mirror its rank variables."""
+    os.environ["RANK"] = os.environ["OMPI_COMM_WORLD_RANK"]
+    os.environ["LOCAL_RANK"] = os.environ["OMPI_COMM_WORLD_LOCAL_RANK"]
+    os.environ["WORLD_SIZE"] = os.environ["OMPI_COMM_WORLD_SIZE"]
+    if verbose:
+        logger.info(f"SageMaker env: rank={os.environ['RANK']} world={os.environ['WORLD_SIZE']}")
+
+
+def set_backend():
+    """Bind ``cdb`` to the torch backend object (the only backend of this framework)."""
+    global cdb
+    if cdb is None and dist.is_initialized():
+        from .torch import TorchBackend
+        cdb = TorchBackend(dist.get_backend())
+    return cdb
+
+
+def init_deepspeed_backend(ds_backend=None, timeout=None, init_method=None):
+    """Reference hook for non-torch backends; here every name resolves to the torch process group."""
+    if ds_backend not in (None, "nccl", "gloo"):
+        logger.warning(f"backend {ds_backend} is not available in this build; using the torch process group")
+    return set_backend()
+
+
+def timed_op(func):
+    """Decorator form of the comms-logger instrumentation (reference ``timed_op``)."""
+    return _timed(func.__name__)(func)

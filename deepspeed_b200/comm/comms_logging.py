@@ -137,3 +137,9 @@ class CommsLogger:
                              (f"  straggler {r['straggler_ms']:.3f} ms" if "straggler_ms" in r else ""))
             log_dist("\n".join(lines), ranks=[0])
         return rows
+
+
+def get_caller_func(frame=3):
+    """Name of the function ``frame`` levels up the stack (used to label collectives in debug logs)."""
+    import sys
+    return sys._getframe(frame).f_code.co_name

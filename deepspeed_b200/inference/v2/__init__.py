@@ -3,3 +3,4 @@ from .config_v2 import RaggedInferenceEngineConfig, DeepSpeedTPConfig, DSStateMa
 from .engine_v2 import InferenceEngineV2  # noqa: F401
 from .engine_factory import build_hf_engine, build_engine_from_model  # noqa: F401
 from .scheduling_utils import SchedulingResult, SchedulingError  # noqa: F401
+from .engine_factory import build_engine_from_ds_checkpoint  # noqa: F401,E402

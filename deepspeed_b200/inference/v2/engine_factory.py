@@ -141,3 +141,43 @@ def build_engine_from_ds_checkpoint(path: str, engine_config=None, debug_level=N
                 v = v.to(dev)
             setattr(lw, s, v)
     return InferenceEngineV2(model, engine_config, tp_group=group)
+
+
+def build_engine_from_ds_checkpoint(path: str, engine_config=None, debug_level=None) -> InferenceEngineV2:
+    """Re-create an engine from ``InferenceEngineV2.serialize(path)`` output: the per-rank, already sharded / fused weights
+    are loaded as they are (no checkpoint re-mapping)."""
+    import torch
+    from .model_implementations.arch import ArchSpec
+    from .model_implementations.ragged_transformer import LayerWeights, RaggedTransformer
+    engine_config = _as_cfg(engine_config)
+    from deepspeed_b200 import comm as dist
+    tp = engine_config.tensor_parallel.tp_size
+    rank = dist.get_rank() % tp if (dist.is_initialized() and tp > 1) else 0
+    blob = torch.load(os.path.join(path, f"params_rank_{rank}.pt"), map_location="cpu", weights_only=False)
+    assert blob["tp_size"] == tp, f"checkpoint was serialized for tp_size={blob['tp_size']}, engine config asks for {tp}"
+    spec = ArchSpec(**blob["spec"])
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sample = next(v for v in blob["globals"].values() if torch.is_tensor(v))
+    group = None
+    if tp > 1:
+        from deepspeed_b200.utils import groups
+        if groups.ranks_of("tp") is None:
+            groups._init_tp_mesh_device(tensor_model_parallel_size=tp)
+        group = groups.get_tensor_model_parallel_group()
+    model = RaggedTransformer(spec, group, tp, rank, sample.dtype, dev)
+
+    def put(v):
+        if torch.is_tensor(v):
+            return v.to(dev)
+        if isinstance(v, list):
+            return [put(x) for x in v]
+        if hasattr(v, "q") and hasattr(v, "params"):
+            v.q, v.params = v.q.to(dev), v.params.to(dev)
+        return v
+
+    for k, v in blob["globals"].items():
+        setattr(model, k, put(v))
+    for lw, saved in zip(model.layers, blob["layers"]):
+        for s, v in saved.items():
+            setattr(lw, s, put(v))
+    return InferenceEngineV2(model, engine_config, tp_group=group)

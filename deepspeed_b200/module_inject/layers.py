@@ -208,3 +208,33 @@ def _gather_dim(t, group, dim):
         [dist.broadcast(o if i != dist.get_rank(group) else o.copy_(t), src=dist.get_global_rank(group, i) if group else i,
                         group=group) for i, o in enumerate(outs)]
     return torch.cat(outs, dim=dim)
+
+
+AUTOTP_TRAINING_MODE = False  # set through ``set_autotp_mode``: training builds autograd-aware TP layers
+
+
+class EmbeddingLayer(nn.Module):
+    """Plain embedding holding its weight as a parameter (reference ``module_inject/layers.py:EmbeddingLayer``)."""
+
+    def __init__(self, weight_shape=None, dtype=torch.half, weight=None, bias=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(weight_shape, dtype=dtype) if weight is None else weight)
+
+    def forward(self, input):
+        return F.embedding(input, self.weight)
+
+
+class Normalize(nn.Module):
+    """LayerNorm whose weight / bias can be injected tensors (reference ``module_inject/layers.py:Normalize``)."""
+
+    def __init__(self, dim=None, dtype=torch.float, eps=1e-5, weight=None, bias=None):
+        super().__init__()
+        if weight is not None:
+            self.weight, self.bias = weight, bias
+        else:
+            self.norm = nn.LayerNorm(dim, eps=eps).to(dtype)
+            self.weight, self.bias = self.norm.weight, self.norm.bias
+        self.eps = eps
+
+    def forward(self, input):
+        return F.layer_norm(input, input.shape[-1:], self.weight, self.bias, self.eps)

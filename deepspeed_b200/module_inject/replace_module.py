@@ -141,3 +141,28 @@ def revert_transformer_layer(orig_layer_impl, model, config, preln=False):
             setattr(parent, name, new.to(f.attn_ow.device, f.attn_ow.dtype))
             n += 1
     return model
+
+
+class GroupQuantizer:
+    """Symmetric int8 group quantiser applied to weights as they are sharded into the fused layers (reference
+    ``module_inject/replace_module.py:GroupQuantizer``)."""
+
+    def __init__(self, q_int8=True, group_size=1, num_bits=8, num_groups=0):
+        self.q_int8, self.group_size, self.num_bits, self.num_groups = q_int8, group_size, num_bits, num_groups
+
+    def quantize(self, inputs, qkv=True, count=1, parallel_dim=0):
+        if not self.q_int8 or not qkv:
+            inputs = nn.Parameter(inputs, requires_grad=False)
+            inputs.scale = torch.empty(1)
+            return inputs
+        q_range = 2**self.num_bits
+        groups = self.num_groups if self.num_groups > 0 else max(1, inputs.shape[0] // self.group_size)
+        flat = inputs.detach().float().reshape(groups, -1)
+        bound = torch.maximum(flat.amax(1), flat.amin(1).abs())
+        scale = q_range / (2 * bound + 1e-5)
+        q = (flat * scale[:, None]).round().clamp(-q_range // 2, q_range // 2 - 1).reshape(inputs.shape).to(torch.int8)
+        out = nn.Parameter(q, requires_grad=False)
+        # the fused kernels consume INVERSE scales, one row per tensor-parallel slice of the weight
+        parts = [1.0 / s for s in scale.reshape(count, -1)] if count > 1 else [1.0 / scale]
+        out.scale = torch.cat([p.reshape(1, -1) for p in parts], dim=0).reshape(-1).unsqueeze(0)
+        return out

@@ -132,3 +132,13 @@ def as_plain(obj: Any):
     if isinstance(obj, BaseModel):
         return obj.model_dump()
     return obj
+
+
+class DeepSpeedConfigObject:
+    """Legacy (non-pydantic) config base: JSON repr of the instance dict (reference ``config_utils.py``)."""
+
+    def repr(self):
+        return self.__dict__
+
+    def __repr__(self):
+        return json.dumps(self.__dict__, sort_keys=True, indent=4, cls=ScientificNotationEncoder)

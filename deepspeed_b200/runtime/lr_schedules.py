@@ -314,3 +314,73 @@ def get_config_from_args(args):
         if hasattr(args, k):
             cfg["params"][k] = getattr(args, k)
     return cfg, None
+
+
+# ---- parameter-name constants + CLI override helpers (reference ``lr_schedules.py:22-58, 124-262``) -------------------------
+LR_RANGE_TEST_MIN_LR, LR_RANGE_TEST_STEP_RATE = "lr_range_test_min_lr", "lr_range_test_step_rate"
+LR_RANGE_TEST_STEP_SIZE, LR_RANGE_TEST_STAIRCASE = "lr_range_test_step_size", "lr_range_test_staircase"
+EDGE_VALUE, MID_VALUE = "edge_value", "mid_value"
+CYCLE_FIRST_STEP_SIZE, CYCLE_FIRST_STAIR_COUNT = "cycle_first_step_size", "cycle_first_stair_count"
+CYCLE_SECOND_STEP_SIZE, CYCLE_SECOND_STAIR_COUNT = "cycle_second_step_size", "cycle_second_stair_count"
+DECAY_STEP_SIZE = "decay_step_size"
+CYCLE_MIN_LR, CYCLE_MAX_LR, DECAY_LR_RATE = "cycle_min_lr", "cycle_max_lr", "decay_lr_rate"
+CYCLE_MIN_MOM, CYCLE_MAX_MOM, DECAY_MOM_RATE = "cycle_min_mom", "cycle_max_mom", "decay_mom_rate"
+WARMUP_MIN_LR, WARMUP_MAX_LR, WARMUP_NUM_STEPS, WARMUP_TYPE = "warmup_min_lr", "warmup_max_lr", "warmup_num_steps", "warmup_type"
+WARMUP_MIN_RATIO, COS_MIN_RATIO, TOTAL_NUM_STEPS = "warmup_min_ratio", "cos_min_ratio", "total_num_steps"
+
+_ARG_KEYS = {
+    LR_RANGE_TEST: (LR_RANGE_TEST_MIN_LR, LR_RANGE_TEST_STEP_RATE, LR_RANGE_TEST_STEP_SIZE, LR_RANGE_TEST_STAIRCASE),
+    ONE_CYCLE: (CYCLE_FIRST_STEP_SIZE, CYCLE_FIRST_STAIR_COUNT, CYCLE_SECOND_STEP_SIZE, CYCLE_SECOND_STAIR_COUNT, DECAY_STEP_SIZE,
+                CYCLE_MIN_LR, CYCLE_MAX_LR, DECAY_LR_RATE, CYCLE_MIN_MOM, CYCLE_MAX_MOM, DECAY_MOM_RATE),
+    WARMUP_LR: (WARMUP_MIN_LR, WARMUP_MAX_LR, WARMUP_NUM_STEPS, WARMUP_TYPE),
+}
+
+
+def parse_arguments():
+    """Parse the convergence-tuning flags from ``sys.argv`` (unknown flags are returned separately)."""
+    parser = add_tuning_arguments(argparse.ArgumentParser())
+    return parser.parse_known_args()
+
+
+def _override(args, params, keys):
+    for k in keys:
+        v = getattr(args, k, None)
+        if v is not None:
+            params[k] = v
+
+
+def override_lr_range_test_params(args, params):
+    _override(args, params, _ARG_KEYS[LR_RANGE_TEST])
+
+
+def override_1cycle_params(args, params):
+    _override(args, params, _ARG_KEYS[ONE_CYCLE])
+
+
+def override_warmupLR_params(args, params):
+    _override(args, params, _ARG_KEYS[WARMUP_LR])
+
+
+def override_params(args, params):
+    """Command-line values win over the config file for every schedule family."""
+    for keys in _ARG_KEYS.values():
+        _override(args, params, keys)
+
+
+def get_lr_from_config(config):
+    """-> (peak lr implied by a scheduler config block, error message)."""
+    if "type" not in config:
+        return None, "LR schedule type not defined in config"
+    if "params" not in config:
+        return None, "LR schedule params not defined in config"
+    kind, params = config["type"], config["params"]
+    if kind not in VALID_LR_SCHEDULES:
+        return None, f"{kind} is not a valid LR schedule"
+    key = {LR_RANGE_TEST: LR_RANGE_TEST_MIN_LR, ONE_CYCLE: CYCLE_MAX_LR}.get(kind, WARMUP_MAX_LR)
+    return params[key], ""
+
+
+def update_lr(param_groups, lrs):
+    for group, lr in zip(param_groups, lrs):
+        group["lr"] = lr
+    return [g["lr"] for g in param_groups]

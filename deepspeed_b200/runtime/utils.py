@@ -316,3 +316,180 @@ def required_torch_version(min_version=None, max_version=None):
     if max_version is not None and v > pv.parse(str(max_version)):
         return False
     return True
+
+
+# ---- additional reference helpers (``runtime/utils.py``) ---------------------------------------------------------------
+import contextlib as _contextlib  # noqa: E402
+from math import prod, sqrt  # noqa: E402,F401
+
+noop_context = _contextlib.nullcontext
+
+
+class DummyOptim:
+    """Optimizer stand-in for engines built without one: exposes the parameters as a single group."""
+
+    def __init__(self, params):
+        self.param_groups = [{"params": list(params)}]
+
+
+def move_to_device(item, device, criterion_func=lambda t: True):
+    """Recursively ``.to(device)`` every tensor in a nested list / tuple / dict for which ``criterion_func`` holds."""
+    if torch.is_tensor(item):
+        return item.to(device) if criterion_func(item) else item
+    if isinstance(item, (list, tuple)):
+        return type(item)(move_to_device(v, device, criterion_func) for v in item)
+    if isinstance(item, dict):
+        return {k: move_to_device(v, device, criterion_func) for k, v in item.items()}
+    return item
+
+
+def copy_to_device(item, device, criterion_func=lambda t: True):
+    """As :func:`move_to_device` but always returns new storage (detached clones)."""
+    if torch.is_tensor(item):
+        return item.detach().clone().to(device) if criterion_func(item) else item
+    if isinstance(item, (list, tuple)):
+        return type(item)(copy_to_device(v, device, criterion_func) for v in item)
+    if isinstance(item, dict):
+        return {k: copy_to_device(v, device, criterion_func) for k, v in item.items()}
+    return item
+
+
+def is_moe_param(param) -> bool:
+    return getattr(param, "allreduce", True) is False
+
+
+def get_weight_norm(parameters, norm_type=2, mpu=None):
+    """Norm of the parameter VALUES (not gradients), tensor-parallel aware like :func:`get_grad_norm`."""
+    if torch.is_tensor(parameters):
+        parameters = [parameters]
+    tensors = [p.data for p in parameters]
+    return get_global_norm_of_tensors(tensors, norm_type=norm_type, mpu=mpu)
+
+
+def get_flattened_grad_norm(parameters, norm_type=2, mpu=None, grad_norm_mask=None):
+    """Norm over already-flattened gradient buffers; ``grad_norm_mask[i]`` ([k, 2] index ranges) zeroes the segments of
+    buffer ``i`` that must not be counted twice (tensor-parallel replicas)."""
+    if torch.is_tensor(parameters):
+        parameters = [parameters]
+    grads = []
+    for i, p in enumerate(parameters):
+        if p.grad is None:
+            continue
+        g = p.grad.detach().float().reshape(-1)
+        if grad_norm_mask is not None and len(grad_norm_mask) > i and grad_norm_mask[i] is not None and len(grad_norm_mask[i]):
+            g = g.clone()
+            for lo, hi in torch.as_tensor(grad_norm_mask[i]).reshape(-1, 2).tolist():
+                g[int(lo):int(hi)] = 0
+        grads.append(g)
+    if not grads:
+        return 0.0
+    return get_global_norm_of_tensors(grads, norm_type=norm_type, mpu=mpu)
+
+
+def get_norm_with_moe_layers(non_expert_norm, mpu, expert_tensors, norm_type=2):
+    """Combine the dense-parameter norm with every expert group's norm (each reduced over its expert-parallel group)."""
+    from deepspeed_b200.utils import groups
+    total = float(non_expert_norm)**norm_type if norm_type != float("inf") else float(non_expert_norm)
+    for name, tensors in (expert_tensors or {}).items():
+        if not tensors:
+            continue
+        n = get_global_norm_of_tensors(tensors, norm_type=norm_type, mpu=mpu, moe_ep_group=groups._get_expert_parallel_group(name))
+        total = max(total, float(n)) if norm_type == float("inf") else total + float(n)**norm_type
+    return total if norm_type == float("inf") else total**(1.0 / norm_type)
+
+
+get_norm_with_moe_layers_fast = get_norm_with_moe_layers
+
+
+def get_inactive_params(param_list):
+    """ZeRO-3 parameters whose full tensor is currently not materialised."""
+    from deepspeed_b200.runtime.zero.partition_parameters import is_zero_param
+    return [p for p in param_list if is_zero_param(p) and getattr(p, "ds_status", None) == "NOT_AVAILABLE"]
+
+
+def compare_tensors_in_structures(a, b) -> bool:
+    """Structural + exact equality of nested lists / tuples / dicts of tensors."""
+    if type(a) is not type(b):
+        return False
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(compare_tensors_in_structures(x, y) for x, y in zip(a, b))
+    if isinstance(a, dict):
+        return a.keys() == b.keys() and all(compare_tensors_in_structures(a[k], b[k]) for k in a)
+    if torch.is_tensor(a):
+        return a.shape == b.shape and bool(torch.equal(a, b))
+    return a == b
+
+
+def all_gather_into_tensor_dp_groups(groups_flat, partitioned_param_groups, dp_process_group):
+    """One ``all_gather_into_tensor`` per parameter group (the bucketed variant is :func:`all_gather_dp_groups`)."""
+    from deepspeed_b200 import comm as dist
+    for gi, flat in enumerate(groups_flat):
+        group = dp_process_group[gi] if isinstance(dp_process_group, (list, tuple)) else dp_process_group
+        rank = dist.get_rank(group)
+        dist.all_gather_into_tensor(flat, partitioned_param_groups[gi][rank], group=group)
+
+
+# ---- memory introspection --------------------------------------------------------------------------------------------
+def _mem(fn, default=0):
+    return fn() if torch.cuda.is_available() else default
+
+
+def torch_memory_reserved():
+    return _mem(torch.cuda.memory_reserved)
+
+
+def torch_max_memory_reserved():
+    return _mem(torch.cuda.max_memory_reserved)
+
+
+def mem_alloced():
+    return _mem(torch.cuda.memory_allocated)
+
+
+def mem_cached():
+    return torch_memory_reserved()
+
+
+def empty_cache():
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+
+
+def get_ma_status():
+    from deepspeed_b200 import comm as dist
+    if dist.is_initialized() and dist.get_rank() != 0:
+        return 0
+    return mem_alloced()
+
+
+def memory_status(msg, print_rank=-1, reset_max=False):
+    from deepspeed_b200 import comm as dist
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if print_rank != -1 and rank != print_rank:
+        return
+    gb = 1024**3
+    cur, peak = mem_alloced() / gb, _mem(torch.cuda.max_memory_allocated) / gb
+    res, res_peak = torch_memory_reserved() / gb, torch_max_memory_reserved() / gb
+    if reset_max and torch.cuda.is_available():
+        torch.cuda.reset_peak_memory_stats()
+    print(f"RANK={rank} MEMSTATS {msg} current alloc={cur:0.4f}GB (max={peak:0.4f}GB) current cache={res:0.4f}GB "
+          f"(max={res_peak:0.4f}GB)")
+
+
+# ---- optimizer-state residency for torch optimizers ------------------------------------------------------------------
+def offload_adam_states(optimizer, device, pin_memory=False, non_blocking=False):
+    """Move ``exp_avg`` / ``exp_avg_sq`` of a torch Adam-family optimizer to ``device`` (host pinned if asked)."""
+    for state in optimizer.state.values():
+        for k in ("exp_avg", "exp_avg_sq"):
+            t = state.get(k)
+            if torch.is_tensor(t):
+                dst = torch.empty_like(t, device=device)
+                if pin_memory and torch.device(device).type == "cpu" and torch.cuda.is_available():
+                    dst = dst.pin_memory()
+                dst.copy_(t, non_blocking=non_blocking)
+                state[k] = dst
+
+
+def reload_adam_states(optimizer, device, non_blocking=False):
+    offload_adam_states(optimizer, device, pin_memory=False, non_blocking=non_blocking)

@@ -22,3 +22,32 @@ def __getattr__(name):
         from . import mem_estimator
         return getattr(mem_estimator, name)
     raise AttributeError(name)
+
+
+import contextlib as _contextlib  # noqa: E402
+
+
+@_contextlib.contextmanager
+def unwrap_model_for_generation(model):
+    """Gather every ZeRO-3 parameter of ``model`` for the duration of a ``generate()`` call (no per-layer fetches inside
+    the autoregressive loop), then re-partition."""
+    from .partition_parameters import GatheredParameters, is_zero_param
+    params = [p for p in model.parameters() if is_zero_param(p)]
+    if not params:
+        yield model
+        return
+    zo = None
+    for p in params:
+        ref = getattr(p, "_ds_zero", None)
+        zo = ref() if ref is not None else None
+        if zo is not None:
+            break
+    if zo is not None and hasattr(zo, "gather_all"):
+        zo.gather_all()
+        try:
+            yield model
+        finally:
+            zo.release_all()
+        return
+    with GatheredParameters(params):
+        yield model

@@ -129,3 +129,19 @@ class DeepSpeedZeroConfig(DeepSpeedConfigModel):
         if oo and oo.ratio < 1.0:
             assert self.stage == ZeroStageEnum.weights, "Partial offloading only supported for ZeRO Stage 3."
         return self
+
+
+ZERO_FORMAT = '''"zero_optimization": {"stage": [0|1|2|3], "stage3_max_live_parameters": 1e9, "stage3_max_reuse_distance": 1e9,
+  "stage3_prefetch_bucket_size": 5e8, "stage3_param_persistence_threshold": 1e5, "allgather_bucket_size": 5e8,
+  "reduce_bucket_size": 5e8, "overlap_comm": false, "reduce_scatter": true, "contiguous_gradients": true, "sub_group_size": 1e9,
+  "offload_param": {...}, "offload_optimizer": {...}, "zero_hpz_partition_size": 1, "zero_quantized_weights": false,
+  "zero_quantized_gradients": false, "mics_shard_size": -1, "ignore_unused_parameters": true, "round_robin_gradients": false}'''
+
+
+def read_zero_config_deprecated(param_dict):
+    """``"zero_optimization": true`` (pre-0.3 boolean form) -> stage 1 with the old ``allgather_size`` key honoured."""
+    from deepspeed_b200.runtime.config_utils import get_scalar_param
+    cfg = {"stage": 1 if param_dict.get("zero_optimization") else 0}
+    if cfg["stage"] > 0:
+        cfg["allgather_bucket_size"] = get_scalar_param(param_dict, "allgather_size", 5e8)
+    return cfg

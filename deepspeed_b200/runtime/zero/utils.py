@@ -33,3 +33,52 @@ def get_lst_from_rank0(lst, group=None):
     obj = [list(lst)]
     dist.broadcast_object_list(obj, src=0, group=group)
     return obj[0]
+
+
+# ---- additional reference helpers (``runtime/zero/utils.py``) --------------------------------------------------------
+class ZeRORuntimeException(Exception):
+    pass
+
+
+def _zero_supported():
+    try:
+        return _supported()
+    except Exception:
+        return []
+
+
+ZERO_SUPPORTED_OPTIMIZERS = _zero_supported()
+
+
+def is_builtin_type(obj):
+    return obj.__class__.__module__ in ("__builtin__", "builtins")
+
+
+def isinstance_namedtuple(obj) -> bool:
+    return isinstance(obj, tuple) and hasattr(obj, "_asdict") and hasattr(obj, "_fields")
+
+
+def apply_to_tensors_only(function, value, warning_msg_fn=None):
+    """Apply ``function`` to every tensor inside nested lists / tuples / namedtuples / dicts, keep everything else."""
+    import torch
+    if isinstance_namedtuple(value):
+        return value.__class__(*(apply_to_tensors_only(function, v, warning_msg_fn) for v in value))
+    if isinstance(value, (tuple, list)):
+        return value.__class__(apply_to_tensors_only(function, v, warning_msg_fn) for v in value)
+    if isinstance(value, dict):
+        return {k: apply_to_tensors_only(function, v, warning_msg_fn) for k, v in value.items()}
+    if isinstance(value, torch.Tensor):
+        return function(value)
+    if warning_msg_fn is not None and not is_builtin_type(value):
+        from deepspeed_b200.utils import logger
+        logger.warning(warning_msg_fn(value))
+    return value
+
+
+def get_mapping_to_flat_buffer(tensors):
+    """[(tensor, offset, numel)] of ``tensors`` laid out back to back in one flat buffer."""
+    out, offset = [], 0
+    for t in tensors:
+        out.append((t, offset, t.numel()))
+        offset += t.numel()
+    return out

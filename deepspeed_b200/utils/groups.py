@@ -426,3 +426,55 @@ def _init_tp_mesh_device(tensor_model_parallel_size=1, data_parallel_size=None):
 
 def ranks_of(name: str):
     return _ranks.get(name)
+
+
+# ---- public accessors + explicit TP overrides (reference ``utils/groups.py``) ------------------------------------------
+_tp_rank_override = None
+_tp_world_override = None
+
+
+def get_data_parallel_group():
+    return _get_data_parallel_group()
+
+
+def get_data_parallel_world_size():
+    return _get_data_parallel_world_size()
+
+
+def get_data_parallel_rank():
+    return _get_data_parallel_rank()
+
+
+def get_model_parallel_group():
+    return _get_model_parallel_group()
+
+
+def get_model_parallel_world_size():
+    return _tp_world_override if _tp_world_override is not None else _get_model_parallel_world_size()
+
+
+def get_model_parallel_rank():
+    return _tp_rank_override if _tp_rank_override is not None else _get_model_parallel_rank()
+
+
+def set_tensor_model_parallel_world_size(world_size):
+    global _tp_world_override
+    _tp_world_override = world_size
+
+
+def set_tensor_model_parallel_rank(rank):
+    global _tp_rank_override
+    _tp_rank_override = rank
+
+
+def get_tensor_model_parallel_src_rank():
+    """Global rank of the first member of this rank's tensor-parallel group."""
+    from deepspeed_b200 import comm as dist
+    tp = get_model_parallel_world_size()
+    return (dist.get_rank() // tp) * tp if dist.is_initialized() else 0
+
+
+def __getattr__(name):
+    if name == "mpu":
+        return _mpu
+    raise AttributeError(name)

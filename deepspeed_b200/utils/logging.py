@@ -110,3 +110,27 @@ def set_log_level(level):
     if isinstance(level, str):
         level = get_log_level_from_string(level)
     logger.setLevel(level)
+
+
+log_levels = {"debug": logging.DEBUG, "info": logging.INFO, "warning": logging.WARNING, "error": logging.ERROR,
+              "critical": logging.CRITICAL}
+
+
+def get_current_level():
+    return logger.getEffectiveLevel()
+
+
+def should_log_le(max_log_level_str):
+    """Is the current level at most ``max_log_level_str`` (i.e. would a message of that level be shown)?"""
+    if not isinstance(max_log_level_str, str):
+        raise ValueError(f"{max_log_level_str} is not a string")
+    key = max_log_level_str.lower()
+    if key not in log_levels:
+        raise ValueError(f"{max_log_level_str} is not one of the `logging` levels")
+    return get_current_level() <= log_levels[key]
+
+
+def print_configuration(args, name):
+    logger.info(f"{name}:")
+    for arg in sorted(vars(args)):
+        logger.info(f"  {arg} {'.' * max(1, 29 - len(arg))} {getattr(args, arg)}")

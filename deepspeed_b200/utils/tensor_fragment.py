@@ -140,3 +140,68 @@ def get_hp_fragment_mapping(lp_param, lp_start=None, flat_hp_partition=None, gra
         return []
     rt, slot = zo.unit_of_param[id(lp_param)], zo.slot_of_param[id(lp_param)]
     return [(p0, a0, ln) for (r, p0, a0, ln) in param_fragments(rt.u, slot, zo.shard_world) if r == zo.shard_rank]
+
+
+# ---- reference data types (``utils/tensor_fragment.py:13-40``) -----------------------------------------------------------
+from dataclasses import dataclass as _dataclass  # noqa: E402
+from typing import Dict as _Dict  # noqa: E402
+
+
+@_dataclass
+class fragment_address:
+    numel: int
+    start: int
+
+
+@_dataclass
+class tensor_fragment:
+    """One contiguous piece of a low-precision parameter inside this rank's flat high-precision partition."""
+    lp_fragment: torch.Tensor
+    lp_fragment_address: fragment_address
+    hp_fragment: torch.Tensor
+    hp_fragment_address: fragment_address
+    gradient_dict: _Dict = None
+    offload_gradient_dict: _Dict = None
+    use_offload: bool = False
+    param_group_index: int = 0
+    optim_fragment: _Dict = None
+
+    def update_hp(self):
+        self.hp_fragment.data.copy_(self.lp_fragment.data)
+
+    def update_lp(self):
+        self.lp_fragment.data.copy_(self.hp_fragment.data)
+
+    def get_optim_state_fragment(self, key):
+        if self.optim_fragment is None or key not in self.optim_fragment:
+            raise ValueError(f"{key} not found in optimizer state fragment")
+        return self.optim_fragment[key]
+
+    def set_optim_state_fragment(self, flat_hp_partition, optim_fragment):
+        a = self.hp_fragment_address
+        self.optim_fragment = {k: v.narrow(0, a.start, a.numel) for k, v in optim_fragment.items()
+                               if torch.is_tensor(v) and v.dim() > 0 and v.numel() == flat_hp_partition.numel()}
+
+    def get_hp_fragment_address(self):
+        return self.hp_fragment_address
+
+    def get_optim_state_keys(self):
+        return list((self.optim_fragment or {}).keys())
+
+    def get_hp_fragment(self, optim_state_key=None):
+        return self.hp_fragment if optim_state_key is None else self.get_optim_state_fragment(optim_state_key)
+
+
+def map_to_flat_opt_states(flat_hp_tensor, lp_tensors, optim_state, opt_keys):
+    """Build flat optimizer-state buffers shaped like ``flat_hp_tensor`` out of the per-parameter states of
+    ``lp_tensors`` (used when a torch optimizer's state must follow a flattened master copy)."""
+    for key in opt_keys:
+        buf = torch.zeros_like(flat_hp_tensor)
+        offset = 0
+        for lp in lp_tensors:
+            st = optim_state.get(lp, {})
+            if key in st and torch.is_tensor(st[key]) and st[key].numel() == lp.numel():
+                buf.narrow(0, offset, lp.numel()).copy_(st[key].reshape(-1))
+                st[key] = buf.narrow(0, offset, lp.numel()).view_as(lp)
+            offset += lp.numel()
+        optim_state.setdefault(flat_hp_tensor, {})[key] = buf

@@ -260,3 +260,10 @@ def trim_mean(data, trim_percent):
     k = int(round(n * trim_percent))
     kept = data[k:n - k] or data
     return sum(kept) / len(kept)
+
+
+CudaEventTimer = _EventTimer  # reference name
+
+
+def mean(values):
+    return sum(values) / len(values) if values else 0.0

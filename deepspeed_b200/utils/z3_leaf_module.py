@@ -42,3 +42,10 @@ def set_z3_leaf_modules(model, leaf_module_classes: List[Type]):
 
 def unset_z3_leaf_modules(model, leaf_module_classes: List[Type]):
     return _mark(model, leaf_module_classes, False)
+
+
+def set_z3_leaf_module(model: torch.nn.Module, flag: bool):
+    """Mark / unmark one module as a ZeRO-3 leaf (its children are gathered together with it)."""
+    model._z3_leaf = bool(flag)
+    for p in model.parameters():
+        p._z3_leaf_param = bool(flag)

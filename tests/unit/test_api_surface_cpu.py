@@ -1,0 +1,128 @@
+"""Reference API names that user code imports directly: presence + behaviour of the small helpers."""
+import argparse
+
+import pytest
+import torch
+
+from tests.common import run_distributed
+
+
+def test_top_level_and_lr_cli_helpers():
+    import deepspeed_b200 as ds
+    from deepspeed_b200.runtime import lr_schedules as L
+    assert ds.version == ds.__version__ and ds.ADAM_OPTIMIZER == "adam" and callable(ds.replace_transformer_layer)
+    assert ds.git_hash and ds.TORCH_DISTRIBUTED_DEFAULT_PORT == 29500 and ds.domino.__name__.endswith("domino")
+    p = ds.add_tuning_arguments(argparse.ArgumentParser())
+    args = p.parse_args(["--lr_schedule", "OneCycle", "--cycle_max_lr", "0.5"])
+    cfg, err = L.get_config_from_args(args)
+    assert err is None and cfg["type"] == "OneCycle"
+    assert L.get_lr_from_config(cfg) == (0.5, "")
+    assert L.get_lr_from_config({"type": "nope", "params": {}})[0] is None
+    params = {}
+    L.override_params(args, params)
+    assert params[L.CYCLE_MAX_LR] == 0.5 and L.WARMUP_NUM_STEPS in params
+    groups = [{"lr": 0.0}, {"lr": 0.0}]
+    assert L.update_lr(groups, [0.1, 0.2]) == [0.1, 0.2]
+
+
+def test_runtime_utils_helpers():
+    from deepspeed_b200.runtime.utils import (DummyOptim, compare_tensors_in_structures, copy_to_device, get_flattened_grad_norm,
+                                              get_weight_norm, is_moe_param, move_to_device, noop_context, offload_adam_states)
+    from deepspeed_b200.runtime.zero.utils import apply_to_tensors_only, get_mapping_to_flat_buffer, isinstance_namedtuple
+    w = torch.nn.Parameter(torch.tensor([3.0, 4.0]))
+    assert DummyOptim([w]).param_groups[0]["params"][0] is w
+    nested = {"a": [torch.ones(2), (torch.zeros(1), 5)], "b": "x"}
+    moved = move_to_device(nested, "cpu")
+    assert compare_tensors_in_structures(nested, moved) and moved["a"][1][1] == 5
+    cp = copy_to_device(nested, "cpu")
+    assert cp["a"][0] is not nested["a"][0] and compare_tensors_in_structures(cp, nested)
+    assert not compare_tensors_in_structures(nested, {"a": [torch.ones(2)], "b": "x"})
+    assert abs(float(get_weight_norm([w])) - 5.0) < 1e-6
+    w.grad = torch.tensor([1.0, 2.0])
+    assert abs(float(get_flattened_grad_norm([w], grad_norm_mask=[torch.tensor([[0, 1]])])) - 2.0) < 1e-6
+    assert not is_moe_param(w)
+    with noop_context():
+        pass
+    opt = torch.optim.Adam([w], lr=0.1)
+    opt.step()
+    offload_adam_states(opt, "cpu")
+    assert opt.state[w]["exp_avg"].device.type == "cpu"
+    from collections import namedtuple
+    NT = namedtuple("NT", "x y")
+    out = apply_to_tensors_only(lambda t: t + 1, NT(torch.zeros(1), [torch.ones(1), 7]))
+    assert isinstance_namedtuple(out) and float(out.x) == 1.0 and float(out.y[0]) == 2.0 and out.y[1] == 7
+    m = get_mapping_to_flat_buffer([torch.zeros(3), torch.zeros(2, 2)])
+    assert [(o, n) for _, o, n in m] == [(0, 3), (3, 4)]
+
+
+def test_logging_timer_group_and_fragment_names():
+    from deepspeed_b200.checkpoint import SubparamShape
+    from deepspeed_b200.module_inject import EmbeddingLayer, GroupQuantizer, Normalize
+    from deepspeed_b200.runtime.config_utils import DeepSpeedConfigObject
+    from deepspeed_b200.runtime.zero.config import read_zero_config_deprecated
+    from deepspeed_b200.utils import groups, tensor_fragment
+    from deepspeed_b200.utils.logging import get_current_level, should_log_le
+    from deepspeed_b200.utils.tensor_fragment import fragment_address, map_to_flat_opt_states
+    from deepspeed_b200.utils.timer import CudaEventTimer, mean
+    assert should_log_le("critical") and get_current_level() >= 0 and mean([1, 3]) == 2 and CudaEventTimer is not None
+    with pytest.raises(ValueError):
+        should_log_le("loud")
+    assert read_zero_config_deprecated({"zero_optimization": True, "allgather_size": 7}) == {"stage": 1, "allgather_bucket_size": 7}
+    assert groups.get_model_parallel_world_size() == 1 and groups.get_tensor_model_parallel_src_rank() == 0
+    groups.set_tensor_model_parallel_world_size(4)
+    groups.set_tensor_model_parallel_rank(3)
+    assert (groups.get_model_parallel_world_size(), groups.get_model_parallel_rank()) == (4, 3)
+    groups.set_tensor_model_parallel_world_size(None)
+    groups.set_tensor_model_parallel_rank(None)
+    lp, hp = torch.zeros(4), torch.arange(10.)
+    frag = tensor_fragment(lp_fragment=lp, lp_fragment_address=fragment_address(4, 0), hp_fragment=hp.narrow(0, 2, 4),
+                           hp_fragment_address=fragment_address(4, 2))
+    frag.update_lp()
+    assert lp.tolist() == [2.0, 3.0, 4.0, 5.0]
+    frag.set_optim_state_fragment(hp, {"exp_avg": torch.arange(10.) * 2, "step": torch.tensor(3)})
+    assert frag.get_optim_state_fragment("exp_avg").tolist() == [4.0, 6.0, 8.0, 10.0] and frag.get_optim_state_keys() == ["exp_avg"]
+    a, b = torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(3))
+    state = {a: {"exp_avg": torch.ones(2)}, b: {"exp_avg": torch.full((3, ), 2.0)}}
+    flat = torch.zeros(5)
+    map_to_flat_opt_states(flat, [a, b], state, ["exp_avg"])
+    assert state[flat]["exp_avg"].tolist() == [1, 1, 2, 2, 2] and state[b]["exp_avg"].data_ptr() == state[flat]["exp_avg"][2:].data_ptr()
+    emb = EmbeddingLayer(weight=torch.nn.Parameter(torch.eye(4)))
+    assert torch.equal(emb(torch.tensor([2])), torch.eye(4)[2:3])
+    n = Normalize(dim=4, dtype=torch.float32)
+    assert n(torch.randn(2, 4)).shape == (2, 4)
+    q = GroupQuantizer(q_int8=True, group_size=4).quantize(torch.randn(16, 8))
+    assert q.dtype == torch.int8 and q.scale.shape == (1, 4)
+    assert SubparamShape(["a"], (4, 2), 0).partition_dim == 0
+
+    class C(DeepSpeedConfigObject):
+
+        def __init__(self):
+            self.x = 1
+
+    assert '"x": 1' in repr(C())
+
+
+def _ds_ckpt_roundtrip(tmp):
+    pytest.importorskip("transformers")
+    from transformers import AutoConfig, AutoModelForCausalLM
+    from deepspeed_b200.inference.v2 import build_engine_from_ds_checkpoint, build_hf_engine
+    from deepspeed_b200.runtime.zero import unwrap_model_for_generation
+    cfg = AutoConfig.for_model("llama", vocab_size=64, hidden_size=32, num_hidden_layers=1, num_attention_heads=4, num_key_value_heads=2,
+                               intermediate_size=64, max_position_embeddings=64)
+    torch.manual_seed(0)
+    hf = AutoModelForCausalLM.from_config(cfg).eval()
+    sm = {"state_manager": {"max_context": 64, "max_ragged_batch_size": 64, "max_ragged_sequence_count": 4,
+                            "memory_config": {"mode": "allocate", "size": 8}}}
+    eng = build_hf_engine(hf, sm, dtype=torch.float32, device="cpu")
+    prompt = torch.randint(0, 64, (9, ))
+    ref = eng.put([0], [prompt])[0]
+    eng.serialize(tmp)
+    eng2 = build_engine_from_ds_checkpoint(tmp, sm)
+    out = eng2.put([0], [prompt])[0]
+    assert torch.allclose(ref, out, atol=1e-6)
+    with unwrap_model_for_generation(hf) as m:  # no ZeRO params: plain pass-through
+        assert m is hf
+
+
+def test_serialized_engine_roundtrip(tmp_path):
+    run_distributed(_ds_ckpt_roundtrip, 1, (str(tmp_path), ))
