@@ -14,4 +14,4 @@ The method names follow the reference ABC so user code written against
 from .real_accelerator import get_accelerator, set_accelerator, is_current_accelerator_supported  # noqa: F401
 from .b200_accelerator import B200Accelerator  # noqa: F401
 from .host_accelerator import HostAccelerator  # noqa: F401
-from .base import _NullStream as DeepSpeedAccelerator  # noqa: F401,E402  (reference ABC name)
+from .base import AcceleratorBase as DeepSpeedAccelerator  # noqa: F401,E402  (reference ABC name)
