@@ -389,3 +389,107 @@ def configure(mpu_, deepspeed_config=None, partition_activations=None, contiguou
 
 def is_configured():
     return _configured
+
+
+# =====================================================================================================
+# functional helpers under the reference's names (``checkpointing.py:143-460``); the checkpoint function above does
+# the same work through ``_Saved`` objects
+# =====================================================================================================
+def detach_variable(inputs, device=None):
+    """Detached copies (optionally moved) that keep ``requires_grad``; non-tensors pass through."""
+    if not isinstance(inputs, tuple):
+        raise RuntimeError(f"Only tuple of tensors is supported. Got Unsupported input type: {type(inputs).__name__}")
+    out = []
+    for inp in inputs:
+        if not torch.is_tensor(inp):
+            out.append(inp)
+            continue
+        x = inp.detach() if device is None else inp.to(device=device).detach()
+        x.requires_grad = inp.requires_grad
+        out.append(x)
+    return tuple(out)
+
+
+def extract_tensors(all_objects):
+    """Split a tuple / list into (tensors, non-tensors, flags); ``merge_tensors`` is the inverse."""
+    flags = [torch.is_tensor(v) for v in all_objects]
+    tensors = [v for v, f in zip(all_objects, flags) if f]
+    others = [v for v, f in zip(all_objects, flags) if not f]
+    if isinstance(all_objects, tuple):
+        return tuple(tensors), tuple(others), tuple(flags)
+    return tensors, others, flags
+
+
+def merge_tensors(tensor_objects, non_tensor_objects, tensor_flags):
+    t, o = iter(tensor_objects), iter(non_tensor_objects)
+    return tuple(next(t) if f else next(o) for f in tensor_flags)
+
+
+def is_activation_to_checkpoint(item):
+    """Only floating-point tensors large enough to split across the tensor-parallel group are partitioned."""
+    _, size, _ = _tp()
+    return torch.is_tensor(item) and item.is_floating_point() and item.numel() >= size
+
+
+def partition_activations(args, cpu_checkpoint=False, contiguous_checkpoint=False):
+    """This rank's slice of every checkpointable tensor in ``args`` (others unchanged)."""
+    out = []
+    for i, item in enumerate(args):
+        if not is_activation_to_checkpoint(item):
+            out.append(item)
+            continue
+        psz, start = get_partition_size(item), get_partition_start(item)
+        flat = item.detach().contiguous().view(-1)
+        piece = flat[start:start + psz]
+        if piece.numel() < psz:
+            piece = torch.cat([piece, piece.new_zeros(psz - piece.numel())])
+        if contiguous_checkpoint:
+            buf = _contiguous_buffer(("partition", i), psz, item.dtype, torch.device("cpu") if cpu_checkpoint else item.device)
+            buf[:psz].copy_(piece)
+            piece = buf[:psz]
+        elif cpu_checkpoint:
+            piece = piece.to("cpu")
+        else:
+            piece = piece.clone()
+        out.append(piece)
+    return out
+
+
+def get_partitioned_activations_for_backward(args, inputs, contiguous_checkpoint=False):
+    """Interleave each partition with the shape tensor needed to rebuild it: [part0, size0, part1, size1, ...]."""
+    new_args = []
+    for i, (arg, inp) in enumerate(zip(args, inputs)):
+        if not is_activation_to_checkpoint(inp):
+            new_args.append(arg)
+            new_args.append(None)
+            continue
+        new_args.append(arg)
+        new_args.append(torch.tensor(inp.size(), dtype=torch.int64))
+    return new_args
+
+
+def get_cpu_activations_for_backward(args, inputs):
+    new_args = []
+    for arg, inp in zip(args, inputs):
+        new_args.append(arg if not is_activation_to_checkpoint(inp) else arg.to("cpu"))
+    return new_args
+
+
+def gather_partitioned_activations(tensors, device=None):
+    """Inverse of :func:`get_partitioned_activations_for_backward`: all-gather every (partition, size) pair."""
+    assert len(tensors) % 2 == 0, f"Expected even count of tensors, instead got {len(tensors)}"
+    _, size, group = _tp()
+    out = []
+    for part, shape in zip(tensors[0::2], tensors[1::2]):
+        if shape is None or not torch.is_tensor(part):
+            out.append(part)
+            continue
+        numel = int(torch.as_tensor(shape).prod())
+        x = part.to(device) if device is not None else part
+        if size == 1:
+            out.append(x[:numel].view(*[int(s) for s in shape]))
+            continue
+        full = torch.empty(x.numel() * size, dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(full, x.contiguous(), group=group)
+        out.append(full[:numel].view(*[int(s) for s in shape]))
+    return out

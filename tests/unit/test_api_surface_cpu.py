@@ -126,3 +126,21 @@ def _ds_ckpt_roundtrip(tmp):
 
 def test_serialized_engine_roundtrip(tmp_path):
     run_distributed(_ds_ckpt_roundtrip, 1, (str(tmp_path), ))
+
+
+def test_activation_checkpoint_functional_helpers():
+    from deepspeed_b200.runtime.activation_checkpointing import checkpointing as C
+    x = torch.randn(3, 4, requires_grad=True)
+    d = C.detach_variable((x, 5))
+    assert d[0].requires_grad and d[0].grad_fn is None and d[1] == 5
+    t, o, f = C.extract_tensors((x, "a", torch.ones(1), 3))
+    assert len(t) == 2 and o == ("a", 3) and f == (True, False, True, False)
+    merged = C.merge_tensors(t, o, f)
+    assert merged[1] == "a" and merged[2] is t[1]
+    parts = C.partition_activations([x, 7])
+    assert parts[1] == 7 and parts[0].numel() == 12  # tp = 1: the "partition" is the whole tensor
+    packed = C.get_partitioned_activations_for_backward(parts, [x, 7])
+    back = C.gather_partitioned_activations(packed)
+    assert torch.equal(back[0], x.detach()) and back[1] == 7
+    with pytest.raises(RuntimeError):
+        C.detach_variable([x])
