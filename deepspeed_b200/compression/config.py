@@ -56,3 +56,45 @@ def get_compression_config(param_dict):
     lr.setdefault(C.LAYER_REDUCTION_ENABLED, False)
     out[C.LAYER_REDUCTION] = lr
     return out
+
+
+# ---- per-technique accessors (reference ``compression/config.py:get_*``) -------------------------------------------------
+def _accessors():
+    names = {"weight_quantization": C.WEIGHT_QUANTIZATION, "activation_quantization": C.ACTIVATION_QUANTIZATION,
+             "sparse_pruning": C.SPARSE_PRUNING, "row_pruning": C.ROW_PRUNING, "head_pruning": C.HEAD_PRUNING,
+             "channel_pruning": C.CHANNEL_PRUNING}
+    out = {}
+    for short, key in names.items():
+        out[f"get_{short}"] = (lambda k: lambda param_dict: _technique(param_dict, k))(key)
+        out[f"get_{short}_shared_parameters"] = (lambda k: lambda param_dict: _technique({k: param_dict}, k)[C.SHARED_PARAMETERS])(key)
+        out[f"get_{short}_different_groups"] = (lambda k: lambda param_dict: _technique({k: param_dict}, k)[C.DIFFERENT_GROUPS])(key)
+    for n, f in out.items():
+        f.__name__ = n
+        f.__doc__ = "``param_dict``: the ``compression_training`` block (``get_<t>``) or the technique's own block (the two others)."
+    return out
+
+
+globals().update(_accessors())
+
+
+def get_layer_reduction(param_dict):
+    """``param_dict``: the ``compression_training`` block -> the layer-reduction section with ``enabled`` defaulted."""
+    lr = copy.deepcopy(param_dict.get(C.LAYER_REDUCTION, {}))
+    lr.setdefault(C.LAYER_REDUCTION_ENABLED, False)
+    return lr
+
+
+def get_layer_reduction_enabled(param_dict):
+    return bool(param_dict.get(C.LAYER_REDUCTION, {}).get(C.LAYER_REDUCTION_ENABLED, False))
+
+
+def get_layer_reduction_params(param_dict):
+    lr = copy.deepcopy(param_dict.get(C.LAYER_REDUCTION, {}))
+    lr.pop(C.LAYER_REDUCTION_ENABLED, None)
+    return lr or False
+
+
+def get_quantize_enabled(param_dict):
+    """Is weight quantisation switched on in the ``compression_training`` block?"""
+    return bool(param_dict.get(C.COMPRESSION_TRAINING, param_dict).get(C.WEIGHT_QUANTIZATION, {}).get(C.SHARED_PARAMETERS, {}).get(
+        C.TECHNIQUE_ENABLED, False))

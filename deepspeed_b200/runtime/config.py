@@ -589,3 +589,278 @@ def _dtype_from_str(s):
     if s not in table:
         raise ValueError(f"Invalid communication_data_type. Supported data types: {sorted(table)}. Got: {s}")
     return table[s]
+
+
+# =====================================================================================================================
+# Functional accessors over the raw config dict (reference ``runtime/config.py:get_*``).  The engine reads the typed
+# ``DeepSpeedConfig`` above; these exist for tools / user code written against the functional API.
+# =====================================================================================================================
+import copy as _copy  # noqa: E402
+
+from deepspeed_b200.runtime import constants as K  # noqa: E402
+from deepspeed_b200.runtime.config_utils import get_scalar_param  # noqa: E402,F401
+from deepspeed_b200.inference.v2.inference_utils import DtypeEnum  # noqa: E402,F401
+
+
+def _section_flag(section, key, default):
+    return lambda param_dict: get_scalar_param(param_dict[section], key, default) if section in param_dict else False
+
+
+def _section_rest(section, drop):
+    def f(param_dict):
+        if section not in param_dict:
+            return False
+        d = _copy.copy(param_dict[section])
+        d.pop(drop, None)
+        return d
+    return f
+
+
+def _top(key, default):
+    return lambda param_dict: get_scalar_param(param_dict, key, default)
+
+
+def _bf16_section(param_dict):
+    return next((param_dict[k] for k in (K.BFLOAT16, K.BFLOAT16_OLD) if k in param_dict), None)
+
+
+get_pld_enabled = _section_flag(K.PROGRESSIVE_LAYER_DROP, K.PLD_ENABLED, K.PLD_ENABLED_DEFAULT)
+get_pld_params = _section_rest(K.PROGRESSIVE_LAYER_DROP, K.PLD_ENABLED)
+get_amp_enabled = _section_flag(K.AMP, K.AMP_ENABLED, K.AMP_ENABLED_DEFAULT)
+get_amp_params = _section_rest(K.AMP, K.AMP_ENABLED)
+get_fp16_enabled = _section_flag(K.FP16, K.FP16_ENABLED, K.FP16_ENABLED_DEFAULT)
+
+
+def get_bfloat16_enabled(param_dict):
+    sec = _bf16_section(param_dict)
+    return get_scalar_param(sec, K.BFLOAT16_ENABLED, K.BFLOAT16_ENABLED_DEFAULT) if sec is not None else False
+
+
+def get_bfloat16_immediate_grad_update(param_dict):
+    sec = _bf16_section(param_dict)
+    return get_scalar_param(sec, K.BFLOAT16_IMMEDIATE_GRAD_UPDATE, K.BFLOAT16_IMMEDIATE_GRAD_UPDATE_DEFAULT) if sec is not None else False
+
+
+def _fp16_field(key, default, off=False):
+    return lambda param_dict: get_scalar_param(param_dict[K.FP16], key, default) if get_fp16_enabled(param_dict) else off
+
+
+get_fp16_master_weights_and_grads_enabled = _fp16_field(K.FP16_MASTER_WEIGHTS_AND_GRADS, K.FP16_MASTER_WEIGHTS_AND_GRADS_DEFAULT)
+get_fp16_auto_cast = _fp16_field(K.FP16_AUTO_CAST, K.FP16_AUTO_CAST_DEFAULT, off=None)
+
+
+def get_loss_scale(param_dict):
+    if get_fp16_enabled(param_dict):
+        return get_scalar_param(param_dict[K.FP16], K.FP16_LOSS_SCALE, K.FP16_LOSS_SCALE_DEFAULT)
+    return 1.0 if get_bfloat16_enabled(param_dict) else K.FP16_LOSS_SCALE_DEFAULT
+
+
+def get_initial_dynamic_scale(param_dict):
+    if get_fp16_enabled(param_dict):
+        power = get_scalar_param(param_dict[K.FP16], K.FP16_INITIAL_SCALE_POWER, K.FP16_INITIAL_SCALE_POWER_DEFAULT)
+    else:
+        power = 0 if get_bfloat16_enabled(param_dict) else K.FP16_INITIAL_SCALE_POWER_DEFAULT
+    return 2**power
+
+
+def get_dynamic_loss_scale_args(param_dict):
+    """Keyword arguments of the dynamic loss scaler, or None when none of its knobs is set."""
+    if not get_fp16_enabled(param_dict):
+        return None
+    fp16 = param_dict[K.FP16]
+    knobs = (K.FP16_INITIAL_SCALE_POWER, K.FP16_LOSS_SCALE_WINDOW, K.FP16_MIN_LOSS_SCALE, K.FP16_HYSTERESIS, K.FP16_CONSECUTIVE_HYSTERESIS)
+    if not any(k in fp16 for k in knobs):
+        return None
+    return {"init_scale": 2**get_scalar_param(fp16, K.FP16_INITIAL_SCALE_POWER, K.FP16_INITIAL_SCALE_POWER_DEFAULT),
+            "scale_window": get_scalar_param(fp16, K.FP16_LOSS_SCALE_WINDOW, K.FP16_LOSS_SCALE_WINDOW_DEFAULT),
+            "delayed_shift": get_scalar_param(fp16, K.FP16_HYSTERESIS, K.FP16_HYSTERESIS_DEFAULT),
+            "consecutive_hysteresis": get_scalar_param(fp16, K.FP16_CONSECUTIVE_HYSTERESIS, K.FP16_CONSECUTIVE_HYSTERESIS_DEFAULT),
+            "min_scale": get_scalar_param(fp16, K.FP16_MIN_LOSS_SCALE, K.FP16_MIN_LOSS_SCALE_DEFAULT)}
+
+
+get_gradient_accumulation_steps = _top(K.GRADIENT_ACCUMULATION_STEPS, K.GRADIENT_ACCUMULATION_STEPS_DEFAULT)
+get_sparse_gradients_enabled = _top(K.SPARSE_GRADIENTS, K.SPARSE_GRADIENTS_DEFAULT)
+get_prescale_gradients = _top(K.PRESCALE_GRADIENTS, K.PRESCALE_GRADIENTS_DEFAULT)
+get_gradient_predivide_factor = _top(K.GRADIENT_PREDIVIDE_FACTOR, K.GRADIENT_PREDIVIDE_FACTOR_DEFAULT)
+get_steps_per_print = _top(K.STEPS_PER_PRINT, K.STEPS_PER_PRINT_DEFAULT)
+get_disable_allgather = _top(K.DISABLE_ALLGATHER, K.DISABLE_ALLGATHER_DEFAULT)
+get_dump_state = _top(K.DUMP_STATE, K.DUMP_STATE_DEFAULT)
+get_gradient_clipping = _top(K.GRADIENT_CLIPPING, K.GRADIENT_CLIPPING_DEFAULT)
+get_graph_harvesting = _top(K.GRAPH_HARVESTING, K.GRAPH_HARVESTING_DEFAULT)
+get_train_batch_size = _top(K.TRAIN_BATCH_SIZE, K.TRAIN_BATCH_SIZE_DEFAULT)
+get_train_micro_batch_size_per_gpu = _top(K.TRAIN_MICRO_BATCH_SIZE_PER_GPU, K.TRAIN_MICRO_BATCH_SIZE_PER_GPU_DEFAULT)
+get_wall_clock_breakdown = _top(K.WALL_CLOCK_BREAKDOWN, K.WALL_CLOCK_BREAKDOWN_DEFAULT)
+get_memory_breakdown = _top(K.MEMORY_BREAKDOWN, K.MEMORY_BREAKDOWN_DEFAULT)
+get_zero_allow_untested_optimizer = _top(K.ZERO_ALLOW_UNTESTED_OPTIMIZER, K.ZERO_ALLOW_UNTESTED_OPTIMIZER_DEFAULT)
+get_zero_force_ds_cpu_optimizer = _top(K.ZERO_FORCE_DS_CPU_OPTIMIZER, K.ZERO_FORCE_DS_CPU_OPTIMIZER_DEFAULT)
+get_dataloader_drop_last = _top(K.DATALOADER_DROP_LAST, K.DATALOADER_DROP_LAST_DEFAULT)
+
+
+def get_communication_data_type(param_dict, comm_type=K.COMMUNICATION_DATA_TYPE, comm_data_type_default=K.COMMUNICATION_DATA_TYPE_DEFAULT):
+    import torch
+    val = get_scalar_param(param_dict, comm_type, comm_data_type_default)
+    if val is None:
+        return None  # decided later from the training dtype
+    table = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16, "bfp16": torch.bfloat16}
+    if str(val).lower() not in table:
+        raise ValueError(f"Invalid communication_data_type. Supported data types: {sorted(table)}. Got: {val}")
+    return table[str(val).lower()]
+
+
+def _named(section, field, default=None):
+    def f(param_dict):
+        sec = param_dict.get(section)
+        return sec.get(field, default) if isinstance(sec, dict) else default
+    return f
+
+
+get_optimizer_name = _named(K.OPTIMIZER, K.TYPE, K.OPTIMIZER_TYPE_DEFAULT)
+get_optimizer_params = _named(K.OPTIMIZER, K.OPTIMIZER_PARAMS)
+get_optimizer_legacy_fusion = _named(K.OPTIMIZER, K.LEGACY_FUSION, K.LEGACY_FUSION_DEFAULT)
+get_scheduler_name = _named(K.SCHEDULER, K.TYPE, K.SCHEDULER_TYPE_DEFAULT)
+get_scheduler_params = _named(K.SCHEDULER, K.SCHEDULER_PARAMS)
+
+
+def get_optimizer_gradient_clipping(param_dict):
+    params = get_optimizer_params(param_dict)
+    return params.get(K.MAX_GRAD_NORM) if isinstance(params, dict) else None
+
+
+def get_pipeline_config(param_dict):
+    """The ``pipeline`` section over its defaults."""
+    out = PipelineConfig().model_dump()
+    out.update(param_dict.get("pipeline", {}))
+    return out
+
+
+def get_hybrid_engine_config(param_dict):
+    return HybridEngineConfig(**param_dict.get("hybrid_engine", {}))
+
+
+def get_expert_data_topo_config(param_dict):
+    return get_scalar_param(param_dict, K.USE_DATA_BEFORE_EXPERT_PARALLEL, K.USE_DATA_BEFORE_EXPERT_PARALLEL_DEFAULT)
+
+
+def _eig(key, default):
+    return lambda param_dict: get_scalar_param(param_dict[K.EIGENVALUE], key, default) if K.EIGENVALUE in param_dict else default
+
+
+get_eigenvalue_enabled = _eig(K.EIGENVALUE_ENABLED, K.EIGENVALUE_ENABLED_DEFAULT)
+get_eigenvalue_verbose = _eig(K.EIGENVALUE_VERBOSE, K.EIGENVALUE_VERBOSE_DEFAULT)
+get_eigenvalue_max_iter = _eig(K.EIGENVALUE_MAX_ITER, K.EIGENVALUE_MAX_ITER_DEFAULT)
+get_eigenvalue_tol = _eig(K.EIGENVALUE_TOL, K.EIGENVALUE_TOL_DEFAULT)
+get_eigenvalue_stability = _eig(K.EIGENVALUE_STABILITY, K.EIGENVALUE_STABILITY_DEFAULT)
+get_eigenvalue_gas_boundary_resolution = _eig(K.EIGENVALUE_GAS_BOUNDARY_RESOLUTION, K.EIGENVALUE_GAS_BOUNDARY_RESOLUTION_DEFAULT)
+get_eigenvalue_layer_name = _eig(K.EIGENVALUE_LAYER_NAME, K.EIGENVALUE_LAYER_NAME_DEFAULT)
+get_eigenvalue_layer_num = _eig(K.EIGENVALUE_LAYER_NUM, K.EIGENVALUE_LAYER_NUM_DEFAULT)
+
+
+def get_eigenvalue_config(param_dict):
+    """(enabled, verbose, max_iter, tol, stability, gas_boundary_resolution, layer_name, layer_num)"""
+    if not get_eigenvalue_enabled(param_dict):
+        return (False, K.EIGENVALUE_VERBOSE_DEFAULT, K.EIGENVALUE_MAX_ITER_DEFAULT, K.EIGENVALUE_TOL_DEFAULT, K.EIGENVALUE_STABILITY_DEFAULT,
+                K.EIGENVALUE_GAS_BOUNDARY_RESOLUTION_DEFAULT, K.EIGENVALUE_LAYER_NAME_DEFAULT, K.EIGENVALUE_LAYER_NUM_DEFAULT)
+    return (True, get_eigenvalue_verbose(param_dict), get_eigenvalue_max_iter(param_dict), get_eigenvalue_tol(param_dict),
+            get_eigenvalue_stability(param_dict), get_eigenvalue_gas_boundary_resolution(param_dict),
+            get_eigenvalue_layer_name(param_dict), get_eigenvalue_layer_num(param_dict))
+
+
+def get_checkpoint_params(param_dict):
+    return param_dict.get(K.CHECKPOINT, {})
+
+
+def get_data_types_params(param_dict):
+    return param_dict.get(K.DATA_TYPES, {})
+
+
+def get_checkpoint_tag_validation_mode(checkpoint_params):
+    mode = str(checkpoint_params.get(K.CHECKPOINT_TAG_VALIDATION, K.CHECKPOINT_TAG_VALIDATION_DEFAULT)).upper()
+    if mode not in K.CHECKPOINT_TAG_VALIDATION_MODES:
+        raise DeepSpeedConfigError(f"Checkpoint config contains invalid tag_validation value of {mode}, expecting one of "
+                                   f"{K.CHECKPOINT_TAG_VALIDATION_MODES}")
+    return mode
+
+
+def get_checkpoint_parallel_write_pipeline(checkpoint_params):
+    par = checkpoint_params.get(K.CHECKPOINT_PARALLEL_WRITE, {})
+    val = par.get(K.CHECKPOINT_PARALLEL_WRITE_PIPELINE_STAGE, K.CHECKPOINT_PARALLEL_WRITE_PIPELINE_STAGE_DEFAULT)
+    if val not in (True, False):
+        raise DeepSpeedConfigError(f"checkpoint::parallel_write::pipeline_stage value of '{val}' is invalid, expecting: true or false")
+    return val
+
+
+# ---- sparse attention section -----------------------------------------------------------------------------------------
+def get_sparse_attention_mode(param_dict):
+    return param_dict.get(K.SPARSE_MODE, K.SPARSE_MODE_DEFAULT)
+
+
+def get_sparse_attention_type(param_dict):
+    return param_dict.get(K.SPARSE_ATTENTION_TYPE, K.SPARSE_ATTENTION_TYPE_DEFAULT)
+
+
+def _sparse(mode, *fields):
+    """Builder of a ``get_sparse_<mode>_config``: the mode + ``block`` + the listed (key, default) fields."""
+    def f(sparsity):
+        out = {K.SPARSE_MODE: mode, K.SPARSE_BLOCK: get_scalar_param(sparsity, K.SPARSE_BLOCK, K.SPARSE_BLOCK_DEFAULT)}
+        for key, default in fields:
+            out[key] = get_scalar_param(sparsity, key, default)
+        return out
+    return f
+
+
+_LAYOUT = (K.SPARSE_DIFFERENT_LAYOUT_PER_HEAD, K.SPARSE_DIFFERENT_LAYOUT_PER_HEAD_DEFAULT)
+get_sparse_dense_config = _sparse(K.SPARSE_DENSE_MODE)
+get_sparse_fixed_config = _sparse(K.SPARSE_FIXED_MODE, _LAYOUT, (K.SPARSE_NUM_LOCAL_BLOCKS, K.SPARSE_NUM_LOCAL_BLOCKS_DEFAULT),
+                                  (K.SPARSE_NUM_GLOBAL_BLOCKS, K.SPARSE_NUM_GLOBAL_BLOCKS_DEFAULT),
+                                  (K.SPARSE_ATTENTION_TYPE, K.SPARSE_ATTENTION_TYPE_DEFAULT),
+                                  (K.SPARSE_HORIZONTAL_GLOBAL_ATTENTION, K.SPARSE_HORIZONTAL_GLOBAL_ATTENTION_DEFAULT),
+                                  (K.SPARSE_NUM_DIFFERENT_GLOBAL_PATTERNS, K.SPARSE_NUM_DIFFERENT_GLOBAL_PATTERNS_DEFAULT))
+get_sparse_variable_config = _sparse(K.SPARSE_VARIABLE_MODE, _LAYOUT, (K.SPARSE_NUM_RANDOM_BLOCKS, K.SPARSE_NUM_RANDOM_BLOCKS_DEFAULT),
+                                     (K.SPARSE_LOCAL_WINDOW_BLOCKS, K.SPARSE_LOCAL_WINDOW_BLOCKS_DEFAULT),
+                                     (K.SPARSE_GLOBAL_BLOCK_INDICES, K.SPARSE_GLOBAL_BLOCK_INDICES_DEFAULT),
+                                     (K.SPARSE_GLOBAL_BLOCK_END_INDICES, K.SPARSE_GLOBAL_BLOCK_END_INDICES_DEFAULT),
+                                     (K.SPARSE_ATTENTION_TYPE, K.SPARSE_ATTENTION_TYPE_DEFAULT),
+                                     (K.SPARSE_HORIZONTAL_GLOBAL_ATTENTION, K.SPARSE_HORIZONTAL_GLOBAL_ATTENTION_DEFAULT))
+get_sparse_bigbird_config = _sparse(K.SPARSE_BIGBIRD_MODE, _LAYOUT, (K.SPARSE_NUM_RANDOM_BLOCKS, K.SPARSE_NUM_RANDOM_BLOCKS_DEFAULT),
+                                    (K.SPARSE_NUM_SLIDING_WINDOW_BLOCKS, K.SPARSE_NUM_SLIDING_WINDOW_BLOCKS_DEFAULT),
+                                    (K.SPARSE_NUM_GLOBAL_BLOCKS, K.SPARSE_NUM_GLOBAL_BLOCKS_DEFAULT))
+get_sparse_bslongformer_config = _sparse(K.SPARSE_BSLONGFORMER_MODE, _LAYOUT,
+                                         (K.SPARSE_NUM_SLIDING_WINDOW_BLOCKS, K.SPARSE_NUM_SLIDING_WINDOW_BLOCKS_DEFAULT),
+                                         (K.SPARSE_GLOBAL_BLOCK_INDICES, K.SPARSE_GLOBAL_BLOCK_INDICES_DEFAULT),
+                                         (K.SPARSE_GLOBAL_BLOCK_END_INDICES, K.SPARSE_GLOBAL_BLOCK_END_INDICES_DEFAULT))
+_SPARSE_BUILDERS = {K.SPARSE_DENSE_MODE: get_sparse_dense_config, K.SPARSE_FIXED_MODE: get_sparse_fixed_config,
+                    K.SPARSE_VARIABLE_MODE: get_sparse_variable_config, K.SPARSE_BIGBIRD_MODE: get_sparse_bigbird_config,
+                    K.SPARSE_BSLONGFORMER_MODE: get_sparse_bslongformer_config}
+
+
+def get_sparse_attention(param_dict):
+    if K.SPARSE_ATTENTION not in param_dict:
+        return None
+    sparsity = param_dict[K.SPARSE_ATTENTION]
+    mode = get_sparse_attention_mode(sparsity)
+    if mode not in _SPARSE_BUILDERS:
+        raise NotImplementedError(f"Given sparsity mode, {mode}, has not been implemented yet!")
+    return _SPARSE_BUILDERS[mode](sparsity)
+
+
+class DeepSpeedConfigWriter:
+    """Accumulate config entries and write / reload them as JSON (reference ``DeepSpeedConfigWriter``)."""
+
+    def __init__(self, data=None):
+        self.data = data if data is not None else {}
+
+    def add_config(self, key, value):
+        self.data[key] = value
+
+    def load_config(self, filename):
+        with open(filename) as f:
+            self.data = json.load(f, object_pairs_hook=dict_raise_error_on_duplicate_keys)
+
+    def write_config(self, filename):
+        with open(filename, "w") as f:
+            json.dump(self.data, f)
+
+
+for _n, _f in list(globals().items()):  # give the generated accessors proper names
+    if _n.startswith("get_") and callable(_f) and getattr(_f, "__name__", "") in ("<lambda>", "f"):
+        _f.__name__ = _n

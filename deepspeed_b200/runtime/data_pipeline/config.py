@@ -34,3 +34,69 @@ def get_curriculum_params_legacy(param_dict):
     d = copy.copy(param_dict.get(C.CURRICULUM_LEARNING, {}))
     d.pop(C.CURRICULUM_LEARNING_ENABLED, None)
     return d or False
+
+
+# ---- section accessors (reference ``runtime/data_pipeline/config.py:get_*``); ``param_dict`` is the section's parent ----
+def _full(param_dict):
+    return get_data_efficiency_config({C.DATA_EFFICIENCY: param_dict}) if C.DATA_EFFICIENCY not in param_dict else \
+        get_data_efficiency_config(param_dict)
+
+
+def get_data_efficiency_enabled(param_dict):
+    return _full(param_dict)[C.DATA_EFFICIENCY_ENABLED]
+
+
+def get_data_efficiency_seed(param_dict):
+    return _full(param_dict)[C.DATA_EFFICIENCY_SEED]
+
+
+def get_data_sampling(param_dict):
+    return _full(param_dict)[C.DATA_SAMPLING]
+
+
+def get_data_sampling_enabled(param_dict):
+    return get_data_sampling(param_dict)[C.DATA_SAMPLING_ENABLED]
+
+
+def get_data_sampling_num_epochs(param_dict):
+    return get_data_sampling(param_dict)[C.DATA_SAMPLING_NUM_EPOCHS]
+
+
+def get_data_sampling_num_workers(param_dict):
+    return get_data_sampling(param_dict)[C.DATA_SAMPLING_NUM_WORKERS]
+
+
+def get_curriculum_learning(param_dict):
+    return get_data_sampling(param_dict)[C.CURRICULUM_LEARNING]
+
+
+def get_curriculum_learning_enabled(param_dict):
+    return get_curriculum_learning(param_dict)[C.CURRICULUM_LEARNING_ENABLED]
+
+
+def get_curriculum_learning_params(param_dict):
+    d = dict(get_curriculum_learning(param_dict))
+    d.pop(C.CURRICULUM_LEARNING_ENABLED, None)
+    return d or False
+
+
+def get_data_routing(param_dict):
+    return _full(param_dict)[C.DATA_ROUTING]
+
+
+def get_data_routing_enabled(param_dict):
+    return get_data_routing(param_dict)[C.DATA_ROUTING_ENABLED]
+
+
+def get_random_ltd(param_dict):
+    return get_data_routing(param_dict)[C.RANDOM_LTD]
+
+
+def get_random_ltd_enabled(param_dict):
+    return get_random_ltd(param_dict)[C.RANDOM_LTD_ENABLED]
+
+
+def get_random_ltd_params(param_dict):
+    d = dict(get_random_ltd(param_dict))
+    d.pop(C.RANDOM_LTD_ENABLED, None)
+    return d or False

@@ -144,3 +144,42 @@ def test_activation_checkpoint_functional_helpers():
     assert torch.equal(back[0], x.detach()) and back[1] == 7
     with pytest.raises(RuntimeError):
         C.detach_variable([x])
+
+
+def test_functional_config_getters(tmp_path):
+    from deepspeed_b200.compression import config as CC
+    from deepspeed_b200.runtime import config as C
+    from deepspeed_b200.runtime.data_pipeline import config as DC
+    d = {"fp16": {"enabled": True, "loss_scale_window": 500, "initial_scale_power": 10},
+         "optimizer": {"type": "AdamW", "params": {"lr": 1e-3, "max_grad_norm": 2.0}}, "scheduler": {"type": "WarmupLR", "params": {}},
+         "train_batch_size": 8, "gradient_clipping": 1.5, "communication_data_type": "bf16",
+         "sparse_attention": {"mode": "bigbird", "block": 32}, "eigenvalue": {"enabled": True, "max_iter": 7},
+         "checkpoint": {"tag_validation": "fail", "parallel_write": {"pipeline_stage": True}}, "amp": {"enabled": True, "opt_level": "O1"}}
+    assert C.get_fp16_enabled(d) and C.get_loss_scale(d) == 0 and C.get_initial_dynamic_scale(d) == 1024
+    args = C.get_dynamic_loss_scale_args(d)
+    assert args["scale_window"] == 500 and args["init_scale"] == 1024 and args["min_scale"] == 1
+    assert C.get_optimizer_name(d) == "AdamW" and C.get_optimizer_gradient_clipping(d) == 2.0 and C.get_scheduler_name(d) == "WarmupLR"
+    assert C.get_train_batch_size(d) == 8 and C.get_gradient_clipping(d) == 1.5 and C.get_communication_data_type(d) is torch.bfloat16
+    assert C.get_amp_enabled(d) and C.get_amp_params(d) == {"opt_level": "O1"} and C.get_pld_enabled(d) is False
+    sa = C.get_sparse_attention(d)
+    assert sa["mode"] == "bigbird" and sa["block"] == 32 and sa["num_sliding_window_blocks"] == 3
+    assert C.get_eigenvalue_config(d)[:3] == (True, False, 7) and C.get_eigenvalue_config({})[0] is False
+    ck = C.get_checkpoint_params(d)
+    assert C.get_checkpoint_tag_validation_mode(ck) == "FAIL" and C.get_checkpoint_parallel_write_pipeline(ck) is True
+    with pytest.raises(C.DeepSpeedConfigError):
+        C.get_checkpoint_tag_validation_mode({"tag_validation": "maybe"})
+    with pytest.raises(ValueError):
+        C.get_communication_data_type({"communication_data_type": "int3"})
+    assert C.get_bfloat16_enabled({"bfloat16": {"enabled": True}}) and C.get_loss_scale({"bf16": {"enabled": True}}) == 1.0
+    w = C.DeepSpeedConfigWriter()
+    w.add_config("train_batch_size", 4)
+    w.write_config(str(tmp_path / "c.json"))
+    w2 = C.DeepSpeedConfigWriter()
+    w2.load_config(str(tmp_path / "c.json"))
+    assert w2.data == {"train_batch_size": 4}
+    wq = CC.get_weight_quantization({"weight_quantization": {"shared_parameters": {"enabled": True},
+                                                             "different_groups": {"g": {"params": {"start_bits": 8, "target_bits": 4}}}}})
+    assert wq["shared_parameters"]["enabled"] and wq["different_groups"]["g"]["params"]["quantization_period"] == 1
+    assert CC.get_layer_reduction_params({"layer_reduction": {"enabled": True, "keep_number_layer": 2}}) == {"keep_number_layer": 2}
+    de = {"data_efficiency": {"enabled": True, "data_routing": {"random_ltd": {"enabled": True, "x": 1}}}}
+    assert DC.get_data_efficiency_enabled(de) and DC.get_random_ltd_params(de) == {"x": 1} and DC.get_data_sampling_num_epochs(de) == 1000
