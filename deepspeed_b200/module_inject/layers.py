@@ -238,3 +238,194 @@ class Normalize(nn.Module):
 
     def forward(self, input):
         return F.layer_norm(input, input.shape[-1:], self.weight, self.bias, self.eps)
+
+
+# =====================================================================================================================
+# Layout-specific variants (reference ``module_inject/layers.py``: fused_LinearLayer, conv_LinearLayer, GateUpPack_LinearLayer,
+# Yuan_*, TensorParallelConv2d, ...).  They differ from LinearLayer / LinearAllreduce only in HOW the weight is cut.
+# =====================================================================================================================
+def get_auto_tp_mode():
+    from deepspeed_b200.runtime.tensor_parallel.config import AUTOTP_MODE
+    return AUTOTP_MODE.TRAINING if AUTOTP_TRAINING_MODE else AUTOTP_MODE.INFERENCE
+
+
+def is_autotp_training_mode():
+    return bool(AUTOTP_TRAINING_MODE)
+
+
+class _PresplitColumn(TensorParallel_Layer):
+    """Column-parallel layer built from an already computed local weight / bias."""
+
+    def __init__(self, weight, bias, mp_group, name=None):
+        super().__init__(mp_group, name)
+        self.support_training = True
+        self.weight = nn.Parameter(weight.contiguous())
+        self.bias = nn.Parameter(bias.contiguous()) if bias is not None else None
+        self._mark(self.weight, self.bias)
+
+    def forward(self, input):
+        x = ColumnParallel.apply(self.mp_group, input) if self.training else input
+        return F.linear(x, self.weight, self.bias)
+
+
+class fused_LinearLayer(_PresplitColumn):
+    """Column-parallel layer over a FUSED q/k/v projection whose internal layout is family specific (per-head
+    interleaved, grouped, blocked ...): the slice keeps whole heads together (``fusedqkv_utils.prepare_tp_fused_qkvw``)."""
+
+    def __init__(self, module, mp_group, skip_partition=False, fused_module=None, **kwargs):
+        from .fusedqkv_utils import prepare_tp_fused_qkvw
+        world = dist.get_world_size(mp_group) if mp_group is not None else 1
+        rank = dist.get_rank(mp_group) if mp_group is not None else 0
+        w, b = module.weight.data, (module.bias.data if getattr(module, "bias", None) is not None else None)
+        if not skip_partition and world > 1:
+            owner = fused_module if fused_module is not None else kwargs.get("fused_type", "glmtype")
+            w = prepare_tp_fused_qkvw(owner, w, world, rank)
+            b = prepare_tp_fused_qkvw(owner, b, world, rank) if b is not None else None
+        super().__init__(w.clone(), None if b is None else b.clone(), mp_group, kwargs.get("name"))
+
+
+class GateUpPack_LinearLayer(_PresplitColumn):
+    """Column-parallel layer over a packed ``[gate | up]`` projection (phi-3 ``gate_up_proj``): both halves are cut."""
+
+    def __init__(self, module, mp_group, skip_partition=False, **kwargs):
+        from .fusedqkv_utils import shard_chunk_mlp
+        world = dist.get_world_size(mp_group) if mp_group is not None else 1
+        rank = dist.get_rank(mp_group) if mp_group is not None else 0
+        w, b = module.weight.data, (module.bias.data if getattr(module, "bias", None) is not None else None)
+        if not skip_partition and world > 1:
+            w, b = shard_chunk_mlp(w, b, rank, world)
+        super().__init__(w.clone(), None if b is None else b.clone(), mp_group, kwargs.get("name"))
+
+
+class conv_LinearLayer(_PresplitColumn):
+    """Column-parallel layer built from a GPT-2 style ``Conv1D`` (weight stored ``[in, out]``)."""
+
+    def __init__(self, module, mp_group, skip_partition=False, fused_parts=1, **kwargs):
+        world = dist.get_world_size(mp_group) if mp_group is not None else 1
+        rank = dist.get_rank(mp_group) if mp_group is not None else 0
+        w = module.weight.data.t()  # -> [out, in]
+        b = module.bias.data if getattr(module, "bias", None) is not None else None
+        if not skip_partition and world > 1:
+            w = _split_rows(w, world, rank, fused_parts)
+            b = _split_rows(b, world, rank, fused_parts) if b is not None else None
+        super().__init__(w.clone(), None if b is None else b.clone(), mp_group, kwargs.get("name"))
+
+
+class Conv_LinearALlreduce(LinearAllreduce):
+    """Row-parallel layer built from a ``Conv1D`` (weight ``[in, out]``)."""
+
+    def __init__(self, module, mp_group, **kwargs):
+        super().__init__(None, mp_group, weight=module.weight.data.t(), bias=getattr(module, "bias", None), **kwargs)
+
+
+class Yuan_LinearLayer(_PresplitColumn):
+    """Yuan's q/k projection stores ``[q | k]`` stacked: each half is cut separately so heads stay aligned."""
+
+    def __init__(self, module, mp_group, skip_partition=False, **kwargs):
+        from .fusedqkv_utils import shard_value_with_share_qk
+        world = dist.get_world_size(mp_group) if mp_group is not None else 1
+        rank = dist.get_rank(mp_group) if mp_group is not None else 0
+        w, b = module.weight.data, (module.bias.data if getattr(module, "bias", None) is not None else None)
+        if not skip_partition and world > 1:
+            w, b = shard_value_with_share_qk(w, b, rank, world, True)
+        super().__init__(w.clone(), None if b is None else b.clone(), mp_group, kwargs.get("name"))
+
+
+class Yuan_LinearAllreduce(LinearAllreduce):
+    """Row-parallel output projection of Yuan (input columns follow the same head split as the value projection)."""
+
+
+class FusedModuleWrapper:
+    """Wrap a fused module so attribute access is forwarded and ``forward`` splits the fused output when needed."""
+
+    def __init__(self, fused_module: nn.Module):
+        self.fused_module = fused_module
+
+    def __getattr__(self, item):
+        return getattr(self.__dict__["fused_module"], item)
+
+    def __call__(self, *args, **kwargs):
+        return self.fused_module(*args, **kwargs)
+
+
+class RMSNormalize(nn.Module):
+    """RMSNorm with injectable weight (reference ``RMSNormalize``); kernel path through ``transformer_ops.rms_norm``."""
+
+    def __init__(self, dim=None, dtype=torch.float, eps=1e-5, weight=None):
+        super().__init__()
+        self.weight = weight if weight is not None else nn.Parameter(torch.ones(dim, dtype=dtype))
+        self.eps = eps
+
+    def forward(self, hidden_states):
+        from deepspeed_b200.ops.kernels.transformer_ops import rms_norm
+        return rms_norm(hidden_states, self.weight, self.eps)
+
+
+class OPTEmbedding(EmbeddingLayer):
+    """OPT learned positions: position ids come from the attention mask and are shifted by 2."""
+
+    def __init__(self, weight_shape=None, weight=None, bias=None):
+        super().__init__(weight_shape, weight=weight)
+        self.offset = 2
+
+    def forward(self, attention_mask: torch.LongTensor, past_key_values_length: int = 0, position_ids: int = 0):
+        attention_mask = attention_mask.long()
+        positions = (torch.cumsum(attention_mask, dim=1).type_as(attention_mask) * attention_mask).long() - 1
+        positions = positions[:, past_key_values_length:]
+        return super().forward(positions + self.offset)
+
+
+# ---- tensor-parallel convolutions ------------------------------------------------------------------------------------
+class TensorParallelConv2d(nn.Module):
+
+    def __init__(self, conv, rank, world_size, shard_by_oc):
+        super().__init__()
+        self.rank, self.world_size, self.shard_by_oc = rank, world_size, shard_by_oc
+        self.shard_weights(conv)
+
+    def shard_weights(self, conv):
+        """Keep this rank's output channels (``shard_by_oc``) or input channels of ``conv`` in place."""
+        if self.world_size == 1:
+            return
+        oc, ic = conv.weight.shape[:2]
+        if self.shard_by_oc:
+            s, e = shard_bounds(oc, self.world_size, self.rank)
+            conv.weight.data = conv.weight.data[s:e].clone()
+            if conv.bias is not None:
+                conv.bias.data = conv.bias.data[s:e].clone()
+            conv.out_channels = e - s
+        else:
+            s, e = shard_bounds(ic, self.world_size, self.rank)
+            conv.weight.data = conv.weight.data[:, s:e].clone()
+            if conv.bias is not None:  # the bias is added once: only rank 0 keeps it
+                conv.bias.data = conv.bias.data if self.rank == 0 else torch.zeros_like(conv.bias.data)
+            conv.in_channels = e - s
+            self._ic_range = (s, e)
+
+
+class TensorParallelOcShardConv2d(TensorParallelConv2d):
+    """Output-channel sharded conv: the result is this rank's channel slice (feed an Ic-sharded conv next)."""
+
+    def __init__(self, conv, rank, world_size):
+        super().__init__(conv, rank, world_size, True)
+        self.conv = conv
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return self.conv(input)
+
+
+class TensorParallelIcShardConv2d(TensorParallelConv2d):
+    """Input-channel sharded conv: consumes this rank's channel slice, partial sums are all-reduced."""
+
+    def __init__(self, conv, rank, world_size, mp_group=None):
+        super().__init__(conv, rank, world_size, False)
+        self.conv, self.mp_group = conv, mp_group
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if self.world_size > 1 and input.shape[1] != self.conv.in_channels:
+            s, e = self._ic_range
+            input = input[:, s:e]
+        out = self.conv(input)
+        if self.world_size > 1:
+            dist.inference_all_reduce(out, group=self.mp_group)
+        return out

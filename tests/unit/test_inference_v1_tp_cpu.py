@@ -123,3 +123,57 @@ def _domino_worker():
 
 def test_domino_tp2_matches_dense():
     run_distributed(_domino_worker, 2)
+
+
+def _tp_variants():
+    import torch
+    import torch.distributed as td
+    from torch import nn
+    from deepspeed_b200.module_inject import layers as L
+    r, w = td.get_rank(), td.get_world_size()
+    g = td.group.WORLD
+    torch.manual_seed(0)
+    x = torch.randn(3, 16)
+    # fused [q|k|v] (glm layout), gate/up pack, Conv1D column + row
+    fused = nn.Linear(16, 48)
+    lay = L.fused_LinearLayer(fused, g, fused_type="glmtype")
+    full = fused(x)
+    q, k, v = full.chunk(3, -1)
+    want = torch.cat([t.chunk(w, -1)[r] for t in (q, k, v)], -1)
+    assert torch.allclose(lay(x), want, atol=1e-6)
+    gu = nn.Linear(16, 32, bias=False)
+    lay = L.GateUpPack_LinearLayer(gu, g)
+    a, b = gu(x).chunk(2, -1)
+    assert torch.allclose(lay(x), torch.cat([a.chunk(w, -1)[r], b.chunk(w, -1)[r]], -1), atol=1e-6)
+
+    class Conv1D(nn.Module):
+
+        def __init__(self, nin, nout):
+            super().__init__()
+            self.weight, self.bias = nn.Parameter(torch.randn(nin, nout) * 0.1), nn.Parameter(torch.randn(nout) * 0.1)
+
+        def forward(self, t):
+            return t @ self.weight + self.bias
+
+    c1, c2 = Conv1D(16, 32), Conv1D(32, 16)
+    col, row = L.conv_LinearLayer(c1, g), L.Conv_LinearALlreduce(c2, g)
+    assert torch.allclose(row(col(x)), c2(c1(x)), atol=1e-5)
+    # output-channel sharded conv feeding an input-channel sharded conv == the two full convs
+    torch.manual_seed(1)
+    conv_a, conv_b = nn.Conv2d(3, 8, 3, padding=1), nn.Conv2d(8, 4, 1)
+    img = torch.randn(2, 3, 6, 6)
+    ref = conv_b(conv_a(img))
+    import copy
+    oc = L.TensorParallelOcShardConv2d(copy.deepcopy(conv_a), r, w)
+    ic = L.TensorParallelIcShardConv2d(copy.deepcopy(conv_b), r, w, g)
+    assert torch.allclose(ic(oc(img)), ref, atol=1e-5)
+    assert L.get_auto_tp_mode().value == "INFERENCE" and not L.is_autotp_training_mode()
+    n = L.RMSNormalize(dim=16, dtype=torch.float32)
+    assert torch.allclose(n(x), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5), atol=1e-5)
+    emb = L.OPTEmbedding(weight=nn.Parameter(torch.arange(20.).reshape(10, 2)))
+    out = emb(torch.tensor([[0, 1, 1, 1]]))
+    assert out.shape == (1, 4, 2) and out[0, 1, 0] == 4.0  # first real token -> position 0 -> row 2
+
+
+def test_tp_layer_variants():
+    run_distributed(_tp_variants, 2)
