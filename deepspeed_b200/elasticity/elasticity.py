@@ -190,3 +190,23 @@ def compute_elastic_config(ds_config: dict, target_deepspeed_version: str, world
         fits = [mb for mb in sorted(set(cfg.micro_batches), reverse=True) if batch % mb == 0]
         return batch, gpus, (fits[0] if fits else None)
     return batch, gpus
+
+
+# ---- reference names of the planning primitives ---------------------------------------------------------------------
+def get_candidate_batch_sizes(base_list, max_acceptable_batch_size):
+    return _candidate_batches(list(base_list), max_acceptable_batch_size)
+
+
+def get_valid_gpus(batch_size, micro_batches, min_valid_gpus, max_valid_gpus):
+    return _valid_gpu_counts(batch_size, list(micro_batches), min_valid_gpus, max_valid_gpus)
+
+
+def get_best_candidates(candidate_batch_sizes, micro_batches, min_gpus, max_gpus, prefer_larger):
+    """(batch size, valid gpu counts) of the candidate that admits the most GPU counts (ties by batch size preference)."""
+    best_batch, best_gpus, best_n = int(min(micro_batches)), None, 0
+    for cand in candidate_batch_sizes:
+        gpus = get_valid_gpus(cand, micro_batches, min_gpus, max_gpus)
+        tie = (cand > best_batch) if prefer_larger else (cand < best_batch)
+        if len(gpus) > best_n or (len(gpus) == best_n and tie):
+            best_n, best_gpus, best_batch = len(gpus), gpus, cand
+    return best_batch, best_gpus
