@@ -161,3 +161,102 @@ def number_to_string(n, postfix="", units=None, precision=2):
         if units == u or (units is None and n >= s):
             return f"{round(n / s, precision)} {u}{postfix}"
     return f"{n} {postfix}"
+
+
+def get_val_by_key(d: dict, k):
+    """Depth-first lookup of ``k`` anywhere in a nested dict (reference ``autotuning/utils.py:133``)."""
+    if k in d:
+        return d[k]
+    for sub in (v for v in d.values() if isinstance(v, dict)):
+        hit = get_val_by_key(sub, k)
+        if hit is not None:
+            return hit
+    return None
+
+
+def set_val_by_key(d: dict, k, vv):
+    """Overwrite every occurrence of ``k`` in a nested dict."""
+    stack = [d]
+    while stack:
+        cur = stack.pop()
+        if k in cur:
+            cur[k] = vv
+        stack.extend(v for v in cur.values() if isinstance(v, dict))
+
+
+def fetch_hostfile(hostfile_path):
+    """``host slots=N`` lines → ordered ``{host: N}``; ``None`` when the file does not exist (reference ``:150``)."""
+    import collections
+    from deepspeed_b200.utils.logging import logger
+    if not os.path.isfile(hostfile_path):
+        logger.warning("Unable to find hostfile, will proceed with training with local resources only.")
+        return None
+    pool = collections.OrderedDict()
+    with open(hostfile_path) as fd:
+        for raw in fd:
+            line = raw.split("#", 1)[0].strip()
+            if not line:
+                continue
+            m = re.fullmatch(r"(\S+)\s+slots=(\d+)", line)
+            if m is None:
+                raise ValueError(f"Hostfile is not formatted correctly, unable to proceed with training: {raw!r}")
+            host, slots = m.group(1), int(m.group(2))
+            if host in pool:
+                raise ValueError(f"host {host} is already defined in the hostfile")
+            pool[host] = slots
+    if not pool:
+        raise ValueError("Hostfile is empty or not formatted correctly, unable to proceed with training.")
+    return pool
+
+
+def validate_ds_config(config: dict):
+    """Reject ZeRO configs the tuner should not launch: offload sections on a stage that cannot use them."""
+    z = config.get("zero_optimization") or {}
+    stage = z.get("stage")
+    if not z or stage in (None, 0, 1):
+        return True
+    on = lambda key: bool(z.get(key))
+    if stage == 2:
+        return not (on("cpu_offload") and on("cpu_offload_params"))
+    if stage == 3:
+        off_p, off_o = z.get("offload_param") or {}, z.get("offload_optimizer") or {}
+        nvme = "nvme" in (off_p.get("device"), off_o.get("device"))
+        if nvme:
+            aio = config.get("aio")
+            return bool(aio) and all(os.path.isdir(str(s.get("nvme_path", ""))) for s in (off_p, off_o)
+                                     if s.get("device") == "nvme")
+        return True
+    return True
+
+
+def remove_dupe_dicts(l):
+    """Unique (nested) dicts of ``l``, first occurrence kept."""
+    seen, out = set(), []
+    for d in l:
+        key = json.dumps(d, sort_keys=True)
+        if key not in seen:
+            seen.add(key)
+            out.append(json.loads(key))
+    return out
+
+
+def prune_config(config, ignored_keys=()):
+    """Delete the ``ignored_keys`` sections (wherever they are nested) in place."""
+    for k in ignored_keys or ():
+        del_if_exists(k, config)
+    return config
+
+
+def prune_configs(configs, ignored_keys=()):
+    return remove_dupe_dicts([prune_config(c, ignored_keys) for c in configs])
+
+
+def get_tuning_keys(tuning_space: dict):
+    """Names of the parameters with more than one candidate value."""
+    keys = []
+    for name, val in tuning_space.items():
+        if isinstance(val, dict):
+            keys += get_tuning_keys(val)
+        elif isinstance(val, list) and len(val) > 1:
+            keys.append(name)
+    return keys

@@ -367,3 +367,83 @@ class RowParallelLinear_Compress(LinearLayer_Compress):
         if self.skip_bias_add:
             return out, bias
         return out + bias if bias is not None else out
+
+
+# --- Megatron-style model-parallel region operators (reference ``compression/basic_layer.py:620-765``) ----------------
+# ``mpu``-less functional forms: they act on the framework's tensor-parallel group (``utils.groups``), which is what the
+# ``*_Compress`` parallel layers above use when constructed without an explicit mpu.
+def _tp_group():
+    from deepspeed_b200.utils import groups
+    return groups.get_tensor_model_parallel_group()
+
+
+def _tp_world(group):
+    from deepspeed_b200 import comm as dist
+    return dist.get_world_size(group=group) if dist.is_initialized() else 1
+
+
+def split_tensor_along_last_dim(tensor, num_partitions, contiguous_split_chunks=False):
+    assert tensor.size(-1) % num_partitions == 0, f"{tensor.size(-1)} is not divisible by {num_partitions}"
+    parts = tensor.split(tensor.size(-1) // num_partitions, dim=-1)
+    return tuple(p.contiguous() for p in parts) if contiguous_split_chunks else parts
+
+
+def _reduce(input_, group=None):
+    from deepspeed_b200 import comm as dist
+    group = group if group is not None else _tp_group()
+    if _tp_world(group) > 1:
+        dist.all_reduce(input_, group=group)
+    return input_
+
+
+def _split(input_, group=None):
+    from deepspeed_b200 import comm as dist
+    group = group if group is not None else _tp_group()
+    w = _tp_world(group)
+    return input_ if w == 1 else split_tensor_along_last_dim(input_, w)[dist.get_rank(group=group)].contiguous()
+
+
+def _gather(input_, group=None):
+    from deepspeed_b200 import comm as dist
+    group = group if group is not None else _tp_group()
+    w = _tp_world(group)
+    if w == 1:
+        return input_
+    parts = [torch.empty_like(input_) for _ in range(w)]
+    dist.all_gather(parts, input_.contiguous(), group=group)
+    return torch.cat(parts, dim=-1)
+
+
+def _region(name, fwd, bwd):
+    """Autograd function whose forward is ``fwd`` and whose backward applies ``bwd`` to the incoming gradient."""
+
+    def forward(ctx, x):
+        return fwd(x)
+
+    def backward(ctx, g):
+        return bwd(g)
+
+    return type(name, (torch.autograd.Function, ), {"forward": staticmethod(forward), "backward": staticmethod(backward)})
+
+
+_identity = lambda t: t
+_CopyToModelParallelRegion = _region("_CopyToModelParallelRegion", _identity, lambda g: _reduce(g.clone()))
+_ReduceFromModelParallelRegion = _region("_ReduceFromModelParallelRegion", lambda x: _reduce(x.clone()), _identity)
+_ScatterToModelParallelRegion = _region("_ScatterToModelParallelRegion", _split, _gather)
+_GatherFromModelParallelRegion = _region("_GatherFromModelParallelRegion", _gather, _split)
+
+
+def copy_to_model_parallel_region(input_):
+    return _CopyToModelParallelRegion.apply(input_)
+
+
+def reduce_from_model_parallel_region(input_):
+    return _ReduceFromModelParallelRegion.apply(input_)
+
+
+def scatter_to_model_parallel_region(input_):
+    return _ScatterToModelParallelRegion.apply(input_)
+
+
+def gather_from_model_parallel_region(input_):
+    return _GatherFromModelParallelRegion.apply(input_)

@@ -1,6 +1,7 @@
 """``ds_report``: environment + op compatibility report (reference ``env_report.py``)."""
 import argparse
 import importlib
+import importlib.util
 import os
 import shutil
 import subprocess
@@ -34,6 +35,41 @@ def nvcc_version():
         return f"{RED}[FAIL] cannot find nvcc{END}"
 
 
+def ninja_installed():
+    """True when the ``ninja`` build tool the JIT op loader needs is importable."""
+    return importlib.util.find_spec("ninja") is not None
+
+
+def human_readable_size(size):
+    """Bytes → ``"12.34 GB"`` (binary units)."""
+    units = ["B", "KB", "MB", "GB", "TB", "PB"]
+    v, i = float(size), 0
+    while v >= 1024 and i < len(units) - 1:
+        v, i = v / 1024, i + 1
+    return f"{v:.2f} {units[i]}"
+
+
+def get_shm_size():
+    """(size string, [warnings]) for ``/dev/shm``: NCCL's intra-node transports fall back to sockets when it is tiny
+    (reference ``env_report.py:110``)."""
+    try:
+        total = shutil.disk_usage("/dev/shm").total
+    except OSError:
+        return "UNKNOWN", []
+    warn = []
+    if total < 512 * 1024**2:
+        warn.append(f" {YELLOW} [WARNING] /dev/shm size might be too small, if running in docker increase to at least "
+                    f"--shm-size='1gb' {END}")
+        try:
+            import torch
+            if torch.cuda.is_available():
+                warn.append(f" {YELLOW} [WARNING] see more details about NCCL requirements: "
+                            f"https://docs.nvidia.com/deeplearning/nccl/user-guide/docs/troubleshooting.html#sharing-data {END}")
+        except ImportError:
+            pass
+    return human_readable_size(total), warn
+
+
 def debug_report():
     import torch
     import deepspeed_b200
@@ -50,11 +86,14 @@ def debug_report():
     except Exception:
         pass
     import psutil
-    rows.append(("shared memory (/dev/shm) size", f"{shutil.disk_usage('/dev/shm').total / 2**30:.2f} GB"))
+    shm, shm_warn = get_shm_size()
+    rows.append(("shared memory (/dev/shm) size", shm))
     rows.append(("host memory", f"{psutil.virtual_memory().total / 2**30:.1f} GiB"))
     print("DeepSpeed-B200 general environment info:")
     for k, v in rows:
         print(f"{k} {'.' * (40 - len(k))} {v}")
+    for w in shm_warn:
+        print(w)
 
 
 def parse_arguments():

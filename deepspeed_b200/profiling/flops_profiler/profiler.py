@@ -388,3 +388,35 @@ def get_model_profile(model, input_shape=None, args=(), kwargs=None, print_profi
     if as_string:
         return number_to_string(flops), macs_to_string(macs), params_to_string(params)
     return flops, macs, params
+
+
+# --- per-module aggregation helpers (reference ``profiler.py:1171-1192``) -----------------------------------------------
+def get_module_flops(module):
+    """FLOPs counted under ``module`` including all descendants."""
+    return FlopsProfiler._sum(module, "__flops__")
+
+
+def get_module_macs(module):
+    return FlopsProfiler._sum(module, "__macs__")
+
+
+def get_module_duration(module):
+    """Wall time attributed to ``module``; untimed containers (e.g. ``ModuleList``) report the sum of their children."""
+    own = getattr(module, "__duration__", 0.0) or 0.0
+    return own if own else sum(get_module_duration(c) for c in module.children())
+
+
+def wrapFunc(func, funcFlopCompute):
+    """Wrap a functional op that is invisible to the dispatch-mode counter (a native kernel binding): the wrapper calls
+    ``funcFlopCompute(*args, **kw) -> (flops, macs)`` and reports to whichever profiler is active (reference ``:866``)."""
+    import functools
+
+    @functools.wraps(func)
+    def counted(*args, **kwds):
+        if _ACTIVE:
+            flops, macs = funcFlopCompute(*args, **kwds)
+            add_flops(int(flops), int(macs) if macs else 0)
+        return func(*args, **kwds)
+
+    counted.__wrapped_for_flops__ = func
+    return counted

@@ -120,3 +120,47 @@ def send_recv(send_obj_, peer_stage, send_kind, recv_kind, dynamic=False):
             buf.requires_grad_(True)
         out.append(buf)
     return out[0] if len(out) == 1 else tuple(out)
+
+
+# --- raw tensor send/recv between adjacent stages (reference ``runtime/pipe/p2p.py:46-93``) --------------------------
+_pending = []
+
+
+def can_send_recv() -> bool:
+    """True when the backend has real point-to-point primitives (always, for NCCL ≥ 2.7 and gloo)."""
+    return True
+
+
+def _check_adjacent(src_stage, dest_stage):
+    n = _grid.pipe_parallel_size
+    first, last = 0, n - 1
+    ok = abs(src_stage - dest_stage) == 1 or {src_stage, dest_stage} == {first, last}
+    assert ok, f"Functionality currently limited to send and receive between adjacent ranks only ({src_stage}->{dest_stage})"
+
+
+def send(tensor, dest_stage, async_op=False):
+    """Send ``tensor`` (pre-agreed shape) to the adjacent pipeline stage ``dest_stage``."""
+    _check_adjacent(_grid.get_stage_id(), dest_stage)
+    dst = _grid.stage_to_global(stage_id=dest_stage)
+    if async_op:
+        _pending.append(dist.isend(tensor, dst))
+        return _pending[-1]
+    return dist.send(tensor, dst)
+
+
+def recv(tensor, src_stage, async_op=False):
+    """Receive into ``tensor`` from the adjacent pipeline stage ``src_stage``."""
+    _check_adjacent(src_stage, _grid.get_stage_id())
+    src = _grid.stage_to_global(stage_id=src_stage)
+    if async_op:
+        _pending.append(dist.irecv(tensor, src))
+        return _pending[-1]
+    return dist.recv(tensor, src)
+
+
+def wait():
+    """Complete every outstanding async ``send`` / ``recv``."""
+    while _pending:
+        _pending.pop(0).wait()
+    if torch.cuda.is_available() and dist.get_backend() == "nccl":
+        torch.cuda.current_stream().synchronize()

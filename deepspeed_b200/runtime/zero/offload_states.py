@@ -64,3 +64,30 @@ def reload_optimizer_states(zo, non_blocking=False):
 
 offload_states = offload_optimizer_states
 reload_states = reload_optimizer_states
+
+
+def offload_adam_states(optimizer, device, pin_memory: bool = False, non_blocking: bool = False):
+    """Torch-optimizer flavour (reference ``offload_states.py:19``): moves ``exp_avg`` / ``exp_avg_sq``."""
+    from deepspeed_b200.runtime.utils import offload_adam_states as _impl
+    return _impl(optimizer, device, pin_memory=pin_memory, non_blocking=non_blocking)
+
+
+def reload_adam_states(optimizer, device, non_blocking: bool = False):
+    from deepspeed_b200.runtime.utils import reload_adam_states as _impl
+    return _impl(optimizer, device, non_blocking=non_blocking)
+
+
+def get_state_devices(model, state: OffloadStateTypeEnum):
+    """Devices currently holding ``state`` for a ZeRO engine (reference ``offload_states.py:51``).  ``model`` is the
+    engine (or anything with ``.optimizer`` being the sharded optimizer)."""
+    zo = getattr(model, "optimizer", model)
+    if state == OffloadStateTypeEnum.hp_params:
+        return {zo.master.device} if getattr(zo, "master", None) is not None else set()
+    if state == OffloadStateTypeEnum.lp_params:
+        arena = getattr(zo, "lp_arena", None)
+        return {arena.device} if arena is not None else {p.device for p in model.parameters()}
+    if state in (OffloadStateTypeEnum.lp_grads, OffloadStateTypeEnum.contiguous_grad_buffer):
+        return {zo.grad_arena.device} if getattr(zo, "grad_arena", None) is not None else set()
+    if state == OffloadStateTypeEnum.optim_states:
+        return {t.device for t in zo.flat_opt.state_tensors().values() if torch.is_tensor(t)}
+    raise ValueError(f"unknown offload state {state}")

@@ -183,3 +183,57 @@ def test_functional_config_getters(tmp_path):
     assert CC.get_layer_reduction_params({"layer_reduction": {"enabled": True, "keep_number_layer": 2}}) == {"keep_number_layer": 2}
     de = {"data_efficiency": {"enabled": True, "data_routing": {"random_ltd": {"enabled": True, "x": 1}}}}
     assert DC.get_data_efficiency_enabled(de) and DC.get_random_ltd_params(de) == {"x": 1} and DC.get_data_sampling_num_epochs(de) == 1000
+
+
+def test_autotuning_utils_extra(tmp_path):
+    from deepspeed_b200.autotuning import utils as U
+    d = {"a": {"b": {"c": 3}}, "x": 1}
+    assert U.get_val_by_key(d, "c") == 3 and U.get_val_by_key(d, "nope") is None
+    U.set_val_by_key(d, "c", 9)
+    assert d["a"]["b"]["c"] == 9
+    hf = tmp_path / "hostfile"
+    hf.write_text("worker-0 slots=8\n\n# comment\nworker-1 slots=4\n")
+    assert list(U.fetch_hostfile(str(hf)).items()) == [("worker-0", 8), ("worker-1", 4)]
+    assert U.fetch_hostfile(str(tmp_path / "missing")) is None
+    assert U.validate_ds_config({"zero_optimization": {"stage": 1}})
+    assert not U.validate_ds_config({"zero_optimization": {"stage": 2, "cpu_offload": True, "cpu_offload_params": True}})
+    assert len(U.remove_dupe_dicts([{"a": 1, "b": 2}, {"b": 2, "a": 1}, {"a": 2}])) == 2
+    assert U.prune_configs([{"a": 1, "z": {"k": 1}}, {"a": 1, "z": {"k": 2}}], ["z"]) == [{"a": 1}]
+    assert U.get_tuning_keys({"a": [1, 2], "b": {"c": [1], "d": [3, 4]}}) == ["a", "d"]
+
+
+def test_flops_profiler_module_helpers():
+    import torch
+    from deepspeed_b200.profiling.flops_profiler import profiler as P
+    m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+    prof = P.FlopsProfiler(m)
+    prof.start_profile()
+    calls = []
+    f = P.wrapFunc(lambda x: x * 2, lambda x: (calls.append(1) or 100, 50))
+    f(m(torch.randn(2, 8)))
+    prof.stop_profile()
+    assert P.get_module_flops(m) == prof.get_total_flops() and P.get_module_flops(m) >= 2 * 2 * (8 * 16 + 16 * 4) + 100
+    assert P.get_module_macs(m[0]) == 2 * 8 * 16
+    assert P.get_module_duration(m) >= 0 and calls == [1]
+    prof.end_profile()
+
+
+def test_env_report_helpers():
+    from deepspeed_b200 import env_report as E
+    assert E.human_readable_size(1536) == "1.50 KB"
+    size, warns = E.get_shm_size()
+    assert isinstance(size, str) and isinstance(warns, list)
+    assert E.ninja_installed() in (True, False)
+
+
+def test_model_parallel_region_ops_single_rank():
+    import torch
+    from deepspeed_b200.compression import basic_layer as B
+    x = torch.randn(2, 8, requires_grad=True)
+    for fn in (B.copy_to_model_parallel_region, B.reduce_from_model_parallel_region, B.scatter_to_model_parallel_region,
+               B.gather_from_model_parallel_region):
+        y = fn(x)
+        y.sum().backward()
+        assert torch.equal(y, x)
+    a, b = B.split_tensor_along_last_dim(x, 2, contiguous_split_chunks=True)
+    assert a.shape == (2, 4) and a.is_contiguous()

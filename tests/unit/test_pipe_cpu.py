@@ -143,3 +143,29 @@ def test_pipeline_two_stages_matches_sequential():
 
 def test_pipeline_pp2_dp2_matches_sequential():
     run_distributed(_pipe_train, 4, (2, ), timeout=300)
+
+
+def _raw_p2p():
+    import torch
+    import deepspeed_b200 as ds
+    from deepspeed_b200 import comm as dist
+    from deepspeed_b200.runtime.pipe import p2p
+    from deepspeed_b200.runtime.pipe.topology import PipeDataParallelTopology, PipelineParallelGrid
+    ds.init_distributed()
+    grid = PipelineParallelGrid(PipeDataParallelTopology(num_pp=2, num_dp=1))
+    p2p.init_process_groups(grid)
+    assert p2p.can_send_recv()
+    if grid.get_stage_id() == 0:
+        p2p.send(torch.arange(6.0), 1)
+        p2p.send(torch.ones(3) * 7, 1, async_op=True)
+        p2p.wait()
+    else:
+        a, b = torch.zeros(6), torch.zeros(3)
+        p2p.recv(a, 0)
+        p2p.recv(b, 0, async_op=True)
+        p2p.wait()
+        assert torch.equal(a, torch.arange(6.0)) and torch.equal(b, torch.ones(3) * 7)
+
+
+def test_raw_p2p_send_recv():
+    run_distributed(_raw_p2p, 2)
