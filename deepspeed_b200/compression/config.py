@@ -59,22 +59,85 @@ def get_compression_config(param_dict):
 
 
 # ---- per-technique accessors (reference ``compression/config.py:get_*``) -------------------------------------------------
-def _accessors():
-    names = {"weight_quantization": C.WEIGHT_QUANTIZATION, "activation_quantization": C.ACTIVATION_QUANTIZATION,
-             "sparse_pruning": C.SPARSE_PRUNING, "row_pruning": C.ROW_PRUNING, "head_pruning": C.HEAD_PRUNING,
-             "channel_pruning": C.CHANNEL_PRUNING}
-    out = {}
-    for short, key in names.items():
-        out[f"get_{short}"] = (lambda k: lambda param_dict: _technique(param_dict, k))(key)
-        out[f"get_{short}_shared_parameters"] = (lambda k: lambda param_dict: _technique({k: param_dict}, k)[C.SHARED_PARAMETERS])(key)
-        out[f"get_{short}_different_groups"] = (lambda k: lambda param_dict: _technique({k: param_dict}, k)[C.DIFFERENT_GROUPS])(key)
-    for n, f in out.items():
-        f.__name__ = n
-        f.__doc__ = "``param_dict``: the ``compression_training`` block (``get_<t>``) or the technique's own block (the two others)."
-    return out
+def _shared(key, block):
+    return _technique({key: block}, key)[C.SHARED_PARAMETERS]
 
 
-globals().update(_accessors())
+def _groups(key, block):
+    return _technique({key: block}, key)[C.DIFFERENT_GROUPS]
+
+
+# ``get_<t>(compression_block)`` -> normalised technique; the two others take the technique's own block.
+def get_weight_quantization(param_dict):
+    return _technique(param_dict, C.WEIGHT_QUANTIZATION)
+
+
+def get_weight_quantization_shared_parameters(param_dict):
+    return _shared(C.WEIGHT_QUANTIZATION, param_dict)
+
+
+def get_weight_quantization_different_groups(param_dict):
+    return _groups(C.WEIGHT_QUANTIZATION, param_dict)
+
+
+def get_activation_quantization(param_dict):
+    return _technique(param_dict, C.ACTIVATION_QUANTIZATION)
+
+
+def get_activation_quantization_shared_parameters(param_dict):
+    return _shared(C.ACTIVATION_QUANTIZATION, param_dict)
+
+
+def get_activation_quantization_different_groups(param_dict):
+    return _groups(C.ACTIVATION_QUANTIZATION, param_dict)
+
+
+def get_sparse_pruning(param_dict):
+    return _technique(param_dict, C.SPARSE_PRUNING)
+
+
+def get_sparse_pruning_shared_parameters(param_dict):
+    return _shared(C.SPARSE_PRUNING, param_dict)
+
+
+def get_sparse_pruning_different_groups(param_dict):
+    return _groups(C.SPARSE_PRUNING, param_dict)
+
+
+def get_row_pruning(param_dict):
+    return _technique(param_dict, C.ROW_PRUNING)
+
+
+def get_row_pruning_shared_parameters(param_dict):
+    return _shared(C.ROW_PRUNING, param_dict)
+
+
+def get_row_pruning_different_groups(param_dict):
+    return _groups(C.ROW_PRUNING, param_dict)
+
+
+def get_head_pruning(param_dict):
+    return _technique(param_dict, C.HEAD_PRUNING)
+
+
+def get_head_pruning_shared_parameters(param_dict):
+    return _shared(C.HEAD_PRUNING, param_dict)
+
+
+def get_head_pruning_different_groups(param_dict):
+    return _groups(C.HEAD_PRUNING, param_dict)
+
+
+def get_channel_pruning(param_dict):
+    return _technique(param_dict, C.CHANNEL_PRUNING)
+
+
+def get_channel_pruning_shared_parameters(param_dict):
+    return _shared(C.CHANNEL_PRUNING, param_dict)
+
+
+def get_channel_pruning_different_groups(param_dict):
+    return _groups(C.CHANNEL_PRUNING, param_dict)
 
 
 def get_layer_reduction(param_dict):

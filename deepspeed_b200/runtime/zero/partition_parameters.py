@@ -25,6 +25,8 @@ from torch.nn.modules import module as _nn_module
 from deepspeed_b200 import comm as dist
 from deepspeed_b200.accelerator import get_accelerator
 from deepspeed_b200.utils.logging import logger
+from .gather_handles import (AllGatherCoalescedHandle, AllGatherHandle, AllReduceCoalescedHandle, CUDAQuantizer,  # noqa: F401
+                             MultipleAllGatherHandles, NoGatherCoalescedHandle, NoGatherHandle, QuantizationInfo)
 
 _init_stack: List["Init"] = []
 zero_init_context = 0
@@ -135,10 +137,12 @@ def _attach_methods(p):
     """Per-parameter convenience API mirroring the reference (``param.all_gather()``, ``.partition()``)."""
 
     def all_gather(param_list=None, async_op=False, hierarchy=0):
-        for q in (param_list or [p]):
-            if q.data.numel() == 0:
-                q.data = materialize_full(q)
-                q.ds_status = ZeroParamStatus.AVAILABLE
+        todo = [q for q in (param_list or [p]) if q.data.numel() == 0 and getattr(q, "ds_tensor", None) is not None]
+        if async_op:
+            return all_gather_coalesced(todo)
+        for q in todo:
+            q.data = materialize_full(q)
+            q.ds_status = ZeroParamStatus.AVAILABLE
 
     def partition(param_list=None, hierarchy=0, has_been_updated=False):
         for q in (param_list or [p]):
@@ -159,6 +163,109 @@ def _attach_methods(p):
         "ds_shape": tuple(p.ds_shape),
         "requires_grad": p.requires_grad,
     }
+
+
+@torch.no_grad()
+def all_gather_coalesced(params, quantize=False):
+    """Launch ONE asynchronous all-gather for ``params`` (same process group, same dtype per bucket) and return a handle;
+    ``handle.wait()`` installs the full tensors (reference ``Init._all_gather_dtype`` / ``all_gather_coalesced``)."""
+    params = list(params)
+    for q in params:
+        q.ds_status = ZeroParamStatus.INFLIGHT
+    if not params:
+        return MultipleAllGatherHandles([])
+    by_key = {}
+    for q in params:
+        by_key.setdefault((q.ds_tensor.dtype, id(getattr(q, "ds_group", None))), []).append(q)
+    handles = []
+    for (_, _), bucket in by_key.items():
+        group = getattr(bucket[0], "ds_group", None)
+        world = _world(group)
+        if world == 1:
+            handles.append(NoGatherCoalescedHandle(bucket))
+            continue
+        dev = get_accelerator().current_device_name() if torch.cuda.is_available() else bucket[0].ds_tensor.device
+        local = torch.cat([q.ds_tensor.reshape(-1).to(dev) for q in bucket])
+        if quantize and local.numel() % 8 == 0:
+            info = QuantizationInfo()
+            info.backend = CUDAQuantizer()
+            qv, scales = info.backend.quantize(local)
+            info.partition_sz, info.world_size = local.numel(), world
+            info.quantized_param = torch.empty(world * qv.numel(), dtype=qv.dtype, device=qv.device)
+            info.scale_buffer = torch.empty(world * scales.numel(), dtype=scales.dtype, device=scales.device)
+            work = dist.all_gather_into_tensor(info.quantized_param, qv.reshape(-1), group=group, async_op=True)
+            info.quant_handle = dist.all_gather_into_tensor(info.scale_buffer, scales.reshape(-1), group=group, async_op=True)
+            handles.append(AllGatherCoalescedHandle(work, bucket, None, world, quantization=info))
+            continue
+        flat = torch.empty(world * local.numel(), dtype=local.dtype, device=dev)
+        work = dist.all_gather_into_tensor(flat, local, group=group, async_op=True)
+        parts = [flat.narrow(0, r * local.numel(), local.numel()) for r in range(world)]
+        handles.append(AllGatherCoalescedHandle(work, bucket, parts, world))
+    return handles[0] if len(handles) == 1 else MultipleAllGatherHandles(handles)
+
+
+@torch.no_grad()
+def free_param(param) -> None:
+    """Release the gathered storage of a ZeRO parameter (its slice stays in ``ds_tensor``); reference ``:282``."""
+    assert not getattr(param, "ds_active_sub_modules", None), param.ds_summary()
+    if param.data.is_cuda:
+        param.data.record_stream(torch.cuda.current_stream())
+    param.data = torch.empty(0, dtype=param.dtype, device=param.device)
+    param.ds_status = ZeroParamStatus.NOT_AVAILABLE
+
+
+def get_all_subclasses(cls, include_root=True):
+    """Transitive subclasses of ``cls``."""
+    found, stack = set(), [cls]
+    while stack:
+        for sub in stack.pop().__subclasses__():
+            if sub not in found:
+                found.add(sub)
+                stack.append(sub)
+    if include_root:
+        found.add(cls)
+    return found
+
+
+def _local_device():
+    import os
+    return torch.device(get_accelerator().device_name(int(os.environ.get("LOCAL_RANK", 0)))) if torch.cuda.is_available() \
+        else torch.device("cpu")
+
+
+def zero_wrapper_for_fp_tensor_constructor(fn, target_fp_dtype):
+    """Wrap ``torch.empty``-like constructors so float tensors are born on the local device in ``target_fp_dtype``
+    (reference ``:235``; used while a model is constructed under ``zero.Init(dtype=...)``)."""
+
+    def wrapped_fn(*args, **kwargs):
+        if kwargs.get("device") is None:
+            kwargs["device"] = _local_device()
+        t = fn(*args, **kwargs)
+        if t.is_floating_point():
+            t.data = t.data.to(target_fp_dtype)
+        return t
+
+    return wrapped_fn
+
+
+def get_new_tensor_fn_for_dtype(dtype):
+    """Replacement for ``Tensor.new_tensor``-style class constructors: float results are cast to ``dtype``."""
+
+    def new_tensor(cls, *args, **kwargs):
+        t = torch.empty(0, device=_local_device()).new_empty(*(args or (0, )), **kwargs)
+        return t.to(dtype) if t.is_floating_point() else t
+
+    return new_tensor
+
+
+def print_rank_0(message, debug=False, force=False):
+    if (debug or force) and (not dist.is_initialized() or dist.get_rank() == 0):
+        print(message)
+
+
+def debug_rank0(msg):
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        logger.debug(msg)
 
 
 @torch.no_grad()
@@ -383,3 +490,8 @@ def register_external_parameter(module: nn.Module, parameter: nn.Parameter):
 def unregister_external_parameter(module: nn.Module, parameter: nn.Parameter):
     if hasattr(module, "_external_params"):
         module._external_params.pop(id(parameter), None)
+
+
+# the reference's name for the machinery ``Init`` derives from (``partition_parameters.py:302``): here construction-time
+# sharding is driven by torch's module/parameter registration hooks, so ``Init`` itself is that base
+InsertPostInitMethodToModuleSubClasses = Init

@@ -79,3 +79,63 @@ def _stage3():
 
 def test_stage3_class_and_coordinator():
     run_distributed(_stage3, 2)
+
+
+def _async_param_gather():
+    import torch
+    import deepspeed_b200 as ds
+    from deepspeed_b200.runtime.zero import partition_parameters as PP
+    ds.init_distributed()
+    torch.manual_seed(0)
+    with ds.zero.Init():
+        m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Linear(32, 8))
+    ref = [PP.materialize_full(p).clone() for p in m.parameters()]
+    ps = list(m.parameters())
+    assert all(p.data.numel() == 0 for p in ps)
+    h = ps[0].all_gather(param_list=ps, async_op=True)
+    assert all(p.ds_status == PP.ZeroParamStatus.INFLIGHT for p in ps)
+    h.wait()
+    h.wait()  # idempotent
+    for p, r in zip(ps, ref):
+        assert p.ds_status == PP.ZeroParamStatus.AVAILABLE and torch.equal(p.data, r)
+        PP.free_param(p)
+        assert p.data.numel() == 0 and p.ds_status == PP.ZeroParamStatus.NOT_AVAILABLE
+    # int8 quantised gather (ZeRO++ qwZ): close to the exact tensors
+    big = [p for p in ps if p.ds_tensor.numel() % 8 == 0]
+    hq = PP.all_gather_coalesced(big, quantize=True)
+    hq.wait()
+    for p in big:
+        r = ref[[id(x) for x in ps].index(id(p))]
+        assert (p.data.float() - r.float()).abs().max() <= r.abs().max() / 127 + 1e-6
+
+
+def test_async_param_gather_handles():
+    from tests.common import run_distributed
+    run_distributed(_async_param_gather, 2)
+
+
+def test_partition_parameter_helpers():
+    import torch
+    from deepspeed_b200.runtime.zero import partition_parameters as PP
+
+    class A:
+        pass
+
+    class B(A):
+        pass
+
+    class C(B):
+        pass
+
+    assert PP.get_all_subclasses(A) == {A, B, C} and PP.get_all_subclasses(A, include_root=False) == {B, C}
+    mk = PP.zero_wrapper_for_fp_tensor_constructor(torch.ones, torch.bfloat16)
+    assert mk(3).dtype == torch.bfloat16 and mk(3, dtype=torch.int32).dtype == torch.int32
+    nt = PP.get_new_tensor_fn_for_dtype(torch.float16)
+    assert nt(torch.Tensor, (2, 3)).dtype == torch.float16
+    q = PP.CUDAQuantizer()
+    g = q._groups_for(32000)
+    assert 32000 % (8 * g) == 0 and 32000 / g <= 16000
+    x = torch.randn(32000)
+    qv, sc = q.quantize(x)
+    assert (q.dequantize(qv, sc, dtype=torch.float32) - x).abs().max() <= x.abs().max() / 127 + 1e-6
+    assert PP.InsertPostInitMethodToModuleSubClasses is PP.Init
