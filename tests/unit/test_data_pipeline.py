@@ -105,3 +105,67 @@ def test_random_ltd_wrapper_and_scheduler():
     sched.update_seq(3)
     assert sched.get_current_seq() == 10
     assert all(".random_ltd_layer" not in k for k in save_without_random_ltd(model))
+
+
+def _load_reference_indexed_dataset():
+    import importlib.util
+    import os
+    for root in ("/root/reference/deepspeed", os.path.join(os.path.dirname(__file__), "..", "..", "baseline", "_ref", "deepspeed")):
+        f = os.path.join(root, "runtime", "data_pipeline", "data_sampling", "indexed_dataset.py")
+        if os.path.exists(f):
+            spec = importlib.util.spec_from_file_location("_ref_indexed_dataset", f)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+    return None
+
+
+def test_indexed_dataset_formats_and_interop(tmp_path):
+    import numpy as np
+    import torch
+    from deepspeed_b200.runtime.data_pipeline.data_sampling import indexed_dataset as I
+    samples = [np.arange(5), np.arange(3) + 10, np.arange(7) + 100]
+    # --- legacy TNTIDX: lazy + cached readers
+    pre = str(tmp_path / "legacy")
+    b = I.make_builder(I.data_file_path(pre), impl="cached", dtype=np.int32)
+    for s in samples:
+        b.add_item(torch.from_numpy(s))
+        b.end_document()
+    b.finalize(I.index_file_path(pre))
+    assert I.infer_dataset_impl(pre) == "cached" and I.dataset_exists(pre, "cached")
+    lazy = I.make_dataset(pre, "lazy")
+    assert len(lazy) == 3 and all(np.array_equal(lazy[i], s) for i, s in enumerate(samples))
+    assert [a.tolist() for a in lazy[0:2]] == [s.tolist() for s in samples[:2]]
+    cached = I.make_dataset(pre, "infer")
+    assert isinstance(cached, I.IndexedCachedDataset) and cached.supports_prefetch
+    cached.prefetch([2, 0])
+    assert np.array_equal(cached[2], samples[2]) and np.array_equal(cached[0], samples[0])
+    # --- Megatron MMIDIDX written here
+    meg = str(tmp_path / "meg")
+    b = I.make_builder(I.data_file_path(meg), impl="mmap", dtype=np.uint16, fmt="megatron")
+    for s in samples:
+        b.add_item(s)
+        b.end_document()
+    b.finalize(I.index_file_path(meg))
+    ds = I.make_dataset(meg, "infer")
+    assert ds.dtype == np.uint16 and all(np.array_equal(ds[i], s) for i, s in enumerate(samples))
+    assert I.code(np.int64) == 5 and I.code(torch.int16) == 3 and I.create_doc_idx([3, 0, 2, 0]) == [0, 2, 4]
+    p, tot = I.get_pointers_with_total([2, 3, 4], 4, np.int64)
+    assert p.tolist() == [0, 8, 20] and tot == 36
+    # --- cross-check both directions against the reference implementation when its source is around
+    R = _load_reference_indexed_dataset()
+    if R is None:
+        return
+    rds = R.MMapIndexedDataset(meg, skip_warmup=True)
+    assert len(rds) == 3 and all(np.array_equal(rds[i], s) for i, s in enumerate(samples))
+    assert rds.doc_idx.tolist() == ds.doc_idx.tolist()
+    theirs = str(tmp_path / "theirs")
+    rb = R.MMapIndexedDatasetBuilder(R.data_file_path(theirs), dtype=np.int32)
+    for s in samples:
+        rb.add_item(torch.from_numpy(s))
+        rb.end_document()
+    rb.finalize(R.index_file_path(theirs))
+    mine = I.MMapIndexedDataset(theirs)
+    assert mine.dtype == np.int32 and all(np.array_equal(mine[i], s) for i, s in enumerate(samples))
+    rl = R.IndexedDataset(pre)
+    assert all(np.array_equal(rl[i], s) for i, s in enumerate(samples))
