@@ -9,6 +9,9 @@ This script is copied next to every checkpoint (like the reference's ``utils/zer
 API parity: ``get_fp32_state_dict_from_zero_checkpoint``, ``convert_zero_checkpoint_to_fp32_state_dict``,
 ``load_state_dict_from_zero_checkpoint``.
 
+Checkpoints written by upstream DeepSpeed (``param_shapes`` + ``single_partition_of_fp32_groups`` / ``fp32_flat_groups``)
+are recognised too and consolidated by the same entry points, so existing runs can be converted with this tool.
+
 Layout read (see ``runtime/checkpointing.py``): every DP rank's ``*_optim_states.pt`` holds ``fp32_flat`` — its
 slice of each *unit* (unit u occupies ``[arena_offset, arena_offset+shard_numel)``); the unit's full flat
 buffer is the rank-order concatenation of those slices and ``ds_b200_layout`` in the model-states file lists
@@ -24,8 +27,16 @@ from collections import OrderedDict
 import torch
 
 
-def _natural(s):
-    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+def atoi(text):
+    return int(text) if text.isdigit() else text
+
+
+def natural_keys(text):
+    """Sort key under which ``rank_10`` follows ``rank_9``."""
+    return [atoi(t) for t in re.split(r"(\d+)", text)]
+
+
+_natural = natural_keys
 
 
 def _resolve_tag(checkpoint_dir, tag):
@@ -81,12 +92,179 @@ def _unit_flats(layout, shards, key="fp32_flat", sub=None):
         yield u, torch.cat(parts)
 
 
+# ---- upstream-DeepSpeed checkpoint layout -------------------------------------------------------------------------------
+class zero_model_state:
+    """What a ``*_model_states.pt`` of the upstream layout contributes to consolidation."""
+
+    def __init__(self, buffers, param_shapes, shared_params, ds_version, frozen_param_shapes, frozen_param_fragments):
+        self.buffers, self.param_shapes, self.shared_params, self.ds_version = buffers, param_shapes, shared_params, ds_version
+        self.frozen_param_shapes, self.frozen_param_fragments = frozen_param_shapes, frozen_param_fragments
+
+
+def get_checkpoint_files(checkpoint_dir, glob_pattern):
+    return _files(checkpoint_dir, glob_pattern)
+
+
+def get_optim_files(checkpoint_dir):
+    return get_checkpoint_files(checkpoint_dir, "*_optim_states.pt")
+
+
+def get_model_state_files(checkpoint_dir):
+    return get_checkpoint_files(checkpoint_dir, "*_model_states.pt")
+
+
+def get_model_state_file(checkpoint_dir, zero_stage):
+    if not os.path.isdir(checkpoint_dir):
+        raise FileNotFoundError(f"Directory '{checkpoint_dir}' doesn't exist")
+    name = "mp_rank_00_model_states.pt" if zero_stage <= 2 else "zero_pp_rank_0_mp_rank_00_model_states.pt"
+    f = os.path.join(checkpoint_dir, name)
+    if not os.path.exists(f):
+        raise FileNotFoundError(f"can't find model states file at '{f}'")
+    return f
+
+
+def parse_model_states(files):
+    out = []
+    for f in files:
+        sd = _load(f)
+        if "buffer_names" not in sd:
+            raise ValueError(f"{f} is not a model state checkpoint")
+        names = set(sd["buffer_names"])
+        out.append(zero_model_state(buffers={k: v.float() for k, v in sd["module"].items() if k in names},
+                                    param_shapes=sd["param_shapes"],
+                                    shared_params=[[k, v] for k, v in (sd.get("shared_params") or {}).items()],
+                                    ds_version=sd.get("ds_version"), frozen_param_shapes=sd.get("frozen_param_shapes"),
+                                    frozen_param_fragments=sd.get("frozen_param_fragments")))
+    return out
+
+
+def parse_optim_states(files, ds_checkpoint_dir):
+    """-> ``(zero_stage, world_size, per-rank list of fp32 flat groups)``."""
+    osds = []
+    for f in files:
+        osd = torch.load(f, map_location="cpu", mmap=True, weights_only=False)["optimizer_state_dict"]
+        osd.pop("optimizer_state_dict", None)  # moments are not needed, only the fp32 master weights
+        osds.append(osd)
+    if "zero_stage" not in osds[0]:
+        raise ValueError(f"{files[0]} is not a zero checkpoint")
+    stage, world = osds[0]["zero_stage"], osds[0]["partition_count"]
+    world = max(world) if isinstance(world, (list, tuple)) else world
+    if world != len(files):
+        raise ValueError(f"Expected {world} of '*_optim_states.pt' under '{ds_checkpoint_dir}' but found {len(files)} files. "
+                         "Possibly due to an overwrite of an old checkpoint, or a checkpoint didn't get saved by one or "
+                         "more processes.")
+    key = {1: "single_partition_of_fp32_groups", 2: "single_partition_of_fp32_groups", 3: "fp32_flat_groups"}.get(stage)
+    if key is None:
+        raise ValueError(f"unknown zero stage {stage}")
+    return stage, world, [o[key] for o in osds]
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    return n
+
+
+def zero3_partitioned_param_info(unpartitioned_numel, world_size):
+    """(elements each rank holds, padding on the last rank) of a stage-3 parameter."""
+    per = -(-unpartitioned_numel // world_size)
+    return per, per * world_size - unpartitioned_numel
+
+
+class GatheredTensor:
+    """Deferred stage-3 parameter: remembers where its slice sits in every rank's (virtually concatenated) flat groups and
+    assembles the full tensor only on ``contiguous()`` so consolidation can stream shard by shard."""
+
+    def __init__(self, flat_groups, flat_groups_offset, offset, partitioned_numel, shape):
+        self.flat_groups, self.flat_groups_offset = flat_groups, flat_groups_offset
+        self.offset, self.partitioned_numel, self.shape = offset, partitioned_numel, torch.Size(shape)
+        self.dtype = flat_groups[0][0].dtype
+
+    def _rank_slice(self, groups):
+        lo, hi = self.offset, self.offset + self.partitioned_numel
+        bounds = self.flat_groups_offset
+        pieces = []
+        for g, t in enumerate(groups):
+            a, b = max(lo, bounds[g]), min(hi, bounds[g + 1])
+            if a < b:
+                pieces.append(t[a - bounds[g]:b - bounds[g]])
+        return pieces
+
+    def contiguous(self):
+        chunks = [c for groups in self.flat_groups for c in self._rank_slice(groups)]
+        return torch.cat(chunks)[:self.shape.numel()].view(self.shape).contiguous()
+
+    def numel(self):
+        return self.shape.numel()
+
+
+def to_torch_tensor(state_dict, return_empty_tensor=False):
+    """Materialise the ``GatheredTensor`` entries (shared entries materialised once)."""
+    done, out = {}, {}
+    for name, t in state_dict.items():
+        if not isinstance(t, GatheredTensor):
+            out[name] = t
+        elif id(t) in done:
+            out[name] = out[done[id(t)]]
+        else:
+            done[id(t)] = name
+            out[name] = torch.empty(t.shape, dtype=t.dtype) if return_empty_tensor else t.contiguous()
+    return out
+
+
+def _consolidate_upstream(ds_dir, exclude_frozen_parameters, lazy_mode):
+    stage, world, flats = parse_optim_states(get_optim_files(ds_dir), ds_dir)
+    print(f"Detected checkpoint of type zero stage {stage}, world_size: {world}")
+    states = parse_model_states(get_model_state_files(ds_dir))
+    print(f"Parsing checkpoint created by deepspeed=={states[0].ds_version}")
+    out = OrderedDict(states[0].buffers)
+    frozen = states[0].frozen_param_shapes or {}
+    if frozen and not exclude_frozen_parameters:
+        for name, shape in frozen.items():
+            if stage <= 2:
+                out[name] = states[0].frozen_param_fragments[name]
+            else:
+                frags = [st.frozen_param_fragments[name] for st in states]
+                out[name] = torch.cat(frags)[:_numel(shape)].view(shape)
+    if stage <= 2:
+        align = 2 * world
+        for g, shapes in enumerate(states[0].param_shapes):
+            full = torch.cat([rank_groups[g] for rank_groups in flats])
+            off = 0
+            for name, shape in shapes.items():
+                n = _numel(shape)
+                out[name] = full[off:off + n].view(shape)
+                off += n
+            up = lambda x: -(-x // align) * align
+            if up(off) != up(full.numel()):
+                raise ValueError(f"consumed {off} numels out of {full.numel()} - something is wrong")
+    else:
+        shapes = {k: v for d in states[0].param_shapes for k, v in d.items()}
+        bounds = [0]
+        for t in flats[0]:
+            bounds.append(bounds[-1] + t.numel())
+        off = 0
+        for name, shape in shapes.items():
+            per, _ = zero3_partitioned_param_info(_numel(shape), world)
+            out[name] = GatheredTensor(flats, bounds, off, per, shape)
+            off += per
+        if off * world != bounds[-1] * world:
+            raise ValueError(f"consumed {off * world} numels out of {bounds[-1] * world} - something is wrong")
+    for alias, canon in states[0].shared_params:
+        if canon in out:
+            out[alias] = out[canon]
+    return out if lazy_mode else to_torch_tensor(out)
+
+
 def get_fp32_state_dict_from_zero_checkpoint(checkpoint_dir, tag=None, exclude_frozen_parameters=False, lazy_mode=False):
     ds_dir = _resolve_tag(checkpoint_dir, tag)
     ms = _model_state(ds_dir)
     layout = ms.get("ds_b200_layout")
     if layout is None:
-        raise ValueError("checkpoint has no ds_b200_layout: not a deepspeed_b200 ZeRO checkpoint")
+        if "param_shapes" in ms:
+            return _consolidate_upstream(ds_dir, exclude_frozen_parameters, lazy_mode)
+        raise ValueError("checkpoint has neither ds_b200_layout nor param_shapes: not a ZeRO checkpoint")
     shards = [_load(f)["optimizer_state_dict"] for f in get_optim_shards(ds_dir)[0]]
     world = shards[0]["partition_count"]
     if len(shards) != world:

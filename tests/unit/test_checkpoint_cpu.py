@@ -156,3 +156,91 @@ def test_nebula_tiered_engine(tmp_path):
     os.remove(fast / "global_step3" / "mp_rank_00_model_states.pt")
     sd = eng.load(str(fast / "global_step3" / "mp_rank_00_model_states.pt"))
     assert sd["w"].tolist() == [3.0, 3.0, 3.0]
+
+
+def _write_upstream_ckpt(root, stage, world, with_frozen=True):
+    """Hand-build a checkpoint in the upstream DeepSpeed on-disk layout (what ``zero_to_fp32`` of the reference reads)."""
+    import math
+    import os
+    import torch
+    torch.manual_seed(stage)
+    groups = [{"a.weight": torch.Size([5, 3]), "a.bias": torch.Size([5])}, {"b.weight": torch.Size([7, 2])}]
+    full = {k: torch.randn(*shp) for g in groups for k, shp in g.items()}
+    frozen = {"f.weight": torch.randn(4, 3)} if with_frozen else {}
+    buf = {"bn.running_mean": torch.arange(4.0)}
+    tag = "global_step5"
+    d = os.path.join(root, tag)
+    os.makedirs(d)
+    with open(os.path.join(root, "latest"), "w") as f:
+        f.write(tag)
+    if stage <= 2:
+        align = 2 * world
+        per_rank = [[] for _ in range(world)]
+        for g in groups:
+            flat = torch.cat([full[k].reshape(-1) for k in g])
+            padded = align * math.ceil(flat.numel() / align)
+            flat = torch.cat([flat, torch.zeros(padded - flat.numel())])
+            for r, piece in enumerate(flat.chunk(world)):
+                per_rank[r].append(piece.clone())
+        key = "single_partition_of_fp32_groups"
+        model_files = ["mp_rank_00_model_states.pt"]
+    else:
+        # stage 3: every parameter is split over the ranks; a rank's groups are back-to-back slices (a parameter may even
+        # straddle two sub-groups: put the boundary in the middle of a.bias)
+        names = [k for g in groups for k in g]
+        per_rank_flat = []
+        for r in range(world):
+            pieces = []
+            for k in names:
+                n = full[k].numel()
+                per = math.ceil(n / world)
+                padded = torch.cat([full[k].reshape(-1), torch.zeros(per * world - n)])
+                pieces.append(padded[r * per:(r + 1) * per])
+            per_rank_flat.append(torch.cat(pieces))
+        cut = math.ceil(15 / world) + 1
+        per_rank = [[f[:cut].clone(), f[cut:].clone()] for f in per_rank_flat]
+        key = "fp32_flat_groups"
+        model_files = [f"zero_pp_rank_{r}_mp_rank_00_model_states.pt" for r in range(world)]
+    for r in range(world):
+        torch.save({"optimizer_state_dict": {"zero_stage": stage, "partition_count": world, key: per_rank[r],
+                                             "optimizer_state_dict": {"state": {}}}},
+                   os.path.join(d, f"zero_pp_rank_{r}_mp_rank_00_optim_states.pt"))
+    for r, mf in enumerate(model_files):
+        if stage <= 2:
+            frags = dict(frozen)
+        else:
+            frags = {}
+            for k, v in frozen.items():
+                per = math.ceil(v.numel() / world)
+                padded = torch.cat([v.reshape(-1), torch.zeros(per * world - v.numel())])
+                frags[k] = padded[r * per:(r + 1) * per].clone()
+        torch.save({"module": dict(buf), "buffer_names": list(buf), "param_shapes": groups,
+                    "shared_params": {"tied.weight": "a.weight"}, "ds_version": "0.16.5",
+                    "frozen_param_shapes": {k: v.shape for k, v in frozen.items()} or None,
+                    "frozen_param_fragments": frags or None}, os.path.join(d, mf))
+    expect = dict(full, **frozen, **buf)
+    expect["tied.weight"] = full["a.weight"]
+    return expect
+
+
+@pytest.mark.parametrize("stage,world", [(2, 2), (1, 3), (3, 2), (3, 4)])
+def test_zero_to_fp32_reads_upstream_layout(tmp_path, stage, world):
+    import torch
+    from deepspeed_b200.utils import zero_to_fp32 as Z
+    expect = _write_upstream_ckpt(str(tmp_path), stage, world)
+    sd = Z.get_fp32_state_dict_from_zero_checkpoint(str(tmp_path))
+    assert set(sd) == set(expect)
+    for k, v in expect.items():
+        assert torch.equal(sd[k].float(), v.float()), k
+    no_frozen = Z.get_fp32_state_dict_from_zero_checkpoint(str(tmp_path), exclude_frozen_parameters=True)
+    assert "f.weight" not in no_frozen
+    lazy = Z.get_fp32_state_dict_from_zero_checkpoint(str(tmp_path), lazy_mode=True)
+    if stage == 3:
+        assert isinstance(lazy["a.bias"], Z.GatheredTensor) and torch.equal(lazy["a.bias"].contiguous(), expect["a.bias"])
+        assert Z.zero3_partitioned_param_info(15, 4) == (4, 1)
+    out = tmp_path / "out"
+    Z.convert_zero_checkpoint_to_fp32_state_dict(str(tmp_path), str(out))
+    got = torch.load(out / "pytorch_model.bin")
+    assert torch.equal(got["b.weight"], expect["b.weight"])
+    assert Z.natural_keys("rank_10") > Z.natural_keys("rank_9")
+    assert Z.get_model_state_file(str(tmp_path / "global_step5"), stage).endswith("model_states.pt")
