@@ -9,23 +9,4 @@ from .reshape_meg_2d import meg_2d_parallel_map, reshape_meg_2d_parallel, get_mp
 from .reshape_3d_utils import model_3d_desc, get_model_3d_descriptor  # noqa: F401,E402
 from .zero_checkpoint import ZeROCheckpoint  # noqa: F401,E402
 
-
-from dataclasses import dataclass as _dataclass  # noqa: E402
-
-
-@_dataclass
-class SubparamShape:
-    """Shape recipe of a parameter that is the concatenation of sub-parameters with their own TP slicing (universal
-    checkpoint metadata, reference ``checkpoint/universal_checkpoint.py``)."""
-    patterns: list
-    shape: tuple
-    partition_dim: int
-
-
-def enable_universal_checkpoint(param_list):
-    """Attach the universal-checkpoint loader to every parameter (reference ``checkpoint/utils.py``)."""
-    from .universal_checkpoint import load_hp_checkpoint_state
-    import types
-    for p in param_list:
-        p.load_hp_checkpoint_state = types.MethodType(
-            lambda self, folder, tp_rank=0, tp_world_size=1, key="fp32": load_hp_checkpoint_state(folder, key, self.shape, tp_rank, tp_world_size), p)
+from .universal_checkpoint import SubparamShape, enable_universal_checkpoint  # noqa: F401,E402

@@ -6,6 +6,7 @@ overlap its arena shard, slices the overlapping range, and copies it into its fp
 """
 import os
 import re
+from dataclasses import dataclass
 
 import torch
 
@@ -13,21 +14,71 @@ from deepspeed_b200.runtime.zero.units import param_fragments
 from deepspeed_b200.utils.logging import log_dist, logger
 
 
+@dataclass
+class SubparamShape:
+    """Shape recipe of a parameter that is the concatenation of sub-parameters with their own TP slicing (universal
+    checkpoint metadata, reference ``checkpoint/universal_checkpoint.py:16``).  An entry of ``shape`` may be a tuple: the
+    sizes of the fused sub-parameters along ``partition_dim``."""
+    patterns: list
+    shape: tuple
+    partition_dim: int
+
+
+def _tp_slice(t, blob, tp_rank, tp_world_size, tp_dim):
+    """Cut this rank's TP slice out of a merged tensor, honouring the merge metadata ``ds_to_universal`` recorded."""
+    n_sub = blob.get("param_n_sub_params")
+    sub = blob.get("sub_param_shape")
+    dim = blob.get("cat_dim", tp_dim) if tp_dim is None else tp_dim
+    if sub is not None:
+        pd = sub.partition_dim
+        sizes = sub.shape[pd] if isinstance(sub.shape[pd], tuple) else (sub.shape[pd], )
+        full = [sum(d) if isinstance(d, tuple) else d for d in sub.shape]
+        v = t.view(full)
+        cols, at = [], 0
+        for sz in sizes:
+            cols.append(v.narrow(pd, at, sz).chunk(tp_world_size, dim=pd)[tp_rank])
+            at += sz
+        return torch.cat(cols, dim=pd)
+    if n_sub:
+        subs = t.chunk(n_sub, dim=dim)
+        return torch.cat([x.chunk(tp_world_size, dim=dim)[tp_rank] for x in subs], dim=dim)
+    if dim is None:
+        return t  # replicated / averaged parameter
+    return t.chunk(tp_world_size, dim=dim)[tp_rank]
+
+
 def load_hp_checkpoint_state(folder, key, full_shape, tp_rank=0, tp_world_size=1, tp_dim=None, vocab_pad_to=None):
     """Read ``<folder>/<key>.pt`` and return the (TP-sliced, vocab-padded) full-precision tensor."""
     blob = torch.load(os.path.join(folder, f"{key}.pt"), map_location="cpu", weights_only=False)
+    meta = blob if isinstance(blob, dict) else {}
     t = blob["param"] if isinstance(blob, dict) else blob
+    if vocab_pad_to is None and meta.get("vocab_tensor") and tp_world_size >= 1 and len(full_shape) >= 1:
+        # the merged vocabulary was trimmed to the tokenizer size: re-pad so it divides over the TP ranks
+        rows = full_shape[0] * (tp_world_size if (tp_dim in (None, 0) and meta.get("cat_dim", 0) == 0) else 1)
+        vocab_pad_to = rows if rows > t.shape[0] else None
     if vocab_pad_to is not None and t.dim() >= 1 and t.shape[0] < vocab_pad_to:
         pad = torch.zeros(vocab_pad_to - t.shape[0], *t.shape[1:], dtype=t.dtype)
         t = torch.cat([t, pad], 0)
-    if tp_world_size > 1 and tp_dim is not None:
-        t = t.chunk(tp_world_size, dim=tp_dim)[tp_rank]
+    if tp_world_size > 1 and (tp_dim is not None or meta.keys() & {"cat_dim", "param_n_sub_params", "sub_param_shape"}):
+        t = _tp_slice(t, meta, tp_rank, tp_world_size, tp_dim)
     if tuple(t.shape) != tuple(full_shape):
         if t.numel() == torch.Size(full_shape).numel():
             t = t.reshape(full_shape)
         else:
             raise ValueError(f"{folder}: checkpoint shape {tuple(t.shape)} does not match parameter {tuple(full_shape)}")
     return t
+
+
+def enable_universal_checkpoint(param_list):
+    """Attach ``param.load_hp_checkpoint_state(folder, tp_rank, tp_world_size, key="fp32")`` to every parameter
+    (reference ``universal_checkpoint.py:144``)."""
+    import types
+
+    def _bound(self, folder, tp_rank=0, tp_world_size=1, key="fp32"):
+        return load_hp_checkpoint_state(folder, key, self.shape, tp_rank, tp_world_size)
+
+    for p in param_list:
+        p.load_hp_checkpoint_state = types.MethodType(_bound, p)
 
 
 def load_universal_into_optimizer(zo, zero_dir, load_optimizer_states=True, refresh=True):

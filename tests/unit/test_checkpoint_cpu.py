@@ -244,3 +244,98 @@ def test_zero_to_fp32_reads_upstream_layout(tmp_path, stage, world):
     assert torch.equal(got["b.weight"], expect["b.weight"])
     assert Z.natural_keys("rank_10") > Z.natural_keys("rank_9")
     assert Z.get_model_state_file(str(tmp_path / "global_step5"), stage).endswith("model_states.pt")
+
+
+def test_ds_to_universal_staged_pipeline(tmp_path):
+    """Upstream stage-3 checkpoint → fragments → universal; and TP-slice merge rules round-trip through the loader."""
+    import math
+    import os
+    import torch
+    from deepspeed_b200.checkpoint import ds_to_universal as U
+    from deepspeed_b200.checkpoint import constants as K
+    from deepspeed_b200.checkpoint.universal_checkpoint import load_hp_checkpoint_state, SubparamShape, enable_universal_checkpoint
+    # ---- stage 3, upstream layout, dp=3
+    dp = 3
+    shapes = {"w": torch.Size([4, 5]), "b": torch.Size([7])}
+    full = {s: {k: torch.randn(*shp) for k, shp in shapes.items()} for s in ("fp32", "exp_avg", "exp_avg_sq")}
+    src = tmp_path / "global_step1"
+    os.makedirs(src)
+    for r in range(dp):
+        flat = {}
+        for s in full:
+            parts = []
+            for k, shp in shapes.items():
+                n = shp.numel()
+                per = math.ceil(n / dp)
+                padded = torch.cat([full[s][k].reshape(-1), torch.zeros(per * dp - n)])
+                parts.append(padded[r * per:(r + 1) * per])
+            flat[s] = torch.cat(parts)
+        torch.save({"optimizer_state_dict": {"zero_stage": 3, "partition_count": dp, "fp32_flat_groups": [flat["fp32"]],
+                                             "optimizer_state_dict": {"state": {0: {"exp_avg": flat["exp_avg"],
+                                                                                  "exp_avg_sq": flat["exp_avg_sq"]}}}}},
+                   src / f"zero_pp_rank_{r}_mp_rank_00_optim_states.pt")
+        torch.save({"module": {}, "buffer_names": [], "param_shapes": [shapes], "shared_params": {}, "ds_version": "0.16.5"},
+                   src / f"zero_pp_rank_{r}_mp_rank_00_model_states.pt")
+    out = tmp_path / "universal"
+    U.main(U.parse_arguments(["--input_folder", str(src), "--output_folder", str(out)]))
+    for s in full:
+        for k, shp in shapes.items():
+            got = load_hp_checkpoint_state(str(out / "zero" / k), s, shp)
+            assert torch.equal(got, full[s][k]), (s, k)
+    assert not (out / "tmp").exists() and U.dp_index_to_str(3) == "03"
+    # ---- TP merge rules: write per-(tp, dp) fragments by hand, merge, then re-slice with the loader
+    tp, tmp2, dst = 2, str(tmp_path / "frags"), str(tmp_path / "merged")
+    info = {K.UNIVERSAL_CHECKPOINT_INFO: {}}
+    rules = {K.TP_REPLICATED_PARAMETER_PATTERNS: [r"ln\."], K.PARAMETER_WITH_ROW_PARALLELISM_PATTERNS: [r"row\."],
+             K.PARAMETER_WITH_2_SUB_PARAMS_CAT_DIM_0: [r"glu\."], K.VOCABULARY_PARAMETER_PATTERNS: [r"emb\."],
+             K.ORIGINAL_VOCAB_SIZE: 5,
+             K.PARAMETER_WITH_SUB_PARAMS: [dict(patterns=[r"qkv\."], shape=((4, 2, 2), 3), partition_dim=0)]}
+
+    class _Ck:
+
+        def get_checkpoint_info(self, key=None):
+            return rules
+
+    fulls = {"ln.w": torch.randn(6), "row.w": torch.randn(3, 8), "col.w": torch.randn(8, 3), "glu.w": torch.randn(8, 3),
+             "emb.w": torch.cat([torch.randn(5, 4), torch.zeros(1, 4)]), "qkv.w": torch.randn(8, 3)}
+
+    def tp_slices(name, t):
+        if name.startswith("ln"):
+            return [t, t]
+        if name.startswith("row"):
+            return list(t.chunk(2, dim=1))
+        if name.startswith("glu"):
+            a, b = t.chunk(2, 0)
+            return [torch.cat([a.chunk(2, 0)[r], b.chunk(2, 0)[r]]) for r in range(2)]
+        if name.startswith("qkv"):
+            q, k, v = t.split([4, 2, 2], 0)
+            return [torch.cat([x.chunk(2, 0)[r] for x in (q, k, v)]) for r in range(2)]
+        return list(t.chunk(2, dim=0))
+
+    for name, t in fulls.items():
+        for r, sl in enumerate(tp_slices(name, t)):
+            flat = sl.reshape(-1)
+            half = flat.numel() // 2
+            for st in ("fp32", "exp_avg", "exp_avg_sq"):
+                U.dump_param_fragment(tmp2, r, 0, st, flat, name, 0, half)
+                U.dump_param_fragment(tmp2, r, 1, st, flat, name, half, flat.numel() - half)
+            U.dump_param_fragment(tmp2, r, 0, "step", torch.tensor(7.0), name, 0, 0)
+    unmatched = set()
+    for name, t in fulls.items():
+        sl_shape = tp_slices(name, t)[0].shape
+        unmatched |= U.merge_tp_slices(_Ck(), dst, tmp2, tp, (name, sl_shape)) if name == "ln.w" else set()
+        if name != "ln.w":
+            U.merge_tp_slices(_Ck(), dst, tmp2, tp, (name, sl_shape))
+    for name, t in fulls.items():
+        merged = torch.load(os.path.join(dst, name, "fp32.pt"), weights_only=False)
+        want = t[:5] if name == "emb.w" else t
+        assert torch.equal(merged["param"], want), name
+        # loading back at tp=2 recovers each rank's slice
+        for r, sl in enumerate(tp_slices(name, t)):
+            got = load_hp_checkpoint_state(os.path.join(dst, name), "fp32", sl.shape, tp_rank=r, tp_world_size=2)
+            assert torch.equal(got, sl), (name, r)
+    assert float(torch.load(os.path.join(dst, "ln.w", "step.pt"), weights_only=False)) == 7.0
+    p = torch.nn.Parameter(torch.zeros(8, 3))
+    enable_universal_checkpoint([p])
+    assert torch.equal(p.load_hp_checkpoint_state(os.path.join(dst, "col.w")), fulls["col.w"])
+    assert SubparamShape(patterns=["x"], shape=(1, ), partition_dim=0).partition_dim == 0
