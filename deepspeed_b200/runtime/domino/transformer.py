@@ -14,6 +14,109 @@ from deepspeed_b200 import comm as dist
 from deepspeed_b200.ops.kernels import transformer_ops as T
 
 
+import enum
+
+
+def is_rank_0():
+    return not dist.is_initialized() or dist.get_rank() == 0
+
+
+class DominoModule(nn.Module):
+    """Common base of the Domino building blocks (reference ``transformer.py:18``)."""
+
+
+class LayerType(enum.Enum):
+    encoder = 1
+    decoder = 2
+
+
+class AttnType(enum.Enum):
+    self_attn = 1
+    cross_attn = 2
+
+
+class AttnMaskType(enum.Enum):
+    padding = 1
+    causal = 2
+
+
+class ModelType(enum.Enum):
+    encoder_or_decoder = 1
+    encoder_and_decoder = 2
+
+
+# in-flight backward all-reduces, keyed by "<layer>_<half>[_<stage>]": launched by ``_CopyToModelParallelRegionA.backward``,
+# drained by the matching ``NoOper.backward`` that autograd reaches only after the OTHER half's backward math was issued
+handle_dic = {}
+
+
+class NoOper(torch.autograd.Function):
+    """Identity; in backward it waits for the async gradient all-reduce registered under ``h_id``."""
+
+    @staticmethod
+    def forward(ctx, input_, dic_, h_id):
+        ctx.dic, ctx.h_id = dic_, h_id
+        return input_.view_as(input_)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        h = ctx.dic.pop(ctx.h_id, None)
+        if h is not None:
+            h.wait()
+        return grad_output, None, None
+
+
+def no_oper(input_, dic_, h_id):
+    return NoOper.apply(input_, dic_, h_id)
+
+
+def _group_of(mpu_or_group):
+    if mpu_or_group is None or not hasattr(mpu_or_group, "get_tensor_model_parallel_group"):
+        return mpu_or_group
+    return mpu_or_group.get_tensor_model_parallel_group()
+
+
+class _CopyToModelParallelRegionA(torch.autograd.Function):
+    """Identity forward; backward STARTS the all-reduce of the input gradient and parks the handle in ``dic_[h_id]``
+    (``mpu`` may be a Megatron-style mpu or a process group)."""
+
+    @staticmethod
+    def forward(ctx, mpu, input_, dic_, h_id):
+        ctx.group, ctx.dic, ctx.h_id = _group_of(mpu), dic_, h_id
+        return input_.view_as(input_)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.group is None or dist.get_world_size(ctx.group) == 1:
+            return None, grad_output, None, None
+        g = grad_output.contiguous()
+        ctx.dic[ctx.h_id] = dist.all_reduce(g, group=ctx.group, async_op=True)
+        return None, g, None, None
+
+
+def copy_to_tensor_model_parallel_region_a(mpu, input_, dic_, h_id):
+    return _CopyToModelParallelRegionA.apply(mpu, input_, dic_, h_id)
+
+
+class CoreAttention(DominoModule):
+    """Causal SDPA over this rank's heads: ``[b, np, sq, hn]`` in, ``[sq, b, hp]`` out (reference ``:104``)."""
+
+    def __init__(self, config, layer_number, mpu, attn_mask_type=AttnMaskType.causal):
+        super().__init__()
+        self.layer_number = max(1, layer_number)
+        self.att_dropout_p = getattr(config, "attention_dropout", 0.0)
+        self.attn_mask_type = attn_mask_type
+        world = mpu.get_tensor_model_parallel_world_size() if mpu is not None else 1
+        self.hidden_size_per_partition = config.kv_channels * config.num_attention_heads // world
+
+    def forward(self, query_layer, key_layer, value_layer, attention_mask=None):
+        ctx = F.scaled_dot_product_attention(query_layer, key_layer, value_layer,
+                                             dropout_p=self.att_dropout_p if self.training else 0.0,
+                                             is_causal=self.attn_mask_type == AttnMaskType.causal)
+        sq, b = ctx.shape[2], ctx.shape[0]
+        return ctx.permute(2, 0, 1, 3).reshape(sq, b, self.hidden_size_per_partition)
+
+
 class _AsyncAllReduce(torch.autograd.Function):
     """Forward: start an async all-reduce and stash the handle; backward: plain identity (input grads of a
     row-parallel output are already complete)."""
@@ -60,7 +163,7 @@ class _CopyToTP(torch.autograd.Function):
         return g, None
 
 
-class ShardedAttention(nn.Module):
+class ShardedAttention(DominoModule):
 
     def __init__(self, hidden, heads, tp_group):
         super().__init__()
@@ -72,15 +175,17 @@ class ShardedAttention(nn.Module):
         self.dense = nn.Linear(self.local_heads * self.head_dim, hidden, bias=False)
         self.dense_bias = nn.Parameter(torch.zeros(hidden))
 
-    def forward(self, x):
+    def forward(self, x, grad_sync=None):
         B, S, _ = x.shape
-        qkv = self.qkv(_CopyToTP.apply(x, self.group))
+        x = _CopyToTP.apply(x, self.group) if grad_sync is None else \
+            copy_to_tensor_model_parallel_region_a(self.group, x, handle_dic, grad_sync)
+        qkv = self.qkv(x)
         q, k, v = (t.reshape(B, S, self.local_heads, self.head_dim).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
         o = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, S, -1)
         return self.dense(o)  # partial sum: caller all-reduces
 
 
-class ShardedMLP(nn.Module):
+class ShardedMLP(DominoModule):
 
     def __init__(self, hidden, ffn, tp_group):
         super().__init__()
@@ -90,11 +195,13 @@ class ShardedMLP(nn.Module):
         self.fc2 = nn.Linear(ffn // self.tp, hidden, bias=False)
         self.fc2_bias = nn.Parameter(torch.zeros(hidden))
 
-    def forward(self, x):
-        return self.fc2(F.gelu(self.fc1(_CopyToTP.apply(x, self.group)), approximate="tanh"))
+    def forward(self, x, grad_sync=None):
+        x = _CopyToTP.apply(x, self.group) if grad_sync is None else \
+            copy_to_tensor_model_parallel_region_a(self.group, x, handle_dic, grad_sync)
+        return self.fc2(F.gelu(self.fc1(x), approximate="tanh"))
 
 
-class DominoTransformerLayer(nn.Module):
+class DominoTransformerLayer(DominoModule):
 
     def __init__(self, hidden_size, num_attention_heads, ffn_hidden_size=None, tp_group=None, layernorm_epsilon=1e-5):
         super().__init__()
@@ -110,16 +217,24 @@ class DominoTransformerLayer(nn.Module):
         if x1 is None:
             return self._plain(hidden_states)
         h0, h1 = [], []
+        k = id(self)
+        # Backward overlap: each half's input-gradient all-reduce is STARTED in ``copy_to_..._a.backward`` and WAITED in
+        # the ``no_oper`` node created here, i.e. before either half's compute nodes -- autograd replays nodes in reverse
+        # creation order, so the other half's backward GEMMs are issued between the start and the wait.
+        n0 = no_oper(self.input_layernorm(x0), handle_dic, f"{k}_0_attn")
+        n1 = no_oper(self.input_layernorm(x1), handle_dic, f"{k}_1_attn")
         # ---- attention: a0 reduce overlaps attention of half 1 ----
-        a0 = _AsyncAllReduce.apply(self.self_attention(self.input_layernorm(x0)), self.group, h0)
-        a1 = _AsyncAllReduce.apply(self.self_attention(self.input_layernorm(x1)), self.group, h1)
+        a0 = _AsyncAllReduce.apply(self.self_attention(n0, f"{k}_0_attn"), self.group, h0)
+        a1 = _AsyncAllReduce.apply(self.self_attention(n1, f"{k}_1_attn"), self.group, h1)
         a0 = _WaitHandle.apply(a0, h0)
         r0 = x0 + a0 + self.self_attention.dense_bias
+        p0 = no_oper(self.post_attention_layernorm(r0), handle_dic, f"{k}_0_mlp")
         # ---- MLP of half 0 overlaps the a1 reduce ----
-        m0 = _AsyncAllReduce.apply(self.mlp(self.post_attention_layernorm(r0)), self.group, h0)
+        m0 = _AsyncAllReduce.apply(self.mlp(p0, f"{k}_0_mlp"), self.group, h0)
         a1 = _WaitHandle.apply(a1, h1)
         r1 = x1 + a1 + self.self_attention.dense_bias
-        m1 = _AsyncAllReduce.apply(self.mlp(self.post_attention_layernorm(r1)), self.group, h1)
+        p1 = no_oper(self.post_attention_layernorm(r1), handle_dic, f"{k}_1_mlp")
+        m1 = _AsyncAllReduce.apply(self.mlp(p1, f"{k}_1_mlp"), self.group, h1)
         m0 = _WaitHandle.apply(m0, h0)
         o0 = r0 + m0 + self.mlp.fc2_bias
         m1 = _WaitHandle.apply(m1, h1)
@@ -137,7 +252,7 @@ class DominoTransformerLayer(nn.Module):
         return r + m + self.mlp.fc2_bias
 
 
-class DominoTransformer(nn.Module):
+class DominoTransformer(DominoModule):
 
     def __init__(self, num_layers, hidden_size, num_attention_heads, ffn_hidden_size=None, tp_group=None):
         super().__init__()

@@ -119,6 +119,27 @@ def _domino_worker():
     torch.testing.assert_close(ya, yb, atol=1e-5, rtol=1e-4)
     ya.sum().backward(), yb.sum().backward()
     torch.testing.assert_close(xa.grad, xb.grad, atol=1e-5, rtol=1e-4)
+    # every async backward all-reduce was drained by its NoOper node; weight grads match the dense slice
+    from deepspeed_b200.runtime.domino import transformer as D
+    assert not D.handle_dic
+    torch.testing.assert_close(tp.mlp.fc1.weight.grad, full.mlp.fc1.weight.grad[r * f:(r + 1) * f], atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(tp.input_layernorm.weight.grad, full.input_layernorm.weight.grad, atol=1e-5, rtol=1e-4)
+
+    class _Cfg:
+        attention_dropout, kv_channels, num_attention_heads = 0.0, 8, 4
+
+    class _Mpu:
+        get_tensor_model_parallel_world_size = staticmethod(lambda: w)
+        get_tensor_model_parallel_group = staticmethod(lambda: td.group.WORLD)
+
+    core = D.CoreAttention(_Cfg, 1, _Mpu)
+    q = torch.randn(2, 4 // w, 5, 8)
+    assert core(q, q, q, None).shape == (5, 2, 32 // w)
+    assert D.AttnMaskType.causal.value == 2 and D.LayerType.encoder.value == 1 and D.ModelType.encoder_or_decoder.value == 1
+    t = torch.ones(3, requires_grad=True)
+    y = D.copy_to_tensor_model_parallel_region_a(_Mpu, D.no_oper(t * 1.0, D.handle_dic, "k"), D.handle_dic, "k")
+    y.sum().backward()
+    assert torch.equal(t.grad, torch.full((3, ), float(w))) and not D.handle_dic
 
 
 def test_domino_tp2_matches_dense():
