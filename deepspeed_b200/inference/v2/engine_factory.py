@@ -123,27 +123,6 @@ def build_engine_from_model(module, engine_config=None, dtype=None, device=None)
 
 
 def build_engine_from_ds_checkpoint(path: str, engine_config=None, debug_level=None) -> InferenceEngineV2:
-    """Reload shards written by ``InferenceEngineV2.serialize``."""
-    engine_config = _as_cfg(engine_config)
-    group, tp, rank = _tp(engine_config)
-    blob = torch.load(os.path.join(path, f"params_rank_{rank}.pt"), map_location="cpu", weights_only=False)
-    spec = ArchSpec(**blob["spec"])
-    dev = get_accelerator().current_device_name()
-    ref = blob["globals"]["embed_w"]
-    model = RaggedTransformer(spec, tp_group=group, tp_size=tp, tp_rank=rank, dtype=ref.dtype, device=dev)
-    for k, v in blob["globals"].items():
-        setattr(model, k, v.to(dev) if v is not None else None)
-    for lw, d in zip(model.layers, blob["layers"]):
-        for s, v in d.items():
-            if isinstance(v, list):
-                v = [x.to(dev) for x in v]
-            elif isinstance(v, torch.Tensor):
-                v = v.to(dev)
-            setattr(lw, s, v)
-    return InferenceEngineV2(model, engine_config, tp_group=group)
-
-
-def build_engine_from_ds_checkpoint(path: str, engine_config=None, debug_level=None) -> InferenceEngineV2:
     """Re-create an engine from ``InferenceEngineV2.serialize(path)`` output: the per-rank, already sharded / fused weights
     are loaded as they are (no checkpoint re-mapping)."""
     import torch
@@ -153,7 +132,11 @@ def build_engine_from_ds_checkpoint(path: str, engine_config=None, debug_level=N
     from deepspeed_b200 import comm as dist
     tp = engine_config.tensor_parallel.tp_size
     rank = dist.get_rank() % tp if (dist.is_initialized() and tp > 1) else 0
-    blob = torch.load(os.path.join(path, f"params_rank_{rank}.pt"), map_location="cpu", weights_only=False)
+    from .model_implementations.flat_model_helpers import make_param_filename
+    f = make_param_filename(path, rank, tp)
+    if not os.path.exists(f):
+        f = os.path.join(path, f"params_rank_{rank}.pt")  # layout written by earlier versions
+    blob = torch.load(f, map_location="cpu", weights_only=False)
     assert blob["tp_size"] == tp, f"checkpoint was serialized for tp_size={blob['tp_size']}, engine config asks for {tp}"
     spec = ArchSpec(**blob["spec"])
     dev = "cuda" if torch.cuda.is_available() else "cpu"

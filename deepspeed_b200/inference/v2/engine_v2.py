@@ -140,4 +140,19 @@ class InferenceEngineV2:
         blob = {"spec": m.spec.__dict__, "tp_size": m.tp_size, "globals": {k: getattr(m, k) for k in
                 ("embed_w", "pos_w", "final_ln_w", "final_ln_b", "lm_head_w", "lm_head_b")},
                 "layers": [{s: getattr(lw, s) for s in lw.__slots__} for lw in m.layers]}
-        torch.save(blob, os.path.join(save_path, f"params_rank_{m.tp_rank}.pt"))
+        from .model_implementations import flat_model_helpers as F
+        torch.save(blob, F.make_param_filename(save_path, m.tp_rank, m.tp_size))
+        # side files (reference layout): per-rank tensor table + the model config, so tools can inspect a serialized model
+        # without unpickling the weights
+        table, off = {}, 0
+        for name, t in m.flat_tensors().items():
+            off = F.pad_to_aligned_offset(off)
+            table[name] = {"offset": off, "shape": list(t.shape), "dtype": str(t.dtype)}
+            off += t.numel() * t.element_size()
+        with open(F.make_metadata_filename(save_path, m.tp_rank, m.tp_size), "w") as f:
+            f.write(F.to_model_metadata(table, policy=type(m).__name__).model_dump_json())
+        if m.tp_rank == 0:
+            import json
+            with open(F.make_model_config_filename(save_path), "w") as f:
+                json.dump({"spec": {k: (v if isinstance(v, (int, float, str, bool, type(None), list, dict)) else str(v))
+                                    for k, v in m.spec.__dict__.items()}, "tp_size": m.tp_size}, f)

@@ -7,7 +7,72 @@ from typing import Dict, Tuple
 
 import torch
 
+from typing import Optional
+
+from deepspeed_b200.runtime.config_utils import DeepSpeedConfigModel
+
 ALIGN = 256  # every tensor starts on a 256-byte boundary (TMA / vector friendly)
+
+
+class TensorMetadata(DeepSpeedConfigModel):
+    """Where one tensor lives in the flat buffer."""
+    dtype: Optional[str] = None
+    shape: Optional[Tuple[int, ...]] = None
+    strides: Optional[Tuple[int, ...]] = None
+    offset: int
+
+
+class ParameterMetadata(DeepSpeedConfigModel):
+    """A parameter = its main tensor + auxiliary tensors (quantisation scales ...)."""
+    core_param: Optional[TensorMetadata] = None
+    aux_params: Dict[str, TensorMetadata] = {}
+
+
+class LayerMetadata(DeepSpeedConfigModel):
+    params: Dict[str, ParameterMetadata] = {}
+
+
+class ModelMetadata(DeepSpeedConfigModel):
+    """``layers``: ``"<i>"`` for transformer layers, ``"non_transformer"`` for embeddings / final norm / unembed."""
+    policy: str = ""
+    layers: Dict[str, LayerMetadata] = {}
+
+
+def make_param_filename(base: str, rank: int, n_ranks: int) -> str:
+    return os.path.join(base, f"params_rank_{rank}_of_{n_ranks}.pt")
+
+
+def make_metadata_filename(base: str, rank: int, n_ranks: int) -> str:
+    return os.path.join(base, f"metadata_rank_{rank}_of_{n_ranks}.json")
+
+
+def make_model_config_filename(base: str) -> str:
+    return os.path.join(base, "ds_model_config.json")
+
+
+def to_model_metadata(meta: dict, policy: str = "") -> ModelMetadata:
+    """Group the flat ``name -> record`` table by layer / parameter (``x.scales`` is an aux tensor of ``x.q``)."""
+    layers: Dict[str, dict] = {}
+    for name, m in meta.items():
+        parts = name.split(".")
+        if parts[0] == "layers" and len(parts) > 2:
+            layer, pname = parts[1], ".".join(parts[2:])
+        else:
+            layer, pname = "non_transformer", name
+        strides, acc = [], 1
+        for d in reversed(m["shape"]):
+            strides.insert(0, acc)
+            acc *= d
+        tm = TensorMetadata(dtype=m["dtype"], shape=tuple(m["shape"]), strides=tuple(strides), offset=m["offset"])
+        params = layers.setdefault(layer, {})
+        if pname.endswith(".scales"):
+            params.setdefault(pname[:-7], {"core": None, "aux": {}})["aux"]["scales"] = tm
+        else:
+            key = pname[:-2] if pname.endswith(".q") else pname
+            params.setdefault(key, {"core": None, "aux": {}})["core"] = tm
+    return ModelMetadata(policy=policy, layers={
+        l: LayerMetadata(params={k: ParameterMetadata(core_param=v["core"], aux_params=v["aux"]) for k, v in ps.items()})
+        for l, ps in layers.items()})
 
 
 def pad_to_aligned_offset(offset: int, alignment: int = ALIGN) -> int:

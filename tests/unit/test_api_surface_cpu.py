@@ -120,6 +120,14 @@ def _ds_ckpt_roundtrip(tmp):
     eng2 = build_engine_from_ds_checkpoint(tmp, sm)
     out = eng2.put([0], [prompt])[0]
     assert torch.allclose(ref, out, atol=1e-6)
+    import json
+    import os
+    from deepspeed_b200.inference.v2.model_implementations import flat_model_helpers as F
+    assert os.path.exists(F.make_param_filename(tmp, 0, 1)) and os.path.exists(F.make_model_config_filename(tmp))
+    md = F.ModelMetadata(**json.load(open(F.make_metadata_filename(tmp, 0, 1))))
+    assert "0" in md.layers and "non_transformer" in md.layers and md.policy == "RaggedTransformer"
+    emb = md.layers["non_transformer"].params["embed_w"].core_param
+    assert emb.shape == (64, 32) and emb.strides == (32, 1) and emb.offset % 256 == 0
     with unwrap_model_for_generation(hf) as m:  # no ZeRO params: plain pass-through
         assert m is hf
 
