@@ -101,3 +101,42 @@ def test_nvme_tooling_sweep_logs_and_param_generation(tmp_path):
     run_job(Job(["echo", "hello"], str(out)))
     assert out.read_text().strip() == "hello"
     assert validate() is True
+
+
+def test_autotuning_scheduler_reservations_and_concurrency(tmp_path):
+    import json
+    import os
+    import threading
+    import time
+    import types
+    from deepspeed_b200.autotuning import scheduler as S
+    n = S.Node("h", 4)
+    a = n.reserve_slots(3)
+    assert a == [0, 1, 2] and n.reserve_slots(2) is None
+    r = S.Reservation(n, a)
+    assert S.include_string([r]) == "h:0,1,2"
+    r.restore_slots()
+    assert n.idle_slots == [0, 1, 2, 3]
+    assert S.get_user() and S.get_job_id()
+    live, peak, lock = [0], [0], threading.Lock()
+
+    def runner(exp, rd):
+        with lock:
+            live[0] += 1
+            peak[0] = max(peak[0], live[0])
+        time.sleep(0.15)
+        with open(os.path.join(rd, "metrics.json"), "w") as f:
+            json.dump({"throughput": exp["num_gpus"] * 10.0 + exp["exp_id"]}, f)
+        with lock:
+            live[0] -= 1
+
+    rm = S.ResourceManager(types.SimpleNamespace(user_script="x.py", user_args=[]), ["localhost"], 4, str(tmp_path), None,
+                           runner=runner)
+    exps = [{"name": f"e{i}", "ds_config": {}, "num_gpus": g, "num_nodes": 1} for i, g in enumerate([2, 2, 4, 1, 8])]
+    rm.schedule_experiments_dicts(exps)
+    rm.run()
+    assert peak[0] == 2  # the two 2-GPU experiments ran side by side; the 4-GPU one had to wait for both
+    assert len(rm.finished) == 5 and "needs 1x8" in rm.finished[4][1]
+    best, val = rm.parse_results("throughput")
+    assert best["name"] == "e2" and val == 42.0
+    assert rm.status() == "localhost (4 idle gpus)"
