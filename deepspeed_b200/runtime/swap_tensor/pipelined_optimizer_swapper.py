@@ -21,3 +21,26 @@ class PipelinedOptimizerSwapper(FlatStateSwapper):
 
     def swap_out_optimizer_state(self, flat_opt, async_swap=True):
         self.flush(flat_opt, wait=not async_swap)
+
+
+class OptimizerSwapOp:
+    """One queued unit of pipelined swap work (reference ``pipelined_optimizer_swapper.py:21``): the ranges being read /
+    written and whether the corresponding aio batch has been waited for."""
+
+    def __init__(self, aio_handle, read_op, param_info, allocated_buffers, state_buffers, num_ops):
+        self.aio_handle, self.read_op, self.param_info = aio_handle, read_op, param_info
+        self.allocated_buffers, self.state_buffers = allocated_buffers, state_buffers
+        self.wait_required = True
+        self.num_ops = num_ops
+
+    def is_parameter(self, parameter):
+        from .optimizer_utils import OptimizerSwapper
+        return OptimizerSwapper.parameter_id(parameter) == self.param_info.param_id
+
+    def wait(self):
+        assert self.wait_required
+        self.aio_handle.wait()
+        self.wait_required = False
+
+
+SYNC_SWAP_IN, ASYNC_SWAP_IN, SYNC_SWAP_OUT, ASYNC_SWAP_OUT = "sync_swap_in", "async_swap_in", "sync_swap_out", "async_swap_out"

@@ -493,3 +493,64 @@ def offload_adam_states(optimizer, device, pin_memory=False, non_blocking=False)
 
 def reload_adam_states(optimizer, device, non_blocking=False):
     offload_adam_states(optimizer, device, pin_memory=False, non_blocking=non_blocking)
+
+
+# ---- misc parity helpers (reference ``runtime/utils.py:53, :453, :1003``) ------------------------------------------------
+graph_cache = {}
+
+
+def graph_process(replay_first_step, func, *args, **kwargs):
+    """Capture ``func(*args)`` (device-only work on static addresses) into a CUDA graph on first use, replay afterwards;
+    keyed by ``func.__name__``.  Without a GPU the function simply runs."""
+    if not torch.cuda.is_available():
+        return func(*args, **kwargs)
+    g = graph_cache.get(func.__name__)
+    if g is not None:
+        g.replay()
+        return
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        func(*args, **kwargs)  # warm-up outside capture: lazy inits, autotune, allocator growth
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        func(*args, **kwargs)
+    graph_cache[func.__name__] = g
+    if replay_first_step:
+        g.replay()
+
+
+def get_grad_zeros(parameters, mpu=None):
+    """Number of exactly-zero gradient elements over ``parameters`` (model-parallel aware: replicated parameters are
+    counted on TP rank 0 only, then summed over the model-parallel group)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    tp_rank = mpu.get_model_parallel_rank() if mpu is not None and hasattr(mpu, "get_model_parallel_rank") else 0
+    total = 0.0
+    for p in parameters:
+        if p.grad is None or getattr(p, "ds_pipe_replicated", False):
+            continue
+        if tp_rank > 0 and not getattr(p, "model_parallel", False) and not getattr(p, "tensor_model_parallel", False):
+            continue
+        total += float(p.grad.numel() - torch.count_nonzero(p.grad))
+    t = torch.tensor([total], dtype=torch.float32,
+                     device="cuda" if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+                     else "cpu")
+    if mpu is not None and dist.is_initialized():
+        dist.all_reduce(t, group=mpu.get_model_parallel_group())
+    return t.item()
+
+
+class TLinear(torch.nn.Linear):
+    """Linear whose weight is stored transposed relative to ``orig_layer`` (``[in, out]`` checkpoints → ``[out, in]``)."""
+
+    def __init__(self, orig_layer, name=""):
+        self.name = name
+        w = orig_layer.weight
+        super().__init__(w.shape[1], w.shape[0], bias=orig_layer.bias is not None, device=w.device, dtype=w.dtype)
+        self.weight.data = w.data.t().contiguous()
+        self.bias = orig_layer.bias
+
+    def forward(self, input):
+        return torch.nn.functional.linear(input, self.weight, self.bias)

@@ -9,6 +9,9 @@ from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
 from deepspeed_b200.runtime.zero.mem_estimator import (  # noqa: F401  (the reference defines these here)
     estimate_zero3_model_states_mem_needs, estimate_zero3_model_states_mem_needs_all_cold,
     estimate_zero3_model_states_mem_needs_all_live)
+from deepspeed_b200.runtime.zero._stage_helpers import (  # noqa: F401,A004
+    input, isclose, lcm, model_to_params, move_to_cpu, print_rank_0, pg_correctness_test, OPTIMIZER_TIMERS, INITIAL_MICRO_STEP_ID)
+from deepspeed_b200.runtime.zero import unwrap_model_for_generation  # noqa: F401,E402
 from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer
 
 

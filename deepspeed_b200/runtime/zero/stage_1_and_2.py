@@ -12,6 +12,8 @@ from deepspeed_b200.runtime.zero.config import DeepSpeedZeroConfig
 from deepspeed_b200.runtime.zero.mem_estimator import (  # noqa: F401  (the reference defines these here)
     estimate_zero2_model_states_mem_needs, estimate_zero2_model_states_mem_needs_all_cold,
     estimate_zero2_model_states_mem_needs_all_live)
+from deepspeed_b200.runtime.zero._stage_helpers import (  # noqa: F401,A004
+    input, split_half_float_double, isclose, lcm, get_alignment_padding, print_rank_msg, model_to_params, move_to_cpu, pg_correctness_test, OPTIMIZER_TIMERS)
 from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer
 
 

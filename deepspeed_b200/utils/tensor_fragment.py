@@ -205,3 +205,26 @@ def map_to_flat_opt_states(flat_hp_tensor, lp_tensors, optim_state, opt_keys):
                 st[key] = buf.narrow(0, offset, lp.numel()).view_as(lp)
             offset += lp.numel()
         optim_state.setdefault(flat_hp_tensor, {})[key] = buf
+
+
+# --- method-style accessors (reference ``tensor_fragment.py:87-130``): the reference binds these on every low-precision
+# parameter (``param.get_full_hp_param()``); ``link_hp_params``-style callers can bind them with ``types.MethodType``.
+def get_full_hp_param(self, optim_state_key=None):
+    """fp32 master weight (``optim_state_key=None``) or the named optimizer state, assembled over the DP group."""
+    if optim_state_key is None:
+        return safe_get_full_fp32_param(self)
+    return safe_get_full_optimizer_state(self, optim_state_key)
+
+
+def set_full_hp_param(self, value, optim_state_key=None):
+    if optim_state_key is None:
+        return safe_set_full_fp32_param(self, value)
+    return safe_set_full_optimizer_state(self, value, optim_state_key)
+
+
+def get_full_hp_grad(self):
+    return safe_get_full_grad(self)
+
+
+def set_full_hp_grad(self, value):
+    return safe_set_full_grad(self, value)

@@ -134,3 +134,36 @@ def test_named_optimizer_swappers(tmp_path, kind):
     sw.swap_out_optimizer_state(flat, async_swap=False)
     assert torch.equal(flat.state["exp_avg"].detach(), torch.full((3500, ), 1.5))
     assert torch.equal(flat.state["exp_avg_sq"].detach(), ref)
+
+
+def test_per_parameter_optimizer_swapper(tmp_path):
+    import torch
+    from deepspeed_b200.runtime.swap_tensor.optimizer_utils import (FlattenedTensorSwapInfo, OptimizerStateSwapInfo,
+                                                                      OptimizerSwapper)
+    from deepspeed_b200.runtime.swap_tensor.pipelined_optimizer_swapper import OptimizerSwapOp
+    p = torch.nn.Parameter(torch.randn(512, 1024))  # 2 MiB fp32: above the aio threshold
+    small = torch.nn.Parameter(torch.randn(8))
+    opt = torch.optim.Adam([p, small], lr=1e-2)
+    p.grad, small.grad = torch.randn_like(p), torch.randn_like(small)
+    opt.step()
+    sw = OptimizerSwapper(None, {"block_size": 1 << 20, "queue_depth": 8, "intra_op_parallelism": 1, "single_submit": False,
+                                 "overlap_events": True, "use_gds": False}, str(tmp_path), opt, p.numel(), "cpu",
+                          torch.float32, None)
+    assert sw.swappable_tensor(param=p) and not sw.swappable_tensor(param=small)
+    want = [p.detach().clone(), opt.state[p]["exp_avg"].clone(), opt.state[p]["exp_avg_sq"].clone()]
+    sw.swap_out_optimizer_state(p)
+    assert p.numel() == 0 and opt.state[p]["exp_avg"].numel() == 0
+    g = torch.randn(512 * 1024)
+    half = g.numel() // 2
+    sw.swap_out_gradients(p, [0, half, g.numel() - 16], [g[:half], g[half:g.numel() - 16], g[-16:]])
+    info = sw._get_param_swap_info(p)
+    assert isinstance(info, OptimizerStateSwapInfo) and info.has_gradients() and len(info.unswapped_gradients) == 2
+    assert all(isinstance(x, FlattenedTensorSwapInfo) for x in info.swapped_gradients.values())
+    sw.swap_in_optimizer_state(p)
+    assert torch.equal(p.detach(), want[0]) and torch.equal(opt.state[p]["exp_avg"], want[1])
+    assert torch.equal(opt.state[p]["exp_avg_sq"], want[2]) and torch.equal(p.grad.reshape(-1), g)
+    opt.step()  # the optimizer keeps working on the swapped-in storage
+    op = OptimizerSwapOp(sw.aio_handle, True, info, [], [], 3)
+    assert op.is_parameter(p) and not op.is_parameter(small)
+    op.wait()
+    assert not op.wait_required
