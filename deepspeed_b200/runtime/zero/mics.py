@@ -142,6 +142,46 @@ class MiCS_Init(Init):
                          config=config, enabled=enabled, dtype=dtype, mpu=mpu)
 
 
+def has_hierarchical_all_gather_groups(comm_groups: "MiCS_CommGroups") -> bool:
+    """Two-level (intra-node, then inter-node) all-gather groups exist (reference ``mics.py:29``)."""
+    return getattr(comm_groups, "param_intra_node_group", None) is not None and \
+        getattr(comm_groups, "param_inter_node_shard_group", None) is not None
+
+
+class MiCS_AllGatherCoalescedHandle:
+    """Handle of a MiCS coalesced gather: identical to the ZeRO-3 handle, scoped to the shard group (the hierarchical
+    variant issues its two stages inside ``hierarchical_all_gather`` and hands back a completed handle)."""
+
+    def __new__(cls, allgather_handle, params, partitions, world_size):
+        from .gather_handles import AllGatherCoalescedHandle
+        return AllGatherCoalescedHandle(allgather_handle, params, partitions, world_size)
+
+
+def _mics_offload_cls():
+    from .parameter_offload import DeepSpeedZeRoOffload
+
+    class MiCS_Offload(DeepSpeedZeRoOffload):
+        """Parameter-offload manager whose partitioning scope is the MiCS shard group (reference ``mics.py:334``)."""
+
+        def __init__(self, module, *args, ds_config=None, dp_process_group=None, mpu=None, **kw):
+            shard = getattr(getattr(ds_config, "zero_config", None), "mics_shard_size", -1) if ds_config is not None else -1
+            self.mics_comm_groups = None
+            if shard and shard > 0 and dist.is_initialized():
+                self.mics_comm_groups = create_mics_comm_groups(shard, dp_process_group, mpu=mpu)
+                dp_process_group = self.mics_comm_groups.param_shard_group
+            super().__init__(module, *args, ds_config=ds_config, dp_process_group=dp_process_group, mpu=mpu, **kw)
+
+    return MiCS_Offload
+
+
+def __getattr__(name):
+    if name == "MiCS_Offload":  # built lazily: parameter_offload imports the sharded optimizer
+        cls = _mics_offload_cls()
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)
+
+
 def MiCS_Optimizer(module, *, shard_size, dp_group=None, **kw):
     """Factory: the ZeRO-3 optimizer over (shard group, replica group)."""
     from deepspeed_b200.runtime.zero.sharded import ZeroShardedOptimizer

@@ -91,3 +91,36 @@ class DeepSpeedZeRoOffload:
             self._zo.destroy()
 
     _remove_module_hooks = destroy
+
+
+class ZeROOrderedDict(dict):
+    """``module._parameters`` replacement that fetches a partitioned parameter on first touch (reference
+    ``parameter_offload.py:45``): code that reaches into ``module._parameters[name]`` outside ``forward`` (weight tying,
+    custom init) sees the full tensor instead of the empty placeholder."""
+
+    def __init__(self, parent_module, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._parent_module = parent_module
+        self._in_forward = False
+
+    def __reduce__(self):
+        return (dict, (), None, None, iter(self.items()))
+
+    def __getitem__(self, key):
+        param = super().__getitem__(key)
+        if param is None or not hasattr(param, "ds_status"):
+            return param
+        from .partition_parameters import ZeroParamStatus
+        if param.ds_status == ZeroParamStatus.NOT_AVAILABLE and not self._in_forward:
+            if getattr(self._parent_module, "_parameters", None) is not None and hasattr(param, "all_gather"):
+                param.all_gather()
+        return param
+
+
+def _inject_parameters(module, cls):
+    """Swap every sub-module's ``_parameters`` dict for ``cls(parent_module=...)`` keeping the entries."""
+    for m in module.modules():
+        new = cls(parent_module=m)
+        for k, v in m._parameters.items():
+            new[k] = v
+        m._parameters = new

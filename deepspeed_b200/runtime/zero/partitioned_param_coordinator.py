@@ -130,3 +130,22 @@ class PartitionedParameterCoordinator:
     @property
     def available_parameter_numel(self):
         return sum(rt.u.full_numel for rt in self.zo.rts if rt.state != NOT_GATHERED and not rt.u.persistent)
+
+
+def debug_rank0(message: str) -> None:
+    from deepspeed_b200 import comm as dist
+    from deepspeed_b200.utils.logging import logger
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        logger.debug(message)
+
+
+def get_all_parameters(sub_module, recurse=False):
+    """Own + externally registered parameters of a module (reference ``partitioned_param_coordinator.py:31``)."""
+    import itertools
+    ext = getattr(sub_module, "_external_params", None) or getattr(sub_module, "ds_external_parameters", lambda: ())
+    ext_items = ext.items() if isinstance(ext, dict) else (ext() if callable(ext) else ext)
+    return itertools.chain(sub_module.named_parameters(recurse=recurse), ext_items)
+
+
+def iter_params(module, recurse=False):
+    return (p for _, p in get_all_parameters(module, recurse))

@@ -218,3 +218,31 @@ class FPDT_LogitsLoss(torch.nn.Module):
         from deepspeed_b200.ops.linear import chunked_linear_xent
         return chunked_linear_xent(hidden.reshape(-1, hidden.shape[-1]), self.weight, labels.reshape(-1),
                                    chunk=self.chunk_size, ignore_index=self.ignore_index)
+
+
+# ---- element-wise helpers of the reference module (``fpdt_layer.py:32, :1044-1053``) -----------------------------------
+def _rotate_half_backward(x):
+    x1, x2 = x.chunk(2, dim=-1)
+    return torch.cat((x2, -x1), dim=-1)
+
+
+def apply_rotary_pos_emb_backward(grad_output, freqs_cos, freqs_sin):
+    """Adjoint of ``sequence.layer.apply_rotary_pos_emb``."""
+    rot = freqs_cos.shape[-1]
+    g, g_pass = grad_output[..., :rot], grad_output[..., rot:]
+    g = g * freqs_cos + _rotate_half_backward(g * freqs_sin)
+    return g if g_pass.shape[-1] == 0 else torch.cat((g, g_pass), dim=-1)
+
+
+_GELU_K, _GELU_C = 0.7978845608028654, 0.044715
+
+
+def bias_gelu(x):
+    """tanh-approximated GELU."""
+    return 0.5 * x * (1.0 + torch.tanh(_GELU_K * x * (1.0 + _GELU_C * x * x)))
+
+
+def bias_gelu_back(g, x):
+    th = torch.tanh(_GELU_K * x * (1.0 + _GELU_C * x * x))
+    d = 0.5 * (1.0 + th) + 0.5 * x * (1.0 - th * th) * _GELU_K * (1.0 + 3.0 * _GELU_C * x * x)
+    return d * g

@@ -137,3 +137,42 @@ class DistributedAttention(torch.nn.Module):
             v = _SeqAllToAll.apply(g, value, self.scatter_idx, self.gather_idx, batch_dim_idx)
         ctx = self.local_attn(q, k, v, *args, **kwargs)
         return _SeqAllToAll.apply(g, ctx, self.gather_idx, self.scatter_idx, batch_dim_idx)
+
+
+# ---- functional helpers kept for callers of the reference module (``sequence/layer.py:59-170``) -------------------------
+def post_all2all(permute_idx, res_shape):
+    """Closure applied to an all-to-all result: optional permute, then reshape to ``res_shape``."""
+
+    def post_func(t):
+        if permute_idx is not None:
+            t = t.permute(permute_idx)
+        return t.reshape(res_shape).contiguous()
+
+    return post_func
+
+
+def pre_all2all_fun(permute_idx, inp_shape, input):
+    t = input.reshape(inp_shape)
+    return (t.permute(permute_idx) if permute_idx is not None else t).contiguous()
+
+
+def _rotate_half(x):
+    """``[x1, x2] -> [-x2, x1]`` over the two halves of the last dimension."""
+    x1, x2 = x.chunk(2, dim=-1)
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(t, freqs_cos, freqs_sin):
+    """NeoX-style rotary embedding on the leading ``freqs_cos.shape[-1]`` features of ``t`` ([seq, ..., dim]); the rest
+    passes through."""
+    rot = freqs_cos.shape[-1]
+    head, tail = t[..., :rot], t[..., rot:]
+    head = head * freqs_cos + _rotate_half(head) * freqs_sin
+    return head if tail.shape[-1] == 0 else torch.cat((head, tail), dim=-1)
+
+
+def uneven_heads_all2all(input, scatter_idx, gather_idx, batch_dim_idx, group):
+    """All-to-all for head counts that do not divide the sequence-parallel degree (first ranks take one extra head)."""
+    if dist.get_world_size(group) == 1:
+        return input
+    return _a2a_uneven(input, group, scatter_idx, gather_idx)
