@@ -34,6 +34,37 @@ def pre_handle(args, tid, read_op):
     return {"file": filename, "handle": handle, "buffer": buf, "elapsed_sec": 0.0, "num_bytes": args.io_size}
 
 
+def pre_handle_read(pool_params):
+    args, tid = pool_params
+    return pre_handle(args, tid, True)
+
+
+def pre_handle_write(pool_params):
+    args, tid = pool_params
+    return pre_handle(args, tid, False)
+
+
+def main_parallel_read(pool_params):
+    """Asynchronous submit + wait (the handle's worker threads split the file): ``--io_parallel`` > 1 path."""
+    args, tid, ctxt = pool_params
+    t = time.perf_counter()
+    ctxt["handle"].async_pread(ctxt["buffer"], ctxt["file"])
+    ctxt["handle"].wait()
+    if args.gpu:
+        torch.cuda.synchronize()
+    ctxt["elapsed_sec"] += time.perf_counter() - t
+    return ctxt
+
+
+def main_parallel_write(pool_params):
+    args, tid, ctxt = pool_params
+    t = time.perf_counter()
+    ctxt["handle"].async_pwrite(ctxt["buffer"], ctxt["file"])
+    ctxt["handle"].wait()
+    ctxt["elapsed_sec"] += time.perf_counter() - t
+    return ctxt
+
+
 def main_handle_read(pool_params):
     args, tid, ctxt = pool_params
     t = time.perf_counter()
@@ -61,16 +92,19 @@ def post_handle(pool_params):
 
 
 def _aio_handle_task(args, tid, read_op):
-    ctxt = pre_handle(args, tid, read_op)
-    main = main_handle_read if read_op else main_handle_write
+    sched = get_schedule(args, read_op)
+    ctxt = sched["pre"]((args, tid))
     for _ in range(args.loops):
-        main((args, tid, ctxt))
-    post_handle((args, tid, ctxt))
+        sched["main"]((args, tid, ctxt))
+    sched["post"]((args, tid, ctxt))
     return ctxt["num_bytes"] * args.loops, ctxt["elapsed_sec"]
 
 
 def get_schedule(args, read_op):
-    return {"pre": pre_handle, "main": main_handle_read if read_op else main_handle_write, "post": post_handle}
+    parallel = getattr(args, "io_parallel", 1) and getattr(args, "io_parallel", 1) > 1
+    if read_op:
+        return {"pre": pre_handle_read, "main": main_parallel_read if parallel else main_handle_read, "post": post_handle}
+    return {"pre": pre_handle_write, "main": main_parallel_write if parallel else main_handle_write, "post": post_handle}
 
 
 def aio_handle_multiprocessing(args, read_op):

@@ -5,6 +5,7 @@ import argparse
 import itertools
 import json
 import os
+import sys
 import shutil
 
 from .perf import _parse_size, run_io_benchmark
@@ -160,6 +161,40 @@ def run_read_sweep(sweep_config, flush_cache_job=None, sync_job=None, cmd_lines=
 
 def run_write_sweep(sweep_config, flush_cache_job=None, sync_job=None, cmd_lines=None):
     return run_sweep_op(sweep_config, WRITE_OP_DESC, cmd_lines)
+
+
+def script_path():
+    return os.path.dirname(os.path.realpath(__file__))
+
+
+def async_io_setup():
+    """Is the native async-io op usable here?"""
+    from deepspeed_b200.ops.op_builder import AsyncIOBuilder
+    return AsyncIOBuilder().is_compatible()
+
+
+def gds_io_setup():
+    """Is GPUDirect Storage usable here (cuFile present and the GDS op builds)?"""
+    from deepspeed_b200.ops.op_builder import GDSBuilder
+    return GDSBuilder().is_compatible()
+
+
+def create_perf_jobs(io_op_desc, log_dir, cmd_lines):
+    """One ``Job`` per configuration, each logging to its own file (run with ``launch_sweep``)."""
+    from .ds_aio_job import Job
+    py = [sys.executable, "-m", "deepspeed_b200.nvme.test_ds_aio", f"--{io_op_desc}"]
+    return [Job(cmd_line=py + list(c), output_file=os.path.join(log_dir, get_log_file(io_op_desc, c)))
+            for c in cmd_lines]
+
+
+def launch_sweep(sweep_jobs, sync_job=None, flush_cache_job=None, verbose=False):
+    """Run jobs one after another, optionally flushing the page cache / syncing in between."""
+    from .ds_aio_job import run_job
+    for job in sweep_jobs:
+        for aux in (flush_cache_job, sync_job):
+            if aux is not None:
+                run_job(aux, verbose)
+        run_job(job, verbose)
 
 
 def sweep_main(args):

@@ -88,8 +88,60 @@ def _run(cmd: List[str]):
     return proc.stdout
 
 
+class MissingCUDAException(Exception):
+    pass
+
+
+class CUDAMismatchException(Exception):
+    pass
+
+
+DEFAULT_COMPUTE_CAPABILITIES = "10.0a"
+
+
+def installed_cuda_version(name=""):
+    """(major, minor) of the toolkit ``nvcc`` belongs to (reference ``builder.py:47``)."""
+    nv = nvcc_path()
+    if nv is None:
+        raise MissingCUDAException("CUDA_HOME does not exist, unable to compile CUDA op(s)")
+    out = _run([nv, "-V"])
+    import re
+    m = re.search(r"release (\d+)\.(\d+)", out)
+    if m is None:
+        raise MissingCUDAException(f"cannot parse `nvcc -V` output: {out!r}")
+    return int(m.group(1)), int(m.group(2))
+
+
+def get_default_compute_capabilities():
+    return DEFAULT_COMPUTE_CAPABILITIES
+
+
+def assert_no_cuda_mismatch(name=""):
+    """The toolkit must be able to target sm_100a (CUDA ≥ 12.8) and share torch's CUDA major version; minor-version skew
+    is tolerated (the kernels use a C ABI, no torch headers).  ``DS_SKIP_CUDA_CHECK=1`` downgrades errors to warnings."""
+    major, minor = installed_cuda_version(name)
+    problems = []
+    if (major, minor) < (12, 8):
+        problems.append(f"CUDA {major}.{minor} cannot compile for sm_100a (needs >= 12.8)")
+    try:
+        import torch
+        tv = torch.version.cuda
+        if tv and int(tv.split(".")[0]) != major:
+            problems.append(f"installed CUDA {major}.{minor} does not match the version torch was built with ({tv})")
+    except ImportError:
+        pass
+    if problems:
+        if os.environ.get("DS_SKIP_CUDA_CHECK", "0") == "1":
+            print("[WARNING] " + "; ".join(problems))
+            return True
+        raise CUDAMismatchException(f">- DeepSpeed-B200 op builder ({name}): " + "; ".join(problems))
+    return True
+
+
 class OpBuilder:
     """Build one shared library from a list of sources (``.cu`` via nvcc, ``.cpp`` via g++)."""
+    VERSION_CHECKED = False
+
     NAME = "base"
     SOURCES: List[str] = []
     EXTRA_NVCC: List[str] = []
@@ -117,6 +169,93 @@ class OpBuilder:
 
     def lib_path(self) -> Path:
         return LIB_DIR / f"lib{self.NAME}.so"
+
+    # toolchain probes (reference ``OpBuilder`` helpers) ------------------------------------------------------------
+    def builder(self):
+        return self
+
+    def extra_ldflags(self):
+        return list(self.LINK_LIBS)
+
+    def nvcc_args(self):
+        return []
+
+    def cxx_args(self):
+        return CXX_FLAGS + self.EXTRA_CXX
+
+    @staticmethod
+    def validate_torch_version(torch_info=None):
+        """In-tree libraries carry no torch ABI, so any installed torch is fine; kept for callers of the reference API."""
+        return True
+
+    validate_torch_op_version = validate_torch_version
+
+    @staticmethod
+    def is_rocm_pytorch():
+        return False
+
+    @staticmethod
+    def is_sycl_enabled():
+        return False
+
+    def hipify_extension(self):
+        pass
+
+    def sycl_extension(self):
+        pass
+
+    def strip_empty_entries(self, args):
+        return [a for a in args if len(a) > 0]
+
+    def command_exists(self, cmd):
+        cmds = cmd if isinstance(cmd, (list, tuple)) else [cmd]
+        ok = any(shutil.which(c) is not None for c in cmds)
+        if not ok:
+            self.warning(f"{self.name} requires one of {cmds}, none of which is on PATH")
+        return ok
+
+    def warning(self, msg):
+        print(f"\033[93m [WARNING] \033[0m {msg}")
+
+    def deepspeed_src_path(self, code_path):
+        return str(CSRC / code_path) if not os.path.isabs(code_path) else code_path
+
+    def has_function(self, funcname, libraries, library_dirs=None, verbose=False):
+        """Can a program calling ``funcname`` be linked against ``libraries``?"""
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            src = os.path.join(d, "probe.c")
+            with open(src, "w") as f:
+                f.write(f"#ifdef __cplusplus\nextern \"C\"\n#endif\nchar {funcname}(void);\nint main(void) {{ {funcname}(); return 0; }}\n")
+            cmd = [os.environ.get("CC", "gcc"), src, "-o", os.path.join(d, "probe")] + \
+                [f"-L{p}" for p in (library_dirs or [])] + [f"-l{l}" for l in libraries]
+            return subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
+
+    def _cpu_flags(self):
+        try:
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+        except OSError:
+            pass
+        return set()
+
+    def cpu_arch(self):
+        """``-march=native`` unless the host is not x86 (then the compiler default)."""
+        import platform
+        return "-march=native" if platform.machine() in ("x86_64", "AMD64") else ""
+
+    def simd_width(self):
+        """The macro the CPU kernels are compiled with: ``-D__AVX512__`` / ``-D__AVX256__`` / scalar."""
+        flags = self._cpu_flags()
+        if "avx512f" in flags:
+            return "-D__AVX512__"
+        if "avx2" in flags:
+            return "-D__AVX256__"
+        return "-D__SCALAR__"
+
+    def get_cuda_compile_flag(self):
+        return "-D__ENABLE_CUDA__" if nvcc_path() is not None else "-D__DISABLE_CUDA__"
 
     def installed(self) -> bool:
         return self.lib_path().exists()
@@ -199,6 +338,29 @@ class CUDAOpBuilder(OpBuilder):
     def compute_capability_args(self, cross_compile_archs=None):
         return list(ARCH_FLAGS)
 
+    def filter_ccs(self, ccs):
+        """Only sm_100a is ever built: every requested capability collapses to it."""
+        return [["10", "0a"]]
+
+    def version_dependent_macros(self):
+        return ["-DVERSION_GE_1_1", "-DVERSION_GE_1_3", "-DVERSION_GE_1_5"]
+
+    def libraries_args(self):
+        return ["cudart"]
+
+    def is_compatible(self, verbose=False):
+        if not super().is_compatible(verbose):
+            return False
+        if nvcc_path() is not None and not OpBuilder.VERSION_CHECKED:
+            try:
+                assert_no_cuda_mismatch(self.name)
+            except (CUDAMismatchException, MissingCUDAException) as e:
+                if verbose:
+                    self.warning(str(e))
+                return self.lib_path().exists()
+            OpBuilder.VERSION_CHECKED = True
+        return True
+
     def nvcc_args(self):
         return NVCC_FLAGS + self.EXTRA_NVCC
 
@@ -209,5 +371,11 @@ class CUDAOpBuilder(OpBuilder):
 class CPUOpBuilder(OpBuilder):
     NEEDS_CUDA = False
 
+    def get_cuda_lib64_path(self):
+        return os.path.join(cuda_home(), "lib64")
+
     def include_paths(self):
         return [str(CSRC / "include")]
+
+
+TorchCPUOpBuilder = CPUOpBuilder  # reference name of the host-op base class

@@ -1,0 +1,3 @@
+"""``FusedLionBuilder`` (reference ``op_builder/fused_lion.py``): the op lives in one of the two in-tree native libraries; see
+``op_builder/__init__.py``."""
+from . import FusedLionBuilder  # noqa: F401

@@ -1,0 +1,3 @@
+"""``SparseAttnBuilder`` (reference ``op_builder/sparse_attn.py``): the op lives in one of the two in-tree native libraries; see
+``op_builder/__init__.py``."""
+from . import SparseAttnBuilder  # noqa: F401

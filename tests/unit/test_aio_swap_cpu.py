@@ -167,3 +167,26 @@ def test_per_parameter_optimizer_swapper(tmp_path):
     assert op.is_parameter(p) and not op.is_parameter(small)
     op.wait()
     assert not op.wait_required
+
+
+def test_nvme_benchmark_schedules(tmp_path):
+    import types
+    from deepspeed_b200.nvme import ds_aio_basic as B, ds_aio_handle as H, perf_run_sweep as S
+    args = types.SimpleNamespace(mapping_list=[(0, str(tmp_path))], io_size=1 << 20, loops=2, block_size=1 << 18, queue_depth=4,
+                                 single_submit=False, sequential_requests=False, io_parallel=2, use_gds=False, gpu=False,
+                                 validate=False, multi_process=1)
+    for mod in (B, H):
+        for read_op in (False, True):
+            sched = mod.get_schedule(args, read_op)
+            assert set(sched) == {"pre", "main", "post"}
+            ctxt = sched["pre"]((args, 0))
+            for _ in range(args.loops):
+                sched["main"]((args, 0, ctxt))
+            assert ctxt["elapsed_sec"] > 0 and ctxt["num_bytes"] == 1 << 20
+            sched["post"]((args, 0, ctxt))
+    assert H.get_schedule(args, True)["main"] is H.main_parallel_read
+    args.io_parallel = 1
+    assert H.get_schedule(args, True)["main"] is H.main_handle_read
+    jobs = S.create_perf_jobs("read", str(tmp_path), [["--block_size", "1M", "--queue_depth", "8"]])
+    assert len(jobs) == 1 and "--read" in jobs[0].cmd() and jobs[0].output_file.endswith(".txt")
+    assert S.async_io_setup() in (True, False) and S.script_path().endswith("nvme")

@@ -245,3 +245,17 @@ def test_model_parallel_region_ops_single_rank():
         assert torch.equal(y, x)
     a, b = B.split_tensor_along_last_dim(x, 2, contiguous_split_chunks=True)
     assert a.shape == (2, 4) and a.is_contiguous()
+
+
+def test_op_builder_import_paths_and_probes():
+    from deepspeed_b200.ops.op_builder import AsyncIOBuilder, FusedAdamBuilder  # noqa: F401
+    from deepspeed_b200.ops.op_builder.cpu_adam import CPUAdamBuilder
+    from deepspeed_b200.ops.op_builder.all_ops import __op_builders__
+    from deepspeed_b200.op_builder import builder as B
+    from deepspeed_b200.op_builder.fused_adam import FusedAdamBuilder as F2
+    assert F2 is FusedAdamBuilder and len(__op_builders__) >= 20 and CPUAdamBuilder().is_compatible()
+    assert B.get_default_compute_capabilities() == "10.0a" and B.TorchCPUOpBuilder is B.CPUOpBuilder
+    b = B.CUDAOpBuilder()
+    assert b.filter_ccs(["8.0", "9.0"]) == [["10", "0a"]] and b.simd_width().startswith("-D__")
+    assert b.has_function("pthread_create", ("pthread", )) and not b.has_function("definitely_not_a_symbol_xyz", ("m", ))
+    assert b.strip_empty_entries(["a", "", "b"]) == ["a", "b"] and b.builder() is b and not b.is_rocm_pytorch()
