@@ -1,5 +1,5 @@
 """Policies tie a checkpoint format to a model implementation (reference ``model_implementations/inference_policy_base.py``)."""
-from abc import ABC, abstractmethod
+from abc import ABC, ABCMeta, abstractmethod
 from typing import Any, Iterable, Optional, Tuple
 
 import torch
@@ -8,7 +8,8 @@ from .arch import ArchSpec, arch_from_hf_config
 from .ragged_transformer import RaggedTransformer
 from .weights import load_hf_weights
 
-POLICIES = {}
+POLICIES = {}  # model_type -> policy class
+POLICIES_BY_NAME = {}  # class name -> policy class
 
 
 class ContainerMap:
@@ -55,14 +56,22 @@ class ContainerMap:
             raise RuntimeError(f"containers {missing} are missing parameters after loading the checkpoint")
 
 
-class InferenceV2Policy(ABC):
+class PolicyMeta(ABCMeta):
+    """Registers every concrete policy under its ``model_type`` (and its class name) in ``POLICIES`` at class creation
+    (reference ``inference_policy_base.py:95``)."""
+
+    def __new__(mcs, name, bases, dct):
+        cls = super().__new__(mcs, name, bases, dct)
+        if name != "InferenceV2Policy":
+            POLICIES_BY_NAME[name] = cls
+            if dct.get("model_type") or getattr(cls, "model_type", None):
+                POLICIES[cls.model_type] = cls
+        return cls
+
+
+class InferenceV2Policy(ABC, metaclass=PolicyMeta):
     """``model_config``: the HF config (object or dict); ``checkpoint_engine``: yields ``(name, tensor)``."""
     model_type: str = None
-
-    def __init_subclass__(cls, **kw):
-        super().__init_subclass__(**kw)
-        if cls.model_type:
-            POLICIES[cls.model_type] = cls
 
     def __init__(self, model_config: Any, checkpoint_engine: Optional[Any] = None, inf_checkpoint_path: Optional[str] = None) -> None:
         self._model_config = model_config

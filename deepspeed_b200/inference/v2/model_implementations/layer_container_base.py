@@ -14,20 +14,48 @@ import torch
 from .parameter_base import ParameterBase
 
 
-class LayerContainer:
+def make_finalization_callback(all_names):
+    """Build the callback a container hands to its parameters: marks the parameter (looked up by identity under any of
+    ``all_names``) as finalised."""
+
+    def finalization_callback(self, param: ParameterBase, finalized_param=None) -> None:
+        for name in all_names:
+            if self._params.get(name) is param:
+                self._finalized.add(name)
+
+    return finalization_callback
+
+
+class LayerMetaclass(type):
+    """Analyses a container class once: which annotations are ``ParameterBase`` types (``annotation_attrs``), the compiled
+    ``PARAM_MAPPING`` routing rules, and the finalisation callback (reference ``layer_container_base.py:42``)."""
+
+    def __new__(mcs, clsname, bases, attrs):
+        cls = super().__new__(mcs, clsname, bases, attrs)
+        try:
+            hints = get_type_hints(cls)
+        except Exception:
+            hints = dict(attrs.get("__annotations__", {}))
+        cls.annotation_attrs = {n: h for n, h in hints.items() if isinstance(h, type) and issubclass(h, ParameterBase)}
+        rules = []
+        for src, targets in getattr(cls, "PARAM_MAPPING", {}).items():
+            rx = re.compile("^" + re.escape(src).replace("\\*", r"(\d+)") + "$")
+            rules.append((rx, list(targets) if isinstance(targets, (list, tuple)) else [targets]))
+        cls._compiled_rules = rules
+        cls._finalization_callback = make_finalization_callback(tuple(cls.annotation_attrs))
+        return cls
+
+
+class LayerContainer(metaclass=LayerMetaclass):
     PARAM_MAPPING = {}
 
     def __init__(self, model=None) -> None:
         self.inference_model = model
         self._params = {}
         self._finalized = set()
-        for name, hint in get_type_hints(type(self)).items():
-            if isinstance(hint, type) and issubclass(hint, ParameterBase):
-                self._params[name] = hint(model, on_complete=lambda p, n=name: self._finalized.add(n))
-        self._rules = []
-        for src, targets in self.PARAM_MAPPING.items():
-            rx = re.compile("^" + re.escape(src).replace("\\*", r"(\d+)") + "$")
-            self._rules.append((rx, targets if isinstance(targets, (list, tuple)) else [targets]))
+        for name, ptype in type(self).annotation_attrs.items():
+            self._params[name] = ptype(model, on_complete=lambda p: type(self)._finalization_callback(self, p))
+        self._rules = type(self)._compiled_rules
 
     def __getattr__(self, name):
         params = self.__dict__.get("_params", {})

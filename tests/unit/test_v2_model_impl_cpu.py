@@ -138,3 +138,47 @@ def test_moe_container_list_dependencies():
     assert c.is_initialized and c.moe_mlp_1.shape == (3, 64, 16)
     assert float(c.moe_mlp_1[2, 0, 0]) == 2.0 and float(c.moe_mlp_1[2, 32, 0]) == 12.0
     assert not c.set_dependency("unknown.weight", torch.zeros(1))
+
+
+def test_parameter_and_container_metaclasses():
+    import types
+    import torch
+    from deepspeed_b200.inference.v2.model_implementations import parameter_base as P
+    from deepspeed_b200.inference.v2.model_implementations.layer_container_base import LayerContainer, LayerMetaclass
+    from deepspeed_b200.inference.v2.model_implementations.inference_policy_base import POLICIES_BY_NAME, PolicyMeta, InferenceV2Policy
+
+    class Fused(P.ParameterBase):
+        a: torch.Tensor
+        b: torch.Tensor
+        experts = P.ParametrizedList("n_experts")
+
+        def finalize(self):
+            return torch.cat([self.a, self.b] + list(self.experts))
+
+    assert isinstance(Fused, P.ParameterMetaclass) and Fused.tensor_dependencies == ("a", "b")
+    assert set(Fused.list_dependencies) == {"experts"} and Fused.n_dependencies == 3 and isinstance(Fused.a, property)
+    model = types.SimpleNamespace(n_experts=2)
+    f = Fused(model)
+    f.a, f.b = torch.zeros(1), torch.ones(1)
+    f.experts[0] = torch.full((1, ), 2.0)
+    assert f.result is None
+    with pytest.raises(ValueError):
+        f.experts = []
+    f.experts[1] = torch.full((1, ), 3.0)
+    assert f.result.tolist() == [0.0, 1.0, 2.0, 3.0]
+
+    class Sub(Fused):
+        c: torch.Tensor
+
+    assert Sub.tensor_dependencies == ("a", "b", "c")
+
+    class C(LayerContainer):
+        w: Fused
+        PARAM_MAPPING = {"x.a": "w.a", "x.b": "w.b", "e.*.w": "w.experts"}
+
+    assert isinstance(C, LayerMetaclass) and list(C.annotation_attrs) == ["w"] and len(C._compiled_rules) == 3
+    c = C(model)
+    for name, t in (("x.a", torch.zeros(1)), ("x.b", torch.ones(1)), ("e.0.w", torch.ones(1)), ("e.1.w", torch.ones(1))):
+        assert c.set_dependency(name, t)
+    assert c.is_initialized and c.w.numel() == 4 and not c.set_dependency("nope", torch.zeros(1))
+    assert isinstance(InferenceV2Policy, PolicyMeta) and "Llama2Policy" in POLICIES_BY_NAME
