@@ -98,3 +98,60 @@ class QuantizedLinear(torch.nn.Module):
 
     def forward(self, x):
         return maybe_quantized_linear(x, self.qw, self.bias)
+
+
+# ---- ZeRO-Inference style post-init quantisation wrappers (reference ``inference/quantization/layers.py:20-110``) ------
+# One compat blob per ORIGINAL weight object: tied weights (embedding ↔ lm_head) are quantised once and shared.
+quantized_weight_registry = {}
+is_zero3_enabled = False
+
+
+def get_quantize_weight_fn(quantizer, pre_quant_weight):
+    """Deferred ``quantizer.quantize(weight)`` → ``(codes, scale, min)``."""
+
+    def func():
+        return quantizer.quantize(pre_quant_weight.data)
+
+    return func
+
+
+def get_quantized_weight_wrapper(model, pre_quant_weight, quantize_weight_fn):
+    """The packed quantised parameter standing for ``pre_quant_weight`` (created on first request, then shared)."""
+    from .utils import concat_to_compat_param
+    key = id(pre_quant_weight)
+    blob = quantized_weight_registry.get(key)
+    if blob is None:
+        codes, scale, mn = quantize_weight_fn()
+        blob = concat_to_compat_param(codes, scale, mn)
+        blob.quant_shape, blob.quant_groups = tuple(codes.shape), scale.numel()
+        blob.quant_scale_shape, blob.quant_dtype = tuple(scale.shape), scale.dtype
+        quantized_weight_registry[key] = blob
+    elif is_zero3_enabled:
+        from deepspeed_b200.runtime.zero import register_external_parameter
+        register_external_parameter(model, blob)
+    return blob
+
+
+class QuantizedEmbedding(torch.nn.Embedding):
+    """``nn.Embedding`` whose table is stored group-quantised (4 / 8 bit asymmetric); only the looked-up rows are
+    dequantised when rows are whole groups, otherwise the table is dequantised transiently."""
+
+    def __init__(self, config, pre_quant_layer: torch.nn.Embedding) -> None:
+        from .utils import DeQuantizer, Quantizer
+        w = pre_quant_layer.weight
+        assert pre_quant_layer.max_norm is None and pre_quant_layer.norm_type == 2, "Not supported"
+        assert not pre_quant_layer.scale_grad_by_freq and not pre_quant_layer.sparse, "Not supported"
+        super().__init__(pre_quant_layer.num_embeddings, pre_quant_layer.embedding_dim, padding_idx=pre_quant_layer.padding_idx,
+                         _weight=w, device=w.device, dtype=w.dtype)
+        self.config = config
+        self.weight = get_quantized_weight_wrapper(self, w, get_quantize_weight_fn(Quantizer(config), w))
+        self.weight.dequantizer = DeQuantizer(config, w.dtype)
+
+    def _table(self):
+        from .utils import split_compat_param
+        p = self.weight
+        codes, scale, mn = split_compat_param(p.data, p.quant_shape, p.quant_groups, p.quant_dtype)
+        return p.dequantizer.dequantize(codes, scale.view(p.quant_scale_shape), mn.view(p.quant_scale_shape))
+
+    def forward(self, input):
+        return torch.nn.functional.embedding(input, self._table(), self.padding_idx)

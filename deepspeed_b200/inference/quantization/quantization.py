@@ -14,6 +14,17 @@ def _init_group_wise_weight_quantization(model, ds_config):
     for name, mod in list(model.named_modules()):
         for cname, child in list(mod.named_children()):
             full = f"{name}.{cname}" if name else cname
+            if isinstance(child, torch.nn.Embedding):
+                for pat, qc in wq.items():
+                    if re.search(pat, full) and qc.get("num_bits", 8) in (4, 8) and not qc.get("fp", False):
+                        from .layers import QuantizedEmbedding
+                        gs = qc.get("group_size", 128)
+                        if child.embedding_dim % gs == 0:
+                            setattr(mod, cname, QuantizedEmbedding({"num_bits": qc.get("num_bits", 8), "group_size": gs,
+                                                                    "group_dim": qc.get("group_dim", 1),
+                                                                    "symmetric": False}, child))
+                        break
+                continue
             if not isinstance(child, torch.nn.Linear):
                 continue
             for pat, qc in wq.items():

@@ -141,3 +141,25 @@ def wrap_load_from_state_dict(f):
                 _quantize_param(p, p.quant_config)
 
     return wrapper
+
+
+def get_quantizer_module():
+    """The native quantiser op (reference ``utils.py:get_quantizer_cuda_module``)."""
+    from deepspeed_b200.ops.quantizer import quantizer
+    return quantizer
+
+
+get_quantizer_cuda_module = get_quantizer_module
+
+
+def get_AsyncPartitionedParameterSwapper(model: nn.Module):
+    """The NVMe parameter swapper attached to any ZeRO-3 parameter of ``model`` (``None`` when parameters stay resident)."""
+    for p in model.parameters():
+        sw = getattr(p, "nvme_swapper", None)
+        if sw is not None:
+            return sw
+        zo = getattr(p, "_ds_zero", None)
+        zo = zo() if callable(zo) else None
+        if zo is not None and getattr(zo, "param_swapper", None) is not None:
+            return zo.param_swapper
+    return None

@@ -166,3 +166,68 @@ class GroupQuantizer:
         parts = [1.0 / s for s in scale.reshape(count, -1)] if count > 1 else [1.0 / scale]
         out.scale = torch.cat([p.reshape(1, -1) for p in parts], dim=0).reshape(-1).unsqueeze(0)
         return out
+
+
+def get_transformer_name(replaced_module):
+    """Dotted path of the ``ModuleList`` holding the transformer layers (``"transformer.h"``, ``"model.layers"`` ...): the
+    first child that contains a ModuleList of (injected or original) layers."""
+    for n, c in replaced_module.named_children():
+        for name, child in c.named_children():
+            if isinstance(child, nn.ModuleList) and len(child) > 0:
+                return f"{n}.{name}"
+    return ""
+
+
+def skip_level_0_prefix(model, state_dict):
+    """Checkpoints of BLOOM / OPT drop the top-level module name from their keys -- unless the keys start with ``model.``."""
+    import re
+    if state_dict is not None and any(re.match(r"^model[.]", k) for k in state_dict.keys()):
+        return False
+    text = str(model)
+    m = re.search(r": (.*?)Model", text) or re.search(r": (.*?)Stack", text) or re.match(r"(.*?)Model", text)
+    return m is not None and m.group(1).lower() in ("bloom", "opt")
+
+
+def replace_module(model, orig_class, replace_fn, _replace_policy, checkpoint=None):
+    """Replace every instance of ``orig_class`` (or, with ``orig_class=None``, of every class a registered policy names) by
+    ``replace_fn(child, policy, layer_id)``; ``checkpoint`` (``.pt`` / ``.safetensors``) is loaded once and the matching
+    slice of its state dict is pushed into each replaced module (reference ``replace_module.py:619``)."""
+    sd = None
+    if checkpoint is not None:
+        if str(checkpoint).endswith(".safetensors"):
+            from safetensors.torch import load_file
+            sd = load_file(checkpoint)
+        else:
+            sd = torch.load(checkpoint, map_location="cpu", weights_only=False)
+    policies = {}
+    if orig_class is not None:
+        policies[orig_class] = (replace_fn, _replace_policy)
+    else:
+        from .replace_policy import replace_policies
+        for plcy in replace_policies:
+            orig = getattr(plcy, "_orig_layer_class", None)
+            for cls in (orig if isinstance(orig, (list, tuple)) else [orig]):
+                if cls is not None:
+                    policies[cls] = (replace_fn, plcy)
+    assert policies, "No default policy found! Please specify your policy injection_policy (like {BertLayer:HFBEertLayerPolicy})."
+    skip0 = skip_level_0_prefix(model, sd)
+    counter = [0]
+
+    def walk(mod, prefix, level):
+        for name, child in list(mod.named_children()):
+            full = prefix + name
+            hit = policies.get(type(child))
+            if hit is None:
+                walk(child, full + "." if not (level == 0 and skip0) else prefix, level + 1)
+                continue
+            fn, pol = hit
+            new = fn(child, pol, counter[0])
+            counter[0] += 1
+            if sd is not None:
+                own = {k[len(full) + 1:]: v for k, v in sd.items() if k.startswith(full + ".")}
+                if own:
+                    new.load_state_dict(own, strict=False)
+            setattr(mod, name, new)
+
+    walk(model, "", 0)
+    return model

@@ -118,3 +118,23 @@ def test_weight_only_quantized_linear_all_formats_host(mode, tol):
     assert deq.shape == w.shape and (deq - w).abs().max() < tol * w.abs().max()
     y = maybe_quantized_linear(x, qw)
     assert torch.allclose(y, x @ deq.t(), atol=1e-5)
+
+
+def test_quantized_embedding_and_post_init_quant():
+    import torch
+    from deepspeed_b200.inference.quantization import _init_group_wise_weight_quantization
+    from deepspeed_b200.inference.quantization.layers import QuantizedEmbedding, QuantizedLinear
+
+    class M(torch.nn.Module):
+
+        def __init__(self):
+            super().__init__()
+            self.embed = torch.nn.Embedding(32, 128)
+            self.proj = torch.nn.Linear(128, 128)
+
+    m = M()
+    ref = m.embed(torch.arange(32))
+    _init_group_wise_weight_quantization(m, {"weight_quantization": {"post_init_quant": {"embed": {"num_bits": 8, "group_size": 64},
+                                                                                      "proj": {"num_bits": 8, "group_size": 64}}}})
+    assert isinstance(m.embed, QuantizedEmbedding) and isinstance(m.proj, QuantizedLinear)
+    assert m.embed.weight.dtype == torch.uint8 and (m.embed(torch.arange(32)) - ref).abs().max() < 0.05
