@@ -68,6 +68,17 @@ def init_compression(model, deepspeed_config, teacher_model=None, mpu=None):
         assert teacher_model is not None, "Teacher model is required for layer reduction"
         student_initialization(c_model, teacher_model, deepspeed_config)
     compression_preparation(c_model, get_compress_methods(c_model, cfg, mpu=mpu), mpu)
+    sp = cfg[C.SPARSE_PRUNING][C.SHARED_PARAMETERS]
+    if sp[C.TECHNIQUE_ENABLED] and sp[C.SPARSE_PRUNING_METHOD] == C.SPARSE_PRUNING_METHOD_SNIP_MOMENTUM:
+        # block-sparse SNIP-momentum pruning: masks are driven by hooks on the model (step begin) and on the optimizer
+        # (``rewrite_optimizer_step(optimizer).pruners = model.pruners``; the engine does this when it builds the optimizer)
+        from .helper import generate_pruners, register_on_step_begin
+        c_model.pruners = generate_pruners(
+            {"target_sparsity": 1 - sp.get(C.SPARSE_PRUNING_DENSE_RATIO, 0.1), "pattern": sp.get(C.SPARSE_PRUNING_BLOCK_PATTERN, "4x1"),
+             "pruning_frequency": sp.get(C.SPARSE_PRUNING_SCHEDULE_OFFSET_STRIDE, 1), "start_step": sp[C.TECHNIQUE_SCHEDULE_OFFSET],
+             "end_step": sp.get(C.TECHNIQUE_SCHEDULE_OFFSET_END, sp[C.TECHNIQUE_SCHEDULE_OFFSET]),
+             "excluded_op_names": sp.get(C.SPARSE_PRUNING_EXCLUDED_MODULES, [])}, c_model)
+        c_model._pruner_hook = register_on_step_begin(c_model)
     return model
 
 

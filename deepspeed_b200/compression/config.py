@@ -44,7 +44,7 @@ def _technique(block, name):
             p.setdefault(C.WEIGHT_QUANTIZATION_PERIOD, 1)
         elif name == C.ACTIVATION_QUANTIZATION:
             assert C.ACTIVATION_QUANTIZE_BITS in p
-        else:
+        elif not (name == C.SPARSE_PRUNING and shared.get(C.SPARSE_PRUNING_METHOD) == C.SPARSE_PRUNING_METHOD_SNIP_MOMENTUM):
             assert "dense_ratio" in p, f"{name} group {gname} requires dense_ratio"
     return {C.SHARED_PARAMETERS: shared, C.DIFFERENT_GROUPS: groups}
 

@@ -135,3 +135,133 @@ def convert_conv1d_to_linear(model, convert_type):
                 lin.bias.data = module.bias.data
             recursive_setattr(model, name, lin.to(module.weight.device))
     return model
+
+
+# ---- SNIP-momentum block pruning (reference ``helper.py:257-322`` delegates to neural_compressor; native here) ----------
+class SnipMomentumPruner:
+    """Block-sparse magnitude×gradient pruning with momentum.
+
+    Every optimizer step the criterion ``score ← β·score + |w ⊙ ∂L/∂w|`` (summed over ``N×M`` blocks) is updated; every
+    ``pruning_frequency`` steps between ``start_step`` and ``end_step`` the mask is re-drawn so that the globally
+    lowest-scoring blocks are removed, the sparsity following the cubic ramp ``s_t = s·(1-(1-p)^3)``.  After every
+    optimizer step the mask is re-applied, so pruned blocks stay zero."""
+
+    def __init__(self, modules, target_sparsity, pattern="4x1", pruning_frequency=1, start_step=0, end_step=0, beta=0.9):
+        import torch
+        self.modules = dict(modules)
+        self.target_sparsity = float(target_sparsity)
+        n, m = (int(v) for v in str(pattern).lower().split("x"))
+        self.block = (n, m)
+        self.pruning_frequency = max(1, int(pruning_frequency))
+        self.start_step, self.end_step, self.beta = int(start_step), max(int(end_step), int(start_step)), beta
+        self.global_step = 0
+        self.scores = {k: torch.zeros(self._blocks(mod.weight), device=mod.weight.device) for k, mod in self.modules.items()}
+        self.masks = {k: torch.ones_like(mod.weight, dtype=torch.bool) for k, mod in self.modules.items()}
+        self.current_sparsity = 0.0
+
+    def _blocks(self, w):
+        n, m = self.block
+        assert w.dim() == 2 and w.shape[0] % n == 0 and w.shape[1] % m == 0, f"weight {tuple(w.shape)} not tileable by {n}x{m}"
+        return w.shape[0] // n, w.shape[1] // m
+
+    def _reduce(self, t):
+        n, m = self.block
+        r, c = t.shape[0] // n, t.shape[1] // m
+        return t.reshape(r, n, c, m).sum(dim=(1, 3))
+
+    def _expand(self, blk):
+        n, m = self.block
+        return blk.repeat_interleave(n, 0).repeat_interleave(m, 1)
+
+    def _sparsity_at(self, step):
+        if step >= self.end_step:
+            return self.target_sparsity
+        span = max(1, self.end_step - self.start_step)
+        p = min(1.0, max(0.0, (step - self.start_step) / span))
+        return self.target_sparsity * (1.0 - (1.0 - p)**3)
+
+    # ---- hooks
+    def on_step_begin(self, local_step=0):
+        import torch
+        step = self.global_step
+        if step < self.start_step or step > self.end_step or (step - self.start_step) % self.pruning_frequency:
+            return
+        want = self._sparsity_at(step)
+        allv = torch.cat([s.reshape(-1) for s in self.scores.values()])
+        k = int(want * allv.numel())
+        if k <= 0 or not bool(allv.any()):
+            return
+        thr = torch.kthvalue(allv, k).values
+        for name, s in self.scores.items():
+            self.masks[name] = self._expand(s > thr)
+        self.current_sparsity = want
+        self._apply()
+
+    def on_before_optimizer_step(self):
+        import torch
+        with torch.no_grad():
+            for name, mod in self.modules.items():
+                if mod.weight.grad is not None:
+                    self.scores[name].mul_(self.beta).add_(self._reduce((mod.weight * mod.weight.grad).abs().float()))
+
+    def on_after_optimizer_step(self):
+        self._apply()
+        self.global_step += 1
+
+    def _apply(self):
+        import torch
+        with torch.no_grad():
+            for name, mod in self.modules.items():
+                mod.weight.mul_(self.masks[name].to(mod.weight.dtype))
+
+    def sparsity(self):
+        tot = sum(m.numel() for m in self.masks.values())
+        return 1.0 - sum(int(m.sum()) for m in self.masks.values()) / max(1, tot)
+
+
+def generate_pruners(config, model):
+    """``config``: dict (or object) with ``target_sparsity, pattern, pruning_frequency, start_step, end_step,
+    excluded_op_names``.  One pruner over every 2-D ``nn.Linear`` weight not excluded and tileable by the block pattern."""
+    import re
+    import torch
+    get = (lambda k, d=None: config.get(k, d)) if isinstance(config, dict) else (lambda k, d=None: getattr(config, k, d))
+    excluded = list(get("excluded_op_names", []) or [])
+    n, m = (int(v) for v in str(get("pattern", "4x1")).lower().split("x"))
+    mods = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Linear) and not any(re.search(p, name) for p in excluded):
+            if mod.weight.shape[0] % n == 0 and mod.weight.shape[1] % m == 0:
+                mods[name] = mod
+    if not mods:
+        from deepspeed_b200.utils.logging import logger
+        logger.warning("one pruner hooks no layers, please have a check")
+    return [SnipMomentumPruner(mods, get("target_sparsity", 0.9), get("pattern", "4x1"), get("pruning_frequency", 1),
+                               get("start_step", 0), get("end_step", 0))]
+
+
+def register_on_step_begin(model):
+    """Forward pre-hook that lets every pruner of ``model.pruners`` refresh its mask at the start of a step."""
+
+    def hook(module, inputs):
+        if module.training:
+            for pruner in module.pruners:
+                pruner.on_step_begin(0)
+
+    return model.register_forward_pre_hook(hook)
+
+
+def rewrite_optimizer_step(opt):
+    """Wrap ``opt.step`` with the pruners' before / after callbacks (``opt.pruners`` is read at call time)."""
+    import types
+
+    def new_step(self, closure=None):
+        for pruner in getattr(self, "pruners", ()):
+            pruner.on_before_optimizer_step()
+        res = self.orig_step(closure) if closure is not None else self.orig_step()
+        for pruner in getattr(self, "pruners", ()):
+            pruner.on_after_optimizer_step()
+        return res
+
+    opt.orig_step = opt.step
+    opt.step = types.MethodType(new_step, opt)
+    return opt

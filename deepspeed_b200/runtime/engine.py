@@ -598,7 +598,12 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
         pass  # clipping is fused into the sharded optimizer step
 
     def _take_model_step(self, lr_kwargs=None):
+        pruners = getattr(self.module, "pruners", None) or ()  # SNIP-momentum sparse pruning (compression.helper)
+        for pr in pruners:
+            pr.on_before_optimizer_step()
         self.optimizer.step()
+        for pr in pruners:
+            pr.on_after_optimizer_step()
         overflow = getattr(self.optimizer, "overflow", False)
         self._step_applied = not overflow
         if overflow:

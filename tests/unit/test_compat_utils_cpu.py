@@ -122,3 +122,33 @@ def _cdb():
 
 def test_object_style_backend():
     run_distributed(_cdb, 2)
+
+
+def test_snip_momentum_block_pruning():
+    import torch
+    from deepspeed_b200.compression.helper import generate_pruners, register_on_step_begin, rewrite_optimizer_step
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 3))
+    model.pruners = generate_pruners({"target_sparsity": 0.5, "pattern": "4x1", "pruning_frequency": 2, "start_step": 1,
+                                      "end_step": 9, "excluded_op_names": [r"^3$"]}, model)
+    pr = model.pruners[0]
+    assert set(pr.modules) == {"0", "2"}  # the 3x8 head is excluded by name
+    h = register_on_step_begin(model)
+    opt = rewrite_optimizer_step(torch.optim.SGD(model.parameters(), lr=0.05))
+    opt.pruners = model.pruners
+    seen = []
+    for step in range(14):
+        x = torch.randn(8, 16)
+        loss = model(x).square().mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        seen.append(pr.sparsity())
+    h.remove()
+    assert seen[0] == 0.0 and all(b >= a - 1e-9 for a, b in zip(seen, seen[1:]))  # cubic ramp: monotone
+    assert abs(seen[-1] - 0.5) < 0.02
+    for name, mod in pr.modules.items():
+        w = mod.weight
+        assert torch.all(w[~pr.masks[name]] == 0)
+        blocks = (w != 0).reshape(w.shape[0] // 4, 4, w.shape[1]).float().mean(1)
+        assert torch.all((blocks == 0) | (blocks == 1))  # whole 4x1 blocks live or die together
