@@ -29,6 +29,46 @@ class DeepSpeedMoEInferenceConfig(DeepSpeedInferenceConfig):
         self.scale_attn_by_inverse_layer_idx = scale_attn_by_inverse_layer_idx
 
 
+class DeepSpeedMLPFunction(torch.autograd.Function):
+    """Inference-only expert MLP: ``act(x W1ᵀ + b1) W2ᵀ`` (+ all-reduce over the expert model-parallel group); the output bias
+    is added by the caller after the reduction (reference ``moe_inference.py:104``)."""
+
+    @staticmethod
+    def forward(ctx, input, inter_w, inter_b, config, output_b, output_w, q_scales=None, q_groups=1, merge_count=1,
+                mp_group=None, async_op=False):
+        h = _act(F.linear(input, inter_w, inter_b), config.mlp_act_func_type)
+        out = F.linear(h, output_w)
+        if mp_group is not None and dist.is_initialized() and dist.get_world_size(group=mp_group) > 1:
+            dist.all_reduce(out, group=mp_group, async_op=async_op)
+        return out + output_b
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        raise RuntimeError("You are running with DeepSpeed Inference mode. Please switch to Training mode for running "
+                           "backward!")
+
+
+class DeepSpeedMoEMLP(nn.Module):
+    """One expert's FFN, its hidden dimension sharded over the expert model-parallel group (reference ``:138``)."""
+
+    def __init__(self, config, q_scales=None, q_groups=1, merge_count=1, mlp_extra_grouping=False, mp_group=None):
+        super().__init__()
+        self.config = config
+        dt = torch.float16 if getattr(config, "fp16", False) else (torch.bfloat16 if getattr(config, "bf16", False) else torch.float32)
+        dt = getattr(config, "dtype", dt) or dt
+        mp = dist.get_world_size(group=mp_group) if (mp_group is not None and dist.is_initialized()) else 1
+        inter = config.intermediate_size // mp
+        p = lambda *shape: nn.Parameter(torch.empty(*shape, dtype=dt), requires_grad=False)
+        self.attn_nw, self.attn_nb = p(config.hidden_size), p(config.hidden_size)
+        self.inter_w, self.inter_b = p(inter, config.hidden_size), p(inter)
+        self.output_w, self.output_b = p(config.hidden_size, inter), p(config.hidden_size)
+        self.q_scales, self.q_groups, self.merge_count, self.mp_group = q_scales, q_groups, merge_count, mp_group
+
+    def forward(self, input, async_op=False):
+        return DeepSpeedMLPFunction.apply(input, self.inter_w, self.inter_b, self.config, self.output_b, self.output_w,
+                                          self.q_scales, self.q_groups, self.merge_count, self.mp_group, async_op)
+
+
 class DeepSpeedMoEInference(DeepSpeedTransformerInference):
 
     def __init__(self, config, mp_group=None, ep_group=None, expert_mp_group=None, quantize_scales=None,
@@ -55,12 +95,23 @@ class DeepSpeedMoEInference(DeepSpeedTransformerInference):
         ids, w, _ = M.top_k_gating(F.linear(x2, self.gate_w).float(), c.k, normalize=c.k > 1)
         out = torch.zeros(Tn, H, dtype=torch.float32, device=x2.device)
         ep_rank = dist.get_rank(self.ep_group) if self.ep_group is not None else 0
-        for le in range(self.n_local):
-            ge = ep_rank * self.n_local + le
-            we = (w * (ids == ge)).sum(-1, keepdim=True)
-            ye = F.linear(_act(F.linear(x2, self.expert_inter_w[le], self.expert_inter_b[le]), c.mlp_act_func_type),
+        # only the tokens routed to an expert visit it: sort the (token, slot) pairs by expert once, then run each local
+        # expert on its contiguous run
+        flat_e = ids.reshape(-1)
+        order = torch.argsort(flat_e, stable=True)
+        tok = (order // ids.shape[1])
+        counts = torch.bincount(flat_e, minlength=self.n_global)
+        starts = torch.cumsum(counts, 0) - counts
+        wflat = w.reshape(-1)[order]
+        lo, hi = ep_rank * self.n_local, (ep_rank + 1) * self.n_local
+        bounds = torch.stack([starts[lo:hi], counts[lo:hi]], 1).tolist()
+        for le, (s0, n) in enumerate(bounds):
+            if n == 0:
+                continue
+            rows = tok[s0:s0 + n]
+            ye = F.linear(_act(F.linear(x2[rows], self.expert_inter_w[le], self.expert_inter_b[le]), c.mlp_act_func_type),
                           self.expert_out_w[le], self.expert_out_b[le])
-            out.addcmul_(ye.float(), we)
+            out.index_add_(0, rows, ye.float() * wflat[s0:s0 + n, None])
         if self.ep_size > 1:
             dist.all_reduce(out, group=self.ep_group)
         return out.to(x2.dtype)

@@ -50,3 +50,97 @@ class WorkspaceOp(BaseOp):
     @classmethod
     def set_seen(cls, layer_id, n):
         cls._seen[layer_id] = n
+
+
+class InferenceContext:
+    """Process-wide decode state for the v1 kernel-injected layers (reference ``workspace.py:14``): the running token
+    count and one ``(key, value)`` cache pair per layer shaped ``[batch, heads, max_tokens, head_dim]``.
+
+    ``update_cache`` writes the new keys / values (whole prompt, or one decode position) and returns views of the valid
+    prefix -- what an attention kernel reads."""
+    _instance = None
+
+    def __init__(self):
+        self.kv_cache = None
+        self.kv_cache_size = None
+        self.kv_cache_elem_dtype = None
+        self.num_tokens = 1
+        self.static_shapes = False
+        self._spec = None
+
+    @classmethod
+    def Instance(cls):
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    # ---- workspace
+    def gen_workspace(self, num_layers, num_heads, batch_size, prompt_len, hidden_dim, mp_size, external_cache, elem_dtype, rank,
+                      max_out_tokens, min_out_tokens):
+        """Size the caches: ``max_out_tokens`` positions (at least the prompt + ``min_out_tokens``)."""
+        heads = num_heads // mp_size
+        tokens = max(int(max_out_tokens), int(prompt_len) + int(min_out_tokens))
+        self._spec = (num_layers, batch_size, heads, tokens, hidden_dim // num_heads, elem_dtype, bool(external_cache))
+        self.kv_cache = None
+        self.kv_cache_elem_dtype = elem_dtype
+        return self._retake_workspace()
+
+    def retake_workspace(self):
+        return True
+
+    def _retake_workspace(self):
+        assert self._spec is not None, "Need to call gen_workspace once to set up the workspace"
+        if self.kv_cache is None:
+            layers, b, h, t, d, dt, external = self._spec
+            self.kv_cache_size = (b, h, t, d)
+            if external:
+                self.kv_cache = []
+                return True
+            dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+            self.kv_cache = [(torch.zeros(self.kv_cache_size, dtype=dt, device=dev),
+                              torch.zeros(self.kv_cache_size, dtype=dt, device=dev)) for _ in range(layers)]
+        return True
+
+    def release_workspace(self):
+        self.kv_cache = None
+
+    # ---- token counter
+    def reset_tokens(self, initial_tokens=1):
+        self.num_tokens = initial_tokens
+
+    def current_tokens(self):
+        return self.num_tokens
+
+    def advance_tokens(self):
+        self.num_tokens = self.num_tokens + 1
+
+    # ---- cache
+    def update_cache(self, layer_id, token_idx, is_prompt, bat_0213_key, bat_0213_value):
+        """``bat_0213_*``: ``[batch, heads, seq, head_dim]``.  Prompt: cache[:, :, :seq] = k/v and the tail is zeroed;
+        decode: position ``token_idx-1`` is written (``token_idx`` may be a 1-element tensor for static-shape graphs)."""
+        assert self._retake_workspace(), "Could not allocate workspace"
+        if is_prompt:
+            self.static_shapes = token_idx is not None
+            self.reset_tokens(bat_0213_key.shape[2] if token_idx is None else token_idx)
+        if token_idx is None:
+            token_idx = self.current_tokens()
+        b = bat_0213_key.shape[0]
+        kc, vc = self.kv_cache[layer_id]
+        if is_prompt:
+            seq = bat_0213_key.shape[2]
+            for cache, new in ((kc, bat_0213_key), (vc, bat_0213_value)):
+                cache[:b, :, :seq].copy_(new)
+                dead = torch.arange(cache.shape[2], device=cache.device) >= (token_idx if torch.is_tensor(token_idx) else int(token_idx))
+                cache[:b].masked_fill_(dead.view(1, 1, -1, 1), 0)
+        elif self.static_shapes:
+            assert torch.is_tensor(token_idx), "token_idx is expected to be torch.Tensor"
+            kc[:b].index_copy_(2, token_idx.reshape(-1) - 1, bat_0213_key)
+            vc[:b].index_copy_(2, token_idx.reshape(-1) - 1, bat_0213_value)
+        else:
+            assert isinstance(token_idx, int), "token_idx is expected to be int"
+            kc[:b, :, token_idx - 1:token_idx] = bat_0213_key
+            vc[:b, :, token_idx - 1:token_idx] = bat_0213_value
+        k, v = kc[:b], vc[:b]
+        if not self.static_shapes:
+            k, v = k[:, :, :token_idx], v[:, :, :token_idx]
+        return k, v

@@ -36,6 +36,36 @@ DeepSpeedOptimizerCallable = object
 DeepSpeedSchedulerCallable = object
 
 
+def split_half_float_double_sparse(tensors):
+    """Group gradients for bucketed reduction: ``([(dtype, [SparseTensor...])], [(dtype, [dense...])])``
+    (reference ``engine.py:126``)."""
+    from deepspeed_b200.runtime.sparse_tensor import SparseTensor
+    supported = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
+    sparse, dense = {}, {}
+    for t in tensors:
+        assert t.dtype in supported, f"attempting to reduce an unsupported grad type: {t.dtype}"
+        (sparse if isinstance(t, SparseTensor) else dense).setdefault(t.dtype, []).append(t)
+    order = lambda d: [(dt, d[dt]) for dt in supported if dt in d]
+    return order(sparse), order(dense)
+
+
+class EngineTimers:
+    """Names of the wall-clock timers the engine drives, grouped by phase (reference ``engine.py:149``)."""
+
+    def __init__(self, enable_micro_timers, enable_global_timers):
+        from deepspeed_b200.utils import timer as T
+        phases = ("forward", "backward", "backward_inner", "backward_reduce", "step")
+        table = {"micro": dict(zip(phases, (T.FORWARD_MICRO_TIMER, T.BACKWARD_MICRO_TIMER, T.BACKWARD_INNER_MICRO_TIMER,
+                                            T.BACKWARD_REDUCE_MICRO_TIMER, T.STEP_MICRO_TIMER))),
+                 "global": dict(zip(phases, (T.FORWARD_GLOBAL_TIMER, T.BACKWARD_GLOBAL_TIMER, T.BACKWARD_INNER_GLOBAL_TIMER,
+                                             T.BACKWARD_REDUCE_GLOBAL_TIMER, T.STEP_GLOBAL_TIMER)))}
+        on = {"micro": enable_micro_timers, "global": enable_global_timers}
+        for ph in phases:
+            setattr(self, f"{ph}_timers", [table[k][ph] for k in ("micro", "global") if on[k]])
+        self.micro_timers = list(table["micro"].values()) if enable_micro_timers else []
+        self.global_timers = list(table["global"].values()) if enable_global_timers else []
+
+
 class DeepSpeedEngine(CheckpointMixin, nn.Module):
 
     def __init__(self, args=None, model=None, optimizer=None, model_parameters=None, training_data=None,

@@ -155,3 +155,36 @@ def test_diffusers_block_and_attention():
     assert torch.allclose(fused(x), blk(x), atol=1e-5)
     a = torch.randn(1, 3, 3, 4)  # [N, H, W, C]
     assert torch.allclose(nhwc_bias_add(a, torch.ones(4)), a + 1)
+
+
+def test_inference_context_and_moe_mlp():
+    import types
+    import torch
+    from deepspeed_b200.ops.transformer.inference.op_binding.workspace import InferenceContext
+    from deepspeed_b200.ops.transformer.inference.moe_inference import DeepSpeedMoEMLP
+    ctx = InferenceContext.Instance()
+    assert ctx is InferenceContext.Instance()
+    ctx.gen_workspace(num_layers=2, num_heads=4, batch_size=2, prompt_len=5, hidden_dim=32, mp_size=1, external_cache=False,
+                      elem_dtype=torch.float32, rank=0, max_out_tokens=16, min_out_tokens=1)
+    k0, v0 = torch.randn(2, 4, 5, 8), torch.randn(2, 4, 5, 8)
+    k, v = ctx.update_cache(1, None, True, k0, v0)
+    assert k.shape == (2, 4, 5, 8) and torch.equal(k, k0) and ctx.current_tokens() == 5
+    ctx.advance_tokens()
+    k1, v1 = torch.randn(2, 4, 1, 8), torch.randn(2, 4, 1, 8)
+    k, v = ctx.update_cache(1, None, False, k1, v1)
+    assert k.shape == (2, 4, 6, 8) and torch.equal(k[:, :, :5], k0) and torch.equal(v[:, :, 5:], v1)
+    assert float(ctx.kv_cache[1][0][:, :, 6:].abs().sum()) == 0 and float(ctx.kv_cache[0][0].abs().sum()) == 0
+    ctx.release_workspace()
+    cfg = types.SimpleNamespace(hidden_size=16, intermediate_size=32, mlp_act_func_type=None, dtype=torch.float32)
+    from deepspeed_b200.utils.types import ActivationFuncType
+    cfg.mlp_act_func_type = ActivationFuncType.GELU
+    mlp = DeepSpeedMoEMLP(cfg)
+    for p in mlp.parameters():
+        torch.nn.init.normal_(p, std=0.1)
+    x = torch.randn(3, 16)
+    ref = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(x, mlp.inter_w, mlp.inter_b),
+                                                             approximate="tanh"), mlp.output_w, mlp.output_b)
+    got = mlp(x)
+    assert torch.allclose(got, ref, atol=1e-4) or torch.allclose(
+        got, torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(x, mlp.inter_w, mlp.inter_b)),
+                                        mlp.output_w, mlp.output_b), atol=1e-4)
