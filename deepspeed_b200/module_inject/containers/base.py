@@ -6,6 +6,7 @@ the canonical tensors for this tensor-parallel rank, instantiates the family's f
 wraps it in an adapter that speaks the original layer's calling convention (argument names, tuple-or-tensor return,
 HF ``Cache`` bookkeeping) so the surrounding Hugging Face model code keeps working unchanged.
 """
+from abc import ABC
 import inspect
 
 import torch
@@ -190,3 +191,10 @@ class BaseTransformerContainer:
         if device is not None:
             self.module.to(device)
         return InjectedLayer(self.module, self.child, self.layer_id, self.policy.causal())
+
+
+class BaseConvolutionContainer(ABC):
+    """Placeholder base for convolutional (diffusers) containers: they need no shared state (reference ``base.py:20``)."""
+
+    def __init__(self):
+        pass

@@ -36,41 +36,49 @@ class EvoformerFusedAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, do):
         q, k, v, bias1, bias2, o = ctx.saved_tensors
-        qt, kt, vt, dot = (t.transpose(-2, -3) for t in (q, k, v, do))
-        shape = qt.shape
-        Q, K, V, O, DO = (_flat(t) for t in (qt, kt, vt, o, dot))
-        N, H, L, D = Q.shape
-        scale = D**-0.5
-        ct = torch.float64 if Q.dtype == torch.float64 else torch.float32
-        b1 = _flat(bias1.expand(*shape[:-3], *bias1.shape[-3:])) if bias1 is not None else None
-        b2 = _flat(bias2.expand(*shape[:-3], *bias2.shape[-3:])) if bias2 is not None else None
-        dQ, dK, dV = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
-        db1 = torch.zeros(bias1.shape, dtype=ct, device=q.device) if (bias1 is not None and
-                                                                                  ctx.needs_input_grad[3]) else None
-        db2 = torch.zeros(bias2.shape, dtype=ct, device=q.device) if (bias2 is not None and
-                                                                                  ctx.needs_input_grad[4]) else None
-        for s in range(0, N, ctx.chunk):
-            e = min(s + ctx.chunk, N)
-            sc = torch.matmul(Q[s:e].to(ct), K[s:e].to(ct).transpose(-1, -2)) * scale
-            if b1 is not None:
-                sc = sc + b1[s:e].to(ct)
-            if b2 is not None:
-                sc = sc + b2[s:e].to(ct)
-            P = torch.softmax(sc, -1)
-            dOf = DO[s:e].to(ct)
-            dV[s:e] = torch.matmul(P.transpose(-1, -2), dOf).to(V.dtype)
-            dP = torch.matmul(dOf, V[s:e].to(ct).transpose(-1, -2))
-            delta = (dOf * O[s:e].to(ct)).sum(-1, keepdim=True)
-            dS = P * (dP - delta)
-            dQ[s:e] = (torch.matmul(dS, K[s:e].to(ct)) * scale).to(Q.dtype)
-            dK[s:e] = (torch.matmul(dS.transpose(-1, -2), Q[s:e].to(ct)) * scale).to(K.dtype)
-            if db1 is not None:
-                _accum_bias_grad(db1, dS, bias1, shape, s, e)
-            if db2 is not None:
-                _accum_bias_grad(db2, dS, bias2, shape, s, e)
-        un = lambda t: t.view(shape).transpose(-2, -3)
-        return (un(dQ), un(dK), un(dV), db1.to(bias1.dtype) if db1 is not None else None,
-                db2.to(bias2.dtype) if db2 is not None else None, None)
+        dq, dk, dv, db1, db2 = attention_bwd(do, q, k, v, o.transpose(-2, -3), None, bias1, bias2,
+                                             bias1 is not None and ctx.needs_input_grad[3],
+                                             bias2 is not None and ctx.needs_input_grad[4], chunk=ctx.chunk)
+        return dq, dk, dv, db1, db2, None
+
+
+def attention_bwd(dO, Q, K, V, O, lse, bias1, bias2, bias1_grad, bias2_grad, chunk=64):
+    """Gradients of evoformer attention for ``[*, L, H, D]`` operands (reference ``evoformer_attn.py:33``).  The softmax is
+    recomputed chunk by chunk over the flattened leading dims (``lse`` is accepted for signature parity and not needed);
+    returns ``(dQ, dK, dV, dB1, dB2)`` with ``None`` for bias gradients that were not requested."""
+    qt, kt, vt, ot, dot = (t.transpose(-2, -3) for t in (Q, K, V, O, dO))
+    shape = qt.shape
+    Qf, Kf, Vf, Of, DOf = (_flat(t) for t in (qt, kt, vt, ot, dot))
+    N, H, L, D = Qf.shape
+    scale = D**-0.5
+    ct = torch.float64 if Qf.dtype == torch.float64 else torch.float32
+    b1 = _flat(bias1.expand(*shape[:-3], *bias1.shape[-3:])) if bias1 is not None else None
+    b2 = _flat(bias2.expand(*shape[:-3], *bias2.shape[-3:])) if bias2 is not None else None
+    dQ, dK, dV = torch.empty_like(Qf), torch.empty_like(Kf), torch.empty_like(Vf)
+    db1 = torch.zeros(bias1.shape, dtype=ct, device=Q.device) if (bias1 is not None and bias1_grad) else None
+    db2 = torch.zeros(bias2.shape, dtype=ct, device=Q.device) if (bias2 is not None and bias2_grad) else None
+    for s in range(0, N, chunk):
+        e = min(s + chunk, N)
+        sc = torch.matmul(Qf[s:e].to(ct), Kf[s:e].to(ct).transpose(-1, -2)) * scale
+        if b1 is not None:
+            sc = sc + b1[s:e].to(ct)
+        if b2 is not None:
+            sc = sc + b2[s:e].to(ct)
+        P = torch.softmax(sc, -1)
+        dOc = DOf[s:e].to(ct)
+        dV[s:e] = torch.matmul(P.transpose(-1, -2), dOc).to(Vf.dtype)
+        dP = torch.matmul(dOc, Vf[s:e].to(ct).transpose(-1, -2))
+        delta = (dOc * Of[s:e].to(ct)).sum(-1, keepdim=True)
+        dS = P * (dP - delta)
+        dQ[s:e] = (torch.matmul(dS, Kf[s:e].to(ct)) * scale).to(Qf.dtype)
+        dK[s:e] = (torch.matmul(dS.transpose(-1, -2), Qf[s:e].to(ct)) * scale).to(Kf.dtype)
+        if db1 is not None:
+            _accum_bias_grad(db1, dS, bias1, shape, s, e)
+        if db2 is not None:
+            _accum_bias_grad(db2, dS, bias2, shape, s, e)
+    un = lambda t: t.view(shape).transpose(-2, -3)
+    return (un(dQ), un(dK), un(dV), db1.to(bias1.dtype) if db1 is not None else None,
+            db2.to(bias2.dtype) if db2 is not None else None)
 
 
 def _accum_bias_grad(db, dS, bias, full_shape, s, e):

@@ -173,3 +173,24 @@ class DeepSpeedTransformerLayer(nn.Module):
         if not c.pre_layer_norm:
             out = T.layer_norm(out, self.norm_w, self.norm_b, c.layer_norm_eps)
         return (out, ) if c.return_tuple else out
+
+
+class DeepSpeedTransformerFunction:
+    """Functional entry point of the fused training layer (reference ``transformer.py:143``).  The reference routes forward
+    and backward through one hand-written autograd ``Function``; here the layer is a composition of fused autograd ops, so
+    ``apply`` runs the layer's stages with an explicit parameter list and autograd differentiates it."""
+
+    @staticmethod
+    def apply(input, input_mask, self, grads, layer_id, attn_qkvw, attn_qkvb, attn_ow, attn_ob, attn_nw, attn_nb, inter_w,
+              inter_b, output_w, output_b, norm_w, norm_b, config):
+        names = ("attn_qkvw", "attn_qkvb", "attn_ow", "attn_ob", "attn_nw", "attn_nb", "inter_w", "inter_b", "output_w",
+                 "output_b", "norm_w", "norm_b")
+        given = (attn_qkvw, attn_qkvb, attn_ow, attn_ob, attn_nw, attn_nb, inter_w, inter_b, output_w, output_b, norm_w, norm_b)
+        saved = {n: self._parameters[n] for n in names}
+        try:
+            for n, t in zip(names, given):  # run with the caller's tensors (they may be views / re-materialised copies)
+                self._parameters[n] = t
+            out = DeepSpeedTransformerLayer.forward(self, input, input_mask, grads=grads)
+        finally:
+            self._parameters.update(saved)
+        return out[0] if isinstance(out, tuple) else out
