@@ -31,3 +31,18 @@ class DeepSpeedAutotuningConfig(DeepSpeedConfigModel):
 
 def get_autotuning_config(param_dict):
     return DeepSpeedAutotuningConfig(**(param_dict.get("autotuning") or {}))
+
+
+MODEL_INFO_KEY_DEFAULT_DICT = {"profile": False, "num_params": None, "hidden_size": None, "num_layers": None}
+
+
+def get_model_info_config(param_dict):
+    """The ``autotuning.model_info`` section with defaults filled in, or ``None`` when absent."""
+    sec = param_dict.get("model_info")
+    if sec is None:
+        return None
+    return {k: sec.get(k, d) for k, d in MODEL_INFO_KEY_DEFAULT_DICT.items()}
+
+
+def get_default_model_info_config():
+    return dict(MODEL_INFO_KEY_DEFAULT_DICT)

@@ -597,3 +597,6 @@ def init_deepspeed_backend(ds_backend=None, timeout=None, init_method=None):
 def timed_op(func):
     """Decorator form of the comms-logger instrumentation (reference ``timed_op``)."""
     return _timed(func.__name__)(func)
+
+
+from torch.distributed import ProcessGroup  # noqa: E402,F401  (type used in signatures of the reference API)

@@ -18,3 +18,6 @@ class CommsConfig:
     def __init__(self, ds_config: dict):
         self.comms_logger = CommsLoggerConfig(**ds_config.get("comms_logger", {}))
         self.comms_logger_enabled = self.comms_logger.enabled
+
+
+DeepSpeedCommsConfig = CommsConfig  # reference class name

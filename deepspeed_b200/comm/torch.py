@@ -217,3 +217,15 @@ class TorchBackend(Backend):
         from torch.distributed.device_mesh import init_device_mesh
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         return init_device_mesh(dev, mesh_shape, mesh_dim_names=mesh_dim_names)
+
+
+def disable_compiler_collective(func):
+    """Decorator kept for parity (reference ``comm/torch.py:23``): collectives are never traced here (no ``torch.compile`` on
+    the hot path), so the function is returned unchanged."""
+    return func
+
+
+def get_coalescing_manager(group, device, reqs, async_op):
+    """Context manager that batches the collectives issued inside it into one NCCL group call."""
+    import torch
+    return torch.distributed.distributed_c10d._coalescing_manager(group, device=device, async_ops=async_op)

@@ -116,3 +116,12 @@ def cli_main():
 
 if __name__ == "__main__":
     cli_main()
+
+
+def installed_cann_path():
+    """Ascend toolkits are not a target of this build (single-vendor: NVIDIA sm_100a)."""
+    return None
+
+
+def installed_cann_version():
+    return None

@@ -22,3 +22,18 @@ class BlockedFlashAttn(DSKernelBase):
         out.copy_(R.paged_attention(qkv, kv_cache, seq_of, pos_of, block_table, n_q_heads, n_kv_heads, self.head_size, block_size,
                                     softmax_scale))
         return out
+
+
+def get_q_block_size(head_size: int) -> int:
+    """Query tile of the prefill attention kernel: 128 rows (one tcgen05 M=128 tile) for every head size it supports."""
+    if head_size % 16 != 0 or head_size > 256:
+        raise ValueError(f"unsupported head size {head_size}")
+    return 128
+
+
+def get_kv_block_size(head_size: int) -> int:
+    """Preferred KV-cache page: 128 tokens up to head size 128 (one TMA box per page), 64 above so a K+V page pair stays
+    within the shared-memory stage budget."""
+    if head_size % 16 != 0 or head_size > 256:
+        raise ValueError(f"unsupported head size {head_size}")
+    return 128 if head_size <= 128 else 64

@@ -27,3 +27,13 @@ class MLP2Parameter(ParameterBase):
 
     def finalize(self) -> torch.Tensor:
         return self.inference_model.transform_mlp_2_param(self.params)
+
+
+class FusedGatedMLPParameter(ParameterBase):
+    """Checkpoints that already store ``[gate; up]`` as one matrix (Phi-3 ``gate_up_proj``): split, then hand both halves
+    to the model in the order its fused SwiGLU kernel expects (reference ``mlp_parameters.py:69``)."""
+    params: torch.Tensor
+
+    def finalize(self) -> torch.Tensor:
+        half = self.params.shape[0] // 2
+        return self.inference_model.transform_mlp_1_param(torch.cat([self.params[:half], self.params[half:]], dim=0))

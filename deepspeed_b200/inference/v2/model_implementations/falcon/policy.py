@@ -1,6 +1,6 @@
 """Policy for Falcon (parallel attention/MLP, multi-query or grouped fused QKV) (reference ``model_implementations/falcon/policy.py``)."""
 from ..inference_policy_base import ContainerMap, InferenceV2Policy
-from .container import FalconNonTransformerContainer, FalconTransformerContainer
+from .container import FalconNewArchTransformerContainer, FalconNonTransformerContainer, FalconTransformerContainer
 from .model import FalconInferenceModel
 
 
@@ -18,7 +18,9 @@ class FalconPolicy(InferenceV2Policy):
         """Declarative checkpoint map: one transformer container per layer + the non-transformer container."""
         model = model if model is not None else self.instantiate_model(None)
         cmap = ContainerMap()
-        cmap.set_transformer_params(["transformer.h"], [FalconTransformerContainer(model) for _ in range(model.num_layers)])
+        new_arch = bool(getattr(model.spec, "extras", {}).get("new_decoder_architecture"))
+        layer_cls = FalconNewArchTransformerContainer if new_arch else FalconTransformerContainer
+        cmap.set_transformer_params(["transformer.h"], [layer_cls(model) for _ in range(model.num_layers)])
         cmap.set_non_transformer_params(FalconNonTransformerContainer(model))
         cmap.set_unmapped_params([])
         return cmap

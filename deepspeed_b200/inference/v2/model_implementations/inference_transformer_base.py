@@ -16,3 +16,22 @@ class DSTransformerModelBase(DSInferenceModelBase):
 
 
 DSTransformerModelBase.register(RaggedTransformer)
+
+
+class DSMoETransformerModelBase(DSTransformerModelBase):
+    """Adds the routed-expert properties (reference ``inference_transformer_base.py:532``): ``RaggedTransformer`` serves
+    dense and MoE families alike, its ``ArchSpec`` carries the expert count / top-k / score normalisation."""
+    n_experts: int
+    n_top_k: int
+    normalize_expert_scores: bool
+
+    @classmethod
+    def __subclasshook__(cls, other):
+        return NotImplemented
+
+    @staticmethod
+    def is_moe(model) -> bool:
+        return int(getattr(getattr(model, "spec", None), "num_experts", 0) or 0) > 0
+
+
+DSMoETransformerModelBase.register(RaggedTransformer)

@@ -123,3 +123,10 @@ class RaggedBatchWrapper:
     @property
     def is_pure_decode(self) -> bool:
         return self._n_seqs == self._n_tokens and self._n_seqs > 0
+
+
+def to_padded(original_size: int) -> int:
+    """Round a token / sequence count up to the granularity CUDA-graph buckets and GEMM tiles like: 64 up to 512, 128
+    above (reference ``ragged_wrapper.py:17``)."""
+    g = 64 if original_size <= 512 else 128
+    return (original_size + g - 1) // g * g

@@ -22,15 +22,20 @@ def env_mapping(env, rank_name_list=None, local_rank_name_list=None):
     return env
 
 
-def main(argv=None):
-    p = argparse.ArgumentParser()
+def parse_args(args=None):
+    p = argparse.ArgumentParser(description="DeepSpeed launcher helper: maps the MPI/Slurm environment onto RANK/LOCAL_RANK "
+                                "and runs the user script")
     p.add_argument("--launcher", default="mpich")
     p.add_argument("--module", action="store_true")
     p.add_argument("--no_python", action="store_true")
     p.add_argument("--no_local_rank", action="store_true")
     p.add_argument("user_script")
     p.add_argument("user_args", nargs=argparse.REMAINDER)
-    a = p.parse_args(argv)
+    return p.parse_args(args)
+
+
+def main(argv=None):
+    a = parse_args(argv)
     env = env_mapping(os.environ.copy())
     cmd = ([] if a.no_python else [sys.executable, "-u"] + (["-m"] if a.module else [])) + [a.user_script]
     if not a.no_local_rank:

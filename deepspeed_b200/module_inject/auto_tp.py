@@ -191,3 +191,53 @@ def tp_model_init(model, tp_size, dtype, config=None, **kwargs):
     AutoTP(model, mp_group=tp_group, mp_size=tp_size, **kwargs).replace()
     model.ds_autotp_parsed = True
     return model
+
+
+def move(tensor, device, copy=True):
+    from .layers import move as _move
+    return _move(tensor, device, copy)
+
+
+class Loading:
+    """Checkpoint-to-module loading helpers for meta-initialised models (reference ``auto_tp.py:132``): modules that AutoTP
+    does not shard (norms, embeddings, plain linears) still need their weights pulled from the state dict."""
+    _LAYERS = (nn.Linear, nn.Embedding, nn.LayerNorm)
+    _NAME_RX = ("RMSNorm", "LayerNorm", "RotaryEmbedding", "SharedEmbedding", "LearnedPositionalEmbedding", "FalconLinear",
+                "MoEGate")
+
+    @staticmethod
+    def is_load_module(module):
+        name = module._get_name()
+        return isinstance(module, Loading._LAYERS) or any(k in name for k in Loading._NAME_RX)
+
+    @staticmethod
+    def _real(t):
+        """A meta tensor cannot be copied into: swap it for host storage of the same shape."""
+        if t.data.is_meta:
+            return nn.Parameter(torch.empty_like(t.data, device="cpu"), requires_grad=t.requires_grad)
+        return t
+
+    @staticmethod
+    def load_buffer(module, state_dict, prefix):
+        for name, buf in list(module._buffers.items()):
+            if buf is None:
+                continue
+            if buf.is_meta:
+                module._buffers[name] = torch.empty_like(buf, device="cpu")
+            if prefix + name in state_dict:
+                module._buffers[name].data.copy_(state_dict[prefix + name])
+
+    @staticmethod
+    def load(module, state_dict, prefix, mp_group=None):
+        slicer = ReplaceWithTensorSlicing(mp_group=mp_group)
+        target = module if hasattr(module, "weight") else getattr(module, "norm", None)
+        for attr in ("weight", "bias"):
+            key = prefix + attr
+            if key not in state_dict or target is None or getattr(target, attr, None) is None:
+                continue
+            cur = Loading._real(getattr(target, attr))
+            if attr == "weight" and "query_key_value" in prefix and target is module:
+                new = slicer.strided_copy(cur.data, state_dict[key], num_splits=3)
+            else:
+                new = slicer.copy(cur.data, state_dict[key])
+            setattr(target, attr, new if isinstance(new, nn.Parameter) else nn.Parameter(new, requires_grad=cur.requires_grad))

@@ -429,3 +429,17 @@ class TensorParallelIcShardConv2d(TensorParallelConv2d):
         if self.world_size > 1:
             dist.inference_all_reduce(out, group=self.mp_group)
         return out
+
+
+def set_autotp_mode(training=False):
+    """Select what AutoTP layers are built for: training (autograd-aware collectives) or inference."""
+    global AUTOTP_TRAINING_MODE
+    AUTOTP_TRAINING_MODE = bool(training)
+
+
+def move(tensor, device, copy=True):
+    """Materialise ``tensor`` on ``device``: meta tensors become uninitialised storage, real ones are copied so the (often
+    much larger, un-sharded) source can be freed."""
+    if tensor.is_meta:
+        return torch.empty_like(tensor, device=device)
+    return tensor.to(device, copy=copy)

@@ -253,3 +253,29 @@ class MOELayer(nn.Module):
             C = C_full
         y = moe_ops.gather(eo.reshape(E * C, H), g.weights.to(torch.float32), slots, T, k)
         return y.reshape(x.shape).to(x.dtype)
+
+
+USE_EINSUM = True
+
+
+def einsum(rule, a, b):
+    """``torch.einsum`` with the handful of contractions MoE gating / dispatch uses rewritten as plain broadcasts and
+    matmuls (they hit cuBLAS directly and skip einsum's planning; reference ``sharded_moe.py:117``)."""
+    if USE_EINSUM:
+        return torch.einsum(rule, a, b)
+    if rule == "s,se->se":
+        return a.reshape(a.shape[0], -1) * b
+    if rule == "se,sc->sec":
+        return a.unsqueeze(2) * b.unsqueeze(1)
+    if rule == "se,se->s":
+        return (a * b).sum(-1)
+    if rule == "se,sec->sec":
+        return a.unsqueeze(2) * b
+    if rule == "sec,sm->ecm":
+        s, e, c = a.shape
+        return torch.matmul(a.reshape(s, e * c).t(), b).reshape(e, c, b.shape[1])
+    if rule == "sec,ecm->sm":
+        return torch.matmul(a.reshape(a.shape[0], -1), b.reshape(-1, b.shape[-1]))
+    if rule == "ks,ksm->sm":
+        return (a.unsqueeze(-1) * b).sum(0)
+    return torch.einsum(rule, a, b)

@@ -16,3 +16,9 @@ def matmul_fp8(inp, weight, scale, quantization_group_size, quantizer: FP_Quanti
     q.orig_shape, q.orig_dtype = torch.Size([k, n]), inp.dtype
     w = q.dequantize(weight, q_bits=8, q_mantisa_bits=3, scale=scale).view(k, n).to(inp.dtype)
     return torch.matmul(inp, w)
+
+
+def matmul_fp8_fallback(inp, weight, scale, quantization_group_size, quantizer: FP_Quantize = None):
+    """Library-only path (dequantise → ``torch.matmul``); what ``matmul_fp8`` does for shapes the fused weight-only kernel
+    does not cover (reference ``fp8_gemm.py``)."""
+    return matmul_fp8(inp, weight, scale, quantization_group_size, quantizer)

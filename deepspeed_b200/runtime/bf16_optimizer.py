@@ -14,3 +14,9 @@ def BF16_Optimizer(init_optimizer, param_names=None, mpu=None, clip_grad=0.0, no
                                 model_dtype=torch.bfloat16, grad_accum_dtype=grad_acc_dtype or torch.float32,
                                 gradient_accumulation_steps=gradient_accumulation_steps, gradient_clipping=clip_grad, mpu=mpu,
                                 timers=timers)
+
+
+def print_rank_0(message, debug=False, force=False):
+    from deepspeed_b200 import comm as dist
+    if (debug or force) and (not dist.is_initialized() or dist.get_rank() == 0):
+        print(message)

@@ -130,3 +130,85 @@ class DistributedDataAnalyzer(DataAnalyzer):
 
     def run_map_reduce(self):
         super().run_map_reduce(self.comm_group)
+
+
+class Dist:
+    """Collective helpers over tensors of per-rank different length (reference ``data_analyzer.py:732``)."""
+
+    @staticmethod
+    def min_max(tensor, comm_group):
+        """Global (min, max); meaningful on rank 0 of the group (reduce, not all-reduce)."""
+        from deepspeed_b200 import comm as dist
+        lo, hi = tensor.min().clone(), tensor.max().clone()
+        dist.reduce(lo, 0, op=dist.ReduceOp.MIN, group=comm_group)
+        dist.reduce(hi, 0, op=dist.ReduceOp.MAX, group=comm_group)
+        return lo.item(), hi.item()
+
+    @staticmethod
+    def gather_v(tensor, dst, comm_group, num_workers, worker_id):
+        """Variable-length gather to ``dst``: lengths are exchanged first, payloads padded to the longest, padding dropped
+        on arrival.  Returns the list of per-rank tensors on ``dst`` and ``None`` elsewhere."""
+        from deepspeed_b200 import comm as dist
+        n = torch.tensor([tensor.shape[0]], dtype=torch.int64, device=tensor.device)
+        sizes = torch.zeros(num_workers, dtype=torch.int64, device=tensor.device)
+        dist.all_gather_into_tensor(sizes, n, group=comm_group)
+        longest = int(sizes.max())
+        padded = torch.zeros((longest, ) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        padded[:tensor.shape[0]] = tensor
+        parts = [torch.empty_like(padded) for _ in range(num_workers)]
+        dist.all_gather(parts, padded, group=comm_group)  # gloo/nccl agnostic; the extra copies are tiny index tensors
+        if worker_id != dst:
+            return None
+        return [p[:int(s)] for p, s in zip(parts, sizes)]
+
+    @staticmethod
+    def sample_sort(tensor, comm_group, num_workers, n_samples=100):
+        """Distributed sample sort of the rows of a 2-D tensor by their first column: every rank ends up with one
+        contiguous, locally sorted key range (rank r's keys ≤ rank r+1's)."""
+        from deepspeed_b200 import comm as dist
+        order = torch.argsort(tensor[:, 0], stable=True)
+        tensor = tensor[order]
+        if num_workers == 1:
+            return tensor
+        n = tensor.shape[0]
+        if n > 0:
+            pick = torch.round(torch.linspace(0, n - 1, n_samples)).long()
+            samples = tensor[pick, 0].contiguous()
+        else:
+            samples = torch.zeros(n_samples, dtype=tensor.dtype, device=tensor.device)
+        allsamp = [torch.zeros_like(samples) for _ in range(num_workers)]
+        dist.all_gather(allsamp, samples, group=comm_group)
+        allsamp = torch.cat(allsamp).sort().values
+        cuts = allsamp[torch.round(torch.linspace(0, allsamp.numel() - 1, num_workers + 1)).long()].clone()
+        cuts[0], cuts[-1] = torch.iinfo(torch.int64).min if not tensor.is_floating_point() else float("-inf"), \\
+            (torch.iinfo(torch.int64).max if not tensor.is_floating_point() else float("inf"))
+        sends = [tensor[(tensor[:, 0] >= cuts[r]) & (tensor[:, 0] < cuts[r + 1])].contiguous() for r in range(num_workers)]
+        me = dist.get_rank(group=comm_group)
+        got = []
+        for r in range(num_workers):  # one variable-length gather per destination rank
+            part = Dist.gather_v(sends[r], r, comm_group, num_workers, me)
+            if part is not None:
+                got = part
+        out = torch.cat(got) if got else tensor[:0]
+        return out[torch.argsort(out[:, 0], stable=True)]
+
+
+def test_compare_both_data_analyzers(dataset, save_path="./_data_analyzer_cmp", num_workers=1, metric_names=("seqlen", ),
+                                     metric_functions=None, metric_types=("single_value_per_sample", )):
+    """Run the single-process and the distributed analyzer on ``dataset`` and check that they wrote identical index files
+    (reference ``data_analyzer.py:843``: a self-check users run before trusting the distributed path)."""
+    import filecmp
+    import os
+    fns = metric_functions or [lambda batch: torch.tensor([len(x) for x in batch]) if isinstance(batch, (list, tuple))
+                               else (batch != 0).sum(-1)]
+    a_dir, b_dir = os.path.join(save_path, "single"), os.path.join(save_path, "distributed")
+    DataAnalyzer(dataset, num_workers=1, worker_id=0, batch_size=4, metric_names=list(metric_names), metric_functions=list(fns),
+                 metric_types=list(metric_types), save_path=a_dir).run_map_reduce()
+    DistributedDataAnalyzer(dataset, num_workers=num_workers, worker_id=0, batch_size=4, metric_names=list(metric_names),
+                            metric_functions=list(fns), metric_types=list(metric_types), save_path=b_dir).run_map_reduce()
+    same = True
+    for root, _, files in os.walk(a_dir):
+        for f in files:
+            other = os.path.join(b_dir, os.path.relpath(os.path.join(root, f), a_dir))
+            same = same and os.path.exists(other) and filecmp.cmp(os.path.join(root, f), other, shallow=False)
+    return same

@@ -120,3 +120,7 @@ def CreateLossScaler(dtype, static_loss_scale, dynamic_scaling, dynamic_loss_arg
         return DynamicLossScaler(dtype=dtype, **kwargs)
     loss_scale_value = static_loss_scale if dtype == torch.half else 1.0
     return LossScaler(scale=loss_scale_value or 1.0)
+
+
+def to_python_float(t):
+    return t.item() if hasattr(t, "item") else t[0]

@@ -337,3 +337,7 @@ class PipelineEngine(DeepSpeedEngine):
             tag = open(os.path.join(load_dir, "latest")).read().strip()
         self._curr_ckpt_path = os.path.join(load_dir, str(tag))
         return super().load_checkpoint(load_dir, tag, **kw)
+
+
+def is_even(number):
+    return number % 2 == 0

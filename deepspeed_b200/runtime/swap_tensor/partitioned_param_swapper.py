@@ -107,3 +107,9 @@ class AsyncPartitionedParameterSwapper:
 
     def status(self, pid):
         return self._status.get(pid, PartitionedParamStatus.NOT_AVAILABLE)
+
+
+def print_rank_0(message, debug=False, force=False):
+    from deepspeed_b200 import comm as dist
+    if (debug or force) and (not dist.is_initialized() or dist.get_rank() == 0):
+        print(message)

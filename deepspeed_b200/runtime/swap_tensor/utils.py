@@ -170,3 +170,12 @@ class SwapBufferManager:
     def free(self, buffers):
         for b in buffers:
             self.free_buffer_index.append(self.used_buffer_index.pop(id(b)))
+
+
+def print_object(obj, name, exclude_list=()):
+    """Log every attribute of ``obj`` as an aligned ``name ..... value`` table."""
+    from deepspeed_b200.utils.logging import logger
+    logger.info(f"{name}:")
+    for arg in sorted(vars(obj)):
+        if arg not in exclude_list:
+            logger.info(f"  {arg} {'.' * max(1, 29 - len(arg))} {getattr(obj, arg)}")

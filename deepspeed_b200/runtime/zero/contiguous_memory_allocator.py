@@ -108,3 +108,9 @@ class ContiguousMemoryAllocator:
                 for param, numel, shape in b.params:
                     param.data = b.tensor.narrow(0, 0, numel).view(shape)
             cur += b.size
+
+
+def print_rank_0(message, debug=False, force=False):
+    from deepspeed_b200 import comm as dist
+    if (debug or force) and (not dist.is_initialized() or dist.get_rank() == 0):
+        print(message)

@@ -60,3 +60,9 @@ class LinearModuleForZeroStage3(nn.Module):
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
+
+
+def print_rank_0(message, debug=False, force=False):
+    from deepspeed_b200 import comm as dist
+    if (debug or force) and (not dist.is_initialized() or dist.get_rank() == 0):
+        print(message)

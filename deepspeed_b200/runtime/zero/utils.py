@@ -82,3 +82,9 @@ def get_mapping_to_flat_buffer(tensors):
         out.append((t, offset, t.numel()))
         offset += t.numel()
     return out
+
+
+def is_zero_param(parameter):
+    """Is ``parameter`` managed (sharded) by ZeRO-3?"""
+    import torch
+    return torch.is_tensor(parameter) and hasattr(parameter, "ds_id")

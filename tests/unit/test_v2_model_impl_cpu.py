@@ -182,3 +182,34 @@ def test_parameter_and_container_metaclasses():
         assert c.set_dependency(name, t)
     assert c.is_initialized and c.w.numel() == 4 and not c.set_dependency("nope", torch.zeros(1))
     assert isinstance(InferenceV2Policy, PolicyMeta) and "Llama2Policy" in POLICIES_BY_NAME
+
+
+def test_falcon_new_arch_container_and_misc_v2_helpers():
+    import types
+    import torch
+    from deepspeed_b200.inference.v2.model_implementations.falcon import FalconNewArchTransformerContainer, FalconPolicy
+    from deepspeed_b200.inference.v2.model_implementations.common_parameters.mlp_parameters import FusedGatedMLPParameter
+    from deepspeed_b200.inference.v2.model_implementations.inference_transformer_base import DSMoETransformerModelBase
+    from deepspeed_b200.inference.v2.modules.implementations.linear.quantized_linear import fp_quantize
+    from deepspeed_b200.inference.v2.ragged.ragged_wrapper import to_padded
+    from deepspeed_b200.inference.v2.kernels.ragged_ops.blocked_flash.blocked_flash import get_kv_block_size, get_q_block_size
+    cfg = {"model_type": "falcon", "vocab_size": 64, "hidden_size": 32, "num_hidden_layers": 1, "num_attention_heads": 4,
+           "num_kv_heads": 2, "new_decoder_architecture": True, "parallel_attn": True, "bias": False}
+    pol = FalconPolicy(cfg)
+    model = pol.instantiate_model(None)
+    cmap = pol.build_container_map(model)
+    layer = cmap.transformer_params[0] if not callable(cmap.transformer_params) else list(cmap.transformer_params())[0]
+    assert isinstance(layer, FalconNewArchTransformerContainer)
+    for name, shape in (("self_attention.query_key_value.weight", (2 * (2 + 2) * 8, 32)), ("self_attention.dense.weight", (32, 32)),
+                        ("mlp.dense_h_to_4h.weight", (128, 32)), ("mlp.dense_4h_to_h.weight", (32, 128)), ("ln_attn.weight", (32, )),
+                        ("ln_attn.bias", (32, )), ("ln_mlp.weight", (32, )), ("ln_mlp.bias", (32, ))):
+        assert layer.set_dependency(name, torch.randn(*shape)), name
+    assert layer.is_initialized
+    fake = types.SimpleNamespace(transform_mlp_1_param=lambda t: t)
+    p = FusedGatedMLPParameter(fake)
+    p.params = torch.arange(8.0).reshape(4, 2)
+    assert torch.equal(p.result, torch.arange(8.0).reshape(4, 2))
+    assert DSMoETransformerModelBase.is_moe(types.SimpleNamespace(spec=types.SimpleNamespace(num_experts=8)))
+    q, s = fp_quantize(torch.randn(4, 32).half())
+    assert q.dtype == torch.float16 and s.shape == (4, 1) and float(q.abs().max()) <= 28.0
+    assert to_padded(1) == 64 and to_padded(513) == 640 and get_q_block_size(128) == 128 and get_kv_block_size(256) == 64
