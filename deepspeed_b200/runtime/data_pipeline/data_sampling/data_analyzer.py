@@ -180,8 +180,10 @@ class Dist:
         dist.all_gather(allsamp, samples, group=comm_group)
         allsamp = torch.cat(allsamp).sort().values
         cuts = allsamp[torch.round(torch.linspace(0, allsamp.numel() - 1, num_workers + 1)).long()].clone()
-        cuts[0], cuts[-1] = torch.iinfo(torch.int64).min if not tensor.is_floating_point() else float("-inf"), \\
-            (torch.iinfo(torch.int64).max if not tensor.is_floating_point() else float("inf"))
+        if tensor.is_floating_point():
+            cuts[0], cuts[-1] = float("-inf"), float("inf")
+        else:
+            cuts[0], cuts[-1] = torch.iinfo(tensor.dtype).min, torch.iinfo(tensor.dtype).max
         sends = [tensor[(tensor[:, 0] >= cuts[r]) & (tensor[:, 0] < cuts[r + 1])].contiguous() for r in range(num_workers)]
         me = dist.get_rank(group=comm_group)
         got = []

@@ -169,3 +169,34 @@ def test_indexed_dataset_formats_and_interop(tmp_path):
     assert mine.dtype == np.int32 and all(np.array_equal(mine[i], s) for i, s in enumerate(samples))
     rl = R.IndexedDataset(pre)
     assert all(np.array_equal(rl[i], s) for i, s in enumerate(samples))
+
+
+def _dist_helpers():
+    import torch
+    import deepspeed_b200 as ds
+    from deepspeed_b200 import comm as dist
+    from deepspeed_b200.runtime.data_pipeline.data_sampling.data_analyzer import Dist
+    ds.init_distributed()
+    r, w = dist.get_rank(), dist.get_world_size()
+    t = torch.arange(3 + 2 * r, dtype=torch.int64) + 10 * r
+    lo, hi = Dist.min_max(t.clone(), None)
+    if r == 0:
+        assert (lo, hi) == (0, 14)
+    parts = Dist.gather_v(t, 0, None, w, r)
+    if r == 0:
+        assert [p.tolist() for p in parts] == [[0, 1, 2], [10, 11, 12, 13, 14]]
+    else:
+        assert parts is None
+    g = torch.Generator().manual_seed(r)
+    rows = torch.stack([torch.randint(0, 1000, (50, ), generator=g), torch.arange(50) + 100 * r], 1)
+    mine = Dist.sample_sort(rows, None, w, n_samples=10)
+    assert torch.all(mine[1:, 0] >= mine[:-1, 0])
+    edge = torch.tensor([int(mine[0, 0]) if len(mine) else 10**9, int(mine[-1, 0]) if len(mine) else -1, len(mine)])
+    allv = [torch.zeros_like(edge) for _ in range(w)]
+    dist.all_gather(allv, edge)
+    assert sum(int(v[2]) for v in allv) == 100 and int(allv[0][1]) <= int(allv[1][0])
+
+
+def test_data_analyzer_dist_helpers():
+    from tests.common import run_distributed
+    run_distributed(_dist_helpers, 2)
