@@ -38,3 +38,14 @@ class Softmax:
         e = torch.exp(v - mx[:, rid][..., None])
         den = torch.zeros(B, self.n_groups, blk, device=dev).index_add_(1, rid, e.sum(-1))
         return (e / den[:, rid][..., None]).to(x.dtype)
+
+
+def next_power_of_2(n):
+    """Smallest power of two ≥ ``n`` (row-tile sizing helper of the reference softmax)."""
+    n = int(n)
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+def num_warps(n):
+    """Warps per CTA the block-sparse softmax uses for a row of ``n`` elements: 4 / 8 / 16 by row length."""
+    return 4 if n < 512 else (8 if n < 2048 else 16)
