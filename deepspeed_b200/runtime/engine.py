@@ -49,6 +49,9 @@ def split_half_float_double_sparse(tensors):
     return order(sparse), order(dense)
 
 
+from deepspeed_b200.runtime.engine_accessors import EngineConfigAccessors  # noqa: E402
+
+
 class EngineTimers:
     """Names of the wall-clock timers the engine drives, grouped by phase (reference ``engine.py:149``)."""
 
@@ -66,7 +69,7 @@ class EngineTimers:
         self.global_timers = list(table["global"].values()) if enable_global_timers else []
 
 
-class DeepSpeedEngine(CheckpointMixin, nn.Module):
+class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
 
     def __init__(self, args=None, model=None, optimizer=None, model_parameters=None, training_data=None,
                  lr_scheduler=None, mpu=None, dist_init_required=None, collate_fn=None, config=None,
@@ -784,7 +787,7 @@ class DeepSpeedEngine(CheckpointMixin, nn.Module):
             if bucket:
                 self.allreduce_and_copy(bucket)
 
-    def sparse_allreduce(self, sparse_tensor, dp_group=None):
+    def sparse_allreduce(self, sparse_tensor, dp_group=None, dp_world_size=None):
         from deepspeed_b200.runtime.sparse_tensor import sparse_allreduce
         return sparse_allreduce(sparse_tensor, dp_group or self.seq_data_parallel_group)
 

@@ -305,3 +305,48 @@ def test_reference_public_names_exist_at_same_paths():
             if missing:
                 problems.append(f"{rel}: {missing}")
     assert not problems, "\n".join(problems)
+
+
+def _engine_accessors():
+    import torch
+    import deepspeed_b200 as ds
+    from deepspeed_b200.runtime import engine_accessors as A
+    from deepspeed_b200.runtime.sparse_tensor import SparseTensor
+    model = torch.nn.Linear(8, 8)
+    eng, *_ = ds.initialize(model=model, config={"train_batch_size": 2, "optimizer": {"type": "Adam", "params": {"lr": 1e-3}},
+                                                 "zero_optimization": {"stage": 1, "reduce_bucket_size": 1234},
+                                                 "flops_profiler": {"enabled": False, "profile_step": 7},
+                                                 "autotuning": {"enabled": False}})
+    names = list(A._DIRECT) + [n for sec in A._NESTED.values() for n in sec]
+    names += ["autotuning_enabled", "autotuning_metric_path", "autotuning_model_info_path", "autotuning_metric",
+              "autotuning_profile_model_info", "flops_profiler_enabled", "flops_profiler_profile_step", "flops_profiler_detailed",
+              "data_sampling_enabled", "curriculum_learning_enabled", "random_ltd_enabled", "zero_use_cpu_optimizer",
+              "zero_cpu_offload", "zero_partial_offload", "zero_nvme_offload_optimizer", "postscale_gradients",
+              "is_elastic_model_parallel_supported", "quantize_training", "get_pld_theta"]
+    for n in names:
+        getattr(eng, n)()  # every accessor resolves against a default config
+    assert eng.zero_reduce_bucket_size() == 1234 and eng.flops_profiler_profile_step() == 7 and not eng.zero_cpu_offload()
+    assert eng.autotuning_metric_path().endswith("autotuning_metric.json") and eng.postscale_gradients()
+    assert eng.communication_data_type == torch.float32
+    eng.communication_data_type = torch.bfloat16
+    assert eng.communication_data_type == torch.bfloat16
+    assert eng.is_map_style_dataset([1, 2]) and not eng.is_iterable_style_dataset([1])
+    from deepspeed_b200 import comm as dist
+    r = dist.get_rank()
+    dense = torch.zeros(6, 4)
+    dense[r] = r + 1.0
+    dense[4] = 1.0
+    sp = SparseTensor(dense)
+    sp.orig_dense_tensor = dense
+    want = torch.zeros(6, 4)
+    want[0], want[1], want[4] = 0.5, 1.0, 1.0
+    assert torch.allclose(eng.sparse_allreduce_bucket([sp], None)[0].to_dense(), want)
+    eng.sparse_allreduce_no_retain([sp], None)
+    assert torch.allclose(dense, want)
+    ts = [torch.full((3, ), float(r + 1)), torch.full((2, 2), float(2 * r))]
+    eng.allreduce_no_retain(ts, None, numel_per_bucket=2)
+    assert torch.allclose(ts[0], torch.full((3, ), 1.5)) and torch.allclose(ts[1], torch.full((2, 2), 1.0))
+
+
+def test_engine_config_accessors_and_sparse_collectives():
+    run_distributed(_engine_accessors, 2)
