@@ -213,3 +213,30 @@ def test_falcon_new_arch_container_and_misc_v2_helpers():
     q, s = fp_quantize(torch.randn(4, 32).half())
     assert q.dtype == torch.float16 and s.shape == (4, 1) and float(q.abs().max()) <= 28.0
     assert to_padded(1) == 64 and to_padded(513) == 640 and get_q_block_size(128) == 128 and get_kv_block_size(256) == 64
+
+
+def test_model_module_layer_builders_and_arch_properties():
+    import torch
+    from deepspeed_b200.inference.v2.inference_utils import ActivationType, NormTypeEnum
+    from deepspeed_b200.inference.v2.model_implementations.llama_v2.model import Llama2InferenceModel
+    from deepspeed_b200.inference.v2.model_implementations.mixtral.model import MixtralInferenceModel
+    from deepspeed_b200.inference.v2.modules.configs import PositionalEmbeddingType
+    cfg = {"model_type": "llama", "vocab_size": 64, "hidden_size": 64, "num_hidden_layers": 1, "num_attention_heads": 4,
+           "num_key_value_heads": 2, "intermediate_size": 64, "max_position_embeddings": 128, "rope_theta": 5000.0}
+    m = Llama2InferenceModel.from_hf_config(cfg, dtype=torch.float32, device="cpu")
+    assert m.mlp_activation_fn == ActivationType.SiGLU and m.norm_type == NormTypeEnum.RMSNorm and m.gated_mlp
+    assert m.positional_embedding_type == PositionalEmbeddingType.rotate_half and m.positional_embedding_config.theta_base == 5000.0
+    assert (m.n_heads_q_local, m.n_heads_kv_local, m.max_sequence_length) == (4, 2, 128)
+    qkv, out, m1, m2, norm = m.make_qkv_layer(), m.make_attn_out_layer(), m.make_mlp_1_layer(), m.make_mlp_2_layer(), m.make_norm_layer()
+    x = torch.randn(5, 64)
+    w_qkv = qkv.transform_param(torch.randn(16 * (4 + 4), 64))
+    assert qkv(x, w_qkv).shape == (5, 128)
+    w1 = m1.transform_param(torch.randn(128, 64))
+    h = m1(x, w1)
+    assert h.shape == (5, 64)  # gated: 2x rows in, intermediate out
+    assert m2(h, m2.transform_param(torch.randn(64, 64))).shape == (5, 64)
+    assert m.make_attn_layer() is m.attn and m.make_embedding_layer() is m.embed and m.make_unembedding_layer() is m.unembed
+    moe_cfg = {"model_type": "mixtral", "vocab_size": 64, "hidden_size": 64, "num_hidden_layers": 1, "num_attention_heads": 4,
+               "num_key_value_heads": 2, "intermediate_size": 64, "num_local_experts": 4, "num_experts_per_tok": 2}
+    mm = MixtralInferenceModel.from_hf_config(moe_cfg, dtype=torch.float32, device="cpu")
+    assert (mm.n_experts, mm.n_top_k) == (4, 2) and mm.make_moe_layer() is mm.moe
