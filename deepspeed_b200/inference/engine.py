@@ -302,6 +302,62 @@ class InferenceEngine(nn.Module):
         self._cuda_graphs = None
         InferenceEngine.inference_mp_group = None
 
+    # ---- model-specific patches of the AutoTP path (reference ``inference/engine.py:207-228``) ---------------------------
+    def remove_mask_prepare_for_bloom(self):
+        """BLOOM builds its own causal mask; the fused layers want the raw padding mask."""
+        tr = getattr(self.module, "transformer", None)
+        if tr is not None and hasattr(tr, "_prepare_attn_mask"):
+            tr._prepare_attn_mask = lambda attention_mask, *args, **kwargs: attention_mask
+
+    def build_alibi_tensor(self):
+        """Under tensor parallelism ALiBi slopes must be generated for this rank's heads only."""
+        from deepspeed_b200.module_inject import auto_tp_model_utils as U
+        tr = getattr(self.module, "transformer", None)
+        if tr is not None:
+            if hasattr(tr, "build_alibi_tensor"):
+                tr.build_alibi_tensor = U.build_bloom_alibi_tensor
+            if hasattr(tr, "build_mpt_alibi_tensor"):
+                tr.build_mpt_alibi_tensor_orig = tr.build_mpt_alibi_tensor
+                tr.__class__.build_mpt_alibi_tensor = U.build_mpt_alibi_tensor
+        inner = getattr(self.module, "model", None)
+        if inner is not None and hasattr(inner, "get_alibi_mask"):
+            inner.get_alibi_mask_orig = inner.get_alibi_mask
+            inner.__class__.get_alibi_mask = U.get_alibi_mask
+
+    def build_attn_bias(self):
+        from deepspeed_b200.module_inject import auto_tp_model_utils as U
+        tr = getattr(self.module, "transformer", None)
+        if tr is not None and hasattr(tr, "_attn_bias"):
+            tr._attn_bias_orig = tr._attn_bias
+            tr.__class__._attn_bias = U.build_mpt_atten_bias_tensor
+
+    def load_model_with_checkpoint(self, r_module):
+        """Fill a (possibly meta-initialised) module tree from ``self.sd`` -- the state dict of the checkpoint shard being
+        loaded -- slicing tensors for this TP rank; embeddings tied to ``lm_head`` are re-tied afterwards."""
+        from deepspeed_b200.module_inject.auto_tp import Loading
+        sd = getattr(self, "sd", None)
+        assert sd is not None, "set engine.sd (the checkpoint state dict) before load_model_with_checkpoint"
+
+        def walk(mod, prefix=""):
+            for name, child in mod.named_children():
+                full = prefix + name + "."
+                if Loading.is_load_module(child) and any(k.startswith(full) for k in sd):
+                    Loading.load(child, sd, full, mp_group=self.mp_group)
+                    Loading.load_buffer(child, sd, full)
+                else:
+                    walk(child, full)
+
+        walk(r_module)
+        emb, head = None, getattr(r_module, "lm_head", None)
+        for n, m in r_module.named_modules():
+            if isinstance(m, nn.Embedding) and ("embed_tokens" in n or "wte" in n or "word_embeddings" in n):
+                emb = m
+        if emb is not None and head is not None and getattr(head, "weight", None) is not None and head.weight.is_meta:
+            head.weight = emb.weight
+
+    @property
+    def is_compiled(self) -> bool:
+        return bool(getattr(self, "_is_compiled", False))
 
 
 @torch.no_grad()

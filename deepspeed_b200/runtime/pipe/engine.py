@@ -338,6 +338,42 @@ class PipelineEngine(DeepSpeedEngine):
         self._curr_ckpt_path = os.path.join(load_dir, str(tag))
         return super().load_checkpoint(load_dir, tag, **kw)
 
+    # ---- small public knobs of the reference engine ---------------------------------------------------------------------
+    has_attention_mask = False
+    agg_additional_losses = None
+
+    def set_has_attention_mask(self, value):
+        """Declare that the last tensor of a stage's tuple output is an attention mask (never differentiated)."""
+        assert isinstance(value, bool)
+        self.has_attention_mask = value
+
+    def reset_activation_shape(self):
+        """Forget the negotiated activation / gradient shapes: the next send re-transmits the shape header (call when a
+        curriculum changes the sequence length)."""
+        p2p._meta_cache.clear()
+        self.grad_layer = None
+
+    def log_for_device(self, *msg):
+        print(f"RANK={dist.get_rank()} PIPE-ID={self.stage_id} DATA-ID={self.grid.data_parallel_id} ::", *msg, flush=True)
+
+    def tput_log(self, *msg):
+        if self.global_rank == 0 and self.global_steps % self.steps_per_print() == 0:
+            print(*msg)
+
+    def mem_status(self, msg, print_rank=-1, reset_max=False):
+        if print_rank not in (-1, self.global_rank) or not torch.cuda.is_available():
+            return
+        a, r = torch.cuda.memory_allocated() / 2**30, torch.cuda.memory_reserved() / 2**30
+        m = torch.cuda.max_memory_allocated() / 2**30
+        if reset_max:
+            torch.cuda.reset_peak_memory_stats()
+        print(f"RANK={self.global_rank} STAGE={self.stage_id} MEMSTATS {msg} allocated={a:.2f}GB reserved={r:.2f}GB peak={m:.2f}GB")
+
+    def get_additional_losses(self):
+        """Extra named losses the model reported on the last stage (``PipelineModule.get_additional_losses``)."""
+        return self.agg_additional_losses
+
+
 
 def is_even(number):
     return number % 2 == 0

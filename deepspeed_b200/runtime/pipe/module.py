@@ -336,3 +336,16 @@ class PipelineModule(nn.Module):
             sd = checkpoint_engine.load(files[0], map_location="cpu")
             layer.load_state_dict(sd, strict=strict)
         self._synchronize_tied_weights()
+
+    def set_checkpoint_interval(self, interval):
+        """Layers per activation-checkpoint segment (0 disables)."""
+        assert interval >= 0
+        self.activation_checkpoint_interval = interval
+
+    @property
+    def checkpoint_interval(self):
+        return self.activation_checkpoint_interval
+
+    def get_additional_losses(self):
+        """Override to report ``{"name": value}`` extra losses from the last stage; ``None`` by default."""
+        return None

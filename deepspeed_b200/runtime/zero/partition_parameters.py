@@ -373,6 +373,20 @@ class Init(contextlib.AbstractContextManager):
         self._seen_params.clear()
         return False
 
+    # ---- group facts (reference ``Init.get_partition_dp_group`` etc.) -----------------------------------------------
+    def get_partition_dp_group(self, param=None):
+        return getattr(param, "ds_group", None) if param is not None and hasattr(param, "ds_group") else self.group
+
+    def get_partition_rank(self):
+        return _rank(self.group)
+
+    @property
+    def num_partitions(self):
+        return _world(self.group)
+
+    def get_dp_process_group(self):
+        return self.group
+
     # ---- hooks -----------------------------------------------------------------------------------
     def _on_param_registered(self, module, name, param):
         if param is not None:
