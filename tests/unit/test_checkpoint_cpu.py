@@ -339,3 +339,34 @@ def test_ds_to_universal_staged_pipeline(tmp_path):
     enable_universal_checkpoint([p])
     assert torch.equal(p.load_hp_checkpoint_state(os.path.join(dst, "col.w")), fulls["col.w"])
     assert SubparamShape(patterns=["x"], shape=(1, ), partition_dim=0).partition_dim == 0
+
+
+def test_deepspeed_checkpoint_layer_file_maps(tmp_path):
+    import torch
+    from deepspeed_b200.checkpoint import DeepSpeedCheckpoint
+    d = tmp_path / "global_step3"
+    d.mkdir()
+    for layer in (1, 3, 4, 5, 6, 8):  # embedding, 4 transformer layers, final norm
+        for tp in range(2):
+            torch.save({"w": torch.full((2, 3), float(10 * layer + tp))}, d / f"layer_{layer:02d}-model_{tp:02d}-model_states.pt")
+    for pp in range(2):
+        for tp in range(2):
+            torch.save({"global_steps": 3, "args": {"a": 1}, "module": {"x": torch.full((1, ), float(pp * 2 + tp))}},
+                       d / f"mp_rank_{pp * 2 + tp:02d}_model_states.pt")
+    ck = DeepSpeedCheckpoint(str(d), tp_degree=2, pp_degree=2)
+    assert ck.original_tp_degree in (2, 4)  # without zero files the tp/pp split of mp_rank files is ambiguous
+    ck.original_tp_degree, ck.original_pp_degree, ck._maps = 2, 2, None
+    assert ck.get_embedding_layer_id() == "layer_01" and ck.get_final_norm_layer_id() == "layer_08"
+    assert ck.get_pp_transformer_map(0) == ["layer_03", "layer_04"] and ck.get_pp_transformer_map(1) == ["layer_05", "layer_06"]
+    assert [f.split("/")[-1] for f in ck.get_embedding_files(1)] == ["layer_01-model_01-model_states.pt"]
+    st = ck.get_transformer_state(tp_index=1, pp_index=1)
+    assert len(st) == 2 and float(st[0]["w"][0, 0]) == 51.0 and float(st[1]["w"][0, 0]) == 61.0
+    assert float(ck.get_final_norm_state(0)["w"][0, 0]) == 80.0 and float(ck.get_embedding_state(0)["w"][0, 0]) == 10.0
+    assert len(ck.get_2d_parallel_files(tp_index=1, pp_index=0)) == 1 and ck.get_iteration() == 3 and ck.validate_files()
+    # contraction tp 2 -> 1: the two TP slices of a layer are merged
+    ck1 = DeepSpeedCheckpoint(str(d), tp_degree=1, pp_degree=2)
+    ck1.original_tp_degree, ck1.original_pp_degree, ck1._maps = 2, 2, None
+    merged = ck1.get_transformer_state(tp_index=0, pp_index=0)[0]["w"]
+    assert merged.shape == (4, 3) and merged[:, 0].tolist() == [30.0, 30.0, 31.0, 31.0]
+    assert len(ck1.get_2d_parallel_files(tp_index=0, pp_index=1)) == 2
+    ck1.show_pp_transformer_map()
