@@ -131,6 +131,100 @@ class AutoTP:
     def replace(self):
         return self._replace()
 
+    # ---- structure discovery helpers (reference ``auto_tp.py:215-282``) ------------------------------------------------
+    @staticmethod
+    def in_module_list(module, module_list):
+        return any(type(item).__name__ == type(module).__name__ for item in module_list)
+
+    @staticmethod
+    def get_module_list(model):
+        """One representative of every distinct block class found inside the model's ``ModuleList``s."""
+        found = []
+        for child in model.children():
+            if isinstance(child, nn.ModuleList):
+                for blk in child.children():
+                    if not AutoTP.in_module_list(blk, found):
+                        found.append(blk)
+            else:
+                found += [m for m in AutoTP.get_module_list(child) if not AutoTP.in_module_list(m, found)]
+        return found
+
+    @staticmethod
+    def get_layers(parent, module):
+        """Execution-ordered ``"parent.linear"`` names of a block, with ``"ln"`` markers where a layer norm sits."""
+        out = []
+        for key, sub in module._modules.items():
+            if _is_linear(sub):
+                out.append(f"{parent}.{key}")
+            elif isinstance(sub, nn.LayerNorm) or key in ("LayerNorm", "layer_norm") or "RMSNorm" in type(sub).__name__:
+                out.append("ln")
+            elif sub is not None:
+                out += AutoTP.get_layers(key, sub)
+        return out
+
+    @staticmethod
+    def update_policy_list(policy_list, new_module, new_gems):
+        """Merge ``(type(new_module), gems)`` into the policy list (gems of an already-listed class are unioned)."""
+        for i, (cls, gems) in enumerate(policy_list):
+            if cls is type(new_module):
+                policy_list[i] = (cls, set(new_gems) | set(gems))
+                return policy_list
+        policy_list.append((type(new_module), new_gems))
+        return policy_list
+
+    @staticmethod
+    def kernel_supported(module_list):
+        """Does a kernel-injection policy exist for any of these block instances?"""
+        from .replace_policy import replace_policies
+        classes = set()
+        for plcy in replace_policies:
+            orig = getattr(plcy, "_orig_layer_class", None)
+            for c in (orig if isinstance(orig, (list, tuple)) else [orig]):
+                if c is not None:
+                    classes.add(c)
+        return any(type(m) in classes for m in module_list)
+
+    def set_tensor_parallel_config(self, mp_size, mp_group):
+        from .layers import is_autotp_training_mode
+        if is_autotp_training_mode():
+            from deepspeed_b200.utils import groups
+            self.mp_group = groups.get_tensor_model_parallel_group()
+            self.mp_size = groups.get_tensor_model_parallel_world_size()
+            return
+        self.mp_size, self.mp_group = mp_size, mp_group
+
+    def update_mp_params(self, child):
+        """Divide the head / width attributes of one attention module by the TP degree (once)."""
+        if getattr(child, "replaced", False):
+            return
+        from .tp_shard import get_shard_size
+        for a in HEAD_ATTRS:
+            v = getattr(child, a, None)
+            if isinstance(v, int):
+                setattr(child, a, get_shard_size(v, self.mp_size))
+        child.replaced = True
+
+    def update_linear_policies(self):
+        """Which leaf classes are sharded: ``nn.Linear`` (and HF ``Conv1D`` for GPT-2 style blocks)."""
+        self.conv_linear_layer = False
+        classes = [nn.Linear]
+        try:
+            from transformers.pytorch_utils import Conv1D
+            classes.append(Conv1D)
+        except ImportError:
+            pass
+        self.linear_policies = {c: self._replace for c in classes}
+        return self.linear_policies
+
+    @staticmethod
+    def get_model_num_kv_heads(config):
+        for name in ("multi_query_group_num", "num_kv_heads", "num_key_value_heads", "num_attention_heads", "n_heads",
+                     "attention_heads"):
+            v = getattr(config, name, None)
+            if v is not None:
+                return v
+        return None
+
 
 def _is_linear(m):
     return isinstance(m, nn.Linear) or (hasattr(m, "weight") and getattr(m, "in_features", None) is not None and

@@ -119,6 +119,12 @@ class MMapIndexedDatasetBuilder:
         self._f.write(arr.tobytes(order="C"))
         self._sizes.append(arr.size)
 
+    def add_item_numpy(self, np_array):
+        """``add_item`` for an array that is already numpy (cast to the dataset dtype if needed)."""
+        arr = np_array if np_array.dtype == self._dtype else np_array.astype(self._dtype)
+        self._f.write(arr.tobytes(order="C"))
+        self._sizes.append(arr.size)
+
     def add_items(self, arr_list):
         for a in arr_list:
             self.add_item(a)
@@ -175,17 +181,35 @@ class MMapIndexedDataset(torch.utils.data.Dataset):
             off = f.tell()
         self._dtype = np.dtype(table[dcode])
         self._idx = np.memmap(index_file_path(path), mode="r", order="C")
-        self.sizes = np.frombuffer(self._idx, dtype=np.int32, count=n, offset=off)
+        self._sizes = np.frombuffer(self._idx, dtype=np.int32, count=n, offset=off)
         self._ptrs = np.frombuffer(self._idx, dtype=np.int64, count=n, offset=off + self.sizes.nbytes)
-        self.doc_idx = np.frombuffer(self._idx, dtype=np.int64, count=ndocs, offset=off + self.sizes.nbytes + self._ptrs.nbytes)
+        self._doc_idx = np.frombuffer(self._idx, dtype=np.int64, count=ndocs, offset=off + self.sizes.nbytes + self._ptrs.nbytes)
         self._bin = np.memmap(data_file_path(path), mode="r", order="C")
 
     @property
     def dtype(self):
         return self._dtype
 
+    @property
+    def sizes(self):
+        return self._sizes
+
+    def size(self, index):
+        return self._sizes[index]
+
+    @property
+    def doc_idx(self):
+        return self._doc_idx
+
+    def get_doc_idx(self):
+        return self._doc_idx
+
+    def set_doc_idx(self, doc_idx_):
+        """Replace the document boundaries (used when a corpus is re-segmented without rewriting the data file)."""
+        self._doc_idx = np.asarray(doc_idx_, dtype=np.int64)
+
     def __len__(self):
-        return len(self.sizes)
+        return len(self._sizes)
 
     def __getitem__(self, idx):
         if isinstance(idx, (int, np.integer)):
