@@ -20,6 +20,16 @@ class MultiNodeRunner(ABC):
         self.user_script = args.user_script
 
     @abstractmethod
+    def parse_user_args(self):
+        """User-script arguments as they must appear on the launcher's command line (runners that go through a remote shell
+        override this to quote arguments containing spaces)."""
+        return list(self.args.user_args)
+
+    def validate_args(self):
+        """Reject argument combinations this runner cannot honour (overridden per backend)."""
+        if getattr(self.args, "include", "") and getattr(self.args, "exclude", ""):
+            raise ValueError("--include and --exclude are mutually exclusive")
+
     def backend_exists(self):
         ...
 

@@ -36,16 +36,26 @@ class TensorBoardMonitor(Monitor):
     def __init__(self, config):
         super().__init__(config)
         self.summary_writer = None
+        self.output_path, self.job_name = config.output_path, config.job_name
         if self.enabled and _rank() == 0:
+            self.get_summary_writer()
+
+    def get_summary_writer(self, base=os.path.join(os.path.expanduser("~"), "tensorboard")):
+        """Create (once) the ``SummaryWriter`` under ``<output_path or base>/<job_name>``; rank 0 only."""
+        if self.summary_writer is None and self.enabled and _rank() == 0:
             try:
                 from torch.utils.tensorboard import SummaryWriter
-                base = config.output_path or os.path.join(os.path.expanduser("~"), "tensorboard")
-                log_dir = os.path.join(base, config.job_name)
+                log_dir = os.path.join(self.output_path or base, self.job_name)
                 os.makedirs(log_dir, exist_ok=True)
                 self.summary_writer = SummaryWriter(log_dir=log_dir)
             except Exception as e:
                 logger.warning(f"tensorboard monitor disabled: {e}")
                 self.enabled = False
+        return self.summary_writer
+
+    def flush(self):
+        if self.enabled and self.summary_writer is not None and _rank() == 0:
+            self.summary_writer.flush()
 
     def write_events(self, event_list, flush=True):
         if self.summary_writer is None:
@@ -121,6 +131,10 @@ class CometMonitor(Monitor):
             except Exception as e:
                 logger.warning(f"comet monitor disabled: {e}")
                 self.enabled = False
+
+    @property
+    def samples_log_interval(self):
+        return getattr(self, "_samples_log_interval", 1)
 
     def write_events(self, event_list):
         if self.experiment is None:

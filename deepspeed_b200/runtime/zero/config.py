@@ -118,13 +118,13 @@ class DeepSpeedZeroConfig(DeepSpeedConfigModel):
     b200_nvls: Optional[bool] = None  # None == auto (multimem when the multicast object binds)
 
     @model_validator(mode="after")
-    def _overlap_comm_default(self):
+    def overlap_comm_valid(self):
         if self.overlap_comm is None:
             self.__dict__["overlap_comm"] = self.stage == ZeroStageEnum.weights
         return self
 
     @model_validator(mode="after")
-    def _offload_ratio_check(self):
+    def offload_ratio_check(self):
         oo = self.offload_optimizer
         if oo and oo.ratio < 1.0:
             assert self.stage == ZeroStageEnum.weights, "Partial offloading only supported for ZeRO Stage 3."

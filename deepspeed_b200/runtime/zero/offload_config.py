@@ -44,7 +44,7 @@ class DeepSpeedZeroOffloadOptimizerConfig(DeepSpeedConfigModel):
     b200_swap_window: int = Field(pp_int(1 << 26), ge=1)  # NVMe tier: elements per pinned streaming window
 
     @model_validator(mode="after")
-    def _set_pipeline(self):
+    def set_pipeline(self):
         self.__dict__["pipeline"] = self.pipeline_read or self.pipeline_write
         return self
 

@@ -32,3 +32,26 @@ class OnDevice(contextlib.AbstractContextManager):
             self._stack.close()
             self._stack = None
         return False
+
+    # ---- constructor wrappers (reference ``init_on_device.py:42-62``) -------------------------------------------------
+    # The context itself does not need them (``torch.device`` + default dtype cover every factory function); they are
+    # offered for code that wraps individual constructors explicitly.
+    def fp_tensor_constructor(self, fn, target_fp_dtype):
+        """Wrap a factory (``torch.empty`` ...) so results land on ``self.device`` and float results use ``target_fp_dtype``."""
+
+        def wrapped_fn(*args, **kwargs):
+            if kwargs.get("device") is None:
+                kwargs["device"] = self.device
+            t = fn(*args, **kwargs)
+            return t.to(target_fp_dtype) if t.is_floating_point() else t
+
+        return wrapped_fn
+
+    def get_new_tensor_fn_for_dtype(self, dtype):
+        """Replacement for ``Tensor.__new__``-style construction: ``new_tensor(cls, *sizes)``."""
+
+        def new_tensor(cls, *args):
+            t = torch.empty(0, device=self.device).new_empty(*args)
+            return t.to(dtype) if t.is_floating_point() else t
+
+        return new_tensor

@@ -64,6 +64,45 @@ class LoggerFactory:
             raise ValueError("name for logger cannot be None")
         return _build_logger(name, level)
 
+    @staticmethod
+    def create_warning_filter(logger):
+        """Logging filter that warns ONCE if logging happens while a graph is being captured / traced (host-side logging
+        inside a captured region is a silent no-op on replay)."""
+        warned = False
+
+        def warn_once(record):
+            nonlocal warned
+            if not warned and _is_capturing():
+                warned = True
+                logger.warning("logging inside a captured / traced region: messages will not repeat on replay "
+                               "(set DISABLE_LOGS_WHILE_COMPILING=1 to silence)")
+            return True
+
+        return warn_once
+
+    @staticmethod
+    def logging_decorator(func):
+        """Skip the wrapped logging call entirely while capturing / tracing."""
+        import functools
+
+        @functools.wraps(func)
+        def wrapper(*args, **kwargs):
+            if _is_capturing():
+                return None
+            return func(*args, **kwargs)
+
+        return wrapper
+
+
+def _is_capturing():
+    try:
+        import torch
+        if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            return True
+        return bool(getattr(torch.compiler, "is_compiling", lambda: False)())
+    except Exception:
+        return False
+
 
 def should_log(ranks=None) -> bool:
     """True when this process' rank is in ``ranks`` (``None``/``[-1]`` = everyone)."""
