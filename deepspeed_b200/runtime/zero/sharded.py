@@ -940,6 +940,76 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
     cur_scale = loss_scale
 
+    # ---- small reference-named conveniences (``stage3.py:563-571, :2079``; ``stage_1_and_2.py``) -----------------------
+    def set_lr(self, lr):
+        for g in self.param_groups:
+            g["lr"] = lr
+
+    def get_lr(self):
+        return self.param_groups[0]["lr"]
+
+    def override_loss_scale(self, loss_scale):
+        """Use ``loss_scale`` (e.g. from an outer trainer) instead of the internal scaler from now on."""
+        if loss_scale != self.external_loss_scale:
+            logger.info(f"[deepspeed] setting loss scale from {self.external_loss_scale} -> {loss_scale}")
+        self.custom_loss_scaler = True
+        self.external_loss_scale = loss_scale
+
+    def has_overflow(self, partition_gradients=True):
+        """Did the last ``step`` skip because of inf/nan gradients?  (The check itself is fused into the step kernel.)"""
+        return bool(self.overflow)
+
+    def get_param_id(self, param):
+        return id(param)
+
+    def is_moe_group(self, group):
+        return bool(group.get("moe", False))
+
+    def reset_cpu_buffers(self):
+        """Host staging buffers are owned by the offload runtime and reused across steps; nothing to reset per step."""
+
+    def get_grad_norm_direct(self, gradients=None, params=None, norm_type=2):
+        """Global gradient norm of the current (already reduced) gradient arena over the DP group."""
+        import math
+        g = self.grad_arena
+        if g is None or self.fused_in_backward:
+            # the step was applied unit by unit during backward: gradients no longer exist as a whole
+            n = self.get_global_grad_norm()
+            return float(n) if n is not None else 0.0
+        if norm_type == math.inf:
+            t = g.abs().max().float().reshape(1)
+            if self.shard_world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.dp_group)
+            return float(t.item())
+        t = g.float().norm(norm_type).pow(norm_type).reshape(1)
+        if self.shard_world > 1 and self.stage >= 2:
+            dist.all_reduce(t, group=self.dp_group)
+        return float(t.item()**(1.0 / norm_type))
+
+    @staticmethod
+    def defragment(tensors):
+        """Move ``tensors`` into ONE contiguous flat buffer (each becomes a view of it) going through the host so the
+        device allocator can release the scattered originals before the flat buffer is allocated; returns the buffer."""
+        assert len({t.dtype for t in tensors}) == 1 and len({t.device for t in tensors}) == 1
+        dev = tensors[0].device
+        host = torch.empty(sum(t.numel() for t in tensors), dtype=tensors[0].dtype,
+                           pin_memory=dev.type == "cuda" and torch.cuda.is_available())
+        off = []
+        pos = 0
+        for t in tensors:
+            n = t.numel()
+            host[pos:pos + n].copy_(t.data.reshape(-1))
+            off.append(pos)
+            t.data = torch.empty(0, dtype=t.dtype, device=dev)  # drop the scattered storage
+            pos += n
+        if dev.type == "cuda":
+            torch.cuda.empty_cache()
+        flat = host.to(dev)
+        sizes = [off[i + 1] - off[i] for i in range(len(off) - 1)] + [host.numel() - off[-1]]
+        for t, o, n in zip(tensors, off, sizes):
+            t.data = flat[o:o + n]
+        return flat
+
     def backward(self, loss, retain_graph=False):
         self._in_backward = True
         if self.custom_loss_scaler:

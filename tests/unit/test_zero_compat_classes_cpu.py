@@ -139,3 +139,28 @@ def test_partition_parameter_helpers():
     qv, sc = q.quantize(x)
     assert (q.dequantize(qv, sc, dtype=torch.float32) - x).abs().max() <= x.abs().max() / 127 + 1e-6
     assert PP.InsertPostInitMethodToModuleSubClasses is PP.Init
+
+
+def _zero_conveniences():
+    import torch
+    import deepspeed_b200 as ds
+    model = torch.nn.Linear(8, 8)
+    eng, opt, *_ = ds.initialize(model=model, config={"train_batch_size": 2, "optimizer": {"type": "Adam", "params": {"lr": 1e-3}},
+                                                      "zero_optimization": {"stage": 2}})
+    assert opt.get_lr() == 1e-3
+    opt.set_lr(5e-4)
+    assert all(g["lr"] == 5e-4 for g in opt.param_groups) and not opt.dynamic_loss_scale and not opt.has_overflow()
+    loss = eng(torch.randn(1, 8)).square().mean()
+    eng.backward(loss)
+    assert opt.get_grad_norm_direct() >= 0
+    eng.step()
+    opt.override_loss_scale(4.0)
+    assert opt.loss_scale == 4.0 and opt.custom_loss_scaler
+    ts = [torch.arange(3.0), torch.arange(4.0) + 10]
+    flat = type(opt).defragment(ts)
+    assert flat.tolist() == [0, 1, 2, 10, 11, 12, 13] and ts[1].data_ptr() == flat[3:].data_ptr()
+
+
+def test_zero_optimizer_conveniences():
+    from tests.common import run_distributed
+    run_distributed(_zero_conveniences, 2)
