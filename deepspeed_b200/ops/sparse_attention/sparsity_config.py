@@ -101,6 +101,38 @@ class FixedSparsityConfig(SparsityConfig):
             layout[h] = m.long()
         return self.check_and_propagate_first_head_layout(layout)
 
+    def set_local_layout(self, h, layout):
+        """OR the block-diagonal local windows (``num_local_blocks`` wide; lower triangle only when causal) into head ``h``."""
+        n = layout.shape[1]
+        r, c = _grid(n)
+        m = (r // self.num_local_blocks == c // self.num_local_blocks)
+        if self.attention == "unidirectional":
+            m &= c <= r
+        layout[h] |= m.long()
+        return layout
+
+    def set_global_layout(self, h, layout):
+        """OR the global columns of head ``h`` (last ``num_global_blocks`` of every window, rotated per head when
+        ``num_different_global_patterns`` > 1) -- and the matching rows with ``horizontal_global_attention``."""
+        n = layout.shape[1]
+        L, G = self.num_local_blocks, self.num_global_blocks
+        r, c = _grid(n)
+        first = L - (1 + h % self.num_different_global_patterns) * G
+        end = n - n % L
+        cols = torch.zeros(n, dtype=torch.bool)
+        for s0 in range(first, end, L):
+            cols[s0:s0 + G] = True
+        if end < n:
+            s0 = min(end + first, n - G)
+            cols[s0:s0 + G] = True
+        gm = cols[None, :].expand(n, n).clone()
+        if self.attention == "unidirectional":
+            gm &= c <= r
+        layout[h] |= gm.long()
+        if self.horizontal_global_attention:
+            layout[h] |= cols[:, None].expand(n, n).long()
+        return layout
+
 
 class VariableSparsityConfig(SparsityConfig):
     """Random blocks + variable-size local windows + explicit global block indices."""
@@ -163,6 +195,50 @@ class VariableSparsityConfig(SparsityConfig):
             layout[h] = m.long()
         return self.check_and_propagate_first_head_layout(layout)
 
+    def set_random_layout(self, h, layout):
+        """OR ``num_random_blocks`` random block columns per block row into head ``h`` (causal rows draw from their past)."""
+        n = layout.shape[1]
+        if n < self.num_random_blocks:
+            raise ValueError(f"Number of random blocks, {self.num_random_blocks}, must be smaller than overall number of "
+                             f"blocks in a row, {n}!")
+        uni = getattr(self, "attention", "bidirectional") == "unidirectional"
+        for row in range(n):
+            hi = n if not uni else row + 1
+            for col in random.sample(range(hi), min(self.num_random_blocks, hi)):
+                layout[h, row, col] = 1
+        return layout
+
+    def set_local_layout(self, h, layout):
+        """OR the variable-width local windows (``local_window_blocks``; the last width repeats) into head ``h``."""
+        n = layout.shape[1]
+        r, c = _grid(n)
+        uni = self.attention == "unidirectional"
+        start, sizes = 0, list(self.local_window_blocks)
+        while start < n:
+            w = sizes.pop(0) if sizes else self.local_window_blocks[-1]
+            end = min(start + w, n)
+            blk = (r >= start) & (r < end) & (c >= start) & (c < end)
+            if uni:
+                blk &= c <= r
+            layout[h] |= blk.long()
+            start = end
+        return layout
+
+    def set_global_layout(self, h, layout):
+        """OR the global block columns ``[start, end)`` (rows too with ``horizontal_global_attention``) into head ``h``."""
+        n = layout.shape[1]
+        r, c = _grid(n)
+        uni = self.attention == "unidirectional"
+        ends = self.global_block_end_indices or [i + 1 for i in self.global_block_indices]
+        for s0, e in zip(self.global_block_indices, ends):
+            if s0 < n:
+                e = min(e, n)
+                col = (c >= s0) & (c < e)
+                layout[h] |= ((col & (r >= s0)) if uni else col.expand(n, n)).long()
+                if self.horizontal_global_attention:
+                    layout[h] |= ((r >= s0) & (r < e)).expand(n, n).long()
+        return layout
+
 
 class BigBirdSparsityConfig(SparsityConfig):
 
@@ -201,6 +277,43 @@ class BigBirdSparsityConfig(SparsityConfig):
             layout[h] = m.long()
         return self.check_and_propagate_first_head_layout(layout)
 
+    def set_random_layout(self, h, layout):
+        """OR ``num_random_blocks`` random block columns per block row into head ``h`` (causal rows draw from their past)."""
+        n = layout.shape[1]
+        if n < self.num_random_blocks:
+            raise ValueError(f"Number of random blocks, {self.num_random_blocks}, must be smaller than overall number of "
+                             f"blocks in a row, {n}!")
+        uni = getattr(self, "attention", "bidirectional") == "unidirectional"
+        for row in range(n):
+            hi = n if not uni else row + 1
+            for col in random.sample(range(hi), min(self.num_random_blocks, hi)):
+                layout[h, row, col] = 1
+        return layout
+
+    def set_sliding_window_layout(self, h, layout):
+        """OR the band ``|row - col| <= num_sliding_window_blocks // 2`` into head ``h``."""
+        n = layout.shape[1]
+        if n < self.num_sliding_window_blocks:
+            raise ValueError(f"Number of sliding window blocks, {self.num_sliding_window_blocks}, must be smaller than "
+                             f"overall number of blocks in a row, {n}!")
+        r, c = _grid(n)
+        w = self.num_sliding_window_blocks // 2
+        layout[h] |= ((c >= r - w) & (c <= r + w)).long()
+        return layout
+
+    def set_global_layout_itc(self, h, layout):
+        """ITC global attention: the first ``num_global_blocks`` block rows and columns attend / are attended everywhere."""
+        n = layout.shape[1]
+        if n < self.num_global_blocks:
+            raise ValueError(f"Number of global blocks, {self.num_global_blocks}, must be smaller than overall number of "
+                             f"blocks in a row, {n}!")
+        r, c = _grid(n)
+        g = self.num_global_blocks
+        layout[h] |= ((c < g) | (r < g)).expand(n, n).long()
+        if self.attention == "unidirectional":
+            layout[h] &= (c <= r).long()
+        return layout
+
 
 class BSLongformerSparsityConfig(SparsityConfig):
 
@@ -238,6 +351,30 @@ class BSLongformerSparsityConfig(SparsityConfig):
                 m &= c <= r
             layout[h] = m.long()
         return self.check_and_propagate_first_head_layout(layout)
+
+    def set_sliding_window_layout(self, h, layout):
+        """OR the band ``|row - col| <= num_sliding_window_blocks // 2`` into head ``h``."""
+        n = layout.shape[1]
+        if n < self.num_sliding_window_blocks:
+            raise ValueError(f"Number of sliding window blocks, {self.num_sliding_window_blocks}, must be smaller than "
+                             f"overall number of blocks in a row, {n}!")
+        r, c = _grid(n)
+        w = self.num_sliding_window_blocks // 2
+        layout[h] |= ((c >= r - w) & (c <= r + w)).long()
+        return layout
+
+    def set_global_layout(self, h, layout):
+        """OR the global block rows and columns ``[start, end)`` into head ``h``."""
+        n = layout.shape[1]
+        r, c = _grid(n)
+        ends = self.global_block_end_indices or [i + 1 for i in self.global_block_indices]
+        for s0, e in zip(self.global_block_indices, ends):
+            if s0 < n:
+                e = min(e, n)
+                layout[h] |= (((c >= s0) & (c < e)) | ((r >= s0) & (r < e))).expand(n, n).long()
+        if self.attention == "unidirectional":
+            layout[h] &= (c <= r).long()
+        return layout
 
 
 class LocalSlidingWindowSparsityConfig(SparsityConfig):

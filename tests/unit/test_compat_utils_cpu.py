@@ -152,3 +152,24 @@ def test_snip_momentum_block_pruning():
         assert torch.all(w[~pr.masks[name]] == 0)
         blocks = (w != 0).reshape(w.shape[0] // 4, 4, w.shape[1]).float().mean(1)
         assert torch.all((blocks == 0) | (blocks == 1))  # whole 4x1 blocks live or die together
+
+
+def test_sparsity_layout_setters_compose_to_make_layout():
+    import torch
+    from deepspeed_b200.ops.sparse_attention.sparsity_config import (BigBirdSparsityConfig, BSLongformerSparsityConfig,
+                                                                     FixedSparsityConfig, VariableSparsityConfig)
+    cases = [(FixedSparsityConfig(num_heads=2, block=16, num_local_blocks=4, num_global_blocks=1, attention="unidirectional"),
+              ("set_local_layout", "set_global_layout")),
+             (BSLongformerSparsityConfig(num_heads=2, block=16, num_sliding_window_blocks=3, global_block_indices=[0, 5]),
+              ("set_sliding_window_layout", "set_global_layout")),
+             (VariableSparsityConfig(num_heads=2, block=16, local_window_blocks=[2, 4], global_block_indices=[0]),
+              ("set_local_layout", "set_global_layout")),
+             (BigBirdSparsityConfig(num_heads=2, block=16, num_random_blocks=0, num_sliding_window_blocks=3, num_global_blocks=1),
+              ("set_random_layout", "set_sliding_window_layout", "set_global_layout_itc"))]
+    for cfg, setters in cases:
+        want = cfg.make_layout(256)
+        lay = cfg.setup_layout(256)
+        for h in range(cfg.num_layout_heads):
+            for name in setters:
+                lay = getattr(cfg, name)(h, lay)
+        assert torch.equal(cfg.check_and_propagate_first_head_layout(lay), want), type(cfg).__name__
