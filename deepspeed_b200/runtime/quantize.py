@@ -69,25 +69,49 @@ class Quantizer:
                             f"quantization period = {p.q_period}, index = {index}")
         assert p.start_bits >= p.target_bits, "Quantization bit is lower than target precision bits!"
         x = p.data
+        if p.start_bits >= 16:
+            return x
+        if p.start_bits == 1:
+            q = self.quantize_binary(x)
+        elif p.start_bits == 2:
+            q = self.quantize_tenary(x)
+        else:
+            q = self.quantize_highbit(x, p.start_bits)
+        return self.mixed_fp16_quantize(x, q, index, start_bits=p.start_bits, target_bits=p.target_bits)
+
+    # ---- the three quantisers (reference ``quantize.py:78-127``) -----------------------------------------------------
+    def _groups_for(self, x):
         groups = self.q_groups
         while x.numel() % groups:
             groups -= 1
-        if p.start_bits >= 16:
-            q = x
-        elif p.start_bits == 1:
-            flat = x.reshape(groups, -1).float()
-            m = flat.abs().mean(dim=1, keepdim=True)
-            q = (flat.sign() * m).reshape(x.shape).to(x.dtype)
-        elif p.start_bits == 2:
-            flat = x.reshape(groups, -1).float()
-            thres = 0.7 * flat.abs().mean(dim=1, keepdim=True)
-            mask = (flat.abs() > thres).float()
-            alpha = (flat.abs() * mask).sum(1, keepdim=True) / mask.sum(1, keepdim=True).clamp(min=1)
-            q = (alpha * flat.sign() * mask).reshape(x.shape).to(x.dtype)
-        else:
-            q = Q.fake_quantize(x.contiguous().view(-1), groups, p.start_bits,
-                                Q.Symmetric if self.q_type == 0 else Q.Asymmetric, stochastic=self.q_rounding == 1,
-                                seed=self.qsteps).view(x.shape)
-        if self.q_mixed_fp16 and p.start_bits >= p.target_bits - 1 and self.quantize_real_ratio > 0:
-            q = self.quantize_real_ratio * x + (1 - self.quantize_real_ratio) * q
-        return q
+        return groups
+
+    def quantize_highbit(self, inputs, num_bits):
+        """Uniform fake quantisation to ``num_bits`` (≥3) per group on the native quantiser kernel."""
+        return Q.fake_quantize(inputs.contiguous().view(-1), self._groups_for(inputs), num_bits,
+                               Q.Symmetric if self.q_type == 0 else Q.Asymmetric, stochastic=self.q_rounding == 1,
+                               seed=self.qsteps).view(inputs.shape)
+
+    def quantize_tenary(self, inputs):
+        """Ternary {-α, 0, +α}: threshold 0.7·mean|w| per group, α the mean magnitude of the surviving weights."""
+        flat = inputs.reshape(self._groups_for(inputs), -1).float()
+        thres = 0.7 * flat.abs().mean(dim=1, keepdim=True)
+        mask = (flat.abs() > thres).float()
+        alpha = (flat.abs() * mask).sum(1, keepdim=True) / mask.sum(1, keepdim=True).clamp(min=1)
+        return (alpha * flat.sign() * mask).reshape(inputs.shape).to(inputs.dtype)
+
+    def quantize_binary(self, inputs):
+        """Binary sign(w)·mean|w| per group."""
+        flat = inputs.reshape(self._groups_for(inputs), -1).float()
+        return (flat.sign() * flat.abs().mean(dim=1, keepdim=True)).reshape(inputs.shape).to(inputs.dtype)
+
+    def mixed_fp16_quantize(self, input, input_q, index, start_bits=None, target_bits=None):
+        """Blend the real and the quantised weights while the schedule is within one bit of the target
+        (``quantize_real_ratio`` decays to 0 through ``update_fp16_ratio``)."""
+        if start_bits is None:
+            start_bits = self.q_start_bits[index] if hasattr(self, "q_start_bits") else None
+            target_bits = getattr(self, "q_target_bits", None)
+        near = start_bits is not None and target_bits is not None and start_bits >= target_bits - 1
+        if self.q_mixed_fp16 and near and self.quantize_real_ratio > 0:
+            return self.quantize_real_ratio * input + (1 - self.quantize_real_ratio) * input_q
+        return input_q
