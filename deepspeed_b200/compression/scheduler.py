@@ -17,6 +17,11 @@ class compression_scheduler:
         self.training_steps = 0
         self.weight_quantization_enabled = False
         self.verbose = {t: False for t in C.TECHNIQUES}
+        self.make_init()
+
+    def make_init(self):
+        """Resolve every technique's module groups against the model once."""
+        model, compression_config = self.model, self.compression_config
         self.different_compression_methods = {}
         for method, mc in compression_config.items():
             if method == C.LAYER_REDUCTION:
@@ -37,7 +42,10 @@ class compression_scheduler:
         e = self.different_compression_methods.get(method)
         if not e or not e[C.TECHNIQUE_ENABLED]:
             return
-        if self.training_steps >= e[C.SHARED_PARAMETERS][C.TECHNIQUE_SCHEDULE_OFFSET]:
+        shared = e[C.SHARED_PARAMETERS]
+        end = shared.get(C.TECHNIQUE_SCHEDULE_OFFSET_END) if method == C.SPARSE_PRUNING else None
+        if self.training_steps >= shared[C.TECHNIQUE_SCHEDULE_OFFSET] and (end is None or end <= shared[
+                C.TECHNIQUE_SCHEDULE_OFFSET] or self.training_steps <= end):
             for _, names, _ in e[C.DIFFERENT_GROUPS]:
                 for n in names:
                     setattr(recursive_getattr(self.model, n), _FLAG[method], True)
@@ -46,8 +54,31 @@ class compression_scheduler:
             if method == C.WEIGHT_QUANTIZATION:
                 self.weight_quantization_enabled = True
 
+    # one entry point per technique, as in the reference scheduler
+    def check_weight_quantization(self):
+        self._check(C.WEIGHT_QUANTIZATION)
+
+    def check_activation_quantization(self):
+        self._check(C.ACTIVATION_QUANTIZATION)
+
+    def check_sparse_pruning(self):
+        self._check(C.SPARSE_PRUNING)
+
+    def check_head_pruning(self):
+        self._check(C.HEAD_PRUNING)
+
+    def check_row_pruning(self):
+        self._check(C.ROW_PRUNING)
+
+    def check_channel_pruning(self):
+        self._check(C.CHANNEL_PRUNING)
+
+    def check_all_modules(self):
+        for check in (self.check_weight_quantization, self.check_activation_quantization, self.check_sparse_pruning,
+                      self.check_head_pruning, self.check_row_pruning, self.check_channel_pruning):
+            check()
+
     def step(self, step_zero_check=False):
         if not step_zero_check:
             self.training_steps += 1
-        for m in C.TECHNIQUES:
-            self._check(m)
+        self.check_all_modules()
