@@ -87,6 +87,62 @@ class DeepSpeedDataSampler:
             out = np.intersect1d(out, s, assume_unique=True)
         return out
 
+    # ---- range queries and the cluster view (reference ``data_sampler.py:133-262``) ----------------------------------
+    # The reference materialises, per difficulty step, a *cluster* file of the samples that became admissible and draws
+    # every batch from the clusters proportionally to their size.  The default path above keeps one shuffled pool of the
+    # admissible set instead; these methods expose the same queries / cluster mechanics over in-memory index arrays.
+    def get_sample_based_on_metric_value(self, metric, value_start, value_end):
+        """Sample ids whose metric value lies in ``(value_start, value_end]`` (``None`` when empty)."""
+        rows = [g for v, g in zip(self.metric_values[metric], self.sample_index[metric]) if value_start < v <= value_end]
+        return np.concatenate(rows) if rows else None
+
+    def get_sample_based_on_metric_percentile(self, metric, percentile_start, percentile_end):
+        """Sample ids ranked (by metric, easiest first) between the two percentiles of the metric's ``max_difficulty`` scale."""
+        order = np.concatenate(self.sample_index[metric]) if self.sample_index[metric] else np.zeros(0, self.index_dtype)
+        cl = self.data_efficiency_config[C.DATA_SAMPLING][C.CURRICULUM_LEARNING][C.CURRICULUM_LEARNING_METRICS][metric]
+        top = cl.get(C.CURRICULUM_LEARNING_MAX_DIFFICULTY, 100)
+        per = len(order) // max(1, top)
+        lo, hi = per * percentile_start, (len(order) if percentile_end >= top else per * percentile_end)
+        return order[lo:hi] if hi > lo else None
+
+    def get_new_cluster(self, previous_difficulties):
+        """Append the samples admitted by the move ``previous_difficulties → current_difficulties`` as a new cluster."""
+        if not hasattr(self, "data_clusters"):
+            self.data_clusters, self.data_cluster_sizes, self.data_cluster_current_position = [], [], []
+        now = self._admissible()
+        if previous_difficulties:
+            cur, self.current_difficulties = self.current_difficulties, dict(previous_difficulties)
+            before = self._admissible()
+            self.current_difficulties = cur
+            now = np.setdiff1d(now, before, assume_unique=True)
+        if now.size == 0:
+            return False
+        self.data_clusters.append(self.np_rng.permutation(now))
+        self.data_cluster_sizes.append(int(now.size))
+        self.data_cluster_current_position.append(0)
+        return True
+
+    def sample_from_clusters(self):
+        """How many samples of the next global batch come from each cluster (multinomial over cluster sizes)."""
+        w = np.asarray(self.data_cluster_sizes, dtype=np.float64)
+        picks = self.np_rng.choice(len(w), self.global_batch_size, replace=True, p=w / w.sum())
+        return np.bincount(picks, minlength=len(w))
+
+    def reshuffle_clusters(self, cidx):
+        self.data_clusters[cidx] = self.np_rng.permutation(self.data_clusters[cidx])
+
+    def get_sample_from_cluster(self, cidx, num_samples):
+        """Next ``num_samples`` ids of cluster ``cidx``; wraps around (after a reshuffle) when the cluster is exhausted."""
+        pos = self.data_cluster_current_position[cidx]
+        out = list(self.data_clusters[cidx][pos:pos + num_samples])
+        self.data_cluster_current_position[cidx] = pos + num_samples
+        while len(out) < num_samples:
+            self.reshuffle_clusters(cidx)
+            more = num_samples - len(out)
+            out += list(self.data_clusters[cidx][:more])
+            self.data_cluster_current_position[cidx] = more
+        return out
+
     def get_next_global_batch(self):
         if self.curriculum_learning_enabled:
             self.curriculum_step += 1

@@ -70,6 +70,21 @@ def test_indexed_dataset_analyzer_sampler(tmp_path):
     assert len(batch) == 2
     sd = sampler.state_dict()
     sampler.load_state_dict(sd)
+    # range queries + the cluster view over the same index
+    lens = np.asarray(Lens.lens)
+    got = sampler.get_sample_based_on_metric_value("seqlen", 5, 8)
+    assert sorted(got.tolist()) == sorted(np.nonzero((lens > 5) & (lens <= 8))[0].tolist())
+    assert sampler.get_sample_based_on_metric_value("seqlen", 1000, 2000) is None
+    everything = sampler.get_sample_based_on_metric_percentile("seqlen", 0, 12)  # the top of the scale closes the range
+    assert sorted(everything.tolist()) == list(range(len(lens))) and list(lens[everything]) == sorted(lens)
+    sampler.current_difficulties = {"seqlen": 6}
+    assert sampler.get_new_cluster({}) and not sampler.get_new_cluster({"seqlen": 6})
+    sampler.current_difficulties = {"seqlen": 12}
+    assert sampler.get_new_cluster({"seqlen": 6})
+    assert sum(sampler.data_cluster_sizes) == len(lens) and sampler.sample_from_clusters().sum() == sampler.global_batch_size
+    n0 = sampler.data_cluster_sizes[0]
+    drawn = sampler.get_sample_from_cluster(0, n0 + 1)  # wraps around after a reshuffle
+    assert len(drawn) == n0 + 1 and set(drawn) == set(sampler.data_clusters[0].tolist())
 
 
 def test_random_ltd_wrapper_and_scheduler():
