@@ -124,6 +124,31 @@ class RaggedBatchWrapper:
     def is_pure_decode(self) -> bool:
         return self._n_seqs == self._n_tokens and self._n_seqs > 0
 
+    # ---- reference-named views (``ragged_wrapper.py:230-280``) -------------------------------------------------------
+    def batch_metadata_buffer(self, on_device: bool = True) -> torch.Tensor:
+        """``[n_tokens, n_sequences]`` as int32 (what the reference's kernels read first)."""
+        t = torch.tensor([self._n_tokens, self._n_seqs], dtype=torch.int32)
+        return t.to(self.device) if on_device else t
+
+    def tokens_to_seq(self, on_device: bool = True) -> torch.Tensor:
+        """Sequence slot of every token in the batch."""
+        return self.seq_of() if on_device else self._h("seq_of")[:self._n_tokens]
+
+    def inflight_seq_descriptors(self, on_device: bool = True) -> torch.Tensor:
+        """``[n_sequences, 4]`` rows of (first token, tokens in this batch, tokens already seen, 0)."""
+        rows = [(t0, n, seen, 0) for (t0, n, seen) in self.seq_layout]
+        t = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4)
+        return t.to(self.device) if on_device else t
+
+    def kv_ptrs(self, on_device: bool = True) -> torch.Tensor:
+        """Per-sequence KV block ids (the block table plays the role of the reference's pointer array)."""
+        bt = self.block_table() if on_device else self._h("block_table").view(self._max_S, self._max_blocks)
+        return bt[:self._n_seqs]
+
+    def masks(self, on_device: bool = True):
+        """No explicit masks: causal masking is derived from token positions inside the attention kernels."""
+        return None
+
 
 def to_padded(original_size: int) -> int:
     """Round a token / sequence count up to the granularity CUDA-graph buckets and GEMM tiles like: 64 up to 512, 128

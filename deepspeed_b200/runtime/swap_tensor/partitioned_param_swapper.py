@@ -108,6 +108,69 @@ class AsyncPartitionedParameterSwapper:
     def status(self, pid):
         return self._status.get(pid, PartitionedParamStatus.NOT_AVAILABLE)
 
+    # ---- parameter-object flavoured API of the reference (``partitioned_param_swapper.py:147-418``) --------------------
+    # Ids are ``param.ds_id`` (or a unit id): the methods above take ids, these take the parameter objects.
+    @staticmethod
+    def _pid(param):
+        return getattr(param, "ds_id", param)
+
+    def get_path(self, param, must_exist=False):
+        path = self._path(self._pid(param))
+        assert not must_exist or os.path.exists(path), f"Path for param id {self._pid(param)} does not exist"
+        return path
+
+    def remove_partition_and_release_buffers(self, params):
+        """Give the pinned buffers of ``params`` back to the pool (their data stays on NVMe)."""
+        self.release([self._pid(p) for p in params])
+
+    def swap_into_buffer(self, param, dest_buffer):
+        """Synchronously read the shard of ``param`` into ``dest_buffer`` (through a pool buffer when the destination is
+        not pinned / not a whole number of I/O blocks)."""
+        pid = self._pid(param)
+        n = self._numel.get(pid, dest_buffer.numel())
+        pinned_ok = dest_buffer.is_pinned() and dest_buffer.is_contiguous()
+        if pinned_ok:
+            self.aio_read.sync_pread(dest_buffer[:n], self._path(pid))
+        else:
+            buf = self.swap_in([pid], async_op=False)[0]
+            dest_buffer.reshape(-1)[:n].copy_(buf[:n])
+            self._release(pid)
+        self._status[pid] = PartitionedParamStatus.AVAILABLE
+
+    def reserve_available_buffers(self):
+        """Take every currently free pool buffer (used as scratch by the optimizer swapper); returns the tensors."""
+        self._reserved = list(self._free)
+        self._free = []
+        return [self._pool[i] for i in self._reserved]
+
+    def release_reserved_buffers(self):
+        self._free.extend(getattr(self, "_reserved", []))
+        self._reserved = []
+
+    def reserve_partitioned_swap_space(self, partition_num_elems):
+        """One pinned staging area large enough for all listed shards (each rounded to the I/O alignment)."""
+        align = max(1, 4096 // self.dtype.itemsize)
+        self._stage_offsets, pos = [], 0
+        for n in partition_num_elems:
+            self._stage_offsets.append((pos, n))
+            pos += -(-n // align) * align
+        self.partitioned_swap_buffer = _pinned(pos, self.dtype)
+
+    def swap_out_partitioned_params(self, dst_fp16_params, src_fp32_params):
+        """Cast the updated fp32 shards into the staging area and write each to its parameter's swap file."""
+        assert getattr(self, "partitioned_swap_buffer", None) is not None, "call reserve_partitioned_swap_space first"
+        assert len(dst_fp16_params) == len(src_fp32_params)
+        self.synchronize_writes()
+        for (pos, n), p, src in zip(self._stage_offsets, dst_fp16_params, src_fp32_params):
+            pid = self._pid(p)
+            stage = self.partitioned_swap_buffer[pos:pos + src.numel()]
+            stage.copy_(src.reshape(-1))
+            self._numel[pid] = src.numel()
+            self.aio_write.async_pwrite(stage, self._path(pid))
+            self.pending_writes += 1
+            self._status[pid] = PartitionedParamStatus.NOT_AVAILABLE
+        self.synchronize_writes()
+
 
 def print_rank_0(message, debug=False, force=False):
     from deepspeed_b200 import comm as dist

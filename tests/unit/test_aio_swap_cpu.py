@@ -190,3 +190,30 @@ def test_nvme_benchmark_schedules(tmp_path):
     jobs = S.create_perf_jobs("read", str(tmp_path), [["--block_size", "1M", "--queue_depth", "8"]])
     assert len(jobs) == 1 and "--read" in jobs[0].cmd() and jobs[0].output_file.endswith(".txt")
     assert S.async_io_setup() in (True, False) and S.script_path().endswith("nvme")
+
+
+def test_param_swapper_param_object_api(tmp_path):
+    import types
+    import torch
+    from deepspeed_b200.runtime.swap_tensor.partitioned_param_swapper import AsyncPartitionedParameterSwapper, PartitionedParamStatus
+    oc = types.SimpleNamespace(nvme_path=str(tmp_path), buffer_size=4096, buffer_count=3)
+    sw = AsyncPartitionedParameterSwapper(oc, torch.float32, aio_config={"block_size": 1 << 20, "queue_depth": 8,
+                                                                        "intra_op_parallelism": 1, "single_submit": False,
+                                                                        "overlap_events": True, "use_gds": False})
+    params = [types.SimpleNamespace(ds_id=i) for i in range(2)]
+    new = [torch.arange(1000.0), torch.arange(2000.0) * 2]
+    sw.reserve_partitioned_swap_space([t.numel() for t in new])
+    sw.swap_out_partitioned_params(params, new)
+    assert all(sw.status(p.ds_id) == PartitionedParamStatus.NOT_AVAILABLE for p in params)
+    assert sw.get_path(params[1], must_exist=True).endswith("1_param.tensor.swp")
+    dst = torch.zeros(2000)
+    sw.swap_into_buffer(params[1], dst)
+    assert torch.equal(dst, new[1]) and sw.status(1) == PartitionedParamStatus.AVAILABLE
+    bufs = sw.reserve_available_buffers()
+    assert len(bufs) == 3 and sw.available_swap_in_buffers() == 0
+    sw.release_reserved_buffers()
+    assert sw.available_swap_in_buffers() == 3
+    got = sw.swap_in([0], async_op=False)[0]
+    assert torch.equal(got, new[0])
+    sw.remove_partition_and_release_buffers([params[0]])
+    assert sw.available_swap_in_buffers() == 3
