@@ -35,73 +35,132 @@ class DataAnalyzer:
         os.makedirs(d, exist_ok=True)
         return d
 
-    def run_map(self):
+    # ---- map: every worker scans its slice and writes per-worker partial results --------------------------------------
+    def init_metric_results(self, thread_id=0, metric_names=None, metric_types=None, metric_dtypes=None, save_path=None,
+                            worker_id=None):
+        """Empty accumulator per metric: ``{"pairs": [(sample, value)...]}`` or ``{"total": None}``."""
+        names = metric_names or self.metric_names
+        kinds = metric_types or self.metric_types
+        return {n: ({"pairs": []} if k == "single_value_per_sample" else {"total": None}) for n, k in zip(names, kinds)}
+
+    def update_metric_results(self, data, metric_types, metric_dtypes, metric_functions, metric_results, batch_start_idx=0,
+                              sample_ids=None):
+        """Evaluate every metric function on one collated batch and fold the values into ``metric_results``."""
+        for name, fn, kind in zip(self.metric_names, metric_functions, metric_types):
+            v = fn(data)
+            if kind == "single_value_per_sample":
+                vals = np.asarray(v).reshape(-1).tolist()
+                ids = sample_ids if sample_ids is not None else range(batch_start_idx, batch_start_idx + len(vals))
+                metric_results[name]["pairs"].extend(zip(ids, vals))
+            elif kind == "accumulate_value_over_samples":
+                cur = metric_results[name]["total"]
+                metric_results[name]["total"] = v if cur is None else cur + v
+            else:
+                raise ValueError(f"unknown metric type {kind}")
+        return metric_results
+
+    def finalize_metric_results(self, metric_types, metric_dtypes, metric_results):
+        """Persist this worker's partial results under ``<save_path>/<metric>/worker<id>/``."""
+        for name, kind in zip(self.metric_names, metric_types):
+            d = self._wdir(name)
+            if kind == "accumulate_value_over_samples":
+                np.save(os.path.join(d, "accumulate.npy"), np.asarray(metric_results[name]["total"]))
+            else:
+                np.save(os.path.join(d, "sample_to_metric.npy"),
+                        np.asarray(metric_results[name]["pairs"], dtype=np.int64).reshape(-1, 2))
+
+    def run_map_helper(self, thread_id=0):
         lo, hi = self._my_range()
-        results = {n: [] for n in self.metric_names}
-        accum = {}
-        for s in range(lo, hi, self.batch_size):
-            idx = list(range(s, min(s + self.batch_size, hi)))
+        results = self.init_metric_results(thread_id)
+        for s0 in range(lo, hi, self.batch_size):
+            idx = list(range(s0, min(s0 + self.batch_size, hi)))
             if self.sample_indices is not None:
                 idx = [self.sample_indices[i] for i in idx]
             batch = [self.dataset[i] for i in idx]
             batch = self.collate_fn(batch) if self.collate_fn else torch.utils.data.default_collate(batch)
-            for name, fn, kind in zip(self.metric_names, self.metric_functions, self.metric_types):
-                v = fn(batch)
-                if kind == "single_value_per_sample":
-                    results[name].extend(zip(idx, np.asarray(v).reshape(-1).tolist()))
-                elif kind == "accumulate_value_over_samples":
-                    accum[name] = v if name not in accum else accum[name] + v
-                else:
-                    raise ValueError(f"unknown metric type {kind}")
-        for name, dt in zip(self.metric_names, self.metric_dtypes):
-            d = self._wdir(name)
-            if name in accum:
-                np.save(os.path.join(d, "accumulate.npy"), np.asarray(accum[name]))
-            else:
-                arr = np.asarray(results[name], dtype=np.int64).reshape(-1, 2)
-                np.save(os.path.join(d, "sample_to_metric.npy"), arr)
+            self.update_metric_results(batch, self.metric_types, self.metric_dtypes, self.metric_functions, results,
+                                       sample_ids=idx)
+        self.finalize_metric_results(self.metric_types, self.metric_dtypes, results)
 
-    def run_reduce(self):
-        for name, kind, dt in zip(self.metric_names, self.metric_types, self.metric_dtypes):
-            base = os.path.join(self.save_path, name)
+    def run_map(self):
+        self.run_map_helper(0)
+
+    # ---- reduce: worker 0 merges the partial results into the index files the sampler reads --------------------------
+    def _builder(self, base, name, suffix, dtype):
+        return MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_{suffix}.bin"), dtype=dtype), \
+            os.path.join(base, f"{name}_{suffix}.idx")
+
+    def merge_gather_map_stats(self, num_workers, num_threads, num_threads_reduce, t_idx_reduce, metric_save_path, metric_name,
+                               return_dict):
+        """Concatenate the workers' ``(sample, value)`` tables of one metric (sorted by sample id) into ``return_dict``."""
+        pairs = np.concatenate([np.load(os.path.join(metric_save_path, f"worker{w}", "sample_to_metric.npy"))
+                                for w in range(num_workers)])
+        return_dict[t_idx_reduce] = pairs[np.argsort(pairs[:, 0], kind="stable")]
+        return return_dict[t_idx_reduce]
+
+    def merge_sample_to_metric(self, pairs, base, name, dtype):
+        """``<metric>_sample_to_metric``: row i holds the metric value of sample i."""
+        b, idx = self._builder(base, name, "sample_to_metric", dtype)
+        for v in pairs[:, 1]:
+            b.add_item(np.asarray([v]))
+        b.end_document()
+        b.finalize(idx)
+
+    def merge_metric_to_sample(self, pairs, base, name, dtype):
+        """``<metric>_index_to_sample`` / ``_index_to_metric``: one row per distinct value (ascending) with its samples."""
+        groups = defaultdict(list)
+        for i, v in pairs:
+            groups[int(v)].append(int(i))
+        values = sorted(groups)
+        (i2s, i2s_idx), (i2m, i2m_idx) = self._builder(base, name, "index_to_sample", np.int64), \
+            self._builder(base, name, "index_to_metric", dtype)
+        for v in values:
+            i2s.add_item(np.asarray(groups[v], dtype=np.int64))
+            i2m.add_item(np.asarray([v]))
+        i2s.end_document(), i2m.end_document()
+        i2s.finalize(i2s_idx), i2m.finalize(i2m_idx)
+        return groups, values
+
+    def get_metric_value_percentiles(self, metric_name, num_sample_per_value, total_num_samples):
+        """Log how many samples fall under each difficulty percentile; returns ``{percentile: metric value}``."""
+        out, seen, pct = {}, 0, 1
+        for v in sorted(num_sample_per_value):
+            seen += num_sample_per_value[v]
+            while pct <= 100 and seen >= total_num_samples * pct / 100.0:
+                out[pct] = v
+                pct += 1
+        return out
+
+    def output_index_to_sample_percentile(self, groups, values, base, name):
+        """``<metric>_index_to_sample_percentile_merged``: samples in difficulty order, cut into 100 equal rows."""
+        b, idx = self._builder(base, name, "index_to_sample_percentile_merged", np.int64)
+        order = np.concatenate([np.asarray(groups[v], dtype=np.int64) for v in values]) if values else np.zeros(0, np.int64)
+        for chunk in np.array_split(order, 100):
+            b.add_item(chunk)
+        b.end_document()
+        b.finalize(idx)
+
+    def merge_map_results(self, dataset, metric_names, metric_types, save_path, num_workers, num_threads, num_threads_reduce):
+        for name, kind, dt in zip(metric_names, metric_types, self.metric_dtypes):
+            base = os.path.join(save_path, name)
             if kind == "accumulate_value_over_samples":
                 total = None
-                for w in range(self.num_workers):
+                for w in range(num_workers):
                     a = np.load(os.path.join(base, f"worker{w}", "accumulate.npy"))
                     total = a if total is None else total + a
-                b = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_metric_value.bin"), dtype=dt)
+                b, idx = self._builder(base, name, "metric_value", dt)
                 b.add_item(np.asarray(total).reshape(-1))
                 b.end_document()
-                b.finalize(os.path.join(base, f"{name}_metric_value.idx"))
+                b.finalize(idx)
                 continue
-            pairs = np.concatenate([np.load(os.path.join(base, f"worker{w}", "sample_to_metric.npy"))
-                                    for w in range(self.num_workers)])
-            pairs = pairs[np.argsort(pairs[:, 0], kind="stable")]
-            s2m = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_sample_to_metric.bin"), dtype=dt)
-            for v in pairs[:, 1]:
-                s2m.add_item(np.asarray([v]))
-            s2m.end_document()
-            s2m.finalize(os.path.join(base, f"{name}_sample_to_metric.idx"))
-            groups = defaultdict(list)
-            for i, v in pairs:
-                groups[int(v)].append(int(i))
-            values = sorted(groups)
-            i2s = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_sample.bin"), dtype=np.int64)
-            i2m = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_metric.bin"), dtype=dt)
-            for v in values:
-                i2s.add_item(np.asarray(groups[v], dtype=np.int64))
-                i2m.add_item(np.asarray([v]))
-            i2s.end_document(), i2m.end_document()
-            i2s.finalize(os.path.join(base, f"{name}_index_to_sample.idx"))
-            i2m.finalize(os.path.join(base, f"{name}_index_to_metric.idx"))
-            # percentile merged view used by percentile-based difficulty
-            merged = MMapIndexedDatasetBuilder(os.path.join(base, f"{name}_index_to_sample_percentile_merged.bin"),
-                                               dtype=np.int64)
-            order = np.concatenate([np.asarray(groups[v], dtype=np.int64) for v in values]) if values else np.zeros(0, np.int64)
-            for chunk in np.array_split(order, 100):
-                merged.add_item(chunk)
-            merged.end_document()
-            merged.finalize(os.path.join(base, f"{name}_index_to_sample_percentile_merged.idx"))
+            pairs = self.merge_gather_map_stats(num_workers, num_threads, num_threads_reduce, 0, base, name, {})
+            self.merge_sample_to_metric(pairs, base, name, dt)
+            groups, values = self.merge_metric_to_sample(pairs, base, name, dt)
+            self.output_index_to_sample_percentile(groups, values, base, name)
+
+    def run_reduce(self):
+        self.merge_map_results(self.dataset, self.metric_names, self.metric_types, self.save_path, self.num_workers,
+                               getattr(self, "num_threads", 1), getattr(self, "num_threads_reduce", 1))
 
     def run_map_reduce(self, comm_group=None):
         self.run_map()
