@@ -193,6 +193,144 @@ class Autotuner:
             self.optimal_ds_config = exp["ds_config"]
         return best
 
+    # ---- config accessors and micro-batch search helpers (reference ``autotuner.py:200-300, :640-1075``) -------------
+    def max_train_batch_size(self):
+        return self.autotuning_config.max_train_batch_size
+
+    def max_train_micro_batch_size_per_gpu(self):
+        c = self.autotuning_config
+        cap = c.max_train_micro_batch_size_per_gpu
+        if self.max_train_batch_size():
+            gpus = self.exp_num_gpus * self.exp_num_nodes // max(1, self.mp_size())
+            cap = min(cap, max(1, self.max_train_batch_size() // max(1, gpus)))
+        return cap
+
+    def min_train_micro_batch_size_per_gpu(self):
+        return self.autotuning_config.min_train_micro_batch_size_per_gpu
+
+    def num_tuning_micro_batch_sizes(self):
+        return self.autotuning_config.num_tuning_micro_batch_sizes
+
+    def fp16_enabled(self):
+        return bool((self.user_config.get("fp16") or {}).get("enabled", False))
+
+    def get_activation_memory_per_gpu(self):
+        return (self.model_info or {}).get("activation_mem_per_gpu")
+
+    def get_val_from_user_args(self, ds_name):
+        """Numeric value the user script was given for the argument mapped to config key ``ds_name``."""
+        arg = (self.autotuning_config.arg_mappings or {}).get(ds_name)
+        ua = list(self.args.user_args)
+        if arg in ua and ua.index(arg) + 1 < len(ua) and str(ua[ua.index(arg) + 1]).isnumeric():
+            return ua[ua.index(arg) + 1]
+        return None
+
+    def get_gas_from_user_config(self):
+        gas = self.user_config.get("gradient_accumulation_steps", 1)
+        if gas == "auto":
+            gas = int(self.get_val_from_user_args("gradient_accumulation_steps") or 1)
+        elif not isinstance(gas, int):
+            logger.info("Specifying a list of gradient_accumulation_steps to tune is not supported. 1 would be used.")
+            gas = 1
+        assert gas > 0, "Gradient accumulation steps must be positive."
+        return gas
+
+    def get_tuning_micro_batch_size_list(self, min_micro_batch_size, max_micro_batch_size, num_tuning_micro_batch_sizes):
+        """``(candidates, max_train_batch_size)``: up to ``num_tuning_micro_batch_sizes`` values spread evenly over
+        ``[min, max]`` (both ends included), capped so that ``mbs * gas * gpus`` stays under ``max_train_batch_size``."""
+        if min_micro_batch_size <= 0 or max_micro_batch_size <= 0:
+            return [], 0
+        gpus = self.exp_num_gpus * self.exp_num_nodes // max(1, self.mp_size())
+        gas = self.get_gas_from_user_config()
+        cap = self.max_train_batch_size()
+        if cap:
+            max_micro_batch_size = min(max_micro_batch_size, max(1, cap // (gas * gpus)))
+        if min_micro_batch_size > max_micro_batch_size:
+            return [], 0
+        n = max(1, num_tuning_micro_batch_sizes)
+        if n == 1 or min_micro_batch_size == max_micro_batch_size:
+            vals = [max_micro_batch_size]
+        else:
+            step = (max_micro_batch_size - min_micro_batch_size) / (n - 1)
+            vals = sorted({int(round(min_micro_batch_size + i * step)) for i in range(n)})
+        return vals, max_micro_batch_size * gas * gpus
+
+    def run_ds_config(self, ds_config, exp_name):
+        """Run ONE configuration now; returns its metric value (``None`` if the run produced none, e.g. OOM)."""
+        exp = {"name": exp_name, "ds_config": ds_config, "num_gpus": self.exp_num_gpus, "num_nodes": self.exp_num_nodes,
+               "hostfile": getattr(self.args, "hostfile", None)}
+        with open(os.path.join(self.exps_dir, f"{exp_name}.json"), "w") as f:
+            json.dump(exp, f)
+        self.rm.schedule_experiments_dicts([exp])
+        self.rm.run()
+        val = self.rm.metric_of(exp, self.metric())
+        self.rm.clear()
+        return val
+
+    def get_plateau_mbs(self, tuning_space_name):
+        """Largest micro batch before the metric stopped improving by more than 5 % (0 if the space has no records)."""
+        recs = sorted((r for r in self.records.get(tuning_space_name, []) if r[1] is not None),
+                      key=lambda r: r[0]["ds_config"]["train_micro_batch_size_per_gpu"])
+        prev_val, prev_mbs = None, 0
+        for exp, val, _ in recs:
+            if prev_val and (val < prev_val or (val - prev_val) / prev_val < 0.05):
+                break
+            prev_val, prev_mbs = val, exp["ds_config"]["train_micro_batch_size_per_gpu"]
+        return prev_mbs
+
+    def get_min_max_micro_batch_size(self, stage, min_micro_batch_size, calculated_max_micro_batch_size):
+        """Probe by running: the smallest micro batch that runs at all, then binary search for the largest that still fits
+        under ``calculated_max_micro_batch_size``.  ``(-1, -1)`` when nothing runs."""
+        if min_micro_batch_size > calculated_max_micro_batch_size:
+            return -1, -1
+        space = f"{K.TUNING_MICRO_BATCH_SIZE_PREFIX}{stage}"
+        base = copy.deepcopy(self.user_config)
+        base.pop(K.AUTOTUNING, None)
+        base.pop("train_batch_size", None)
+        base.setdefault("zero_optimization", {})["stage"] = stage
+        base["gradient_accumulation_steps"] = self.get_gas_from_user_config()
+
+        def fits(mbs):
+            cfg = copy.deepcopy(base)
+            cfg["train_micro_batch_size_per_gpu"] = mbs
+            name = f"{space}_gas{cfg['gradient_accumulation_steps']}_tmbspg{mbs}"
+            val = self.run_ds_config(cfg, name)
+            self.update_records(space, {"name": name, "ds_config": cfg}, val, 1)
+            return val is not None
+
+        lo = max(1, min_micro_batch_size)
+        if not fits(lo):
+            return -1, -1
+        hi = calculated_max_micro_batch_size
+        if hi > lo and fits(hi):
+            return lo, hi
+        best, left, right = lo, lo + 1, hi - 1
+        while left <= right:
+            mid = (left + right) // 2
+            if fits(mid):
+                best, left = mid, mid + 1
+            else:
+                right = mid - 1
+        return lo, best
+
+    def run_tuning_micro_batch_sizes(self, tuning_micro_batch_sizes, max_train_batch_size_per_gpu, min_gas, max_gas, stage):
+        """Run the listed micro batches (gas fixed to the user's value) and return the fastest one."""
+        space = f"{K.TUNING_MICRO_BATCH_SIZE_PREFIX}{stage}"
+        base = copy.deepcopy(self.user_config)
+        base.pop(K.AUTOTUNING, None)
+        base.pop("train_batch_size", None)
+        base.setdefault("zero_optimization", {})["stage"] = stage
+        gas = min(max(self.get_gas_from_user_config(), min_gas or 1), max_gas or 10**9)
+        for mbs in tuning_micro_batch_sizes:
+            if max_train_batch_size_per_gpu and mbs * gas > max_train_batch_size_per_gpu:
+                continue
+            cfg = copy.deepcopy(base)
+            cfg["train_micro_batch_size_per_gpu"], cfg["gradient_accumulation_steps"] = mbs, gas
+            name = f"{space}_gas{gas}_tmbspg{mbs}"
+            self.update_records(space, {"name": name, "ds_config": cfg}, self.run_ds_config(cfg, name), 1)
+        rec = self.get_best_space_record(space)
+        return rec[0]["ds_config"]["train_micro_batch_size_per_gpu"] if rec else 0
+
     # ---- records / reporting
     def update_records(self, space_name, exp, metric_val, num_exps):
         self.records.setdefault(space_name, []).append((exp, metric_val, num_exps))

@@ -140,3 +140,36 @@ def test_autotuning_scheduler_reservations_and_concurrency(tmp_path):
     best, val = rm.parse_results("throughput")
     assert best["name"] == "e2" and val == 42.0
     assert rm.status() == "localhost (4 idle gpus)"
+
+
+def test_autotuner_micro_batch_search_helpers(tmp_path):
+    import json
+    import os
+    import types
+    from deepspeed_b200.autotuning.autotuner import Autotuner
+    cfg_path = tmp_path / "ds.json"
+    cfg_path.write_text(json.dumps({"train_micro_batch_size_per_gpu": "auto", "gradient_accumulation_steps": "auto",
+                                    "fp16": {"enabled": True},
+                                    "autotuning": {"enabled": True, "results_dir": str(tmp_path / "res"),
+                                                   "exps_dir": str(tmp_path / "exps"), "max_train_batch_size": 64,
+                                                   "arg_mappings": {"gradient_accumulation_steps": "--gas"}}}))
+    limit = 11  # the fake runner "runs out of memory" above this micro batch
+
+    def runner(exp, rd):
+        mbs = exp["ds_config"]["train_micro_batch_size_per_gpu"]
+        if mbs <= limit:
+            with open(os.path.join(rd, "metrics.json"), "w") as f:
+                json.dump({"throughput": 100.0 * mbs / (mbs + 4)}, f)
+
+    args = types.SimpleNamespace(user_script="train.py", user_args=["--deepspeed_config", str(cfg_path), "--gas", "2"],
+                                 hostfile=None)
+    at = Autotuner(args, {"localhost": [0, 1]}, runner=runner)
+    assert at.fp16_enabled() and at.get_gas_from_user_config() == 2 and at.get_val_from_user_args("gradient_accumulation_steps") == "2"
+    assert at.max_train_micro_batch_size_per_gpu() <= 32 and at.get_activation_memory_per_gpu() is None
+    assert at.get_min_max_micro_batch_size(1, 1, 16) == (1, 11)  # binary search finds the memory limit
+    vals, max_tbs = at.get_tuning_micro_batch_size_list(1, 11, 3)
+    assert vals == [1, 6, 11] and max_tbs == 11 * 2 * 2
+    assert at.get_tuning_micro_batch_size_list(0, 4, 3) == ([], 0)
+    best = at.run_tuning_micro_batch_sizes(vals, None, 1, 4, stage=1)
+    assert best == 11 and at.get_plateau_mbs("z1") >= 1
+    assert at.run_ds_config({"train_micro_batch_size_per_gpu": 50}, "too_big") is None
