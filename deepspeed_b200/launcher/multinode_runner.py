@@ -19,7 +19,6 @@ class MultiNodeRunner(ABC):
         self.user_arguments = list(args.user_args)
         self.user_script = args.user_script
 
-    @abstractmethod
     def parse_user_args(self):
         """User-script arguments as they must appear on the launcher's command line (runners that go through a remote shell
         override this to quote arguments containing spaces)."""
@@ -30,6 +29,7 @@ class MultiNodeRunner(ABC):
         if getattr(self.args, "include", "") and getattr(self.args, "exclude", ""):
             raise ValueError("--include and --exclude are mutually exclusive")
 
+    @abstractmethod
     def backend_exists(self):
         ...
 
