@@ -40,7 +40,10 @@ class CheckpointMixin:
             groups._get_data_parallel_rank()
         # who writes the (replicated) model states; every DP rank writes its own ZeRO shard
         self.save_non_zero_checkpoint = dp_rank == 0 or self.zero_optimization_partition_weights()
-        self.save_zero_checkpoint = self.optimizer is not None
+        # every DP rank writes its own ZeRO shard; an unsharded optimizer (stage 0) is replicated -> dp rank 0 only
+        sharded = getattr(self.optimizer, "shard_world", 1) > 1 or self.zero_optimization_partition_weights()
+        self.save_zero_checkpoint = self.optimizer is not None and (sharded or dp_rank == 0)
+        self._optimizer_replicated = self.optimizer is not None and not sharded
         self._dp_rank_for_ckpt = dp_rank
 
     # ---- names ---------------------------------------------------------------------------------------
@@ -57,8 +60,8 @@ class CheckpointMixin:
 
     def _get_zero_ckpt_name(self, checkpoints_path, tag):
         bf16 = self.bfloat16_enabled()
-        return os.path.join(checkpoints_path, str(tag),
-                            f"{self._get_zero_ckpt_prefix(self._dp_rank_for_ckpt, bf16)}_optim_states.pt")
+        dp_rank = 0 if getattr(self, "_optimizer_replicated", False) else self._dp_rank_for_ckpt
+        return os.path.join(checkpoints_path, str(tag), f"{self._get_zero_ckpt_prefix(dp_rank, bf16)}_optim_states.pt")
 
     def _get_expert_ckpt_name(self, checkpoints_path, layer_id, expert_id, tag, mp_placeholder=None):
         mp = f"{_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
@@ -260,8 +263,10 @@ class CheckpointMixin:
                                              load_lr_scheduler_states, load_module_only, custom_load_fn)
         if path is None:
             return None, None
-        if self.optimizer is not None and not load_module_only:
-            ok = self._load_zero_checkpoint(load_dir, tag, load_optimizer_states)
+        if self.optimizer is not None and (not load_module_only or self.zero_optimization_partition_weights()):
+            # ZeRO-3 keeps the weights themselves in the per-rank shards: a module-only load still reads the fp32
+            # partitions (optimizer moments are left alone)
+            ok = self._load_zero_checkpoint(load_dir, tag, load_optimizer_states and not load_module_only)
             if not ok:
                 return None, None
         return path, client
@@ -323,12 +328,12 @@ class CheckpointMixin:
     @torch.no_grad()
     def _resync_arena_from_module(self):
         """After ``module.load_state_dict`` (stage <= 2) refresh the fp32 master from the parameters."""
-        zo = self.optimizer
-        if zo.master is None:
-            return
-        for rt in zo.rts:
-            a = rt.u.arena_offset
-            zo.master[a:a + rt.u.shard_numel].copy_(zo._lp_shard(rt.u))
+        for zo in getattr(self.optimizer, "parts", None) or [self.optimizer]:  # every reduction domain (dense + experts)
+            if zo.master is None:
+                continue
+            for rt in zo.rts:
+                a = rt.u.arena_offset
+                zo.master[a:a + rt.u.shard_numel].copy_(zo._lp_shard(rt.u))
 
     def _load_zero_checkpoint(self, load_dir, tag, load_optimizer_states=True):
         path = self._get_zero_ckpt_name(load_dir, tag)

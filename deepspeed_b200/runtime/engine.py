@@ -429,7 +429,11 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         self._config.gradient_accumulation_steps = train_batch_size // mb
         self._config.train_batch_size = train_batch_size
         if self.optimizer is not None:
-            self.optimizer.gas = self._config.gradient_accumulation_steps
+            if hasattr(self.optimizer, "set_gradient_accumulation_steps"):
+                # re-evaluates the fused-in-backward policy (a gradient arena is needed once GAS > 1)
+                self.optimizer.set_gradient_accumulation_steps(self._config.gradient_accumulation_steps)
+            else:
+                self.optimizer.gas = self._config.gradient_accumulation_steps
 
     def set_train_micro_batch_size(self, micro_batch_size):
         self._config.train_batch_size = micro_batch_size * self.gradient_accumulation_steps() * self.dp_world_size
@@ -592,7 +596,10 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
     def set_gradient_accumulation_boundary(self, is_boundary):
         self._is_gradient_accumulation_boundary = is_boundary
         if self.optimizer is not None:
-            self.optimizer._forced_boundary = is_boundary
+            if hasattr(self.optimizer, "set_forced_boundary"):
+                self.optimizer.set_forced_boundary(is_boundary)
+            else:
+                self.optimizer._forced_boundary = is_boundary
 
     @contextlib.contextmanager
     def no_sync(self):

@@ -42,6 +42,11 @@ class PipelineEngine(DeepSpeedEngine):
         self.total_loss = None
         self.agg_loss = torch.tensor(0.0, device=self.device)
         self.loss_model = self.module.loss_fn
+        if self.optimizer is not None and hasattr(self.optimizer, "disable_fused_in_backward") \
+                and list(self.module.get_tied_weights_and_groups()):
+            # tied copies on different stages must see the SUM of their gradients before the update: the step cannot
+            # be fused into backward (reference pipe/engine.py:284 _exec_reduce_tied_grads precedes the step)
+            self.optimizer.disable_fused_in_backward("tied weights across pipeline stages")
         if self.training_data is not None:
             self._build_data_iter(self.training_data)
         log_dist(f"PipelineEngine: stages={self.num_stages} stage_id={self.stage_id} micro_batches={self.micro_batches} "

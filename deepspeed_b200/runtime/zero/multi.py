@@ -69,6 +69,18 @@ class ZeroOptimizerGroup:
     def zero_grad(self, set_to_none=True):
         self.parts[0].zero_grad(set_to_none)
 
+    def set_gradient_accumulation_steps(self, gas):
+        for p in self.parts:
+            p.set_gradient_accumulation_steps(gas)
+
+    def set_forced_boundary(self, is_boundary):
+        for p in self.parts:
+            p.set_forced_boundary(is_boundary)
+
+    def disable_fused_in_backward(self, reason):
+        for p in self.parts:
+            p.disable_fused_in_backward(reason)
+
     def step(self, closure=None):
         for p in self.parts:
             p.prepare_step()

@@ -221,10 +221,10 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self.prefetch_depth = max(0, int(self.zc.b200_unit_prefetch))
 
         # ---- fusion policy ------------------------------------------------------------------------
-        fib = self.zc.b200_fused_optimizer_in_backward
-        can_fuse = (self.flat_opt.fused and not getattr(self.flat_opt, "per_tensor", False) and self.clip == 0.0
-                    and self.gas == 1 and not self.dynamic_loss_scale and not self.offload_optimizer)
-        self.fused_in_backward = bool(can_fuse if fib is None else (fib and can_fuse))
+        self._fib_request = self.zc.b200_fused_optimizer_in_backward
+        self._forced_boundary = None
+        self._accum = 0  # micro steps accumulated since the last optimizer step
+        self.fused_in_backward = self._fusion_policy()
 
         self._allocate(broadcast_init)
         self._register_hooks()
@@ -245,6 +245,42 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     # =========================================================================================
     # construction
     # =========================================================================================
+    def _fusion_policy(self) -> bool:
+        """May the optimizer step run unit by unit inside backward (no gradient arena at all)?  Only when nothing
+        needs the *whole* gradient first: no clipping, no accumulation, no loss scaling of any kind (fp16 always
+        unscales + checks overflow, reference ``stage3.py:2086-2130``), no offload, a flat fused optimizer."""
+        scaled = (self.model_dtype == torch.float16 or self.dynamic_loss_scale
+                  or float(self.loss_scaler.cur_scale) != 1.0)
+        can_fuse = (self.flat_opt.fused and not getattr(self.flat_opt, "per_tensor", False) and self.clip == 0.0
+                    and self.gas == 1 and not scaled and not self.offload_optimizer
+                    and not getattr(self, "_no_fuse_reason", None))
+        fib = self._fib_request
+        return bool(can_fuse if fib is None else (fib and can_fuse))
+
+    def disable_fused_in_backward(self, reason: str):
+        """Fall back to the two-phase step (reduce + accumulate, then one fused step); allocates the gradient arena
+        if the fused path had elided it.  Used when something discovered after construction needs whole gradients
+        (gradient accumulation turned on, tied weights across pipeline stages, ...)."""
+        self._no_fuse_reason = reason
+        if not self.fused_in_backward:
+            return
+        self.fused_in_backward = False
+        self._ensure_grad_arena()
+        log_dist(f"ZeroShardedOptimizer[{self.name}]: fused-in-backward step disabled ({reason})", ranks=[0])
+
+    def _ensure_grad_arena(self):
+        if self.grad_arena is None:
+            st_dev = "cpu" if self.offload_optimizer else self.device
+            gdt = torch.float32 if (self.offload_optimizer or not self.flat_opt.fused) else self.grad_accum_dtype
+            self.grad_arena = self._empty(self.arena_numel, gdt, st_dev, pin=True)
+            self.grad_arena.zero_()
+
+    def set_gradient_accumulation_steps(self, gas: int):
+        """Change GAS after construction (``engine.set_train_batch_size``): re-evaluates the fusion policy."""
+        self.gas = max(1, int(gas))
+        if self.gas > 1:
+            self.disable_fused_in_backward(f"gradient_accumulation_steps={self.gas}")
+
     def _make_param_groups(self, client_optimizer, param_groups, defaults):
         keep = self.param_filter or (lambda p: True)
         if client_optimizer is not None:
@@ -356,9 +392,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         # accumulated gradient shard: only allocated when the fused-in-backward path is off
         self.grad_arena = None
         if not self.fused_in_backward:
-            gdt = torch.float32 if (self.offload_optimizer or not self.flat_opt.fused) else self.grad_accum_dtype
-            self.grad_arena = self._empty(self.arena_numel, gdt, st_dev, pin=True)
-            self.grad_arena.zero_()
+            self._ensure_grad_arena()
         self._lp_stage = self._empty(max(u.shard_numel for u in self.units), lp, "cpu", pin=True) \
             if self.offload_optimizer else None
 
@@ -785,7 +819,25 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     # gradient reduction
     # =========================================================================================
     def is_gradient_accumulation_boundary(self):
-        return (self.micro_step + 1) % self.gas == 0
+        """Will the micro step in flight be followed by an optimizer step?  The engine may force the answer
+        (``engine.set_gradient_accumulation_boundary``, reference ``engine.py:2160``)."""
+        if self._forced_boundary is not None:
+            return bool(self._forced_boundary)
+        return (self._accum + 1) % self.gas == 0
+
+    def set_forced_boundary(self, is_boundary):
+        """``None`` returns to counting micro steps against ``gradient_accumulation_steps``."""
+        self._forced_boundary = is_boundary
+        if is_boundary is not None and self.fused_in_backward:
+            # the fused path needs to know *before* backward whether this micro step ends in a step; a caller that
+            # drives boundaries by hand may also accumulate, which needs the gradient arena
+            self.disable_fused_in_backward("gradient accumulation boundary is driven by the caller")
+
+    def _first_micro(self, rt=None) -> bool:
+        """True when this reduction must OVERWRITE the accumulated gradient (first micro step after an optimizer
+        step and the unit has not been reduced yet in this micro step); a second reduction of the same unit inside
+        one backward (weight used inside and outside a re-entrant checkpoint region) accumulates."""
+        return self._accum == 0 and not (rt is not None and rt.reduced_this_micro)
 
     @instrument_w_nvtx
     def _reduce_unit(self, rt: _UnitRT):
@@ -858,9 +910,14 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         u = rt.u
         a, b = u.arena_offset, u.arena_offset + u.shard_numel
         if self.fused_in_backward and self.is_gradient_accumulation_boundary():
+            if rt.reduced_this_micro:
+                raise RuntimeError(
+                    f"ZeRO unit '{u.name}' produced gradients twice in one backward (a weight used both inside and "
+                    f"outside a re-entrant activation-checkpoint region) while the optimizer step is fused into "
+                    f"backward; set zero_optimization.b200_fused_optimizer_in_backward=false for this model")
             self._step_range(a, b, shard_g, grad_offset=a, grad_scale=scale)
             return
-        first = (self.micro_step % self.gas) == 0
+        first = self._first_micro(rt)
         dst = self.grad_arena[a:b]
         if dst.device != shard_g.device:  # optimizer offload: D2H through the pinned arena
             if first:
@@ -877,11 +934,12 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         u = rt.u
         a, b = u.arena_offset, u.arena_offset + u.shard_numel
         boundary = self.is_gradient_accumulation_boundary()
-        if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()) and self.master is not None:
+        if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()) and self.master is not None \
+                and not rt.reduced_this_micro:
             self._symm.reduce_scatter_adam(self, rt, full_g, scale)
             return None
         if self.grad_arena is not None and self.grad_arena.is_cuda and not self.fused_in_backward:
-            first = (self.micro_step % self.gas) == 0
+            first = self._first_micro(rt)
             self._symm.reduce_scatter_accumulate(full_g, self.grad_arena[a:b], u.shard_numel, scale,
                                                  accumulate=not first)
             return None
@@ -899,7 +957,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                         rt.grad_full[sl.offset:sl.offset + sl.numel].zero_()
                 rt.pending = 0
                 self._reduce_unit(rt)
-        if self.grad_arena is not None and (self.micro_step % self.gas) == 0:
+        if self.grad_arena is not None and self._accum == 0:
             # units that produced no gradient at all this micro step must not keep stale values
             for rt in self.rts:
                 if not rt.reduced_this_micro and rt.n_trainable:
@@ -928,6 +986,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 from deepspeed_b200.runtime.zero.utils import assert_ints_same_as_other_ranks
                 assert_ints_same_as_other_ranks(order, self.dp_group)
         self.micro_step += 1
+        self._accum += 1
 
     # =========================================================================================
     # backward / step API (reference-compatible)
@@ -982,7 +1041,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.dp_group)
             return float(t.item())
         t = g.float().norm(norm_type).pow(norm_type).reshape(1)
-        if self.shard_world > 1 and self.stage >= 2:
+        if self.shard_world > 1:  # the arena holds this rank's shard for every sharded stage (1, 2 and 3)
             dist.all_reduce(t, group=self.dp_group)
         return float(t.item()**(1.0 / norm_type))
 
@@ -1196,6 +1255,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             ev = torch.cuda.Event()
             ev.record()
             self._step_event = ev
+        self._accum = 0
         self.global_step += 1
 
     # =========================================================================================
