@@ -46,6 +46,12 @@ def parse():
     ap.add_argument("--layers", type=int, default=None, help="debug only: truncate depth (invalidates the result)")
     ap.add_argument("--checkpoint-layers", type=int, default=None)
     ap.add_argument("--fused-collectives", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--model-impl", default="native", choices=["native", "hf"],
+                    help="b200 arm only: 'native' = deepspeed_b200.models.llama (fused kernels); 'hf' = the SAME "
+                    "transformers.LlamaForCausalLM module the reference arm trains, under this framework's engine")
+    ap.add_argument("--clip", type=float, default=0.0, help="gradient_clipping (both arms)")
+    ap.add_argument("--gas", type=int, default=1, help="gradient_accumulation_steps (both arms); a timed step = one "
+                    "optimizer step = GAS micro-batches")
     ap.add_argument("--local_rank", type=int, default=0)
     return ap.parse_args()
 
@@ -135,6 +141,54 @@ def timed_loop(torch, dist_mod, world, steps, body):
     return float(ms.item()) / 1e3
 
 
+def common_config(args, world):
+    """The part of the JSON line that must be IDENTICAL in both arms (the driver diffs it)."""
+    return {
+        "model": args.model + ("" if args.layers is None else f"-TRUNCATED-{args.layers}L"),
+        "global_batch": args.micro_batch * world * args.gas,
+        "micro_batch_per_gpu": args.micro_batch,
+        "seq_len": args.seq,
+        "parallelism": f"zero{args.zero_stage}-dp{world}",
+        "zero_stage": args.zero_stage,
+        "optimizer": "AdamW(lr=1e-5, betas=(0.9,0.95), eps=1e-8, wd=0.1), fp32 master + moments",
+        "gradient_clipping": args.clip,
+        "gradient_accumulation_steps": args.gas,
+        "precision": "bf16 params/activations/grads-in-flight",
+        "l2": "working set (>= 100 GB of parameter/optimizer state streamed per step) >> 126 MB L2",
+    }
+
+
+def ds_config_for(args, zero):
+    return {
+        "train_micro_batch_size_per_gpu": args.micro_batch,
+        "gradient_accumulation_steps": args.gas,
+        "gradient_clipping": args.clip,
+        "bf16": {"enabled": True},
+        "optimizer": {"type": "AdamW", "params": {"lr": 1e-5, "betas": [0.9, 0.95], "eps": 1e-8, "weight_decay": 0.1}},
+        "zero_optimization": zero,
+        "steps_per_print": 10**9,
+    }
+
+
+def hf_llama(torch, mc, grad_ckpt=False):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    hf_cfg = LlamaConfig(vocab_size=mc.vocab_size, hidden_size=mc.hidden_size, intermediate_size=mc.intermediate_size,
+                         num_hidden_layers=mc.num_hidden_layers, num_attention_heads=mc.num_attention_heads,
+                         num_key_value_heads=mc.num_key_value_heads, max_position_embeddings=mc.max_position_embeddings,
+                         rms_norm_eps=mc.rms_norm_eps, rope_theta=mc.rope_theta, tie_word_embeddings=False,
+                         use_cache=False)
+    torch.manual_seed(1234)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device("cuda"):
+        m = LlamaForCausalLM(hf_cfg)
+    torch.set_default_dtype(prev)
+    if grad_ckpt:
+        m.gradient_checkpointing_enable()
+    m.train()
+    return m
+
+
 def pick_checkpoint_layers(torch, cfg, micro_batch, seq, world, stage, explicit):
     """Activation-recompute policy: keep everything when it fits in HBM, else checkpoint just enough
     layers.  Model states per rank (ZeRO-3): (2 + 4 + 4 + 4) B/param / world (+2 B/param gathered pool)."""
@@ -170,24 +224,27 @@ def run_b200(args):
     cfg = llama_config(args.model, **over)
     cfg.checkpoint_layers = pick_checkpoint_layers(torch, cfg, args.micro_batch, args.seq, world, args.zero_stage,
                                                    args.checkpoint_layers)
-    torch.manual_seed(1234)
-    prev = torch.get_default_dtype()
-    torch.set_default_dtype(torch.bfloat16)
-    with torch.device("cuda"):
-        model = LlamaForCausalLM(cfg)
-    torch.set_default_dtype(prev)
+    hf = args.model_impl == "hf"
     zero = {"stage": args.zero_stage, "overlap_comm": True}
     if args.fused_collectives != "auto":
         zero["b200_fused_collectives"] = args.fused_collectives == "on"
-    ds_config = {
-        "train_micro_batch_size_per_gpu": args.micro_batch,
-        "gradient_accumulation_steps": 1,
-        "bf16": {"enabled": True},
-        "optimizer": {"type": "AdamW", "params": {"lr": 1e-5, "betas": [0.9, 0.95], "eps": 1e-8, "weight_decay": 0.1}},
-        "zero_optimization": zero,
-        "steps_per_print": 10**9,
-    }
-    engine, _, _, _ = ds.initialize(model=model, config=ds_config)
+    ds_config = ds_config_for(args, zero)
+    hf_ckpt = bool(args.checkpoint_layers)
+
+    def build():
+        if hf:
+            # the engine's own contribution in isolation: same HF module as the reference arm, this framework's engine
+            model = hf_llama(torch, cfg, grad_ckpt=hf_ckpt)
+        else:
+            torch.manual_seed(1234)
+            prev = torch.get_default_dtype()
+            torch.set_default_dtype(torch.bfloat16)
+            with torch.device("cuda"):
+                model = LlamaForCausalLM(cfg)
+            torch.set_default_dtype(prev)
+        return ds.initialize(model=model, config=ds_config)[0]
+
+    engine = build()
     B, S = args.micro_batch, args.seq
     g = torch.Generator().manual_seed(rank)
     n_batches = 4
@@ -195,21 +252,41 @@ def run_b200(args):
     dev = [h.cuda() for h in host]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
+    gas = args.gas
+
+    def fwd(ids):
+        return engine(input_ids=ids, labels=ids).loss if hf else engine(ids, labels=ids)
+
     def step_dev(i):
-        ids = dev[i % n_batches]
-        loss = engine(ids, labels=ids)
-        engine.backward(loss)
-        engine.step()
+        for k in range(gas):
+            loss = fwd(dev[(i * gas + k) % n_batches])
+            engine.backward(loss)
+            engine.step()
 
     def step_e2e(i):
-        ids = host[i % n_batches].to("cuda", non_blocking=True)  # H2D from pinned memory, every step
-        loss = engine(ids, labels=ids)
-        engine.backward(loss)
-        engine.step()
+        for k in range(gas):
+            ids = host[(i * gas + k) % n_batches].to("cuda", non_blocking=True)  # H2D from pinned memory, every micro step
+            loss = fwd(ids)
+            engine.backward(loss)
+            engine.step()
         loss_host.copy_(loss.detach().float().reshape(1), non_blocking=False)  # D2H read of the result
 
-    for i in range(args.warmup):
-        step_e2e(i)
+    try:
+        for i in range(args.warmup):
+            step_e2e(i)
+    except torch.OutOfMemoryError:
+        if not hf or hf_ckpt:
+            raise
+        # same policy as the reference arm: the HF module keeps every activation; retry with HF gradient checkpointing
+        engine.destroy() if hasattr(engine, "destroy") else None
+        del engine
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        hf_ckpt = True
+        engine = build()
+        for i in range(args.warmup):
+            step_e2e(i)
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
@@ -235,7 +312,7 @@ def run_b200(args):
         exposed = {"all_gather_ms_per_step": float(t[0]), "reduce_scatter_adam_ms_per_step": float(t[1]),
                    "total_ms_per_step": float(t[0] + t[1]), "how": "CUDA-event brackets around compute-stream waits, "
                    "max over ranks, mean of 2 steps"}
-    tokens_per_step = B * S * world
+    tokens_per_step = B * S * world * gas
     if rank == 0:
         val = tokens_per_step * args.steps / t_dev
         e2e = tokens_per_step * args.steps / t_e2e
@@ -261,19 +338,16 @@ def run_b200(args):
             "dtype": "bf16",
             "data": "synthetic random token ids, random-init weights (no network for datasets/checkpoints)",
             "impl": "b200",
-            "config": {
-                "model": args.model + ("" if args.layers is None else f"-TRUNCATED-{args.layers}L"),
-                "global_batch": B * world,
-                "micro_batch_per_gpu": B,
-                "seq_len": S,
-                "parallelism": f"zero{args.zero_stage}-dp{world}",
-                "optimizer": "AdamW fp32 master+states (fused sm_100a kernel)",
-                "activation_checkpoint_layers": cfg.checkpoint_layers,
+            "config": common_config(args, world),
+            "details": {
+                "model_impl": "transformers.LlamaForCausalLM (sdpa)" if hf else "deepspeed_b200.models.llama (fused sm_100a kernels)",
+                "optimizer_impl": "fused sm_100a AdamW kernel",
+                "activation_checkpoint_layers": cfg.checkpoint_layers if not hf else None,
+                "hf_gradient_checkpointing": hf_ckpt if hf else None,
                 "fused_in_backward_optimizer": bool(engine.optimizer.fused_in_backward),
                 "collectives": "nvlink-peer-kernels" if engine.optimizer._symm is not None else "nccl",
                 "gemm_backend": __import__("deepspeed_b200.ops.gemm", fromlist=["x"]).get_backend(),
-                "gemm_autotune_choices": _gemm_choice_summary(),
-                "l2": "working set (>=100 GB of parameter/optimizer state streamed per step) >> 126 MB L2",
+                "gemm_choices": _gemm_choice_summary(),
             },
             "model_tflops_per_gpu": flops / 1e12,
             "mfu_vs_measured_sustained": (flops / 1e12) / peaks["bf16_tflops_sustained"] if peaks.get(
@@ -283,7 +357,7 @@ def run_b200(args):
                 "value": e2e,
                 "unit": "tokens/s",
                 "ms_per_step": t_e2e / args.steps * 1e3,
-                "h2d_bytes_per_step": B * S * 8,
+                "h2d_bytes_per_step": B * S * 8 * gas,
                 "d2h_bytes_per_step": 4,
             },
             "gpu_launches": launches,
@@ -294,13 +368,12 @@ def run_b200(args):
 
 
 def _gemm_choice_summary():
-    """How many distinct GEMM problems the per-shape autotuner gave to each implementation."""
+    """Which implementation served each distinct GEMM problem of the step (persisted table / first-use measurement)."""
     from deepspeed_b200.ops import gemm
-    out = {}
-    for k, v in gemm.tuning_table().items():
-        kind = k[0] if isinstance(k[0], str) else "nt"
-        out[f"{kind}:{v}"] = out.get(f"{kind}:{v}", 0) + 1
-    return out
+    used = gemm.tuning_table()
+    own = sorted(k for k, v in used.items() if v == "own")
+    lib = sorted(k for k, v in used.items() if v == "lib")
+    return {"own_tcgen05": len(own), "cublas": len(lib), "cublas_shapes": lib, "measured_online": gemm.tuning_measurements()}
 
 
 def run_reference(args):
@@ -330,31 +403,11 @@ def run_reference(args):
         over["num_hidden_layers"] = args.layers
     mc = llama_config(args.model, **over)
     deepspeed.init_distributed(dist_backend="nccl")
-    hf_cfg = LlamaConfig(vocab_size=mc.vocab_size, hidden_size=mc.hidden_size, intermediate_size=mc.intermediate_size,
-                         num_hidden_layers=mc.num_hidden_layers, num_attention_heads=mc.num_attention_heads,
-                         num_key_value_heads=mc.num_key_value_heads, max_position_embeddings=mc.max_position_embeddings,
-                         rms_norm_eps=mc.rms_norm_eps, rope_theta=mc.rope_theta, tie_word_embeddings=False,
-                         use_cache=False)
     B, S = args.micro_batch, args.seq
-    ds_config = {
-        "train_micro_batch_size_per_gpu": B,
-        "gradient_accumulation_steps": 1,
-        "bf16": {"enabled": True},
-        "optimizer": {"type": "AdamW", "params": {"lr": 1e-5, "betas": [0.9, 0.95], "eps": 1e-8, "weight_decay": 0.1}},
-        "zero_optimization": {"stage": args.zero_stage, "overlap_comm": True},
-        "steps_per_print": 10**9,
-    }
+    ds_config = ds_config_for(args, {"stage": args.zero_stage, "overlap_comm": True})
 
     def build(grad_ckpt):
-        torch.manual_seed(1234)
-        prev = torch.get_default_dtype()
-        torch.set_default_dtype(torch.bfloat16)
-        with torch.device("cuda"):
-            m = LlamaForCausalLM(hf_cfg)
-        torch.set_default_dtype(prev)
-        if grad_ckpt:
-            m.gradient_checkpointing_enable()
-        m.train()
+        m = hf_llama(torch, mc, grad_ckpt)
         eng, _, _, _ = deepspeed.initialize(model=m, model_parameters=m.parameters(), config=ds_config)
         return eng
 
@@ -369,17 +422,21 @@ def run_reference(args):
             engine = build(ckpt_used)
             dev = [h.cuda() for h in host]
 
+            gas = args.gas
+
             def step_dev(i):
-                ids = dev[i % n_batches]
-                loss = engine(input_ids=ids, labels=ids).loss
-                engine.backward(loss)
-                engine.step()
+                for k in range(gas):
+                    ids = dev[(i * gas + k) % n_batches]
+                    loss = engine(input_ids=ids, labels=ids).loss
+                    engine.backward(loss)
+                    engine.step()
 
             def step_e2e(i):
-                ids = host[i % n_batches].to("cuda", non_blocking=True)
-                loss = engine(input_ids=ids, labels=ids).loss
-                engine.backward(loss)
-                engine.step()
+                for k in range(gas):
+                    ids = host[(i * gas + k) % n_batches].to("cuda", non_blocking=True)
+                    loss = engine(input_ids=ids, labels=ids).loss
+                    engine.backward(loss)
+                    engine.step()
                 loss_host.copy_(loss.detach().float().reshape(1))
 
             for i in range(args.warmup):
@@ -408,7 +465,7 @@ def run_reference(args):
     t_e2e = timed_loop(torch, _D, world, args.steps, step_e2e)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        tokens_per_step = B * S * world
+        tokens_per_step = B * S * world * args.gas
         out = {
             "metric": "tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B ZeRO-3 bf16 training",
             "value": tokens_per_step * args.steps / t_dev,
@@ -423,20 +480,17 @@ def run_reference(args):
             "dtype": "bf16",
             "data": "synthetic random token ids, random-init weights",
             "impl": "reference",
-            "config": {
-                "model": args.model + ("" if args.layers is None else f"-TRUNCATED-{args.layers}L"),
-                "global_batch": B * world,
-                "micro_batch_per_gpu": B,
-                "seq_len": S,
-                "parallelism": f"zero{args.zero_stage}-dp{world}",
-                "optimizer": "reference FusedAdam (AdamW)",
-                "hf_gradient_checkpointing": ckpt_used,
+            "config": common_config(args, world),
+            "details": {
                 "model_impl": "transformers.LlamaForCausalLM (sdpa)",
+                "optimizer_impl": "reference FusedAdam (AdamW)",
+                "hf_gradient_checkpointing": ckpt_used,
                 "deepspeed_version": deepspeed.__version__,
             },
             "clocks": clocks,
             "e2e": {"value": tokens_per_step * args.steps / t_e2e, "unit": "tokens/s",
-                    "ms_per_step": t_e2e / args.steps * 1e3, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4},
+                    "ms_per_step": t_e2e / args.steps * 1e3, "h2d_bytes_per_step": B * S * 8 * args.gas,
+                    "d2h_bytes_per_step": 4},
             "gpu_launches": 0,
             "max_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
         }

@@ -21,7 +21,6 @@ def convert_to_universal(input_folder, output_folder, tag=None, keep_temp_folder
     ds_dir = Z._resolve_tag(input_folder, tag) if (tag is not None or os.path.isfile(os.path.join(input_folder, "latest"))) \
         else input_folder
     ms = Z._model_state(ds_dir)
-    layout = ms["ds_b200_layout"]
     by_mp = Z.get_optim_shards(ds_dir)
     if len(by_mp) > 1:
         raise NotImplementedError("TP-sharded checkpoints: convert each mp rank separately (tp merge uses "
@@ -29,6 +28,10 @@ def convert_to_universal(input_folder, output_folder, tag=None, keep_temp_folder
     shards = [Z._load(f)["optimizer_state_dict"] for f in by_mp[0]]
     zero_dir = os.path.join(output_folder, "zero")
     os.makedirs(zero_dir, exist_ok=True)
+    if "fp32_flat" not in shards[0]:
+        # the reference's on-disk layout (stock DeepSpeed, or this framework's default checkpoint.b200_shard_layout)
+        return _convert_reference_layout(ms, shards, output_folder, zero_dir)
+    layout = ms["ds_b200_layout"]
     state_names = list(shards[0].get("flat_state", {}).keys())
     step = shards[0].get("group_steps", [0])
     flats = {"fp32": list(Z._unit_flats(layout, shards))}
@@ -54,6 +57,96 @@ def convert_to_universal(input_folder, output_folder, tag=None, keep_temp_folder
     with open(os.path.join(parent, "latest_universal"), "w") as f:
         f.write(os.path.basename(os.path.normpath(output_folder)))
     print(f"universal checkpoint: {n} parameters x {1 + len(state_names)} tensors -> {output_folder}")
+    return output_folder
+
+
+def reference_param_states(shards, param_shapes):
+    """Per-parameter tensors out of reference-layout optimizer shards (all DP ranks of one mp rank).
+
+    -> ``(OrderedDict name -> {"fp32": t, "exp_avg": t, ...} (param-shaped), steps per group, inner param_groups)``.
+    Stage 3: each parameter contributes ``ceil(numel / world)`` elements to every rank's flat (sub-groups are consecutive
+    runs of parameters, so concatenating a rank's sub-group flats restores the walk).  Stage 1/2: the rank partitions of a
+    group concatenate to the group's flat, parameters sit back to back in it."""
+    from collections import OrderedDict
+    world = len(shards)
+    stage3 = "fp32_flat_groups" in shards[0]
+    inner0 = shards[0].get("optimizer_state_dict" if stage3 else "base_optimizer_state") or {}
+    pgs = inner0.get("param_groups", []) if isinstance(inner0, dict) else []
+    out = OrderedDict()
+    steps = []
+
+    def states_of(sd, idx):
+        inner = sd.get("optimizer_state_dict" if stage3 else "base_optimizer_state") or {}
+        st = inner.get("state", {}) if isinstance(inner, dict) else {i: x for i, x in enumerate(inner)}
+        return st.get(idx) or {}
+
+    if stage3:
+        per_rank = []
+        for sd in shards:
+            flats = sd["fp32_flat_groups"]
+            acc = {"fp32": [f.float().reshape(-1) for f in flats]}
+            for i, f in enumerate(flats):
+                for k, v in states_of(sd, i).items():
+                    if torch.is_tensor(v) and v.numel() == f.numel():
+                        acc.setdefault(k, []).append(v.float().reshape(-1))
+            per_rank.append({k: torch.cat(v) for k, v in acc.items()})
+        st0 = states_of(shards[0], 0)
+        step0 = st0.get("step", pgs[0].get("step", 0) if pgs else 0)
+        steps = [float(step0) for _ in (param_shapes or [None])]
+        off = 0
+        for shapes in param_shapes:
+            for name, shape in shapes.items():
+                n = Z._numel(shape)
+                per = -(-n // world)
+                out[name] = {k: torch.cat([pr[k][off:off + per] for pr in per_rank])[:n].view(*shape).clone()
+                             for k in per_rank[0]}
+                off += per
+    else:
+        for g, shapes in enumerate(param_shapes):
+            keys = {"fp32": [sd["single_partition_of_fp32_groups"][g].float().reshape(-1) for sd in shards]}
+            P = None
+            for r, sd in enumerate(shards):
+                for k, v in states_of(sd, g).items():
+                    if torch.is_tensor(v) and v.dim() > 0 and v.numel() > 1:
+                        keys.setdefault(k, []).append(v.float().reshape(-1))
+            st0 = states_of(shards[0], g)
+            steps.append(float(st0.get("step", pgs[g].get("step", 0) if g < len(pgs) else 0)))
+            full = {k: torch.cat(v) for k, v in keys.items()}
+            off = 0
+            for name, shape in shapes.items():
+                n = Z._numel(shape)
+                out[name] = {k: t[off:off + n].view(*shape).clone() for k, t in full.items()}
+                off += n
+    return out, steps, pgs
+
+
+def _convert_reference_layout(ms, shards, output_folder, zero_dir):
+    params, steps, pgs = reference_param_states(shards, ms["param_shapes"])
+    group_of = {name: g for g, shapes in enumerate(ms["param_shapes"]) for name in shapes}
+    for name, states in params.items():
+        d = os.path.join(zero_dir, name)
+        os.makedirs(d, exist_ok=True)
+        for key, t in states.items():
+            torch.save({"param": t}, os.path.join(d, f"{key}.pt"))
+        g = group_of.get(name, 0)
+        torch.save(torch.tensor(float(steps[g] if g < len(steps) else 0)), os.path.join(d, "step.pt"))
+    ms = dict(ms)
+    ms[UNIVERSAL_CHECKPOINT_INFO] = {UNIVERSAL_CHECKPOINT_VERSION_KEY: UNIVERSAL_CHECKPOINT_VERSION_VALUE}
+    s0 = shards[0]
+    ls = s0.get("loss_scaler")
+    ms["optimizer_meta"] = {
+        "param_groups": [{k: v for k, v in g.items() if k not in ("params", "step")} for g in pgs],
+        "group_steps": s0.get("b200_group_steps", [int(x) for x in steps]),
+        "global_step": s0.get("b200_global_step", int(max(steps) if steps else 0)),
+        "loss_scaler": ls if isinstance(ls, dict) else None,
+        "zero_stage": s0.get("zero_stage"),
+    }
+    torch.save(ms, os.path.join(output_folder, "mp_rank_00_model_states.pt"))
+    parent = os.path.dirname(os.path.normpath(output_folder))
+    with open(os.path.join(parent, "latest_universal"), "w") as f:
+        f.write(os.path.basename(os.path.normpath(output_folder)))
+    n_states = len(next(iter(params.values()))) if params else 0
+    print(f"universal checkpoint: {len(params)} parameters x {n_states} tensors -> {output_folder}")
     return output_folder
 
 
@@ -274,10 +367,8 @@ def main(args=None):
     ms = Z._model_state(a.input_folder)
     if "ds_b200_layout" not in ms and "param_shapes" in ms:
         osd = Z._load(Z.get_optim_files(a.input_folder)[0])["optimizer_state_dict"]
-        if osd.get("zero_stage") == 3:
+        if osd.get("zero_stage") == 3 and len(osd.get("fp32_flat_groups", [])) == 1:
             return convert_upstream_stage3_to_universal(a.input_folder, a.output_folder, a.keep_temp_folder)
-        raise NotImplementedError("upstream stage 1/2 checkpoints: consolidate with zero_to_fp32 (weights), or convert "
-                                  "with extract_zero_shards/merge_tp_slices over a DeepSpeedCheckpoint")
     return convert_to_universal(a.input_folder, a.output_folder, strict=a.strict,
                                 inject_missing_state=a.inject_missing_state)
 

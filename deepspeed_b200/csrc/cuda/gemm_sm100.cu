@@ -708,10 +708,51 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
         : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+// ---- fused epilogues ------------------------------------------------------------------------------------------
+// EPI_STORE    C = acc
+// EPI_ACCUM    C = C + acc                                   (dW accumulation over micro-batches: no addmm, no memset)
+// EPI_SWIGLU   B = [gate; up] stacked ([2I, K]); a tile multiplies 128 gate rows (leader CTA's half of B) and the
+//              matching 128 up rows (peer CTA's half) so accumulator columns 0-127 / 128-255 are gate / up of the SAME
+//              128 features:  C[M, I] = silu(gate) * up,  optionally gate|up saved to out2 [M, 2I] for backward.
+// EPI_DSWIGLU  acc = d_act tile (dY W_down); aux = saved gate|up [M, 2I]:
+//              dgate = acc * up * silu'(gate) -> C (the [M, I] left half of dgate_up),  dup = acc * silu(gate) -> out2 + I.
+// (cuBLAS cannot express the last two: they remove one full pass over the [tokens, 2I] / [tokens, I] activations each.)
+enum : int { EPI_STORE = 0, EPI_ACCUM = 1, EPI_SWIGLU = 2, EPI_DSWIGLU = 3 };
+
+struct EpiParams {
+    const __nv_bfloat16* aux;  // DSWIGLU: saved gate|up
+    __nv_bfloat16* out2;       // SWIGLU: gate|up save (nullable); DSWIGLU: dgate_up base (dup goes to + inter)
+    __nv_bfloat16* c;          // ACCUM: C base for the read-modify-write
+    int ld_aux, ld_out2, ldc;
+    int inter;                 // I
+    int group_m;               // rasterisation: m-blocks per L2 super-group
+};
+
+__device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+__device__ __forceinline__ float dsilu_f(float g)
+{
+    const float sg = 1.f / (1.f + __expf(-g));
+    return sg * (1.f + g * (1.f - sg));
+}
+
+// Grouped rasterisation: tiles are numbered so that `group_m` consecutive m-blocks share every n-block before the next
+// group starts -- one wave of CTA pairs then touches ~group_m A-blocks and ~pairs/group_m B-blocks instead of all A-blocks
+// and two B-blocks, which keeps the wave's operand set inside L2 for the wide (N = 28672 / 128256) problems.
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk)
+{
+    const int per_group = group_m * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gm = (num_m - first_m) < group_m ? (num_m - first_m) : group_m;
+    const int local = tile - g * per_group;
+    m_blk = first_m + local % gm;
+    n_blk = local / gm;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, int M, int N, int K)
+                 const __grid_constant__ CUtensorMap map_c, int M, int N, int K, const EpiParams ep)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -752,10 +793,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // output-tile geometry: SWIGLU tiles are 128 output features wide (128 gate + 128 up accumulator columns)
+    constexpr int TN = (EPI == EPI_SWIGLU) ? BN / 2 : BN;
     const int num_m = (M + 2 * BM - 1) / (2 * BM);
-    const int num_n = (N + BN - 1) / BN;
+    const int num_n = (N + TN - 1) / TN;
     const int num_tiles = num_m * num_n;
     const int num_k = (K + BK - 1) / BK;
+    const int group_m = ep.group_m > 0 ? ep.group_m : num_m;
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -763,10 +807,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = pair; tile < num_tiles; tile += n_pairs) {
-                const int m_blk = tile % num_m;
-                const int n_blk = tile / num_m;
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
                 const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
-                const int n0 = n_blk * BN + static_cast<int>(rank) * (BN / 2);
+                // this CTA's half of the B tile: plain = columns [rank*128, +128) of the tile; SWIGLU = gate rows for the
+                // leader, the matching up rows (I further down the stacked weight) for the peer
+                const int n0 = (EPI == EPI_SWIGLU) ? static_cast<int>(rank) * ep.inter + n_blk * TN
+                                                   : n_blk * BN + static_cast<int>(rank) * (BN / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx_leader(full_bar(stage), A_STAGE_BYTES + B2_STAGE_BYTES);
@@ -832,46 +879,108 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ew = warp - 4;
         const int etid = threadIdx.x - 128;
         const int row = ew * 32 + lane;
+        constexpr int kChunks = TN / CCHUNK;  // 64-column output chunks per tile (4, SWIGLU: 2)
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
-            const int m_blk = tile % num_m;
-            const int n_blk = tile / num_m;
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
             const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+            const int grow = m0 + row;  // this thread's global row
+            const bool row_ok = grow < M;
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / CCHUNK; ++c) {
+            for (int c = 0; c < kChunks; ++c) {
                 const int buf = c & 1;
+                const int col0 = n_blk * TN + c * CCHUNK;  // first output column of this chunk
                 if (etid == 0) tma_store_wait_read<1>();
                 epi_bar_sync();
-                uint32_t r[64];
-                tmem_ld_32x32(taddr + c * CCHUNK, r);
-                tmem_ld_32x32(taddr + c * CCHUNK + 32, r + 32);
-                tmem_ld_wait();
-                if (c == BN / CCHUNK - 1) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(tempty_bar(as));
-                }
                 uint8_t* crow = smem + SMEM2_C + buf * C_BUF_BYTES + row * 128;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float f[8];
+                for (int h = 0; h < 2; ++h) {  // two 32-column halves: bounds the live registers of the fused modes
+                    const int colh = col0 + h * 32;
+                    Vec16 x0[4], x1[4];  // operands fetched from global memory (issued before the TMEM wait)
+                    if constexpr (EPI == EPI_ACCUM) {
+                        const __nv_bfloat16* src = ep.c + static_cast<int64_t>(grow) * ep.ldc + colh;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j * 8 + e]);
-                    const Vec16 v = Elem<__nv_bfloat16>::pack(f);
-                    const uint32_t dst = smem_u32(crow + ((j ^ (row & 7)) << 4));
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
-                                 "r"(v.w[3])
-                                 : "memory");
+                        for (int j = 0; j < 4; ++j) {
+                            if (row_ok && colh + j * 8 < N) x0[j] = ld_plain(src + j * 8);
+                            else x0[j] = Vec16{{0, 0, 0, 0}};
+                        }
+                    }
+                    if constexpr (EPI == EPI_DSWIGLU) {
+                        const __nv_bfloat16* src = ep.aux + static_cast<int64_t>(grow) * ep.ld_aux + colh;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (row_ok && colh + j * 8 < N) {
+                                x0[j] = ld_stream(src + j * 8);
+                                x1[j] = ld_stream(src + ep.inter + j * 8);
+                            } else {
+                                x0[j] = Vec16{{0, 0, 0, 0}};
+                                x1[j] = Vec16{{0, 0, 0, 0}};
+                            }
+                        }
+                    }
+                    uint32_t r[32], r2[32];
+                    tmem_ld_32x32(taddr + c * CCHUNK + h * 32, r);
+                    if constexpr (EPI == EPI_SWIGLU) tmem_ld_32x32(taddr + BN / 2 + c * CCHUNK + h * 32, r2);
+                    tmem_ld_wait();
+                    if (c == kChunks - 1 && h == 1) {
+                        // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(tempty_bar(as));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j * 8 + e]);
+                        if constexpr (EPI == EPI_ACCUM) {
+                            float o[8];
+                            Elem<__nv_bfloat16>::unpack(x0[j], o);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] += o[e];
+                        }
+                        if constexpr (EPI == EPI_SWIGLU) {
+                            float u[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) u[e] = __uint_as_float(r2[j * 8 + e]);
+                            if (ep.out2 != nullptr && row_ok && colh + j * 8 < N) {
+                                __nv_bfloat16* dst = ep.out2 + static_cast<int64_t>(grow) * ep.ld_out2 + colh + j * 8;
+                                st_plain(dst, Elem<__nv_bfloat16>::pack(f));
+                                st_plain(dst + ep.inter, Elem<__nv_bfloat16>::pack(u));
+                            }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]) * u[e];
+                        }
+                        if constexpr (EPI == EPI_DSWIGLU) {
+                            float g[8], u[8], du[8];
+                            Elem<__nv_bfloat16>::unpack(x0[j], g);
+                            Elem<__nv_bfloat16>::unpack(x1[j], u);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                du[e] = f[e] * silu_f(g[e]);
+                                f[e] = f[e] * u[e] * dsilu_f(g[e]);
+                            }
+                            if (row_ok && colh + j * 8 < N)
+                                st_plain(ep.out2 + static_cast<int64_t>(grow) * ep.ld_out2 + ep.inter + colh + j * 8,
+                                         Elem<__nv_bfloat16>::pack(du));
+                        }
+                        const Vec16 v = Elem<__nv_bfloat16>::pack(f);
+                        const uint32_t dst = smem_u32(crow + (((h * 4 + j) ^ (row & 7)) << 4));  // 128B swizzle
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                                     "r"(v.w[3])
+                                     : "memory");
+                    }
                 }
                 fence_async_smem();
                 epi_bar_sync();
                 if (etid == 0 && m0 < M) {
-                    tma_store_2d(&map_c, sbase + SMEM2_C + buf * C_BUF_BYTES, n_blk * BN + c * CCHUNK, m0);
+                    tma_store_2d(&map_c, sbase + SMEM2_C + buf * C_BUF_BYTES, col0, m0);
                     tma_store_commit();
                 }
             }
@@ -959,31 +1068,49 @@ static int launch(const void* a, const void* b, void* c, int M, int N, int K, in
 
 static bool g_attr2_set = false;
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI>
 static int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int M, int N, int K, int grid,
-                       cudaStream_t stream)
+                       const EpiParams& ep, cudaStream_t stream)
 {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_2cta_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_2cta_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              SMEM2_TOTAL);
         if (e != cudaSuccess) return static_cast<int>(e);
         attr = true;
     }
-    gemm_2cta_kernel<A_MN, B_MN><<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K);
+    gemm_2cta_kernel<A_MN, B_MN, EPI><<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K, ep);
     return 0;
 }
 
-// 2-CTA (cta_group::2) GEMM, 256x256 tiles per CTA pair:  C[M,N] = op(A) x op(B), bf16 in/out, fp32 accumulate.
+template <int EPI>
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int M,
+                          int N, int K, int grid, const EpiParams& ep, cudaStream_t stream)
+{
+    if (a_mn && b_mn) return launch_2cta<true, true, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
+    if (a_mn) return launch_2cta<true, false, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
+    if (b_mn) return launch_2cta<false, true, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
+    return launch_2cta<false, false, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
+}
+
+// 2-CTA (cta_group::2) GEMM, 256x256 tiles per CTA pair:  C[M,N] = epi(op(A) x op(B)), bf16 in/out, fp32 accumulate.
 //   a_mn == 0: A is stored [M, K] row-major (K-major)      a_mn == 1: A is stored [K, M] row-major (MN-major)
 //   b_mn == 0: B is stored [N, K] row-major (K-major)      b_mn == 1: B is stored [K, N] row-major (MN-major)
 // so (0,0) = "NT" (y = x W^T), (0,1) = "NN" (dx = dy W), (1,1) = "TN" (dW = dy^T x).  lda/ldb are row strides in elements.
-DSB_EXPORT int dsb_gemm_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
-                                  int a_mn, int b_mn, int sms, cudaStream_t stream)
+//   epi: 0 store, 1 accumulate into C, 2 SwiGLU (B = [gate; up] stacked [2*inter, K], N = inter, C = [M, inter], out2 =
+//   optional gate|up save [M, 2*inter]), 3 dSwiGLU (N = inter, aux = saved gate|up, C = out2 = dgate|dup [M, 2*inter]).
+//   group_m: m-blocks (of 256 rows) per rasterisation super-group, <= 0 = column-major tile order.
+DSB_EXPORT int dsb_gemm_bf16_2cta_ex(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                     int a_mn, int b_mn, int epi, const void* aux, int ld_aux, void* out2, int ld_out2,
+                                     int inter, int group_m, int sms, cudaStream_t stream)
 {
     if (lda % 8 || ldb % 8 || ldc % 8) return -2;
-    if ((a_mn ? M : K) % 8 || (b_mn ? N : K) % 8) return -2;
+    if ((a_mn ? M : K) % 8 || (b_mn ? N : K) % 8 || N % 8) return -2;
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return -2;
+    if (epi < 0 || epi > 3) return -2;
+    if (epi == EPI_SWIGLU && (a_mn || b_mn || inter != N || inter % (BN / 2) || (out2 && (ld_out2 % 8)))) return -2;
+    if (epi == EPI_DSWIGLU && (a_mn || !aux || !out2 || inter != N || ld_aux % 8 || ld_out2 % 8)) return -2;
+    if ((reinterpret_cast<uintptr_t>(aux) | reinterpret_cast<uintptr_t>(out2)) & 15) return -2;
     CUtensorMap ma, mb, mc;
     int rc;
     if (a_mn) {
@@ -991,11 +1118,13 @@ DSB_EXPORT int dsb_gemm_bf16_2cta(const void* a, const void* b, void* c, int M, 
     } else if ((rc = make_map(&ma, a, M, K, lda, BM, BK))) {
         return rc;
     }
+    const uint64_t b_rows = (epi == EPI_SWIGLU) ? static_cast<uint64_t>(2) * inter : static_cast<uint64_t>(N);
     if (b_mn) {
         if ((rc = make_map(&mb, b, K, N, ldb, 64, 64))) return rc;
-    } else if ((rc = make_map(&mb, b, N, K, ldb, BN / 2, BK))) {
+    } else if ((rc = make_map(&mb, b, b_rows, K, ldb, BN / 2, BK))) {
         return rc;
     }
+    // C map spans exactly [M, N]: a partial last tile is clipped by the TMA unit (dSwiGLU: N = inter, i.e. the dgate half)
     if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
     if (!g_attr2_set) {
         int dev = 0;
@@ -1003,21 +1132,39 @@ DSB_EXPORT int dsb_gemm_bf16_2cta(const void* a, const void* b, void* c, int M, 
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
         g_attr2_set = true;
     }
+    EpiParams ep;
+    ep.aux = static_cast<const __nv_bfloat16*>(aux);
+    ep.out2 = static_cast<__nv_bfloat16*>(out2);
+    ep.c = static_cast<__nv_bfloat16*>(c);
+    ep.ld_aux = ld_aux;
+    ep.ld_out2 = ld_out2;
+    ep.ldc = ldc;
+    ep.inter = inter;
+    ep.group_m = group_m;
     int grid = (sms > 0 ? sms : g_sm_count) & ~1;
-    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+    const int tn = (epi == EPI_SWIGLU) ? BN / 2 : BN;
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + tn - 1) / tn);
     if (grid / 2 > tiles) grid = tiles * 2;
     if (grid < 2) return -2;
-    if (a_mn && b_mn)
-        rc = launch_2cta<true, true>(ma, mb, mc, M, N, K, grid, stream);
-    else if (a_mn)
-        rc = launch_2cta<true, false>(ma, mb, mc, M, N, K, grid, stream);
-    else if (b_mn)
-        rc = launch_2cta<false, true>(ma, mb, mc, M, N, K, grid, stream);
-    else
-        rc = launch_2cta<false, false>(ma, mb, mc, M, N, K, grid, stream);
+    switch (epi) {
+        case EPI_STORE: rc = dispatch_major<EPI_STORE>(a_mn, b_mn, ma, mb, mc, M, N, K, grid, ep, stream); break;
+        case EPI_ACCUM: rc = dispatch_major<EPI_ACCUM>(a_mn, b_mn, ma, mb, mc, M, N, K, grid, ep, stream); break;
+        case EPI_SWIGLU: rc = launch_2cta<false, false, EPI_SWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream); break;
+        default:
+            rc = b_mn ? launch_2cta<false, true, EPI_DSWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream)
+                      : launch_2cta<false, false, EPI_DSWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream);
+            break;
+    }
     if (rc) return rc;
     DSB_CHECK_LAUNCH();
     return 0;
+}
+
+DSB_EXPORT int dsb_gemm_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,
+                                  int a_mn, int b_mn, int sms, cudaStream_t stream)
+{
+    return dsb_gemm_bf16_2cta_ex(a, b, c, M, N, K, lda, ldb, ldc, a_mn, b_mn, EPI_STORE, nullptr, 0, nullptr, 0, 0, 8, sms,
+                                 stream);
 }
 
 DSB_EXPORT int dsb_gemm_nt_bf16_2cta(const void* a, const void* b, void* c, int M, int N, int K, int lda, int ldb, int ldc,

@@ -164,6 +164,9 @@ class LlamaMLP(nn.Module):
         self.act = cfg.hidden_act
 
     def forward(self, x):
+        if self.act == "silu" and self.gate_up_proj.bias is None and self.down_proj.bias is None:
+            from deepspeed_b200.ops.linear import swiglu_mlp
+            return swiglu_mlp(x, self.gate_up_proj.weight, self.down_proj.weight)
         return self.down_proj(T.gated_act(self.gate_up_proj(x), self.act))
 
 

@@ -68,19 +68,32 @@ def matmul_nt_2cta(a, b, out=None, sms=0):
     return out
 
 
-def matmul_2cta(a, b, a_mn: bool, b_mn: bool, out=None, sms=0):
-    """CTA-pair kernel with selectable operand majorness.
+EPI_STORE, EPI_ACCUM, EPI_SWIGLU, EPI_DSWIGLU = 0, 1, 2, 3
+
+
+def matmul_2cta(a, b, a_mn: bool, b_mn: bool, out=None, sms=0, epi=EPI_STORE, aux=None, out2=None, inter=0, group_m=8):
+    """CTA-pair kernel with selectable operand majorness and fused epilogue.
 
     ``a_mn=False``: ``a`` is [M, K];  ``a_mn=True``: ``a`` is [K, M] (the kernel multiplies by its transpose).
     ``b_mn=False``: ``b`` is [N, K];  ``b_mn=True``: ``b`` is [K, N].
-    Result ``[M, N]`` bf16.  Rows may be strided (views of larger buffers)."""
+    Result ``[M, N]`` bf16.  Rows may be strided (views of larger buffers).
+    ``epi``: ``EPI_ACCUM`` adds into ``out``; ``EPI_SWIGLU`` -- ``b`` is ``[2*inter, K]`` (gate rows, then up rows), ``out``
+    is ``[M, inter]`` = ``silu(gate) * up`` and ``out2`` (optional ``[M, 2*inter]``) receives gate|up; ``EPI_DSWIGLU`` --
+    ``aux`` is the saved gate|up ``[M, 2*inter]``, ``out`` the dgate half and ``out2`` the whole ``[M, 2*inter]`` dgate|dup.
+    ``group_m``: m-blocks per rasterisation super-group (L2 locality)."""
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
-    Nn = b.shape[1] if b_mn else b.shape[0]
+    if epi == EPI_SWIGLU:
+        Nn = inter
+    else:
+        Nn = b.shape[1] if b_mn else b.shape[0]
     if out is None:
+        assert epi != EPI_ACCUM
         out = torch.empty(M, Nn, dtype=torch.bfloat16, device=a.device)
-    rc = N.cuda().dsb_gemm_bf16_2cta(N.ptr(a), N.ptr(b), N.ptr(out), M, Nn, K, a.stride(0), b.stride(0), out.stride(0),
-                                     int(a_mn), int(b_mn), sms, N.stream())
-    N.check(rc, "gemm_bf16_2cta")
+    rc = N.cuda().dsb_gemm_bf16_2cta_ex(N.ptr(a), N.ptr(b), N.ptr(out), M, Nn, K, a.stride(0), b.stride(0), out.stride(0),
+                                        int(a_mn), int(b_mn), int(epi), N.ptr(aux), aux.stride(0) if aux is not None else 0,
+                                        N.ptr(out2), out2.stride(0) if out2 is not None else 0, int(inter), int(group_m),
+                                        sms, N.stream())
+    N.check(rc, "gemm_bf16_2cta_ex")
     return out
 
 

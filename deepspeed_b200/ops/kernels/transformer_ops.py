@@ -223,6 +223,41 @@ def rope_qk_inplace(qkv, n_q, n_kv, head_dim, table, positions=None, seq_len=Non
 # ---------------------------------------------------------------------------------------------------
 # gated activation (SwiGLU & friends)
 # ---------------------------------------------------------------------------------------------------
+def gated_act_fwd_raw(gu, act=ACT_SILU):
+    """``act(gate) * up`` of a contiguous packed ``[T, 2I]`` tensor, no autograd."""
+    if isinstance(act, str):
+        act = act_code(act)
+    inter = gu.shape[-1] // 2
+    if gu.is_cuda:
+        out = torch.empty(gu.shape[0], inter, dtype=gu.dtype, device=gu.device)
+        rc = N.cuda().dsb_gated_act_fwd(_p(gu), _p(out), N.c_i64(gu.shape[0]), inter, act, N.dt(gu), N.stream())
+        N.check(rc, "gated_act_fwd")
+        return out
+    g, u = gu[:, :inter].float(), gu[:, inter:].float()
+    return (_act_torch(g, act) * u).to(gu.dtype)
+
+
+def gated_act_bwd(dout, gu, act=ACT_SILU):
+    """Gradient of :func:`gated_act` w.r.t. the packed ``[T, 2I]`` input: ``[d * up * act'(gate) | d * act(gate)]``."""
+    if isinstance(act, str):
+        act = act_code(act)
+    inter = gu.shape[-1] // 2
+    d2 = dout.reshape(-1, inter)
+    if not d2.is_contiguous():
+        d2 = d2.contiguous()
+    if gu.is_cuda:
+        dgu = torch.empty_like(gu)
+        rc = N.cuda().dsb_gated_act_bwd(_p(d2), _p(gu), _p(dgu), N.c_i64(gu.shape[0]), inter, act, N.dt(gu), N.stream())
+        N.check(rc, "gated_act_bwd")
+        return dgu
+    g = gu[:, :inter].float().requires_grad_(True)
+    u = gu[:, inter:].float()
+    with torch.enable_grad():
+        a = _act_torch(g, act)
+        (da, ) = torch.autograd.grad(a, g, torch.ones_like(a))
+    return torch.cat([d2.float() * u * da, d2.float() * a.detach()], dim=-1).to(gu.dtype)
+
+
 class _GatedActFn(torch.autograd.Function):
 
     @staticmethod
@@ -231,13 +266,7 @@ class _GatedActFn(torch.autograd.Function):
         gu = gate_up.reshape(-1, 2 * inter)
         if not gu.is_contiguous():
             gu = gu.contiguous()
-        if gu.is_cuda:
-            out = torch.empty(gu.shape[0], inter, dtype=gu.dtype, device=gu.device)
-            rc = N.cuda().dsb_gated_act_fwd(_p(gu), _p(out), N.c_i64(gu.shape[0]), inter, act, N.dt(gu), N.stream())
-            N.check(rc, "gated_act_fwd")
-        else:
-            g, u = gu[:, :inter].float(), gu[:, inter:].float()
-            out = (_act_torch(g, act) * u).to(gu.dtype)
+        out = gated_act_fwd_raw(gu, act)
         ctx.act, ctx.inter, ctx.shape = act, inter, gate_up.shape
         ctx.save_for_backward(gu)
         return out.view(*gate_up.shape[:-1], inter)
@@ -245,21 +274,7 @@ class _GatedActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         (gu, ) = ctx.saved_tensors
-        inter = ctx.inter
-        d2 = dout.reshape(-1, inter).contiguous()
-        if gu.is_cuda:
-            dgu = torch.empty_like(gu)
-            rc = N.cuda().dsb_gated_act_bwd(_p(d2), _p(gu), _p(dgu), N.c_i64(gu.shape[0]), inter, ctx.act, N.dt(gu),
-                                            N.stream())
-            N.check(rc, "gated_act_bwd")
-        else:
-            g = gu[:, :inter].float().requires_grad_(True)
-            u = gu[:, inter:].float()
-            with torch.enable_grad():
-                a = _act_torch(g, ctx.act)
-                (da, ) = torch.autograd.grad(a, g, torch.ones_like(a))
-            dgu = torch.cat([d2.float() * u * da, d2.float() * a.detach()], dim=-1).to(gu.dtype)
-        return dgu.view(ctx.shape), None
+        return gated_act_bwd(dout, gu, ctx.act).view(ctx.shape), None
 
 
 def _act_torch(g, act):

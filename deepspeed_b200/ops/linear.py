@@ -58,11 +58,9 @@ class _FlatLinearFn(torch.autograd.Function):
             if zo is not None:
                 gv = zo.grad_view_for(w)
                 if gv.dtype == dy2.dtype:
-                    if zo.grad_is_fresh(w):
-                        from deepspeed_b200.ops import gemm
-                        gemm.matmul_tn(dy2, x2, out=gv)
-                    else:
-                        gv.addmm_(dy2.t(), x2)
+                    from deepspeed_b200.ops import gemm
+                    # first micro step: overwrite; later ones: accumulate in the GEMM epilogue (no addmm, no memset)
+                    gemm.matmul_tn(dy2, x2, out=gv, accumulate=not zo.grad_is_fresh(w))
                 else:
                     g = torch.mm(dy2.t(), x2)
                     gv.copy_(g) if zo.grad_is_fresh(w) else gv.add_(g)
@@ -81,6 +79,66 @@ def flat_linear(x, weight, bias=None):
             y = y + bias
         return y.view(*x.shape[:-1], weight.shape[0])
     return _FlatLinearFn.apply(x, weight, bias)
+
+
+def _write_weight_grad(w, dy2, x2):
+    """dW = dy2^T x2 for parameter ``w``: straight into the ZeRO flat gradient view when there is one (returns None),
+    else returned for autograd."""
+    from deepspeed_b200.ops import gemm
+    zo = _zo_of(w)
+    if zo is None:
+        return gemm.matmul_tn(dy2, x2)
+    gv = zo.grad_view_for(w)
+    if gv.dtype == dy2.dtype:
+        gemm.matmul_tn(dy2, x2, out=gv, accumulate=not zo.grad_is_fresh(w))
+    else:
+        g = torch.mm(dy2.t(), x2)
+        gv.copy_(g) if zo.grad_is_fresh(w) else gv.add_(g)
+    zo.mark_grad_ready(w)
+    return None
+
+
+class _SwiGLUMLPFn(torch.autograd.Function):
+    """``down(silu(gate(x)) * up(x))`` as ONE autograd node over three GEMM launches per direction:
+
+    forward   gate|up GEMM with the SwiGLU applied in its epilogue (gate|up saved for backward from the same
+              accumulators) -> down GEMM;
+    backward  ``dY W_down`` GEMM with the SwiGLU *backward* applied in its epilogue (the ``[tokens, I]`` intermediate
+              gradient never reaches memory) -> dW_down, dX and dW_gate_up GEMMs, weight gradients written (or
+              accumulated, GAS > 1) directly into the ZeRO flat gradient views.
+    Reference role: the three ``nn.Linear`` + ``ACT2FN`` of an HF MLP block / ``csrc/transformer/gelu_kernels.cu``
+    (``fused_bias_gelu``) -- there the activation is a separate pass over the intermediate tensor."""
+
+    @staticmethod
+    def forward(ctx, x, w_gu, w_down):
+        from deepspeed_b200.ops import gemm
+        x2 = x.reshape(-1, x.shape[-1])
+        need_grad = any(ctx.needs_input_grad)  # (grad mode is off inside Function.forward)
+        act, gu = gemm.gate_up_swiglu(x2, w_gu, save_gate_up=need_grad)
+        y = gemm.matmul_nt(act, w_down)
+        ctx.w_gu, ctx.w_down = w_gu, w_down
+        ctx.save_for_backward(x2, gu, act)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w_down.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        from deepspeed_b200.ops import gemm
+        x2, gu, act = ctx.saved_tensors
+        w_gu, w_down = ctx.w_gu, ctx.w_down
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dgu = gemm.down_dx_dswiglu(dy2, w_down, gu)
+        dw_down = _write_weight_grad(w_down, dy2, act) if ctx.needs_input_grad[2] else None
+        dx = gemm.matmul_nn(dgu, w_gu).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        dw_gu = _write_weight_grad(w_gu, dgu, x2) if ctx.needs_input_grad[1] else None
+        return dx, dw_gu, dw_down
+
+
+def swiglu_mlp(x, w_gate_up, w_down):
+    """Fused SwiGLU MLP block (no biases): see :class:`_SwiGLUMLPFn`."""
+    return _SwiGLUMLPFn.apply(x, w_gate_up, w_down)
 
 
 class _ChunkedLinearXent(torch.autograd.Function):

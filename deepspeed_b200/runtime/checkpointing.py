@@ -101,9 +101,15 @@ class CheckpointMixin:
         return {"shard_world": zo.shard_world, "arena_numel": zo.arena_numel, "units": units, "stage": zo.stage}
 
     def _get_zero_param_shapes(self):
-        """List (per optimizer group) of ``OrderedDict name -> shape`` (reference engine.py:3536)."""
+        """List (per optimizer group) of ``OrderedDict name -> shape`` (reference engine.py:3536), in the order the
+        optimizer shards flatten the parameters (``ref_layout.group_param_order``)."""
         shapes = []
         if self.optimizer is None:
+            return shapes
+        if hasattr(self.optimizer, "rts") and not hasattr(self.optimizer, "parts"):
+            from deepspeed_b200.runtime.zero.ref_layout import group_param_order
+            for lst in group_param_order(self.optimizer):
+                shapes.append(OrderedDict((s.name, torch.Size(s.shape)) for _, s in lst))
             return shapes
         names = {id(p): n for n, p in self.module.named_parameters()}
         for g in self.optimizer.param_groups:
@@ -200,8 +206,12 @@ class CheckpointMixin:
     def _save_zero_checkpoint(self, save_path, tag):
         from deepspeed_b200 import __version__
         path = self._get_zero_ckpt_name(save_path, tag)
-        zsd = dict(optimizer_state_dict=self.optimizer.state_dict(), ds_config=self._config._param_dict,
-                   ds_version=__version__)
+        layout = (self._config._param_dict.get("checkpoint") or {}).get("b200_shard_layout", "reference")
+        try:
+            osd = self.optimizer.state_dict(layout=layout)
+        except TypeError:  # client / wrapped optimizers without the layout switch
+            osd = self.optimizer.state_dict()
+        zsd = dict(optimizer_state_dict=osd, ds_config=self._config._param_dict, ds_version=__version__)
         self.checkpoint_engine.save(zsd, path)
         if dist.get_rank() == 0:
             self._copy_recovery_script(save_path)
@@ -293,6 +303,7 @@ class CheckpointMixin:
             bufs = {k: v for k, v in ckpt["module"].items() if k in ckpt.get("buffer_names", [])}
             if bufs:
                 self.module.load_state_dict(bufs, strict=False)
+        self._loaded_param_shapes = ckpt.get("param_shapes")
         self.loaded_checkpoint_dp_world_size = ckpt.get("dp_world_size")
         self.loaded_checkpoint_mp_world_size = ckpt.get("mp_world_size")
         if not module_only:
@@ -342,9 +353,12 @@ class CheckpointMixin:
                            f"convert with ds_to_universal and set checkpoint.load_universal")
             return False
         zsd = self.checkpoint_engine.load(path, map_location="cpu")
+        kw = {}
+        if getattr(self, "_loaded_param_shapes", None) is not None:
+            kw["param_shapes"] = self._loaded_param_shapes  # parameter order of the shards (a stock checkpoint's own)
         self.optimizer.load_state_dict(zsd["optimizer_state_dict"], load_optimizer_states=load_optimizer_states,
                                        load_from_fp32_weights=self._config.zero_config.load_from_fp32_weights
-                                       or self.zero_optimization_partition_weights())
+                                       or self.zero_optimization_partition_weights(), **kw)
         log_dist(f"loaded zero checkpoint {path}", ranks=[0])
         return True
 

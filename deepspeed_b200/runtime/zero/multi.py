@@ -107,10 +107,11 @@ class ZeroOptimizerGroup:
     def get_global_grad_norm(self):
         return self.parts[0].get_global_grad_norm()
 
-    def state_dict(self):
-        return {"multi": [p.state_dict() for p in self.parts], "names": [p.name for p in self.parts]}
+    def state_dict(self, layout=None):
+        # several reduction domains: always the arena layout (the reference's MoE shards are organised per expert group)
+        return {"multi": [p.state_dict(layout="arena") for p in self.parts], "names": [p.name for p in self.parts]}
 
-    def load_state_dict(self, sd, load_optimizer_states=True, load_from_fp32_weights=True):
+    def load_state_dict(self, sd, load_optimizer_states=True, load_from_fp32_weights=True, param_shapes=None):
         for p, s in zip(self.parts, sd["multi"]):
             p.load_state_dict(s, load_optimizer_states, load_from_fp32_weights)
 

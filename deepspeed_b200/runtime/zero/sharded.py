@@ -1405,7 +1405,16 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 arena[a0:a0 + ln].copy_(flat[p0:p0 + ln].to(arena.device, arena.dtype))
 
     # ---- state dict ---------------------------------------------------------------------------------
-    def state_dict(self):
+    def state_dict(self, layout=None):
+        """This rank's optimizer shard.  ``layout="reference"`` (the default for sharded stages, see
+        ``checkpoint.b200_shard_layout``) writes the reference's on-disk format (``fp32_flat_groups`` +
+        ``optimizer_state_dict`` for stage 3; ``single_partition_of_fp32_groups`` + ``base_optimizer_state`` +
+        ``param_slice_mappings`` + ``group_paddings`` for stage 1/2 -- ``runtime/zero/ref_layout.py``) so stock tools read
+        it; ``layout="arena"`` dumps the rank-local arenas as they are (no re-partitioning traffic)."""
+        layout = layout or getattr(self, "checkpoint_layout", "arena")
+        if layout == "reference" and self.stage >= 1 and self.state_swapper is None:
+            from deepspeed_b200.runtime.zero.ref_layout import export_reference_state
+            return export_reference_state(self)
         sd = {
             "zero_stage": self.stage,
             "loss_scaler": self.loss_scaler.state_dict(),
@@ -1425,7 +1434,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             sd["flat_state"] = {k: v.detach().cpu().clone() for k, v in self.flat_opt.state_tensors().items()}
         return sd
 
-    def load_state_dict(self, sd, load_optimizer_states=True, load_from_fp32_weights=True):
+    def load_state_dict(self, sd, load_optimizer_states=True, load_from_fp32_weights=True, param_shapes=None):
+        from deepspeed_b200.runtime.zero import ref_layout
+        if ref_layout.is_reference_layout(sd):  # written by stock DeepSpeed or by us with layout="reference"
+            ref_layout.import_reference_state(self, sd, load_optimizer_states, load_from_fp32_weights, param_shapes)
+            return
         assert sd["partition_count"] == self.shard_world, (
             f"checkpoint was saved with {sd['partition_count']} shards but this run has {self.shard_world}; "
             f"use the universal checkpoint path to reshape")

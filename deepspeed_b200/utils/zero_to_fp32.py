@@ -261,10 +261,14 @@ def get_fp32_state_dict_from_zero_checkpoint(checkpoint_dir, tag=None, exclude_f
     ds_dir = _resolve_tag(checkpoint_dir, tag)
     ms = _model_state(ds_dir)
     layout = ms.get("ds_b200_layout")
-    if layout is None:
+    first = _load(get_optim_shards(ds_dir)[0][0])["optimizer_state_dict"]
+    if layout is None or "fp32_flat" not in first:
+        # upstream on-disk layout: written by stock DeepSpeed, or by this framework with checkpoint.b200_shard_layout =
+        # "reference" (the default)
         if "param_shapes" in ms:
             return _consolidate_upstream(ds_dir, exclude_frozen_parameters, lazy_mode)
         raise ValueError("checkpoint has neither ds_b200_layout nor param_shapes: not a ZeRO checkpoint")
+    del first
     shards = [_load(f)["optimizer_state_dict"] for f in get_optim_shards(ds_dir)[0]]
     world = shards[0]["partition_count"]
     if len(shards) != world:

@@ -42,7 +42,7 @@ for _ in range(2):
     step()
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
     for _ in range(a.steps):
         step()
     torch.cuda.synchronize()
@@ -51,4 +51,12 @@ os.makedirs(os.path.dirname(a.out), exist_ok=True)
 with open(a.out, "w") as f:
     f.write(f"# {a.model} layers={cfg.num_hidden_layers} seq={a.seq} mb={a.micro_batch} steps={a.steps}\n")
     f.write(tab)
+    # who launches the generic ATen element-wise kernels (fills / copies / adds)?  grouped by input shape
+    rows = [r for r in prof.key_averages(group_by_input_shape=True)
+            if any(k in r.key for k in ("fill_", "zero_", "copy_", "aten::add", "aten::mul", "aten::cat", "index"))
+            and r.device_time_total > 200]
+    rows.sort(key=lambda r: -r.device_time_total)
+    f.write("\n\n# generic ATen element-wise ops by input shape (device time over the profiled steps)\n")
+    for r in rows[:40]:
+        f.write(f"{r.key:40s} calls={r.count:5d} cuda_ms={r.device_time_total / 1e3:9.3f} shapes={r.input_shapes}\n")
 print(tab[-6000:])
