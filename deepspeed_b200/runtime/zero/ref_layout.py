@@ -18,7 +18,6 @@ host) so that the *stock* ``zero_to_fp32.py`` / ``ds_to_universal.py`` read this
 shard) so a checkpoint written by stock DeepSpeed resumes in-engine at the same DP degree.
 """
 from collections import OrderedDict
-from dataclasses import dataclass
 from typing import Dict, List
 
 import torch
@@ -38,11 +37,11 @@ CLIP_GRAD = "clip_grad"
 DS_VERSION = "ds_version"
 
 
-@dataclass
-class fragment_address:
-    """Same field names as the reference's ``utils/tensor_fragment.py:13`` (tools read ``.start`` / ``.numel``)."""
-    numel: int
-    start: int
+def fragment_address(numel: int, start: int):
+    """Same field names as the reference's ``utils/tensor_fragment.py:13`` (tools read ``.start`` / ``.numel``), but a
+    stdlib object so the shard unpickles without this package (the stock ``zero_to_fp32.py`` loads the whole file)."""
+    import types
+    return types.SimpleNamespace(numel=int(numel), start=int(start))
 
 
 def is_reference_layout(sd) -> bool:
@@ -99,6 +98,7 @@ def _torch_param_groups(zo):
     return groups
 
 
+@torch.no_grad()
 def export_reference_state(zo) -> dict:
     """This rank's optimizer shard in the reference layout (collective: every DP rank must call it)."""
     from deepspeed_b200 import __version__
@@ -268,6 +268,7 @@ def _flat_states_by_group(sd, n_groups, stage3):
     return per_group, steps
 
 
+@torch.no_grad()
 def import_reference_state(zo, sd, load_optimizer_states=True, load_from_fp32_weights=True, param_shapes=None):
     """Scatter a reference-layout shard (ours or stock DeepSpeed's) into the arenas (collective over the DP group)."""
     world, rank = zo.shard_world, zo.shard_rank

@@ -35,9 +35,12 @@ def _save_worker(d, stage):
     eng, *_ = ds.initialize(model=SimpleModel(), config=_cfg(stage, ds.comm.get_world_size()))
     _steps(eng, 3, 1)
     eng.save_checkpoint(d, tag="t3", client_state={"hello": 7})
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    at_save = {n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()}
+    if ds.comm.get_rank() == 0:
+        torch.save(at_save, os.path.join(d, "expect_at_save.pt"))
     # continue 2 more steps and record the parameters the resumed run must reproduce
     _steps(eng, 2, 2)
-    from deepspeed_b200.utils import safe_get_full_fp32_param
     full = {n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()}
     if ds.comm.get_rank() == 0:
         torch.save(full, os.path.join(d, "expect.pt"))
@@ -370,3 +373,114 @@ def test_deepspeed_checkpoint_layer_file_maps(tmp_path):
     assert merged.shape == (4, 3) and merged[:, 0].tolist() == [30.0, 30.0, 31.0, 31.0]
     assert len(ck1.get_2d_parallel_files(tp_index=0, pp_index=1)) == 2
     ck1.show_pp_transformer_map()
+
+
+# ---- interop with the UNMODIFIED reference (baseline/_ref), both directions -------------------------------------------
+_REF = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(_REF, "deepspeed")), reason="baseline/_ref is not installed")
+
+_REF_SAVE = r'''
+import os, sys
+sys.path.insert(0, {ref!r})
+os.environ.setdefault("DS_ACCELERATOR", "cpu")
+import torch, torch.distributed as dist
+import deepspeed
+sys.path.insert(0, {root!r})
+from tests.unit.simple_model import SimpleModel, make_batch
+out, stage = sys.argv[1], int(sys.argv[2])
+deepspeed.init_distributed(dist_backend="gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+model = SimpleModel()
+cfg = {{"train_micro_batch_size_per_gpu": 4, "zero_optimization": {{"stage": stage, "stage3_param_persistence_threshold": 0}},
+       "zero_allow_untested_optimizer": True, "zero_force_ds_cpu_optimizer": False}}
+opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.01)
+eng, *_ = deepspeed.initialize(model=model, optimizer=opt, config=cfg)
+g = torch.Generator().manual_seed(1)
+def steps(n):
+    for _ in range(n):
+        x, y = make_batch(w, 4, g)
+        eng.backward(eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4])); eng.step()
+steps(3)
+eng.save_checkpoint(out, tag="ref3", client_state={{"hello": 7}})
+steps(2)
+from deepspeed.utils import safe_get_full_fp32_param
+full = {{n: safe_get_full_fp32_param(p).detach().cpu().clone() for n, p in eng.module.named_parameters()}}
+if r == 0:
+    torch.save(full, os.path.join(out, "expect_after5.pt"))
+dist.barrier()
+'''
+
+
+def _run_ref_save(d, stage):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    script = os.path.join(d, "ref_save.py")
+    with open(script, "w") as f:
+        f.write(_REF_SAVE.format(ref=_REF, root=root))
+    env = dict(os.environ, DS_ACCELERATOR="cpu", PYTHONPATH=root)
+    port = 29700 + os.getpid() % 200
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), script, d, str(stage)], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def _resume_from_ref_worker(d, stage):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    torch.manual_seed(123)  # different init: everything must come from the stock checkpoint
+    cfg = {"train_micro_batch_size_per_gpu": 4, "optimizer": {"type": "AdamW", "params": {"lr": 1e-2, "weight_decay": 0.01}},
+           "zero_optimization": {"stage": stage, "stage3_param_persistence_threshold": 0}}
+    eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+    path, client = eng.load_checkpoint(d, tag="ref3")
+    assert path is not None and client["hello"] == 7 and eng.global_steps == 3
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        make_batch(w, 4, g)  # the batches the reference run consumed before saving
+    for _ in range(2):
+        x, y = make_batch(w, 4, g)
+        eng.backward(eng(x[r * 4:(r + 1) * 4], y[r * 4:(r + 1) * 4]))
+        eng.step()
+    exp = torch.load(os.path.join(d, "expect_after5.pt"))
+    for n, p in eng.module.named_parameters():
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), exp[n], atol=2e-6, rtol=1e-5)
+
+
+@needs_ref
+@pytest.mark.parametrize("stage", [2, 3])
+def test_resume_in_engine_from_stock_deepspeed_checkpoint(tmp_path, stage):
+    """(i) the unmodified reference trains 3 steps on gloo ws=2 and saves; this engine resumes from those files and its
+    next 2 steps land on the reference's own continuation."""
+    d = str(tmp_path)
+    _run_ref_save(d, stage)
+    run_distributed(_resume_from_ref_worker, 2, (d, stage))
+
+
+@needs_ref
+@pytest.mark.parametrize("stage", [1, 3])
+def test_stock_zero_to_fp32_reads_our_checkpoint(tmp_path, stage):
+    """(ii) a checkpoint saved HERE is consolidated by the reference's own ``zero_to_fp32.py`` (no deepspeed_b200 import)."""
+    import subprocess
+    import sys
+    d = str(tmp_path)
+    run_distributed(_save_worker, 2, (d, stage))
+    import shutil
+    script = os.path.join(d, "stock_zero_to_fp32.py")  # the reference copies its script next to the checkpoint too
+    shutil.copyfile(os.path.join(_REF, "deepspeed", "utils", "zero_to_fp32.py"), script)
+    out = os.path.join(d, "consolidated")
+    env = dict(os.environ, PYTHONPATH=_REF, DS_ACCELERATOR="cpu")  # the stock script imports the stock package only
+    p = subprocess.run([sys.executable, script, d, out, "--tag", "t3"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=d)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    files = [f for f in os.listdir(out) if f.endswith(".bin") or f.endswith(".pt")]
+    assert files, os.listdir(out)
+    got = {}
+    for f in files:
+        got.update(torch.load(os.path.join(out, f), map_location="cpu", weights_only=False))
+    exp = torch.load(os.path.join(d, "expect_at_save.pt"))
+    assert set(exp) <= set(got)
+    for n, v in exp.items():
+        torch.testing.assert_close(got[n].float(), v, atol=1e-6, rtol=1e-5)
