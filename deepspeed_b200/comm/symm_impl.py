@@ -167,6 +167,8 @@ class SymmContext:
         # worlds need more CTAs per kernel to keep up with backward (measured on Llama-3-8B: 2 GPUs 394.8 ms @64 -> 390.1 ms
         # @128; 8 GPUs prefer 64, which leaves more SM issue slots to the concurrent GEMMs)
         self.ctas = int(os.environ.get("DSB200_SYMM_CTAS", "128" if self.world <= 2 else "64"))
+        # the LAST reduction of a backward pass has no GEMM left to share the SMs with: give it the whole chip
+        self.tail_ctas = int(os.environ.get("DSB200_SYMM_TAIL_CTAS", "148"))
         self.ag_ctas = int(os.environ.get("DSB200_SYMM_AG_CTAS", str(self.ctas)))
         self.ag_mode = os.environ.get("DSB200_SYMM_AG", "ce").lower()  # "ce" (DMA engines) | "kernel" (SM pull)
         # signal pads live in their own small segment (never multicast-bound)
@@ -268,17 +270,17 @@ class SymmContext:
         return self._partials
 
     def reduce_scatter_accumulate(self, full_g: torch.Tensor, dst: torch.Tensor, shard_numel: int, scale: float,
-                                  accumulate: bool):
+                                  accumulate: bool, tail: bool = False):
         grads, mc = self._peers(full_g)
         if os.environ.get("DSB200_NVLS_RS", "1") == "0":
             mc = ctypes.c_void_p(0)
         rc = self.lib.dsb_symm_reduce_scatter_acc(grads, mc, N.ptr(dst), ctypes.c_int64(shard_numel), N.dt(full_g),
                                                   N.dt(dst), N.c_f(scale), int(accumulate), self._pads, self.rank,
                                                   self.world, CH_RS, self._take_epochs(CH_RS, 2), ctypes.c_void_p(0),
-                                                  self.ctas, N.stream())
+                                                  max(self.ctas, self.tail_ctas) if tail else self.ctas, N.stream())
         N.check(rc, "symm_reduce_scatter_acc")
 
-    def reduce_scatter_adam(self, zo, rt, full_g: torch.Tensor, scale: float):
+    def reduce_scatter_adam(self, zo, rt, full_g: torch.Tensor, scale: float, tail: bool = False):
         """Reduce-scatter fused with the AdamW update of this rank's shard of unit ``rt``."""
         u = rt.u
         a = u.arena_offset
@@ -303,8 +305,8 @@ class SymmContext:
         rc = self.lib.dsb_symm_reduce_scatter_adam(grads, mc, N.ptr(zo.master[a:a + n]), N.ptr(st["exp_avg"][a:a + n]),
                                                    N.ptr(st["exp_avg_sq"][a:a + n]), N.ptr(lp), ctypes.c_int64(n),
                                                    N.dt(full_g), N.dt(lp), N.c_f(scale), arr, len(segs), self._pads,
-                                                   self.rank, self.world, CH_RS, self._take_epochs(CH_RS, 2), self.ctas,
-                                                   N.stream())
+                                                   self.rank, self.world, CH_RS, self._take_epochs(CH_RS, 2),
+                                                   max(self.ctas, self.tail_ctas) if tail else self.ctas, N.stream())
         N.check(rc, "symm_reduce_scatter_adam")
 
     def all_reduce_(self, t: torch.Tensor) -> bool:

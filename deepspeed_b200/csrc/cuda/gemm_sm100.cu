@@ -749,11 +749,29 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = local / gm;
 }
 
+// Shared-memory plan of the CTA-pair kernel.  The dSwiGLU epilogue trades two pipeline stages for a double-buffered
+// staging area of the saved gate|up tiles (TMA-loaded by an otherwise idle warp while the MMAs of the tile still run).
+template <int EPI>
+struct Smem2 {
+    static constexpr int kStages = (EPI == EPI_DSWIGLU) ? 4 : STAGES2;
+    static constexpr uint32_t A = 0;
+    static constexpr uint32_t B = A + kStages * A_STAGE_BYTES;
+    static constexpr uint32_t C = B + kStages * B2_STAGE_BYTES;
+    static constexpr uint32_t AUX = C + 2 * C_BUF_BYTES;  // [2 buffers][gate chunk | up chunk] of 128 rows x 64 columns
+    static constexpr uint32_t AUX_BYTES = (EPI == EPI_DSWIGLU) ? 2 * 2 * C_BUF_BYTES : 0;
+    static constexpr uint32_t BAR = AUX + AUX_BYTES;
+    static constexpr uint32_t TOTAL = BAR + 256 + 1024;
+};
+
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, int M, int N, int K, const EpiParams ep)
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_aux, int M, int N,
+                 int K, const EpiParams ep)
 {
+    using L = Smem2<EPI>;
+    constexpr int STAGES2 = L::kStages;  // shadows the namespace constant: the ring depth of THIS instantiation
+    constexpr uint32_t SMEM2_A = L::A, SMEM2_B = L::B, SMEM2_C = L::C, SMEM2_BAR = L::BAR;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t sbase = smem_u32(smem);
@@ -763,6 +781,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto tfull_bar = [&](int s) { return bar_base + 8 * (2 * STAGES2 + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8 * (2 * STAGES2 + 2 + s); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM2_BAR + 8 * (2 * STAGES2 + 4));
+    auto aux_full_bar = [&](int b) { return bar_base + 8 * (2 * STAGES2 + 5 + b); };
+    auto aux_empty_bar = [&](int b) { return bar_base + 8 * (2 * STAGES2 + 7 + b); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -775,6 +795,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+        if constexpr (EPI == EPI_DSWIGLU) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_aux) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) {
@@ -784,6 +805,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+        }
+        if constexpr (EPI == EPI_DSWIGLU) {
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(aux_full_bar(b), 1);   // the loader's arrive.expect_tx (+ the TMA bytes)
+                mbar_init(aux_empty_bar(b), 4);  // one arrival per epilogue warp of THIS CTA
+            }
         }
         fence_barrier_init();
     }
@@ -874,12 +901,34 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 umma_commit2(tfull_bar(as));
             }
         }
+    } else if (warp == 3) {
+        // ===================== dSwiGLU: stage the saved gate|up tiles of upcoming chunks (both CTAs) =====================
+        if constexpr (EPI == EPI_DSWIGLU) {
+            if (elect_one()) {
+                uint32_t cnt = 0;
+                for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+                    int m_blk, n_blk;
+                    tile_coords(tile, num_m, num_n, group_m, m_blk, n_blk);
+                    const int m0 = m_blk * 2 * BM + static_cast<int>(rank) * BM;
+                    for (int c = 0; c < TN / CCHUNK; ++c, ++cnt) {
+                        const int b = cnt & 1;
+                        mbar_wait(aux_empty_bar(b), ((cnt >> 1) & 1) ^ 1);
+                        mbar_expect_tx(aux_full_bar(b), 2 * C_BUF_BYTES);
+                        const uint32_t dst = sbase + L::AUX + b * 2 * C_BUF_BYTES;
+                        const int col0 = n_blk * TN + c * CCHUNK;
+                        tma_load_2d(dst, &map_aux, aux_full_bar(b), col0, m0);                         // gate chunk
+                        tma_load_2d(dst + C_BUF_BYTES, &map_aux, aux_full_bar(b), ep.inter + col0, m0);  // up chunk
+                    }
+                }
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int ew = warp - 4;
         const int etid = threadIdx.x - 128;
         const int row = ew * 32 + lane;
         constexpr int kChunks = TN / CCHUNK;  // 64-column output chunks per tile (4, SWIGLU: 2)
+        uint32_t aux_cnt = 0;
         int it = 0;
         for (int tile = pair; tile < num_tiles; tile += n_pairs, ++it) {
             int m_blk, n_blk;
@@ -899,10 +948,16 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (etid == 0) tma_store_wait_read<1>();
                 epi_bar_sync();
                 uint8_t* crow = smem + SMEM2_C + buf * C_BUF_BYTES + row * 128;
+                const uint8_t* arow = nullptr;  // dSwiGLU: this thread's row of the staged gate chunk (up: + C_BUF_BYTES)
+                if constexpr (EPI == EPI_DSWIGLU) {
+                    const int ab = aux_cnt & 1;
+                    mbar_wait(aux_full_bar(ab), (aux_cnt >> 1) & 1);
+                    arow = smem + L::AUX + ab * 2 * C_BUF_BYTES + row * 128;
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {  // two 32-column halves: bounds the live registers of the fused modes
                     const int colh = col0 + h * 32;
-                    Vec16 x0[4], x1[4];  // operands fetched from global memory (issued before the TMEM wait)
+                    Vec16 x0[4], x1[4];  // operands fetched from global / shared memory (issued before the TMEM wait)
                     if constexpr (EPI == EPI_ACCUM) {
                         const __nv_bfloat16* src = ep.c + static_cast<int64_t>(grow) * ep.ldc + colh;
 #pragma unroll
@@ -912,16 +967,11 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                     if constexpr (EPI == EPI_DSWIGLU) {
-                        const __nv_bfloat16* src = ep.aux + static_cast<int64_t>(grow) * ep.ld_aux + colh;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (row_ok && colh + j * 8 < N) {
-                                x0[j] = ld_stream(src + j * 8);
-                                x1[j] = ld_stream(src + ep.inter + j * 8);
-                            } else {
-                                x0[j] = Vec16{{0, 0, 0, 0}};
-                                x1[j] = Vec16{{0, 0, 0, 0}};
-                            }
+                        for (int j = 0; j < 4; ++j) {  // same 128-byte swizzle as the C staging rows (TMA wrote them)
+                            const uint32_t off = static_cast<uint32_t>(((h * 4 + j) ^ (row & 7)) << 4);
+                            x0[j] = *reinterpret_cast<const Vec16*>(arow + off);
+                            x1[j] = *reinterpret_cast<const Vec16*>(arow + C_BUF_BYTES + off);
                         }
                     }
                     uint32_t r[32], r2[32];
@@ -976,6 +1026,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                      "r"(v.w[3])
                                      : "memory");
                     }
+                }
+                if constexpr (EPI == EPI_DSWIGLU) {
+                    // this warp's reads of the staged gate|up chunk are complete: hand the buffer back to the loader
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(aux_empty_bar(aux_cnt & 1));
+                    ++aux_cnt;
                 }
                 fence_async_smem();
                 epi_bar_sync();
@@ -1069,28 +1125,29 @@ static int launch(const void* a, const void* b, void* c, int M, int N, int K, in
 static bool g_attr2_set = false;
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int M, int N, int K, int grid,
-                       const EpiParams& ep, cudaStream_t stream)
+static int launch_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, int M,
+                       int N, int K, int grid, const EpiParams& ep, cudaStream_t stream)
 {
     static bool attr = false;
+    constexpr uint32_t smem = Smem2<EPI>::TOTAL;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_2cta_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             SMEM2_TOTAL);
+                                             smem);
         if (e != cudaSuccess) return static_cast<int>(e);
         attr = true;
     }
-    gemm_2cta_kernel<A_MN, B_MN, EPI><<<grid, kThreads, SMEM2_TOTAL, stream>>>(ma, mb, mc, M, N, K, ep);
+    gemm_2cta_kernel<A_MN, B_MN, EPI><<<grid, kThreads, smem, stream>>>(ma, mb, mc, mx, M, N, K, ep);
     return 0;
 }
 
 template <int EPI>
-static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, int M,
-                          int N, int K, int grid, const EpiParams& ep, cudaStream_t stream)
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
+                          const CUtensorMap& mx, int M, int N, int K, int grid, const EpiParams& ep, cudaStream_t stream)
 {
-    if (a_mn && b_mn) return launch_2cta<true, true, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
-    if (a_mn) return launch_2cta<true, false, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
-    if (b_mn) return launch_2cta<false, true, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
-    return launch_2cta<false, false, EPI>(ma, mb, mc, M, N, K, grid, ep, stream);
+    if (a_mn && b_mn) return launch_2cta<true, true, EPI>(ma, mb, mc, mx, M, N, K, grid, ep, stream);
+    if (a_mn) return launch_2cta<true, false, EPI>(ma, mb, mc, mx, M, N, K, grid, ep, stream);
+    if (b_mn) return launch_2cta<false, true, EPI>(ma, mb, mc, mx, M, N, K, grid, ep, stream);
+    return launch_2cta<false, false, EPI>(ma, mb, mc, mx, M, N, K, grid, ep, stream);
 }
 
 // 2-CTA (cta_group::2) GEMM, 256x256 tiles per CTA pair:  C[M,N] = epi(op(A) x op(B)), bf16 in/out, fp32 accumulate.
@@ -1126,6 +1183,8 @@ DSB_EXPORT int dsb_gemm_bf16_2cta_ex(const void* a, const void* b, void* c, int 
     }
     // C map spans exactly [M, N]: a partial last tile is clipped by the TMA unit (dSwiGLU: N = inter, i.e. the dgate half)
     if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
+    CUtensorMap mx = mc;  // dSwiGLU: the saved gate|up activations [M, 2*inter], staged chunk by chunk by the loader warp
+    if (epi == EPI_DSWIGLU && (rc = make_map(&mx, aux, M, static_cast<uint64_t>(2) * inter, ld_aux, BM, CCHUNK))) return rc;
     if (!g_attr2_set) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1147,12 +1206,12 @@ DSB_EXPORT int dsb_gemm_bf16_2cta_ex(const void* a, const void* b, void* c, int 
     if (grid / 2 > tiles) grid = tiles * 2;
     if (grid < 2) return -2;
     switch (epi) {
-        case EPI_STORE: rc = dispatch_major<EPI_STORE>(a_mn, b_mn, ma, mb, mc, M, N, K, grid, ep, stream); break;
-        case EPI_ACCUM: rc = dispatch_major<EPI_ACCUM>(a_mn, b_mn, ma, mb, mc, M, N, K, grid, ep, stream); break;
-        case EPI_SWIGLU: rc = launch_2cta<false, false, EPI_SWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream); break;
+        case EPI_STORE: rc = dispatch_major<EPI_STORE>(a_mn, b_mn, ma, mb, mc, mx, M, N, K, grid, ep, stream); break;
+        case EPI_ACCUM: rc = dispatch_major<EPI_ACCUM>(a_mn, b_mn, ma, mb, mc, mx, M, N, K, grid, ep, stream); break;
+        case EPI_SWIGLU: rc = launch_2cta<false, false, EPI_SWIGLU>(ma, mb, mc, mx, M, N, K, grid, ep, stream); break;
         default:
-            rc = b_mn ? launch_2cta<false, true, EPI_DSWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream)
-                      : launch_2cta<false, false, EPI_DSWIGLU>(ma, mb, mc, M, N, K, grid, ep, stream);
+            rc = b_mn ? launch_2cta<false, true, EPI_DSWIGLU>(ma, mb, mc, mx, M, N, K, grid, ep, stream)
+                      : launch_2cta<false, false, EPI_DSWIGLU>(ma, mb, mc, mx, M, N, K, grid, ep, stream);
             break;
     }
     if (rc) return rc;

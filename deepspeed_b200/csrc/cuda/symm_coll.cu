@@ -199,6 +199,19 @@ __device__ __forceinline__ void reduce8_mc_bf16(const void* mc_addr, float* acc)
     Elem<__nv_bfloat16>::unpack(v, acc);
 }
 
+// raw form of the above (the sum as packed bf16): lets a thread keep several switch reductions in flight before it
+// starts consuming them -- one 16-byte request per thread cannot cover the NVLink round trip
+__device__ __forceinline__ Vec16 mc_ld_reduce_raw(const void* mc_addr)
+{
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+                 : "l"(mc_addr)
+                 : "memory");
+    return v;
+}
+constexpr int kRsUnroll = 4;
+
 template <typename T, typename TD>
 __global__ void __launch_bounds__(512)
 reduce_scatter_acc_kernel(PeerPtrs grads, const void* __restrict__ mc_grads, TD* __restrict__ dst, int64_t shard_elems,
@@ -211,12 +224,7 @@ reduce_scatter_acc_kernel(PeerPtrs grads, const void* __restrict__ mc_grads, TD*
     const int64_t n8 = shard_elems >> 3;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     float ss = 0.f;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
-        float acc[8];
-        if (mc_grads != nullptr && sizeof(T) == 2)
-            reduce8_mc_bf16(static_cast<const char*>(mc_grads) + ((base + (i << 3)) * sizeof(T)), acc);
-        else
-            reduce8<T>(grads, rank, world, base + (i << 3), acc);
+    auto consume = [&](int64_t i, float* acc) {
         TD* d = dst + (i << 3);
         if (accumulate) {
             float old[8];
@@ -240,6 +248,29 @@ reduce_scatter_acc_kernel(PeerPtrs grads, const void* __restrict__ mc_grads, TD*
         } else {
             st_plain(d, Elem<TD>::pack(acc));
         }
+    };
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (mc_grads != nullptr && sizeof(T) == 2) {
+        const char* mc = static_cast<const char*>(mc_grads) + base * sizeof(T);
+        for (; i + (kRsUnroll - 1) * stride < n8; i += kRsUnroll * stride) {
+            Vec16 raw[kRsUnroll];
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u) raw[u] = mc_ld_reduce_raw(mc + ((i + u * stride) << 4));
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u) {
+                float acc[8];
+                Elem<__nv_bfloat16>::unpack(raw[u], acc);
+                consume(i + u * stride, acc);
+            }
+        }
+    }
+    for (; i < n8; i += stride) {
+        float acc[8];
+        if (mc_grads != nullptr && sizeof(T) == 2)
+            reduce8_mc_bf16(static_cast<const char*>(mc_grads) + ((base + (i << 3)) * sizeof(T)), acc);
+        else
+            reduce8<T>(grads, rank, world, base + (i << 3), acc);
+        consume(i, acc);
     }
     if (sumsq_partials != nullptr) {
         ss = block_reduce<SumOp>(ss, scratch);
@@ -269,19 +300,13 @@ reduce_scatter_adam_kernel(PeerPtrs grads, const void* __restrict__ mc_grads, fl
     const int64_t base = static_cast<int64_t>(rank) * shard_elems;
     const int64_t n8 = shard_elems >> 3;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
-        const int64_t o = i << 3;
-        float g[8];
-        if (mc_grads != nullptr && sizeof(T) == 2)
-            reduce8_mc_bf16(static_cast<const char*>(mc_grads) + ((base + o) * sizeof(T)), g);
-        else
-            reduce8<T>(grads, rank, world, base + o, g);
+    auto adam = [&](int64_t o, const float* g) {
         // segments are 8-aligned (PARAM_ALIGN), so one lookup per vector
         int si = -1;
 #pragma unroll 1
         for (int k = 0; k < segs.n; ++k)
             if (o >= segs.s[k].start && o < segs.s[k].end) si = k;
-        if (si < 0) continue;  // frozen / unmanaged range
+        if (si < 0) return;  // frozen / unmanaged range
         const AdamSeg a = segs.s[si];
         float p[8], mm[8], vv[8];
         Elem<float>::unpack(ld_stream(master + o), p);
@@ -307,6 +332,31 @@ reduce_scatter_adam_kernel(PeerPtrs grads, const void* __restrict__ mc_grads, fl
         st_stream(v + o, Elem<float>::pack(vv));
         st_stream(v + o + 4, Elem<float>::pack(vv + 4));
         st_plain(lp_out + o, Elem<TO>::pack(p));
+    };
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (mc_grads != nullptr && sizeof(T) == 2) {
+        // NVLS: keep kRsUnroll switch reductions per thread in flight (the NVLink round trip is several microseconds)
+        const char* mc = static_cast<const char*>(mc_grads) + base * sizeof(T);
+        for (; i + (kRsUnroll - 1) * stride < n8; i += kRsUnroll * stride) {
+            Vec16 raw[kRsUnroll];
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u) raw[u] = mc_ld_reduce_raw(mc + ((i + u * stride) << 4));
+#pragma unroll
+            for (int u = 0; u < kRsUnroll; ++u) {
+                float g[8];
+                Elem<__nv_bfloat16>::unpack(raw[u], g);
+                adam((i + u * stride) << 3, g);
+            }
+        }
+    }
+    for (; i < n8; i += stride) {
+        const int64_t o = i << 3;
+        float g[8];
+        if (mc_grads != nullptr && sizeof(T) == 2)
+            reduce8_mc_bf16(static_cast<const char*>(mc_grads) + ((base + o) * sizeof(T)), g);
+        else
+            reduce8<T>(grads, rank, world, base + o, g);
+        adam(o, g);
     }
     gate_exit(pads, rank, world, channel, epoch);
 }

@@ -28,6 +28,11 @@ import torch
 _ALIASES = {"sm100": "own", "cublas": "lib", "auto": "auto", "own": "own", "lib": "lib"}
 _backend = _ALIASES.get(os.environ.get("DSB200_GEMM", "auto").lower(), "auto")
 TIE_MARGIN = 0.03
+# fused-epilogue forms: the library alternative is a GEMM plus a separate element-wise pass over the [tokens, 2I]
+# activations; timed alone that pass runs at full HBM bandwidth, inside a training step it shares HBM with the overlapped
+# reduce-scatter / optimizer kernels (measured 0.23 ms alone vs 0.3-0.67 ms in-step), while the fused epilogue's traffic
+# hides under the MMAs -- so the fused kernel is kept unless the library pair is clearly (> 10 %) faster in isolation
+FUSED_TIE_MARGIN = 0.10
 GROUP_M = int(os.environ.get("DSB200_GEMM_GROUP_M", "8"))
 _TABLE_PATH = os.path.join(os.path.dirname(__file__), "gemm_table.json")
 
@@ -130,6 +135,10 @@ def _time_interleaved(fns, warm=5, iters=20):
     return [sorted(x)[len(x) // 2] for x in samples]
 
 
+def _margin(key):
+    return FUSED_TIE_MARGIN if key.startswith(("nt_swiglu", "nn_dswiglu")) else TIE_MARGIN
+
+
 def _choose(key, own_fn, lib_fn):
     """-> "own" | "lib" for problem ``key``; ``own_fn`` / ``lib_fn`` run the problem on scratch outputs."""
     if _backend != "auto":
@@ -142,7 +151,7 @@ def _choose(key, own_fn, lib_fn):
             else:
                 try:
                     t_own, t_lib = _time_interleaved([own_fn, lib_fn])
-                    choice = "own" if t_own <= t_lib * (1.0 + TIE_MARGIN) else "lib"
+                    choice = "own" if t_own <= t_lib * (1.0 + _margin(key)) else "lib"
                     _measured[key] = {"own_ms": t_own, "lib_ms": t_lib}
                 except Exception:
                     choice = "lib"

@@ -173,7 +173,8 @@ class _ChunkedLinearXent(torch.autograd.Function):
                     from deepspeed_b200.ops import gemm
                     gemm.matmul_tn(grad, hc, out=dw_tmp)
                 else:
-                    dw_tmp.addmm_(grad.t(), hc)
+                    from deepspeed_b200.ops import gemm
+                    gemm.matmul_tn(grad, hc, out=dw_tmp, accumulate=True)  # accumulate in the GEMM epilogue
             first = False
         ctx.weight_ref = weight
         ctx.assumed_scale = assumed_scale

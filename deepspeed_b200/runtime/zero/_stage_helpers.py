@@ -6,7 +6,8 @@ import torch
 
 from deepspeed_b200 import comm as dist
 
-pg_correctness_test = False
+# (the reference's ``pg_correctness_test`` debug switch lives on as ``zero_optimization.b200_verify_collectives``: every
+# in-kernel NVLink collective is cross-checked against NCCL at run time, see ``sharded.py:_verify_reduce_scatter``)
 OPTIMIZER_ALLGATHER_TIMER, OPTIMIZER_GRADIENTS_TIMER, OPTIMIZER_STEP_TIMER = "optimizer_allgather", "optimizer_gradients", \
     "optimizer_step"
 OPTIMIZER_TIMERS = [OPTIMIZER_ALLGATHER_TIMER, OPTIMIZER_GRADIENTS_TIMER, OPTIMIZER_STEP_TIMER]

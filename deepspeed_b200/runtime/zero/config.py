@@ -6,6 +6,7 @@ All reference keys are accepted with the same defaults.  B200-specific additions
 * ``b200_fused_collectives``: ``"auto" | true | false`` -- use in-kernel peer-memory
   all-gather / reduce-scatter(+Adam) instead of NCCL.
 * ``b200_unit_prefetch``: how many ZeRO-3 units to gather ahead.
+* ``b200_verify_collectives``: N > 0 cross-checks every symmetric-memory collective against NCCL for N steps.
 """
 import sys
 from enum import Enum
@@ -116,6 +117,9 @@ class DeepSpeedZeroConfig(DeepSpeedConfigModel):
     b200_unit_prefetch: int = Field(1, ge=0)
     b200_fused_optimizer_in_backward: Optional[bool] = None  # None == auto (on when no clipping / GAS==1)
     b200_nvls: Optional[bool] = None  # None == auto (multimem when the multicast object binds)
+    # debug: for the first N optimizer steps run the NCCL collective next to every in-kernel NVLink collective and assert
+    # agreement (the reference's ``pg_correctness_test`` switch, stage_1_and_2.py:36, made real)
+    b200_verify_collectives: int = Field(0, ge=0)
 
     @model_validator(mode="after")
     def overlap_comm_valid(self):

@@ -236,6 +236,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self._in_backward = False
         self._symm = None
         self._maybe_enable_symm()
+        self._verify_left = int(getattr(self.zc, "b200_verify_collectives", 0) or 0) if self._symm is not None else 0
+        self.verify_report = {"all_gather": 0, "reduce_scatter": 0, "max_rel_err": 0.0}
         log_dist(
             f"ZeroShardedOptimizer: stage={self.stage} units={len(self.units)} arena={self.arena_numel:,} elems/rank "
             f"shard_world={self.shard_world} fused_in_backward={self.fused_in_backward} "
@@ -730,6 +732,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             return
         if self._symm is not None and self._symm.owns(full) and self._symm.owns(shard):
             self._symm.all_gather(full, shard, u.shard_numel)
+            if self._verify_left > 0:
+                self._verify_all_gather(full, shard, u)
             return
         mg = getattr(self, "mics_groups", None)
         if mg is not None and mg.param_inter_node_shard_group is not None:
@@ -793,6 +797,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     def gather_all(self):
         """Gather every unit (used by state-dict export / GatheredParameters on the whole model)."""
         for rt in self.rts:
+            self._ensure_ready(rt)
             if self.transient and not rt.u.persistent and rt.state == NOT_GATHERED:
                 buf = torch.empty(rt.u.full_numel, dtype=self.model_dtype, device=self.device)
                 shard = self._lp_shard(rt.u)
@@ -928,20 +933,51 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             return
         flat_ops.scale_cast(shard_g, dst, scale=scale, accumulate=not first)
 
+    # ---- runtime cross-check of the in-kernel collectives against NCCL (zero_optimization.b200_verify_collectives) ---------
+    def _verify_all_gather(self, full, shard, u):
+        ref = torch.empty(u.full_numel, dtype=full.dtype, device=full.device)
+        dist.all_gather_into_tensor(ref, shard.contiguous(), group=self.dp_group)
+        if not torch.equal(ref, full[:u.full_numel]):
+            bad = int((ref != full[:u.full_numel]).sum())
+            raise RuntimeError(f"b200_verify_collectives: symmetric all-gather of unit '{u.name}' differs from NCCL in "
+                               f"{bad} of {u.full_numel} elements")
+        self.verify_report["all_gather"] += 1
+
+    def _verify_reduce_scatter(self, rt, full_g, scale):
+        """Reduce ``full_g`` twice -- NCCL and the NVLink kernel (into scratch) -- before the real kernel consumes it."""
+        u = rt.u
+        ref = torch.empty(u.shard_numel, dtype=full_g.dtype, device=full_g.device)
+        dist.reduce_scatter_tensor(ref, full_g[:u.full_numel].clone(), group=self.dp_group)
+        got = torch.empty(u.shard_numel, dtype=torch.float32, device=full_g.device)
+        self._symm.reduce_scatter_accumulate(full_g, got, u.shard_numel, 1.0, accumulate=False)
+        refs = ref.float()
+        denom = float(refs.abs().max().clamp(min=1e-6))
+        err = float((got - refs).abs().max()) / denom
+        # bf16 rounding of the NCCL / switch sums bounds the disagreement
+        if not (err < 2e-2):
+            raise RuntimeError(f"b200_verify_collectives: symmetric reduce-scatter of unit '{u.name}' deviates from NCCL "
+                               f"(max rel err {err:.3e})")
+        self.verify_report["reduce_scatter"] += 1
+        self.verify_report["max_rel_err"] = max(self.verify_report["max_rel_err"], err)
+
     def _symm_reduce(self, rt: _UnitRT, full_g, scale):
         """In-kernel reduce-scatter over NVLink peer memory, fused with scale + (Adam | accumulate).
         Returns ``None`` when the kernel consumed the gradient, else ``(shard_grad, remaining_scale)``."""
         u = rt.u
         a, b = u.arena_offset, u.arena_offset + u.shard_numel
+        if self._verify_left > 0:
+            self._verify_reduce_scatter(rt, full_g, scale)
         boundary = self.is_gradient_accumulation_boundary()
+        # the unit that forward visited first is reduced last: nothing is left to overlap with, so it gets every SM
+        tail = bool(self._trace_done and self._trace and u.index == self._trace[0])
         if self.fused_in_backward and boundary and isinstance(self.flat_opt, _adam_cls()) and self.master is not None \
                 and not rt.reduced_this_micro:
-            self._symm.reduce_scatter_adam(self, rt, full_g, scale)
+            self._symm.reduce_scatter_adam(self, rt, full_g, scale, tail=tail)
             return None
         if self.grad_arena is not None and self.grad_arena.is_cuda and not self.fused_in_backward:
             first = self._first_micro(rt)
             self._symm.reduce_scatter_accumulate(full_g, self.grad_arena[a:b], u.shard_numel, scale,
-                                                 accumulate=not first)
+                                                 accumulate=not first, tail=tail)
             return None
         tmp = self._rs_tmp[u.index % 2][:u.shard_numel]
         self._symm.reduce_scatter_accumulate(full_g, tmp, u.shard_numel, scale, accumulate=False)
@@ -1257,6 +1293,36 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             self._step_event = ev
         self._accum = 0
         self.global_step += 1
+        self._prefetch_next_forward()
+        if self._verify_left > 0:
+            self._verify_left -= 1
+            if self._verify_left == 0:
+                log_dist(f"b200_verify_collectives: NVLink kernels agreed with NCCL ({self.verify_report})", ranks=[0])
+
+    def _prefetch_next_forward(self):
+        """Start gathering the first units of the NEXT forward right after the step that produced their new values.
+
+        The parameter pool is idle between ``step()`` and the next ``forward`` (loss read-back, data loading, the engine's
+        Python), and the first forward units otherwise wait for a cold all-gather with nothing to overlap (the 3.6 ms
+        "exposed all-gather" of the 8-GPU Llama-3-8B run).  Only done once the unit order is known and for as many units
+        as the pool can hold next to the usual look-ahead."""
+        if not (self.transient and self._trace_done and self._trace and self.on_cuda and self.ag_stream is not None):
+            return
+        if self.offload_param or not torch.is_grad_enabled():
+            return
+        n = 0
+        for idx in self._trace:
+            rt = self.rts[idx]
+            if rt.u.persistent:
+                continue
+            if n >= 1 + self.prefetch_depth:
+                break
+            if rt.state == NOT_GATHERED and rt.temp_refs == 0:
+                slot = self.param_pool[rt.u.index % len(self.param_pool)]
+                if slot.owner is not None and slot.owner is not rt and slot.owner.state != NOT_GATHERED:
+                    break  # the pool slot is still held: leave it to the regular on-demand path
+                self._launch_gather(rt)
+            n += 1
 
     # =========================================================================================
     # GatheredParameters / external-parameter support
@@ -1265,9 +1331,18 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         rt = self.unit_of_param[id(p)]
         return (not self.transient) or rt.u.persistent or rt.state != NOT_GATHERED
 
+    def _ensure_ready(self, rt):
+        """A unit gathered speculatively (look-ahead / post-step prefetch) is only ordered on ``ag_stream``: make the
+        current stream wait for it before anybody outside forward/backward touches the data."""
+        if rt.state == INFLIGHT:
+            if rt.gather_event is not None and self.on_cuda:
+                torch.cuda.current_stream().wait_event(rt.gather_event)
+            rt.state = GATHERED
+
     def gather_param_temp(self, p):
         """Gather the unit owning ``p`` into a private buffer (outside the rotating pool)."""
         rt = self.unit_of_param[id(p)]
+        self._ensure_ready(rt)
         if rt.state == NOT_GATHERED:
             buf = torch.empty(rt.u.full_numel, dtype=self.model_dtype, device=self.device)
             shard = self._lp_shard(rt.u)
@@ -1294,6 +1369,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         """Propagate an in-place edit of a gathered parameter: broadcast from ``src_rank`` then refresh
         this rank's low-precision shard and fp32 master."""
         rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        self._ensure_ready(rt)
         full = rt.full[s.offset:s.offset + s.numel]
         if self.dp_world > 1:
             src = dist.get_global_rank(self.dp_group, src_rank) if self.dp_group is not None else src_rank
@@ -1309,6 +1385,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
     def get_full_lp_param(self, p):
         rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        self._ensure_ready(rt)
         if rt.state != NOT_GATHERED and rt.full is not None:
             return rt.full[s.offset:s.offset + s.numel].view(s.shape)
         arena = self._lp_arena_as_flat()
@@ -1388,6 +1465,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             if r == self.shard_rank:
                 dst = self._lp_shard(rt.u)[a0 - rt.u.arena_offset:a0 - rt.u.arena_offset + ln]
                 dst.copy_(value.reshape(-1)[p0:p0 + ln].to(dst.device, dst.dtype))
+        self._ensure_ready(rt)
         if rt.state == GATHERED and rt.full is not None:
             rt.full[s.offset:s.offset + s.numel].copy_(value.reshape(-1).to(rt.full.device, rt.full.dtype))
 

@@ -95,6 +95,7 @@ def problems(cfg, tokens, chunk):
     out.append(("nt", c, V, H))                # LM head chunk
     out.append(("nn", c, H, V))
     out.append(("tn", V, H, c))
+    out.append(("tn_acc", V, H, c))
     return out
 
 
@@ -159,7 +160,7 @@ for model in a.models.split(","):
             t_own, t_lib = min(ts[:-1]), ts[-1]
             best_gm = gms[ts.index(t_own)]
             flops = 2.0 * M * N * Kd * (2 if kind == "nt_swiglu" else 1)
-            choice = "own" if t_own <= t_lib * (1 + gemm.TIE_MARGIN) else "lib"
+            choice = "own" if t_own <= t_lib * (1 + gemm._margin(key)) else "lib"
             shapes[key] = {"choice": choice, "own_ms": round(t_own, 4), "lib_ms": round(t_lib, 4),
                            "own_tflops": round(flops / t_own / 1e9, 1), "lib_tflops": round(flops / t_lib / 1e9, 1),
                            "group_m": best_gm, "model": model}

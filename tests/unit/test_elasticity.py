@@ -55,3 +55,53 @@ def test_engine_config_uses_elastic_batch():
     cfg = DeepSpeedConfig(c)
     assert cfg.world_size == 4
     assert cfg.train_batch_size == cfg.train_micro_batch_size_per_gpu * cfg.gradient_accumulation_steps * 4
+
+
+def test_elastic_agent_supervision_policy():
+    """The run-loop policy of DSElasticAgent (reference elastic_agent.py:127-188) as a pure function."""
+    from deepspeed_b200.elasticity.elastic_agent import (CONTINUE, FAIL, FINISH, RESCALE, RESTART, supervise_decision)
+    assert supervise_decision("SUCCEEDED", 3, 4, 4, 0) == FINISH
+    assert supervise_decision("HEALTHY", 3, 4, 4, 0) == CONTINUE
+    assert supervise_decision("HEALTHY", 0, 4, 4, 2) == RESCALE          # growth is free: no restart budget needed
+    assert supervise_decision("FAILED", 2, 4, 4, 0) == RESTART
+    assert supervise_decision("UNHEALTHY", 0, 4, 4, 0) == FAIL
+    assert supervise_decision("HEALTHY", 1, 4, 3, 0) == RESTART          # a participant left the rendezvous
+    assert supervise_decision("HEALTHY", 0, 4, 4, 0, dead_nodes=1) == FAIL  # lost heartbeat, budget exhausted
+    import pytest
+    with pytest.raises(RuntimeError):
+        supervise_decision("INIT", 1, 1, 1, 0)
+
+
+def test_elastic_agent_run_loop_restarts_then_finishes():
+    """Drive ``DSElasticAgent._invoke_run`` with a scripted worker group: FAILED -> restart -> new node -> rescale ->
+    SUCCEEDED; restart budget is charged only for the failure."""
+    import types
+    from torch.distributed.elastic.agent.server.api import RunResult, WorkerState
+    from deepspeed_b200.elasticity.elastic_agent import DSElasticAgent
+    agent = DSElasticAgent.__new__(DSElasticAgent)
+    script = [WorkerState.FAILED, WorkerState.HEALTHY, WorkerState.HEALTHY, WorkerState.SUCCEEDED]
+    waiting = [0, 1, 0, 0]
+    calls = {"restart": 0, "barrier": 0, "tick": 0}
+    rdzv = types.SimpleNamespace(
+        _state_holder=types.SimpleNamespace(state=types.SimpleNamespace(participants={"a": 0, "b": 1}, last_heartbeats={})),
+        _settings=None, num_nodes_waiting=lambda: waiting[min(calls["tick"] - 1, 3)])
+    spec = types.SimpleNamespace(role="trainer", monitor_interval=0.0, rdzv_handler=rdzv, max_restarts=2,
+                                 get_entrypoint_name=lambda: "train.py")
+    agent._worker_group = types.SimpleNamespace(spec=spec, state=WorkerState.HEALTHY, group_rank=0)
+    agent._remaining_restarts = 2
+    agent._exit_barrier_timeout = 1
+    agent._initialize_workers = lambda wg: None
+
+    def monitor(wg):
+        st = script[calls["tick"]]
+        calls["tick"] += 1
+        return RunResult(state=st)
+
+    agent._monitor_workers = monitor
+    agent._restart_workers = lambda wg: calls.__setitem__("restart", calls["restart"] + 1)
+    agent._stop_workers = lambda wg: None
+    agent._exit_barrier = lambda: calls.__setitem__("barrier", calls["barrier"] + 1)
+    res = agent._invoke_run()
+    assert res.state == WorkerState.SUCCEEDED
+    assert calls["restart"] == 2 and calls["barrier"] == 1
+    assert agent._remaining_restarts == 1  # only the FAILED tick consumed an attempt
