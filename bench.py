@@ -143,12 +143,13 @@ def timed_loop(torch, dist_mod, world, steps, body):
 
 def common_config(args, world):
     """The part of the JSON line that must be IDENTICAL in both arms (the driver diffs it)."""
+    par = f"zero{args.zero_stage}-dp{world}" + (f"-ep{world}" if args.model.startswith("mixtral") else "")
     return {
         "model": args.model + ("" if args.layers is None else f"-TRUNCATED-{args.layers}L"),
         "global_batch": args.micro_batch * world * args.gas,
         "micro_batch_per_gpu": args.micro_batch,
         "seq_len": args.seq,
-        "parallelism": f"zero{args.zero_stage}-dp{world}",
+        "parallelism": par,
         "zero_stage": args.zero_stage,
         "optimizer": "AdamW(lr=1e-5, betas=(0.9,0.95), eps=1e-8, wd=0.1), fp32 master + moments",
         "gradient_clipping": args.clip,
@@ -221,9 +222,17 @@ def run_b200(args):
     over = {}
     if args.layers is not None:
         over["num_hidden_layers"] = args.layers
-    cfg = llama_config(args.model, **over)
-    cfg.checkpoint_layers = pick_checkpoint_layers(torch, cfg, args.micro_batch, args.seq, world, args.zero_stage,
-                                                   args.checkpoint_layers)
+    moe = args.model.startswith("mixtral") or args.model.endswith("-moe")
+    if moe:
+        # BASELINE config 3: Mixtral with expert parallelism over all ranks (dispatch / combine = the in-kernel NVLink
+        # all-to-all of moe/symm_ep.py); dense parameters ZeRO-sharded over the data-parallel group
+        from deepspeed_b200.models.mixtral import MixtralForCausalLM, mixtral_config
+        cfg = mixtral_config(args.model, ep_size=world, **over)
+        cfg.checkpoint_layers = 0
+    else:
+        cfg = llama_config(args.model, **over)
+        cfg.checkpoint_layers = pick_checkpoint_layers(torch, cfg, args.micro_batch, args.seq, world, args.zero_stage,
+                                                       args.checkpoint_layers)
     hf = args.model_impl == "hf"
     zero = {"stage": args.zero_stage, "overlap_comm": True}
     if args.fused_collectives != "auto":
@@ -236,11 +245,11 @@ def run_b200(args):
             # the engine's own contribution in isolation: same HF module as the reference arm, this framework's engine
             model = hf_llama(torch, cfg, grad_ckpt=hf_ckpt)
         else:
-            torch.manual_seed(1234)
+            torch.manual_seed(1234 + (rank if moe else 0))  # experts differ per rank, dense weights are broadcast
             prev = torch.get_default_dtype()
             torch.set_default_dtype(torch.bfloat16)
             with torch.device("cuda"):
-                model = LlamaForCausalLM(cfg)
+                model = MixtralForCausalLM(cfg) if moe else LlamaForCausalLM(cfg)
             torch.set_default_dtype(prev)
         return ds.initialize(model=model, config=ds_config)[0]
 
@@ -321,7 +330,13 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        flops = cfg.flops_per_token(S) * val / world
+        if moe:  # active parameters per token: attention + top-k experts + router
+            h_, i_, L_ = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+            mm = 2 * (h_ * (cfg.q_size + 2 * cfg.kv_size) + cfg.q_size * h_ + cfg.num_experts_per_tok * 3 * h_ * i_ +
+                      h_ * cfg.num_local_experts) * L_ + 2 * h_ * cfg.vocab_size
+            flops = 3 * (mm + 4 * S * cfg.q_size * L_ * 0.5) * val / world
+        else:
+            flops = cfg.flops_per_token(S) * val / world
         out = {
             "metric": ("tokens/sec (whole job, device-timed, max over ranks) Llama-3-8B ZeRO-3 bf16 training"
                        if (args.model == "llama3-8b" and args.zero_stage == 3) else

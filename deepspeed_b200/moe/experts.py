@@ -46,6 +46,13 @@ class GroupedSwiGLUExperts(nn.Module):
             p.group_name = expert_group_name
 
     def forward(self, inputs):
+        """``inputs``: [E_local, tokens, hidden] (capacity-padded dispatch buffer) -> same shape."""
+        if inputs.is_cuda and inputs.dtype == torch.bfloat16 and self.act == "silu" and inputs.shape[1] >= 256:
+            # tcgen05 path: per expert the fused gate|up GEMM (+) SwiGLU, down GEMM, and in backward the dSwiGLU-fused
+            # input-gradient GEMM plus weight-gradient GEMMs written straight into the stacked parameters' flat ZeRO
+            # gradient views (one launch per expert and projection: every problem is [tokens x 14336 x 4096]-sized)
+            from deepspeed_b200.ops.linear import grouped_swiglu_mlp
+            return grouped_swiglu_mlp(inputs, self.w13, self.w2)
         from deepspeed_b200.ops.kernels.transformer_ops import gated_act
         gu = torch.bmm(inputs, self.w13.transpose(1, 2))
         h = gated_act(gu, self.act)

@@ -27,6 +27,7 @@ class CudaKernelsBuilder(CUDAOpBuilder):
         "cuda/symm_coll.cu",
         "cuda/gemm_sm100.cu",
         "cuda/attention.cu",
+        "cuda/attn_sm100.cu",
         "cuda/moe_symm.cu",
         "cuda/wq_gemm.cu",
         "cuda/symm_mem.cpp",

@@ -141,6 +141,73 @@ def swiglu_mlp(x, w_gate_up, w_down):
     return _SwiGLUMLPFn.apply(x, w_gate_up, w_down)
 
 
+class _GroupedSwiGLUFn(torch.autograd.Function):
+    """Stacked SwiGLU experts on a capacity-padded dispatch buffer ``x [E, C, H]`` with ``w13 [E, 2I, H]``, ``w2 [E, H, I]``
+    (the MoE training path, reference ``moe/experts.py:13`` + ``sharded_moe.py:586``): per expert the same three fused GEMM
+    launches per direction as :class:`_SwiGLUMLPFn`; the per-expert weight gradients (K = that expert's token rows) land
+    in the expert's slice of the stacked parameter's flat ZeRO gradient view."""
+
+    @staticmethod
+    def forward(ctx, x, w13, w2):
+        from deepspeed_b200.ops import gemm
+        E, C, H = x.shape
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty(E, C, w2.shape[1], dtype=x.dtype, device=x.device)
+        gus, acts = [], []
+        for e in range(E):
+            act, gu = gemm.gate_up_swiglu(x[e], w13[e], save_gate_up=need_grad)
+            gemm.matmul_nt(act, w2[e], out=y[e])
+            gus.append(gu)
+            acts.append(act)
+        ctx.w13, ctx.w2 = w13, w2
+        ctx.saved = (x, gus, acts) if need_grad else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from deepspeed_b200.ops import gemm
+        x, gus, acts = ctx.saved
+        ctx.saved = None
+        w13, w2 = ctx.w13, ctx.w2
+        E = x.shape[0]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        views = {}
+        for w, need in ((w13, ctx.needs_input_grad[1]), (w2, ctx.needs_input_grad[2])):
+            if not need:
+                views[id(w)] = (None, None, False)
+                continue
+            zo = _zo_of(w)
+            if zo is not None and zo.grad_view_for(w).dtype == dy.dtype:
+                views[id(w)] = (zo, zo.grad_view_for(w), not zo.grad_is_fresh(w))
+            else:
+                views[id(w)] = (None, torch.empty_like(w), False)
+        for e in range(E):
+            dgu = gemm.down_dx_dswiglu(dy[e], w2[e], gus[e])
+            _, g2, acc2 = views[id(w2)]
+            if g2 is not None:
+                gemm.matmul_tn(dy[e], acts[e], out=g2[e], accumulate=acc2)
+            if dx is not None:
+                gemm.matmul_nn(dgu, w13[e], out=dx[e])
+            _, g13, acc13 = views[id(w13)]
+            if g13 is not None:
+                gemm.matmul_tn(dgu, x[e], out=g13[e], accumulate=acc13)
+            gus[e] = acts[e] = None
+        outs = []
+        for w in (w13, w2):
+            zo, g, _ = views[id(w)]
+            if zo is not None:
+                zo.mark_grad_ready(w)
+                outs.append(None)
+            else:
+                outs.append(g)
+        return dx, outs[0], outs[1]
+
+
+def grouped_swiglu_mlp(x, w13, w2):
+    return _GroupedSwiGLUFn.apply(x, w13, w2)
+
+
 class _ChunkedLinearXent(torch.autograd.Function):
 
     @staticmethod

@@ -263,6 +263,11 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
                 self.optimizer.mics_groups = mg  # two-hop parameter gathers when the shard group spans nodes
                 self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
                 return
+            oo = c.zero_config.offload_optimizer
+            ratio = float(getattr(oo, "ratio", 1.0)) if oo is not None else 1.0
+            if oo is not None and str(getattr(oo.device, "value", oo.device)) == "cpu" and 0.0 < ratio < 1.0 and stage == 3:
+                self.optimizer = self._build_twin_flow(stage, common, ratio)
+                return
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
             self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
             return
@@ -280,6 +285,35 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
                                               getattr(p, "allreduce", True) is False, **common))
             ep_groups.append(groups._get_expert_parallel_group(en))
         self.optimizer = ZeroOptimizerGroup(parts, ep_groups)
+
+    def _build_twin_flow(self, stage, common, ratio):
+        """ZeRO-Offload++ "Twin-Flow" (``offload_optimizer.ratio`` < 1, reference ``stage3.py:854-856``): the optimizer
+        state of the first ``ratio`` of the parameters lives on the host and is stepped by the CPU optimizer, the rest
+        stays in HBM and is stepped by the fused GPU kernel.  Two sharded-state domains behind one optimizer facade: the
+        GPU domain keeps every fast path (fused reduce-scatter + Adam inside backward), the host domain streams its
+        gradients out / parameters in on side streams meanwhile."""
+        import copy as _copy
+        from deepspeed_b200.runtime.zero.multi import ZeroOptimizerGroup
+        params = [p for p in self.module.parameters()]
+        total = sum(int(getattr(p, "ds_numel", p.numel())) for p in params)
+        host_ids, acc = set(), 0
+        for p in params:
+            if acc >= ratio * total:
+                break
+            host_ids.add(id(p))
+            acc += int(getattr(p, "ds_numel", p.numel()))
+        zc_gpu = _copy.deepcopy(common["zero_config"])
+        zc_gpu.__dict__["offload_optimizer"] = None
+        host = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, name="twinflow:host",
+                                    param_filter=lambda p: id(p) in host_ids, **common)
+        gpu_common = dict(common, zero_config=zc_gpu)
+        dev = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, name="twinflow:device",
+                                   param_filter=lambda p: id(p) not in host_ids, **gpu_common)
+        for part in (host, dev):
+            part.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
+        log_dist(f"Twin-Flow offload: {acc / max(total, 1):.1%} of {total:,} parameters stepped on the host, the rest on "
+                 f"the device", ranks=[0])
+        return ZeroOptimizerGroup([host, dev], [None, None])
 
     def _configure_zero_inference(self):
         self.optimizer = ZeroShardedOptimizer(self.module, 3, optimizer_name="sgd", optimizer_params={"lr": 0.0},

@@ -219,6 +219,15 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self.ag_stream = torch.cuda.Stream() if overlap else None
         self.rs_stream = torch.cuda.Stream() if overlap else None
         self.prefetch_depth = max(0, int(self.zc.b200_unit_prefetch))
+        # host-offload tier: reduced gradient shards leave the GPU on ``d2h_stream`` (pinned cudaMemcpyAsync, nothing on
+        # the compute stream waits for them) and updated parameters come back on ``h2d_stream`` while the CPU optimizer is
+        # already working on the next unit (reference stage3.py:1466-1527 async D2H of reduced shards,
+        # swap_tensor/pipelined_optimizer_swapper.py:52)
+        off_cuda = self.offload_optimizer and self.on_cuda
+        self.d2h_stream = torch.cuda.Stream() if off_cuda else None
+        self.h2d_stream = torch.cuda.Stream() if off_cuda else None
+        self._d2h_slots, self._d2h_i, self._d2h_adds, self._grad_stage = None, 0, [], None
+        self._h2d_slots, self._h2d_i = None, 0
 
         # ---- fusion policy ------------------------------------------------------------------------
         self._fib_request = self.zc.b200_fused_optimizer_in_backward
@@ -924,12 +933,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             return
         first = self._first_micro(rt)
         dst = self.grad_arena[a:b]
-        if dst.device != shard_g.device:  # optimizer offload: D2H through the pinned arena
-            if first:
-                tmp = shard_g.float().mul_(scale)
-                dst.copy_(tmp, non_blocking=True)
-            else:
-                dst.add_(shard_g.float().mul_(scale).cpu())
+        if dst.device != shard_g.device:  # optimizer offload: asynchronous D2H into the pinned arena
+            self._offload_grad(a, b, shard_g, scale, first)
             return
         flat_ops.scale_cast(shard_g, dst, scale=scale, accumulate=not first)
 
@@ -959,6 +964,63 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                                f"(max rel err {err:.3e})")
         self.verify_report["reduce_scatter"] += 1
         self.verify_report["max_rel_err"] = max(self.verify_report["max_rel_err"], err)
+
+    # ---- host-offload pipeline -------------------------------------------------------------------------------------------
+    def _offload_grad(self, a, b, shard_g, scale, first):
+        """Scale the reduced shard to fp32 on the device and copy it to the pinned host gradient arena on ``d2h_stream``.
+        Later micro steps land in a pinned staging arena and are added on the host in :meth:`end_backward` (the copy
+        engine cannot accumulate); nothing here blocks the host or the compute stream."""
+        n = b - a
+        if self.d2h_stream is None:  # no CUDA: plain host path
+            t = shard_g.float().mul_(scale).cpu()
+            self.grad_arena[a:b].copy_(t) if first else self.grad_arena[a:b].add_(t)
+            return
+        if self._d2h_slots is None:
+            cap = max(u.shard_numel for u in self.units)
+            self._d2h_slots = [_Slot(torch.empty(cap, dtype=torch.float32, device=self.device)) for _ in range(2)]
+        slot = self._d2h_slots[self._d2h_i % 2]
+        self._d2h_i += 1
+        cur = torch.cuda.current_stream()
+        if slot.free_event is not None:
+            cur.wait_event(slot.free_event)  # the copy that last read this staging buffer has finished
+        tmp = slot.buf[:n]
+        flat_ops.scale_cast(shard_g, tmp, scale=scale)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.d2h_stream.wait_event(ev)
+        if first:
+            host = self.grad_arena[a:b]
+        else:
+            if self._grad_stage is None:
+                self._grad_stage = self._empty(self.arena_numel, torch.float32, "cpu", pin=True)
+            host = self._grad_stage[a:b]
+            self._d2h_adds.append((a, b))
+        with torch.cuda.stream(self.d2h_stream):
+            host.copy_(tmp, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        slot.free_event = done
+
+    def _drain_offloaded_grads(self):
+        """Host-side join of the gradient D2H copies + the accumulation of later micro steps."""
+        if self.d2h_stream is None:
+            return
+        self.d2h_stream.synchronize()
+        for (a, b) in self._d2h_adds:
+            self.grad_arena[a:b].add_(self._grad_stage[a:b])
+        self._d2h_adds.clear()
+
+    def _lp_upload_slot(self, n):
+        """Pinned low-precision staging for one piece of updated parameters (two rotate so the CPU optimizer of piece
+        k+1 overlaps the H2D copy of piece k)."""
+        if self._h2d_slots is None:
+            cap = max(u.shard_numel for u in self.units)
+            self._h2d_slots = [_Slot(self._empty(cap, self.model_dtype, "cpu", pin=True)) for _ in range(2)]
+        slot = self._h2d_slots[self._h2d_i % 2]
+        self._h2d_i += 1
+        if slot.free_event is not None:
+            slot.free_event.synchronize()
+        return slot
 
     def _symm_reduce(self, rt: _UnitRT, full_g, scale):
         """In-kernel reduce-scatter over NVLink peer memory, fused with scale + (Adam | accumulate).
@@ -993,6 +1055,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                         rt.grad_full[sl.offset:sl.offset + sl.numel].zero_()
                 rt.pending = 0
                 self._reduce_unit(rt)
+        if self.offload_optimizer:
+            self._drain_offloaded_grads()
         if self.grad_arena is not None and self._accum == 0:
             # units that produced no gradient at all this micro step must not keep stale values
             for rt in self.rts:
@@ -1023,6 +1087,10 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 assert_ints_same_as_other_ranks(order, self.dp_group)
         self.micro_step += 1
         self._accum += 1
+        if self._accum % self.gas != 0 and self._forced_boundary is None:
+            # more micro batches follow before the step: parameters are unchanged, so the first units of the next forward
+            # can be gathered right away (with GAS > 1 every micro step would otherwise start with a cold all-gather)
+            self._prefetch_next_forward()
 
     # =========================================================================================
     # backward / step API (reference-compatible)
@@ -1135,14 +1203,31 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             else:  # NVMe tier: never touch more than one swap window of state at a time
                 for c in range(s1, e1, win):
                     work.append((rt, gi, c, min(c + win, e1)))
+        upload = self.offload_optimizer and self.h2d_stream is not None and self.master is not None \
+            and not self.offload_param
         for i, (rt, gi, s1, e1) in enumerate(work):
             if self.state_swapper is not None and i + 1 < len(work):
                 self.state_swapper.prefetch(self.flat_opt, work[i + 1][2], work[i + 1][3])
             p = self._piece_master(rt, s1, e1)
             g = grad[s1 - grad_offset:e1 - grad_offset]
             out = self._piece_lp(rt, s1, e1) if write_lp else None
+            slot = None
+            if upload:
+                # the CPU optimizer writes the low-precision copy of this piece into pinned staging in the same pass;
+                # its H2D copy then overlaps the CPU work on the next piece
+                slot = self._lp_upload_slot(e1 - s1)
+                out = slot.buf[:e1 - s1]
             self.flat_opt.step_segment(s1, e1, p, g, out, self.param_groups[gi], self._peek_step(gi),
                                        grad_scale=grad_scale, d_gscale=d_gscale, d_skip=d_skip)
+            if slot is not None:
+                with torch.cuda.stream(self.h2d_stream):
+                    self._piece_lp(rt, s1, e1).copy_(out, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                slot.free_event = ev
+        if upload:
+            torch.cuda.current_stream().wait_stream(self.h2d_stream)
+            self._uploaded_lp = True
         if self.state_swapper is not None:
             self.state_swapper.flush(self.flat_opt)
 
@@ -1212,8 +1297,16 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         elif getattr(self.flat_opt, "per_tensor", False):
             self._step_per_tensor(gscale, d_gscale, d_skip)
         else:
-            self._step_range(0, self.arena_numel, self.grad_arena, 0, gscale, d_gscale, d_skip)
-            if self.offload_optimizer:
+            if self.offload_optimizer and d_skip is not None and int(d_skip.item()):
+                # inf / nan gradients (the statistics live on the host for the offload tier): nothing is updated
+                self.overflow = True
+                self.skipped_steps += 1
+                self._post_step(skipped=True)
+                return
+            self._uploaded_lp = False
+            self._step_range(0, self.arena_numel, self.grad_arena, 0, gscale, d_gscale, None if self.offload_optimizer
+                             else d_skip)
+            if self.offload_optimizer and not self._uploaded_lp:
                 self._master_to_lp(0, self.arena_numel)
         for gi in range(len(self.group_steps)):
             self.group_steps[gi] += 1

@@ -216,3 +216,23 @@ def test_swiglu_mlp_matches_autograd(backend):
             assert (got.float() - ref.float()).abs().max().item() < 3e-2 * s + 1e-2
     finally:
         gemm.set_backend(prev)
+
+
+def test_grouped_swiglu_experts_match_bmm_reference():
+    """MoE training experts: tcgen05 per-expert fused path vs the batched-GEMM autograd reference."""
+    from deepspeed_b200.moe.experts import GroupedSwiGLUExperts
+    torch.manual_seed(0)
+    E, C, H, I = 2, 512, 256, 384
+    ex = GroupedSwiGLUExperts(E, H, I).cuda().bfloat16()
+    x = (torch.randn(E, C, H, device="cuda") * 0.5).bfloat16().requires_grad_(True)
+    y = ex(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    xr = x.detach().float().requires_grad_(True)
+    w13, w2 = ex.w13.detach().float().requires_grad_(True), ex.w2.detach().float().requires_grad_(True)
+    gu = torch.bmm(xr, w13.transpose(1, 2))
+    yr = torch.bmm(torch.nn.functional.silu(gu[..., :I]) * gu[..., I:], w2.transpose(1, 2))
+    yr.backward(gy.float())
+    for got, ref in ((y, yr), (x.grad, xr.grad), (ex.w13.grad, w13.grad), (ex.w2.grad, w2.grad)):
+        s = ref.abs().max().item()
+        assert (got.float() - ref).abs().max().item() < 3e-2 * s + 1e-2

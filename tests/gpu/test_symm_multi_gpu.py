@@ -167,8 +167,12 @@ def _rs_adam_kernel():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         pulled = n * (w - 1) * 2 / 1e9  # bytes that must cross NVLink into this rank
         hbm = n * (2 + 6 * 4 + 2) / 1e9 + n * w * 0  # local: grad shard read + m/v/master r+w + lp write
-        out[name] = {"ms": t.item(), "nvlink_GBps_in": pulled / t.item() * 1e3,
-                     "frac_of_770GBps_peer_copy": pulled / t.item() * 1e3 / 770.0, "local_hbm_GB": hbm}
+        # roofline = the slower of (bytes over NVLink at the measured 770 GB/s peer-copy rate) and (local optimizer-state
+        # traffic at the measured 6.56 TB/s copy bandwidth): small worlds are HBM-bound, 8 ranks are link-bound
+        t_link, t_hbm = pulled / 770.0 * 1e3, hbm / 6555.8 * 1e3
+        out[name] = {"ms": t.item(), "nvlink_GBps_in": pulled / t.item() * 1e3, "local_hbm_GB": hbm,
+                     "roofline_ms": max(t_link, t_hbm), "bound": "nvlink" if t_link > t_hbm else "hbm",
+                     "frac_of_roofline": max(t_link, t_hbm) / t.item()}
     if r == 0:
         rec = {"kernel": "reduce_scatter_adam (NVLS multimem.ld_reduce + AdamW)", "world": w, "shard_elems": n,
                "ctas": {"overlap": ctx.ctas, "tail": max(ctx.ctas, ctx.tail_ctas)}, **out}

@@ -194,3 +194,38 @@ def _stage0_files_worker(d):
 
 def test_stage0_writes_one_optimizer_shard(tmp_path):
     run_distributed(_stage0_files_worker, 2, (str(tmp_path), ))
+
+
+def _twin_flow_worker():
+    """offload_optimizer.ratio < 1: host + device optimizer domains must track a plain AdamW run (incl. clipping)."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.runtime.zero.multi import ZeroOptimizerGroup
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    torch.manual_seed(0)
+    model = SimpleModel()
+    ref = copy.deepcopy(model)
+    cfg = base_config(3, clip=1.0)
+    cfg["zero_optimization"]["offload_optimizer"] = {"device": "cpu", "ratio": 0.5}
+    eng, opt, *_ = ds.initialize(model=model, config=cfg)
+    assert isinstance(opt, ZeroOptimizerGroup) and [p.name for p in opt.parts] == ["twinflow:host", "twinflow:device"]
+    assert opt.parts[0].offload_optimizer and not opt.parts[1].offload_optimizer
+    n0 = sum(s.numel for u in opt.parts[0].units for s in u.slots)
+    n1 = sum(s.numel for u in opt.parts[1].units for s in u.slots)
+    assert 0.3 < n0 / (n0 + n1) < 0.8, (n0, n1)
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.01)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(4):
+        x, y = make_batch(w, 4, g)
+        eng.backward(eng(x[r * 4:(r + 1) * 4], y[r * 4:(r + 1) * 4]))
+        eng.step()
+        ref(x, y).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        ropt.step()
+        ropt.zero_grad()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach(), atol=1e-5, rtol=1e-4)
+
+
+def test_twin_flow_partial_offload_matches_adamw():
+    run_distributed(_twin_flow_worker, 2)
