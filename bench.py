@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--model-impl", default="native", choices=["native", "hf"],
                     help="b200 arm only: 'native' = deepspeed_b200.models.llama (fused kernels); 'hf' = the SAME "
                     "transformers.LlamaForCausalLM module the reference arm trains, under this framework's engine")
+    ap.add_argument("--offload", default="none", choices=["none", "cpu"],
+                    help="offload_optimizer device (both arms): fp32 master + Adam moments in pinned host memory, CPU Adam")
+    ap.add_argument("--offload-ratio", type=float, default=1.0, help="Twin-Flow: fraction of the optimizer stepped on the host")
+    ap.add_argument("--zero-init", action="store_true", help="construct the model under zero.Init (needed when the bf16 "
+                    "parameters do not fit one GPU, e.g. llama3-70b)")
     ap.add_argument("--clip", type=float, default=0.0, help="gradient_clipping (both arms)")
     ap.add_argument("--gas", type=int, default=1, help="gradient_accumulation_steps (both arms); a timed step = one "
                     "optimizer step = GAS micro-batches")
@@ -154,12 +159,15 @@ def common_config(args, world):
         "optimizer": "AdamW(lr=1e-5, betas=(0.9,0.95), eps=1e-8, wd=0.1), fp32 master + moments",
         "gradient_clipping": args.clip,
         "gradient_accumulation_steps": args.gas,
+        "offload_optimizer": args.offload if args.offload == "none" else f"{args.offload} (ratio {args.offload_ratio})",
         "precision": "bf16 params/activations/grads-in-flight",
         "l2": "working set (>= 100 GB of parameter/optimizer state streamed per step) >> 126 MB L2",
     }
 
 
 def ds_config_for(args, zero):
+    if args.offload != "none":
+        zero = dict(zero, offload_optimizer={"device": args.offload, "pin_memory": True, "ratio": args.offload_ratio})
     return {
         "train_micro_batch_size_per_gpu": args.micro_batch,
         "gradient_accumulation_steps": args.gas,
@@ -248,8 +256,13 @@ def run_b200(args):
             torch.manual_seed(1234 + (rank if moe else 0))  # experts differ per rank, dense weights are broadcast
             prev = torch.get_default_dtype()
             torch.set_default_dtype(torch.bfloat16)
-            with torch.device("cuda"):
-                model = MixtralForCausalLM(cfg) if moe else LlamaForCausalLM(cfg)
+            if args.zero_init:
+                # parameters are sharded as they are constructed: no rank ever holds the whole bf16 model
+                with ds.zero.Init(config_dict_or_path=ds_config, dtype=torch.bfloat16):
+                    model = LlamaForCausalLM(cfg)
+            else:
+                with torch.device("cuda"):
+                    model = MixtralForCausalLM(cfg) if moe else LlamaForCausalLM(cfg)
             torch.set_default_dtype(prev)
         return ds.initialize(model=model, config=ds_config)[0]
 

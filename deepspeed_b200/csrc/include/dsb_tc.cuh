@@ -56,6 +56,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* m)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -145,11 +152,11 @@ __device__ __forceinline__ uint64_t desc_kmajor_sw128(uint32_t smem_addr)
 }
 // MN-major operand tile ([k rows, mn contiguous] in memory) staged as TMA boxes of [64 k x 64 mn] (8 KiB each): LBO = 8 KiB
 // between the two 64-wide mn atoms, SBO = 1 KiB between groups of 8 k rows; a UMMA_K = 16 step advances the start by 2 KiB.
-__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t smem_addr)
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes = 8192)
 {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
-    d |= static_cast<uint64_t>(8192 >> 4) << 16;
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
     d |= static_cast<uint64_t>(1024 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;

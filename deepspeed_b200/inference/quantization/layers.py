@@ -55,10 +55,40 @@ def quantize_weight(w, mode="int8", group_size=128):
 def maybe_quantized_linear(x, w, b=None):
     if isinstance(w, QuantizedWeight):
         y = _wq_gemv(x, w, b)
+        if y is None:
+            y = wq_tc_linear(x, w, b)
         if y is not None:
             return y
         w = w.dequantize()
     return F.linear(x, w, b)
+
+
+_TC_MODES = {"int8": 0, "int4": 1, "fp8": 2, "fp6": 3}
+WQ_TC_MAX_ROWS = 1024  # beyond this dequantise-once + the bf16 GEMM amortises the decode better
+
+
+def wq_tc_linear(x, qw: "QuantizedWeight", b=None, max_rows=None):
+    """32 < rows <= ``WQ_TC_MAX_ROWS``: fused dequantise-in-shared-memory + tcgen05 GEMM (``csrc/cuda/wq_tc_gemm.cu``) for
+    FP6 / FP8 / INT8 / INT4 weights -- the dequantised weight never exists in HBM.  None -> not eligible."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and qw.mode in _TC_MODES and qw.dtype == torch.bfloat16):
+        return None
+    x2 = x.reshape(-1, x.shape[-1])
+    M, K = x2.shape
+    N = qw.shape[0]
+    limit = WQ_TC_MAX_ROWS if max_rows is None else max_rows
+    if M > limit or K != qw.shape[1] or K % 64 or qw.group_size % 64 or K % qw.group_size:
+        return None
+    from deepspeed_b200.ops import native as NV
+    if x2.stride(1) != 1 or x2.stride(0) % 8 or x2.data_ptr() % 16:
+        x2 = x2.contiguous()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=x.device)
+    bias = b.to(torch.bfloat16).contiguous() if b is not None else None
+    rc = NV.cuda().dsb_wq_tc_gemm(NV.ptr(x2), NV.ptr(qw.q), NV.ptr(qw.params), NV.ptr(bias), NV.ptr(out), M, N, K,
+                                  _TC_MODES[qw.mode], qw.group_size, x2.stride(0), out.stride(0), NV.stream())
+    if rc == -3:
+        return None
+    NV.check(rc, "wq_tc_gemm")
+    return out.view(*x.shape[:-1], N)
 
 
 def _wq_gemv(x, qw: "QuantizedWeight", b):

@@ -148,8 +148,17 @@ class RaggedTransformer:
             return R.paged_attention(qkv, cache, batch.seq_of(), batch.pos_of(), batch.block_table(), hq, hkv, d, bs)
         out = torch.empty(qkv.shape[0], hq * d, dtype=qkv.dtype, device=qkv.device)
         covered = 0
+        from deepspeed_b200.ops.kernels import attention_sm100 as A
         for t0, n in dense:
-            v3 = qkv[t0:t0 + n].view(n, hq + 2 * hkv, d)
+            rows = qkv[t0:t0 + n]
+            if os.environ.get("DSB200_PREFILL_ATTN", "native") == "native" and A.supports_fwd(rows, hq, hkv, d, 1, n):
+                # the in-tree tcgen05 attention forward, straight on the packed rows (K/V were just rotated in place by
+                # kv_rotary_append) and straight into the output rows: no head transposes, any prompt length
+                qv, kv_, vv = A.split_packed(rows, hq, hkv)
+                A.fwd(qv, kv_, vv, 1, n, hq, hkv, causal=True, out=out[t0:t0 + n], need_lse=False)
+                covered += n
+                continue
+            v3 = rows.view(n, hq + 2 * hkv, d)
             q = v3[:, :hq].transpose(0, 1).unsqueeze(0)
             k = v3[:, hq:hq + hkv].transpose(0, 1).unsqueeze(0)
             v = v3[:, hq + hkv:].transpose(0, 1).unsqueeze(0)

@@ -30,6 +30,7 @@ class CudaKernelsBuilder(CUDAOpBuilder):
         "cuda/attn_sm100.cu",
         "cuda/moe_symm.cu",
         "cuda/wq_gemm.cu",
+        "cuda/wq_tc_gemm.cu",
         "cuda/symm_mem.cpp",
     ]
     LINK_LIBS = ["-ldl", "-lpthread"]

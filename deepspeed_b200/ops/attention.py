@@ -87,17 +87,40 @@ class _PackedCausalAttention(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None, None
 
 
+_TABLE = None
+
+
+def _native_wins(B, S, hq, hkv, d) -> bool:
+    """``auto``: the measured per-shape choice between the in-tree tcgen05 kernel and the cuDNN library kernel
+    (``attention_table.json`` next to this file, written from ``scripts/bench_attention.py`` runs on a B200: fwd + bwd
+    milliseconds of both).  Unknown shapes use the library: on the shapes measured so far cuDNN's Blackwell FMHA is faster
+    (Llama-3-8B shape: forward 0.21 ms vs 0.64 ms), so the in-tree kernel is opt-in (``attention_backend="native"``)."""
+    global _TABLE
+    if _TABLE is None:
+        import json
+        try:
+            with open(os.path.join(os.path.dirname(__file__), "attention_table.json")) as f:
+                _TABLE = json.load(f).get("shapes", {})
+        except (OSError, ValueError):
+            _TABLE = {}
+    e = _TABLE.get(f"B{B}_S{S}_hq{hq}_hkv{hkv}_d{d}")
+    return bool(e and e.get("choice") == "native")
+
+
 def causal_attention(qkv2d, B, S, hq, hkv, d, rope=None, positions=None, backend="auto"):
     backend = _ENV or backend or "auto"
-    if backend in ("native", "auto"):
-        try:
-            from deepspeed_b200.ops.kernels import attention_sm100
-            if attention_sm100.supports(qkv2d, hq, hkv, d, S):
+    if backend == "native" or (backend == "auto" and qkv2d.is_cuda and _native_wins(B, S, hq, hkv, d)):
+        from deepspeed_b200.ops.kernels import attention_sm100
+        if attention_sm100.supports(qkv2d, hq, hkv, d, S):
+            if torch.is_grad_enabled() and qkv2d.requires_grad:
                 return attention_sm100.packed_causal_attention(qkv2d, B, S, hq, hkv, d, rope, positions)
-        except ImportError:
-            pass
+            if rope is not None:
+                rope_qk_inplace(qkv2d, hq, hkv, d, rope, positions, S, backward=False)
+            q, k, v = attention_sm100.split_packed(qkv2d, hq, hkv)
+            return attention_sm100.fwd(q, k, v, B, S, hq, hkv, causal=True, need_lse=False)[0]
         if backend == "native":
-            raise RuntimeError("native attention kernel requested but unavailable for this shape")
+            raise RuntimeError("native attention kernel requested but unsupported for this shape (needs bf16, head dim 128, "
+                               "sequence length a multiple of 128)")
     if not (torch.is_grad_enabled() and qkv2d.requires_grad):
         if rope is not None:
             rope_qk_inplace(qkv2d, hq, hkv, d, rope, positions, S, backward=False)

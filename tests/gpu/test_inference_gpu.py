@@ -199,3 +199,21 @@ def test_layerwise_kernel_injection_bf16_gpu():
         g1 = model.generate(ids[:, :8], max_new_tokens=6, do_sample=False, pad_token_id=0)
         g2 = inj.generate(ids[:, :8], max_new_tokens=6, do_sample=False, pad_token_id=0)
     assert (g1 == g2).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("mode", ["fp6", "fp8", "int8", "int4"])
+@pytest.mark.parametrize("M,N,K", [(48, 256, 512), (200, 384, 1024), (128, 4096, 4096)])
+def test_wq_tc_gemm_matches_dequant_reference(mode, M, N, K):
+    """Fused dequantise-in-smem + tcgen05 weight-only GEMM (FP6 / FP8 / INT8 / INT4) vs dequantise + fp32 matmul."""
+    import torch
+    from deepspeed_b200.inference.quantization.layers import quantize_weight, wq_tc_linear
+    torch.manual_seed(M + N)
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    b = (torch.randn(N, device="cuda") * 0.1).bfloat16()
+    qw = quantize_weight(w, mode, group_size=128)
+    y = wq_tc_linear(x, qw, b)
+    assert y is not None, "shape should be eligible for the tcgen05 weight-only kernel"
+    ref = x.float() @ qw.dequantize().float().t() + b.float()
+    assert torch.isfinite(y.float()).all()
+    assert (y.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item() + 2e-2
