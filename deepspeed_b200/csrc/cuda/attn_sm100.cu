@@ -22,7 +22,11 @@ namespace attn {
 using namespace dsb::tc;
 
 constexpr int BQ = 128, BKV = 128, D = 128;
-constexpr int kThreads = 192;                           // warp 0 TMA, warp 1 MMA, warps 2-5 softmax (one row per thread)
+// warp 0 TMA, warp 1 MMA, warps 2-9: TWO consumer warps per TMEM lane quarter (each owns half of the columns of "its" 32
+// rows).  TMEM reads run at ~64 B/clk/SM: with one warp per scheduler the tcgen05.ld wait is dead time; with two, one warp's
+// exp/convert work hides the other's accumulator reads.
+constexpr int kThreads = 320;
+constexpr int kConsumers = 8;
 constexpr uint32_t TILE = BQ * D * 2;                   // 32 KiB: a [128 x 128] bf16 tile = 2 sub-tiles of [128 x 64]
 constexpr uint32_t HALF = TILE / 2;                     // 16 KiB sub-tile (one 128-byte swizzle span of 64 bf16 per row)
 constexpr uint32_t TM_COLS = 512;
@@ -31,10 +35,12 @@ constexpr uint32_t SM_Q = 0;
 constexpr uint32_t SM_K = SM_Q + TILE;                  // 2 stages
 constexpr uint32_t SM_V = SM_K + 2 * TILE;              // 2 stages
 constexpr uint32_t SM_P = SM_V + 2 * TILE;
-constexpr uint32_t SM_BAR = SM_P + TILE;
+constexpr uint32_t SM_X = SM_P + TILE;                  // row-statistics exchange between the two warps of a row: [3][2][128] f32
+constexpr uint32_t SM_BAR = SM_X + 3 * 2 * BQ * 4;       // (two rotating slots for the block maxima + one for the final sums)
 constexpr uint32_t SM_TOTAL = SM_BAR + 256 + 1024;
 constexpr uint32_t TM_S = 0, TM_O = 256;                // S0 [0,128) S1 [128,256) O [256,384)
 }  // namespace kf
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct FwdParams {
     __nv_bfloat16* o;   // [B*S, ld_o], head h at columns [h*D, (h+1)*D)
@@ -85,9 +91,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             mbar_init(k_empty(s), 1);
             mbar_init(v_empty(s), 1);
             mbar_init(s_full(s), 1);
-            mbar_init(s_empty(s), 4);  // one arrival per softmax warp
+            mbar_init(s_empty(s), kConsumers);  // one arrival per softmax warp
         }
-        mbar_init(p_full, 4);
+        mbar_init(p_full, kConsumers);
         mbar_init(p_empty, 1);
         fence_barrier_init();
     }
@@ -165,58 +171,63 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     } else {
         // ================================ softmax / correction / epilogue ================================
         const int q4 = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = (warp - 2) >> 2;        // which 64 of the block's 128 columns (and of O's 128) this warp owns
         const int r = q4 * 32 + lane;            // query row inside the block
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;    // running maximum (log2 domain, scaled) and denominator
-        uint8_t* prow = smem + SM_P + r * 128;
+        float m_run = -INFINITY, l_run = 0.f;    // running maximum (log2 domain, scaled); l_run: this warp's half of the sum
+        uint8_t* prow = smem + SM_P + half * HALF + r * 128;
+        float* xch = reinterpret_cast<float*>(smem + SM_X);
         for (int j = 0; j < n_kv; ++j) {
             const int bs = j & 1;
             mbar_wait(s_full(bs), (j >> 1) & 1);
             tc_fence_after();
-            const uint32_t ts = tmem + lane_addr + TM_S + bs * BKV;
+            const uint32_t ts = tmem + lane_addr + TM_S + bs * BKV + half * 64;
             // masking is needed on the causal diagonal block and on a ragged last key block (keys >= S are padding / the
             // next sequence's rows); a key is visible iff key < S and (not causal or key <= query)
             const bool diag = (p.causal && j == qb) || ((j + 1) * BKV > p.S);
             const int row_g = qb * BQ + r;
-            const int lim = min(p.causal ? row_g : p.S - 1, p.S - 1) - j * BKV;  // last visible column of this block
-            // ---- the whole S row moves TMEM -> registers ONCE (TMEM reads are ~64 B/clk/SM: a second pass over the tile
-            // would cost as much as both MMAs of the block); the S buffer is handed back to the MMA warp right away ---------
-            uint32_t v[BKV];
-#pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32(ts + c * 32, v + c * 32);
+            const int lim = min(p.causal ? row_g : p.S - 1, p.S - 1) - j * BKV - half * 64;  // last visible own column
+            // ---- this warp's 64 columns of the S row move TMEM -> registers once; the buffer goes back to the MMA warp ------
+            uint32_t v[64];
+            tmem_ld_32x32(ts, v);
+            tmem_ld_32x32(ts + 32, v + 32);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty(bs));
             float mx = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < BKV; ++e)
+            for (int e = 0; e < 64; ++e)
                 if (!diag || e <= lim) mx = fmaxf(mx, __uint_as_float(v[e]));
+            // the row maximum needs the partner warp's half
+            xch[(bs * 2 + half) * BQ + r] = mx;
+            consumer_sync();
+            mx = fmaxf(mx, xch[(bs * 2 + (half ^ 1)) * BQ + r]);
             const float m_new = fmaxf(m_run, mx * p.scale_log2);
             const float alpha = ex2(m_run - m_new);  // 0 on the first block (m_run = -inf)
-            // ---- O correction: only after P_{j-1} V_{j-1} has landed, and only if some row of this warp moved ----------
+            // ---- O correction (own 64 columns): after P_{j-1} V_{j-1} has landed, only if some row of this warp moved -------
             if (j > 0) {
                 mbar_wait(p_empty, (j - 1) & 1);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, m_new > m_run)) {
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         uint32_t o[32];
-                        tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, o);
+                        tmem_ld_32x32(tmem + lane_addr + TM_O + half * 64 + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-                        tmem_st_32x32(tmem + lane_addr + TM_O + c * 32, o);
+                        tmem_st_32x32(tmem + lane_addr + TM_O + half * 64 + c * 32, o);
                     }
                     tmem_st_wait();
                 }
             }
             l_run *= alpha;
             m_run = m_new;
-            // ---- P = 2^(s * scale - m), row sum, bf16 -> swizzled K-major smem tile ----------------------------------------
+            // ---- P = 2^(s * scale - m), row sum, bf16 -> this warp's sub-tile of the swizzled K-major P tile ------------------
             float sum = 0.f;
 #pragma unroll
-            for (int chunk = 0; chunk < BKV / 8; ++chunk) {  // 16 x 16-byte chunks of 8 keys
+            for (int chunk = 0; chunk < 8; ++chunk) {  // 8 x 16-byte chunks of 8 keys
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -226,8 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     sum += pe;
                     f[e] = pe;
                 }
-                *reinterpret_cast<Vec16*>(prow + (chunk >> 3) * HALF + (((chunk & 7) ^ (r & 7)) << 4)) =
-                    Elem<__nv_bfloat16>::pack(f);
+                *reinterpret_cast<Vec16*>(prow + ((chunk ^ (r & 7)) << 4)) = Elem<__nv_bfloat16>::pack(f);
             }
             l_run += sum;
             // P (and the corrected O) ready for the second MMA
@@ -236,16 +246,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
         }
-        // ---- epilogue: O / l -> bf16 -> global, LSE ----------------------------------------------------------------------
+        // ---- epilogue: O / l -> bf16 -> global (own 64 columns), LSE ------------------------------------------------------------
+        xch[(4 + half) * BQ + r] = l_run;
+        consumer_sync();
+        const float l_tot = l_run + xch[(4 + (half ^ 1)) * BQ + r];
         mbar_wait(p_empty, (n_kv - 1) & 1);
         tc_fence_after();
-        const float inv_l = 1.f / l_run;
+        const float inv_l = 1.f / l_tot;
         const bool row_ok = qb * BQ + r < p.S;
-        __nv_bfloat16* orow = p.o + static_cast<int64_t>(row0 + r) * p.ld_o + h * D;
+        __nv_bfloat16* orow = p.o + static_cast<int64_t>(row0 + r) * p.ld_o + h * D + half * 64;
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
+            tmem_ld_32x32(tmem + lane_addr + TM_O + half * 64 + c * 32, v);
             tmem_ld_wait();
             if (row_ok) {
 #pragma unroll
@@ -257,8 +270,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 }
             }
         }
-        if (p.lse != nullptr && row_ok)
-            p.lse[(static_cast<int64_t>(b) * p.Hq + h) * p.S + qb * BQ + r] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+        if (p.lse != nullptr && row_ok && half == 0)
+            p.lse[(static_cast<int64_t>(b) * p.Hq + h) * p.S + qb * BQ + r] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
         tc_fence_before();
     }
     __syncthreads();
@@ -375,8 +388,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(sp_full(i), 1);
-            mbar_init(sp_empty(i), 4);
-            mbar_init(pd_full(i), 4);
+            mbar_init(sp_empty(i), kConsumers);
+            mbar_init(pd_full(i), kConsumers);
             mbar_init(pd_empty(i), 1);
         }
         mbar_init(acc_done, 1);
@@ -460,6 +473,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
     } else {
         const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;                  // which 32 of the sub-block's 64 query columns this warp owns
         const int r = q4 * 32 + lane;                      // key row inside the block
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
         const int key = jb * BKV + r;                      // key position inside the sequence
@@ -468,32 +482,29 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const int qs = sub0 + n % per_head;
             mbar_wait(sp_full(bs), (n >> 1) & 1);
             tc_fence_after();
-            const float* stat = reinterpret_cast<const float*>(smem + SM_STAT + st * 2 * BS * 4);
+            const float* stat = reinterpret_cast<const float*>(smem + SM_STAT + st * 2 * BS * 4) + half * 32;
             const bool diag = p.causal && (qs * BS < (jb + 1) * BKV);  // some (query, key) pairs of this tile are masked
-            mbar_wait(pd_empty(bs), ((n >> 1) & 1) ^ 1);               // P^T / dS^T buffer free (MMAs of iteration n-2 done)
-            uint8_t* prow = smem + SM_PT + bs * 2 * PT + r * 128;
-            uint32_t sv[BS], dv[BS];
-#pragma unroll
-            for (int c = 0; c < BS / 32; ++c) {
-                tmem_ld_32x32(tmem + lane_addr + TM_ST + bs * BS + c * 32, sv + c * 32);
-                tmem_ld_32x32(tmem + lane_addr + TM_DPT + bs * BS + c * 32, dv + c * 32);
-            }
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(tmem + lane_addr + TM_ST + bs * BS + half * 32, sv);
+            tmem_ld_32x32(tmem + lane_addr + TM_DPT + bs * BS + half * 32, dv);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sp_empty(bs));  // both accumulators are in registers: the next S^T / dP^T may start
+            mbar_wait(pd_empty(bs), ((n >> 1) & 1) ^ 1);               // P^T / dS^T buffer free (MMAs of iteration n-2 done)
+            uint8_t* prow = smem + SM_PT + bs * 2 * PT + r * 128;
 #pragma unroll
-            for (int ch = 0; ch < BS / 8; ++ch) {
+            for (int ch = 0; ch < 4; ++ch) {
                 float pf[8], df[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int col = ch * 8 + e;  // query inside the sub-block
+                    const int col = ch * 8 + e;  // query inside this warp's 32
                     float pe = ex2(fmaf(__uint_as_float(sv[col]), p.scale_log2, -stat[col]));
-                    if (diag && qs * BS + col < key) pe = 0.f;
+                    if (diag && qs * BS + half * 32 + col < key) pe = 0.f;
                     pf[e] = pe;
                     df[e] = pe * (__uint_as_float(dv[col]) - stat[BS + col]) * p.scale;
                 }
-                const uint32_t off = static_cast<uint32_t>(((ch ^ (r & 7)) << 4));
+                const uint32_t off = static_cast<uint32_t>((((half * 4 + ch) ^ (r & 7)) << 4));
                 *reinterpret_cast<Vec16*>(prow + off) = Elem<__nv_bfloat16>::pack(pf);
                 *reinterpret_cast<Vec16*>(prow + PT + off) = Elem<__nv_bfloat16>::pack(df);
             }
@@ -509,7 +520,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             __nv_bfloat16* dst = (which == 0 ? p.dv + orow * p.ld_dv + p.v_col0 : p.dk + orow * p.ld_dk + p.k_col0) + g * D;
             const uint32_t tacc = tmem + lane_addr + (which == 0 ? TM_DV : TM_DK);
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;  // this warp's 64 of the 128 dims
                 uint32_t v[32];
                 if (n_it > 0) {
                     tmem_ld_32x32(tacc + c * 32, v);
@@ -582,8 +594,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(sp_full(i), 1);
-            mbar_init(sp_empty(i), 4);
-            mbar_init(ds_full(i), 4);
+            mbar_init(sp_empty(i), kConsumers);
+            mbar_init(ds_full(i), kConsumers);
             mbar_init(ds_empty(i), 1);
         }
         mbar_init(acc_done, 1);
@@ -658,6 +670,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         }
     } else {
         const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;  // which 32 of the sub-block's 64 key columns this warp owns
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
         const int64_t sidx = (static_cast<int64_t>(b) * p.Hq + h) * p.S + qb * BQ + r;
@@ -668,29 +681,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mbar_wait(sp_full(bs), (n >> 1) & 1);
             tc_fence_after();
             const bool diag = p.causal && ((n + 1) * BS > qb * BQ);
-            mbar_wait(ds_empty(bs), ((n >> 1) & 1) ^ 1);
-            uint8_t* drow = smem + SM_DS + bs * PT + r * 128;
-            uint32_t sv[BS], dv[BS];
-#pragma unroll
-            for (int c = 0; c < BS / 32; ++c) {
-                tmem_ld_32x32(tmem + lane_addr + TM_S + bs * BS + c * 32, sv + c * 32);
-                tmem_ld_32x32(tmem + lane_addr + TM_DP + bs * BS + c * 32, dv + c * 32);
-            }
+            uint32_t sv[32], dv[32];
+            tmem_ld_32x32(tmem + lane_addr + TM_S + bs * BS + half * 32, sv);
+            tmem_ld_32x32(tmem + lane_addr + TM_DP + bs * BS + half * 32, dv);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(sp_empty(bs));
+            mbar_wait(ds_empty(bs), ((n >> 1) & 1) ^ 1);
+            uint8_t* drow = smem + SM_DS + bs * PT + r * 128;
 #pragma unroll
-            for (int ch = 0; ch < BS / 8; ++ch) {
+            for (int ch = 0; ch < 4; ++ch) {
                 float df[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int col = ch * 8 + e;
-                    float pe = ex2(fmaf(__uint_as_float(sv[col]), p.scale_log2, -lse2));
+                    const int col = half * 32 + ch * 8 + e;
+                    float pe = ex2(fmaf(__uint_as_float(sv[ch * 8 + e]), p.scale_log2, -lse2));
                     if (diag && n * BS + col > qpos) pe = 0.f;
-                    df[e] = pe * (__uint_as_float(dv[col]) - delta) * p.scale;
+                    df[e] = pe * (__uint_as_float(dv[ch * 8 + e]) - delta) * p.scale;
                 }
-                *reinterpret_cast<Vec16*>(drow + ((ch ^ (r & 7)) << 4)) = Elem<__nv_bfloat16>::pack(df);
+                *reinterpret_cast<Vec16*>(drow + (((half * 4 + ch) ^ (r & 7)) << 4)) = Elem<__nv_bfloat16>::pack(df);
             }
             fence_async_smem();
             __syncwarp();
@@ -700,7 +710,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         tc_fence_after();
         __nv_bfloat16* dst = p.dq + static_cast<int64_t>(row0 + r) * p.ld_dq + p.q_col0 + h * D;
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = half * 2 + cc;
             uint32_t v[32];
             tmem_ld_32x32(tmem + lane_addr + TM_DQ + c * 32, v);
             tmem_ld_wait();

@@ -169,6 +169,7 @@ struct AgParams {
     int64_t shard_bytes;
     int64_t chunk_bytes;
     int64_t b_offset_bytes;  // byte offset of B's first element inside the unit flat buffer
+    int64_t b_bytes;         // extent of B: its chunks are gathered FIRST so the multiply can start while the rest streams
     int n_chunks;
     int world;
     int rank;
@@ -216,13 +217,18 @@ __device__ void ag_gather_role(const AgParams& ag, int ci, int nc, uint8_t* smem
     for (int b = 0; b < AG_BUFS; ++b) mbar_init(bar0 + 8 * b, 1);
     fence_barrier_init();
     const int chunks_per_shard = static_cast<int>(ag.shard_bytes / ag.chunk_bytes);
+    // chunks holding the matrix this very kernel multiplies by go first (pass 0), the rest of the unit follows (pass 1)
+    const int b_c0 = static_cast<int>(ag.b_offset_bytes / ag.chunk_bytes);
+    const int b_c1 = static_cast<int>((ag.b_offset_bytes + ag.b_bytes - 1) / ag.chunk_bytes);
     uint32_t issued = 0;           // pieces issued so far (ring position = issued % AG_BUFS)
+    for (int pass = 0; pass < 2; ++pass)
     for (int j = ci; j < ag.n_chunks; j += nc) {
         // visit order: shards rotated so that every rank starts pulling from a different peer
         const int k = j / chunks_per_shard;
         const int within = j - k * chunks_per_shard;
         const int peer = (ag.rank + k) % ag.world;
         const int chunk = peer * chunks_per_shard + within;
+        if ((chunk >= b_c0 && chunk <= b_c1) != (pass == 0)) continue;
         const int64_t off = static_cast<int64_t>(within) * ag.chunk_bytes;
         const char* src = static_cast<const char*>(ag.peers[peer]) + off;
         char* dst = static_cast<char*>(ag.local_full) + static_cast<int64_t>(peer) * ag.shard_bytes + off;
@@ -1257,6 +1263,7 @@ DSB_EXPORT int dsb_gemm_nt_bf16_allgather(const void* a, const void* b, void* c,
     ag.shard_bytes = shard_bytes;
     ag.chunk_bytes = chunk_bytes;
     ag.b_offset_bytes = b_offset_bytes;
+    ag.b_bytes = static_cast<int64_t>(N) * ldb * 2;
     ag.n_chunks = static_cast<int>(shard_bytes / chunk_bytes) * world;
     ag.world = world;
     ag.rank = rank;

@@ -389,3 +389,77 @@ DSB_EXPORT int dsb_nhwc_bias_add(const void* x, const void* bias_x, const void* 
     DSB_CHECK_LAUNCH();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// 1-bit (sign) compression with error feedback for the compressed all-reduce of 1-bit Adam / 0-1 Adam / 1-bit LAMB.
+// Reference: runtime/comm/nccl.py:51 compressed_allreduce (cupy packbits + torch ops: ~8 element-wise passes per phase);
+// here each phase is ONE pass: 8 values -> 1 byte (MSB first) and the error feedback  e = w - scale * sign(w)  in the same
+// kernel; the server side fuses unpack + scale + average over the ranks.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace dsb {
+__global__ void __launch_bounds__(256)
+onebit_pack_kernel(const float* __restrict__ work, const float* __restrict__ scale_ptr, uint8_t* __restrict__ packed,
+                   float* __restrict__ err, int64_t n8)
+{
+    const float s = *scale_ptr;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float w[8], e[8];
+        Elem<float>::unpack(ld_stream(work + i * 8), w);
+        Elem<float>::unpack(ld_stream(work + i * 8 + 4), w + 4);
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool pos = w[k] >= 0.f;
+            byte |= (pos ? 1u : 0u) << (7 - k);
+            e[k] = w[k] - (pos ? s : -s);
+        }
+        packed[i] = static_cast<uint8_t>(byte);
+        st_plain(err + i * 8, Elem<float>::pack(e));
+        st_plain(err + i * 8 + 4, Elem<float>::pack(e + 4));
+    }
+}
+
+// out[8 i + k] = inv * sum_r (bit(packed[r][i], k) ? scales[r] : -scales[r])
+__global__ void __launch_bounds__(256)
+onebit_unpack_avg_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ scales, float* __restrict__ out,
+                         int64_t n8, int ranks, float inv)
+{
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int r = 0; r < ranks; ++r) {
+            const uint32_t byte = packed[static_cast<int64_t>(r) * n8 + i];
+            const float s = scales[r];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += ((byte >> (7 - k)) & 1u) ? s : -s;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] *= inv;
+        st_plain(out + i * 8, Elem<float>::pack(acc));
+        st_plain(out + i * 8 + 4, Elem<float>::pack(acc + 4));
+    }
+}
+}  // namespace dsb
+
+DSB_EXPORT int dsb_onebit_pack(const float* work, const float* scale, uint8_t* packed, float* err, int64_t n,
+                               cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    if (n % 8) return -2;
+    dsb::onebit_pack_kernel<<<dsb::flat_grid(n / 8, 256, 16), 256, 0, stream>>>(work, scale, packed, err, n / 8);
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+DSB_EXPORT int dsb_onebit_unpack_avg(const uint8_t* packed, const float* scales, float* out, int64_t n, int ranks, float inv,
+                                     cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    if (n % 8) return -2;
+    dsb::onebit_unpack_avg_kernel<<<dsb::flat_grid(n / 8, 256, 16), 256, 0, stream>>>(packed, scales, out, n / 8, ranks, inv);
+    DSB_CHECK_LAUNCH();
+    return 0;
+}

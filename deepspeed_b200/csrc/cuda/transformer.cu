@@ -209,16 +209,36 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
 }
 
 // out[c] = sum_r part[r, c]  (fixed order -> deterministic); optional accumulate into out.
+// A CTA owns 32 columns; its 8 warps stride over the rows (coalesced 128-byte row segments), partial sums meet in shared
+// memory in a fixed order.  (One thread per column left only hidden/256 CTAs on the chip: 35 us for a 10 MB reduction.)
 template <typename TO>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ part, TO* __restrict__ out,
                                                       int nrows, int ncols, int accumulate)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     float acc = 0.f;
-    for (int r = 0; r < nrows; ++r) acc += part[static_cast<int64_t>(r) * ncols + c];
-    if (accumulate) acc += Elem<TO>::to_f(out[c]);
-    out[c] = Elem<TO>::from_f(acc);
+    if (c < ncols) {
+        int r = w;
+        for (; r + 24 < nrows; r += 32) {  // 4 independent loads in flight per thread
+            const float a0 = part[static_cast<int64_t>(r) * ncols + c];
+            const float a1 = part[static_cast<int64_t>(r + 8) * ncols + c];
+            const float a2 = part[static_cast<int64_t>(r + 16) * ncols + c];
+            const float a3 = part[static_cast<int64_t>(r + 24) * ncols + c];
+            acc += (a0 + a1) + (a2 + a3);
+        }
+        for (; r < nrows; r += 8) acc += part[static_cast<int64_t>(r) * ncols + c];
+    }
+    red[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < ncols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][lane];
+        if (accumulate) t += Elem<TO>::to_f(out[c]);
+        out[c] = Elem<TO>::from_f(t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,7 +639,7 @@ DSB_EXPORT int dsb_norm_bwd(const void* dy, const void* x, const void* w, const 
                                                                     rstd, (const T*)dres, (T*)dx, dw_part, db_part,
                                                                     rows, hidden);
     })
-    const int cg = (hidden + 255) / 256;
+    const int cg = (hidden + 31) / 32;
     DISPATCH_T(wdtype, TO, {
         colsum_kernel<TO><<<cg, 256, 0, stream>>>(dw_part, (TO*)dw, grid, hidden, accumulate_dw);
         if (kind == 1 && db != nullptr)
@@ -632,7 +652,7 @@ DSB_EXPORT int dsb_norm_bwd(const void* dy, const void* x, const void* w, const 
 DSB_EXPORT int dsb_colsum(const float* part, void* out, int nrows, int ncols, int out_dtype, int accumulate,
                           cudaStream_t stream)
 {
-    const int cg = (ncols + 255) / 256;
+    const int cg = (ncols + 31) / 32;
     DISPATCH_T(out_dtype, TO, { colsum_kernel<TO><<<cg, 256, 0, stream>>>(part, (TO*)out, nrows, ncols, accumulate); })
     DSB_CHECK_LAUNCH();
     return 0;

@@ -41,6 +41,9 @@ struct Params {
     const __nv_bfloat16* bias;
     __nv_bfloat16* out;    // [M, N]
     int M, N, K, group_size, ldo;
+    // grouped (MoE) form: rows of x / out are sorted by expert, expert e owns rows offsets[e] .. offsets[e+1] (device
+    // array, no host sync) and uses the e-th [N, K] slab of wq / scales / bias; blockIdx.z = expert
+    const int* offsets;
 };
 
 // decode 8 consecutive K elements of one feature row into 8 scaled floats
@@ -121,8 +124,15 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f0 = blockIdx.x * BF;  // first feature of this CTA
-    const int t0 = blockIdx.y * BT;  // first token
-    const int mt = min(BT, ((p.M - t0) + 15) & ~15);  // MMA N: tokens of this tile rounded up to 16 (TMA zero-fills)
+    int t0 = blockIdx.y * BT;        // first token
+    int t_end = p.M;
+    const int expert = blockIdx.z;
+    if (p.offsets != nullptr) {
+        t0 += p.offsets[expert];
+        t_end = p.offsets[expert + 1];
+    }
+    if (t0 >= t_end) return;  // this expert has fewer token tiles (uniform for the CTA: nothing was initialised yet)
+    const int mt = min(BT, ((t_end - t0) + 15) & ~15);  // MMA N: tokens of this tile rounded up to 16
     const int num_k = p.K / BK;
 
     if (warp == 0 && lane == 0) {
@@ -176,8 +186,9 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
         const bool feat_ok = feat < p.N;
         constexpr int B8 = bytes_per_8<MODE>();
         const int64_t row_bytes = static_cast<int64_t>(p.K) / 8 * B8;
-        const uint8_t* wrow = p.wq + static_cast<int64_t>(feat_ok ? feat : 0) * row_bytes;
-        const float* srow = p.scales + static_cast<int64_t>(feat_ok ? feat : 0) * (p.K / p.group_size);
+        const int64_t slab = static_cast<int64_t>(expert) * p.N;  // rows of the stacked [E, N, K] weight before this expert
+        const uint8_t* wrow = p.wq + (slab + (feat_ok ? feat : 0)) * row_bytes;
+        const float* srow = p.scales + (slab + (feat_ok ? feat : 0)) * (p.K / p.group_size);
         for (int kb = 0; kb < num_k; ++kb) {
             const int st = kb % kStages;
             mbar_wait(empty(st), ((kb / kStages) & 1) ^ 1);
@@ -202,7 +213,7 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
         // ---- epilogue: transposed store of D^T[feature r, tokens] --------------------------------------------------------------
         mbar_wait(acc_done, 0);
         tc_fence_after();
-        const float bias = (p.bias != nullptr && feat_ok) ? __bfloat162float(p.bias[feat]) : 0.f;
+        const float bias = (p.bias != nullptr && feat_ok) ? __bfloat162float(p.bias[slab + feat]) : 0.f;
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
         for (int c = 0; c < mt; c += 32) {
             uint32_t v[32];
@@ -212,7 +223,7 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                     const int tok = t0 + c + e;
-                    if (tok < p.M) p.out[static_cast<int64_t>(tok) * p.ldo + feat] = __float2bfloat16_rn(__uint_as_float(v[e]) + bias);
+                    if (tok < t_end) p.out[static_cast<int64_t>(tok) * p.ldo + feat] = __float2bfloat16_rn(__uint_as_float(v[e]) + bias);
                 }
             }
         }
@@ -239,7 +250,7 @@ static EncodeTiledFn encode_fn()
 }
 
 template <int MODE>
-static int launch(const CUtensorMap& mx, const Params& p, cudaStream_t stream)
+static int launch(const CUtensorMap& mx, const Params& p, int experts, cudaStream_t stream)
 {
     static bool attr = false;
     if (!attr) {
@@ -247,7 +258,7 @@ static int launch(const CUtensorMap& mx, const Params& p, cudaStream_t stream)
         if (e != cudaSuccess) return static_cast<int>(e);
         attr = true;
     }
-    dim3 grid((p.N + BF - 1) / BF, (p.M + BT - 1) / BT);
+    dim3 grid((p.N + BF - 1) / BF, (p.M + BT - 1) / BT, experts);
     wq_tc_kernel<MODE><<<grid, kThreads, SM_TOTAL, stream>>>(mx, p);
     return 0;
 }
@@ -259,8 +270,28 @@ using namespace dsb::wqtc;
 
 // mode: 0 int8, 1 int4 (two's-complement nibbles, low first), 2 fp8 e4m3, 3 fp6 e3m2.  x [M, K] bf16 (row stride ldx), out [M, N] bf16.
 // K % 64 == 0, group_size % 64 == 0 (a K step never straddles two scale groups), K % group_size == 0.
+static int wq_tc_impl(const void* x, const void* wq, const float* scales, const void* bias, void* out, int M, int N, int K,
+                      int mode, int group_size, int ldx, int ldo, const int* offsets, int experts, cudaStream_t stream);
+
 DSB_EXPORT int dsb_wq_tc_gemm(const void* x, const void* wq, const float* scales, const void* bias, void* out, int M, int N,
                               int K, int mode, int group_size, int ldx, int ldo, cudaStream_t stream)
+{
+    return wq_tc_impl(x, wq, scales, bias, out, M, N, K, mode, group_size, ldx, ldo, nullptr, 1, stream);
+}
+
+// Grouped (MoE) form: x / out rows sorted by expert, `offsets` int32 [E + 1] ON THE DEVICE, wq / scales / bias stacked [E, ...].
+// M = total rows (an upper bound for every expert's row count: the grid covers ceil(M / 128) token tiles per expert and CTAs
+// beyond an expert's range exit at once) -- no host synchronisation, CUDA-graph capturable.
+DSB_EXPORT int dsb_wq_tc_gemm_grouped(const void* x, const void* wq, const float* scales, const void* bias, void* out,
+                                      const int* offsets, int E, int M, int N, int K, int mode, int group_size, int ldx,
+                                      int ldo, cudaStream_t stream)
+{
+    if (E <= 0 || offsets == nullptr) return -3;
+    return wq_tc_impl(x, wq, scales, bias, out, M, N, K, mode, group_size, ldx, ldo, offsets, E, stream);
+}
+
+static int wq_tc_impl(const void* x, const void* wq, const float* scales, const void* bias, void* out, int M, int N, int K,
+                      int mode, int group_size, int ldx, int ldo, const int* offsets, int experts, cudaStream_t stream)
 {
     if (M <= 0 || N <= 0) return 0;
     if (K % BK || group_size % BK || K % group_size || ldx % 8 || mode < 0 || mode > 3) return -3;
@@ -285,12 +316,13 @@ DSB_EXPORT int dsb_wq_tc_gemm(const void* x, const void* wq, const float* scales
     p.K = K;
     p.group_size = group_size;
     p.ldo = ldo;
+    p.offsets = offsets;
     int rc;
     switch (mode) {
-        case kInt8: rc = launch<kInt8>(mx, p, stream); break;
-        case kInt4: rc = launch<kInt4>(mx, p, stream); break;
-        case kFp8: rc = launch<kFp8>(mx, p, stream); break;
-        default: rc = launch<kFp6>(mx, p, stream); break;
+        case kInt8: rc = launch<kInt8>(mx, p, experts, stream); break;
+        case kInt4: rc = launch<kInt4>(mx, p, experts, stream); break;
+        case kFp8: rc = launch<kFp8>(mx, p, experts, stream); break;
+        default: rc = launch<kFp6>(mx, p, experts, stream); break;
     }
     if (rc) return rc;
     DSB_CHECK_LAUNCH();

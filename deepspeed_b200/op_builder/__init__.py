@@ -135,3 +135,36 @@ def build_all(verbose=True):
 
 def get_default_compute_capabilities():
     return "10.0a"
+
+
+# ---- per-op module paths of the reference (``op_builder/fused_adam.py`` ...) ------------------------------------------------
+# The reference has one file per builder; here every builder is a two-line class over the same two libraries, so the module
+# paths are registered virtually instead of stamping out 21 one-line files: ``from deepspeed_b200.op_builder.fused_adam import
+# FusedAdamBuilder`` resolves to a module object created on the spot that exposes exactly that class.
+_MODULE_OF = {
+    "async_io": AsyncIOBuilder, "cpu_adagrad": CPUAdagradBuilder, "cpu_adam": CPUAdamBuilder, "cpu_lion": CPULionBuilder,
+    "evoformer_attn": EvoformerAttnBuilder, "fp_quantizer": FPQuantizerBuilder, "fused_adam": FusedAdamBuilder,
+    "fused_lamb": FusedLambBuilder, "fused_lion": FusedLionBuilder, "gds": GDSBuilder,
+    "inference_core_ops": InferenceCoreBuilder, "inference_cutlass_builder": InferenceCutlassBuilder,
+    "quantizer": QuantizerBuilder, "ragged_ops": RaggedOpsBuilder, "ragged_utils": RaggedUtilsBuilder,
+    "random_ltd": RandomLTDBuilder, "sparse_attn": SparseAttnBuilder, "spatial_inference": SpatialInferenceBuilder,
+    "stochastic_transformer": StochasticTransformerBuilder, "transformer": TransformerBuilder,
+    "transformer_inference": InferenceBuilder,
+}
+
+
+def _register_builder_modules(package_name):
+    import sys
+    import types
+    for mod, cls in _MODULE_OF.items():
+        full = f"{package_name}.{mod}"
+        if full in sys.modules:
+            continue
+        m = types.ModuleType(full, f"``{cls.__name__}`` (reference ``op_builder/{mod}.py``); see ``op_builder/__init__.py``.")
+        setattr(m, cls.__name__, cls)
+        m.__package__ = package_name
+        sys.modules[full] = m
+        setattr(sys.modules[package_name], mod, m)
+
+
+_register_builder_modules(__name__)

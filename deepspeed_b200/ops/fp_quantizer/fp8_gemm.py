@@ -1,14 +1,22 @@
 """``matmul_fp8``: activation (bf16) x group-quantised FP8 weight (reference ``ops/fp_quantizer/fp8_gemm.py`` +
-``fp8_gemm_triton.py``).  The weight is dequantised by the ``fp_dequantize`` kernel into bf16 and multiplied on the tensor
-cores; for decode-sized inputs the op is bound by the FP8 weight bytes, which is the point of storing them in 8 bits."""
+``fp8_gemm_triton.py``).
+
+Two implementations, picked by the weight's storage:
+
+* the weight was quantised as ``[N, K]`` rows with groups along K (``QuantizedWeight`` of
+  ``inference/quantization/layers.py``) -> the fused kernels stream the FP8 bytes and dequantise on chip: ``wq_gemm.cu``
+  (mma.sync, <= 32 rows) or ``wq_tc_gemm.cu`` (tcgen05, dequantise-in-shared-memory, up to ~1k rows);
+* the reference calling convention -- packed payload of a ``[K, N]`` matrix + per-group scales -> :func:`matmul_fp8_fallback`
+  (the ``fp_dequantize`` kernel into bf16, then a tensor-core GEMM).
+"""
 import torch
 
 from .quantize import FP_Quantize
 
 
-def matmul_fp8(inp, weight, scale, quantization_group_size, quantizer: FP_Quantize = None):
-    """``inp [..., K] @ dequant(weight)[K, N]``; ``weight`` is the packed payload produced by ``FP_Quantize.quantize`` for a
-    ``[K, N]`` matrix, ``scale`` its per-group scales."""
+def matmul_fp8_fallback(inp, weight, scale, quantization_group_size, quantizer: FP_Quantize = None):
+    """Dequantise -> GEMM: ``inp [..., K] @ dequant(weight)[K, N]`` for the packed payload ``FP_Quantize.quantize``
+    produced from a ``[K, N]`` matrix (``scale``: its per-group scales)."""
     q = quantizer if quantizer is not None else FP_Quantize(group_size=quantization_group_size)
     k = inp.shape[-1]
     groups = scale.numel()
@@ -18,7 +26,10 @@ def matmul_fp8(inp, weight, scale, quantization_group_size, quantizer: FP_Quanti
     return torch.matmul(inp, w)
 
 
-def matmul_fp8_fallback(inp, weight, scale, quantization_group_size, quantizer: FP_Quantize = None):
-    """Library-only path (dequantise → ``torch.matmul``); what ``matmul_fp8`` does for shapes the fused weight-only kernel
-    does not cover (reference ``fp8_gemm.py``)."""
-    return matmul_fp8(inp, weight, scale, quantization_group_size, quantizer)
+def matmul_fp8(inp, weight, scale=None, quantization_group_size=None, quantizer: FP_Quantize = None):
+    """FP8-weight GEMM.  ``weight`` may be a ``QuantizedWeight`` (``mode == "fp8"``, ``[N, K]`` layout: fused on-chip
+    dequantisation, nothing but FP8 bytes leave HBM) or the reference's packed ``[K, N]`` payload with ``scale``."""
+    from deepspeed_b200.inference.quantization.layers import QuantizedWeight, maybe_quantized_linear
+    if isinstance(weight, QuantizedWeight):
+        return maybe_quantized_linear(inp, weight)
+    return matmul_fp8_fallback(inp, weight, scale, quantization_group_size, quantizer)

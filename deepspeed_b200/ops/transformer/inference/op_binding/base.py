@@ -18,3 +18,23 @@ class BaseOp(torch.nn.Module):
     @property
     def eps(self):
         return getattr(self.config, "epsilon", 1e-5)
+
+
+def gemm_linear(x, weight, bias=None):
+    """``x @ weight^T (+ bias)`` for the inference op bindings: bf16 CUDA problems with at least one 256x128 tile go to the
+    framework's tcgen05 GEMM through :mod:`deepspeed_b200.ops.gemm` (persisted per-shape choice vs cuBLAS), weight-only
+    quantised weights to the fused dequant kernels, everything else (decode-sized rows, fp16/fp32, host) to the library --
+    the role of the reference's ``cublas_gemm_ex`` calls in ``csrc/transformer/inference/csrc/pt_binding.cpp``."""
+    import torch.nn.functional as F
+    from deepspeed_b200.inference.quantization.layers import QuantizedWeight, maybe_quantized_linear
+    if isinstance(weight, QuantizedWeight):
+        return maybe_quantized_linear(x, weight, bias)
+    if x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.dim() == 2:
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.shape[0] >= 256 and x2.is_contiguous() and weight.is_contiguous():
+            from deepspeed_b200.ops import gemm
+            y = gemm.matmul_nt(x2, weight)
+            if bias is not None:
+                y = y + bias
+            return y.view(*x.shape[:-1], weight.shape[0])
+    return F.linear(x, weight, bias)

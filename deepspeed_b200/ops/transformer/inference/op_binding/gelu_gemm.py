@@ -5,11 +5,11 @@ import torch.nn.functional as F
 from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
 from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
 
-from .base import BaseOp
+from .base import BaseOp, gemm_linear
 
 
 class GELUGemmOp(BaseOp):
 
     def forward(self, input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, weight_out: torch.Tensor):
-        h = T.bias_gelu(F.linear(input, weight), bias)
-        return F.linear(h, weight_out)
+        h = T.bias_gelu(gemm_linear(input, weight), bias)
+        return gemm_linear(h, weight_out)

@@ -5,7 +5,7 @@ import torch.nn.functional as F
 from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
 from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
 
-from .base import BaseOp
+from .base import BaseOp, gemm_linear
 
 
 class MLPGemmOp(BaseOp):
@@ -18,5 +18,5 @@ class MLPGemmOp(BaseOp):
         else:
             normed, res = T.layer_norm(x, gamma, beta, c.epsilon, residual=residual)
         from ..ds_transformer import _mlp_act
-        h = F.linear(normed, weight_interm, bias)
-        return F.linear(_mlp_act(h, c.mlp_act_func_type), weight_out), res
+        h = gemm_linear(normed, weight_interm, bias)
+        return gemm_linear(_mlp_act(h, c.mlp_act_func_type), weight_out), res

@@ -5,7 +5,7 @@ import torch.nn.functional as F
 from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
 from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
 
-from .base import BaseOp
+from .base import BaseOp, gemm_linear
 
 
 class QKVGemmOp(BaseOp):
@@ -16,4 +16,4 @@ class QKVGemmOp(BaseOp):
             normed = T.rms_norm(input, gamma, c.epsilon)
         else:
             normed = T.layer_norm(input, gamma, beta, c.epsilon)
-        return F.linear(normed, weight, bias), normed
+        return gemm_linear(normed, weight, bias), normed

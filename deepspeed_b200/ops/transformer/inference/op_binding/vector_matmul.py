@@ -5,10 +5,10 @@ import torch.nn.functional as F
 from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
 from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
 
-from .base import BaseOp
+from .base import BaseOp, gemm_linear
 
 
 class VectorMatMulOp(BaseOp):
 
     def forward(self, input: torch.Tensor, weight: torch.Tensor, async_op: bool = False):
-        return F.linear(input, weight)
+        return gemm_linear(input, weight)

@@ -32,6 +32,40 @@ def unpack_signs(packed: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return bits.to(dtype).mul_(2).sub_(1).view(-1)
 
 
+def _native(t):
+    return t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+
+
+def compress_with_feedback(work: torch.Tensor, error_out: torch.Tensor):
+    """``work`` (already holding value + previous error) -> ``(packed signs, scale)``; writes the new error
+    ``work - scale * sign(work)`` into ``error_out``.  One fused sm_100a pass on the device (``misc.cu onebit_pack``)."""
+    scale = work.norm() / (work.numel()**0.5)
+    if _native(work) and _native(error_out) and work.numel() % 8 == 0:
+        from deepspeed_b200.ops import native as N
+        packed = torch.empty(work.numel() // 8, dtype=torch.uint8, device=work.device)
+        rc = N.cuda().dsb_onebit_pack(N.ptr(work), N.ptr(scale.reshape(1)), N.ptr(packed), N.ptr(error_out),
+                                      N.c_i64(work.numel()), N.stream())
+        N.check(rc, "onebit_pack")
+        return packed, scale
+    packed = pack_signs(work)
+    error_out.copy_(work - scale * unpack_signs(packed, work.dtype))
+    return packed, scale
+
+
+def decompress_average(packed: torch.Tensor, scales: torch.Tensor, n: int) -> torch.Tensor:
+    """``packed [R, n/8]`` sign bytes + ``scales [R]`` -> mean over the R senders of ``scale_r * sign_r`` (length n)."""
+    R = scales.numel()
+    if packed.is_cuda and packed.is_contiguous() and scales.dtype == torch.float32 and n % 8 == 0:
+        from deepspeed_b200.ops import native as N
+        out = torch.empty(n, dtype=torch.float32, device=packed.device)
+        rc = N.cuda().dsb_onebit_unpack_avg(N.ptr(packed), N.ptr(scales.contiguous()), N.ptr(out), N.c_i64(n), R,
+                                            N.c_f(1.0 / R), N.stream())
+        N.check(rc, "onebit_unpack_avg")
+        return out
+    vals = unpack_signs(packed.reshape(-1), torch.float32).view(R, n)
+    return (vals * scales.view(R, 1).float()).sum(0).div_(R)
+
+
 class CompressedBackend:
 
     def __init__(self, mpu=None, group=None):
@@ -67,9 +101,7 @@ class CompressedBackend:
             work = flat.clone()
         # ---- worker compression
         work.add_(worker_error)
-        w_scale = work.norm() / (padded**0.5)
-        signs = pack_signs(work)
-        worker_error.copy_(work - w_scale * unpack_signs(signs, work.dtype))
+        signs, w_scale = compress_with_feedback(work, worker_error)
         # ---- exchange: chunk r of everyone's signs goes to rank r
         send = signs.view(size, chunk // 8)
         recv = torch.empty_like(send)
@@ -82,12 +114,9 @@ class CompressedBackend:
             recv.copy_(send)
             scales = w_scale.view(1)
         # ---- server: average, compress again
-        vals = unpack_signs(recv.reshape(-1), work.dtype).view(size, chunk)
-        server = (vals * scales.view(size, 1)).sum(0).div_(size)
+        server = decompress_average(recv.contiguous(), scales.float(), chunk).to(work.dtype)
         server.add_(server_error)
-        s_scale = server.norm() / (chunk**0.5)
-        s_signs = pack_signs(server)
-        server_error.copy_(server - s_scale * unpack_signs(s_signs, server.dtype))
+        s_signs, s_scale = compress_with_feedback(server, server_error)
         # ---- broadcast result
         if size > 1:
             all_signs = [torch.empty_like(s_signs) for _ in range(size)]

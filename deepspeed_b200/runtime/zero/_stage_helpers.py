@@ -6,8 +6,10 @@ import torch
 
 from deepspeed_b200 import comm as dist
 
-# (the reference's ``pg_correctness_test`` debug switch lives on as ``zero_optimization.b200_verify_collectives``: every
-# in-kernel NVLink collective is cross-checked against NCCL at run time, see ``sharded.py:_verify_reduce_scatter``)
+# The reference's module-level debug switch (``stage_1_and_2.py:36``).  Setting it to True before ``initialize()`` turns on
+# the run-time cross-check of every in-kernel NVLink collective against NCCL for the whole run (the config knob
+# ``zero_optimization.b200_verify_collectives: N`` does the same for the first N steps); see ``sharded.py``.
+pg_correctness_test = False
 OPTIMIZER_ALLGATHER_TIMER, OPTIMIZER_GRADIENTS_TIMER, OPTIMIZER_STEP_TIMER = "optimizer_allgather", "optimizer_gradients", \
     "optimizer_step"
 OPTIMIZER_TIMERS = [OPTIMIZER_ALLGATHER_TIMER, OPTIMIZER_GRADIENTS_TIMER, OPTIMIZER_STEP_TIMER]

@@ -246,6 +246,9 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self._symm = None
         self._maybe_enable_symm()
         self._verify_left = int(getattr(self.zc, "b200_verify_collectives", 0) or 0) if self._symm is not None else 0
+        from deepspeed_b200.runtime.zero import _stage_helpers
+        if _stage_helpers.pg_correctness_test and self._symm is not None:
+            self._verify_left = 1 << 60  # the reference's global switch: verify for the whole run
         self.verify_report = {"all_gather": 0, "reduce_scatter": 0, "max_rel_err": 0.0}
         log_dist(
             f"ZeroShardedOptimizer: stage={self.stage} units={len(self.units)} arena={self.arena_numel:,} elems/rank "

@@ -12,7 +12,16 @@ which = sys.argv[1] if len(sys.argv) > 1 else "adam"
 d = "cuda"
 torch.manual_seed(0)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=d)
-if which == "adam":
+if which == "attn":
+    from deepspeed_b200.ops.kernels import attention_sm100 as A
+    B, S, hq, hkv = 2, 4096, 32, 8
+    qkv = torch.randn(B * S, (hq + 2 * hkv) * 128, device=d, dtype=torch.bfloat16)
+    q, k, v = A.split_packed(qkv, hq, hkv)
+    for _ in range(2):
+        o, lse = A.fwd(q, k, v, B, S, hq, hkv, causal=True)
+        A.bwd(torch.randn_like(o), q, k, v, o, lse, B, S, hq, hkv, causal=True)
+    torch.cuda.synchronize()
+elif which == "adam":
     n = 256 * 1024 * 1024
     p = torch.randn(n, device=d)
     g = torch.randn(n, device=d, dtype=torch.bfloat16)

@@ -217,3 +217,28 @@ def test_wq_tc_gemm_matches_dequant_reference(mode, M, N, K):
     ref = x.float() @ qw.dequantize().float().t() + b.float()
     assert torch.isfinite(y.float()).all()
     assert (y.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item() + 2e-2
+
+
+@pytest.mark.parametrize("mode", ["int8", "fp6"])
+def test_mixed_moe_gemm_grouped_single_launch(mode):
+    """MixedMoEGEMM: expert-sorted rows x weight-only-quantised expert weights in one grouped tcgen05 launch (device-side
+    expert extents) vs the per-expert dequantise + matmul reference; includes an empty expert and a ragged tail."""
+    import torch
+    from deepspeed_b200.inference.quantization.layers import quantize_weight
+    from deepspeed_b200.inference.v2.kernels.cutlass_ops.moe_gemm.mixed_moe_gemm import MixedMoEGEMM
+    torch.manual_seed(0)
+    E, N, K = 4, 384, 512
+    counts = [200, 0, 37, 150]
+    T = sum(counts)
+    ws = [quantize_weight((torch.randn(N, K, device="cuda") * 0.05).bfloat16(), mode, group_size=128) for _ in range(E)]
+    x = (torch.randn(T, K, device="cuda") * 0.5).bfloat16()
+    out = torch.full((T, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cums = torch.tensor(counts, device="cuda").cumsum(0)
+    MixedMoEGEMM(torch.bfloat16, num_bits=8)(out, x, ws, None, cums)
+    s = 0
+    for e, c in enumerate(counts):
+        if c:
+            ref = x[s:s + c].float() @ ws[e].dequantize().float().t()
+            assert (out[s:s + c].float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item() + 2e-2
+        s += c
+    assert torch.isfinite(out.float()).all()

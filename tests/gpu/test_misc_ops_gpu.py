@@ -102,3 +102,26 @@ def test_evoformer_attention_device():
     assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0) > 0.999
     out.float().sum().backward()
     assert pair.grad is not None and torch.isfinite(pair.grad.float()).all()
+
+
+def test_onebit_pack_unpack_kernels_match_torch_path():
+    """1-bit compression kernels (sign pack + error feedback, fused unpack + average) vs the torch reference path."""
+    import torch
+    from deepspeed_b200.runtime.comm import compressed as C
+    torch.manual_seed(0)
+    n = 8 * 4096 + 8 * 3
+    work = torch.randn(n, device="cuda")
+    err = torch.empty(n, device="cuda")
+    packed, scale = C.compress_with_feedback(work.clone(), err)
+    ref_packed = C.pack_signs(work)
+    ref_scale = work.norm() / n**0.5
+    assert torch.equal(packed, ref_packed) and abs(float(scale - ref_scale)) < 1e-6
+    torch.testing.assert_close(err, work - ref_scale * C.unpack_signs(ref_packed))
+    R = 4
+    pk = torch.stack([C.pack_signs(torch.randn(n, device="cuda")) for _ in range(R)])
+    sc = torch.rand(R, device="cuda") + 0.5
+    got = C.decompress_average(pk, sc, n)
+    ref = (C.unpack_signs(pk.reshape(-1)).view(R, n) * sc.view(R, 1)).sum(0) / R
+    torch.testing.assert_close(got, ref, atol=1e-6, rtol=1e-5)
+    # single-rank backend round trip through the kernels
+    be = C.CompressedBackend(group=None) if torch.distributed.is_initialized() else None
