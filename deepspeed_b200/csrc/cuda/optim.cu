@@ -385,6 +385,9 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const TI* __restrict__ 
                                                           const float* __restrict__ d_scale)
 {
     const float s = a * (d_scale ? *d_scale : 1.f);
+    // in-place scaling by exactly 1 (a device-resident factor that is almost always 1, e.g. the LM-head gradient's loss
+    // re-scale) is the identity: every thread sees the same scalar, so the whole grid leaves before touching memory
+    if (!accumulate && s == 1.f && static_cast<const void*>(x) == static_cast<const void*>(y)) return;
     const int64_t n8 = n >> 3;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const bool aligned =

@@ -212,6 +212,7 @@ class _ChunkedLinearXent(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, weight, labels, chunk, ignore_index, assumed_scale):
+        from deepspeed_b200.ops import gemm
         T, H = h.shape
         valid = (labels != ignore_index)
         n_valid = valid.sum().clamp(min=1).to(torch.float32)
@@ -219,11 +220,18 @@ class _ChunkedLinearXent(torch.autograd.Function):
         need_dh = h.requires_grad
         need_dw = weight.requires_grad
         dh = torch.empty_like(h) if need_dh else None
-        dw_tmp = None
+        # Where the weight gradient accumulates over the token chunks: straight in the ZeRO flat gradient view when this is
+        # the first contribution of the micro step (the chunk GEMMs' epilogues store / accumulate there: no [V, H] scratch,
+        # no copy); otherwise a per-call scratch (several forwards may precede their backwards, so it cannot be shared).
+        dw_tmp, direct = None, False
         if need_dw:
-            # per-call scratch (the caching allocator recycles the block): several forwards may precede
-            # their backwards, so this must not be shared between calls
-            dw_tmp = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
+            zo = _zo_of(weight)
+            if zo is not None and zo.grad_is_fresh(weight):
+                gv = zo.grad_view_for(weight)
+                if gv.dtype == weight.dtype and weight.is_cuda:
+                    dw_tmp, direct = gv, True
+            if dw_tmp is None:
+                dw_tmp = torch.empty(weight.shape, dtype=weight.dtype, device=weight.device)
         total = torch.zeros((), dtype=torch.float32, device=h.device)
         first = True
         for s in range(0, T, chunk):
@@ -233,21 +241,16 @@ class _ChunkedLinearXent(torch.autograd.Function):
             loss_rows, grad = softmax_xent_fwd_bwd(logits, labels[s:e].contiguous(), 1.0, inv_n, ignore_index, True)
             total = total + loss_rows.sum()
             if need_dh:
-                from deepspeed_b200.ops import gemm
                 gemm.matmul_nn(grad, weight, out=dh[s:e])
             if need_dw:
-                if first:
-                    from deepspeed_b200.ops import gemm
-                    gemm.matmul_tn(grad, hc, out=dw_tmp)
-                else:
-                    from deepspeed_b200.ops import gemm
-                    gemm.matmul_tn(grad, hc, out=dw_tmp, accumulate=True)  # accumulate in the GEMM epilogue
+                gemm.matmul_tn(grad, hc, out=dw_tmp, accumulate=not first)  # accumulate in the GEMM epilogue
             first = False
         ctx.weight_ref = weight
         ctx.assumed_scale = assumed_scale
         ctx.need_dw = need_dw
         ctx.dh = dh
         ctx.dw_tmp = dw_tmp
+        ctx.direct = direct
         return total / n_valid
 
     @staticmethod
@@ -260,7 +263,14 @@ class _ChunkedLinearXent(torch.autograd.Function):
         dw = None
         if ctx.need_dw:
             zo = _zo_of(w)
-            if zo is not None:
+            if ctx.direct and zo is not None:
+                # the gradient already sits in the flat view; fold the (almost always unit) upstream factor in place -- the
+                # kernel returns before touching memory when the device-resident factor is exactly 1
+                from deepspeed_b200.ops.kernels import flat_ops
+                flat = ctx.dw_tmp.view(-1)
+                flat_ops.scale_cast(flat, flat, scale=1.0, d_scale=r.reshape(1))
+                zo.mark_grad_ready(w)
+            elif zo is not None:
                 gv = zo.grad_view_for(w)
                 if zo.grad_is_fresh(w):
                     torch.mul(ctx.dw_tmp, r.to(ctx.dw_tmp.dtype), out=gv) if gv.dtype == ctx.dw_tmp.dtype else gv.copy_(
@@ -271,6 +281,7 @@ class _ChunkedLinearXent(torch.autograd.Function):
             else:
                 dw = ctx.dw_tmp * r.to(ctx.dw_tmp.dtype)
         ctx.dh = None
+        ctx.dw_tmp = None
         return dh, dw, None, None, None, None
 
 
