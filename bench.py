@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--offload-ratio", type=float, default=1.0, help="Twin-Flow: fraction of the optimizer stepped on the host")
     ap.add_argument("--zero-init", action="store_true", help="construct the model under zero.Init (needed when the bf16 "
                     "parameters do not fit one GPU, e.g. llama3-70b)")
+    ap.add_argument("--no-exposed", action="store_true", help="skip the 3 extra steps that measure exposed communication")
     ap.add_argument("--clip", type=float, default=0.0, help="gradient_clipping (both arms)")
     ap.add_argument("--gas", type=int, default=1, help="gradient_accumulation_steps (both arms); a timed step = one "
                     "optimizer step = GAS micro-batches")
@@ -320,7 +321,7 @@ def run_b200(args):
     # exposed (non-overlapped) communication: 2 extra, untimed-for-throughput steps with every compute-stream
     # wait on a collective bracketed by CUDA events (the bracket holds no kernels => elapsed == stall)
     exposed = None
-    if world > 1 and hasattr(engine.optimizer, "measure_exposed"):
+    if world > 1 and hasattr(engine.optimizer, "measure_exposed") and not args.no_exposed:
         step_dev(0)  # settle: absorbs the rank skew left by the timing epilogue (host-side all-reduce of the timings)
         torch.cuda.synchronize()
         ds.comm.barrier()

@@ -8,6 +8,7 @@
 // pointwise_ops}.cu (N8) and inference/v2 core_ops norms / gated activations (N9a).
 // All kernels are HBM-bound: one pass over the data with 16-byte accesses, the row cached in
 // registers between the statistics pass and the output pass, fp32 math.
+#include <cstdlib>
 #include "dsb_common.cuh"
 
 namespace dsb {
@@ -205,6 +206,148 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
                 for (int e = 0; e < kPer; ++e) d2[e] = db_acc[k][e];
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm backward, bulk-async edition (bf16, hidden % 1024 == 0, hidden <= 8192): the register-cached kernel above keeps
+// 4 CTAs x 3 rows in flight per SM and stalls every row on load -> reduce -> store; here one producer thread streams whole
+// rows (x | dy | dres) through a 4-stage shared-memory ring with cp.async.bulk + mbarrier complete_tx, 4 compute warps
+// consume them (conflict-free 16-byte shared loads), so ~190 KB per SM are in flight and loads never wait for math.
+// ------------------------------------------------------------------------------------------------
+namespace nb {
+constexpr int kStages = 4;
+constexpr int kComputeThreads = 128;
+__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n)); }
+__device__ __forceinline__ void mb_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+}  // namespace nb
+
+template <int VPT>  // 16-byte vectors per compute thread per tensor: hidden = 128 * VPT * 8
+__global__ void __launch_bounds__(nb::kComputeThreads + 32)
+rmsnorm_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ rstd_in,
+                        const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ dw_part, int rows, int hidden)
+{
+    using namespace nb;
+    extern __shared__ __align__(128) uint8_t sm_raw[];
+    const uint32_t row_bytes = static_cast<uint32_t>(hidden) * 2;
+    const int n_in = dres ? 3 : 2;
+    // [stage][x | dy | dres] rows, then the weight row, the reduction scratch and the barriers
+    uint8_t* ring = sm_raw;
+    __nv_bfloat16* w_s = reinterpret_cast<__nv_bfloat16*>(sm_raw + kStages * 3 * row_bytes);
+    float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(w_s) + row_bytes);
+    const uint32_t bar0 = s32(red + 8);
+    auto full = [&](int s) { return bar0 + 8 * s; };
+    auto empty = [&](int s) { return bar0 + 8 * (kStages + s); };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mb_init(full(s), 1);
+            mb_init(empty(s), kComputeThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int v = tid; v < hidden / 8; v += blockDim.x) reinterpret_cast<Vec16*>(w_s)[v] = ld_plain(w + v * 8);
+    __syncthreads();
+    const int n_my = rows > static_cast<int>(blockIdx.x) ? (rows - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+
+    if (warp == kComputeThreads / 32) {
+        // ---------------- producer: one thread issues the bulk copies ----------------
+        if (lane == 0) {
+            for (int i = 0; i < n_my; ++i) {
+                const int st = i % kStages;
+                const int64_t row = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+                mb_wait(empty(st), ((i / kStages) & 1) ^ 1);
+                mb_expect(full(st), n_in * row_bytes);
+                const uint32_t dst = s32(ring + st * 3 * row_bytes);
+                bulk_load(dst, x + row * hidden, row_bytes, full(st));
+                bulk_load(dst + row_bytes, dy + row * hidden, row_bytes, full(st));
+                if (dres) bulk_load(dst + 2 * row_bytes, dres + row * hidden, row_bytes, full(st));
+            }
+        }
+        return;
+    }
+    // ---------------- consumers ----------------
+    float dw_acc[VPT][8];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dw_acc[k][e] = 0.f;
+    for (int i = 0; i < n_my; ++i) {
+        const int st = i % kStages;
+        const int64_t row = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+        const float rstd = rstd_in[row];
+        mb_wait(full(st), (i / kStages) & 1);
+        const uint8_t* base = ring + st * 3 * row_bytes;
+        Vec16 cx[VPT], cdy[VPT], cres[VPT];
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int v = tid + k * kComputeThreads;
+            cx[k] = *reinterpret_cast<const Vec16*>(base + v * 16);
+            cdy[k] = *reinterpret_cast<const Vec16*>(base + row_bytes + v * 16);
+            if (dres) cres[k] = *reinterpret_cast<const Vec16*>(base + 2 * row_bytes + v * 16);
+            float xf[8], df[8], wf[8];
+            Elem<__nv_bfloat16>::unpack(cx[k], xf);
+            Elem<__nv_bfloat16>::unpack(cdy[k], df);
+            Elem<__nv_bfloat16>::unpack(reinterpret_cast<const Vec16*>(w_s)[v], wf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float xhat = xf[e] * rstd;
+                s2 = fmaf(df[e] * wf[e], xhat, s2);
+                dw_acc[k][e] = fmaf(df[e], xhat, dw_acc[k][e]);
+            }
+        }
+        // the row is in registers: give the slot back before the reduction / stores
+        __syncwarp();
+        if (lane == 0) mb_arrive(empty(st));
+        s2 = warp_reduce<SumOp>(s2);
+        const int slot = (i & 1) * 4;  // two rotating scratch rows: a fast warp may already be one row ahead
+        if (lane == 0) red[slot + warp] = s2;
+        asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
+        const float m2 = (red[slot] + red[slot + 1] + red[slot + 2] + red[slot + 3]) / hidden;
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+            const int v = tid + k * kComputeThreads;
+            float xf[8], df[8], wf[8], o[8];
+            Elem<__nv_bfloat16>::unpack(cx[k], xf);
+            Elem<__nv_bfloat16>::unpack(cdy[k], df);
+            Elem<__nv_bfloat16>::unpack(reinterpret_cast<const Vec16*>(w_s)[v], wf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = rstd * (df[e] * wf[e] - xf[e] * rstd * m2);
+            if (dres) {
+                float r[8];
+                Elem<__nv_bfloat16>::unpack(cres[k], r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += r[e];
+            }
+            st_plain(dx + row * hidden + v * 8, Elem<__nv_bfloat16>::pack(o));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        float* dst = dw_part + static_cast<int64_t>(blockIdx.x) * hidden + (tid + k * kComputeThreads) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e] = dw_acc[k][e];
     }
 }
 
@@ -609,6 +752,16 @@ DSB_EXPORT int dsb_norm_fwd(const void* x, const void* residual, const void* w, 
     return 0;
 }
 
+static bool dsb_norm_bwd_bulk_disabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DSB200_NORM_BWD_BULK");
+        v = (e && e[0] == '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 DSB_EXPORT int dsb_norm_bwd_grid(int rows)
 {
     // HBM-bound persistent kernel: exactly one wave of resident CTAs (4 per SM at 128 threads x ~120 registers); more
@@ -628,7 +781,43 @@ DSB_EXPORT int dsb_norm_bwd(const void* dy, const void* x, const void* w, const 
     if (hidden % per != 0) return -2;
     const int threads = norm_threads(hidden, per);
     if (threads > 512) return -2;
-    const int grid = dsb_norm_bwd_grid(rows);
+    int grid = dsb_norm_bwd_grid(rows);
+    const bool bulk = kind == 0 && dtype == kBF16 && hidden % 1024 == 0 && hidden <= 8192 && rows >= 1024 &&
+                      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dres) |
+                        reinterpret_cast<uintptr_t>(dx)) & 15) == 0 && !dsb_norm_bwd_bulk_disabled();
+    if (bulk) {
+        // 2 CTAs per SM: 4 stages x 3 rows each
+        const int vpt = hidden / 1024;
+        const size_t smem = static_cast<size_t>(nb::kStages) * 3 * hidden * 2 + hidden * 2 + 64 + 16 * nb::kStages + 64;
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        const int g2 = rows < kSmCountB200 * per_sm ? rows : kSmCountB200 * per_sm;
+        grid = g2;
+        cudaError_t e = cudaSuccess;
+#define DSB_LAUNCH_NB(V)                                                                                                    \
+    {                                                                                                                       \
+        static size_t attr = 0;                                                                                             \
+        if (smem > attr) {                                                                                                  \
+            e = cudaFuncSetAttribute(rmsnorm_bwd_bulk_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                     static_cast<int>(smem));                                                              \
+            attr = smem;                                                                                                    \
+        }                                                                                                                   \
+        rmsnorm_bwd_bulk_kernel<V><<<grid, nb::kComputeThreads + 32, smem, stream>>>(                                       \
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, rstd, (const __nv_bfloat16*)dres,    \
+            (__nv_bfloat16*)dx, dw_part, rows, hidden);                                                                     \
+    }
+        switch (vpt) {
+            case 1: DSB_LAUNCH_NB(1) break;
+            case 2: DSB_LAUNCH_NB(2) break;
+            case 3: DSB_LAUNCH_NB(3) break;
+            case 4: DSB_LAUNCH_NB(4) break;
+            case 5: DSB_LAUNCH_NB(5) break;
+            case 6: DSB_LAUNCH_NB(6) break;
+            case 7: DSB_LAUNCH_NB(7) break;
+            default: DSB_LAUNCH_NB(8) break;
+        }
+#undef DSB_LAUNCH_NB
+        if (e != cudaSuccess) return static_cast<int>(e);
+    } else
     DISPATCH_T(dtype, T, {
         if (kind == 0)
             norm_bwd_kernel<T, false><<<grid, threads, hidden * sizeof(T), stream>>>((const T*)dy, (const T*)x, (const T*)w, mean,

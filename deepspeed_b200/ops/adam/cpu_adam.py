@@ -34,6 +34,34 @@ def available() -> bool:
     return _load() is not None
 
 
+_threads_set = False
+
+
+def configure_threads(n=None):
+    """Give this rank's host optimizer its share of the cores.  ``torchrun`` exports ``OMP_NUM_THREADS=1`` for every rank;
+    honouring that would run the offload tier's Adam on one core.  ``DSB200_CPU_THREADS`` overrides; default =
+    usable cores // local world size (the reference's launcher does the same core split, ``launcher/launch.py:227``)."""
+    global _threads_set
+    lib = _load()
+    if lib is None:
+        return 0
+    if n is None:
+        import os
+        env = os.environ.get("DSB200_CPU_THREADS")
+        if env:
+            n = int(env)
+        else:
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except AttributeError:
+                cores = os.cpu_count() or 1
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("LOCAL_SIZE", "1")) or 1)
+            n = max(1, min(64, cores // max(1, local)))
+    lib.dsb_cpu_set_threads(int(n))
+    _threads_set = True
+    return int(n)
+
+
 def cpu_adam_flat(p, g, m, v, out=None, *, lr, beta1, beta2, eps, weight_decay, step, adamw=True, bias_correction=True,
                   grad_scale=1.0, d_gscale=None, d_skip=None):
     """Adam on flat host tensors (``p``/``m``/``v`` fp32)."""

@@ -18,6 +18,7 @@ from torch.utils.checkpoint import checkpoint
 
 from deepspeed_b200.ops.kernels import misc_ops as K
 from deepspeed_b200.ops.kernels import transformer_ops as T
+from deepspeed_b200.ops.linear import flat_linear  # forward + both backward GEMMs on the tcgen05 kernel (ops.gemm)
 
 
 class TransformerConfig:
@@ -129,7 +130,7 @@ class DeepSpeedTransformerLayer(nn.Module):
         c = self.config
         B, S, H = x.shape
         nh, d = c.heads, H // c.heads
-        qkv = F.linear(x, self.attn_qkvw)
+        qkv = flat_linear(x, self.attn_qkvw)
         qkv = K.bias_transform_0213(qkv, self.attn_qkvb, B, S, 3, nh, d) if not torch.is_grad_enabled() else \
             (qkv + self.attn_qkvb).view(B, S, 3, nh, d).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
@@ -144,7 +145,7 @@ class DeepSpeedTransformerLayer(nn.Module):
         return ctx.transpose(1, 2).reshape(B, S, H)
 
     def _ffn(self, x):
-        return T.bias_gelu(F.linear(x, self.inter_w), self.inter_b)
+        return T.bias_gelu(flat_linear(x, self.inter_w), self.inter_b)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None, layer_head_mask=None, encoder_hidden_states=None,
                 encoder_attention_mask=None, past_key_value=None, output_attentions=False, grads=None):
@@ -160,7 +161,7 @@ class DeepSpeedTransformerLayer(nn.Module):
             ctx = checkpoint(self._attention, a_in, attention_mask, use_reentrant=False)
         else:
             ctx = self._attention(a_in, attention_mask)
-        a_out = F.linear(ctx, self.attn_ow)
+        a_out = flat_linear(ctx, self.attn_ow)
         x1 = K.dropout(a_out, p, self.training, bias=self.attn_ob, residual=x, seed=self._seed)
         if c.pre_layer_norm:
             f_in = T.layer_norm(x1, self.norm_w, self.norm_b, c.layer_norm_eps)
@@ -168,7 +169,7 @@ class DeepSpeedTransformerLayer(nn.Module):
             x1 = T.layer_norm(x1, self.attn_nw, self.attn_nb, c.layer_norm_eps)
             f_in = x1
         inter = checkpoint(self._ffn, f_in, use_reentrant=False) if (ck and c.gelu_checkpoint) else self._ffn(f_in)
-        f_out = F.linear(inter, self.output_w)
+        f_out = flat_linear(inter, self.output_w)
         out = K.dropout(f_out, p, self.training, bias=self.output_b, residual=x1, seed=self._seed)
         if not c.pre_layer_norm:
             out = T.layer_norm(out, self.norm_w, self.norm_b, c.layer_norm_eps)

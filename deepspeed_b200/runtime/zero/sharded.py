@@ -223,6 +223,10 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         # the compute stream waits for them) and updated parameters come back on ``h2d_stream`` while the CPU optimizer is
         # already working on the next unit (reference stage3.py:1466-1527 async D2H of reduced shards,
         # swap_tensor/pipelined_optimizer_swapper.py:52)
+        if self.offload_optimizer:
+            from deepspeed_b200.ops.adam import cpu_adam as _cpu_adam
+            n_thr = _cpu_adam.configure_threads()
+            log_dist(f"host optimizer: {n_thr} threads per rank", ranks=[0])
         off_cuda = self.offload_optimizer and self.on_cuda
         self.d2h_stream = torch.cuda.Stream() if off_cuda else None
         self.h2d_stream = torch.cuda.Stream() if off_cuda else None
