@@ -755,16 +755,18 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = local / gm;
 }
 
-// Shared-memory plan of the CTA-pair kernel.  The dSwiGLU epilogue trades two pipeline stages for a double-buffered
-// staging area of the saved gate|up tiles (TMA-loaded by an otherwise idle warp while the MMAs of the tile still run).
+// Shared-memory plan of the CTA-pair kernel.  The SwiGLU / dSwiGLU epilogues trade two pipeline stages for a double-buffered
+// staging area of gate|up tiles: dSwiGLU TMA-LOADS the saved activations there (an otherwise idle warp, while the MMAs of
+// the tile still run), SwiGLU stages the gate and up chunks it saves for backward and TMA-STOREs them (full 128-byte lines,
+// asynchronous) next to the activation chunk.
 template <int EPI>
 struct Smem2 {
-    static constexpr int kStages = (EPI == EPI_DSWIGLU) ? 4 : STAGES2;
+    static constexpr int kStages = (EPI == EPI_DSWIGLU || EPI == EPI_SWIGLU) ? 4 : STAGES2;
     static constexpr uint32_t A = 0;
     static constexpr uint32_t B = A + kStages * A_STAGE_BYTES;
     static constexpr uint32_t C = B + kStages * B2_STAGE_BYTES;
     static constexpr uint32_t AUX = C + 2 * C_BUF_BYTES;  // [2 buffers][gate chunk | up chunk] of 128 rows x 64 columns
-    static constexpr uint32_t AUX_BYTES = (EPI == EPI_DSWIGLU) ? 2 * 2 * C_BUF_BYTES : 0;
+    static constexpr uint32_t AUX_BYTES = (EPI == EPI_DSWIGLU || EPI == EPI_SWIGLU) ? 2 * 2 * C_BUF_BYTES : 0;
     static constexpr uint32_t BAR = AUX + AUX_BYTES;
     static constexpr uint32_t TOTAL = BAR + 256 + 1024;
 };
@@ -801,7 +803,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
-        if constexpr (EPI == EPI_DSWIGLU) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_aux) : "memory");
+        if constexpr (EPI == EPI_DSWIGLU || EPI == EPI_SWIGLU) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_aux) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES2; ++s) {
@@ -1005,10 +1007,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             float u[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) u[e] = __uint_as_float(r2[j * 8 + e]);
-                            if (ep.out2 != nullptr && row_ok && colh + j * 8 < N) {
-                                __nv_bfloat16* dst = ep.out2 + static_cast<int64_t>(grow) * ep.ld_out2 + colh + j * 8;
-                                st_plain(dst, Elem<__nv_bfloat16>::pack(f));
-                                st_plain(dst + ep.inter, Elem<__nv_bfloat16>::pack(u));
+                            if (ep.out2 != nullptr) {
+                                // gate / up chunks saved for backward: staged like the output chunk, stored by TMA below
+                                uint8_t* grow_s = smem + L::AUX + buf * 2 * C_BUF_BYTES + row * 128;
+                                const uint32_t off = static_cast<uint32_t>(((h * 4 + j) ^ (row & 7)) << 4);
+                                *reinterpret_cast<Vec16*>(grow_s + off) = Elem<__nv_bfloat16>::pack(f);
+                                *reinterpret_cast<Vec16*>(grow_s + C_BUF_BYTES + off) = Elem<__nv_bfloat16>::pack(u);
                             }
 #pragma unroll
                             for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]) * u[e];
@@ -1043,6 +1047,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 epi_bar_sync();
                 if (etid == 0 && m0 < M) {
                     tma_store_2d(&map_c, sbase + SMEM2_C + buf * C_BUF_BYTES, col0, m0);
+                    if constexpr (EPI == EPI_SWIGLU) {
+                        if (ep.out2 != nullptr) {
+                            const uint32_t sg = sbase + L::AUX + buf * 2 * C_BUF_BYTES;
+                            tma_store_2d(&map_aux, sg, col0, m0);
+                            tma_store_2d(&map_aux, sg + C_BUF_BYTES, ep.inter + col0, m0);
+                        }
+                    }
                     tma_store_commit();
                 }
             }
@@ -1191,6 +1202,8 @@ DSB_EXPORT int dsb_gemm_bf16_2cta_ex(const void* a, const void* b, void* c, int 
     if ((rc = make_map(&mc, c, M, N, ldc, BM, CCHUNK))) return rc;
     CUtensorMap mx = mc;  // dSwiGLU: the saved gate|up activations [M, 2*inter], staged chunk by chunk by the loader warp
     if (epi == EPI_DSWIGLU && (rc = make_map(&mx, aux, M, static_cast<uint64_t>(2) * inter, ld_aux, BM, CCHUNK))) return rc;
+    if (epi == EPI_SWIGLU && out2 && (rc = make_map(&mx, out2, M, static_cast<uint64_t>(2) * inter, ld_out2, BM, CCHUNK)))
+        return rc;
     if (!g_attr2_set) {
         int dev = 0;
         cudaGetDevice(&dev);
