@@ -28,6 +28,7 @@ class CudaKernelsBuilder(CUDAOpBuilder):
         "cuda/gemm_sm100.cu",
         "cuda/attention.cu",
         "cuda/attn_sm100.cu",
+        "cuda/attn_bias.cu",
         "cuda/moe_symm.cu",
         "cuda/wq_gemm.cu",
         "cuda/wq_tc_gemm.cu",

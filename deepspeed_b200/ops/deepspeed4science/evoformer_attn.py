@@ -2,10 +2,13 @@
 ``ops/deepspeed4science/evoformer_attn.py`` over the CUTLASS kernels in ``csrc/deepspeed4science`` N12).
 
 Inputs ``Q/K/V [*, L, H, D]`` with arbitrary leading dims (MSA row / column, pair), ``biases``: a mask bias
-broadcast as ``[*, 1, 1, L]`` and a pair bias ``[1.., H, L, L]``.  The fused flash kernel (SDPA with an additive
-mask) does the work; the bias gradients — the part the reference needs a custom backward for — come from a
-custom autograd function that recomputes the probabilities chunk-wise so the [*, H, L, L] score tensor is never
-materialised for more than ``chunk`` leading rows at a time.
+broadcast as ``[*, 1, 1, L]`` and a pair bias ``[1.., H, L, L]``.
+
+On a GPU with bf16 / fp16 operands and head dim 16 / 32 / 64 (every Evoformer configuration the reference kernel accepts:
+``evoformer_attn.py:36`` asserts ``D <= 64``) the work is done by the hand-written biased flash-attention kernels of
+``csrc/cuda/attn_bias.cu``: forward with both biases folded into the online softmax, backward producing dQ / dK / dV and
+both bias gradients (fp32 accumulation) without ever materialising the ``[*, H, L, L]`` scores.  Other dtypes / head dims
+and the CPU use the chunked PyTorch formulation below (SDPA forward, chunk-wise recomputed backward).
 """
 import torch
 import torch.nn.functional as F
@@ -15,10 +18,55 @@ def _flat(x):
     return x.reshape(-1, *x.shape[-3:])
 
 
+def _native_plan(q, k, v, bias1, bias2):
+    """Arguments for the native kernels, or None when the configuration needs the PyTorch path."""
+    from deepspeed_b200.ops.kernels import attn_bias as AB
+    if not (q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and q.shape[-1] in AB.HEAD_DIMS and q.dim() >= 4
+            and k.shape == q.shape and v.shape == q.shape):
+        return None
+    lead = q.shape[:-3]
+    L, H, D = q.shape[-3:]
+    nb = 1
+    for x in lead:
+        nb *= x
+    if nb > AB.MAX_GRID:
+        return None
+    to4 = lambda t: t.reshape(nb, L, H, D).permute(0, 2, 1, 3)  # logical [NB, H, L, D], no copy for contiguous inputs
+    b1 = b2 = None
+    if bias1 is not None:
+        if bias1.shape[-3:-1] != (1, 1) or bias1.shape[-1] != L:
+            return None
+        b1 = bias1.expand(*lead, 1, 1, L).reshape(nb, L)
+    if bias2 is not None:
+        # pair bias [lead' , H, L, L] where lead' broadcasts over the trailing leading dims (N of [B, N]): the kernel shares
+        # one bias2 batch entry between `nb / B2` consecutive attention batches
+        bl = bias2.shape[:-3]
+        if len(bl) != len(lead) or tuple(bias2.shape[-3:]) != (H, L, L):
+            return None
+        n_b2, seen_one = 1, False
+        for have, want in zip(bl, lead):
+            if have == want and not seen_one:
+                n_b2 *= have
+            elif have == 1:
+                seen_one = True
+            else:
+                return None
+        b2 = bias2.reshape(n_b2, H, L, L)
+    return to4(q), to4(k), to4(v), b1, b2
+
+
 class EvoformerFusedAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, bias1=None, bias2=None, chunk=64):
+        plan = _native_plan(q, k, v, bias1, bias2)
+        ctx.native = plan is not None
+        if plan is not None:
+            from deepspeed_b200.ops.kernels import attn_bias as AB
+            q4, k4, v4, b1, b2 = plan
+            o4, lse = AB.forward(q4, k4, v4, b1, b2)
+            ctx.save_for_backward(q, k, v, bias1, bias2, o4, lse)
+            return o4.permute(0, 2, 1, 3).reshape(q.shape)
         # [*, L, H, D] -> [*, H, L, D]
         qt, kt, vt = (t.transpose(-2, -3) for t in (q, k, v))
         lead = qt.shape[:-3]
@@ -35,6 +83,20 @@ class EvoformerFusedAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, do):
+        if ctx.native:
+            from deepspeed_b200.ops.kernels import attn_bias as AB
+            q, k, v, bias1, bias2, o4, lse = ctx.saved_tensors
+            q4, k4, v4, b1, b2 = _native_plan(q, k, v, bias1, bias2)
+            L, H, D = q.shape[-3:]
+            do4 = do.reshape(-1, L, H, D).permute(0, 2, 1, 3)
+            dq, dk, dv, db1, db2 = AB.backward(do4, q4, k4, v4, o4, lse, b1, b2, need_db1=b1 is not None and ctx.needs_input_grad[3],
+                                               need_db2=b2 is not None and ctx.needs_input_grad[4])
+            un = lambda t: t.permute(0, 2, 1, 3).reshape(q.shape)
+            if db1 is not None:  # sum over the leading dims bias1 broadcasts over, back to its own shape
+                db1 = db1.view(*q.shape[:-3], 1, 1, L).sum_to_size(bias1.shape).to(bias1.dtype)
+            if db2 is not None:
+                db2 = db2.view(bias2.shape).to(bias2.dtype)
+            return un(dq), un(dk), un(dv), db1, db2, None
         q, k, v, bias1, bias2, o = ctx.saved_tensors
         dq, dk, dv, db1, db2 = attention_bwd(do, q, k, v, o.transpose(-2, -3), None, bias1, bias2,
                                              bias1 is not None and ctx.needs_input_grad[3],

@@ -1,10 +1,12 @@
 """Block-sparse self attention (reference ``ops/sparse_attention/sparse_self_attention.py`` +
 Triton ``matmul.py``/``softmax.py``).
 
-B200 formulation: rows of the block layout are grouped by their set of visible key blocks; for each q-block row
-the visible K/V blocks are *gathered* into a dense [q_block, n_vis*block] problem and run through the fused SDPA
-(flash) kernel, so the work scales with the number of non-zero blocks, runs on tensor cores, and is
-differentiable through autograd.  Rows with identical visibility patterns are batched together.
+B200 formulation: on the GPU (bf16 / fp16, head dim 16 / 32 / 64, power-of-two block >= 16) ONE flash-attention kernel
+(``csrc/cuda/attn_bias.cu``) replaces the reference's SDD-matmul -> block softmax -> DSD-matmul chain: the layout is read
+inside the kernel, score tiles without any active block are skipped (work scales with the number of non-zero blocks),
+inactive blocks inside a tile are masked, and the key-padding / attention masks ride the kernel's two additive-bias slots;
+the matching backward kernels give dQ / dK / dV.  The gather + SDPA formulation below remains for CPU / fp32 / other shapes:
+rows of the block layout are grouped by their number of visible key blocks and each group is one batched dense problem.
 """
 import torch
 import torch.nn as nn
@@ -19,6 +21,16 @@ def block_sparse_attention(q, k, v, layout, block, scale=None, key_padding_mask=
     B, H, S, D = q.shape
     nb = S // block
     scale = scale if scale is not None else D**-0.5
+    if _native_ok(q, k, v, block):
+        from deepspeed_b200.ops.kernels.attn_bias import biased_attention
+        b1 = b2 = None
+        if key_padding_mask is not None:
+            kpm = key_padding_mask.float().view(B, S)
+            b1 = (kpm if key_padding_mask_mode == "add" else (1.0 - kpm) * -10000.0).to(q.dtype)
+        if attn_mask is not None:
+            am = attn_mask.float().view(1, 1, S, S)
+            b2 = (am if attn_mask_mode == "add" else (1.0 - am) * -10000.0).to(q.dtype)
+        return biased_attention(q, k, v, b1, b2, layout, block, False, scale)
     lay = layout.to(torch.bool)
     out = torch.zeros_like(q)
     qb = q.view(B, H, nb, block, D)
@@ -56,6 +68,12 @@ def block_sparse_attention(q, k, v, layout, block, scale=None, key_padding_mask=
     return out
 
 
+def _native_ok(q, k, v, block):
+    from deepspeed_b200.ops.kernels import attn_bias as AB
+    return (AB.supported(q, k, v) and q.shape == k.shape == v.shape and block >= 16 and (block & (block - 1)) == 0
+            and q.shape[2] % block == 0)
+
+
 class SparseSelfAttention(nn.Module):
 
     def __init__(self, sparsity_config=SparsityConfig(num_heads=4), key_padding_mask_mode="add", attn_mask_mode="mul",
@@ -75,6 +93,16 @@ class SparseSelfAttention(nn.Module):
             raise ValueError(f"Sequence Length, {L}, needs to be dividable by Block size {self.sparsity_config.block}!")
         nb = L // self.sparsity_config.block
         return self.master_layout[..., :nb, :nb].cpu()
+
+    def _device_layout(self, L, device):
+        """uint8 copy of the layout on ``device`` (cached per sequence length: the kernel reads it every call)."""
+        cache = self.__dict__.setdefault("_layout_cache", {})
+        key = (L, str(device))
+        pending = (self._need_layout_synchronization and torch.distributed.is_available()
+                   and torch.distributed.is_initialized())  # the first call after init broadcasts rank 0's layout
+        if key not in cache or pending:
+            cache[key] = self.get_layout(L).to(device=device, dtype=torch.uint8).contiguous()
+        return cache[key]
 
     def transpose_key_for_scores(self, x, L):
         return x  # kept for API parity: no explicit key transpose is needed by this formulation
@@ -105,6 +133,6 @@ class SparseSelfAttention(nn.Module):
             mode = "add"
         else:
             mode = self.attn_mask_mode
-        layout = self.get_layout(tgt_len).to(query.device)
+        layout = self._device_layout(tgt_len, query.device)
         return block_sparse_attention(query, key, value, layout, self.sparsity_config.block, head_dim**-0.5,
                                       key_padding_mask, attn_mask, self.key_padding_mask_mode, mode)
