@@ -199,14 +199,15 @@ def hf_llama(torch, mc, grad_ckpt=False):
     return m
 
 
-def pick_checkpoint_layers(torch, cfg, micro_batch, seq, world, stage, explicit):
+def pick_checkpoint_layers(torch, cfg, micro_batch, seq, world, stage, explicit, offload=False):
     """Activation-recompute policy: keep everything when it fits in HBM, else checkpoint just enough
     layers.  Model states per rank (ZeRO-3): (2 + 4 + 4 + 4) B/param / world (+2 B/param gathered pool)."""
     if explicit is not None:
         return explicit
     free, total = torch.cuda.mem_get_info()
     n = cfg.num_parameters()
-    states = n * 14 / (world if stage >= 1 else 1) + (n * 2 if stage < 3 or world == 1 else 4 * 2 * 0.6e9)
+    per_param = 2 if offload else 14  # host offload leaves only the bf16 shard (+ transient gradient shards) on the device
+    states = n * per_param / (world if stage >= 1 else 1) + (n * 2 if stage < 3 or world == 1 else 4 * 2 * 0.6e9)
     tokens = micro_batch * seq
     per_layer = tokens * cfg.hidden_size * 2 * 17.5 * 1.05  # ~17.5 h-sized bf16 tensors saved per layer
     ckpt_layer = tokens * cfg.hidden_size * 2 * 2.0
@@ -241,7 +242,7 @@ def run_b200(args):
     else:
         cfg = llama_config(args.model, **over)
         cfg.checkpoint_layers = pick_checkpoint_layers(torch, cfg, args.micro_batch, args.seq, world, args.zero_stage,
-                                                       args.checkpoint_layers)
+                                                       args.checkpoint_layers, offload=args.offload != "none")
     hf = args.model_impl == "hf"
     zero = {"stage": args.zero_stage, "overlap_comm": True}
     if args.fused_collectives != "auto":

@@ -324,10 +324,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
     def _empty(self, n, dtype, device=None, pin=False):
         dev = device or self.device
-        t = torch.empty(n, dtype=dtype, device=dev)
         if pin and torch.device(dev).type == "cpu" and torch.cuda.is_available():
-            t = t.pin_memory()
-        return t
+            # page-locked from the start: `.pin_memory()` on a pageable tensor would hold BOTH copies for a moment, which at
+            # Llama-70B scale is an extra ~70 GB of host memory per arena and rank
+            return torch.empty(n, dtype=dtype, device="cpu", pin_memory=True)
+        return torch.empty(n, dtype=dtype, device=dev)
 
     def _allocate(self, broadcast_init):
         dev = self.device

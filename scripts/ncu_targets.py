@@ -21,6 +21,37 @@ if which == "attn":
         o, lse = A.fwd(q, k, v, B, S, hq, hkv, causal=True)
         A.bwd(torch.randn_like(o), q, k, v, o, lse, B, S, hq, hkv, causal=True)
     torch.cuda.synchronize()
+elif which == "evo":
+    from deepspeed_b200.ops.kernels import attn_bias as AB
+    NB, H, L, D = 128, 8, 256, 32
+    q, k, v = (torch.randn(NB, L, H, D, device=d, dtype=torch.bfloat16).permute(0, 2, 1, 3) for _ in range(3))
+    b1 = torch.zeros(NB, L, device=d, dtype=torch.bfloat16)
+    b2 = torch.randn(1, H, L, L, device=d, dtype=torch.bfloat16)
+    for _ in range(2):
+        o, lse = AB.forward(q, k, v, b1, b2)
+        AB.backward(torch.randn_like(o), q, k, v, o, lse, b1, b2, need_db1=True, need_db2=True)
+    torch.cuda.synchronize()
+elif which == "mlp":
+    from deepspeed_b200.ops import gemm as G
+    x = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16)
+    w_gu = torch.randn(2 * 14336, 4096, device=d, dtype=torch.bfloat16) * 0.02
+    w_dn = torch.randn(4096, 14336, device=d, dtype=torch.bfloat16) * 0.02
+    for _ in range(2):
+        flush.zero_()
+        act, gu = G.gate_up_swiglu(x, w_gu, save_gate_up=True)
+        dy = torch.randn(8192, 4096, device=d, dtype=torch.bfloat16)
+        G.down_dx_dswiglu(dy, w_dn, gu)
+    torch.cuda.synchronize()
+elif which == "wqtc":
+    from deepspeed_b200.inference.quantization import layers as QL
+    w = torch.randn(14336, 4096, device=d, dtype=torch.bfloat16) * 0.02
+    x = torch.randn(256, 4096, device=d, dtype=torch.bfloat16)
+    for mode in ("int8", "fp6"):
+        qw = QL.quantize_weight(w, mode=mode, group_size=128)
+        for _ in range(2):
+            flush.zero_()
+            QL.wq_tc_linear(x, qw)
+    torch.cuda.synchronize()
 elif which == "adam":
     n = 256 * 1024 * 1024
     p = torch.randn(n, device=d)
