@@ -5,7 +5,7 @@ import random
 
 from ..utils import flatten
 from .base_tuner import BaseTuner
-from .cost_model import RidgeCostModel
+from .cost_model import XGBoostCostModel
 
 INIT_NUM = 2
 
@@ -14,7 +14,8 @@ class ModelBasedTuner(BaseTuner):
 
     def __init__(self, exps, resource_manager, metric, tuning_space=None):
         super().__init__(exps, resource_manager, metric)
-        self.cost_model = RidgeCostModel()
+        # boosted trees (the reference's XGBoost model, in tree) once enough configurations were measured; ridge before
+        self.cost_model = XGBoostCostModel("reg")
         self.visited, self.evaluated = set(), []
         self.keys = sorted({k for e in exps for k, v in flatten(e["ds_config"]).items()
                             if isinstance(v, (numbers.Number, bool))})

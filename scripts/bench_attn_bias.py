@@ -6,6 +6,9 @@ import math
 import os
 import statistics
 
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 

@@ -8,3 +8,6 @@ timeout 1500 $TR --master-port 29611 bench.py --gpus 4 --model llama3-70b --offl
 echo "l70b rc=$?" >> gpurun_out/r13_status.txt
 free -g >> gpurun_out/r13_host.txt
 tail -c 1500 gpurun_out/r13_l70b.json; echo; tail -8 gpurun_out/r13_l70b.err | cut -c1-300; cat gpurun_out/r13_status.txt
+timeout 900 python -m pytest tests/gpu/test_zeropp_multi_gpu.py -x -q > gpurun_out/r13_zeropp.log 2>&1
+echo "zeropp rc=$?" >> gpurun_out/r13_status.txt
+tail -5 gpurun_out/r13_zeropp.log; cat gpurun_out/r13_status.txt

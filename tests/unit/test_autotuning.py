@@ -80,3 +80,21 @@ def test_cost_model_ranks():
     m.fit(X[:30], y[:30])
     pred = m.predict(X[30:])
     assert np.corrcoef(pred, y[30:])[0, 1] > 0.98
+
+
+@pytest.mark.parametrize("loss", ["reg", "rank"])
+def test_boosted_trees_cost_model_ranks_nonlinear_surface(loss):
+    """The in-tree stand-in for the reference's XGBoost cost model: depth-3 boosted trees must rank a throughput surface
+    with a threshold (OOM-like cliff) that a linear model cannot express."""
+    import numpy as np
+    from deepspeed_b200.autotuning.tuner import BoostedTreesCostModel
+    rng = np.random.default_rng(1)
+    X = rng.uniform(0, 1, (80, 4))
+    y = 100 * X[:, 0] * (X[:, 1] < 0.6) + 20 * X[:, 2] + 5.0
+    m = BoostedTreesCostModel(loss)
+    m.fit(X[:60], y[:60])
+    pred = m.predict(X[60:])
+    order_true, order_pred = np.argsort(np.argsort(y[60:])), np.argsort(np.argsort(pred))
+    rho = np.corrcoef(order_true, order_pred)[0, 1]
+    assert rho > 0.8, rho
+    assert int(np.argmax(pred)) in set(np.argsort(y[60:])[-3:].tolist())
