@@ -127,6 +127,25 @@ def dist_env(args):
     return rank, world, local
 
 
+def host_memory_limit():
+    """Bytes of host memory this process tree may use: min(MemAvailable, cgroup v2 / v1 limit)."""
+    have = float("inf")
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                have = float(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit():
+                have = min(have, float(v))
+        except OSError:
+            pass
+    return have
+
+
 def timed_loop(torch, dist_mod, world, steps, body):
     """barrier + sync, K steps under CUDA events, sync + barrier; returns max-over-ranks seconds."""
     if world > 1:
@@ -249,6 +268,16 @@ def run_b200(args):
         zero["b200_fused_collectives"] = args.fused_collectives == "on"
     ds_config = ds_config_for(args, zero)
     hf_ckpt = bool(args.checkpoint_layers)
+    if args.offload != "none":
+        # host-offload sizing guard: fp32 master + two moments + fp32 gradient shard = 16 B/param of PINNED host memory for the
+        # offloaded fraction, summed over the ranks of this node.  Refuse (cleanly) rather than take the box down.
+        need = cfg.num_parameters() * 16.0 * args.offload_ratio + 8e9 * world
+        have = host_memory_limit()
+        if need > 0.85 * have:
+            if rank == 0:
+                print(json.dumps({"impl": "b200", "unavailable": f"host offload needs {need / 1e9:.0f} GB of pinned memory, "
+                                  f"the box allows {have / 1e9:.0f} GB", "config": {"model": args.model, "n_gpus": world}}))
+            return
 
     def build():
         if hf:
