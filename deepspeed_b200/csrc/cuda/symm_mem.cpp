@@ -447,3 +447,44 @@ DSB_EXPORT int dsb_symm_all_gather_ce(void* const* shards, void* full, int64_t s
     }
     return 0;
 }
+
+// ---- exact-size page-locked host arenas ------------------------------------------------------------------------------------
+// The ZeRO-Offload tier keeps fp32 master weights, Adam moments and the reduced gradient shard in pinned host memory -- four
+// arenas of (parameters / ranks) * 4 bytes each.  torch's CachingHostAllocator rounds every request up to the next power of
+// two (a 70 GB arena becomes 128 GB), which at Llama-70B scale overshoots the node's memory; these entry points give the
+// arena exactly the bytes it asked for.  The pages are first-touched by several threads (page faulting is what dominates a
+// >10 GB allocation) and then registered with the driver.
+DSB_EXPORT int dsb_pinned_alloc(void** out, int64_t bytes, int touch_threads)
+{
+    if (bytes <= 0 || out == nullptr) return -2;
+    void* p = nullptr;
+    const size_t align = 2u << 20;
+    const size_t sz = (static_cast<size_t>(bytes) + align - 1) / align * align;
+    if (posix_memalign(&p, align, sz) != 0) return -ENOMEM;
+    const int nt = touch_threads > 0 ? touch_threads : 1;
+    std::vector<std::thread> th;
+    const size_t per = (sz / 4096 + nt - 1) / nt * 4096;
+    for (int t = 0; t < nt; ++t) {
+        th.emplace_back([=]() {
+            char* b = static_cast<char*>(p);
+            const size_t lo = static_cast<size_t>(t) * per, hi = lo + per < sz ? lo + per : sz;
+            for (size_t i = lo; i < hi; i += 4096) b[i] = 0;
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaError_t e = cudaHostRegister(p, sz, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        free(p);
+        return static_cast<int>(e);
+    }
+    *out = p;
+    return 0;
+}
+
+DSB_EXPORT int dsb_pinned_free(void* p)
+{
+    if (p == nullptr) return 0;
+    cudaError_t e = cudaHostUnregister(p);
+    free(p);
+    return static_cast<int>(e);
+}

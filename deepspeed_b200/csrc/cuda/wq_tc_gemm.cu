@@ -4,13 +4,14 @@
 //
 // The packed weights are the only large operand, so they go where tcgen05 wants the 128-row operand ("swap AB"):
 //   D^T[128 features, M tokens] = Wdq[128 features, K] * x[M tokens, K]^T
-//   * warps 2-5 (128 threads, one FEATURE row each) stream their row's packed bytes straight from global memory (16-byte
-//     loads, 64 K-elements per step), decode to bf16 with the group scale folded in, and write the 128-byte-swizzled K-major
-//     A tile in shared memory -- the dequantised weight never exists in HBM (the reference's FP6-LLM kernel dequantises in
+//   * warps 2-9 (256 threads, two per FEATURE row, 32 K-elements each per step) stream their row's packed bytes straight from
+//     global memory one pipeline step AHEAD into registers (the load latency of step k+1 hides behind the decode of step k),
+//     decode to bf16 with the group scale folded in, and write the 128-byte-swizzled K-major A tile in shared memory -- the
+//     dequantised weight never exists in HBM (the reference's FP6-LLM kernel dequantises in
 //     registers for mma.sync, inference/v2/kernels/core_ops/cuda_linear/include/kernel_matmul.cuh:22; cutlass mixed_gemm
 //     does the same for int8/int4)
-//   * warp 0 TMA-loads the activation tile x[M_tile, 64] (B operand, N = M_tile <= 128), warp 1's elected thread issues
-//     tcgen05.mma (M = 128, N = M_tile, K = 16) into TMEM; 4-stage mbarrier ring
+//   * warp 0 TMA-loads the activation tile x[M_tile, 64] (B operand, N = M_tile <= 256: up to 256 rows reuse one pass over
+//     the weights), warp 1's elected thread issues tcgen05.mma (M = 128, N = M_tile, K = 16) into TMEM; 4-stage mbarrier ring
 //   * epilogue: the feature-row threads read their accumulator row, add the bias and store the transposed tile (lanes of a
 //     warp write 32 consecutive features of one token: 64-byte segments).
 // For M <= 32 the mma.sync kernel of wq_gemm.cu (no padding waste) stays faster; for very large M dequantise-once + the
@@ -25,9 +26,10 @@ using namespace dsb::tc;
 
 constexpr int BF = 128;   // features per CTA (MMA M)
 constexpr int BK = 64;    // K elements per pipeline step (one 128-byte swizzle row of bf16)
-constexpr int BT = 128;   // max tokens per CTA (MMA N)
+constexpr int BT = 256;   // max tokens per CTA (MMA N)
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kProducerWarps = 8;
+constexpr int kThreads = 64 + kProducerWarps * 32;
 constexpr uint32_t A_BYTES = BF * BK * 2;  // 16 KiB
 constexpr uint32_t B_BYTES = BT * BK * 2;  // 16 KiB
 constexpr uint32_t SM_A = 0, SM_B = kStages * A_BYTES, SM_BAR = SM_B + kStages * B_BYTES;
@@ -138,14 +140,14 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
     if (warp == 0 && lane == 0) {
         prefetch_map(&map_x);
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(a_full(s), 4);
+            mbar_init(a_full(s), kProducerWarps);
             mbar_init(b_full(s), 1);
             mbar_init(empty(s), 1);
         }
         mbar_init(acc_done, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -179,43 +181,53 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
             umma_commit(acc_done);
         }
     } else {
-        // ---- dequantising producers: thread = feature row ------------------------------------------------------------------
-        const int q4 = warp & 3;
+        // ---- dequantising producers: two threads per feature row, each owns 32 of the 64 K elements of a step ------------------
+        const int q4 = warp & 3;             // TMEM lane quadrant this warp may read in the epilogue
+        const int hk = (warp - 2) >> 2;      // which half of the K step (and of the token columns in the epilogue)
         const int r = q4 * 32 + lane;
         const int feat = f0 + r;
         const bool feat_ok = feat < p.N;
         constexpr int B8 = bytes_per_8<MODE>();
+        constexpr int NR = 4 * B8 / 8;       // 8-byte words of packed weights per thread and step
         const int64_t row_bytes = static_cast<int64_t>(p.K) / 8 * B8;
         const int64_t slab = static_cast<int64_t>(expert) * p.N;  // rows of the stacked [E, N, K] weight before this expert
-        const uint8_t* wrow = p.wq + (slab + (feat_ok ? feat : 0)) * row_bytes;
+        const uint8_t* wrow = p.wq + (slab + (feat_ok ? feat : 0)) * row_bytes + hk * 4 * B8;
         const float* srow = p.scales + (slab + (feat_ok ? feat : 0)) * (p.K / p.group_size);
+        uint2 cur[NR], nxt[NR];
+        float sc_cur, sc_nxt = 0.f;
+        auto fetch = [&](int kb, uint2* dst, float& sc) {
+            const uint2* g = reinterpret_cast<const uint2*>(wrow + static_cast<int64_t>(kb) * (BK / 8) * B8);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) dst[i] = feat_ok ? __ldg(g + i) : make_uint2(0u, 0u);
+            sc = feat_ok ? __ldg(srow + (kb * BK) / p.group_size) : 0.f;
+        };
+        fetch(0, cur, sc_cur);
         for (int kb = 0; kb < num_k; ++kb) {
             const int st = kb % kStages;
+            if (kb + 1 < num_k) fetch(kb + 1, nxt, sc_nxt);  // in flight while this step is decoded
             mbar_wait(empty(st), ((kb / kStages) & 1) ^ 1);
-            const float scale = feat_ok ? srow[(kb * BK) / p.group_size] : 0.f;
-            const uint8_t* src = wrow + static_cast<int64_t>(kb) * (BK / 8) * B8;
             uint8_t* arow = smem + SM_A + st * A_BYTES + r * 128;
+            const uint8_t* raw = reinterpret_cast<const uint8_t*>(cur);
 #pragma unroll
-            for (int c = 0; c < BK / 8; ++c) {
+            for (int j = 0; j < 4; ++j) {
                 float f[8];
-                if (feat_ok) {
-                    decode8<MODE>(src + c * B8, scale, f);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = 0.f;
-                }
+                decode8<MODE>(raw + j * B8, sc_cur, f);
+                const int c = hk * 4 + j;
                 *reinterpret_cast<Vec16*>(arow + ((c ^ (r & 7)) << 4)) = Elem<__nv_bfloat16>::pack(f);
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full(st));
+#pragma unroll
+            for (int i = 0; i < NR; ++i) cur[i] = nxt[i];
+            sc_cur = sc_nxt;
         }
         // ---- epilogue: transposed store of D^T[feature r, tokens] --------------------------------------------------------------
         mbar_wait(acc_done, 0);
         tc_fence_after();
         const float bias = (p.bias != nullptr && feat_ok) ? __bfloat162float(p.bias[slab + feat]) : 0.f;
         const uint32_t lane_addr = static_cast<uint32_t>(q4 * 32) << 16;
-        for (int c = 0; c < mt; c += 32) {
+        for (int c = hk * 32; c < mt; c += 64) {  // the two threads of a feature row alternate 32-token column blocks
             uint32_t v[32];
             tmem_ld_32x32(tmem + lane_addr + c, v);
             tmem_ld_wait();
@@ -230,7 +242,7 @@ wq_tc_kernel(const __grid_constant__ CUtensorMap map_x, const Params p)
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 128);
+    if (warp == 1) tmem_dealloc(tmem, BT);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -280,7 +292,7 @@ DSB_EXPORT int dsb_wq_tc_gemm(const void* x, const void* wq, const float* scales
 }
 
 // Grouped (MoE) form: x / out rows sorted by expert, `offsets` int32 [E + 1] ON THE DEVICE, wq / scales / bias stacked [E, ...].
-// M = total rows (an upper bound for every expert's row count: the grid covers ceil(M / 128) token tiles per expert and CTAs
+// M = total rows (an upper bound for every expert's row count: the grid covers ceil(M / 256) token tiles per expert and CTAs
 // beyond an expert's range exit at once) -- no host synchronisation, CUDA-graph capturable.
 DSB_EXPORT int dsb_wq_tc_gemm_grouped(const void* x, const void* wq, const float* scales, const void* bias, void* out,
                                       const int* offsets, int E, int M, int N, int K, int mode, int group_size, int ldx,

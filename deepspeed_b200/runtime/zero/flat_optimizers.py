@@ -26,9 +26,11 @@ class FlatOptimizer:
 
     def init_state(self, numel: int, device, dtype=torch.float32, pin=False):
         for n in self.state_names:
-            t = torch.zeros(numel, dtype=dtype, device=device)
-            if pin and t.device.type == "cpu" and torch.cuda.is_available():
-                t = t.pin_memory()
+            if pin and torch.device(device).type == "cpu" and torch.cuda.is_available():
+                from deepspeed_b200.ops.pinned import pinned_empty
+                t = pinned_empty(numel, dtype).zero_()  # exact-size page-locked arena (see ops/pinned.py)
+            else:
+                t = torch.zeros(numel, dtype=dtype, device=device)
             self.state[n] = t
 
     def step_segment(self, s: int, e: int, p, g, out, group: dict, step: int, grad_scale=1.0, d_gscale=None,

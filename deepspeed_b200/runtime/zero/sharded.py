@@ -327,7 +327,9 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         if pin and torch.device(dev).type == "cpu" and torch.cuda.is_available():
             # page-locked from the start: `.pin_memory()` on a pageable tensor would hold BOTH copies for a moment, which at
             # Llama-70B scale is an extra ~70 GB of host memory per arena and rank
-            return torch.empty(n, dtype=dtype, device="cpu", pin_memory=True)
+            # (and not through torch's pinned allocator for big arenas: it rounds sizes up to a power of two)
+            from deepspeed_b200.ops.pinned import pinned_empty
+            return pinned_empty(n, dtype)
         return torch.empty(n, dtype=dtype, device=dev)
 
     def _allocate(self, broadcast_init):

@@ -4,7 +4,10 @@
 The engine's autotuning hooks measure steps [start_profile_step, end_profile_step) and exit; outside an autotuning
 experiment the loop simply trains for ``--steps`` steps."""
 import argparse
+import os
+import sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a source checkout
 import torch
 
 import deepspeed_b200 as ds

@@ -208,3 +208,46 @@ def test_hybrid_engine_generate_between_training_steps_gpu():
     # bf16 kernels vs the training-path kernels: near ties may flip a token, the bulk must agree
     assert min(agree) > 0.8, agree
     assert eng._packed_at_step == 2 and eng.get_latency_report()["generate_s"] > 0
+
+
+def test_exact_size_pinned_arena_and_offload_step():
+    """ops/pinned.py: big offload arenas are page-locked at their exact size (torch's pinned allocator rounds to a power of
+    two), report ``is_pinned`` and copy asynchronously; a ZeRO-3 + CPU-offload step runs on top of them."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.ops import pinned
+    n = (300 << 20) // 4 + 12345  # just over the native-allocation threshold, deliberately not a power of two
+    before = pinned.live_bytes()
+    t = pinned.pinned_empty(n, torch.float32)
+    assert t.is_pinned() and t.numel() == n and pinned.live_bytes() - before == n * 4
+    src = torch.randn(n, device="cuda")
+    t.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(t, src.cpu())
+    back = t.to("cuda", non_blocking=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(back, src)
+    del t, back
+    import gc
+    gc.collect()
+    assert pinned.live_bytes() == before
+    pinned_threshold = pinned.THRESHOLD_BYTES
+    pinned.THRESHOLD_BYTES = 1 << 16  # force the engine's (small) arenas through the native allocator too
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(512, 1024), torch.nn.GELU(), torch.nn.Linear(1024, 512)).cuda().bfloat16()
+        conf = {"train_micro_batch_size_per_gpu": 4, "bf16": {"enabled": True},
+                "optimizer": {"type": "AdamW", "params": {"lr": 1e-3}},
+                "zero_optimization": {"stage": 3, "offload_optimizer": {"device": "cpu", "pin_memory": True}}}
+        eng, *_ = ds.initialize(model=model, config=conf)
+        assert eng.optimizer.master.is_pinned() and pinned.live_bytes() > before
+        x = torch.randn(4, 512, device="cuda").bfloat16()
+        l0 = None
+        for _ in range(5):
+            loss = eng(x).float().pow(2).mean()
+            eng.backward(loss)
+            eng.step()
+            l0 = l0 if l0 is not None else loss.item()
+        assert loss.item() < l0
+        eng.destroy()
+    finally:
+        pinned.THRESHOLD_BYTES = pinned_threshold
