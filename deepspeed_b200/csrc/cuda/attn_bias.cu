@@ -14,11 +14,14 @@
 // never leave the register file, P / dS are re-used in place as the A operand of the second GEMM.
 //
 // Structure: a CTA is 4 warps x 16 rows = 64 rows; K / V (forward, dQ) or Q / dO (dK / dV) tiles of 64 rows stream through
-// a 2-stage cp.async ring (row pitch padded by 16 B: ldmatrix conflict-free for every D).  Backward is two kernels and has
+// a 2-stage cp.async ring (row pitch padded by 16 B: ldmatrix conflict-free for every D) -- together with the matching
+// [64 x 64] pair-bias tile and the 64 per-key bias values, so no bias load sits on the softmax's critical path.  The
+// block-sparsity layout is turned into a compacted list of active tiles (+ a 4 x 4 sub-block mask each) once per CTA.  Backward is two kernels and has
 // no dQ atomics: (A) one CTA per 64 keys computes the TRANSPOSED scores S^T = K Q^T so P^T / dS^T are already the A operand
 // of dV += P^T dO and dK += dS^T Q, and reduces dS over queries into the mask-bias gradient; (B) one CTA per 64 queries
 // recomputes S, forms dQ += dS K and adds dS into the pair-bias gradient (fp32 vector reductions: the sum over the N rows
 // of the MSA crosses CTAs).
+#include <type_traits>
 #include "dsb_common.cuh"
 
 namespace dsb {
@@ -46,8 +49,11 @@ struct Params {
     int b2_div;                                                            // bias2 batch index = nb / b2_div
     int64_t b2_b, b2_h, b2_r;                                              // bias2 strides
     int64_t g2_b, g2_h;                                                    // db2 strides (row stride = Lk)
-    int lay_bs, lay_nq, lay_nk;
+    int lay_bs, lay_nq, lay_nk;  // lay_bs is a power of two >= 16; lay_sh = log2(lay_bs)
+    int lay_sh;
     int64_t lay_h;
+    int stage_bias;  // both biases are 16-byte tileable: stream them through shared memory with the K/V (Q/dO) tiles
+    int list_cap;    // capacity (tiles) of the active-tile list in shared memory
     float scale;
     int causal;
 };
@@ -202,22 +208,90 @@ __device__ __forceinline__ void mma_p_tile(float (&out)[Cfg<D>::ON][4], const ui
     }
 }
 
-// Is any layout block under the (row tile, col tile) pair of 64 x 64 scores active?
-__device__ __forceinline__ bool tile_active(const Params& p, const uint8_t* lay, int qt, int kt)
+// ---- block-sparsity layout ------------------------------------------------------------------------------------------------
+// A CTA first builds, in parallel, the list of streamed tiles that contain at least one active layout block together with a
+// 16-bit mask of the (up to 4 x 4) layout blocks inside each 64 x 64 score tile; the main loop then walks the compacted list
+// (no dependent global loads, no divisions on the critical path).  mask bit = q_sub * nsb + k_sub.
+__device__ __forceinline__ uint32_t tile_mask(const Params& p, const uint8_t* lay, int qt, int kt)
 {
-    if (lay == nullptr) return true;
-    const int bs = p.lay_bs;
-    const int q_lo = qt * kTile / bs, q_hi = min((qt * kTile + kTile - 1) / bs, p.lay_nq - 1);
-    const int k_lo = kt * kTile / bs, k_hi = min((kt * kTile + kTile - 1) / bs, p.lay_nk - 1);
-    for (int a = q_lo; a <= q_hi; ++a)
-        for (int b = k_lo; b <= k_hi; ++b)
-            if (lay[a * p.lay_nk + b]) return true;
-    return false;
+    if (lay == nullptr) return 0xffffu;
+    const int sh = p.lay_sh;
+    const int nsb = sh >= 6 ? 1 : (kTile >> sh);
+    uint32_t m = 0;
+    for (int a = 0; a < nsb; ++a) {
+        const int qa = min((qt * kTile + (a << sh)) >> sh, p.lay_nq - 1);
+        const bool q_in = sh >= 6 || (qt * kTile + (a << sh)) < (p.lay_nq << sh);
+        for (int b = 0; b < nsb; ++b) {
+            const int kb = min((kt * kTile + (b << sh)) >> sh, p.lay_nk - 1);
+            const bool k_in = sh >= 6 || (kt * kTile + (b << sh)) < (p.lay_nk << sh);
+            if (q_in && k_in && lay[qa * p.lay_nk + kb]) m |= 1u << (a * nsb + b);
+        }
+    }
+    return m;
 }
-__device__ __forceinline__ bool block_on(const Params& p, const uint8_t* lay, int qrow, int kcol)
+
+// Fills idx[0 .. n) with the active tiles of [first, n_tiles) (ascending) and mask[tile] for every tile; returns n.
+// `fixed_is_q`: the CTA owns query tile `fixed` and streams key tiles (forward, dQ) -- otherwise it owns a key tile.
+__device__ __forceinline__ int build_tile_list(const Params& p, const uint8_t* lay, bool fixed_is_q, int fixed, int first,
+                                               int n_tiles, uint16_t* idx, uint16_t* mask, int* count_slot)
 {
-    if (lay == nullptr) return true;
-    return lay[min(qrow / p.lay_bs, p.lay_nq - 1) * p.lay_nk + min(kcol / p.lay_bs, p.lay_nk - 1)] != 0;
+    const int tid = threadIdx.x;
+    for (int t = first + tid; t < n_tiles; t += blockDim.x)
+        mask[t] = static_cast<uint16_t>(fixed_is_q ? tile_mask(p, lay, fixed, t) : tile_mask(p, lay, t, fixed));
+    __syncthreads();
+    if (tid < 32) {
+        int count = 0;
+        for (int base = first; base < n_tiles; base += 32) {
+            const int t = base + tid;
+            const bool on = t < n_tiles && mask[t] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, on);
+            if (on) idx[count + __popc(bal & ((1u << tid) - 1u))] = static_cast<uint16_t>(t);
+            count += __popc(bal);
+        }
+        if (tid == 0) *count_slot = count;
+    }
+    __syncthreads();
+    return *count_slot;
+}
+// is layout block (row sub-block of `row_in_tile`, col sub-block of `col_in_tile`) of a tile with mask `m` active?
+__device__ __forceinline__ bool sub_on(const Params& p, uint32_t m, int q_in_tile, int k_in_tile)
+{
+    const int sh = p.lay_sh;
+    if (sh >= 6) return m != 0;
+    const int nsb = kTile >> sh;
+    return (m >> ((q_in_tile >> sh) * nsb + (k_in_tile >> sh))) & 1u;
+}
+
+// ---- bias tiles in shared memory ----------------------------------------------------------------------------------------------
+constexpr int kBiasPitch = kTile * 2 + 16;                       // bytes per row of a staged [64 x 64] pair-bias tile
+constexpr int kBiasStage = kTile * kBiasPitch + kTile * 2;       // pair-bias tile + 64 per-key bias values
+template <typename T>
+__device__ __forceinline__ void load_bias_tile(uint32_t dst, const T* b2, int64_t b2_r, int row0, int n_rows, int col0, int n_cols,
+                                               const T* b1, int tid)
+{
+    if (b2 != nullptr) {
+#pragma unroll
+        for (int i = tid; i < kTile * 8; i += kThreads) {
+            const int r = i >> 3, c = i & 7;
+            const bool ok = row0 + r < n_rows && col0 + c * 8 < n_cols;
+            cp_async16(dst + r * kBiasPitch + c * 16, b2 + (ok ? static_cast<int64_t>(row0 + r) * b2_r + col0 + c * 8 : 0), ok);
+        }
+    }
+    if (b1 != nullptr && tid < 8) {
+        const bool ok = col0 + tid * 8 < n_cols;
+        cp_async16(dst + kTile * kBiasPitch + tid * 16, b1 + (ok ? col0 + tid * 8 : 0), ok);
+    }
+}
+template <typename T>
+__device__ __forceinline__ float2 lds_pair(const uint8_t* p)
+{
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w);
+        return __half22float2(h);
+    }
 }
 
 template <typename T>
@@ -249,13 +323,17 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const Params p)
 
     int n_kt = (p.Lk + kTile - 1) / kTile;
     if (p.causal) n_kt = min(n_kt, qt + 1);
-    auto next_active = [&](int kt) {
-        while (kt < n_kt && !tile_active(p, lay, qt, kt)) ++kt;
-        return kt;
-    };
+    const bool staged = p.stage_bias && (b1 != nullptr || b2 != nullptr);
+    const uint32_t bias_off = 4 * C::TILE_BYTES;
+    uint8_t* list_base = smem + bias_off + (staged ? 2 * kBiasStage : 0);
+    uint16_t* tl_idx = reinterpret_cast<uint16_t*>(list_base);
+    uint16_t* tl_mask = tl_idx + p.list_cap;
+    int* tl_count = reinterpret_cast<int*>(tl_mask + p.list_cap);
+    const int n_act = build_tile_list(p, lay, true, qt, 0, n_kt, tl_idx, tl_mask, tl_count);
     auto issue = [&](int kt, int buf) {
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES, kp, p.k_r, kt * kTile, p.Lk, tid);
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES + C::TILE_BYTES, vp, p.v_r, kt * kTile, p.Lk, tid);
+        if (staged) load_bias_tile<T>(sb + bias_off + buf * kBiasStage, b2, p.b2_r, qt * kTile, p.Lq, kt * kTile, p.Lk, b1, tid);
         cp_async_commit();
     };
 
@@ -265,17 +343,19 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const Params p)
     float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
     const float sc2 = p.scale * kLog2e;
 
-    int kt = next_active(0), buf = 0;
-    if (kt < n_kt) issue(kt, 0);
-    while (kt < n_kt) {
-        const int nxt = next_active(kt + 1);
-        if (nxt < n_kt) {
-            issue(nxt, buf ^ 1);
+    int buf = 0;
+    if (n_act > 0) issue(tl_idx[0], 0);
+    for (int it = 0; it < n_act; ++it) {
+        const int kt = tl_idx[it];
+        const uint32_t tmask = tl_mask[kt];
+        if (it + 1 < n_act) {
+            issue(tl_idx[it + 1], buf ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
+        const uint8_t* bst = smem + bias_off + buf * kBiasStage;  // staged pair-bias tile | per-key bias
         const uint32_t kb = sb + buf * 2 * C::TILE_BYTES, vb = kb + C::TILE_BYTES;
         float s[8][4];
 #pragma unroll
@@ -286,17 +366,32 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const Params p)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c0 = kt * kTile + j * 8 + 2 * t;
-            const bool on = block_on(p, lay, qt * kTile + warp * 16, kt * kTile + j * 8);
+            const bool on = sub_on(p, tmask, warp * 16, j * 8);
+            float2 sb1 = make_float2(0.f, 0.f), s_lo = sb1, s_hi = sb1;
+            if (staged) {
+                const int cb = (j * 8 + 2 * t) * 2;
+                if (b1) sb1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
+                if (b2) {
+                    s_lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
+                    s_hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int col = c0 + e;
-                float add = 0.f;
                 const bool in = col < p.Lk && on;
-                if (in && b1) add = ldb(b1, col);
-                float a_lo = add, a_hi = add;
-                if (in && b2) {
-                    if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
-                    if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
+                float a_lo, a_hi;
+                if (staged) {
+                    a_lo = (e ? sb1.y : sb1.x) + (e ? s_lo.y : s_lo.x);
+                    a_hi = (e ? sb1.y : sb1.x) + (e ? s_hi.y : s_hi.x);
+                } else {
+                    float add = 0.f;
+                    if (in && b1) add = ldb(b1, col);
+                    a_lo = a_hi = add;
+                    if (in && b2) {
+                        if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
+                        if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
+                    }
                 }
                 const bool v_lo = in && !(p.causal && col > r_lo), v_hi = in && !(p.causal && col > r_hi);
                 s[j][e] = v_lo ? fmaf(s[j][e], sc2, a_lo * kLog2e) : -INFINITY;
@@ -336,7 +431,6 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const Params p)
         }
         mma_p_tile<T, D>(o, pa, vb, lane);
         __syncthreads();
-        kt = nxt;
         buf ^= 1;
     }
     l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
@@ -416,13 +510,19 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
 
     const int n_qt = (p.Lq + kTile - 1) / kTile;
     const int q_first = p.causal ? kt : 0;
-    auto next_active = [&](int qt) {
-        while (qt < n_qt && !tile_active(p, lay, qt, kt)) ++qt;
-        return qt;
-    };
+    const bool staged = p.stage_bias && b2 != nullptr;  // (the per-key bias is a per-thread constant here)
+    const uint32_t bias_off = 4 * C::TILE_BYTES + 2 * 128 * 4;
+    uint8_t* list_base = smem + bias_off + (staged ? 2 * kBiasStage : 0);
+    uint16_t* tl_idx = reinterpret_cast<uint16_t*>(list_base);
+    uint16_t* tl_mask = tl_idx + p.list_cap;
+    int* tl_count = reinterpret_cast<int*>(tl_mask + p.list_cap);
+    const int n_act = build_tile_list(p, lay, false, kt, q_first, n_qt, tl_idx, tl_mask, tl_count);
     auto issue = [&](int qt, int buf) {
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES, qp, p.q_r, qt * kTile, p.Lq, tid);
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES + C::TILE_BYTES, dop, p.o_r, qt * kTile, p.Lq, tid);
+        if (staged)
+            load_bias_tile<T>(sb + bias_off + buf * kBiasStage, b2, p.b2_r, qt * kTile, p.Lq, kt * kTile, p.Lk,
+                              static_cast<const T*>(nullptr), tid);
         cp_async_commit();
         if (tid < kTile) {
             const int r = qt * kTile + tid;
@@ -440,17 +540,19 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
     float g1_lo = 0.f, g1_hi = 0.f;
     const float sc2 = p.scale * kLog2e;
 
-    int qt = next_active(q_first), buf = 0;
-    if (qt < n_qt) issue(qt, 0);
-    while (qt < n_qt) {
-        const int nxt = next_active(qt + 1);
-        if (nxt < n_qt) {
-            issue(nxt, buf ^ 1);
+    int buf = 0;
+    if (n_act > 0) issue(tl_idx[0], 0);
+    for (int it = 0; it < n_act; ++it) {
+        const int qt = tl_idx[it];
+        const uint32_t tmask = tl_mask[qt];
+        if (it + 1 < n_act) {
+            issue(tl_idx[it + 1], buf ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
+        const uint8_t* bst = smem + bias_off + buf * kBiasStage;  // staged pair-bias tile [query in tile][key in tile]
         const uint32_t qb = sb + buf * 2 * C::TILE_BYTES, dob = qb + C::TILE_BYTES;
         const float* st = stat + buf * 128;
         float s[8][4], dp[8][4];
@@ -464,7 +566,7 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
         uint32_t pa[4][4], da[4][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const bool on = block_on(p, lay, qt * kTile + j * 8, kt * kTile + warp * 16);
+            const bool on = sub_on(p, tmask, j * 8, warp * 16);
             float pv[4], dsv[4];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
@@ -472,7 +574,11 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
                 const float l2 = st[qi], dlt = st[64 + qi];
                 const bool qin = qrow < p.Lq && on;
                 float a_lo = b1_lo, a_hi = b1_hi;
-                if (qin && b2) {
+                if (staged) {
+                    const T* brow = reinterpret_cast<const T*>(bst + qi * kBiasPitch);
+                    a_lo += Mma<T>::to_f(brow[warp * 16 + g]) * kLog2e;
+                    a_hi += Mma<T>::to_f(brow[warp * 16 + g + 8]) * kLog2e;
+                } else if (qin && b2) {
                     if (k_lo < p.Lk) a_lo += ldb(b2, static_cast<int64_t>(qrow) * p.b2_r + k_lo) * kLog2e;
                     if (k_hi < p.Lk) a_hi += ldb(b2, static_cast<int64_t>(qrow) * p.b2_r + k_hi) * kLog2e;
                 }
@@ -495,7 +601,6 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
         mma_p_tile<T, D>(dv, pa, dob, lane);  // dV += P^T dO
         mma_p_tile<T, D>(dk, da, qb, lane);   // dK += dS^T Q
         __syncthreads();
-        qt = nxt;
         buf ^= 1;
     }
     T* dkp = static_cast<T*>(p.dk) + nb * p.k_b + h * p.k_h;
@@ -555,13 +660,17 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
 
     int n_kt = (p.Lk + kTile - 1) / kTile;
     if (p.causal) n_kt = min(n_kt, qt + 1);
-    auto next_active = [&](int kt) {
-        while (kt < n_kt && !tile_active(p, lay, qt, kt)) ++kt;
-        return kt;
-    };
+    const bool staged = p.stage_bias && (b1 != nullptr || b2 != nullptr);
+    const uint32_t bias_off = 4 * C::TILE_BYTES;
+    uint8_t* list_base = smem + bias_off + (staged ? 2 * kBiasStage : 0);
+    uint16_t* tl_idx = reinterpret_cast<uint16_t*>(list_base);
+    uint16_t* tl_mask = tl_idx + p.list_cap;
+    int* tl_count = reinterpret_cast<int*>(tl_mask + p.list_cap);
+    const int n_act = build_tile_list(p, lay, true, qt, 0, n_kt, tl_idx, tl_mask, tl_count);
     auto issue = [&](int kt, int buf) {
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES, kp, p.k_r, kt * kTile, p.Lk, tid);
         load_tile<T, D>(sb + buf * 2 * C::TILE_BYTES + C::TILE_BYTES, vp, p.v_r, kt * kTile, p.Lk, tid);
+        if (staged) load_bias_tile<T>(sb + bias_off + buf * kBiasStage, b2, p.b2_r, qt * kTile, p.Lq, kt * kTile, p.Lk, b1, tid);
         cp_async_commit();
     };
     float dq[C::ON][4];
@@ -569,17 +678,19 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
     for (int i = 0; i < C::ON; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
     const float sc2 = p.scale * kLog2e;
 
-    int kt = next_active(0), buf = 0;
-    if (kt < n_kt) issue(kt, 0);
-    while (kt < n_kt) {
-        const int nxt = next_active(kt + 1);
-        if (nxt < n_kt) {
-            issue(nxt, buf ^ 1);
+    int buf = 0;
+    if (n_act > 0) issue(tl_idx[0], 0);
+    for (int it = 0; it < n_act; ++it) {
+        const int kt = tl_idx[it];
+        const uint32_t tmask = tl_mask[kt];
+        if (it + 1 < n_act) {
+            issue(tl_idx[it + 1], buf ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
+        const uint8_t* bst = smem + bias_off + buf * kBiasStage;
         const uint32_t kb = sb + buf * 2 * C::TILE_BYTES, vb = kb + C::TILE_BYTES;
         float s[8][4], dp[8][4];
 #pragma unroll
@@ -593,18 +704,33 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c0 = kt * kTile + j * 8 + 2 * t;
-            const bool on = block_on(p, lay, qt * kTile + warp * 16, kt * kTile + j * 8);
+            const bool on = sub_on(p, tmask, warp * 16, j * 8);
             float dsv[4];
+            float2 sb1 = make_float2(0.f, 0.f), s_lo = sb1, s_hi = sb1;
+            if (staged) {
+                const int cb = (j * 8 + 2 * t) * 2;
+                if (b1) sb1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
+                if (b2) {
+                    s_lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
+                    s_hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int col = c0 + e;
                 const bool in = col < p.Lk && on;
-                float add = 0.f;
-                if (in && b1) add = ldb(b1, col);
-                float a_lo = add, a_hi = add;
-                if (in && b2) {
-                    if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
-                    if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
+                float a_lo, a_hi;
+                if (staged) {
+                    a_lo = (e ? sb1.y : sb1.x) + (e ? s_lo.y : s_lo.x);
+                    a_hi = (e ? sb1.y : sb1.x) + (e ? s_hi.y : s_hi.x);
+                } else {
+                    float add = 0.f;
+                    if (in && b1) add = ldb(b1, col);
+                    a_lo = a_hi = add;
+                    if (in && b2) {
+                        if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
+                        if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
+                    }
                 }
                 const bool v_lo = in && r_lo < p.Lq && !(p.causal && col > r_lo);
                 const bool v_hi = in && r_hi < p.Lq && !(p.causal && col > r_hi);
@@ -634,7 +760,6 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
         }
         mma_p_tile<T, D>(dq, da, kb, lane);  // dQ += dS K
         __syncthreads();
-        kt = nxt;
         buf ^= 1;
     }
     T* dqp = static_cast<T*>(p.dq) + nb * p.q_b + h * p.q_h;
@@ -648,10 +773,13 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
     }
 }
 
+// bias staging (two stages) + active-tile list (index + mask per tile) + its counter
+static int extra_smem(const Params& p) { return (p.stage_bias ? 2 * kBiasStage : 0) + p.list_cap * 4 + 16; }
+
 template <typename T, int D>
 int launch_fwd(const Params& p, cudaStream_t stream)
 {
-    const int smem = 4 * Cfg<D>::TILE_BYTES;
+    const int smem = 4 * Cfg<D>::TILE_BYTES + extra_smem(p);
     cudaFuncSetAttribute(fwd_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const dim3 grid((p.Lq + kTile - 1) / kTile, p.H, p.NB);
     fwd_kernel<T, D><<<grid, kThreads, smem, stream>>>(p);
@@ -664,7 +792,7 @@ int launch_bwd(const Params& p, cudaStream_t stream)
     const int64_t rows = static_cast<int64_t>(p.NB) * p.H * p.Lq * (D / 8);
     delta_kernel<T, D><<<static_cast<unsigned>((rows + 255) / 256), 256, 0, stream>>>(p);
     DSB_CHECK_LAUNCH();
-    const int smem_a = 4 * Cfg<D>::TILE_BYTES + 2 * 128 * 4, smem_b = 4 * Cfg<D>::TILE_BYTES;
+    const int smem_a = 4 * Cfg<D>::TILE_BYTES + 2 * 128 * 4 + extra_smem(p), smem_b = 4 * Cfg<D>::TILE_BYTES + extra_smem(p);
     cudaFuncSetAttribute(bwd_dkdv_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_a);
     cudaFuncSetAttribute(bwd_dq_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b);
     bwd_dkdv_kernel<T, D><<<dim3((p.Lk + kTile - 1) / kTile, p.H, p.NB), kThreads, smem_a, stream>>>(p);
@@ -711,6 +839,18 @@ DSB_EXPORT int dsb_attn_bias(const void* q, const void* k, const void* v, void* 
     if (p.NB <= 0 || p.H <= 0 || p.Lq <= 0 || p.Lk <= 0) return 0;
     if (p.H > 65535 || p.NB > 65535) return -3;
     if (layout != nullptr && (p.lay_bs < 16 || (p.lay_bs & (p.lay_bs - 1)) != 0)) return -4;
+    p.lay_sh = 6;  // no layout: one always-active block per tile
+    if (layout != nullptr) {
+        p.lay_sh = 0;
+        while ((1 << p.lay_sh) < p.lay_bs) ++p.lay_sh;
+    }
+    const int n_tiles = (max(p.Lq, p.Lk) + kTile - 1) / kTile;
+    if (n_tiles > 8192) return -2;
+    p.list_cap = (n_tiles + 7) & ~7;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool b1_ok = bias1 == nullptr || ((p.Lk & 7) == 0 && (p.b1_b & 7) == 0 && al16(bias1));
+    const bool b2_ok = bias2 == nullptr || ((p.Lk & 7) == 0 && ((p.b2_r | p.b2_b | p.b2_h) & 7) == 0 && al16(bias2));
+    p.stage_bias = (bias1 != nullptr || bias2 != nullptr) && b1_ok && b2_ok;
     if (dtype == dsb::kBF16) return dispatch<__nv_bfloat16>(p, D, bwd, stream);
     if (dtype == dsb::kF16) return dispatch<__half>(p, D, bwd, stream);
     return -1;
