@@ -238,6 +238,10 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self._forced_boundary = None
         self._accum = 0  # micro steps accumulated since the last optimizer step
         self.fused_in_backward = self._fusion_policy()
+        # host tier analogue of the fused-in-backward step: each unit's CPU optimizer step starts as soon as its reduced
+        # gradient shard has landed in pinned memory, on a worker thread, while backward is still running on the GPU
+        self.host_step_in_backward = self._host_overlap_policy()
+        self._host_worker = None
 
         self._allocate(broadcast_init)
         self._register_hooks()
@@ -257,7 +261,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         log_dist(
             f"ZeroShardedOptimizer: stage={self.stage} units={len(self.units)} arena={self.arena_numel:,} elems/rank "
             f"shard_world={self.shard_world} fused_in_backward={self.fused_in_backward} "
-            f"offload_opt={self.offload_optimizer} symm={'on' if self._symm else 'off'}",
+            f"offload_opt={self.offload_optimizer} host_step_in_backward={self.host_step_in_backward} "
+            f"symm={'on' if self._symm else 'off'}",
             ranks=[0])
 
     # =========================================================================================
@@ -275,11 +280,25 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         fib = self._fib_request
         return bool(can_fuse if fib is None else (fib and can_fuse))
 
+    def _host_overlap_policy(self) -> bool:
+        """Same preconditions as :meth:`_fusion_policy` (nothing may need the whole gradient first), for the CPU tier."""
+        scaled = (self.model_dtype == torch.float16 or self.dynamic_loss_scale
+                  or float(self.loss_scaler.cur_scale) != 1.0)
+        ok = (self.offload_optimizer and not self.offload_nvme and self.d2h_stream is not None and self.flat_opt.fused
+              and not getattr(self.flat_opt, "per_tensor", False) and self.clip == 0.0 and self.gas == 1 and not scaled
+              and not self.offload_param and not getattr(self, "_no_fuse_reason", None))
+        want = self._fib_request
+        return bool(ok if want is None else (want and ok))
+
     def disable_fused_in_backward(self, reason: str):
         """Fall back to the two-phase step (reduce + accumulate, then one fused step); allocates the gradient arena
         if the fused path had elided it.  Used when something discovered after construction needs whole gradients
         (gradient accumulation turned on, tied weights across pipeline stages, ...)."""
         self._no_fuse_reason = reason
+        if getattr(self, "host_step_in_backward", False):
+            self._join_host_worker()
+            self.host_step_in_backward = False
+            log_dist(f"ZeroShardedOptimizer[{self.name}]: host step inside backward disabled ({reason})", ranks=[0])
         if not self.fused_in_backward:
             return
         self.fused_in_backward = False
@@ -944,6 +963,14 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         first = self._first_micro(rt)
         dst = self.grad_arena[a:b]
         if dst.device != shard_g.device:  # optimizer offload: asynchronous D2H into the pinned arena
+            if self.host_step_in_backward and self.is_gradient_accumulation_boundary():
+                if rt.reduced_this_micro:
+                    raise RuntimeError(
+                        f"ZeRO unit '{u.name}' produced gradients twice in one backward while the host optimizer step "
+                        f"overlaps backward; set zero_optimization.b200_fused_optimizer_in_backward=false for this model")
+                done = self._offload_grad(a, b, shard_g, scale, True)
+                self._host_submit(a, b, done)
+                return
             self._offload_grad(a, b, shard_g, scale, first)
             return
         flat_ops.scale_cast(shard_g, dst, scale=scale, accumulate=not first)
@@ -1010,6 +1037,46 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             done = torch.cuda.Event()
             done.record()
         slot.free_event = done
+        return done
+
+    # ---- CPU optimizer step overlapped with backward -------------------------------------------------------------------------
+    def _host_submit(self, a, b, landed):
+        """Queue "step arena range [a, b) once its gradient has landed" for the worker thread (started lazily)."""
+        import queue
+        import threading
+        if self._host_worker is None:
+            self._host_q = queue.Queue()
+            self._host_err = []
+            dev = torch.cuda.current_device()
+
+            def run():
+                torch.cuda.set_device(dev)
+                while True:
+                    job = self._host_q.get()
+                    try:
+                        if job is None:
+                            return
+                        a_, b_, ev = job
+                        ev.synchronize()  # the D2H copy of this shard has finished (host-side wait, no GPU stall)
+                        # native CPU Adam (the ctypes call releases the GIL) + pinned bf16 staging + H2D on h2d_stream
+                        self._step_range(a_, b_, self.grad_arena, 0, 1.0, join_upload=False)
+                    except BaseException as e:  # surfaced by _join_host_worker on the training thread
+                        self._host_err.append(e)
+                    finally:
+                        self._host_q.task_done()
+
+            self._host_worker = threading.Thread(target=run, name="dsb200-host-step", daemon=True)
+            self._host_worker.start()
+        self._host_q.put((a, b, landed))
+
+    def _join_host_worker(self):
+        if self._host_worker is None:
+            return
+        self._host_q.join()
+        if self._host_err:
+            err = self._host_err.pop()
+            self._host_err.clear()
+            raise err
 
     def _drain_offloaded_grads(self):
         """Host-side join of the gradient D2H copies + the accumulation of later micro steps."""
@@ -1198,7 +1265,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     def _group_hyper(self, gi):
         return self.param_groups[gi]
 
-    def _step_range(self, a, b, grad, grad_offset, grad_scale, d_gscale=None, d_skip=None):
+    def _step_range(self, a, b, grad, grad_offset, grad_scale, d_gscale=None, d_skip=None, join_upload=True):
         """Run the flat optimizer over arena range [a, b).  ``grad`` holds arena coordinates
         ``[grad_offset, ...)``."""
         write_lp = self.master is not None and not self.offload_optimizer
@@ -1236,7 +1303,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                     ev.record()
                 slot.free_event = ev
         if upload:
-            torch.cuda.current_stream().wait_stream(self.h2d_stream)
+            if join_upload:
+                torch.cuda.current_stream().wait_stream(self.h2d_stream)
             self._uploaded_lp = True
         if self.state_swapper is not None:
             self.state_swapper.flush(self.flat_opt)
@@ -1269,6 +1337,15 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             self._allreduce_stats(self.stats)
 
     def finish_step(self, extra_sumsq=None, extra_found_inf=None):
+        if self.host_step_in_backward:
+            # every unit was stepped on the host while backward ran: wait for the stragglers and for their uploads
+            self._join_host_worker()
+            if self.h2d_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.h2d_stream)
+            for gi in range(len(self.group_steps)):
+                self.group_steps[gi] += 1
+            self._post_step()
+            return
         if self.fused_in_backward:
             # parameters were already updated unit-by-unit inside backward
             for gi in range(len(self.group_steps)):
@@ -1514,6 +1591,9 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         for h in self._hook_handles:
             h.remove()
         self._hook_handles.clear()
+        if getattr(self, "_host_worker", None) is not None:
+            self._host_q.put(None)  # stop the host-step worker
+            self._host_worker = None
 
     # =========================================================================================
     # introspection helpers (tensor_fragment API, checkpointing)

@@ -96,8 +96,8 @@ def test_checkpoint_roundtrip_gpu(tmp_path):
     assert abs(l1b - l2b) < 2e-3
 
 
-@pytest.mark.parametrize("tier", ["cpu", "nvme"])
-def test_offload_tiers_match_device_optimizer(tier, tmp_path):
+@pytest.mark.parametrize("tier,clip", [("cpu", 1.0), ("cpu", 0.0), ("nvme", 1.0)])
+def test_offload_tiers_match_device_optimizer(tier, clip, tmp_path):
     """ZeRO-3 with the optimizer state on the host (pinned memory, AVX Adam) or on NVMe-backed swap files streams through
     the same math as the on-device fused Adam (config #4 of BASELINE.json at toy size)."""
     import deepspeed_b200 as ds
@@ -112,7 +112,7 @@ def test_offload_tiers_match_device_optimizer(tier, tmp_path):
         with torch.device("cuda"):
             model = LlamaForCausalLM(cfg).to(torch.bfloat16)
         zo = {"stage": 3, "stage3_param_persistence_threshold": 0}
-        conf = {"train_micro_batch_size_per_gpu": 2, "bf16": {"enabled": True}, "gradient_clipping": 1.0,
+        conf = {"train_micro_batch_size_per_gpu": 2, "bf16": {"enabled": True}, "gradient_clipping": clip,
                 "optimizer": {"type": "AdamW", "params": {"lr": 1e-3, "weight_decay": 0.1}}, "zero_optimization": zo}
         if mode == "cpu":
             zo["offload_optimizer"] = {"device": "cpu", "pin_memory": True}
@@ -121,6 +121,8 @@ def test_offload_tiers_match_device_optimizer(tier, tmp_path):
                                        "pipeline_read": True, "pipeline_write": True}
             conf["aio"] = {"block_size": 1 << 20, "queue_depth": 8}
         eng, *_ = ds.initialize(model=model, config=conf)
+        if mode == "cpu":  # without clipping the CPU Adam of each unit runs on a worker thread while backward continues
+            assert eng.optimizer.host_step_in_backward == (clip == 0.0)
         losses = []
         for _ in range(4):
             loss = eng(ids, labels=ids)
