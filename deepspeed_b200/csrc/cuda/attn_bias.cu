@@ -262,6 +262,14 @@ __device__ __forceinline__ bool sub_on(const Params& p, uint32_t m, int q_in_til
     return (m >> ((q_in_tile >> sh) * nsb + (k_in_tile >> sh))) & 1u;
 }
 
+__device__ __forceinline__ bool all_sub_on(const Params& p, uint32_t m)
+{
+    if (p.lay_sh >= 6) return m != 0;
+    const int nsb = kTile >> p.lay_sh;
+    const uint32_t full = (1u << (nsb * nsb)) - 1u;
+    return (m & full) == full;
+}
+
 // ---- bias tiles in shared memory ----------------------------------------------------------------------------------------------
 constexpr int kBiasPitch = kTile * 2 + 16;                       // bytes per row of a staged [64 x 64] pair-bias tile
 constexpr int kBiasStage = kTile * kBiasPitch + kTile * 2;       // pair-bias tile + 64 per-key bias values
@@ -362,42 +370,65 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const Params p)
         for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         mma_a_tileT<T, D>(s, qf, kb, lane);
 
-        float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c0 = kt * kTile + j * 8 + 2 * t;
-            const bool on = sub_on(p, tmask, warp * 16, j * 8);
-            float2 sb1 = make_float2(0.f, 0.f), s_lo = sb1, s_hi = sb1;
+        // additive bias (times log2 e) of score columns (c0, c0 + 1) of n-tile j for this thread's two rows
+        auto bias_pair = [&](int j, float2& lo, float2& hi) {
+            float2 k1 = make_float2(0.f, 0.f);
+            lo = hi = k1;
             if (staged) {
                 const int cb = (j * 8 + 2 * t) * 2;
-                if (b1) sb1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
+                if (b1) k1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
                 if (b2) {
-                    s_lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
-                    s_hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
+                    lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
+                    hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
+                }
+            } else {  // unaligned shapes: clamped direct loads (out-of-range entries are masked below)
+                const int ca = min(kt * kTile + j * 8 + 2 * t, p.Lk - 1), cb = min(kt * kTile + j * 8 + 2 * t + 1, p.Lk - 1);
+                if (b1) k1 = make_float2(ldb(b1, ca), ldb(b1, cb));
+                if (b2) {
+                    const int64_t ra = static_cast<int64_t>(min(r_lo, p.Lq - 1)) * p.b2_r, rb = static_cast<int64_t>(min(r_hi, p.Lq - 1)) * p.b2_r;
+                    lo = make_float2(ldb(b2, ra + ca), ldb(b2, ra + cb));
+                    hi = make_float2(ldb(b2, rb + ca), ldb(b2, rb + cb));
                 }
             }
+            lo.x = (lo.x + k1.x) * kLog2e;
+            lo.y = (lo.y + k1.y) * kLog2e;
+            hi.x = (hi.x + k1.x) * kLog2e;
+            hi.y = (hi.y + k1.y) * kLog2e;
+        };
+        const bool has_bias = b1 != nullptr || b2 != nullptr;
+        // a tile entirely inside the sequence, below the causal diagonal and with every layout block on needs no masking
+        const bool plain = (kt * kTile + kTile <= p.Lk) && !(p.causal && kt * kTile + kTile - 1 > qt * kTile + warp * 16) &&
+                           all_sub_on(p, tmask);
+        float mx_lo = -INFINITY, mx_hi = -INFINITY;
+        if (plain) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = c0 + e;
-                const bool in = col < p.Lk && on;
-                float a_lo, a_hi;
-                if (staged) {
-                    a_lo = (e ? sb1.y : sb1.x) + (e ? s_lo.y : s_lo.x);
-                    a_hi = (e ? sb1.y : sb1.x) + (e ? s_hi.y : s_hi.x);
-                } else {
-                    float add = 0.f;
-                    if (in && b1) add = ldb(b1, col);
-                    a_lo = a_hi = add;
-                    if (in && b2) {
-                        if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
-                        if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
-                    }
+            for (int j = 0; j < 8; ++j) {
+                float2 lo = make_float2(0.f, 0.f), hi = lo;
+                if (has_bias) bias_pair(j, lo, hi);
+                s[j][0] = fmaf(s[j][0], sc2, lo.x);
+                s[j][1] = fmaf(s[j][1], sc2, lo.y);
+                s[j][2] = fmaf(s[j][2], sc2, hi.x);
+                s[j][3] = fmaf(s[j][3], sc2, hi.y);
+                mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+                mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c0 = kt * kTile + j * 8 + 2 * t;
+                const bool on = sub_on(p, tmask, warp * 16, j * 8);
+                float2 lo = make_float2(0.f, 0.f), hi = lo;
+                if (has_bias) bias_pair(j, lo, hi);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = c0 + e;
+                    const bool in = col < p.Lk && on;
+                    const bool v_lo = in && !(p.causal && col > r_lo), v_hi = in && !(p.causal && col > r_hi);
+                    s[j][e] = v_lo ? fmaf(s[j][e], sc2, e ? lo.y : lo.x) : -INFINITY;
+                    s[j][2 + e] = v_hi ? fmaf(s[j][2 + e], sc2, e ? hi.y : hi.x) : -INFINITY;
+                    mx_lo = fmaxf(mx_lo, s[j][e]);
+                    mx_hi = fmaxf(mx_hi, s[j][2 + e]);
                 }
-                const bool v_lo = in && !(p.causal && col > r_lo), v_hi = in && !(p.causal && col > r_hi);
-                s[j][e] = v_lo ? fmaf(s[j][e], sc2, a_lo * kLog2e) : -INFINITY;
-                s[j][2 + e] = v_hi ? fmaf(s[j][2 + e], sc2, a_hi * kLog2e) : -INFINITY;
-                mx_lo = fmaxf(mx_lo, s[j][e]);
-                mx_hi = fmaxf(mx_hi, s[j][2 + e]);
             }
         }
         mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
@@ -564,33 +595,50 @@ __global__ void __launch_bounds__(kThreads) bwd_dkdv_kernel(const Params p)
         mma_a_tileT<T, D>(s, kf, qb, lane);    // S^T  [16 keys x 64 queries]
         mma_a_tileT<T, D>(dp, vf, dob, lane);  // dP^T
         uint32_t pa[4][4], da[4][4];
+        // full query tile, full key tile, below the causal diagonal for this warp's keys, every layout block on: no masking
+        const bool plain = (qt * kTile + kTile <= p.Lq) && (kt * kTile + kTile <= p.Lk) &&
+                           !(p.causal && kt * kTile + warp * 16 + 15 > qt * kTile) && all_sub_on(p, tmask);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const bool on = sub_on(p, tmask, j * 8, warp * 16);
             float pv[4], dsv[4];
+            const int qi0 = j * 8 + 2 * t;
+            const float2 l2 = *reinterpret_cast<const float2*>(st + qi0), dlt = *reinterpret_cast<const float2*>(st + 64 + qi0);
+            float a_lo[2] = {b1_lo, b1_lo}, a_hi[2] = {b1_hi, b1_hi};
+            if (b2 != nullptr) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int qi = j * 8 + 2 * t + e, qrow = qt * kTile + qi;
-                const float l2 = st[qi], dlt = st[64 + qi];
-                const bool qin = qrow < p.Lq && on;
-                float a_lo = b1_lo, a_hi = b1_hi;
-                if (staged) {
-                    const T* brow = reinterpret_cast<const T*>(bst + qi * kBiasPitch);
-                    a_lo += Mma<T>::to_f(brow[warp * 16 + g]) * kLog2e;
-                    a_hi += Mma<T>::to_f(brow[warp * 16 + g + 8]) * kLog2e;
-                } else if (qin && b2) {
-                    if (k_lo < p.Lk) a_lo += ldb(b2, static_cast<int64_t>(qrow) * p.b2_r + k_lo) * kLog2e;
-                    if (k_hi < p.Lk) a_hi += ldb(b2, static_cast<int64_t>(qrow) * p.b2_r + k_hi) * kLog2e;
+                for (int e = 0; e < 2; ++e) {
+                    if (staged) {
+                        const T* brow = reinterpret_cast<const T*>(bst + (qi0 + e) * kBiasPitch);
+                        a_lo[e] += Mma<T>::to_f(brow[warp * 16 + g]) * kLog2e;
+                        a_hi[e] += Mma<T>::to_f(brow[warp * 16 + g + 8]) * kLog2e;
+                    } else {
+                        const int64_t ro = static_cast<int64_t>(min(qt * kTile + qi0 + e, p.Lq - 1)) * p.b2_r;
+                        a_lo[e] += ldb(b2, ro + min(k_lo, p.Lk - 1)) * kLog2e;
+                        a_hi[e] += ldb(b2, ro + min(k_hi, p.Lk - 1)) * kLog2e;
+                    }
                 }
-                const bool v_lo = qin && k_lo < p.Lk && !(p.causal && k_lo > qrow);
-                const bool v_hi = qin && k_hi < p.Lk && !(p.causal && k_hi > qrow);
-                const float p_lo = v_lo ? fast_exp2(fmaf(s[j][e], sc2, a_lo) - l2) : 0.f;
-                const float p_hi = v_hi ? fast_exp2(fmaf(s[j][2 + e], sc2, a_hi) - l2) : 0.f;
-                pv[e] = p_lo;
-                pv[2 + e] = p_hi;
-                dsv[e] = p_lo * (dp[j][e] - dlt);
-                dsv[2 + e] = p_hi * (dp[j][2 + e] - dlt);
             }
+            if (plain) {
+                pv[0] = fast_exp2(fmaf(s[j][0], sc2, a_lo[0]) - l2.x);
+                pv[1] = fast_exp2(fmaf(s[j][1], sc2, a_lo[1]) - l2.y);
+                pv[2] = fast_exp2(fmaf(s[j][2], sc2, a_hi[0]) - l2.x);
+                pv[3] = fast_exp2(fmaf(s[j][3], sc2, a_hi[1]) - l2.y);
+            } else {
+                const bool on = sub_on(p, tmask, j * 8, warp * 16);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int qrow = qt * kTile + qi0 + e;
+                    const bool qin = qrow < p.Lq && on;
+                    const bool v_lo = qin && k_lo < p.Lk && !(p.causal && k_lo > qrow);
+                    const bool v_hi = qin && k_hi < p.Lk && !(p.causal && k_hi > qrow);
+                    pv[e] = v_lo ? fast_exp2(fmaf(s[j][e], sc2, a_lo[e]) - (e ? l2.y : l2.x)) : 0.f;
+                    pv[2 + e] = v_hi ? fast_exp2(fmaf(s[j][2 + e], sc2, a_hi[e]) - (e ? l2.y : l2.x)) : 0.f;
+                }
+            }
+            dsv[0] = pv[0] * (dp[j][0] - dlt.x);
+            dsv[1] = pv[1] * (dp[j][1] - dlt.y);
+            dsv[2] = pv[2] * (dp[j][2] - dlt.x);
+            dsv[3] = pv[3] * (dp[j][3] - dlt.y);
             g1_lo += dsv[0] + dsv[1];
             g1_hi += dsv[2] + dsv[3];
             pa[j >> 1][(j & 1) * 2] = Mma<T>::pack(pv[0], pv[1]);
@@ -701,43 +749,61 @@ __global__ void __launch_bounds__(kThreads) bwd_dq_kernel(const Params p)
         mma_a_tileT<T, D>(s, qf, kb, lane);
         mma_a_tileT<T, D>(dp, dof, vb, lane);
         uint32_t da[4][4];
+        auto bias_pair = [&](int j, float2& lo, float2& hi) {  // (bias1 + bias2) * log2 e for cols (c0, c0 + 1), rows lo / hi
+            float2 k1 = make_float2(0.f, 0.f);
+            lo = hi = k1;
+            if (staged) {
+                const int cb = (j * 8 + 2 * t) * 2;
+                if (b1) k1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
+                if (b2) {
+                    lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
+                    hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
+                }
+            } else {
+                const int ca = min(kt * kTile + j * 8 + 2 * t, p.Lk - 1), cb = min(kt * kTile + j * 8 + 2 * t + 1, p.Lk - 1);
+                if (b1) k1 = make_float2(ldb(b1, ca), ldb(b1, cb));
+                if (b2) {
+                    const int64_t ra = static_cast<int64_t>(min(r_lo, p.Lq - 1)) * p.b2_r, rb = static_cast<int64_t>(min(r_hi, p.Lq - 1)) * p.b2_r;
+                    lo = make_float2(ldb(b2, ra + ca), ldb(b2, ra + cb));
+                    hi = make_float2(ldb(b2, rb + ca), ldb(b2, rb + cb));
+                }
+            }
+            lo.x = (lo.x + k1.x) * kLog2e;
+            lo.y = (lo.y + k1.y) * kLog2e;
+            hi.x = (hi.x + k1.x) * kLog2e;
+            hi.y = (hi.y + k1.y) * kLog2e;
+        };
+        const bool has_bias = b1 != nullptr || b2 != nullptr;
+        // rows past Lq carry lse = +inf (p = 0), so only columns / causality / layout decide whether masking is needed
+        const bool plain = (kt * kTile + kTile <= p.Lk) && !(p.causal && kt * kTile + kTile - 1 > qt * kTile + warp * 16) &&
+                           all_sub_on(p, tmask);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c0 = kt * kTile + j * 8 + 2 * t;
-            const bool on = sub_on(p, tmask, warp * 16, j * 8);
             float dsv[4];
-            float2 sb1 = make_float2(0.f, 0.f), s_lo = sb1, s_hi = sb1;
-            if (staged) {
-                const int cb = (j * 8 + 2 * t) * 2;
-                if (b1) sb1 = lds_pair<T>(bst + kTile * kBiasPitch + cb);
-                if (b2) {
-                    s_lo = lds_pair<T>(bst + (warp * 16 + g) * kBiasPitch + cb);
-                    s_hi = lds_pair<T>(bst + (warp * 16 + g + 8) * kBiasPitch + cb);
-                }
-            }
+            float2 lo = make_float2(0.f, 0.f), hi = lo;
+            if (has_bias) bias_pair(j, lo, hi);
+            bool on = true;
+            if (plain) {
+                const float p0 = fast_exp2(fmaf(s[j][0], sc2, lo.x) - l2_lo), p1 = fast_exp2(fmaf(s[j][1], sc2, lo.y) - l2_lo);
+                const float p2 = fast_exp2(fmaf(s[j][2], sc2, hi.x) - l2_hi), p3 = fast_exp2(fmaf(s[j][3], sc2, hi.y) - l2_hi);
+                dsv[0] = p0 * (dp[j][0] - dl_lo);
+                dsv[1] = p1 * (dp[j][1] - dl_lo);
+                dsv[2] = p2 * (dp[j][2] - dl_hi);
+                dsv[3] = p3 * (dp[j][3] - dl_hi);
+            } else {
+                on = sub_on(p, tmask, warp * 16, j * 8);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = c0 + e;
-                const bool in = col < p.Lk && on;
-                float a_lo, a_hi;
-                if (staged) {
-                    a_lo = (e ? sb1.y : sb1.x) + (e ? s_lo.y : s_lo.x);
-                    a_hi = (e ? sb1.y : sb1.x) + (e ? s_hi.y : s_hi.x);
-                } else {
-                    float add = 0.f;
-                    if (in && b1) add = ldb(b1, col);
-                    a_lo = a_hi = add;
-                    if (in && b2) {
-                        if (r_lo < p.Lq) a_lo += ldb(b2, static_cast<int64_t>(r_lo) * p.b2_r + col);
-                        if (r_hi < p.Lq) a_hi += ldb(b2, static_cast<int64_t>(r_hi) * p.b2_r + col);
-                    }
+                for (int e = 0; e < 2; ++e) {
+                    const int col = c0 + e;
+                    const bool in = col < p.Lk && on;
+                    const bool v_lo = in && r_lo < p.Lq && !(p.causal && col > r_lo);
+                    const bool v_hi = in && r_hi < p.Lq && !(p.causal && col > r_hi);
+                    const float p_lo = v_lo ? fast_exp2(fmaf(s[j][e], sc2, e ? lo.y : lo.x) - l2_lo) : 0.f;
+                    const float p_hi = v_hi ? fast_exp2(fmaf(s[j][2 + e], sc2, e ? hi.y : hi.x) - l2_hi) : 0.f;
+                    dsv[e] = p_lo * (dp[j][e] - dl_lo);
+                    dsv[2 + e] = p_hi * (dp[j][2 + e] - dl_hi);
                 }
-                const bool v_lo = in && r_lo < p.Lq && !(p.causal && col > r_lo);
-                const bool v_hi = in && r_hi < p.Lq && !(p.causal && col > r_hi);
-                const float p_lo = v_lo ? fast_exp2(fmaf(s[j][e], sc2, a_lo * kLog2e) - l2_lo) : 0.f;
-                const float p_hi = v_hi ? fast_exp2(fmaf(s[j][2 + e], sc2, a_hi * kLog2e) - l2_hi) : 0.f;
-                dsv[e] = p_lo * (dp[j][e] - dl_lo);
-                dsv[2 + e] = p_hi * (dp[j][2 + e] - dl_hi);
             }
             if (g2 != nullptr && on) {
                 if (g2_vec) {

@@ -64,7 +64,11 @@ def maybe_quantized_linear(x, w, b=None):
 
 
 _TC_MODES = {"int8": 0, "int4": 1, "fp8": 2, "fp6": 3}
-WQ_TC_MAX_ROWS = 1024  # beyond this dequantise-once + the bf16 GEMM amortises the decode better
+# Row count up to which the fused kernel beats dequantise-once + bf16 GEMM, per weight format, measured on B200 at
+# [rows x 14336 x 4096] (scripts/bench_wq_tc.py -> profiles/wq_tc_bench_r2.json): int8 1.9x at <= 256 rows, 1.15x at 512,
+# 0.78x at 1024; int4 2.5x / 1.6x / 1.05x; fp8 3.9x / 2.3x / 1.4x; fp6 3.7x / 2.1x / 1.26x.
+WQ_TC_MAX_ROWS_BY_MODE = {"int8": 512, "int4": 1024, "fp8": 1024, "fp6": 1024}
+WQ_TC_MAX_ROWS = 1024
 
 
 def wq_tc_linear(x, qw: "QuantizedWeight", b=None, max_rows=None):
@@ -75,7 +79,7 @@ def wq_tc_linear(x, qw: "QuantizedWeight", b=None, max_rows=None):
     x2 = x.reshape(-1, x.shape[-1])
     M, K = x2.shape
     N = qw.shape[0]
-    limit = WQ_TC_MAX_ROWS if max_rows is None else max_rows
+    limit = min(WQ_TC_MAX_ROWS, WQ_TC_MAX_ROWS_BY_MODE.get(qw.mode, WQ_TC_MAX_ROWS)) if max_rows is None else max_rows
     if M > limit or K != qw.shape[1] or K % 64 or qw.group_size % 64 or K % qw.group_size:
         return None
     from deepspeed_b200.ops import native as NV
