@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/socket.h>
+#include <sys/syscall.h>
 #include <sys/un.h>
 #include <time.h>
 #include <unistd.h>
@@ -454,12 +455,54 @@ DSB_EXPORT int dsb_symm_all_gather_ce(void* const* shards, void* full, int64_t s
 // two (a 70 GB arena becomes 128 GB), which at Llama-70B scale overshoots the node's memory; these entry points give the
 // arena exactly the bytes it asked for.  The pages are first-touched by several threads (page faulting is what dominates a
 // >10 GB allocation) and then registered with the driver.
+// Interleave the pages of the calling thread's next allocations over every NUMA node it may use (the CPU optimizer streams
+// these arenas with all cores of the rank: one node's memory controllers would cap it).  Best effort: raw syscall, no libnuma.
+static void set_interleave(bool on)
+{
+#if defined(__linux__) && defined(__x86_64__)
+    constexpr long kSetMempolicy = 238;
+    constexpr int kDefault = 0, kInterleave = 3;
+    if (!on) {
+        syscall(kSetMempolicy, kDefault, nullptr, 0);
+        return;
+    }
+    unsigned long mask[16] = {0};
+    FILE* f = fopen("/sys/devices/system/node/online", "r");
+    if (f == nullptr) return;
+    char buf[256] = {0};
+    const bool got = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!got) return;
+    int nodes = 0;
+    for (char* tok = strtok(buf, ","); tok != nullptr; tok = strtok(nullptr, ",")) {
+        int lo = 0, hi = 0;
+        if (sscanf(tok, "%d-%d", &lo, &hi) == 2) {
+        } else if (sscanf(tok, "%d", &lo) == 1) {
+            hi = lo;
+        } else {
+            continue;
+        }
+        for (int n = lo; n <= hi && n < 1024; ++n) {
+            mask[n / 64] |= 1ul << (n % 64);
+            ++nodes;
+        }
+    }
+    if (nodes > 1) syscall(kSetMempolicy, kInterleave, mask, 1024 + 1);
+#else
+    (void)on;
+#endif
+}
+
 DSB_EXPORT int dsb_pinned_alloc(void** out, int64_t bytes, int touch_threads)
 {
     if (bytes <= 0 || out == nullptr) return -2;
     void* p = nullptr;
     const size_t align = 2u << 20;
     const size_t sz = (static_cast<size_t>(bytes) + align - 1) / align * align;
+    set_interleave(true);  // inherited by the first-touch threads below
+    struct Restore {
+        ~Restore() { set_interleave(false); }
+    } restore;
     if (posix_memalign(&p, align, sz) != 0) return -ENOMEM;
     const int nt = touch_threads > 0 ? touch_threads : 1;
     std::vector<std::thread> th;
