@@ -60,6 +60,12 @@ def _host_dequant(q, params, groups, bits, sym, dtype):
     return (v.float() * p[:, :1] + p[:, 1:]).to(dtype)
 
 
+def aligned_group_size(n, target=2048):
+    """Group size for quantising ``n`` elements that the device kernels accept (a multiple of 8, at most ``target``);
+    callers pad ``n`` up to a multiple of it."""
+    return target if n >= target else max(8, (n + 7) // 8 * 8)
+
+
 def quantize(x, groups, num_bits=8, q_type=Symmetric, group_perm=None, stochastic=False, seed=0):
     """Returns ``(q, params)``: ``q`` int8 (two values per byte for 4 bit), ``params`` fp32 ``[groups]``
     (symmetric: scale) or ``[groups, 2]`` (asymmetric: scale, offset)."""

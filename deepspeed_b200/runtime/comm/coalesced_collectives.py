@@ -55,22 +55,28 @@ def all_to_all_quant_reduce(tensors: List[torch.Tensor], groups: dict = None, nu
     for t in tensors:
         flat = t.reshape(-1)
         n = flat.numel()
-        per = math.ceil(n / world)
-        pad = per * world - n
-        if pad:
-            flat = torch.cat([flat, flat.new_zeros(pad)])
         if world == 1:
-            out.append(flat[:n].clone())
+            out.append(flat.clone())
             continue
-        per_rank_groups = _groups_for(flat[:per])
+        per0 = math.ceil(n / world)              # elements this rank ends up owning
+        gs = Q.aligned_group_size(per0)          # device kernels: groups of a multiple of 8 elements, never across ranks
+        per = (per0 + gs - 1) // gs * gs         # per-rank chunk padded to whole groups
+        if per * world != n:
+            full = flat.new_zeros(per * world)
+            for r in range(world):               # rank r's slice [r * per0, (r + 1) * per0) moves to chunk r
+                lo_r, hi_r = r * per0, min(n, (r + 1) * per0)
+                if hi_r > lo_r:
+                    full[r * per:r * per + hi_r - lo_r].copy_(flat[lo_r:hi_r])
+            flat = full
+        per_rank_groups = per // gs
         q, params = Q.quantize(flat.contiguous(), per_rank_groups * world, num_bits, Q.Symmetric)
         q_recv, p_recv = torch.empty_like(q), torch.empty_like(params)
         dist.all_to_all_single(q_recv.view(-1), q.view(-1), group=local)
         dist.all_to_all_single(p_recv.view(-1), params.view(-1), group=local)
         deq = Q.dequantize(q_recv, p_recv, per_rank_groups * world, num_bits, Q.Symmetric, dtype=torch.float32)
         red = deq.view(world, per).sum(0).div_(world)
-        lo = rank * per
-        valid = max(0, min(per, n - lo))
+        lo = rank * per0
+        valid = max(0, min(per0, n - lo))
         out.append(red[:valid].to(t.dtype))
     return out
 

@@ -788,16 +788,20 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         own range keeps its exact values (reference ``partition_parameters.py`` quantised all-gather)."""
         from deepspeed_b200.ops.quantizer import quantizer as Q
         n = u.shard_numel
-        g = max(1, n // 2048)
-        while n % g:
-            g -= 1
-        q, params = Q.quantize(shard.contiguous(), g, 8, Q.Symmetric)
+        gs = Q.aligned_group_size(n)       # the device kernels want groups of a multiple of 8 elements:
+        padded = (n + gs - 1) // gs * gs   # quantise a zero-padded copy of the shard when its length is not one
+        g = padded // gs
+        src = shard.contiguous()
+        if padded != n:
+            src = torch.nn.functional.pad(src, (0, padded - n))
+        q, params = Q.quantize(src, g, 8, Q.Symmetric)
         qs = torch.empty(self.shard_world * q.numel(), dtype=q.dtype, device=q.device)
         ps = torch.empty(self.shard_world * params.numel(), dtype=params.dtype, device=params.device)
         dist.all_gather_into_tensor(qs, q.reshape(-1), group=self.dp_group)
         dist.all_gather_into_tensor(ps, params.reshape(-1), group=self.dp_group)
         deq = Q.dequantize(qs, ps, g * self.shard_world, 8, Q.Symmetric, dtype=full.dtype)
-        full.copy_(deq.reshape(-1)[:full.numel()])
+        deq = deq.view(self.shard_world, padded)[:, :n].reshape(-1)
+        full.copy_(deq[:full.numel()])
         lo, hi = u.shard_range(self.shard_rank)
         full[lo:hi].copy_(shard)
 
