@@ -85,3 +85,30 @@ def _mics_hier():
 
 def test_mics_hierarchical_all_gather():
     run_distributed(_mics_hier, 4)
+
+
+def _qgz_uneven():
+    """qgZ with tensor sizes that are not multiples of 8 / of the world size: per-rank chunks are padded to whole quantisation
+    groups (the device kernels need groups of a multiple of 8 elements) and the result is still each rank's slice of the mean."""
+    import math
+    import torch.distributed as td
+    from deepspeed_b200.ops.quantizer import quantizer as Q
+    from deepspeed_b200.runtime.comm.coalesced_collectives import all_to_all_quant_reduce
+    r, w = td.get_rank(), td.get_world_size()
+    assert Q.aligned_group_size(5000) == 2048 and Q.aligned_group_size(13) == 16 and Q.aligned_group_size(3) == 8
+    for n in (1003, 37, 4096 + 5, 3):
+        torch.manual_seed(100 + r)
+        x = torch.randn(n)
+        (mine, ) = all_to_all_quant_reduce([x.clone()], {"local": None}, num_bits=8)
+        full = x.clone()
+        td.all_reduce(full)
+        full /= w
+        per = math.ceil(n / w)
+        want = full[r * per:min(n, (r + 1) * per)]
+        assert mine.shape == want.shape, (n, mine.shape, want.shape)
+        if want.numel():
+            assert (mine - want).abs().max() < 0.05 * (full.abs().max() + 1e-6), n
+
+
+def test_qgz_uneven_sizes_pad_to_aligned_groups():
+    run_distributed(_qgz_uneven, 2)
