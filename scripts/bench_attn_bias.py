@@ -11,6 +11,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from _clocks import Clocks
+
 
 def timeit(fn, warm=5, iters=20):
     for _ in range(warm):
@@ -95,12 +97,14 @@ def sparse(B, H, S, D, block, dtype=torch.bfloat16):
 
 def main():
     out = {"gpu": torch.cuda.get_device_name(0), "evoformer": [], "sparse": []}
+    clk = Clocks()
     for cfg in [(1, 128, 256, 8, 32), (1, 256, 384, 8, 32), (1, 512, 256, 4, 64), (1, 64, 768, 8, 32)]:
         out["evoformer"].append(evoformer(*cfg))
         print(json.dumps(out["evoformer"][-1]))
     for cfg in [(4, 16, 2048, 64, 16), (4, 16, 4096, 64, 64), (2, 16, 8192, 64, 64)]:
         out["sparse"].append(sparse(*cfg))
         print(json.dumps(out["sparse"][-1]))
+    out["clocks"] = clk.stop()
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/attn_bias_bench.json", "w") as f:
         json.dump(out, f, indent=1)

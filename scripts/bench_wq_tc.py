@@ -9,6 +9,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+from _clocks import Clocks
+
 from deepspeed_b200.inference.quantization import layers as QL
 
 
@@ -29,6 +31,7 @@ def timeit(fn, n_rot, warm=4, iters=20):
 
 def main():
     out = {"gpu": torch.cuda.get_device_name(0), "rows": []}
+    clk = Clocks()
     N, K = 14336, 4096
     n_rot = 6  # 6 x 58 MB (int8) > 126 MB L2
     for mode in ("int8", "int4", "fp8", "fp6"):
@@ -48,6 +51,7 @@ def main():
             rec["fused_weight_GBps"] = wbytes / rec["fused_ms"] / 1e6
             out["rows"].append(rec)
             print(json.dumps(rec))
+    out["clocks"] = clk.stop()
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/wq_tc_bench.json", "w") as f:
         json.dump(out, f, indent=1)
