@@ -85,7 +85,10 @@ class SwappedFlatState:
         if self._active is not None and self._active[1] <= s and e <= self._active[2]:
             i, s0, _ = self._active
             return self._bufs[i][s - s0:e - s0]
-        assert e - s <= self.window_elems, f"window {e - s} > {self.window_elems}; step in smaller pieces"
+        if e - s > self.window_elems:
+            # larger than one pinned window (initialisation, checkpoint / debug access to a whole shard): a range object
+            # that reads / writes the file window by window; the optimizer step itself always asks for <= one window
+            return _SwapRange(self, s, e)
         self.flush(wait=False)
         if self._prefetched is not None and self._prefetched[1:] == (s, e):
             i = self._prefetched[0]
@@ -100,17 +103,40 @@ class SwappedFlatState:
         self._active = (i, s, e)
         return self._bufs[i][:e - s]
 
-    def detach(self):
-        """Materialise the whole array (checkpoint save)."""
+    def read_range(self, a, b):
+        """Elements [a, b) as an ordinary host tensor (window-by-window reads)."""
         self.flush()
-        out = torch.empty(self._numel, dtype=self.dtype)
+        out = torch.empty(b - a, dtype=self.dtype)
         tmp = self._bufs[self._free_buf()]
         it = self.dtype.itemsize
-        for s in range(0, self._numel, self.window_elems):
-            e = min(s + self.window_elems, self._numel)
+        for s in range(a, b, self.window_elems):
+            e = min(s + self.window_elems, b)
             self.aio.sync_pread(tmp[:e - s], self.path, s * it)
-            out[s:e].copy_(tmp[:e - s])
+            out[s - a:e - a].copy_(tmp[:e - s])
         return out
+
+    def write_range(self, a, src):
+        """Overwrite elements [a, a + src.numel()) (window-by-window writes)."""
+        self.flush()
+        self._prefetched = None if self._prefetched is None or not (self._prefetched[1] < a + src.numel() and
+                                                                    a < self._prefetched[2]) else self._drop_prefetch()
+        src = src.reshape(-1)
+        b = a + src.numel()
+        assert 0 <= a and b <= self._numel
+        tmp = self._bufs[self._free_buf()]
+        it = self.dtype.itemsize
+        for s in range(a, b, self.window_elems):
+            e = min(s + self.window_elems, b)
+            tmp[:e - s].copy_(src[s - a:e - a])
+            self.aio.sync_pwrite(tmp[:e - s], self.path, s * it)
+
+    def _drop_prefetch(self):
+        self._drain()
+        return None
+
+    def detach(self):
+        """Materialise the whole array (checkpoint save)."""
+        return self.read_range(0, self._numel)
 
     def cpu(self):
         return self.detach()
@@ -137,6 +163,52 @@ class SwappedFlatState:
         return self
 
 
+class _SwapRange:
+    """``swapped[a:b]`` for a range larger than one pinned window: enough of the tensor surface for the code that
+    initialises, checkpoints or inspects a whole shard (``copy_``, ``to``, ``float``, ``cpu``, ``clone``)."""
+
+    def __init__(self, owner, a, b):
+        self.owner, self.a, self.b = owner, a, b
+        self.device, self.dtype = owner.device, owner.dtype
+
+    def numel(self):
+        return self.b - self.a
+
+    @property
+    def shape(self):
+        return torch.Size([self.b - self.a])
+
+    def copy_(self, src, non_blocking=False):
+        src = src.reshape(-1)
+        assert src.numel() == self.b - self.a
+        self.owner.write_range(self.a, src.detach().to("cpu", self.dtype))
+        return self
+
+    def _read(self):
+        return self.owner.read_range(self.a, self.b)
+
+    def to(self, *args, **kw):
+        return self._read().to(*args, **kw)
+
+    def float(self):
+        return self._read().float()
+
+    def cpu(self):
+        return self._read()
+
+    def detach(self):
+        return self._read()
+
+    def clone(self):
+        return self._read()
+
+    def contiguous(self):
+        return self._read()
+
+    def view(self, *shape):
+        return self._read().view(*shape)
+
+
 class FlatStateSwapper:
     """Owns the aio handle + swap folder of one ZeRO optimizer instance and turns a flat optimizer's state
     dict into NVMe-backed arrays."""
@@ -158,22 +230,30 @@ class FlatStateSwapper:
                                                  self.n_windows + (1 if self.pipeline else 0))
         return flat_opt
 
+    def wrap_master(self, numel, dtype=torch.float32):
+        """The fp32 master weights as a swapped array too (reference ``optimizer_utils.py:117``: the swapper owns the
+        fp32 parameter AND its optimizer states) -- nothing of the optimizer then stays resident in host memory."""
+        m = SwappedFlatState("fp32_master", numel, dtype, self.folder, self.aio, self.window_elems,
+                             self.n_windows + (1 if self.pipeline else 0))
+        self.extra = getattr(self, "extra", []) + [m]
+        return m
+
+    def _arrays(self, flat_opt):
+        return [t for t in list(flat_opt.state.values()) + getattr(self, "extra", []) if isinstance(t, SwappedFlatState)]
+
     def prefetch(self, flat_opt, s, e):
         if not self.pipeline:
             return
-        for t in flat_opt.state.values():
-            if isinstance(t, SwappedFlatState):
-                t.prefetch(s, e)
+        for t in self._arrays(flat_opt):
+            t.prefetch(s, e)
 
     def flush(self, flat_opt, wait=True):
-        for t in flat_opt.state.values():
-            if isinstance(t, SwappedFlatState):
-                t.flush(wait=False)
+        for t in self._arrays(flat_opt):
+            t.flush(wait=False)
         if wait:
             self.aio.wait()
-            for t in flat_opt.state.values():
-                if isinstance(t, SwappedFlatState):
-                    t._writing.clear()
+            for t in self._arrays(flat_opt):
+                t._writing.clear()
 
 
 # ---- per-parameter swapper (reference ``optimizer_utils.py:21-480``) ----------------------------------------------------

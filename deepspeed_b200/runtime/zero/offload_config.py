@@ -42,6 +42,7 @@ class DeepSpeedZeroOffloadOptimizerConfig(DeepSpeedConfigModel):
     fast_init: bool = False
     ratio: float = Field(1.0, ge=0.0, le=1.0)  # Twin-Flow: fraction of optimizer state on the host
     b200_swap_window: int = Field(pp_int(1 << 26), ge=1)  # NVMe tier: elements per pinned streaming window
+    b200_swap_master: bool = True  # NVMe tier: the fp32 master weights live in a swap file too (reference behaviour)
 
     @model_validator(mode="after")
     def set_pipeline(self):

@@ -29,7 +29,7 @@ def offload_optimizer_states(zo, include: Optional[Container[OffloadStateTypeEnu
             if torch.is_tensor(t):
                 moved[f"optim:{k}"] = t.device
                 t.data = _move(t.data, dev, pin_memory, non_blocking)
-    if want(OffloadStateTypeEnum.hp_params) and zo.master is not None:
+    if want(OffloadStateTypeEnum.hp_params) and torch.is_tensor(zo.master):  # (an NVMe-resident master is already off-device)
         moved["hp_params"] = zo.master.device
         zo.master.data = _move(zo.master.data, dev, pin_memory, non_blocking)
     if want(OffloadStateTypeEnum.lp_grads) or want(OffloadStateTypeEnum.contiguous_grad_buffer):

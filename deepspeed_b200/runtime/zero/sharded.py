@@ -410,19 +410,25 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
         # ---- master + optimizer state ---------------------------------------------------------------
         st_dev = "cpu" if self.offload_optimizer else dev
-        if lp == torch.float32 and not self.offload_optimizer:
-            self.master = None  # fp32 training: the lp shard *is* the master
-        else:
-            self.master = self._empty(self.arena_numel, self.master_dtype, st_dev, pin=True)
-            for rt in self.rts:
-                a = rt.u.arena_offset
-                self.master[a:a + rt.u.shard_numel].copy_(self._lp_shard(rt.u))
-        if self.offload_nvme and not isinstance(self.flat_opt, TorchOptimizerAdapter):
-            # NVMe tier: optimizer moments live in per-rank swap files and stream through pinned windows
+        nvme = self.offload_nvme and not isinstance(self.flat_opt, TorchOptimizerAdapter)
+        if nvme:
+            # NVMe tier: fp32 master weights and optimizer moments live in per-rank swap files and stream through pinned
+            # windows (reference swap_tensor/optimizer_utils.py:117, partitioned_optimizer_swapper.py:27)
             from deepspeed_b200.runtime.swap_tensor import FlatStateSwapper
             oo = self.zc.offload_optimizer
             self.state_swapper = FlatStateSwapper(oo, self.aio_config or {}, str(oo.nvme_path or "/tmp"),
                                                   dist.get_rank())
+        if lp == torch.float32 and not self.offload_optimizer:
+            self.master = None  # fp32 training: the lp shard *is* the master
+        else:
+            if nvme and getattr(self.zc.offload_optimizer, "b200_swap_master", True) and self.master_dtype == torch.float32:
+                self.master = self.state_swapper.wrap_master(self.arena_numel, self.master_dtype)
+            else:
+                self.master = self._empty(self.arena_numel, self.master_dtype, st_dev, pin=True)
+            for rt in self.rts:
+                a = rt.u.arena_offset
+                self.master[a:a + rt.u.shard_numel].copy_(self._lp_shard(rt.u))
+        if nvme:
             self.state_swapper.wrap(self.flat_opt, self.arena_numel)
         else:
             self.flat_opt.init_state(self.arena_numel, st_dev, torch.float32, pin=True)
@@ -1428,6 +1434,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 continue
             dst = self._lp_shard(u)[s - u.arena_offset:e - u.arena_offset]
             src = self.master[s:e]
+            if not isinstance(src, torch.Tensor):
+                src = src.detach()  # NVMe-resident master: read this range back window by window
             if src.device != dst.device:
                 dst.copy_(src.to(dst.dtype), non_blocking=True)
             else:

@@ -99,8 +99,30 @@ def _train(mode, nvme_dir, out):
     sd = {n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()}
     torch.save(sd, out)
     if mode == "nvme":
-        assert eng.optimizer.state_swapper is not None
-        assert any(f.endswith(".swp") for _, _, fs in os.walk(nvme_dir) for f in fs)
+        from deepspeed_b200.runtime.swap_tensor.optimizer_utils import SwappedFlatState
+        from deepspeed_b200.utils import safe_set_full_fp32_param
+        zo = eng.optimizer
+        assert zo.state_swapper is not None
+        assert isinstance(zo.master, SwappedFlatState), "the fp32 master weights must be swapped too, not host resident"
+        files = [f for _, _, fs in os.walk(nvme_dir) for f in fs]
+        assert "fp32_master.swp" in files and any(f.startswith("exp_avg") for f in files), files
+        # debug / checkpoint surface on top of the file-backed arrays (ranges larger than the 200-element window)
+        p0 = next(iter(eng.module.parameters()))
+        before = safe_get_full_fp32_param(p0).clone()
+        safe_set_full_fp32_param(p0, before + 1.0)
+        torch.testing.assert_close(safe_get_full_fp32_param(p0), before + 1.0)
+        safe_set_full_fp32_param(p0, before)
+        m = safe_get_full_optimizer_state(p0, "exp_avg")
+        assert m is not None and m.shape == p0.shape and m.abs().sum() > 0
+        ck = os.path.join(nvme_dir, "ckpt")
+        eng.save_checkpoint(ck, tag="t")
+        x, y = make_batch(1, 4, g)
+        eng.backward(eng(x.bfloat16(), y))
+        eng.step()
+        moved = safe_get_full_fp32_param(p0).clone()
+        assert not torch.equal(moved, before)
+        eng.load_checkpoint(ck, tag="t")
+        torch.testing.assert_close(safe_get_full_fp32_param(p0), before)  # master restored from the checkpoint
 
 
 def test_nvme_offload_matches_cpu_offload(tmp_path):
