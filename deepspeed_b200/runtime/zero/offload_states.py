@@ -36,7 +36,7 @@ def offload_optimizer_states(zo, include: Optional[Container[OffloadStateTypeEnu
         if zo.grad_arena is not None:
             moved["grads"] = zo.grad_arena.device
             zo.grad_arena.data = _move(zo.grad_arena.data, dev, pin_memory, non_blocking)
-    if want(OffloadStateTypeEnum.lp_params) and getattr(zo, "lp_arena", None) is not None and zo.stage == 3:
+    if want(OffloadStateTypeEnum.lp_params) and torch.is_tensor(getattr(zo, "lp_arena", None)) and zo.stage == 3:
         moved["lp_params"] = zo.lp_arena.device
         zo.lp_arena.data = _move(zo.lp_arena.data, dev, pin_memory, non_blocking)
     zo._offloaded_states = moved

@@ -139,6 +139,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         op = self.zc.offload_param
         self.offload_optimizer = bool(oo and str(getattr(oo.device, "value", oo.device)) != "none")
         self.offload_param = bool(op and str(getattr(op.device, "value", op.device)) != "none") and self.stage == 3
+        self.offload_param_nvme = self.offload_param and str(getattr(op.device, "value", op.device)) == "nvme"
         self.offload_pin = bool(oo.pin_memory) if oo else False
         self.offload_ratio = float(oo.ratio) if oo else 1.0
         self.grad_allreduce_enabled = lambda: True
@@ -358,7 +359,19 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self.transient = S3
         # ---- low-precision storage ------------------------------------------------------------
         if S3:
-            if self.offload_param:
+            if self.offload_param_nvme:
+                # ZeRO-Infinity parameter tier: this rank's low-precision shards live in a swap file; a unit's shard passes
+                # through a pinned window on its way to the all-gather and on its way back from the optimizer (reference
+                # swap_tensor/partitioned_param_swapper.py:36 AsyncPartitionedParameterSwapper)
+                import os as _os
+                from deepspeed_b200.runtime.swap_tensor.aio_config import make_handle
+                from deepspeed_b200.runtime.swap_tensor.optimizer_utils import SwappedFlatState
+                opc = self.zc.offload_param
+                folder = _os.path.join(str(opc.nvme_path or "/tmp"), "zero_stage_3", f"{str(lp).split('.')[-1]}params",
+                                       f"rank{dist.get_rank()}")
+                self.lp_arena = SwappedFlatState("lp_params", self.arena_numel, lp, folder, make_handle(self.aio_config or {}),
+                                                 max(u.shard_numel for u in self.units), max(3, int(opc.buffer_count or 3)))
+            elif self.offload_param:
                 self.lp_arena = self._empty(self.arena_numel, lp, "cpu", pin=True)
             else:
                 self.lp_arena = self._symm_or_empty(self.arena_numel, lp)  # peers gather straight from it
@@ -745,7 +758,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         with ctx:
             if self.offload_param:
                 lo, hi = u.shard_range(self.shard_rank)
-                full[lo:hi].copy_(shard, non_blocking=True)
+                # (NVMe tier: the pinned window behind `shard` is recycled by the next unit -- finish the copy first)
+                full[lo:hi].copy_(shard, non_blocking=not self.offload_param_nvme)
                 shard = full[lo:hi]
             self._all_gather(full, shard, u, rt=rt)
             if self.on_cuda:

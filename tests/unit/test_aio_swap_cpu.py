@@ -239,3 +239,56 @@ def test_param_swapper_param_object_api(tmp_path):
     assert torch.equal(got, new[0])
     sw.remove_partition_and_release_buffers([params[0]])
     assert sw.available_swap_in_buffers() == 3
+
+
+def _param_tier(mode, nvme_dir, out):
+    """ZeRO-3 with the parameter shards on the host (pinned) or in NVMe swap files: identical training trajectory."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    torch.manual_seed(0)
+    cfg = base_config(3, "bf16", 1, 1.0)
+    z = cfg["zero_optimization"]
+    z["stage3_param_persistence_threshold"] = 0
+    z["offload_optimizer"] = {"device": "cpu"}
+    if mode == "cpu":
+        z["offload_param"] = {"device": "cpu"}
+    else:
+        z["offload_param"] = {"device": "nvme", "nvme_path": nvme_dir, "buffer_count": 3}
+        cfg["aio"] = {"block_size": 65536, "queue_depth": 4}
+    eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    if mode == "nvme":
+        from deepspeed_b200.runtime.swap_tensor.optimizer_utils import SwappedFlatState
+        assert isinstance(eng.optimizer.lp_arena, SwappedFlatState)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(4):
+        x, y = make_batch(w, 4, g)
+        loss = eng(x[r * 4:(r + 1) * 4].bfloat16(), y[r * 4:(r + 1) * 4])
+        eng.backward(loss)
+        eng.step()
+    sd = {n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()}
+    if mode == "nvme":  # checkpoint round trip on top of the file-backed shards
+        ck = os.path.join(nvme_dir, "ckpt")
+        eng.save_checkpoint(ck, tag="t")
+        x, y = make_batch(w, 4, g)
+        eng.backward(eng(x[r * 4:(r + 1) * 4].bfloat16(), y[r * 4:(r + 1) * 4]))
+        eng.step()
+        eng.load_checkpoint(ck, tag="t")
+        for n, p in eng.module.named_parameters():
+            torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), sd[n])
+        x, y = make_batch(w, 4, torch.Generator().manual_seed(5))
+        assert torch.isfinite(eng(x[r * 4:(r + 1) * 4].bfloat16(), y[r * 4:(r + 1) * 4]))
+    if r == 0:
+        torch.save(sd, out)
+        if mode == "nvme":
+            files = [f for _, _, fs in os.walk(nvme_dir) for f in fs]
+            assert "lp_params.swp" in files, files
+
+
+def test_nvme_param_tier_matches_host_param_tier(tmp_path):
+    a, b = str(tmp_path / "cpu.pt"), str(tmp_path / "nvme.pt")
+    run_distributed(_param_tier, 2, ("cpu", "", a))
+    run_distributed(_param_tier, 2, ("nvme", str(tmp_path / "nvme"), b))
+    sa, sb = torch.load(a), torch.load(b)
+    for k in sa:
+        torch.testing.assert_close(sa[k], sb[k], atol=1e-6, rtol=1e-6)
