@@ -14,73 +14,56 @@ import torch
 from deepspeed_b200 import comm as dist
 
 
-def _block_attn(q, k, v, causal_diag, scale):
-    """Returns (out [B,H,S,D] fp32, lse [B,H,S] fp32) for one K/V block."""
-    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
-    if causal_diag:
-        Sq, Sk = s.shape[-2:]
-        mask = torch.ones(Sq, Sk, dtype=torch.bool, device=s.device).tril_()
-        s = s.masked_fill(~mask, float("-inf"))
-    lse = torch.logsumexp(s, dim=-1)
-    p = torch.exp(s - lse[..., None])
-    return torch.matmul(p, v.float()), lse
-
-
-def _merge(out, lse, o2, l2):
-    if out is None:
-        return o2, l2
-    new = torch.logaddexp(lse, l2)
-    out = out * torch.exp(lse - new)[..., None] + o2 * torch.exp(l2 - new)[..., None]
-    return out, new
-
-
 class _RingAttention(torch.autograd.Function):
+    """Per-hop attention and its backward run on the framework's pair kernels (``fpdt_layer._pair_fwd / _pair_bwd``: tcgen05
+    flash attention for head dim 128 / bf16, the register-accumulator kernels for head dims 16-64, fp32 PyTorch otherwise);
+    like FPDT, the backward of every (local Q, visiting K/V) pair uses the FINAL output and log-sum-exp of the local queries,
+    so the pair contributions simply add and nothing is recomputed in forward mode."""
 
     @staticmethod
     def forward(ctx, q, k, v, group, causal, scale):
+        from deepspeed_b200.sequence.fpdt_layer import _merge, _pair_fwd
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         scale = scale or 1.0 / math.sqrt(q.shape[-1])
+        qs, kb, vb = (t.permute(0, 2, 1, 3).contiguous() for t in (q, k, v))  # [B, S, H, D] blocks travel the ring
         out = lse = None
-        kb, vb = k.contiguous(), v.contiguous()
         src = rank
         for hop in range(world):
             if not causal or src <= rank:
-                o2, l2 = _block_attn(q, kb, vb, causal and src == rank, scale)
+                o2, l2 = _pair_fwd(qs, kb, vb, causal and src == rank, scale)
                 out, lse = _merge(out, lse, o2, l2)
             if hop < world - 1:
                 kb, vb = _rotate(kb, vb, group, rank, world)
                 src = (src - 1) % world
-        ctx.save_for_backward(q, k, v, out.to(q.dtype), lse)
+        o = out.to(q.dtype)
+        ctx.save_for_backward(qs, k, v, o, lse)
         ctx.group, ctx.causal, ctx.scale = group, causal, scale
-        return out.to(q.dtype)
+        return o.permute(0, 2, 1, 3)
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, out, lse = ctx.saved_tensors
+        from deepspeed_b200.sequence.fpdt_layer import _pair_bwd
+        qs, k, v, o, lse = ctx.saved_tensors
         group, causal, scale = ctx.group, ctx.causal, ctx.scale
         world, rank = dist.get_world_size(group), dist.get_rank(group)
-        delta = (dout.float() * out.float()).sum(-1)  # [B,H,S]
-        dq = torch.zeros_like(q, dtype=torch.float32)
-        kb, vb = k.contiguous(), v.contiguous()
-        dkb = torch.zeros_like(k, dtype=torch.float32)
-        dvb = torch.zeros_like(v, dtype=torch.float32)
+        do = dout.permute(0, 2, 1, 3).contiguous()
+        kb, vb = (t.permute(0, 2, 1, 3).contiguous() for t in (k, v))
+        dq = torch.zeros(qs.shape, dtype=torch.float32, device=qs.device)
+        dkb = torch.zeros(kb.shape, dtype=torch.float32, device=kb.device)
+        dvb = torch.zeros(vb.shape, dtype=torch.float32, device=vb.device)
         src = rank
         for hop in range(world):
             if not causal or src <= rank:
-                s = torch.matmul(q.float(), kb.float().transpose(-1, -2)) * scale
-                if causal and src == rank:
-                    Sq, Sk = s.shape[-2:]
-                    s = s.masked_fill(~torch.ones(Sq, Sk, dtype=torch.bool, device=s.device).tril_(), float("-inf"))
-                p = torch.exp(s - lse[..., None])
-                dvb += torch.matmul(p.transpose(-1, -2), dout.float())
-                dp = torch.matmul(dout.float(), vb.float().transpose(-1, -2))
-                ds = p * (dp - delta[..., None]) * scale
-                dq += torch.matmul(ds, kb.float())
-                dkb += torch.matmul(ds.transpose(-1, -2), q.float())
+                dq_i, dk_i, dv_i = _pair_bwd(do, qs, kb, vb, o, lse, causal and src == rank, scale)
+                dq += dq_i
+                dkb += dk_i
+                dvb += dv_i
             # the K/V block travels on together with its gradient accumulators; after P hops both are home
-            kb, vb, dkb, dvb = _rotate4(kb, vb, dkb, dvb, group, rank, world)
+            if world > 1:
+                kb, vb, dkb, dvb = _rotate4(kb, vb, dkb, dvb, group, rank, world)
             src = (src - 1) % world
-        return dq.to(q.dtype), dkb.to(k.dtype), dvb.to(v.dtype), None, None, None
+        back = lambda t, like: t.to(like.dtype).permute(0, 2, 1, 3)
+        return back(dq, qs), back(dkb, k), back(dvb, v), None, None, None
 
 
 def _rotate(a, b, group, rank, world):
