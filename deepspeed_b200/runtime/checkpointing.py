@@ -346,8 +346,41 @@ class CheckpointMixin:
                 a = rt.u.arena_offset
                 zo.master[a:a + rt.u.shard_numel].copy_(zo._lp_shard(rt.u))
 
+    def _saved_zero_shard_files(self, load_dir, tag):
+        """Optimizer shard files of every saved DP rank for this model-parallel rank, in DP-rank order."""
+        import glob
+        import re
+        own = os.path.basename(self._get_zero_ckpt_name(load_dir, tag))
+        pat = re.sub(r"zero_pp_rank_\d+_", "zero_pp_rank_*_", own)
+        files = glob.glob(os.path.join(load_dir, str(tag), pat))
+        key = lambda f: int(re.search(r"zero_pp_rank_(\d+)_", os.path.basename(f)).group(1))
+        return sorted(files, key=key)
+
     def _load_zero_checkpoint(self, load_dir, tag, load_optimizer_states=True):
         path = self._get_zero_ckpt_name(load_dir, tag)
+        zo = self.optimizer
+        saved = self._saved_zero_shard_files(load_dir, tag)
+        want = 1 if getattr(self, "_optimizer_replicated", False) else getattr(zo, "shard_world", 1)
+        if saved and len(saved) != want:
+            # the data-parallel degree changed since the checkpoint was written: reassemble every parameter from ALL saved
+            # shards and re-partition (reference `elastic_checkpoint`; here for stages 1-3)
+            from deepspeed_b200.runtime.zero import ref_layout
+            shards = [self.checkpoint_engine.load(f, map_location="cpu")["optimizer_state_dict"] for f in saved]
+            if not all(ref_layout.is_reference_layout(sd) for sd in shards):
+                raise ValueError(f"the checkpoint under {load_dir}/{tag} was written by {len(saved)} data-parallel ranks in the "
+                                 f"rank-local arena layout; only reference-layout shards (checkpoint.b200_shard_layout="
+                                 f"'reference', the default) can be loaded at a different degree ({want}) -- or convert with "
+                                 f"ds_to_universal")
+            parts = zo.parts if hasattr(zo, "parts") else [zo]
+            if len(parts) != 1:
+                raise ValueError("loading at a different data-parallel degree is not supported for multi-domain (MoE / Twin-Flow) "
+                                 "optimizers; convert with ds_to_universal")
+            ref_layout.import_reference_state_elastic(
+                parts[0], shards, load_optimizer_states=load_optimizer_states,
+                load_from_fp32_weights=self._config.zero_config.load_from_fp32_weights
+                or self.zero_optimization_partition_weights(), param_shapes=getattr(self, "_loaded_param_shapes", None))
+            log_dist(f"loaded zero checkpoint written by {len(saved)} data-parallel ranks into {want} (elastic)", ranks=[0])
+            return True
         if not os.path.exists(path):
             logger.warning(f"The following zero checkpoint path is missing: {path}; if the DP world size changed, "
                            f"convert with ds_to_universal and set checkpoint.load_universal")

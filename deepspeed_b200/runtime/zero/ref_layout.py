@@ -363,3 +363,40 @@ def import_reference_state(zo, sd, load_optimizer_states=True, load_from_fp32_we
                 a0 = rt.u.arena_offset
                 zo._lp_shard(rt.u).copy_(flat[a0:a0 + rt.u.shard_numel])
         zo._refresh_lp_from_master()
+
+
+@torch.no_grad()
+def import_reference_state_elastic(zo, shards, load_optimizer_states=True, load_from_fp32_weights=True, param_shapes=None):
+    """Load a reference-layout checkpoint written with a DIFFERENT data-parallel degree (the reference's
+    ``elastic_checkpoint`` behaviour, ``stage_1_and_2.py:2290 _restore_elastic_base_optimizer_state`` -- extended here to
+    stage 3): ``shards`` are the optimizer shards of ALL saved DP ranks (in rank order); every parameter's fp32 value and
+    optimizer moments are reassembled from them and scattered into this run's arenas.  Host memory: the full fp32 model +
+    moments once per rank while loading, like the reference's elastic path."""
+    from deepspeed_b200.checkpoint.ds_to_universal import reference_param_states
+    order = _named_order(zo, param_shapes)
+    shapes = [OrderedDict((s.name, tuple(s.shape)) for _, s in lst) for lst in order]
+    params, steps, _ = reference_param_states(shards, shapes)
+    arenas = _state_arenas(zo)
+    wanted = (["fp32"] if load_from_fp32_weights else []) + ([k for k in arenas if k != "fp32"] if load_optimizer_states else [])
+    for lst in order:
+        for rt, s in lst:
+            st = params[s.name]
+            for key in wanted:
+                if key not in st:
+                    raise KeyError(f"checkpoint lacks optimizer state '{key}' for parameter '{s.name}'")
+                zo._scatter_into_arena(arenas[key], rt, s, st[key])
+    sd = shards[0]
+    ls = sd.get(LOSS_SCALER)
+    if isinstance(ls, dict):
+        zo.loss_scaler.load_state_dict(ls)
+    if load_optimizer_states:
+        if "b200_group_steps" in sd:
+            zo.group_steps = list(sd["b200_group_steps"])
+        else:
+            zo.group_steps = [int(st or 0) for st in steps][:len(zo.group_steps)] + zo.group_steps[len(steps):]
+        for g, saved in zip(zo.param_groups, (_inner_state(sd) or {}).get("param_groups", []) if isinstance(_inner_state(sd), dict) else []):
+            for k, v in saved.items():
+                if k not in ("params", ) and k in g:
+                    g[k] = v
+    if load_from_fp32_weights:
+        zo._refresh_lp_from_master()

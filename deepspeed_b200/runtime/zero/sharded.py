@@ -1664,6 +1664,10 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     def _lp_arena_as_flat(self):
         if self.lp_arena is not None:
             return self.lp_arena
+        if self.shard_world == 1 and self.full_arena is not None:
+            # one shard per unit == the whole unit, units back to back: the resident buffer IS the arena (a writable view,
+            # so loaders that scatter into it -- fp32 training has no separate master -- really update the parameters)
+            return self.full_arena[:self.arena_numel]
         return torch.cat([self._lp_shard(u) for u in self.units])
 
     def set_full_hp_param(self, value, p):

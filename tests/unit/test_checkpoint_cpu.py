@@ -66,6 +66,32 @@ def test_save_resume_same_shape(tmp_path, stage):
     run_distributed(_resume_worker, 2, (d, stage))
 
 
+def _elastic_resume_worker(d, stage):
+    """Resume at a different data-parallel degree than the checkpoint was written with, in-engine (no offline conversion)."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param, safe_get_full_optimizer_state
+    torch.manual_seed(77)
+    eng, *_ = ds.initialize(model=SimpleModel(), config=_cfg(stage, ds.comm.get_world_size()))
+    path, client = eng.load_checkpoint(d)
+    assert path is not None and client["hello"] == 7 and eng.global_steps == 3
+    at_save = torch.load(os.path.join(d, "expect_at_save.pt"))
+    for n, p in eng.module.named_parameters():
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), at_save[n], atol=0, rtol=0)
+        m = safe_get_full_optimizer_state(p, "exp_avg")
+        assert m is not None and m.abs().sum() > 0, "optimizer moments must be restored too"
+    _steps(eng, 2, 2)
+    exp = torch.load(os.path.join(d, "expect.pt"))
+    for n, p in eng.module.named_parameters():
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), exp[n], atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("stage,saved_world,new_world", [(1, 2, 1), (2, 2, 4), (3, 2, 1), (3, 1, 2)])
+def test_resume_at_a_different_dp_degree(tmp_path, stage, saved_world, new_world):
+    d = str(tmp_path)
+    run_distributed(_save_worker, saved_world, (d, stage))
+    run_distributed(_elastic_resume_worker, new_world, (d, stage))
+
+
 def _universal_resume_worker(d, stage):
     import deepspeed_b200 as ds
     from deepspeed_b200.utils import safe_get_full_fp32_param
