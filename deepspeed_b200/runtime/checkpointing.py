@@ -47,8 +47,17 @@ class CheckpointMixin:
         self._dp_rank_for_ckpt = dp_rank
 
     # ---- names ---------------------------------------------------------------------------------------
+    def _ckpt_mp_rank(self):
+        """The ``mp_rank`` of the file names.  Under pipeline parallelism the reference counts every rank that shares a
+        data-parallel index as one "model" group (``pipe/topology.py:302-313 ds_model_rank``: stage-major, tensor-slice
+        minor), so each pipeline stage writes its own model-states / optimizer files."""
+        grid = getattr(self, "grid", None)
+        if grid is not None and getattr(grid, "pipe_parallel_size", 1) > 1:
+            return grid.get_stage_id() * max(1, grid.get_model_parallel_world_size()) + grid.get_model_parallel_rank()
+        return _mp_rank()
+
     def _get_ckpt_name(self, checkpoints_path, tag, mp_placeholder=None):
-        mp = f"{_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
+        mp = f"{self._ckpt_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
         if self.zero_optimization_partition_weights():
             name = f"zero_pp_rank_{self._dp_rank_for_ckpt}_mp_rank_{mp}_model_states.pt"
         else:
@@ -56,7 +65,7 @@ class CheckpointMixin:
         return os.path.join(checkpoints_path, str(tag), name)
 
     def _get_zero_ckpt_prefix(self, dp_rank, bf16_mode):
-        return f"{'bf16_' if bf16_mode else ''}zero_pp_rank_{dp_rank}_mp_rank_{_mp_rank():02d}"
+        return f"{'bf16_' if bf16_mode else ''}zero_pp_rank_{dp_rank}_mp_rank_{self._ckpt_mp_rank():02d}"
 
     def _get_zero_ckpt_name(self, checkpoints_path, tag):
         bf16 = self.bfloat16_enabled()
@@ -64,7 +73,7 @@ class CheckpointMixin:
         return os.path.join(checkpoints_path, str(tag), f"{self._get_zero_ckpt_prefix(dp_rank, bf16)}_optim_states.pt")
 
     def _get_expert_ckpt_name(self, checkpoints_path, layer_id, expert_id, tag, mp_placeholder=None):
-        mp = f"{_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
+        mp = f"{self._ckpt_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
         return os.path.join(checkpoints_path, str(tag), f"layer_{layer_id}_expert_{expert_id}_mp_rank_{mp}_model_states.pt")
 
     # ---- tag validation -----------------------------------------------------------------------------

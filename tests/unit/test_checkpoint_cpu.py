@@ -510,3 +510,129 @@ def test_stock_zero_to_fp32_reads_our_checkpoint(tmp_path, stage):
     assert set(exp) <= set(got)
     for n, v in exp.items():
         torch.testing.assert_close(got[n].float(), v, atol=1e-6, rtol=1e-5)
+
+
+def _moe_ckpt_worker(d, phase):
+    """Expert-parallel MoE checkpoint: dense weights in the model-states file, every expert in its own
+    ``layer_#_expert_#_mp_rank_##_model_states.pt`` (reference ``engine.py:3376 _save_moe_checkpoint``), the dense and the
+    expert optimizer domains in the ZeRO shard files.  A fresh engine resumed from it continues identically."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.models.mixtral import MixtralForCausalLM, mixtral_config
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    w, r = ds.comm.get_world_size(), ds.comm.get_rank()
+    torch.manual_seed(0 if phase == "save" else 99)
+    cfg = mixtral_config("tiny-moe", ep_size=w)
+    eng, *_ = ds.initialize(model=MixtralForCausalLM(cfg), config={
+        "train_micro_batch_size_per_gpu": 2, "optimizer": {"type": "AdamW", "params": {"lr": 2e-3}},
+        "zero_optimization": {"stage": 1}})
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randint(0, cfg.vocab_size, (2 * w, 32), generator=g)[r * 2:(r + 1) * 2] for _ in range(5)]
+
+    def run(lo, hi):
+        for ids in batches[lo:hi]:
+            eng.backward(eng(ids, labels=ids))
+            eng.step()
+
+    if phase == "save":
+        run(0, 3)
+        eng.save_checkpoint(d, tag="moe")
+        ds.comm.barrier()
+        files = os.listdir(os.path.join(d, "moe"))
+        assert any(f.startswith("layer_") and "_expert_" in f for f in files), files
+        run(3, 5)
+        torch.save({n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()},
+                   os.path.join(d, f"expect_rank{r}.pt"))
+    else:
+        path, _ = eng.load_checkpoint(d, tag="moe")
+        assert path is not None and eng.global_steps == 3
+        run(3, 5)
+        exp = torch.load(os.path.join(d, f"expect_rank{r}.pt"))
+        for n, p in eng.module.named_parameters():  # experts are rank-local: compared per rank
+            torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), exp[n], atol=2e-6, rtol=1e-5, msg=n)
+
+
+def test_moe_expert_parallel_checkpoint_resume(tmp_path):
+    d = str(tmp_path)
+    run_distributed(_moe_ckpt_worker, 2, (d, "save"))
+    run_distributed(_moe_ckpt_worker, 2, (d, "load"))
+
+
+def _pipe_ckpt_worker(d, phase):
+    """Pipeline checkpoint: one ``layer_XX-model_states.pt`` per layer (reference ``pipe/module.py:605 save_state_dict``),
+    loadable by a fresh 2-stage engine; training continues identically."""
+    import deepspeed_b200 as ds
+    from torch import nn
+    from deepspeed_b200.pipe import PipelineModule
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+
+    class Blk(nn.Module):
+
+        def __init__(self, dd):
+            super().__init__()
+            self.l = nn.Linear(dd, dd)
+
+        def forward(self, x):
+            return torch.tanh(self.l(x))
+
+    torch.manual_seed(0 if phase == "save" else 5)
+    dd, micro, mbs = 16, 2, 2
+    model = PipelineModule(layers=[Blk(dd) for _ in range(4)], num_stages=2, loss_fn=nn.MSELoss(), partition_method="uniform")
+    eng, *_ = ds.initialize(model=model, config={"train_micro_batch_size_per_gpu": mbs, "gradient_accumulation_steps": micro,
+                                                 "optimizer": {"type": "Adam", "params": {"lr": 1e-2}},
+                                                 "zero_optimization": {"stage": 0}})
+    g = torch.Generator().manual_seed(5)
+    data = [[(torch.randn(mbs, dd, generator=g), torch.randn(mbs, dd, generator=g)) for _ in range(micro)] for _ in range(4)]
+    own = {n: p for n, p in model.named_parameters()}
+    if phase == "save":
+        for it in range(2):
+            eng.train_batch(data_iter=iter(data[it]))
+        eng.save_checkpoint(d, tag="pp")
+        ds.comm.barrier()
+        files = os.listdir(os.path.join(d, "pp"))
+        assert sum(f.startswith("layer_") and f.endswith("model_states.pt") for f in files) == 4, files
+        for it in range(2, 4):
+            eng.train_batch(data_iter=iter(data[it]))
+        torch.save({n: safe_get_full_fp32_param(p).cpu() for n, p in own.items()},
+                   os.path.join(d, f"expect_stage{eng.stage_id}.pt"))
+    else:
+        path, _ = eng.load_checkpoint(d, tag="pp")
+        assert path is not None and eng.global_steps == 2
+        for it in range(2, 4):
+            eng.train_batch(data_iter=iter(data[it]))
+        exp = torch.load(os.path.join(d, f"expect_stage{eng.stage_id}.pt"))
+        for n, p in own.items():
+            torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), exp[n], atol=2e-6, rtol=1e-5, msg=n)
+
+
+def test_pipeline_layer_checkpoint_resume(tmp_path):
+    d = str(tmp_path)
+    run_distributed(_pipe_ckpt_worker, 2, (d, "save"))
+    run_distributed(_pipe_ckpt_worker, 2, (d, "load"))
+
+
+def _sched_ckpt_worker(d):
+    """LR scheduler state, ``latest`` tag file and client state ride the checkpoint (reference ``engine.py:3218-3290``)."""
+    import deepspeed_b200 as ds
+    cfg = base_config(1, "fp32", 1, 0.0)
+    cfg["scheduler"] = {"type": "WarmupLR", "params": {"warmup_min_lr": 0.0, "warmup_max_lr": 1e-2, "warmup_num_steps": 10}}
+    torch.manual_seed(0)
+    eng, _, _, sched = ds.initialize(model=SimpleModel(), config=cfg)
+    _steps(eng, 4, 1)
+    lr_at_save = eng.get_lr()[0]
+    eng.save_checkpoint(d, client_state={"epoch": 3})  # default tag global_step4 + 'latest'
+    assert open(os.path.join(d, "latest")).read().strip() == "global_step4"
+    _steps(eng, 2, 2)
+    assert eng.get_lr()[0] > lr_at_save
+    torch.manual_seed(9)
+    eng2, _, _, sched2 = ds.initialize(model=SimpleModel(), config=cfg)
+    path, client = eng2.load_checkpoint(d)  # resolves 'latest'
+    assert path is not None and "global_step4" in path and client["epoch"] == 3
+    assert eng2.global_steps == 4 and abs(eng2.get_lr()[0] - lr_at_save) < 1e-12
+    _steps(eng2, 2, 2)
+    assert abs(eng2.get_lr()[0] - eng.get_lr()[0]) < 1e-12
+    path3, _ = eng2.load_checkpoint(d, tag="does_not_exist")
+    assert path3 is None
+
+
+def test_scheduler_state_latest_tag_and_client_state(tmp_path):
+    run_distributed(_sched_ckpt_worker, 1, (str(tmp_path), ))
