@@ -584,6 +584,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             if g is None:
                 return
             self._in_backward = True
+            if g.is_sparse:
+                # nn.Embedding(sparse=True) / `sparse_gradients`: the unit's gradient lives in one flat dense buffer that is
+                # reduced as a whole over NVLink, so a sparse gradient is densified on arrival (the reference's CSR
+                # all-reduce, engine.py:2530 sparse_allreduce, trades bandwidth that NVSwitch does not lack)
+                g = g.to_dense()
             view = self._grad_view(rt, slot)
             if getattr(slot, "_written", False):
                 view.add_(g.reshape(-1))

@@ -169,3 +169,61 @@ def _raw_p2p():
 
 def test_raw_p2p_send_recv():
     run_distributed(_raw_p2p, 2)
+
+
+class _Emb(nn.Module):
+
+    def __init__(self, v, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(v, d) * 0.1)
+
+    def forward(self, ids):
+        return torch.nn.functional.embedding(ids, self.weight)
+
+
+def _tied_head(mod, x):
+    return torch.matmul(x, mod.weight.t())
+
+
+def _pipe_variants(mode):
+    """ZeRO-1 under the pipeline engine, per-layer activation checkpointing, and an embedding tied between the first and the
+    last stage (``TiedLayerSpec``: the copies must receive the same summed gradient and stay identical)."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.pipe import LayerSpec, PipelineModule, TiedLayerSpec
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    torch.manual_seed(0)
+    d, micro, mbs, V = 16, 2, 2, 32
+    if mode == "tied":
+        layers = [TiedLayerSpec("emb", _Emb, V, d), LayerSpec(_Blk, d), LayerSpec(_Blk, d),
+                  TiedLayerSpec("emb", _Emb, V, d, forward_fn=_tied_head)]
+        loss_fn = lambda logits, y: nn.functional.cross_entropy(logits.reshape(-1, V), y.reshape(-1))
+    else:
+        layers = [_Blk(d) for _ in range(4)]
+        loss_fn = nn.MSELoss()
+    kw = {"activation_checkpoint_interval": 1} if mode == "ckpt" else {}
+    model = PipelineModule(layers=layers, num_stages=2, loss_fn=loss_fn, partition_method="uniform", **kw)
+    cfg = {"train_micro_batch_size_per_gpu": mbs, "gradient_accumulation_steps": micro,
+           "optimizer": {"type": "Adam", "params": {"lr": 1e-2}}, "zero_optimization": {"stage": 1 if mode == "zero1" else 0}}
+    eng, *_ = ds.initialize(model=model, config=cfg)
+    losses = []
+    for _ in range(6):
+        g = torch.Generator().manual_seed(1)
+        if mode == "tied":
+            ids = torch.randint(0, V, (mbs, 5), generator=g)
+            data = [(ids, ids) for _ in range(micro)]
+        else:
+            data = [(torch.randn(mbs, d, generator=g), torch.randn(mbs, d, generator=g)) for _ in range(micro)]
+        losses.append(eng.train_batch(data_iter=iter(data)).item())
+    assert losses[-1] < losses[0] - 0.1, losses
+    if mode == "tied":
+        w = [p for n, p in model.named_parameters() if p.shape == (V, d)][0]
+        full = safe_get_full_fp32_param(w)
+        both = [torch.empty_like(full) for _ in range(2)]
+        torch.distributed.all_gather(both, full)
+        assert torch.allclose(both[0], both[1], atol=1e-6), (both[0] - both[1]).abs().max()
+    return losses
+
+
+@pytest.mark.parametrize("mode", ["zero1", "ckpt", "tied"])
+def test_pipeline_zero1_checkpointing_and_tied_layers(mode):
+    run_distributed(_pipe_variants, 2, (mode, ))

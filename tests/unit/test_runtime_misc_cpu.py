@@ -171,3 +171,114 @@ def test_weight_quantization_megatron_state_dict():
     halves = wq.merge_scales_split(2)
     assert len(halves) == 2 and halves[0].shape == (2, 4, 4)
     assert wq.is_qkv(ref["l0.attention.query_key_value.weight"]) and wq.is_mlp(ref["l0.mlp.dense_h_to_4h.weight"])
+
+
+# ---- engine features end to end: dataloader from `training_data`, no_sync, ZeRO-3 16-bit export, progressive layer drop,
+# ---- sparse embedding gradients, wall-clock breakdown + TensorBoard / CSV monitors ------------------------------------------
+import os as _os  # noqa: E402
+
+from torch import nn  # noqa: E402
+from tests.unit.simple_model import SimpleModel, base_config, make_batch  # noqa: E402,F811
+
+os = _os
+
+
+def _engine_feature_worker(which, d):
+    import deepspeed_b200 as ds
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    torch.manual_seed(0)
+    if which == "io":
+        xs = torch.randn(32, 8); ys = torch.randint(0, 4, (32,))
+        class DS(torch.utils.data.Dataset):
+            def __len__(self): return 32
+            def __getitem__(self, i): return xs[i], ys[i]
+        cfg = base_config(1, "fp32", 1, 0.0)
+        eng, opt, loader, _ = ds.initialize(model=SimpleModel(), config=cfg, training_data=DS())
+        assert loader is not None
+        n = 0
+        for x, y in loader:
+            eng.backward(eng(x, y)); eng.step(); n += 1
+        print("io batches", n, len(loader))
+        assert n == len(loader) and n == 32 // (4 * w)
+    elif which == "no_sync":
+        cfg = base_config(1, "fp32", 2, 0.0)  # gas 2
+        eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+        g = torch.Generator().manual_seed(1)
+        x, y = make_batch(w, 4, g)
+        with eng.no_sync():
+            eng.backward(eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4]))
+        eng.step()
+        eng.backward(eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4])); eng.step()
+        assert eng.global_steps == 1
+    elif which == "save16":
+        cfg = base_config(3, "bf16", 1, 0.0)
+        cfg["zero_optimization"]["stage3_gather_16bit_weights_on_model_save"] = True
+        eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+        g = torch.Generator().manual_seed(1)
+        x, y = make_batch(w, 4, g)
+        eng.backward(eng(x[r*4:(r+1)*4].bfloat16(), y[r*4:(r+1)*4])); eng.step()
+        ok = eng.save_16bit_model(d, "model.bin")
+        assert ok
+        if r == 0:
+            sd = torch.load(os.path.join(d, "model.bin"))
+            ref = SimpleModel()
+            missing = ref.load_state_dict(sd, strict=True)
+            print("save16 keys", list(sd)[:3], next(iter(sd.values())).dtype)
+            assert next(iter(sd.values())).dtype == torch.bfloat16
+    elif which == "pld":
+        cfg = base_config(0, "fp32", 1, 0.0)
+        cfg["progressive_layer_drop"] = {"enabled": True, "theta": 0.5, "gamma": 0.01}
+        class M(nn.Module):
+            def __init__(self):
+                super().__init__(); self.l = nn.Linear(8, 4); self.seen = []
+            def forward(self, x, y, progressive_layer_drop=False, pld_theta=None):
+                self.seen.append((progressive_layer_drop, pld_theta))
+                return nn.functional.cross_entropy(self.l(x), y)
+        m = M()
+        eng, *_ = ds.initialize(model=m, config=cfg)
+        g = torch.Generator().manual_seed(1)
+        for _ in range(3):
+            x, y = make_batch(1, 4, g)
+            eng.backward(eng(x, y)); eng.step()
+        print("pld seen", m.seen)
+        assert m.seen[0][0] is True and m.seen[-1][1] < m.seen[0][1] <= 1.0
+        assert abs(eng.get_pld_theta() - m.seen[-1][1]) < 0.1
+    elif which == "sparse":
+        cfg = base_config(0, "fp32", 1, 0.0)
+        cfg["sparse_gradients"] = True
+        cfg["optimizer"] = {"type": "SGD", "params": {"lr": 0.1}}
+        class M(nn.Module):
+            def __init__(self):
+                super().__init__(); self.e = nn.Embedding(50, 8, sparse=True); self.l = nn.Linear(8, 4)
+            def forward(self, ids, y): return nn.functional.cross_entropy(self.l(self.e(ids).mean(1)), y)
+        torch.manual_seed(0)
+        m = M(); import copy; ref = copy.deepcopy(m)
+        eng, *_ = ds.initialize(model=m, config=cfg)
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+        g = torch.Generator().manual_seed(1)
+        for _ in range(3):
+            ids = torch.randint(0, 50, (4 * w, 5), generator=g); y = torch.randint(0, 4, (4 * w,), generator=g)
+            eng.backward(eng(ids[r*4:(r+1)*4], y[r*4:(r+1)*4])); eng.step()
+            ref(ids, y).backward(); ropt.step(); ropt.zero_grad()
+        from deepspeed_b200.utils import safe_get_full_fp32_param
+        for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+            torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach().to_dense() if q.is_sparse else q.detach(), atol=1e-5, rtol=1e-4, msg=n)
+    elif which == "wcb":
+        cfg = base_config(1, "fp32", 1, 0.0)
+        cfg["wall_clock_breakdown"] = True; cfg["steps_per_print"] = 1
+        cfg["tensorboard"] = {"enabled": True, "output_path": d, "job_name": "tb"}
+        cfg["csv_monitor"] = {"enabled": True, "output_path": d, "job_name": "csv"}
+        eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+        g = torch.Generator().manual_seed(1)
+        for _ in range(3):
+            x, y = make_batch(w, 4, g)
+            eng.backward(eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4])); eng.step()
+        if r == 0:
+            print("monitor files", [os.path.join(dp, f) for dp, _, fs in os.walk(d) for f in fs][:6])
+
+
+
+@pytest.mark.parametrize("which", ["io", "no_sync", "save16", "pld", "sparse", "wcb"])
+def test_engine_features_end_to_end(which, tmp_path):
+    from tests.common import run_distributed
+    run_distributed(_engine_feature_worker, 1 if which == "pld" else 2, (which, str(tmp_path)))
