@@ -124,6 +124,65 @@ quantize_kernel(const T* __restrict__ x, int8_t* __restrict__ q, float* __restri
     }
 }
 
+// ---- LoCo (error-feedback) quantisation: q = Q(x + err);  err <- beta * err + (1 - beta) * ((x + err) - deQ(q)) -------------
+// One pass: the compensated values and the old error stay in registers between the range reduction and the write-back
+// (reference csrc/quantization/swizzled_quantize.cu loco_swizzled_quant_kernel).  Symmetric, 4 or 8 bits.
+template <typename T, int BITS>
+__global__ void __launch_bounds__(kThreads)
+loco_quantize_kernel(const T* __restrict__ x, float* __restrict__ err, int8_t* __restrict__ q, float* __restrict__ params,
+                     int group_size, int64_t out_group_stride_bytes, float beta, int reset)
+{
+    __shared__ float scratch[32];
+    constexpr int kPer = Elem<T>::kPerVec;
+    const int g = blockIdx.x;
+    const T* xg = x + static_cast<int64_t>(g) * group_size;
+    float* eg = err + static_cast<int64_t>(g) * group_size;
+    float comp[kMaxCache][kPer], old[kMaxCache][kPer];
+    const int nvec = group_size / kPer;
+    float amax = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxCache; ++k) {
+        const int v = threadIdx.x + k * blockDim.x;
+        if (v < nvec) {
+            Elem<T>::unpack(ld_stream(xg + v * kPer), comp[k]);
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) {
+                old[k][e] = eg[v * kPer + e];
+                comp[k][e] += old[k][e];
+                amax = fmaxf(amax, fabsf(comp[k][e]));
+            }
+        }
+    }
+    amax = block_reduce<MaxOp>(amax, scratch);
+    constexpr float qmax = static_cast<float>((1 << (BITS - 1)) - 1);
+    const float scale = amax > 0.f ? amax / qmax : 1.f;
+    const float inv = 1.f / scale;
+    if (threadIdx.x == 0) params[g] = scale;
+    int8_t* qg = q + static_cast<int64_t>(g) * out_group_stride_bytes;
+#pragma unroll
+    for (int k = 0; k < kMaxCache; ++k) {
+        const int v = threadIdx.x + k * blockDim.x;
+        if (v < nvec) {
+            int qi[kPer];
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) {
+                float f = fminf(fmaxf(rintf(comp[k][e] * inv), -qmax - 1.f), qmax);
+                qi[e] = static_cast<int>(f);
+                const float new_err = comp[k][e] - f * scale;
+                eg[v * kPer + e] = reset ? 0.f : beta * old[k][e] + (1.f - beta) * new_err;
+            }
+            if (BITS == 8) {
+#pragma unroll
+                for (int e = 0; e < kPer; ++e) qg[v * kPer + e] = static_cast<int8_t>(qi[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < kPer; e += 2)
+                    qg[(v * kPer + e) >> 1] = static_cast<int8_t>(((qi[e + 1] & 0xf) << 4) | (qi[e] & 0xf));
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float dequant_one(const int8_t* qg, int i, int bits, bool sym, float scale, float offset)
 {
     int v;
@@ -504,6 +563,25 @@ DSB_EXPORT int dsb_quantize(const void* x, void* q, float* params, int64_t group
         else
             quantize_kernel<T, 4, false><<<groups, kThreads, 0, stream>>>((const T*)x, (int8_t*)q, params, group_size,
                                                                            obytes, group_perm, stochastic, seed);
+    })
+    DSB_CHECK_LAUNCH();
+    return 0;
+}
+
+// x [groups * group_size] (T), err fp32 same length (updated in place), q int8 (4-bit: two per byte), params fp32 [groups]
+DSB_EXPORT int dsb_loco_quantize(const void* x, float* err, void* q, float* params, int64_t groups, int group_size, int bits,
+                                 int dtype, float beta, int reset, cudaStream_t stream)
+{
+    if (groups <= 0) return 0;
+    if (!group_ok(group_size, dtype) || (bits != 4 && bits != 8)) return -2;
+    const int64_t obytes = bits == 8 ? group_size : group_size / 2;
+    DISPATCH_QT(dtype, T, {
+        if (bits == 8)
+            loco_quantize_kernel<T, 8><<<groups, kThreads, 0, stream>>>((const T*)x, err, (int8_t*)q, params, group_size, obytes,
+                                                                        beta, reset);
+        else
+            loco_quantize_kernel<T, 4><<<groups, kThreads, 0, stream>>>((const T*)x, err, (int8_t*)q, params, group_size, obytes,
+                                                                        beta, reset);
     })
     DSB_CHECK_LAUNCH();
     return 0;

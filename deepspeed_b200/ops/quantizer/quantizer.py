@@ -91,6 +91,31 @@ def quantize(x, groups, num_bits=8, q_type=Symmetric, group_perm=None, stochasti
     return q, (params if sym else params.view(groups, 2))
 
 
+def loco_quantize(x, err, groups, num_bits=4, beta=0.8, reset=False):
+    """LoCo error-feedback quantisation in one pass: ``q = Q(x + err)`` (symmetric, ``groups`` groups) and
+    ``err <- beta * err + (1 - beta) * ((x + err) - deQ(q))`` in place (``err`` fp32, same numel; zeroed when ``reset``).
+    Returns ``(q, params)`` like :func:`quantize` (reference ``loco_swizzled_quant``, ``csrc/quantization/swizzled_quantize.cu``)."""
+    x = x.contiguous()
+    n = x.numel()
+    assert n % groups == 0 and err.numel() == n and err.dtype == torch.float32 and err.is_contiguous()
+    gs = n // groups
+    if not x.is_cuda:
+        comp = x.reshape(-1).float() + err.reshape(-1)
+        q, params = _host_quant(comp, groups, num_bits, True)
+        deq = _host_dequant(q, params, groups, num_bits, True, torch.float32).reshape(-1)
+        if reset:
+            err.zero_()
+        else:
+            err.reshape(-1).mul_(beta).add_(comp - deq, alpha=1.0 - beta)
+        return q.reshape(-1), params
+    q = torch.empty(n if num_bits == 8 else n // 2, dtype=torch.int8, device=x.device)
+    params = torch.empty(groups, dtype=torch.float32, device=x.device)
+    rc = N.cuda().dsb_loco_quantize(_p(x), _p(err), _p(q), _p(params), ctypes.c_int64(groups), gs, num_bits, N.dt(x),
+                                    ctypes.c_float(beta), int(bool(reset)), N.stream())
+    N.check(rc, "loco_quantize")
+    return q, params
+
+
 def dequantize(q, params, groups, num_bits=8, q_type=Symmetric, dtype=torch.bfloat16):
     sym = q_type == Symmetric
     n = q.numel() * (1 if num_bits == 8 else 2)

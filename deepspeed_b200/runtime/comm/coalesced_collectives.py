@@ -44,6 +44,34 @@ def _groups_for(t, group_size=2048):
     return g
 
 
+def _rank_chunks(flat, world):
+    """Lay ``flat`` out as ``world`` equal chunks of whole quantisation groups (rank r's elements first in chunk r, zero
+    padded): -> (padded flat, per0 = elements a rank owns, per = padded chunk length, gs = group size)."""
+    n = flat.numel()
+    per0 = math.ceil(n / world)
+    gs = Q.aligned_group_size(per0)          # device kernels: groups of a multiple of 8 elements, never across ranks
+    per = (per0 + gs - 1) // gs * gs
+    if per * world != n:
+        full = flat.new_zeros(per * world)
+        for r in range(world):
+            lo_r, hi_r = r * per0, min(n, (r + 1) * per0)
+            if hi_r > lo_r:
+                full[r * per:r * per + hi_r - lo_r].copy_(flat[lo_r:hi_r])
+        flat = full
+    return flat, per0, per, gs
+
+
+def _exchange_and_reduce(q, params, world, rank, per0, per, gs, n, num_bits, dtype, group):
+    """Quantised payload -> all-to-all -> dequantise -> mean over the senders: this rank's slice of the reduced tensor."""
+    q_recv, p_recv = torch.empty_like(q), torch.empty_like(params)
+    dist.all_to_all_single(q_recv.view(-1), q.view(-1), group=group)
+    dist.all_to_all_single(p_recv.view(-1), params.view(-1), group=group)
+    deq = Q.dequantize(q_recv, p_recv, (per // gs) * world, num_bits, Q.Symmetric, dtype=torch.float32)
+    red = deq.view(world, per).sum(0).div_(world)
+    valid = max(0, min(per0, n - rank * per0))
+    return red[:valid].to(dtype)
+
+
 def all_to_all_quant_reduce(tensors: List[torch.Tensor], groups: dict = None, num_bits=4) -> List[torch.Tensor]:
     """qgZ: gradients travel quantised (int4 intra-node hop, int8 inter-node hop) through all-to-alls and are
     reduced after dequantisation; on a single NVSwitch node this is one quantised all-to-all + local reduce."""
@@ -58,54 +86,41 @@ def all_to_all_quant_reduce(tensors: List[torch.Tensor], groups: dict = None, nu
         if world == 1:
             out.append(flat.clone())
             continue
-        per0 = math.ceil(n / world)              # elements this rank ends up owning
-        gs = Q.aligned_group_size(per0)          # device kernels: groups of a multiple of 8 elements, never across ranks
-        per = (per0 + gs - 1) // gs * gs         # per-rank chunk padded to whole groups
-        if per * world != n:
-            full = flat.new_zeros(per * world)
-            for r in range(world):               # rank r's slice [r * per0, (r + 1) * per0) moves to chunk r
-                lo_r, hi_r = r * per0, min(n, (r + 1) * per0)
-                if hi_r > lo_r:
-                    full[r * per:r * per + hi_r - lo_r].copy_(flat[lo_r:hi_r])
-            flat = full
-        per_rank_groups = per // gs
-        q, params = Q.quantize(flat.contiguous(), per_rank_groups * world, num_bits, Q.Symmetric)
-        q_recv, p_recv = torch.empty_like(q), torch.empty_like(params)
-        dist.all_to_all_single(q_recv.view(-1), q.view(-1), group=local)
-        dist.all_to_all_single(p_recv.view(-1), params.view(-1), group=local)
-        deq = Q.dequantize(q_recv, p_recv, per_rank_groups * world, num_bits, Q.Symmetric, dtype=torch.float32)
-        red = deq.view(world, per).sum(0).div_(world)
-        lo = rank * per0
-        valid = max(0, min(per0, n - lo))
-        out.append(red[:valid].to(t.dtype))
+        flat, per0, per, gs = _rank_chunks(flat, world)
+        q, params = Q.quantize(flat.contiguous(), (per // gs) * world, num_bits, Q.Symmetric)
+        out.append(_exchange_and_reduce(q, params, world, rank, per0, per, gs, n, num_bits, t.dtype, local))
     return out
 
 
 def all_to_all_loco_quant_reduce(params, groups: dict = None, loco_param: dict = None, num_bits=4):
-    """LoCo-ZeRO++: qgZ with an error-feedback buffer per tensor (``p.intra_ef_buf``) so quantisation error is
-    re-injected at the next step (reference :30)."""
+    """LoCo-ZeRO++: qgZ with an error-feedback buffer per tensor (``p.intra_ef_buf``) so the quantisation error is
+    re-injected at the next step (reference :30).  Compensation, quantisation and the error update are ONE kernel
+    (``quant.cu loco_quantize_kernel``); the buffer lives in the padded per-rank chunk layout the payload travels in."""
     loco_param = loco_param or {}
+    groups = groups or {}
+    local = groups.get("local")
+    world, rank = dist.get_world_size(local), dist.get_rank(local)
     beta = float(loco_param.get("err_beta", 0.8))
     reset_T = int(loco_param.get("reset_T", 1024))
     outs = []
     for p in params:
         g = p.grad if hasattr(p, "grad") and p.grad is not None else p
+        flat = g.reshape(-1)
+        n = flat.numel()
+        if world == 1:
+            outs.append(flat.clone())
+            continue
+        flat, per0, per, gs = _rank_chunks(flat, world)
         buf = getattr(p, "intra_ef_buf", None)
-        if buf is None or buf[0].shape != g.shape:
-            buf = [torch.zeros_like(g, dtype=torch.float32), 0]
+        if buf is None or buf[0].numel() != flat.numel() or buf[0].device != flat.device:
+            buf = [torch.zeros(flat.numel(), dtype=torch.float32, device=flat.device), 0]
         err, step = buf
-        comp = g.float() + err
-        qd = Q.fake_quantize(comp.reshape(-1).contiguous(), _groups_for(comp), num_bits, Q.Symmetric).view_as(comp)
-        new_err = comp - qd
         step += 1
-        if step >= reset_T:
-            err.zero_()
-            step = 0
-        else:
-            err.mul_(beta).add_(new_err, alpha=1 - beta)
+        reset = step >= reset_T
+        q, qp = Q.loco_quantize(flat.contiguous(), err, (per // gs) * world, num_bits, beta, reset)
         try:
-            p.intra_ef_buf = [err, step]
+            p.intra_ef_buf = [err, 0 if reset else step]
         except Exception:
             pass
-        outs.extend(all_to_all_quant_reduce([comp.to(g.dtype)], groups, num_bits))
+        outs.append(_exchange_and_reduce(q, qp, world, rank, per0, per, gs, n, num_bits, g.dtype, local))
     return outs

@@ -112,3 +112,42 @@ def _qgz_uneven():
 
 def test_qgz_uneven_sizes_pad_to_aligned_groups():
     run_distributed(_qgz_uneven, 2)
+
+
+def _loco_worker():
+    """LoCo error feedback: the mean of the quantised results over many steps converges to the true mean (the error is
+    re-injected), while plain 4-bit qgZ keeps a bias; the error buffer follows the padded chunk layout."""
+    import torch.distributed as td
+    from deepspeed_b200.ops.quantizer import quantizer as Q
+    from deepspeed_b200.runtime.comm.coalesced_collectives import all_to_all_loco_quant_reduce, all_to_all_quant_reduce
+    r, w = td.get_rank(), td.get_world_size()
+    # single-tensor semantics of the fused op vs its definition
+    x = torch.randn(64)
+    err = torch.randn(64) * 0.01
+    e0 = err.clone()
+    q, p = Q.loco_quantize(x, err, 4, num_bits=8, beta=0.5)
+    comp = x + e0
+    deq = Q.dequantize(q, p, 4, 8, Q.Symmetric, dtype=torch.float32)
+    torch.testing.assert_close(err, 0.5 * e0 + 0.5 * (comp - deq))
+    n = 1003
+    base = torch.randn(n, generator=torch.Generator().manual_seed(7 + r))
+    holder = torch.nn.Parameter(base.clone())
+    full = base.clone()
+    td.all_reduce(full)
+    full /= w
+    per = -(-n // w)
+    want = full[r * per:min(n, (r + 1) * per)]
+    acc_loco, acc_plain = torch.zeros_like(want), torch.zeros_like(want)
+    T = 40
+    for _ in range(T):
+        holder.grad = base.clone()
+        acc_loco += all_to_all_loco_quant_reduce([holder], {"local": None}, {"err_beta": 0.0, "reset_T": 10**6}, num_bits=4)[0]
+        acc_plain += all_to_all_quant_reduce([base.clone()], {"local": None}, num_bits=4)[0]
+    e_loco = (acc_loco / T - want).abs().mean().item()
+    e_plain = (acc_plain / T - want).abs().mean().item()
+    assert e_loco < 0.35 * e_plain + 1e-6, (e_loco, e_plain)
+    assert holder.intra_ef_buf[0].numel() % 8 == 0 and holder.intra_ef_buf[1] == T
+
+
+def test_loco_error_feedback_converges():
+    run_distributed(_loco_worker, 2)
