@@ -326,7 +326,7 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         c = self._config
         if client_lr_scheduler is not None:
             if callable(client_lr_scheduler) and not hasattr(client_lr_scheduler, "step"):
-                self.lr_scheduler = client_lr_scheduler(self.optimizer)
+                self.lr_scheduler = self._build_scheduler_on_our_groups(client_lr_scheduler)
             else:
                 self.lr_scheduler = client_lr_scheduler
                 # a client scheduler built on the client optimizer must drive OUR param groups
@@ -337,9 +337,29 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
             if cls is None:
                 cls = getattr(torch.optim.lr_scheduler, c.scheduler_name, None)
                 assert cls is not None, f"DeepSpeed does not recognize LR scheduler {c.scheduler_name}"
-            self.lr_scheduler = cls(self.optimizer, **(c.scheduler_params or {}))
+            self.lr_scheduler = self._build_scheduler_on_our_groups(lambda o: cls(o, **(c.scheduler_params or {})))
         log_dist(f"DeepSpeed LR Scheduler = {type(self.lr_scheduler).__name__ if self.lr_scheduler else None}",
                  ranks=[0])
+
+    def _build_scheduler_on_our_groups(self, factory):
+        """``factory(optimizer) -> scheduler``.  Framework schedulers accept the engine's optimizer as it is; ``torch.optim``
+        schedulers insist on a ``torch.optim.Optimizer`` instance (the reference hands them its basic optimizer,
+        ``engine.py:985``): build them on a stand-in with the same groups / learning rates, then point them at the real
+        parameter groups so every ``scheduler.step()`` drives the optimizer that actually steps."""
+        try:
+            return factory(self.optimizer)
+        except TypeError:
+            pass
+        groups = self.optimizer.param_groups
+        stand_in = torch.optim.SGD([{"params": [torch.nn.Parameter(torch.zeros(1))], "lr": float(g.get("lr", 1e-3))}
+                                    for g in groups], lr=1e-3)
+        sched = factory(stand_in)
+        for g, sg in zip(groups, stand_in.param_groups):
+            g["lr"] = sg["lr"]
+            if "initial_lr" in sg:
+                g["initial_lr"] = sg["initial_lr"]
+        sched.optimizer = self.optimizer
+        return sched
 
     def _dense_grad_allreduce_enabled(self):
         # the pipeline engine keeps its own switch (1-bit optimizers toggle whichever applies)

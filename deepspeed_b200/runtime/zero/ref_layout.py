@@ -332,8 +332,11 @@ def import_reference_state(zo, sd, load_optimizer_states=True, load_from_fp32_we
                 dist.all_reduce(full, group=zo.dp_group)
             a = u.arena_offset
             lo_u, hi_u = u.shard_range(rank)
-            dst_arena = arenas[key][a:a + u.shard_numel]
-            dst_arena.copy_(full[lo_u:hi_u].to(dst_arena.device, dst_arena.dtype))
+            arena = arenas[key]
+            for s in members:  # only the optimizer's own parameters: frozen parameters / padding in the unit keep their values
+                lo, hi = max(s.offset, lo_u), min(s.offset + s.numel, hi_u)
+                if lo < hi:
+                    arena[a + lo - lo_u:a + hi - lo_u].copy_(full[lo:hi].to(arena.device, arena.dtype))
     # scalars -----------------------------------------------------------------------------------------------------------
     ls = sd.get(LOSS_SCALER)
     if isinstance(ls, dict):

@@ -1,0 +1,126 @@
+"""Engine configurations end to end (2 gloo ranks): fp32 gradient accumulation for bf16, gradient pre-division / pre-scaling,
+fp16 + ZeRO-3 overflow skipping, client optimizer + torch LR scheduler factories, frozen and unused parameters with a
+checkpoint round trip.  Each of these found (or guards against) a real defect."""
+import copy
+import os
+import tempfile
+
+import pytest
+import torch
+from torch import nn
+
+from tests.common import run_distributed
+from tests.unit.simple_model import SimpleModel, base_config, make_batch
+
+
+def train(eng, steps, w, r, dtype=None, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(steps):
+        x, y = make_batch(w, 4, g)
+        xx = x[r*4:(r+1)*4]
+        if dtype is not None: xx = xx.to(dtype)
+        l = eng(xx, y[r*4:(r+1)*4]); eng.backward(l); eng.step(); out.append(l.item())
+    return out
+
+
+def _config_worker(which):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    torch.manual_seed(0)
+    if which == "gradacc_fp32":
+        cfg = base_config(2, "bf16", 2, 1.0); cfg["data_types"] = {"grad_accum_dtype": "fp32"}
+        eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+        ls = train(eng, 6, w, r, torch.bfloat16); assert ls[-1] < ls[0], ls
+    elif which == "predivide":
+        for extra in ({"gradient_predivide_factor": 2.0}, {"prescale_gradients": True}):
+            torch.manual_seed(0)
+            ref = SimpleModel(); m = copy.deepcopy(ref)
+            cfg = base_config(0, "fp32", 1, 0.0); cfg.update(extra); cfg["optimizer"] = {"type": "SGD", "params": {"lr": 0.1}}
+            eng, *_ = ds.initialize(model=m, config=cfg)
+            ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+            g = torch.Generator().manual_seed(1)
+            for _ in range(3):
+                x, y = make_batch(w, 4, g)
+                l = eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4]); eng.backward(l); eng.step()
+                ref(x, y).backward(); ropt.step(); ropt.zero_grad()
+            for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+                torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach(), atol=1e-5, rtol=1e-4, msg=f"{extra} {n}")
+    elif which == "fp16_z3_overflow":
+        cfg = base_config(3, "fp16", 1, 1.0); cfg["fp16"] = {"enabled": True, "initial_scale_power": 4, "loss_scale_window": 2, "hysteresis": 1}
+        eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+        g = torch.Generator().manual_seed(1)
+        x, y = make_batch(w, 4, g)
+        before = [safe_get_full_fp32_param(p).clone() for p in eng.module.parameters()]
+        s0 = eng.optimizer.loss_scale
+        l = eng((x[r*4:(r+1)*4] * 1e6).half(), y[r*4:(r+1)*4]); eng.backward(l); eng.step()   # overflow -> skipped
+        after = [safe_get_full_fp32_param(p) for p in eng.module.parameters()]
+        assert all(torch.equal(a, b) for a, b in zip(before, after)), "overflow step must not change parameters"
+        assert eng.optimizer.loss_scale < s0 and eng.skipped_steps == 1, (eng.optimizer.loss_scale, s0, eng.skipped_steps)
+        ls = train(eng, 6, w, r, torch.float16); assert ls[-1] < ls[0] and all(l == l for l in ls), ls
+    elif which == "client_opt":
+        for stage in (1, 2):
+            torch.manual_seed(0)
+            m = SimpleModel(); ref = copy.deepcopy(m)
+            opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+            cfg = base_config(stage, "fp32", 1, 0.0); cfg.pop("optimizer", None); cfg["zero_allow_untested_optimizer"] = True
+            sched = lambda o: torch.optim.lr_scheduler.StepLR(o, step_size=2, gamma=0.5)
+            eng, eopt, _, esched = ds.initialize(model=m, optimizer=opt, lr_scheduler=sched, config=cfg)
+            ropt = torch.optim.Adam(ref.parameters(), lr=1e-2); rs = torch.optim.lr_scheduler.StepLR(ropt, 2, 0.5)
+            g = torch.Generator().manual_seed(1)
+            for _ in range(4):
+                x, y = make_batch(w, 4, g)
+                l = eng(x[r*4:(r+1)*4], y[r*4:(r+1)*4]); eng.backward(l); eng.step()
+                ref(x, y).backward(); ropt.step(); ropt.zero_grad(); rs.step()
+            assert abs(eng.get_lr()[0] - ropt.param_groups[0]["lr"]) < 1e-12, (eng.get_lr(), ropt.param_groups[0]["lr"])
+            for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+                torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach(), atol=1e-5, rtol=1e-4, msg=f"stage{stage} {n}")
+    elif which == "frozen_unused":
+        class M(nn.Module):
+            def __init__(self):
+                super().__init__(); self.a = nn.Linear(8, 8); self.frozen = nn.Linear(8, 8); self.unused = nn.Linear(8, 8); self.out = nn.Linear(8, 4)
+                for p in self.frozen.parameters(): p.requires_grad_(False)
+            def forward(self, x, y): return nn.functional.cross_entropy(self.out(self.frozen(torch.tanh(self.a(x)))), y)
+        for stage in (1, 2, 3):
+            torch.manual_seed(0)
+            m = M(); cfg = base_config(stage, "fp32", 1, 0.0)
+            eng, *_ = ds.initialize(model=m, config=cfg)
+            fr0 = safe_get_full_fp32_param(m.frozen.weight).clone(); un0 = safe_get_full_fp32_param(m.unused.weight).clone()
+            gg = torch.Generator().manual_seed(1); xb, yb = make_batch(w, 4, gg); ls = []
+            for _ in range(6):
+                l = eng(xb[r*4:(r+1)*4], yb[r*4:(r+1)*4]); eng.backward(l); eng.step(); ls.append(l.item())
+            assert ls[-1] < ls[0], (stage, ls)
+            assert torch.equal(safe_get_full_fp32_param(m.frozen.weight), fr0), stage
+            d = tempfile.mkdtemp() if r == 0 else None
+            lst = [d]; torch.distributed.broadcast_object_list(lst, 0); d = lst[0]
+            eng.save_checkpoint(d, tag="t")
+            a_w = safe_get_full_fp32_param(m.a.weight).clone()
+            train(eng, 1, w, r, seed=9)
+            eng.load_checkpoint(d, tag="t")
+            torch.testing.assert_close(safe_get_full_fp32_param(m.a.weight), a_w, msg=f"a stage {stage}")
+            torch.testing.assert_close(safe_get_full_fp32_param(m.frozen.weight), fr0, msg=f"frozen stage {stage}")
+
+
+
+@pytest.mark.parametrize("which", ["gradacc_fp32", "predivide", "fp16_z3_overflow", "client_opt", "frozen_unused"])
+def test_engine_configuration(which):
+    run_distributed(_config_worker, 2, (which, ), timeout=400)
+
+
+def _named_sched_worker():
+    import deepspeed_b200 as ds
+    cfg = base_config(1, "fp32", 1, 0.0)
+    cfg["scheduler"] = {"type": "StepLR", "params": {"step_size": 1, "gamma": 0.5}}
+    eng, *_ = ds.initialize(model=SimpleModel(), config=cfg)
+    lr0 = eng.get_lr()[0]
+    g = torch.Generator().manual_seed(1)
+    x, y = make_batch(1, 4, g)
+    eng.backward(eng(x, y))
+    eng.step()
+    assert abs(eng.get_lr()[0] - 0.5 * lr0) < 1e-12
+
+
+def test_named_torch_scheduler_from_config():
+    """``scheduler: {type: <a torch.optim.lr_scheduler class>}`` is built against the engine's parameter groups."""
+    run_distributed(_named_sched_worker, 1)
