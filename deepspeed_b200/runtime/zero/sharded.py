@@ -67,6 +67,7 @@ class _UnitRT:
         self.dense_grads = False  # set by model integrations that write every gradient view
         self.temp_refs = 0  # GatheredParameters / external users holding the unit
         self.home = None  # buffer used by this iteration's forward gather (backward MUST reuse it)
+        self.running = 0  # forward passes of the unit's module currently executing (re-entrancy counter)
         self.consumed = False  # a module hook actually used the gathered copy (vs. a speculative prefetch)
         self.skip_bwd_fetch = False  # module's backward does not read its weights (embedding, fused LM head)
 
@@ -550,12 +551,14 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
         def hook(module, args):
             self.fetch_unit(rt, forward=not self._in_backward)
+            rt.running += 1
 
         return hook
 
     def _make_post_fwd(self, rt):
 
         def hook(module, args, output):
+            rt.running = max(0, rt.running - 1)
             if self._in_backward:
                 return  # recompute inside backward: released by the gradient path
             if torch.is_grad_enabled() and rt.u.index == self._last_forward_unit() and not rt.skip_bwd_fetch:
@@ -739,6 +742,12 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             # speculative prefetch that nobody used (e.g. a module skipped by this forward): evict it
             self._detach_params(occ)
             occ.full, occ.state, occ.gather_event, occ.home = None, NOT_GATHERED, None, None
+        if occ is not None and occ is not rt and occ.state != NOT_GATHERED and not self._in_backward \
+                and occ.running == 0 and occ.temp_refs == 0 and not occ.u.persistent:
+            # a second forward pass before backward (siamese / contrastive losses, evaluation between micro steps): the
+            # unit cached in this buffer -- typically the last unit of the previous pass, kept for its backward -- is idle;
+            # release it (it keeps its home: its own backward gathers it back into the same memory)
+            self.release_unit(occ)
         if occ is not None and occ is not rt and occ.state != NOT_GATHERED:
             if rt.home is not None:
                 raise RuntimeError(

@@ -124,3 +124,66 @@ def _named_sched_worker():
 def test_named_torch_scheduler_from_config():
     """``scheduler: {type: <a torch.optim.lr_scheduler class>}`` is built against the engine's parameter groups."""
     run_distributed(_named_sched_worker, 1)
+
+
+# ---- ZeRO-3 usage patterns against plain PyTorch: non-reentrant activation checkpointing, evaluation between training steps,
+# ---- no prefetch / one live unit, and two forward passes feeding one loss (needs a gather pool that holds every unit) --------
+class _PatternNet(nn.Module):
+    def __init__(self, ckpt=False):
+        super().__init__()
+        self.layers = nn.ModuleList([nn.Linear(8, 8) for _ in range(3)])
+        self.head = nn.Linear(8, 4)
+        self.ckpt = ckpt
+    def body(self, x):
+        from torch.utils.checkpoint import checkpoint
+        for l in self.layers:
+            x = checkpoint(lambda t, l=l: torch.tanh(l(t)), x, use_reentrant=False) if self.ckpt else torch.tanh(l(x))
+        return x
+    def forward(self, x, y=None):
+        h = self.head(self.body(x))
+        return h if y is None else nn.functional.cross_entropy(h, y)
+
+
+def _z3_pattern_worker(which):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    torch.manual_seed(0)
+    extra = {}
+    if which == "two_forwards":
+        extra = {"b200_unit_prefetch": 4}
+    if which == "no_prefetch":
+        extra = {"stage3_prefetch_bucket_size": 0, "stage3_max_live_parameters": 1, "stage3_max_reuse_distance": 0}
+    ref = _PatternNet(ckpt=(which == "ckpt")); m = copy.deepcopy(ref)
+    cfg = base_config(3, "fp32", 1, 0.0); cfg["optimizer"] = {"type": "SGD", "params": {"lr": 0.1}}
+    cfg["zero_optimization"].update(extra); cfg["zero_optimization"]["stage3_param_persistence_threshold"] = 0
+    eng, *_ = ds.initialize(model=m, config=cfg)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(1)
+    for it in range(3):
+        x, y = make_batch(w, 4, g)
+        xs, ys = x[r*4:(r+1)*4], y[r*4:(r+1)*4]
+        if which == "two_forwards":
+            # two forward passes feed one loss (siamese / contrastive style)
+            a = eng(xs); b = eng(xs * 0.5)
+            loss = nn.functional.cross_entropy(a + b, ys)
+            ra = ref(x); rb = ref(x * 0.5); rl = nn.functional.cross_entropy(ra + rb, y)
+        elif which == "eval_between":
+            eng.eval()
+            with torch.no_grad():
+                pred = eng(xs)
+            assert pred.shape == (4, 4)
+            eng.train()
+            loss = eng(xs, ys); rl = ref(x, y)
+        else:
+            loss = eng(xs, ys); rl = ref(x, y)
+        eng.backward(loss); eng.step()
+        rl.backward(); ropt.step(); ropt.zero_grad()
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach(), atol=1e-5, rtol=1e-4, msg=f"{which} {n}")
+
+
+
+@pytest.mark.parametrize("which", ["plain", "ckpt", "two_forwards", "eval_between", "no_prefetch"])
+def test_zero3_usage_patterns(which):
+    run_distributed(_z3_pattern_worker, 2, (which, ))
