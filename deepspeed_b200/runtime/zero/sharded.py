@@ -68,6 +68,8 @@ class _UnitRT:
         self.temp_refs = 0  # GatheredParameters / external users holding the unit
         self.home = None  # buffer used by this iteration's forward gather (backward MUST reuse it)
         self.running = 0  # forward passes of the unit's module currently executing (re-entrancy counter)
+        self.fwd_calls = 0  # grad-enabled forward invocations of the module since the last backward finished
+        self.bwd_calls = 0  # ... and how many of them have been back-propagated
         self.consumed = False  # a module hook actually used the gathered copy (vs. a speculative prefetch)
         self.skip_bwd_fetch = False  # module's backward does not read its weights (embedding, fused LM head)
 
@@ -546,12 +548,15 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             rt.skip_bwd_fetch = bool(getattr(m, "ds_skip_backward_fetch", False))
             if not rt.skip_bwd_fetch:
                 self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
+                self._hook_handles.append(m.register_full_backward_hook(self._make_post_bwd(rt)))
 
     def _make_pre_fwd(self, rt):
 
         def hook(module, args):
             self.fetch_unit(rt, forward=not self._in_backward)
             rt.running += 1
+            if not self._in_backward and torch.is_grad_enabled():
+                rt.fwd_calls += 1
 
         return hook
 
@@ -572,6 +577,19 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         def hook(module, grad_output):
             self._in_backward = True
             self.fetch_unit(rt, forward=False)
+
+        return hook
+
+    def _make_post_bwd(self, rt):
+        """A module that ran MORE THAN ONCE in forward (two passes feeding one loss) is back-propagated once per invocation,
+        and its parameter gradients -- hence the usual release on gradient completion -- only arrive after the last one.
+        Free the gather buffer between invocations so the units of the other pass can use it (every weight-dependent node of
+        this invocation has run once its input gradients exist); the next invocation's pre-backward hook gathers it back."""
+
+        def hook(module, grad_input, grad_output):
+            rt.bwd_calls += 1
+            if rt.fwd_calls > 1 and rt.bwd_calls < rt.fwd_calls and rt.temp_refs == 0:
+                self.release_unit(rt)
 
         return hook
 
@@ -1185,6 +1203,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 if not rt.u.persistent and rt.state != NOT_GATHERED and rt.grad_full is None:
                     self.release_unit(rt)
                 rt.home = None
+                rt.fwd_calls = rt.bwd_calls = 0
         self._in_backward = False
         if not self._trace_done and self._trace:
             self._trace_done = True

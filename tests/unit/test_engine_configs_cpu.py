@@ -127,7 +127,7 @@ def test_named_torch_scheduler_from_config():
 
 
 # ---- ZeRO-3 usage patterns against plain PyTorch: non-reentrant activation checkpointing, evaluation between training steps,
-# ---- no prefetch / one live unit, and two forward passes feeding one loss (needs a gather pool that holds every unit) --------
+# ---- no prefetch / one live unit, and two forward passes feeding one loss (units are released between their backward invocations)
 class _PatternNet(nn.Module):
     def __init__(self, ckpt=False):
         super().__init__()
@@ -150,8 +150,6 @@ def _z3_pattern_worker(which):
     r, w = ds.comm.get_rank(), ds.comm.get_world_size()
     torch.manual_seed(0)
     extra = {}
-    if which == "two_forwards":
-        extra = {"b200_unit_prefetch": 4}
     if which == "no_prefetch":
         extra = {"stage3_prefetch_bucket_size": 0, "stage3_max_live_parameters": 1, "stage3_max_reuse_distance": 0}
     ref = _PatternNet(ckpt=(which == "ckpt")); m = copy.deepcopy(ref)
