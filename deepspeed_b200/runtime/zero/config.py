@@ -120,6 +120,9 @@ class DeepSpeedZeroConfig(DeepSpeedConfigModel):
     # debug: for the first N optimizer steps run the NCCL collective next to every in-kernel NVLink collective and assert
     # agreement (the reference's ``pg_correctness_test`` switch, stage_1_and_2.py:36, made real)
     b200_verify_collectives: int = Field(0, ge=0)
+    # ZeRO-3: post-backward hooks that free a unit between the backward invocations of a module that ran more than once
+    # in forward (siamese / contrastive losses); off = one hook less per unit for strictly single-invocation models
+    b200_multi_forward: bool = True
 
     @model_validator(mode="after")
     def overlap_comm_valid(self):

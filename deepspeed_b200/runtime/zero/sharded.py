@@ -548,7 +548,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             rt.skip_bwd_fetch = bool(getattr(m, "ds_skip_backward_fetch", False))
             if not rt.skip_bwd_fetch:
                 self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
-                self._hook_handles.append(m.register_full_backward_hook(self._make_post_bwd(rt)))
+                if bool(getattr(self.zc, "b200_multi_forward", True)):
+                    self._hook_handles.append(m.register_full_backward_hook(self._make_post_bwd(rt)))
 
     def _make_pre_fwd(self, rt):
 
@@ -587,7 +588,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         this invocation has run once its input gradients exist); the next invocation's pre-backward hook gathers it back."""
 
         def hook(module, grad_input, grad_output):
-            rt.bwd_calls += 1
+            rt.bwd_calls += 1  # invocations are back-propagated last-to-first; the first one (possibly un-hooked) needs no release
             if rt.fwd_calls > 1 and rt.bwd_calls < rt.fwd_calls and rt.temp_refs == 0:
                 self.release_unit(rt)
 
