@@ -56,6 +56,8 @@ class DeepSpeedConfigError(Exception):
 # blocks
 # ------------------------------------------------------------------------------------------------
 class FP16Config(DeepSpeedConfigModel):
+    # the reference reads this block key by key (``config.py:181-260 get_fp16_*``): keys it does not know are ignored
+    model_config = dict(DeepSpeedConfigModel.model_config, extra="allow")
     enabled: bool = False
     auto_cast: bool = False
     loss_scale: float = Field(0.0, ge=0)  # 0 == dynamic
@@ -72,6 +74,7 @@ class FP16Config(DeepSpeedConfigModel):
 
 
 class BF16Config(DeepSpeedConfigModel):
+    model_config = dict(DeepSpeedConfigModel.model_config, extra="allow")  # (same: ``config.py:166-180``)
     enabled: bool = False
     immediate_grad_update: bool = False
     check_grad_overflow: bool = False
@@ -98,6 +101,8 @@ class SchedulerConfig(DeepSpeedConfigModel):
 
 
 class ActivationCheckpointingConfig(DeepSpeedConfigModel):
+    # dict-read in the reference (activation_checkpointing/config.py:63): unknown keys are ignored there
+    model_config = dict(DeepSpeedConfigModel.model_config, extra="allow")
     partition_activations: bool = False
     contiguous_memory_optimization: bool = False
     cpu_checkpointing: bool = False
@@ -107,6 +112,7 @@ class ActivationCheckpointingConfig(DeepSpeedConfigModel):
 
 
 class AIOConfig(DeepSpeedConfigModel):
+    model_config = dict(DeepSpeedConfigModel.model_config, extra="allow")  # dict-read in the reference (swap_tensor/aio_config.py)
     block_size: int = 1048576
     queue_depth: int = 8
     intra_op_parallelism: int = Field(1, alias="thread_count")
