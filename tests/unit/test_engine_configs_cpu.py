@@ -185,3 +185,47 @@ def _z3_pattern_worker(which):
 @pytest.mark.parametrize("which", ["plain", "ckpt", "two_forwards", "eval_between", "no_prefetch"])
 def test_zero3_usage_patterns(which):
     run_distributed(_z3_pattern_worker, 2, (which, ))
+
+
+# ---- initialize() variants: config from args / config_params, explicit parameter groups with per-group lr / weight decay ------
+import argparse  # noqa: E402
+import json  # noqa: E402
+
+
+def _init_variants_worker(which):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    r, w = ds.comm.get_rank(), ds.comm.get_world_size()
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(1); x, y = make_batch(w, 4, g); xs, ys = x[r*4:(r+1)*4], y[r*4:(r+1)*4]
+    if which == "args_path":
+        d = tempfile.mkdtemp(); p = os.path.join(d, "c.json"); json.dump(base_config(1, "fp32", 1, 0.0), open(p, "w"))
+        ap = argparse.ArgumentParser(); ap = ds.add_config_arguments(ap)
+        args = ap.parse_args(["--deepspeed", "--deepspeed_config", p])
+        eng, *_ = ds.initialize(args=args, model=SimpleModel())
+        eng.backward(eng(xs, ys)); eng.step()
+        eng2, *_ = ds.initialize(model=SimpleModel(), config_params=base_config(2, "fp32", 1, 0.0))
+        eng2.backward(eng2(xs, ys)); eng2.step()
+    elif which == "param_groups":
+        for stage in (0, 1, 2, 3):
+            torch.manual_seed(0)
+            m = SimpleModel(); ref = copy.deepcopy(m)
+            decay = [p for n, p in m.named_parameters() if p.dim() > 1]; nodecay = [p for n, p in m.named_parameters() if p.dim() <= 1]
+            rdecay = [p for n, p in ref.named_parameters() if p.dim() > 1]; rnodecay = [p for n, p in ref.named_parameters() if p.dim() <= 1]
+            cfg = base_config(stage, "fp32", 1, 0.0); cfg["optimizer"] = {"type": "AdamW", "params": {"lr": 1e-2, "weight_decay": 0.1}}
+            eng, *_ = ds.initialize(model=m, config=cfg, model_parameters=[{"params": decay}, {"params": nodecay, "weight_decay": 0.0, "lr": 5e-2}])
+            ropt = torch.optim.AdamW([{"params": rdecay}, {"params": rnodecay, "weight_decay": 0.0, "lr": 5e-2}], lr=1e-2, weight_decay=0.1)
+            gg = torch.Generator().manual_seed(1)
+            for _ in range(3):
+                xx, yy = make_batch(w, 4, gg)
+                eng.backward(eng(xx[r*4:(r+1)*4], yy[r*4:(r+1)*4])); eng.step()
+                ref(xx, yy).backward(); ropt.step(); ropt.zero_grad()
+            for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+                torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), q.detach(), atol=2e-5, rtol=1e-4, msg=f"stage {stage} {n}")
+            assert [round(l, 6) for l in eng.get_lr()] == [1e-2, 5e-2], eng.get_lr()
+
+
+
+@pytest.mark.parametrize("which", ["args_path", "param_groups"])
+def test_initialize_variants(which):
+    run_distributed(_init_variants_worker, 2, (which, ), timeout=400)
