@@ -11,6 +11,7 @@ from typing import Optional, Union
 import torch
 
 __version__ = "0.1.0"
+__reference_version__ = "0.16.5"  # the upstream release whose API / config / checkpoint contract this package follows
 __version_major__, __version_minor__, __version_patch__ = 0, 1, 0
 __git_hash__ = None
 __git_branch__ = None

@@ -51,6 +51,6 @@ _declare(
 )
 
 _declare(
-    MINIMUM_DEEPSPEED_VERSION="0.1.0",
+    MINIMUM_DEEPSPEED_VERSION="0.3.8",  # the upstream release that introduced elasticity (schedulers pass UPSTREAM version strings)
     DEEPSPEED_ELASTICITY_CONFIG="DEEPSPEED_ELASTICITY_CONFIG",
 )

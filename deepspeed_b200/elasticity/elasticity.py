@@ -150,7 +150,10 @@ def compute_elastic_config(ds_config: dict, target_deepspeed_version: str, world
     if float(cfg.version) > C.LATEST_ELASTICITY_VERSION:
         raise ElasticityConfigError(f"Attempting to run elasticity version {cfg.version} but runtime only supports up "
                                     f"to {C.LATEST_ELASTICITY_VERSION}")
-    if pkg_version.parse(target_deepspeed_version) < pkg_version.parse(C.MINIMUM_DEEPSPEED_VERSION):
+    from deepspeed_b200.git_version_info import version as _own_version
+    # schedulers pass either an UPSTREAM release number (>= 0.3.8 introduced elasticity) or this package's own version
+    if str(target_deepspeed_version) != str(_own_version) and \
+            pkg_version.parse(target_deepspeed_version) < pkg_version.parse(C.MINIMUM_DEEPSPEED_VERSION):
         raise ElasticityError(f"Unable to run elasticity on target deepspeed version of {target_deepspeed_version}, "
                               f"currently {C.MINIMUM_DEEPSPEED_VERSION}+ is required")
     micro = None

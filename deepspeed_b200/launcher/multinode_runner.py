@@ -13,11 +13,17 @@ class MultiNodeRunner(ABC):
 
     def __init__(self, args, world_info_base64, resource_pool=None):
         self.args = args
+        self.validate_args()  # (reference: the constructor validates, multinode_runner.py:21)
         self.world_info_base64 = world_info_base64
         self.resource_pool = resource_pool or {}
         self.exports = {}
-        self.user_arguments = list(args.user_args)
+        self.user_arguments = self.parse_user_args()
         self.user_script = args.user_script
+
+    @staticmethod
+    def _slots(v):
+        """Slot count of a resource-pool entry: the pool maps host -> slot count (hostfile form) or host -> slot list."""
+        return len(v) if hasattr(v, "__len__") else int(v)
 
     def parse_user_args(self):
         """User-script arguments as they must appear on the launcher's command line (runners that go through a remote shell
@@ -42,7 +48,7 @@ class MultiNodeRunner(ABC):
 
     @property
     def name(self):
-        return self.__class__.__name__
+        return self.__class__.__name__.replace("Runner", "").lower()  # "pdsh", "openmpi", "mpich", "impi", "slurm", "mvapich"
 
     def _launch_tail(self):
         tail = []
@@ -53,10 +59,10 @@ class MultiNodeRunner(ABC):
         return tail + [self.user_script] + self.user_arguments
 
     def _total_procs(self):
-        return sum(len(v) for v in self.resource_pool.values())
+        return sum(self._slots(v) for v in self.resource_pool.values())
 
     def _per_node(self):
-        return len(next(iter(self.resource_pool.values()))) if self.resource_pool else 1
+        return self._slots(next(iter(self.resource_pool.values()))) if self.resource_pool else 1
 
 
 class PDSHRunner(MultiNodeRunner):
@@ -80,20 +86,51 @@ class PDSHRunner(MultiNodeRunner):
             launch += ["--enable_elastic_training", f"--max_elastic_nodes={self.args.max_elastic_nodes}",
                        f"--min_elastic_nodes={self.args.min_elastic_nodes}"]
         extra = self.args.launcher_args.split() if self.args.launcher_args else []
-        return ["pdsh", "-S", "-f", str(K.PDSH_MAX_FAN_OUT), "-w", workers] + extra + launch + [self.user_script] + \
-            self.user_arguments
+        pdsh = ["pdsh", "-S", "-f", str(K.PDSH_MAX_FAN_OUT), "-w", workers] + extra
+        # what the runner executes on the workers when the job is interrupted: stop every per-node launcher of this job
+        kill_cmd = pdsh + ["pkill", "-f", "deepspeed_b200.launcher.launch"]
+        return pdsh + launch + [self.user_script] + self.user_arguments, kill_cmd, environment
 
 
 class OpenMPIRunner(MultiNodeRunner):
 
+    def __init__(self, args, world_info_base64, resource_pool=None):
+        super().__init__(args, world_info_base64, resource_pool)
+        self.add_export("UCX_TLS", "tcp")
+
     def backend_exists(self):
         return shutil.which("ompi_info") is not None
 
-    def get_cmd(self, environment, active_resources):
-        if self.args.include or self.args.exclude:
+    def validate_args(self):
+        super().validate_args()
+        self._setup_mpi_environment()
+        if getattr(self.args, "include", "") or getattr(self.args, "exclude", ""):
             raise ValueError(f"{self.name} backend does not support worker include/exclusion")
-        cmd = ["mpirun", "-n", str(self._total_procs()), "-hostfile", self.args.hostfile, "--mca", "btl", "^openib",
-               "--mca", "btl_tcp_if_include", "eth0"] + (self.args.launcher_args.split() if self.args.launcher_args else [])
+        if getattr(self.args, "num_nodes", -1) != -1 or getattr(self.args, "num_gpus", -1) != -1:
+            raise ValueError(f"{self.name} backend does not support limiting num nodes/gpus")
+
+    def _setup_mpi_environment(self):
+        """The OpenMPI path is entered from inside an MPI job: mirror its rank variables into the names the engine reads
+        (reference ``multinode_runner.py:147``)."""
+        required = ["OMPI_COMM_WORLD_LOCAL_RANK", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE"]
+        if not all(v in os.environ for v in required):
+            raise EnvironmentError("MPI environment variables are not set. Ensure you are running the script with an "
+                                   "MPI-compatible launcher.")
+        os.environ["LOCAL_RANK"] = os.environ["OMPI_COMM_WORLD_LOCAL_RANK"]
+        os.environ["RANK"] = os.environ["OMPI_COMM_WORLD_RANK"]
+        os.environ["WORLD_SIZE"] = os.environ["OMPI_COMM_WORLD_SIZE"]
+
+    def get_cmd(self, environment, active_resources):
+        from shlex import split
+        launcher_args = split(self.args.launcher_args) if self.args.launcher_args else []
+        # `--mca btl_tcp_if_include eth0` unless the user chose an interface through --launcher_args
+        btl = ["--mca", "btl_tcp_if_include", "eth0"]
+        for i in range(len(launcher_args) - 1):
+            if launcher_args[i] in ("-mca", "--mca") and launcher_args[i + 1] == "btl_tcp_if_include":
+                btl = []
+                break
+        cmd = ["mpirun", "-n", str(self._total_procs()), "-hostfile", str(self.args.hostfile), "--mca", "btl", "^openib"] + \
+            btl + launcher_args
         for k, v in self.exports.items():
             cmd += ["-x", f"{k}={v}"]
         return cmd + self._launch_tail()
@@ -113,12 +150,12 @@ class MPICHRunner(MultiNodeRunner):
         rank = 0
         total = self._total_procs()
         for h in hosts:
-            for lr in range(len(active_resources[h])):
+            for lr in range(self._slots(active_resources[h])):
                 if not first:
                     cmd.append(":")
                 first = False
                 cmd += ["-n", "1", "-host", h, "-env", "RANK", str(rank), "-env", "LOCAL_RANK", str(lr), "-env",
-                        "WORLD_SIZE", str(total), "-env", "LOCAL_SIZE", str(len(active_resources[h])), "-env",
+                        "WORLD_SIZE", str(total), "-env", "LOCAL_SIZE", str(self._slots(active_resources[h])), "-env",
                         "MASTER_ADDR", str(self.args.master_addr), "-env", "MASTER_PORT", str(self.args.master_port)]
                 for k, v in self.exports.items():
                     cmd += ["-env", k, v]

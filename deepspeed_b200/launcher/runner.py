@@ -204,6 +204,8 @@ def build_launch_cmd(args, world_info_b64, node_rank=0):
 
 def main(args=None):
     args = parse_args(args)
+    if (args.num_nodes >= 0 or args.num_gpus >= 0) and (args.include != "" or args.exclude != ""):
+        raise ValueError("Cannot specify num_nodes/gpus with include/exclude")
     if args.elastic_training:
         assert args.master_addr != "", "Master Addr is required when elastic training is enabled"
     resource_pool = fetch_hostfile(args.hostfile)
@@ -236,6 +238,7 @@ def main(args=None):
         return
     world_info = encode_world_info(active)
     env = os.environ.copy()
+    kill_cmd = None
     if args.elastic_training:
         cfg = _find_ds_config(args.user_args)
         if cfg:
@@ -262,12 +265,21 @@ def main(args=None):
                         if "=" in line:
                             k, v = line.strip().split("=", 1)
                             runner.add_export(k, v)
-        cmd = runner.get_cmd(env, active)
+        got = runner.get_cmd(env, active)
+        if isinstance(got, tuple):  # pdsh: (command, what to run on the workers on interrupt, environment)
+            cmd, kill_cmd, env = got
+        else:
+            cmd = got
     logger.info(f"cmd = {' '.join(map(shlex.quote, cmd))}")
     proc = subprocess.Popen(cmd, env=env)
 
     def _forward(sig, frame):
         proc.send_signal(sig)
+        if kill_cmd is not None:
+            try:
+                subprocess.Popen(kill_cmd, env=env).wait(timeout=30)
+            except Exception:
+                pass
         try:
             proc.wait(timeout=30)
         except subprocess.TimeoutExpired:

@@ -333,7 +333,7 @@ class DeepSpeedConfig:
         from deepspeed_b200.elasticity import compute_elastic_config, ensure_immutable_elastic_config
         from deepspeed_b200.elasticity.constants import (IGNORE_NON_ELASTIC_BATCH_INFO,
                                                          IGNORE_NON_ELASTIC_BATCH_INFO_DEFAULT)
-        from deepspeed_b200 import __version__
+        from deepspeed_b200 import __reference_version__ as __version__  # (elasticity speaks upstream version numbers)
         self.elasticity_enabled = True
         ensure_immutable_elastic_config(runtime_elastic_config_dict=el)
         final_batch, valid_gpus, micro = compute_elastic_config(ds_config=pd,

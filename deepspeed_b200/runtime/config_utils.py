@@ -15,6 +15,10 @@ from pydantic import BaseModel, ConfigDict
 from deepspeed_b200.utils.logging import logger
 
 
+class DeprecatedParameterConflict(AssertionError, ValueError):
+    """A deprecated key and its replacement were both given (the reference asserts, ``config_utils.py:89``)."""
+
+
 class DeepSpeedConfigModel(BaseModel):
     model_config = ConfigDict(
         validate_default=True,
@@ -52,7 +56,7 @@ class DeepSpeedConfigModel(BaseModel):
             target = reduce(getattr, path[:-1], self)
             leaf = path[-1]
             if leaf in getattr(target, "model_fields_set", ()):  # both old and new given
-                raise ValueError(f"Cannot provide deprecated parameter '{name}' and replacing parameter "
+                raise DeprecatedParameterConflict(f"Cannot provide deprecated parameter '{name}' and replacing parameter "
                                  f"'{new_param}' together")
             try:
                 setattr(target, leaf, value)
