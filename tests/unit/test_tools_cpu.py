@@ -51,12 +51,24 @@ def test_launch_env_and_multinode_cmds():
                            launcher_args="", hostfile="/job/hostfile", master_addr="10.0.0.1", master_port=29500,
                            ssh_port=None, no_local_rank=False, save_pid=False, bind_cores_to_rank=False,
                            elastic_training=False, num_nodes=-1, num_gpus=-1)
-    pool = {"h0": [0, 1], "h1": [0, 1]}
-    for name, cls in RUNNERS.items():
-        r = cls(args, "WORLD", pool)
-        r.add_export("NCCL_DEBUG", "INFO")
-        cmd = r.get_cmd({}, pool)
-        assert "t.py" in cmd and any("NCCL_DEBUG" in str(c) for c in cmd), name
+    import os
+    for k, v in (("OMPI_COMM_WORLD_LOCAL_RANK", "0"), ("OMPI_COMM_WORLD_RANK", "0"), ("OMPI_COMM_WORLD_SIZE", "1")):
+        os.environ[k] = v  # the OpenMPI runner validates that it runs inside an MPI job (reference behaviour)
+    try:
+        for pool in ({"h0": [0, 1], "h1": [0, 1]}, {"h0": 2, "h1": 2}):  # slot lists (runner) and slot counts (hostfile form)
+            for name, cls in RUNNERS.items():
+                r = cls(args, "WORLD", pool)
+                assert r.name == name or name.startswith(r.name), (r.name, name)
+                r.add_export("NCCL_DEBUG", "INFO")
+                got = r.get_cmd({}, pool)
+                cmd = got[0] if isinstance(got, tuple) else got  # pdsh: (cmd, kill_cmd, env)
+                if isinstance(got, tuple):
+                    assert got[1][0] == "pdsh" and got[2]["PDSH_RCMD_TYPE"] == "ssh"
+                assert "t.py" in cmd and any("NCCL_DEBUG" in str(c) for c in cmd), name
+    finally:
+        for k in ("OMPI_COMM_WORLD_LOCAL_RANK", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "LOCAL_RANK", "RANK",
+                  "WORLD_SIZE"):
+            os.environ.pop(k, None)
 
 
 def test_env_report_runs(capsys):
