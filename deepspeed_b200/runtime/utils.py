@@ -188,12 +188,16 @@ def _feasible(prefix, num_parts, limit):
 
 
 def partition_balanced(weights, num_parts):
-    """Contiguous partition minimising the heaviest part (binary search over the bottleneck weight)."""
+    """Contiguous partition of ``weights`` into ``num_parts`` parts: first minimise the heaviest part (binary search over the
+    bottleneck), then -- among the partitions that achieve it -- maximise the LIGHTEST part, so no pipeline stage is left
+    (nearly) empty when a more even split with the same bottleneck exists (reference ``runtime/utils.py:583`` solves the
+    linear partition problem for the same max - min objective)."""
     n = len(weights)
     if n <= num_parts:
         return partition_uniform(n, num_parts)
-    prefix = prefix_sum_inc([float(w) for w in weights])
-    lo, hi = max(weights), prefix[-1]
+    w = [float(x) for x in weights]
+    prefix = prefix_sum_inc(w)
+    lo, hi = max(w), prefix[-1]
     best = _feasible(prefix, num_parts, hi)
     for _ in range(64):
         if hi - lo < 1e-6 * max(1.0, hi):
@@ -204,7 +208,42 @@ def partition_balanced(weights, num_parts):
             best, hi = got, mid
         else:
             lo = mid
-    return best
+    cap = max(prefix[e - 1] - (prefix[b - 1] if b else 0.0) for b, e in zip(best[:-1], best[1:]) if e > b) + 1e-9
+    S = [0.0] + prefix
+
+    def split_with_floor(floor):
+        """Boundaries of a split into exactly num_parts parts with every part in [floor, cap], or None."""
+        reach = [[False] * (n + 1) for _ in range(num_parts + 1)]
+        back = [[-1] * (n + 1) for _ in range(num_parts + 1)]
+        reach[0][0] = True
+        for j in range(1, num_parts + 1):
+            for i in range(j, n + 1):
+                for k in range(i - 1, j - 2, -1):
+                    part = S[i] - S[k]
+                    if part > cap:
+                        break
+                    if part >= floor - 1e-9 and reach[j - 1][k]:
+                        reach[j][i], back[j][i] = True, k
+                        break
+        if not reach[num_parts][n]:
+            return None
+        cuts, i = [n], n
+        for j in range(num_parts, 0, -1):
+            i = back[j][i]
+            cuts.append(i)
+        return cuts[::-1]
+
+    candidates = sorted({S[i] - S[k] for k in range(n) for i in range(k + 1, n + 1) if S[i] - S[k] <= cap})
+    good = split_with_floor(candidates[0] if candidates else 0.0)
+    lo_i, hi_i = 0, len(candidates) - 1
+    while lo_i <= hi_i:  # the largest floor that still admits a split
+        mid = (lo_i + hi_i) // 2
+        got = split_with_floor(candidates[mid])
+        if got is not None:
+            good, lo_i = got, mid + 1
+        else:
+            hi_i = mid - 1
+    return good if good is not None else best
 
 
 class PartitionedTensor:

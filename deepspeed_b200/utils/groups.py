@@ -303,7 +303,37 @@ def _get_expert_parallel_group(group_name):
     return _groups.get(f"ep:{group_name}")
 
 
-def _get_expert_parallel_ranks(group_name):
+def _get_expert_parallel_ranks(world_size, tensor_parallel_size_, expert_parallel_size_, pipeline_parallel_size_=1,
+                               use_data_before_expert_parallel_=False):
+    """Rank lists of every expert-parallel and expert-data-parallel group of an E + M (+ P) + D layout (pure function;
+    reference ``utils/groups.py:307``).  Tensor-parallel ranks are adjacent, data-parallel ranks of one tensor slice are
+    ``tensor_parallel_size_`` apart; an expert-parallel group takes ``expert_parallel_size_`` consecutive data-parallel
+    ranks (E + D) or, with ``use_data_before_expert_parallel_``, every ``dp / ep``-th one (D + E); the ranks that hold the
+    same experts form the expert-data-parallel groups.
+
+    world 16, tensor 2, expert 4 -> EP [[0, 2, 4, 6], [8, 10, 12, 14], [1, 3, 5, 7], [9, 11, 13, 15]],
+    EDP [[0, 8], [2, 10], [4, 12], [6, 14], [1, 9], [3, 11], [5, 13], [7, 15]]."""
+    tp, pp, ep = int(tensor_parallel_size_), int(pipeline_parallel_size_), int(expert_parallel_size_)
+    assert world_size % (tp * pp) == 0, f"{world_size} is not divisible by {tp * pp}"
+    dp_world = world_size // (tp * pp)
+    assert dp_world % ep == 0, f"{dp_world} is not divisible by {ep}"
+    ep_groups, edp_groups = [], []
+    pp_stride = world_size // pp
+    for stage_start in range(0, world_size, pp_stride):
+        for t in range(tp):
+            dp_ranks = list(range(stage_start + t, stage_start + pp_stride, tp))
+            if use_data_before_expert_parallel_:
+                stride = dp_world // ep
+                groups_here = [dp_ranks[i::stride] for i in range(stride)]
+            else:
+                groups_here = [dp_ranks[i:i + ep] for i in range(0, dp_world, ep)]
+            ep_groups.extend(groups_here)
+            edp_groups.extend([list(col) for col in zip(*groups_here)])
+    return ep_groups, edp_groups
+
+
+def _expert_parallel_ranks_of(group_name):
+    """Ranks of the named, already created expert-parallel group."""
     return _ranks.get(f"ep:{group_name}", [_rank()])
 
 
