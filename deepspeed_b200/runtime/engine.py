@@ -664,10 +664,14 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
             f"{self.zero_optimization_stage()}"
         assert not getattr(self, "inside_no_sync_ctxt", False), "no_sync context manager reentry is unsupported"
         self.inside_no_sync_ctxt = True
+        if hasattr(self.optimizer, "set_no_sync"):
+            self.optimizer.set_no_sync(True)
         try:
             yield
         finally:
             self.inside_no_sync_ctxt = False
+            if hasattr(self.optimizer, "set_no_sync"):
+                self.optimizer.set_no_sync(False)
 
     @instrument_w_nvtx
     def backward(self, loss, retain_graph=False, scale_wrt_gas=True):
@@ -675,7 +679,7 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         self.timers(BACKWARD_MICRO_TIMER).start()
         self.timers(BACKWARD_GLOBAL_TIMER).start()
         gas = self.gradient_accumulation_steps()
-        if gas > 1 and scale_wrt_gas:
+        if gas > 1 and scale_wrt_gas and not getattr(self, "inside_no_sync_ctxt", False):
             loss = loss / gas
         if self.monitor.enabled and self.is_gradient_accumulation_boundary():
             self._last_loss_for_monitor = loss.detach()
@@ -687,6 +691,8 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
     def zero_grad(self):
         for p in self.module.parameters():
             p.grad = None
+        if self.optimizer is not None and hasattr(self.optimizer, "zero_grad"):
+            self.optimizer.zero_grad()  # also drops gradients parked by no_sync()
 
     def clip_fp32_gradients(self):
         pass  # clipping is fused into the sharded optimizer step
@@ -713,6 +719,8 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
     @instrument_w_nvtx
     def step(self, lr_kwargs=None):
         assert self.optimizer is not None, "must provide optimizer during init in order to use step"
+        assert not getattr(self, "inside_no_sync_ctxt", False), \
+            "It is illegal to call Engine.step() inside no_sync context manager"
         self.timers(STEP_MICRO_TIMER).start()
         self.timers(STEP_GLOBAL_TIMER).start()
         self._step_applied = False

@@ -67,7 +67,12 @@ class ZeroOptimizerGroup:
             p.end_backward()
 
     def zero_grad(self, set_to_none=True):
-        self.parts[0].zero_grad(set_to_none)
+        for p in self.parts:
+            p.zero_grad(set_to_none)
+
+    def set_no_sync(self, on):
+        for p in self.parts:
+            p.set_no_sync(on)
 
     def set_gradient_accumulation_steps(self, gas):
         for p in self.parts:

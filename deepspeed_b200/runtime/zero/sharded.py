@@ -68,6 +68,7 @@ class _UnitRT:
         self.temp_refs = 0  # GatheredParameters / external users holding the unit
         self.home = None  # buffer used by this iteration's forward gather (backward MUST reuse it)
         self.running = 0  # forward passes of the unit's module currently executing (re-entrancy counter)
+        self.unsynced = None  # local gradient parked by backward passes under engine.no_sync()
         self.fwd_calls = 0  # grad-enabled forward invocations of the module since the last backward finished
         self.bwd_calls = 0  # ... and how many of them have been back-propagated
         self.consumed = False  # a module hook actually used the gathered copy (vs. a speculative prefetch)
@@ -940,9 +941,31 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         return self._accum == 0 and not (rt is not None and rt.reduced_this_micro)
 
     @instrument_w_nvtx
+    def set_no_sync(self, on: bool):
+        """``engine.no_sync()``: backward passes keep their gradients local (no reduction, no step); the next synchronised
+        backward reduces them together with its own (reference ``engine.py:2065``)."""
+        self._no_sync = bool(on)
+
     def _reduce_unit(self, rt: _UnitRT):
         u = rt.u
         full_g = rt.grad_full
+        if getattr(self, "_no_sync", False):
+            if rt.unsynced is None:
+                rt.unsynced = full_g[:u.full_numel].clone()
+            else:
+                rt.unsynced.add_(full_g[:u.full_numel])
+            if self.on_cuda:
+                ev2 = torch.cuda.Event()
+                ev2.record()
+                rt.grad_slot.free_event = ev2
+            rt.grad_full = None
+            rt.grad_slot.owner = None if rt.grad_slot.owner is rt else rt.grad_slot.owner
+            if self.transient and not u.persistent:
+                self.release_unit(rt)
+            return
+        if rt.unsynced is not None:
+            full_g[:u.full_numel].add_(rt.unsynced)
+            rt.unsynced = None
         cur = torch.cuda.current_stream() if self.on_cuda else None
         stream = self.rs_stream
         if stream is not None:
@@ -1319,6 +1342,8 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     def zero_grad(self, set_to_none=True):
         for p in self.module.parameters():
             p.grad = None
+        for rt in self.rts:
+            rt.unsynced = None  # gradients parked under engine.no_sync()
 
     def _group_hyper(self, gi):
         return self.param_groups[gi]
@@ -1681,9 +1706,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         return self._gather_arena_piece(self.master, rt, s)
 
     def get_full_hp_grad(self, p):
+        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
+        if rt.unsynced is not None:  # inside engine.no_sync(): this rank's local, not yet reduced gradient
+            return rt.unsynced[s.offset:s.offset + s.numel].view(s.shape).float().clone()
         if self.grad_arena is None:
             return None
-        rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
         return self._gather_arena_piece(self.grad_arena, rt, s)
 
     def get_full_optimizer_state(self, p, key):
