@@ -29,7 +29,15 @@ def _git(*args):
 git_hash = _git("rev-parse", "--short", "HEAD")
 git_branch = _git("rev-parse", "--abbrev-ref", "HEAD")
 accelerator_name = "cuda" if torch.cuda.is_available() else "cpu"
-torch_info = {"version": torch.__version__, "cuda_version": torch.version.cuda or "0.0", "hip_version": "0.0"}
+def _nccl_version():
+    try:
+        return ".".join(str(x) for x in torch.cuda.nccl.version()[:2])
+    except Exception:
+        return "0.0"
+
+
+torch_info = {"version": torch.__version__, "bf16_support": True, "cuda_version": torch.version.cuda or "0.0",
+              "nccl_version": _nccl_version(), "hip_version": "0.0"}
 
 
 def _ops():

@@ -52,6 +52,10 @@ class DeepSpeedConfigError(Exception):
     pass
 
 
+class DeepSpeedBatchConfigError(DeepSpeedConfigError, AssertionError):
+    pass
+
+
 # ------------------------------------------------------------------------------------------------
 # blocks
 # ------------------------------------------------------------------------------------------------
@@ -542,7 +546,8 @@ class DeepSpeedConfig:
             gas = 1
             tb = mb * ws
         else:
-            raise DeepSpeedConfigError("Either train_batch_size or train_micro_batch_size_per_gpu needs to be provided")
+            # (an AssertionError like every other batch-triad check -- the reference asserts here, config.py:975)
+            raise DeepSpeedBatchConfigError("Either train_batch_size or train_micro_batch_size_per_gpu needs to be provided")
         self.train_batch_size, self.train_micro_batch_size_per_gpu, self.gradient_accumulation_steps = tb, mb, gas
 
     def _batch_assertion(self):

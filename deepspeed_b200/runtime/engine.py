@@ -680,7 +680,7 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         self.timers(BACKWARD_GLOBAL_TIMER).start()
         gas = self.gradient_accumulation_steps()
         if gas > 1 and scale_wrt_gas and not getattr(self, "inside_no_sync_ctxt", False):
-            loss = loss / gas
+            loss = loss.float() / gas  # (fp32: the reference scales `loss.float()`, engine.py:2102)
         if self.monitor.enabled and self.is_gradient_accumulation_boundary():
             self._last_loss_for_monitor = loss.detach()
         self.optimizer.backward(loss, retain_graph=retain_graph)

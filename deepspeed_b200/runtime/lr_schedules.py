@@ -152,10 +152,19 @@ class OneCycle(_Schedule):
 
     def _apply_mom(self, moms):
         for g, m in zip(self.optimizer.param_groups, moms):
+            m = m[0] if isinstance(m, (tuple, list)) else m
             if "betas" in g:
                 g["betas"] = (m, g["betas"][1])
             else:
                 g["momentum"] = m
+
+    def _mom_out(self, values):
+        """Per group: ``(beta1, beta2)`` for Adam-style optimizers, the momentum scalar otherwise (reference
+        ``lr_schedules.py:592 get_mom`` returns the ``betas`` pairs)."""
+        out = []
+        for g, m in zip(self.optimizer.param_groups, values):
+            out.append((m, g["betas"][1]) if "betas" in g else m)
+        return out
 
     def _scale(self):
         it = self.last_batch_iteration + 1
@@ -174,14 +183,16 @@ class OneCycle(_Schedule):
         return [lo / f for lo in self.min_lrs]
 
     def get_mom(self):
+        if not self.cycle_momentum:
+            return None
         it = self.last_batch_iteration + 1
         if it < self.total_size:
             s = self._scale()
-            return [hi - (hi - lo) * s for lo, hi in zip(self.min_moms, self.max_moms)]
+            return self._mom_out([hi - (hi - lo) * s for lo, hi in zip(self.min_moms, self.max_moms)])
         decay_it = it - self.total_size + 1
         interval = decay_it / self.decay_step_size if self.decay_step_size else 0.0
         f = 1 + self.decay_mom_rate * interval
-        return [hi * f for hi in self.max_moms]
+        return self._mom_out([hi * f for hi in self.max_moms])
 
     def step(self, batch_iteration=None):
         super().step(batch_iteration)

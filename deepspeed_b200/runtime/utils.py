@@ -94,6 +94,15 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2, mpu=None):
     total = get_grad_norm(parameters, norm_type, mpu)
     if total < 0:
         return total
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        # expert (MoE) parameters differ across data-parallel ranks, so the local norms do too: every rank clips with the
+        # data-parallel MEAN of the norms (reference runtime/utils.py:411-418)
+        from deepspeed_b200.utils import groups
+        pg = groups._get_data_parallel_group()
+        t = torch.tensor([float(total)], dtype=torch.float32,
+                         device="cuda" if dist.get_backend() == "nccl" and torch.cuda.is_available() else "cpu")
+        dist.all_reduce(t, group=pg)
+        total = float(t.item()) / dist.get_world_size(group=pg)
     coef = max_norm / (total + 1e-6)
     if coef < 1:
         for p in parameters:
@@ -119,6 +128,16 @@ class CheckOverflow:
         self.params = [p for g in (param_groups or []) for p in g]
         self.zero_reduce_scatter = zero_reduce_scatter
         self.deepspeed = deepspeed
+        # expert parameters (``allreduce == False``) only exist on some ranks: their overflow state must be agreed inside the
+        # expert-parallel group first (reference runtime/utils.py:182-197)
+        self.has_moe_params = any(getattr(p, "allreduce", True) is False for p in self.params)
+
+    def _moe_group(self):
+        from deepspeed_b200.utils import groups
+        try:
+            return groups._get_max_expert_parallel_group()
+        except Exception:
+            return None
 
     @staticmethod
     def _has_inf_or_nan(x):
@@ -139,6 +158,22 @@ class CheckOverflow:
     def check(self, param_groups=None):
         params = [p for g in (param_groups or []) for p in g] if param_groups is not None else self.params
         return self.has_overflow(params)
+
+    def check_using_norm(self, norm_group, reduce_overflow=True):
+        """Overflow decided from per-group norms (``-1`` marks inf / nan, see ``get_weight_norm``), agreed across the model-
+        parallel group and -- with ``reduce_overflow`` -- across all ranks (reference ``runtime/utils.py:199``)."""
+        overflow = -1 in [float(n) for n in norm_group]
+        dev = "cuda" if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([float(overflow)], device=dev)
+        if dist.is_initialized():
+            if self.has_moe_params:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._moe_group())
+            if self.mpu is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.mpu.get_model_parallel_group())
+            elif reduce_overflow:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.barrier()
+        return bool(t.item())
 
 
 # ---- partitioning ------------------------------------------------------------------------------------------------
@@ -402,7 +437,10 @@ def get_weight_norm(parameters, norm_type=2, mpu=None):
     if torch.is_tensor(parameters):
         parameters = [parameters]
     tensors = [p.data for p in parameters]
-    return get_global_norm_of_tensors(tensors, norm_type=norm_type, mpu=mpu)
+    total = float(get_global_norm_of_tensors(tensors, norm_type=norm_type, mpu=mpu))
+    if total in (float("inf"), -float("inf")) or total != total:
+        total = -1  # the overflow marker CheckOverflow.check_using_norm looks for (reference runtime/utils.py:543)
+    return total
 
 
 def get_flattened_grad_norm(parameters, norm_type=2, mpu=None, grad_norm_mask=None):
