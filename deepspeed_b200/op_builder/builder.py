@@ -191,6 +191,11 @@ class OpBuilder:
     validate_torch_op_version = validate_torch_version
 
     @staticmethod
+    def installed_rocm_version():
+        """(major, minor) of a ROCm toolchain -- there is none on this single-vendor build (reference ``builder.py:163``)."""
+        return 0, 0
+
+    @staticmethod
     def is_rocm_pytorch():
         return False
 

@@ -135,6 +135,66 @@ class CheckpointMixin:
                 od[n] = fn(p)
         return od
 
+    @torch.no_grad()
+    def _frozen_param_fragment(self, p):
+        """Reference ``_get_param_fragment_func`` (engine.py:3520): the whole tensor below stage 3, this DP rank's
+        zero-padded ``ceil(numel / dp)`` piece at stage 3 (collective: every rank walks the parameters in the same order)."""
+        from deepspeed_b200.runtime.zero.partition_parameters import is_zero_param, materialize_full
+        if not (self.zero_optimization_partition_weights() and is_zero_param(p)):
+            return p.detach().cpu().clone()
+        flat = materialize_full(p).detach().reshape(-1)
+        world, rank = self.seq_dp_world_size, self._dp_rank_for_ckpt
+        per = -(-flat.numel() // world)
+        piece = torch.zeros(per, dtype=flat.dtype)
+        lo, hi = rank * per, min((rank + 1) * per, flat.numel())
+        if hi > lo:
+            piece[:hi - lo].copy_(flat[lo:hi])
+        return piece
+
+    @torch.no_grad()
+    def _restore_frozen_params(self, ckpt, load_dir, tag, own_file):
+        """Stage 3: rebuild every frozen parameter from the per-rank pieces saved next to the module state and write it
+        into the unit arenas (below stage 3 the frozen values arrive through the module state dict)."""
+        frags, shapes = ckpt.get("frozen_param_fragments"), ckpt.get("frozen_param_shapes")
+        if not frags or not shapes or self.optimizer is None:
+            return
+        from deepspeed_b200.runtime.zero.partition_parameters import _owner
+        named = dict(self.module.named_parameters())
+        world = self.seq_dp_world_size
+        same = own_file and (ckpt.get("dp_world_size") or 1) == world
+        pieces = None
+        if not same:  # written at another DP degree: read the pieces of every saved rank
+            import glob
+            import re
+            own = os.path.basename(self._get_ckpt_name(load_dir, tag))
+            pat = re.sub(r"zero_pp_rank_\d+_", "zero_pp_rank_*_", own)
+            files = sorted(glob.glob(os.path.join(load_dir, str(tag), pat)),
+                           key=lambda f: int(re.search(r"zero_pp_rank_(\d+)_", os.path.basename(f)).group(1)))
+            pieces = [self.checkpoint_engine.load(f, map_location="cpu").get("frozen_param_fragments") or {} for f in files]
+        for name, shape in shapes.items():
+            p = named.get(name)
+            if p is None or name not in frags:
+                continue
+            n = 1
+            for d in shape:
+                n *= int(d)
+            if same:
+                dev = self.device if dist.get_backend() == "nccl" else "cpu"
+                local = frags[name].reshape(-1).to(dev)
+                if world > 1:
+                    out = torch.empty(local.numel() * world, dtype=local.dtype, device=dev)
+                    dist.all_gather_into_tensor(out, local.contiguous(), group=self.seq_data_parallel_group)
+                else:
+                    out = local
+            else:
+                out = torch.cat([d[name].reshape(-1) for d in pieces])
+            full = out[:n].view(tuple(shape))
+            zo = _owner(p)
+            if zo is not None:
+                zo.set_full_hp_param(full, p)
+            else:
+                p.data.copy_(full.to(p.device, p.dtype))
+
     # ---- save ------------------------------------------------------------------------------------------
     def save_checkpoint(self, save_dir, tag=None, client_state=None, save_latest=True, exclude_frozen_parameters=False):
         client_state = client_state or {}
@@ -170,14 +230,19 @@ class CheckpointMixin:
                 # placeholders only: real values live in the ZeRO shards
                 module_sd = OrderedDict((k, (v if v.numel() else torch.empty(0, dtype=v.dtype)))
                                         for k, v in module_sd.items())
+        # frozen parameters never reach the optimizer shards: the reference (engine.py:3465) keeps them next to the
+        # module state, whole for stage 2 and as this rank's ceil(numel / dp) piece for stage 3
+        save_frozen = (self.optimizer is not None and self.zero_optimization_partition_gradients()
+                       and not exclude_frozen_parameters)
         state = dict(
             module=module_sd,
             buffer_names=[n for n, _ in self.module.named_buffers()],
             optimizer=None,
             param_shapes=self._get_zero_param_shapes() if self.optimizer is not None else None,
             frozen_param_shapes=self._get_zero_frozen_param_attributes(lambda p: torch.Size(
-                getattr(p, "ds_shape", p.shape))) if zero3 else None,
-            frozen_param_fragments=None,
+                getattr(p, "ds_shape", p.shape))) if save_frozen else None,
+            frozen_param_fragments=self._get_zero_frozen_param_attributes(self._frozen_param_fragment)
+            if save_frozen else None,
             shared_params=self._get_shared_params(),
             lr_scheduler=self.lr_scheduler.state_dict() if self.lr_scheduler is not None and hasattr(
                 self.lr_scheduler, "state_dict") else None,
@@ -292,7 +357,8 @@ class CheckpointMixin:
 
     def _load_checkpoint(self, load_dir, tag, strict, load_opt, load_sched, module_only, custom_load_fn):
         path = self._get_ckpt_name(load_dir, tag)
-        if not os.path.exists(path):
+        own_file = os.path.exists(path)
+        if not own_file:
             # ZeRO-3 files are per-DP-rank; fall back to rank-0 file for replicated metadata
             alt = path.replace(f"zero_pp_rank_{self._dp_rank_for_ckpt}_", "zero_pp_rank_0_")
             if os.path.exists(alt):
@@ -312,6 +378,7 @@ class CheckpointMixin:
             bufs = {k: v for k, v in ckpt["module"].items() if k in ckpt.get("buffer_names", [])}
             if bufs:
                 self.module.load_state_dict(bufs, strict=False)
+            self._restore_frozen_params(ckpt, load_dir, tag, own_file=own_file)
         self._loaded_param_shapes = ckpt.get("param_shapes")
         self.loaded_checkpoint_dp_world_size = ckpt.get("dp_world_size")
         self.loaded_checkpoint_mp_world_size = ckpt.get("mp_world_size")

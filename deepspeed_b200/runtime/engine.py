@@ -613,6 +613,20 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         return tuple(cast(a) for a in args), {k: cast(v) for k, v in kwargs.items()}
 
     @instrument_w_nvtx
+    def __getattr__(self, name):
+        """Attributes the engine does not define fall through to the wrapped client module (``engine.config``,
+        ``engine.generate`` ... on a wrapped HF model). Reference: runtime/engine.py:573."""
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            mod = self.__dict__.get("_modules", {}).get("module")
+            if mod is not None and name != "module":
+                try:
+                    return getattr(mod, name)
+                except AttributeError:
+                    pass
+            raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'") from None
+
     def forward(self, *inputs, **kwargs):
         if self.flops_profiler is not None and self.global_steps == self._config.flops_profiler_config.profile_step \
                 and self.global_rank == 0 and self.module.training:

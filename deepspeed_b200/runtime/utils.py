@@ -481,7 +481,7 @@ get_norm_with_moe_layers_fast = get_norm_with_moe_layers
 def get_inactive_params(param_list):
     """ZeRO-3 parameters whose full tensor is currently not materialised."""
     from deepspeed_b200.runtime.zero.partition_parameters import is_zero_param
-    return [p for p in param_list if is_zero_param(p) and getattr(p, "ds_status", None) == "NOT_AVAILABLE"]
+    return [p for p in param_list if is_zero_param(p) and getattr(getattr(p, "ds_status", None), "name", getattr(p, "ds_status", None)) == "NOT_AVAILABLE"]
 
 
 def compare_tensors_in_structures(a, b) -> bool:

@@ -110,11 +110,11 @@ def _next_id():
 @torch.no_grad()
 def materialize_full(p: nn.Parameter, device=None) -> torch.Tensor:
     """Return the full tensor of a ZeRO parameter (all-gather of the per-rank slices)."""
+    zo = _owner(p)
+    if zo is not None:  # adopted by a sharded optimizer: its unit arena is the source of truth
+        return zo.get_full_lp_param(p)
     piece = getattr(p, "ds_tensor", None)
     if piece is None:
-        zo = _owner(p)
-        if zo is not None:
-            return zo.get_full_lp_param(p)
         return p.data
     group = getattr(p, "ds_group", None)
     world = _world(group)
@@ -137,7 +137,13 @@ def _attach_methods(p):
     """Per-parameter convenience API mirroring the reference (``param.all_gather()``, ``.partition()``)."""
 
     def all_gather(param_list=None, async_op=False, hierarchy=0):
-        todo = [q for q in (param_list or [p]) if q.data.numel() == 0 and getattr(q, "ds_tensor", None) is not None]
+        qs = list(param_list or [p])
+        for q in qs:  # adopted by a sharded optimizer: gather the owning unit outside its rotating pool
+            zo = _owner(q)
+            if zo is not None and not getattr(q, "_ds_user_gathered", False):
+                zo.gather_param_temp(q)
+                q._ds_user_gathered = True
+        todo = [q for q in qs if _owner(q) is None and q.data.numel() == 0 and getattr(q, "ds_tensor", None) is not None]
         if async_op:
             return all_gather_coalesced(todo)
         for q in todo:
@@ -146,6 +152,14 @@ def _attach_methods(p):
 
     def partition(param_list=None, hierarchy=0, has_been_updated=False):
         for q in (param_list or [p]):
+            zo = _owner(q)
+            if zo is not None:
+                if has_been_updated and q.data.numel() == q.ds_numel:
+                    zo.set_full_hp_param(q.data, q)
+                if getattr(q, "_ds_user_gathered", False):
+                    q._ds_user_gathered = False
+                    zo.release_param_temp(q)
+                continue
             if has_been_updated and q.data.numel():
                 _write_back(q, q.data)
             if getattr(q, "ds_tensor", None) is not None:
@@ -158,9 +172,9 @@ def _attach_methods(p):
         "id": p.ds_id,
         "status": p.ds_status.name if isinstance(p.ds_status, Enum) else p.ds_status,
         "numel": p.numel(),
-        "ds_numel": p.ds_numel,
+        "ds_numel": getattr(p, "ds_numel", p.numel()),
         "shape": tuple(p.shape),
-        "ds_shape": tuple(p.ds_shape),
+        "ds_shape": tuple(getattr(p, "ds_shape", p.shape)),
         "requires_grad": p.requires_grad,
     }
 
@@ -271,6 +285,10 @@ def debug_rank0(msg):
 @torch.no_grad()
 def _write_back(p, full):
     """Store ``full`` back into the per-rank slice of an Init-sharded parameter."""
+    zo = _owner(p)
+    if zo is not None:
+        zo.set_full_hp_param(full, p)
+        return
     piece = p.ds_tensor
     world, rank = _world(getattr(p, "ds_group", None)), _rank(getattr(p, "ds_group", None))
     sl = piece.numel()
@@ -404,6 +422,10 @@ class Init(contextlib.AbstractContextManager):
                 self._shard_param(p)
 
     def _shard_param(self, p):
+        if p.device.type == "meta":
+            # ``torch.nn.utils.skip_init`` / ``device="meta"`` construction: nothing to shard yet. The parameter is picked
+            # up once it has storage (``to_empty`` then attachment to the parent, or the sweep when the context exits).
+            return
         dev = None
         if self.remote_device in ("cpu", "nvme"):
             dev = "cpu"

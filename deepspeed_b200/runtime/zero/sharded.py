@@ -41,6 +41,11 @@ from deepspeed_b200.utils.nvtx import instrument_w_nvtx
 NOT_GATHERED, INFLIGHT, GATHERED = 0, 1, 2
 
 
+def _param_status():
+    from deepspeed_b200.runtime.zero.partition_parameters import ZeroParamStatus
+    return ZeroParamStatus
+
+
 class _Slot:
     """One buffer of a rotating pool plus the event that marks it reusable."""
 
@@ -513,7 +518,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
     def _point_params(self, rt: _UnitRT, full: torch.Tensor):
         for s in rt.u.slots:
             s.param.data = full[s.offset:s.offset + s.numel].view(s.shape)
-            s.param.ds_status = "AVAILABLE"
+            s.param.ds_status = _param_status().AVAILABLE
 
     def _detach_params(self, rt: _UnitRT):
         for s in rt.u.slots:
@@ -527,7 +532,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 p.data = torch.empty(1, dtype=p.dtype, device=self.device).expand(s.shape)
             else:
                 p.data = torch.empty(0, dtype=p.dtype, device=self.device)
-            p.ds_status = "NOT_AVAILABLE"
+            p.ds_status = _param_status().NOT_AVAILABLE
 
     # =========================================================================================
     # hooks
@@ -539,6 +544,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 p = s.param
                 p.ds_unit_index = rt.u.index
                 p._ds_zero = weakref.ref(self)
+                self._tag_param(rt, s)
                 if p.requires_grad:
                     self._hook_handles.append(p.register_post_accumulate_grad_hook(self._make_grad_hook(rt, s)))
             m = rt.u.module
@@ -551,6 +557,35 @@ class ZeroShardedOptimizer(ZeROOptimizer):
                 self._hook_handles.append(m.register_full_backward_pre_hook(self._make_pre_bwd(rt)))
                 if bool(getattr(self.zc, "b200_multi_forward", True)):
                     self._hook_handles.append(m.register_full_backward_hook(self._make_post_bwd(rt)))
+
+    def _tag_param(self, rt, s):
+        """Reference-style per-parameter introspection attributes (``partition_parameters.py:1111``): ``ds_id``,
+        ``ds_persist`` and ``ds_tensor``. The shard layout here is per *unit*, so ``ds_tensor`` is the (possibly empty)
+        piece of this parameter that falls inside this rank's slice of the unit, not a ``ceil(numel / world)`` block."""
+        p = s.param
+        if not hasattr(p, "ds_id"):
+            from deepspeed_b200.runtime.zero.partition_parameters import _next_id
+            p.ds_id = _next_id()
+        p.ds_persist = bool(rt.u.persistent)
+        if self.stage < 3:
+            return
+        if not hasattr(p, "ds_numel"):
+            p.ds_numel, p.ds_shape = s.numel, s.shape
+        if not hasattr(p, "ds_status"):
+            p.ds_status = _param_status().AVAILABLE
+        if not hasattr(p, "ds_summary"):
+            from deepspeed_b200.runtime.zero.partition_parameters import _attach_methods
+            _attach_methods(p)
+        try:
+            shard = self._lp_shard(rt.u)
+        except Exception:
+            return
+        if not torch.is_tensor(shard):
+            return
+        lo, hi = rt.u.shard_range(self.shard_rank)
+        a, b = max(s.offset, lo), min(s.offset + s.numel, hi)
+        # also drops a zero.Init piece (its value was packed into the unit arena; keeping it would double the lp shard)
+        p.ds_tensor = shard[a - lo:b - lo] if a < b else shard[:0]
 
     def _make_pre_fwd(self, rt):
 

@@ -636,3 +636,44 @@ def _sched_ckpt_worker(d):
 
 def test_scheduler_state_latest_tag_and_client_state(tmp_path):
     run_distributed(_sched_ckpt_worker, 1, (str(tmp_path), ))
+
+
+def _frozen_model(seed):
+    torch.manual_seed(seed)
+    m = SimpleModel()
+    first = next(iter(m.parameters()))
+    first.requires_grad_(False)
+    return m
+
+
+def _frozen_ckpt_worker(d, stage, phase):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_fp32_param
+    from deepspeed_b200.utils.zero_to_fp32 import get_fp32_state_dict_from_zero_checkpoint
+    if phase == "save":
+        eng, *_ = ds.initialize(model=_frozen_model(0), config=_cfg(stage, ds.comm.get_world_size()))
+        _steps(eng, 2, 1)
+        eng.save_checkpoint(d, tag="fz")
+        full = {n: safe_get_full_fp32_param(p).cpu() for n, p in eng.module.named_parameters()}
+        ds.comm.barrier()
+        if ds.comm.get_rank() == 0:
+            torch.save(full, os.path.join(d, "expect.pt"))
+            sd = get_fp32_state_dict_from_zero_checkpoint(d, "fz")
+            for n, v in full.items():
+                torch.testing.assert_close(sd[n].float(), v, atol=1e-6, rtol=1e-5)
+        return
+    eng, *_ = ds.initialize(model=_frozen_model(77), config=_cfg(stage, ds.comm.get_world_size()))
+    path, _ = eng.load_checkpoint(d)
+    assert path is not None
+    exp = torch.load(os.path.join(d, "expect.pt"))
+    for n, p in eng.module.named_parameters():
+        torch.testing.assert_close(safe_get_full_fp32_param(p).cpu(), exp[n], atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("stage,new_world", [(2, 2), (3, 2), (3, 1)])
+def test_frozen_parameters_round_trip(tmp_path, stage, new_world):
+    """Frozen parameters live outside the optimizer shards: saved as reference-layout fragments next to the module state,
+    restored in-engine (also at another DP degree) and read back by zero_to_fp32."""
+    d = str(tmp_path)
+    run_distributed(_frozen_ckpt_worker, 2, (d, stage, "save"))
+    run_distributed(_frozen_ckpt_worker, new_world, (d, stage, "load"))
