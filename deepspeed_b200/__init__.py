@@ -97,11 +97,13 @@ def initialize(args=None,
         if probe is not None and probe.get("sequence_parallel_size", 1) > 1 and probe.get("data_parallel_size"):
             mesh_device = comm.initialize_mesh_device(
                 (probe["data_parallel_size"], probe["sequence_parallel_size"]), ("data_parallel", "sequence_parallel"))
-    cfg = DeepSpeedConfig(config, mpu, mesh_device=mesh_device)
     try:
         from .runtime.pipe.module import PipelineModule
     except ImportError:  # pipeline package optional at import time
         PipelineModule = ()
+    # a PipelineModule carries its own topology: the batch triad is resolved against ITS data-parallel degree
+    cfg_mpu = model.mpu() if (PipelineModule and isinstance(model, PipelineModule) and mpu is None) else mpu
+    cfg = DeepSpeedConfig(config, cfg_mpu, mesh_device=mesh_device)
     if PipelineModule and isinstance(model, PipelineModule):
         from .runtime.pipe.engine import PipelineEngine
         assert mpu is None, "mpu must be None with pipeline parallelism"

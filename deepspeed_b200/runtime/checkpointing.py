@@ -72,6 +72,11 @@ class CheckpointMixin:
         dp_rank = 0 if getattr(self, "_optimizer_replicated", False) else self._dp_rank_for_ckpt
         return os.path.join(checkpoints_path, str(tag), f"{self._get_zero_ckpt_prefix(dp_rank, bf16)}_optim_states.pt")
 
+    def _get_optimizer_ckpt_name(self, checkpoints_path, tag, expp_rank):
+        """Reference name of the per-expert-parallel-rank optimizer file of a non-ZeRO MoE run (engine.py:2844). Every
+        optimizer here is a sharded one and goes through ``_get_zero_ckpt_name``; kept for tools that build the path."""
+        return os.path.join(checkpoints_path, str(tag), f"expp_rank_{expp_rank}_mp_rank_{self._ckpt_mp_rank():02d}_optim_states.pt")
+
     def _get_expert_ckpt_name(self, checkpoints_path, layer_id, expert_id, tag, mp_placeholder=None):
         mp = f"{self._ckpt_mp_rank():02d}" if mp_placeholder is None else mp_placeholder
         return os.path.join(checkpoints_path, str(tag), f"layer_{layer_id}_expert_{expert_id}_mp_rank_{mp}_model_states.pt")
@@ -250,7 +255,7 @@ class CheckpointMixin:
             (self.training_dataloader is not None and getattr(self.training_dataloader, "curriculum_learning_enabled",
                                                               False)) else None,
             random_ltd=None,
-            sparse_tensor_module_names=set(),
+            sparse_tensor_module_names=set(getattr(self, "sparse_tensor_module_names", ())),
             skipped_steps=self.skipped_steps,
             global_steps=self.global_steps,
             global_samples=self.global_samples,
@@ -265,12 +270,23 @@ class CheckpointMixin:
 
     def _get_shared_params(self):
         """Tied parameters: ``{alias_name: canonical_name}`` (reference engine.py:3575)."""
-        seen, shared = {}, {}
+        names = {}
         for n, p in self.module.named_parameters(remove_duplicate=False):
-            if id(p) in seen:
-                shared[n] = seen[id(p)]
-            else:
-                seen[id(p)] = n
+            names.setdefault(id(p), []).append(n)
+        # the canonical name of a tied group is the one the optimizer shards are written under (consolidation tools
+        # resolve ``alias -> canonical`` against the flattened fp32 weights)
+        in_shards = set()
+        if self.optimizer is not None:
+            for od in self._get_zero_param_shapes():
+                in_shards.update(od.keys())
+        shared = {}
+        for group in names.values():
+            if len(group) < 2:
+                continue
+            canon = next((n for n in group if n in in_shards), group[0])
+            for n in group:
+                if n != canon:
+                    shared[n] = canon
         return shared
 
     def _save_checkpoint(self, save_dir, tag, client_state, exclude_frozen_parameters=False):
@@ -379,6 +395,14 @@ class CheckpointMixin:
             if bufs:
                 self.module.load_state_dict(bufs, strict=False)
             self._restore_frozen_params(ckpt, load_dir, tag, own_file=own_file)
+        saved_sparse = ckpt.get("sparse_tensor_module_names", ckpt.get("csr_tensor_module_names"))
+        if saved_sparse is not None:
+            if strict:
+                self.sparse_tensor_module_names = set(saved_sparse)
+            else:  # keep what is sparse in both models; parameters new to this model keep their own setting
+                mine, here = set(self.sparse_tensor_module_names), dict(self.module.named_parameters())
+                keep = {n for n in mine if not (n in ckpt["module"] and n not in saved_sparse)}
+                self.sparse_tensor_module_names = keep | {n for n in saved_sparse if n in here}
         self._loaded_param_shapes = ckpt.get("param_shapes")
         self.loaded_checkpoint_dp_world_size = ckpt.get("dp_world_size")
         self.loaded_checkpoint_mp_world_size = ckpt.get("mp_world_size")

@@ -188,6 +188,13 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
                 model.to(dtype)
             if not self.dont_change_device:
                 model.to(self.device)
+        # embedding tables whose gradients the user asked to treat as sparse (reference engine.py:333); gradients are
+        # densified into the unit's flat buffer before the reduce-scatter here, the set is kept for checkpoint parity
+        self.sparse_tensor_module_names = set()
+        if self._config.sparse_gradients_enabled:
+            for name, sub in model.named_modules():
+                if isinstance(sub, (nn.Embedding, nn.EmbeddingBag)):
+                    self.sparse_tensor_module_names.add(name + ".weight")
         # MoE discovery: create expert groups before the optimizer partitions parameters
         self.has_moe_layers = False
         self.num_experts = []
@@ -269,6 +276,8 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
                 self.optimizer = self._build_twin_flow(stage, common, ratio)
                 return
             self.optimizer = ZeroShardedOptimizer(self.module, stage, dp_group=self.seq_data_parallel_group, **common)
+            from deepspeed_b200.runtime.zero.sharded import tag_reference_class
+            tag_reference_class(self.optimizer)
             self.optimizer.grad_allreduce_enabled = self._dense_grad_allreduce_enabled
             return
         # MoE: dense parameters over the DP group, every expert family over its expert-data-parallel group

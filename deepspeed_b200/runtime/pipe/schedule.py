@@ -212,7 +212,9 @@ def fuse_exchanges(cmds):
     while i < len(cmds):
         a = cmds[i]
         b = cmds[i + 1] if i + 1 < len(cmds) else None
-        if isinstance(a, SendActivation) and isinstance(b, RecvGrad):
+        if isinstance(a, SendActivation) and isinstance(b, RecvGrad) and a.buffer_id != b.buffer_id:
+            # (same buffer = the SAME micro batch: its gradient only exists after the next stage has consumed this very
+            # activation -- a dependency, not an exchange; e.g. one micro batch per step. Those stay sequential.)
             out.append(SendActivationRecvGrad(send_buffer=a.buffer_id, recv_buffer=b.buffer_id))
             i += 2
         elif isinstance(a, SendGrad) and isinstance(b, RecvActivation):

@@ -41,6 +41,48 @@ from deepspeed_b200.utils.nvtx import instrument_w_nvtx
 NOT_GATHERED, INFLIGHT, GATHERED = 0, 1, 2
 
 
+class _InnerOptimizerView:
+    """Read-only face of the flat optimizer in the shape user code expects from ``engine.optimizer.optimizer``."""
+
+    def __init__(self, zo):
+        self._zo = zo
+
+    @property
+    def param_groups(self):
+        return self._zo.param_groups
+
+    @property
+    def state(self):
+        zo = self._zo
+        st = {k: v for k, v in (zo.flat_opt.state_tensors() or {}).items() if torch.is_tensor(v)}
+        st["step"] = max(zo.group_steps) if zo.group_steps else 0
+        key = zo.master if torch.is_tensor(zo.master) else 0
+        return {key: st}
+
+    def state_dict(self):
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return {"state": {0: next(iter(self.state.values()))}, "param_groups": groups}
+
+
+def tag_reference_class(opt):
+    """Give an engine-built optimizer the reference's class for its stage so ``isinstance(engine.optimizer,
+    DeepSpeedZeroOptimizer_Stage3)`` style checks in user code keep working (the subclasses only add the reference's
+    constructor signature)."""
+    if opt.stage == 3:
+        from deepspeed_b200.runtime.zero.stage3 import DeepSpeedZeroOptimizer_Stage3 as cls
+    elif opt.stage in (1, 2):
+        from deepspeed_b200.runtime.zero.stage_1_and_2 import DeepSpeedZeroOptimizer as cls
+    elif opt.model_dtype == torch.float16:
+        from deepspeed_b200.runtime.fp16.fused_optimizer import FP16_Optimizer as cls
+    elif opt.model_dtype == torch.bfloat16:
+        from deepspeed_b200.runtime.bf16_optimizer import BF16_Optimizer as cls
+    else:
+        return opt
+    if type(opt) is ZeroShardedOptimizer:
+        opt.__class__ = cls
+    return opt
+
+
 def _param_status():
     from deepspeed_b200.runtime.zero.partition_parameters import ZeroParamStatus
     return ZeroParamStatus
@@ -1426,6 +1468,28 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             self._uploaded_lp = True
         if self.state_swapper is not None:
             self.state_swapper.flush(self.flat_opt)
+
+    # ---- reference-style introspection (stage3.py / stage_1_and_2.py attribute names) ---------------------------------
+    @property
+    def fp32_partitioned_groups_flat(self):
+        """This rank's fp32 master partition(s). The reference keeps one flat tensor per sub-group; here every unit's
+        shard lives in ONE arena, exposed as a single-entry list."""
+        return [self.master] if torch.is_tensor(self.master) else []
+
+    single_partition_of_fp32_groups = fp32_partitioned_groups_flat
+
+    @property
+    def optimizer(self):
+        """The wrapped optimizer as the reference exposes it (``engine.optimizer.optimizer``): ``param_groups``,
+        ``state`` (this rank's flat moment arenas + step count) and ``state_dict()``."""
+        return _InnerOptimizerView(self)
+
+    @property
+    def state(self):
+        """torch-style ``optimizer.state`` (one entry: this rank's flat moment arenas and the step count)."""
+        return self.optimizer.state
+
+    nccl_start_alignment_factor = 2  # reference constant (element alignment of partition starts); arenas here are 16 B aligned
 
     def _peek_step(self, gi):
         # group_steps is advanced once per global step in step(); during fused-in-backward calls the

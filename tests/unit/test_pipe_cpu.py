@@ -99,11 +99,11 @@ class _Blk(nn.Module):
         return torch.tanh(self.l(x))
 
 
-def _pipe_train(num_stages):
+def _pipe_train(num_stages, micro=4):
     import deepspeed_b200 as ds
     from deepspeed_b200.pipe import LayerSpec, PipelineModule
     torch.manual_seed(0)
-    d, L, micro, mbs = 16, 4, 4, 2
+    d, L, mbs = 16, 4, 2
     ref_layers = [_Blk(d) for _ in range(L)]
     ref = nn.Sequential(*copy.deepcopy(ref_layers))
     w = torch.distributed.get_world_size()
@@ -139,6 +139,16 @@ def _pipe_train(num_stages):
 
 def test_pipeline_two_stages_matches_sequential():
     run_distributed(_pipe_train, 2, (2, ))
+
+
+def test_pipeline_single_micro_batch_per_step():
+    """One micro batch per step: the activation send and the gradient receive of the SAME micro batch are a dependency,
+    not an exchange (they must not be posted as one grouped operation)."""
+    from deepspeed_b200.runtime.pipe import schedule as S
+    fused = S.fuse_exchanges([S.SendActivation(buffer_id=0), S.RecvGrad(buffer_id=0), S.SendActivation(buffer_id=1),
+                              S.RecvGrad(buffer_id=0)])
+    assert [type(c).__name__ for c in fused] == ["SendActivation", "RecvGrad", "SendActivationRecvGrad"]
+    run_distributed(_pipe_train, 2, (2, 1))
 
 
 def test_pipeline_pp2_dp2_matches_sequential():
