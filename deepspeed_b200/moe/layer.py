@@ -56,6 +56,10 @@ class MoE(nn.Module):
             if groups._get_expert_parallel_group(self.expert_group_name) is None and \
                     self.expert_group_name not in groups._expert_parallel_size:
                 groups._create_expert_and_data_parallel(self.ep_size, use_data_before_expert_parallel_)
+        if self.enable_expert_tensor_parallelism:
+            # experts are themselves tensor-sliced: every TP rank runs the exchange on the full token set
+            # (reference groups._create_expert_data_and_model_parallel records the degree the same way)
+            groups.expert_tensor_parallel_world_size = max(int(groups._get_model_parallel_world_size() or 1), 1)
         self.deepspeed_moe._set_ep_group(groups._get_expert_parallel_group(self.expert_group_name))
 
     def forward(self, hidden_states, used_token=None):

@@ -60,7 +60,53 @@ def _capacity(num_tokens, num_experts, capacity_factor, min_capacity, k=1):
 
 
 class GateOutput:
+    """Routing decision in INDEX form (``[T, k]`` expert ids / slots / weights) -- what the permutation kernels consume.
+    Indexing or unpacking it yields the reference's dense 4-tuple ``(l_aux, combine_weights [T, E, C], dispatch_mask
+    [T, E, C], exp_counts)`` (``sharded_moe.py:374``), materialised on demand for code written against that form."""
     __slots__ = ("l_aux", "expert_ids", "weights", "positions", "offsets", "counts", "capacity", "k")
+
+    def dense(self):
+        T, k = self.expert_ids.shape
+        E, C = self.counts.numel(), int(self.capacity)
+        combine = torch.zeros(T, E, C, dtype=self.weights.dtype, device=self.weights.device)
+        pos = self.positions.view(T, k).long()
+        ok = (pos >= 0) & (pos < C)
+        t = torch.arange(T, device=pos.device)[:, None].expand(T, k)
+        combine = combine.index_put((t[ok], self.expert_ids.long()[ok], pos[ok]), self.weights[ok])
+        mask = torch.zeros(T, E, C, dtype=torch.bool, device=pos.device)
+        mask[t[ok], self.expert_ids.long()[ok], pos[ok]] = True
+        return self.l_aux, combine, mask, self.counts
+
+    def __iter__(self):
+        return iter(self.dense())
+
+    def __getitem__(self, i):
+        return self.dense()[i]
+
+    def __len__(self):
+        return 4
+
+
+def _keep_most_probable(ids, probs, counts, offsets, cap):
+    """``drop_policy="probs"`` (reference ``topkgating``): when an expert is over capacity the ``cap`` most probable
+    assignments stay; the survivors take their slots in token order. Dropped assignments get slot ``cap``."""
+    e = ids.reshape(-1).long()
+    n = e.numel()
+    ar = torch.arange(n, device=e.device)
+    by_w = torch.argsort(probs.reshape(-1), descending=True, stable=True)
+    order = by_w[torch.argsort(e[by_w], stable=True)]  # grouped by expert, most probable first
+    off = offsets.long()[:counts.numel()]
+    rank = torch.empty_like(e)
+    rank[order] = ar - off[e[order]]
+    kept = rank < cap
+    tok = torch.argsort(e, stable=True)  # grouped by expert, token order inside
+    kept_t = kept[tok].long()
+    before = torch.cumsum(kept_t, 0) - kept_t
+    base = before[off.clamp(max=max(n - 1, 0))]
+    slot = before - base[e[tok]]
+    pos = torch.empty_like(e)
+    pos[tok] = torch.where(kept_t.bool(), slot, torch.full_like(slot, cap))
+    return pos.to(torch.int32).view_as(ids)
 
 
 def topkgating(logits, k, capacity_factor, min_capacity, drop_tokens=True, ep_group=None, use_rts=False,
@@ -102,6 +148,8 @@ def topkgating(logits, k, capacity_factor, min_capacity, drop_tokens=True, ep_gr
             dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=ep_group)
         cap = int(mx.item())
         cap = max(cap, int(min_capacity))
+    if drop_tokens and drop_policy == "probs":
+        positions = _keep_most_probable(flat_ids, gates.gather(1, ids), counts, offsets, cap).reshape(positions.shape)
     out.expert_ids, out.weights, out.positions, out.offsets, out.counts, out.capacity = flat_ids, w, positions, offsets, \
         counts, cap
     return out
@@ -109,12 +157,12 @@ def topkgating(logits, k, capacity_factor, min_capacity, drop_tokens=True, ep_gr
 
 def top1gating(logits, capacity_factor, min_capacity, used_token=None, noisy_gate_policy=None, drop_tokens=True,
                use_rts=True, ep_group=None, use_tutel=False):
-    return topkgating(logits, 1, capacity_factor, min_capacity, drop_tokens, ep_group, use_rts, noisy_gate_policy)
+    return topkgating(logits, 1, capacity_factor, min_capacity, drop_tokens, ep_group, use_rts, noisy_gate_policy,
+                      drop_policy="position")
 
 
 def top2gating(logits, capacity_factor, min_capacity, drop_tokens=True, ep_group=None, top2_2nd_expert_sampling=True):
-    return topkgating(logits, 2, capacity_factor, min_capacity, drop_tokens, ep_group,
-                      noisy_gate_policy="RSample" if False else None)
+    return topkgating(logits, 2, capacity_factor, min_capacity, drop_tokens, ep_group, drop_policy="position")
 
 
 class TopKGate(nn.Module):
@@ -149,7 +197,10 @@ class TopKGate(nn.Module):
         cf = self.capacity_factor if self.training else self.eval_capacity_factor
         return topkgating(logits, self.k, cf, self.min_capacity, self.drop_tokens, self.ep_group,
                           use_rts=self.use_rts and self.training,
-                          noisy_gate_policy=self.noisy_gate_policy if self.training else None)
+                          noisy_gate_policy=self.noisy_gate_policy if self.training else None,
+                          # the reference routes k = 1 / 2 first come first served (top1gating / top2gating) and ranks
+                          # by probability only on the general top-k path
+                          drop_policy="position" if self.k <= 2 else "probs")
 
 
 class MOELayer(nn.Module):

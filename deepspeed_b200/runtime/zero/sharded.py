@@ -357,6 +357,11 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         self._ensure_grad_arena()
         log_dist(f"ZeroShardedOptimizer[{self.name}]: fused-in-backward step disabled ({reason})", ranks=[0])
 
+    def _apply_pending_defuse(self):
+        reason = getattr(self, "_defuse_after_step", None)
+        if reason and (self.fused_in_backward or self.host_step_in_backward):
+            self.disable_fused_in_backward(reason)
+
     def _ensure_grad_arena(self):
         if self.grad_arena is None:
             st_dev = "cpu" if self.offload_optimizer else self.device
@@ -1527,12 +1532,14 @@ class ZeroShardedOptimizer(ZeROOptimizer):
             for gi in range(len(self.group_steps)):
                 self.group_steps[gi] += 1
             self._post_step()
+            self._apply_pending_defuse()
             return
         if self.fused_in_backward:
             # parameters were already updated unit-by-unit inside backward
             for gi in range(len(self.group_steps)):
                 self.group_steps[gi] += 1
             self._post_step()
+            self._apply_pending_defuse()
             return
         inv_scale = 1.0 / float(self.loss_scale)
         need_norm = self.needs_norm()
@@ -1808,6 +1815,15 @@ class ZeroShardedOptimizer(ZeROOptimizer):
         rt, s = self.unit_of_param[id(p)], self.slot_of_param[id(p)]
         if rt.unsynced is not None:  # inside engine.no_sync(): this rank's local, not yet reduced gradient
             return rt.unsynced[s.offset:s.offset + s.numel].view(s.shape).float().clone()
+        if self.fused_in_backward or self.host_step_in_backward:
+            # the step ran unit by unit inside backward and consumed the gradients as they were produced. Keep them from
+            # the next step on (two-phase step) so that gradient introspection works as in the reference.
+            if getattr(self, "_defuse_after_step", None) is None:
+                self._defuse_after_step = "gradient introspection (safe_get_full_grad)"
+                logger.warning("safe_get_full_grad(): gradients of this step were already consumed by the optimizer step "
+                               "fused into backward; switching to the two-phase step so they are available from the next "
+                               "step on (set zero_optimization.b200_fused_optimizer_in_backward=false to start that way)")
+            return None
         if self.grad_arena is None:
             return None
         return self._gather_arena_piece(self.grad_arena, rt, s)

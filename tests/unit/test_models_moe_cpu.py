@@ -79,3 +79,25 @@ def _moe_ep(stage):
 @pytest.mark.parametrize("stage", [1, 2])
 def test_mixtral_style_moe_expert_parallel_ws2(stage):
     run_distributed(_moe_ep, 2, (stage, ))
+
+
+def test_gate_drop_policies_and_dense_view():
+    """``topkgating`` honours ``drop_policy`` (most probable assignments survive vs first come first served) and its
+    result unpacks into the reference's dense ``(l_aux, combine_weights, dispatch_mask, exp_counts)`` form."""
+    import torch
+    from deepspeed_b200.moe.sharded_moe import topkgating
+    logits = torch.tensor([[0.11, 0.2, 0.1, 0.3], [0.3, 0.4, 0.11, 0.1], [0.11, 0.1, 0.6, 0.5], [0.1, 0.11, 0.7, 0.8]])
+
+    def dense(truth, cap=2):
+        t = torch.zeros(4, 4, cap)
+        i, j, k = torch.tensor(truth).t()
+        t[i, j, k] = 1
+        return t
+
+    probs = topkgating(logits, 2, 1, min_capacity=1, drop_policy="probs")
+    assert torch.equal(dense([[0, 1, 0], [1, 0, 0], [1, 1, 1], [2, 2, 0], [2, 3, 0], [3, 2, 1], [3, 3, 1]]), probs[2])
+    pos = topkgating(logits, 2, 1, min_capacity=1, drop_policy="position")
+    assert torch.equal(dense([[0, 1, 0], [0, 3, 0], [1, 0, 0], [1, 1, 1], [2, 2, 0], [2, 3, 1], [3, 2, 1]]), pos[2])
+    l_aux, combine, mask, counts = pos
+    assert combine.shape == (4, 4, 2) and torch.equal(combine != 0, mask) and counts.tolist() == [1, 2, 2, 3]
+    assert l_aux.ndim == 0

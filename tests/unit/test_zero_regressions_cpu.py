@@ -229,3 +229,31 @@ def _twin_flow_worker():
 
 def test_twin_flow_partial_offload_matches_adamw():
     run_distributed(_twin_flow_worker, 2)
+
+
+def _grad_introspection_worker(stage):
+    import deepspeed_b200 as ds
+    from deepspeed_b200.utils import safe_get_full_grad
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 8))
+    cfg = {"train_micro_batch_size_per_gpu": 2, "optimizer": {"type": "Adam", "params": {"lr": 1e-2}},
+           "zero_optimization": {"stage": stage}}
+    eng, *_ = ds.initialize(model=model, config=cfg)
+    assert eng.optimizer.fused_in_backward  # gas 1, no clipping: the step is fused into backward
+    x = torch.randn(2, 8)
+    seen = []
+    for _ in range(3):
+        eng.backward(eng(x).sum())
+        seen.append([safe_get_full_grad(p) for p in model.parameters()])
+        eng.step()
+    # the first call finds the gradients already consumed and switches to the two-phase step; afterwards they are there
+    assert all(g is None for g in seen[0])
+    for grads in seen[1:]:
+        for g, p in zip(grads, model.parameters()):
+            assert g is not None and tuple(g.shape) == tuple(getattr(p, "ds_shape", p.shape)) and g.abs().sum() > 0
+    assert not eng.optimizer.fused_in_backward
+
+
+@pytest.mark.parametrize("stage", [1, 3])
+def test_safe_get_full_grad_switches_off_the_fused_step(stage):
+    run_distributed(_grad_introspection_worker, 2, (stage, ))
