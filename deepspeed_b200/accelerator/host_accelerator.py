@@ -114,6 +114,9 @@ class HostAccelerator(AcceleratorBase):
     def is_pinned(self, tensor):
         return True
 
+    def device_name(self, device_index=None):
+        return "cpu"  # host tensors carry no index (``torch.device("cpu:0") != tensor.device``); reference cpu_accelerator.py:30
+
     def is_fp16_supported(self):
         return False
 

@@ -154,7 +154,8 @@ def init_distributed(dist_backend: Optional[str] = None,
     if config is not None:
         configure(config)
     if dist_init_required is False:
-        return
+        assert dist.is_initialized(), ("Distributed backend is not initialized. Please set dist_init_required to True or "
+                                       "initialize before calling deepspeed.initialize()")
     if dist.is_initialized():
         if cdb is None:
             from .torch import TorchBackend

@@ -28,9 +28,12 @@ class Init:
             _orig = orig
 
             def __new__(cls, *args, **kwargs):
-                bias = kwargs.get("bias", args[2] if len(args) > 2 else True)
+                # Like the reference wrapper (context_manager.py:50) the layer built here is bias-free unless a bias is asked
+                # for EXPLICITLY; the LoRA / quantised variants have none, so an explicit bias keeps the stock layer
+                # (the reference asserts instead).
+                bias = kwargs.get("bias", args[2] if len(args) > 2 else False)
                 dtype = kwargs.get("dtype") or torch.bfloat16
-                if bias:  # LoRA/quantised variants are bias-free: keep the stock layer where a bias is required
+                if bias:
                     return orig(*args, **kwargs)
                 return OptimizedLinear(args[0] if args else kwargs["in_features"],
                                        args[1] if len(args) > 1 else kwargs["out_features"], lora_config=lora,

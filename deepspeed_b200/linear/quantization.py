@@ -12,7 +12,9 @@ from .config import QuantizationConfig
 
 class QuantizedParameter(nn.Parameter):
 
-    def __new__(cls, data=None, requires_grad=False, quantization_config: QuantizationConfig = None, quantizer=None):
+    def __new__(cls, data=None, requires_grad=False, quantization_config: QuantizationConfig = None, quantizer=None, **state):
+        """``state``: the remaining entries of another instance's ``__dict__`` -- HF clones parameters as
+        ``type(p)(p.data, **p.__dict__)``; an already quantised payload is adopted as is."""
         if requires_grad:
             raise ValueError("requires_grad=True is not supported with QuantizedParameter")
         if data is None:
@@ -21,6 +23,8 @@ class QuantizedParameter(nn.Parameter):
         self.quantization_config = quantization_config or QuantizationConfig()
         self.quantizer = quantizer if quantizer is not None else FP_Quantize(group_size=self.quantization_config.group_size)
         self._orig_shape, self._orig_dtype, self._scale = None, None, None
+        for k, v in state.items():
+            setattr(self, k, v)
         self._ensure_quantized(self)
         return self
 

@@ -82,12 +82,58 @@ class TensorParallel_Layer(nn.Module):
     def is_training_mode(self):
         return self.training
 
+    def __deepcopy__(self, memo):
+        """Process groups cannot be copied (or pickled): the clone shares ``mp_group`` (reference layers.py:214)."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        if self.mp_group is not None:
+            memo[id(self.mp_group)] = self.mp_group
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def _mark(self, *params):
         for p in params:
             if p is not None:
                 p.tensor_model_parallel = True
                 p.model_parallel = True
                 p.ds_tp_world = self.tp_world_size
+                # reference ``config_tp_params`` (layers.py:187): the parameter itself can be reassembled / re-split
+                p.ds_is_replaced_module = True
+                p.gather_params = self.gather_params
+                p._tp_partition = self._tp_partition
+
+    # ---- full <-> shard (reference ``gather_params`` / ``_tp_partition``; export, inspection, consolidation) -----------
+    def _full_of(self, idx, shard):
+        """Full tensor of parameter ``idx`` (0 = weight, 1 = bias) from this rank's shard; ``None`` = not sharded."""
+        return None
+
+    @torch.no_grad()
+    def gather_params(self, params_list):
+        """Replace every sharded parameter of ``params_list`` (``[weight, bias]`` order) by its full tensor; the shard is
+        kept in ``param.data_partition`` for :meth:`_tp_partition`. Collective over the TP group."""
+        for idx, p in enumerate(params_list):
+            if p is None or self.tp_world_size == 1 or getattr(p, "data_partition", None) is not None:
+                continue
+            full = self._full_of(idx, p.data)
+            if full is not None:
+                p.data_partition = p.data
+                p.data = full
+
+    @torch.no_grad()
+    def _tp_partition(self, params_list):
+        """Undo :meth:`gather_params` (values written to the full tensor meanwhile are re-split into the shard)."""
+        for idx, p in enumerate(params_list):
+            part = getattr(p, "data_partition", None) if p is not None else None
+            if part is None:
+                continue
+            part.copy_(self._shard_of(idx, p.data))
+            p.data = part
+            p.data_partition = None
+
+    def _shard_of(self, idx, full):
+        raise NotImplementedError
 
 
 class LinearLayer(TensorParallel_Layer):
@@ -99,6 +145,8 @@ class LinearLayer(TensorParallel_Layer):
         w = module.weight if module is not None else weight
         b = module.bias if module is not None and getattr(module, "bias", None) is not None else bias
         self.support_training = True
+        self._fused_parts, self._granularity = fused_parts, granularity
+        self._sharded = not (skip_partition or self.tp_world_size == 1)
         if skip_partition or self.tp_world_size == 1:
             self.weight, self.bias = nn.Parameter(w.data), (nn.Parameter(b.data) if b is not None else None)
         else:
@@ -110,6 +158,15 @@ class LinearLayer(TensorParallel_Layer):
     def forward(self, input):
         x = ColumnParallel.apply(self.mp_group, input) if self.training else input
         return F.linear(x, self.weight, self.bias)
+
+    def _full_of(self, idx, shard):
+        if not self._sharded:
+            return None
+        shards = _gather_list(shard, self.mp_group, 0)
+        return _unsplit_rows(shards, self._fused_parts, self._granularity)
+
+    def _shard_of(self, idx, full):
+        return _split_rows(full, self.tp_world_size, self.tp_index, self._fused_parts, self._granularity)
 
     def extra_repr(self):
         return f"in={self.weight.shape[1]}, out_local={self.weight.shape[0]}, tp={self.tp_world_size}"
@@ -129,6 +186,23 @@ def _split_rows(t, world, rank, fused_parts=1, granularity=1):
     return torch.cat(outs, dim=0).clone()
 
 
+def _unsplit_rows(shards, fused_parts=1, granularity=1):
+    """Inverse of :func:`_split_rows` given every rank's shard."""
+    world = len(shards)
+    if fused_parts == 1:
+        return torch.cat(shards, dim=0)
+    total = sum(sh.shape[0] for sh in shards)
+    sizes = list(fused_parts) if isinstance(fused_parts, (list, tuple)) else [total // fused_parts] * fused_parts
+    pieces = [[] for _ in sizes]
+    for r, sh in enumerate(shards):
+        off = 0
+        for j, n in enumerate(sizes):
+            a, b = shard_bounds(n, world, r, granularity)
+            pieces[j].append(sh[off:off + (b - a)])
+            off += b - a
+    return torch.cat([torch.cat(ps, dim=0) for ps in pieces], dim=0)
+
+
 class LinearAllreduce(TensorParallel_Layer):
     """Row-parallel: each rank owns ``in/P`` input features (``weight`` columns); outputs are summed."""
 
@@ -143,6 +217,7 @@ class LinearAllreduce(TensorParallel_Layer):
             s, e = shard_bounds(w.shape[1], self.tp_world_size, self.tp_index, granularity)
             self.weight = nn.Parameter(w.data[:, s:e].clone())
         self.bias = nn.Parameter(b.data) if b is not None else None  # replicated, added after the reduce
+        self._granularity = granularity
         self._mark(self.weight)
 
     def forward(self, input):
@@ -151,6 +226,15 @@ class LinearAllreduce(TensorParallel_Layer):
         if self.bias is not None:
             out = out + self.bias
         return out
+
+    def _full_of(self, idx, shard):
+        if idx > 0 or self.tp_world_size == 1:  # the bias is replicated
+            return None
+        return torch.cat(_gather_list(shard, self.mp_group, 1), dim=1)
+
+    def _shard_of(self, idx, full):
+        a, b = shard_bounds(full.shape[1], self.tp_world_size, self.tp_index, self._granularity)
+        return full[:, a:b]
 
 
 class LmHeadLinearAllreduce(LinearAllreduce):
@@ -168,46 +252,56 @@ class LmHeadLinearAllreduce(LinearAllreduce):
 
 
 class GatherReplacedLayerParams:
-    """Context manager: temporarily reassemble the full weight of TP layers (for export / inspection)."""
+    """Context manager: temporarily reassemble the full parameters of tensor-parallel layers (export / inspection;
+    reference layers.py:238). ``module`` may be one TP layer or a container of them; collective over the TP group."""
 
     def __init__(self, params, module, enabled=True):
         self.enabled = enabled
         self.module = module
-        self.params = params if isinstance(params, (list, tuple)) else [params]
-        self._saved = []
+        self.params = list(params) if isinstance(params, (list, tuple)) or not torch.is_tensor(params) else [params]
+        self._layers = []
 
     def __enter__(self):
         if not self.enabled:
             return self
         for m in self.module.modules():
-            if isinstance(m, LinearLayer) and m.tp_world_size > 1:
-                self._saved.append((m, "weight", m.weight.data))
-                m.weight.data = _gather_dim(m.weight.data, m.mp_group, 0)
-            elif isinstance(m, LinearAllreduce) and m.tp_world_size > 1:
-                self._saved.append((m, "weight", m.weight.data))
-                m.weight.data = _gather_dim(m.weight.data, m.mp_group, 1)
+            if isinstance(m, TensorParallel_Layer) and m.tp_world_size > 1:
+                ps = [getattr(m, "weight", None), getattr(m, "bias", None)]
+                m.gather_params(ps)
+                self._layers.append((m, ps))
         return self
 
     def __exit__(self, *exc):
-        for m, name, data in self._saved:
-            getattr(m, name).data = data
-        self._saved.clear()
+        for m, ps in self._layers:
+            m._tp_partition(ps)
+        self._layers.clear()
         return False
 
 
-def _gather_dim(t, group, dim):
+def _gather_list(t, group, dim):
+    """Every TP rank's ``t`` (sizes along ``dim`` may differ: uneven head / granularity shards)."""
     world = dist.get_world_size(group)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device), group=group)
+    mine = torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)
     outs = []
-    for s in sizes:
+    for n in sizes:
         shp = list(t.shape)
-        shp[dim] = int(s.item())
+        shp[dim] = int(n.item())
         outs.append(torch.empty(shp, dtype=t.dtype, device=t.device))
-    dist.all_gather(outs, t.contiguous(), group=group) if len({tuple(o.shape) for o in outs}) == 1 else \
-        [dist.broadcast(o if i != dist.get_rank(group) else o.copy_(t), src=dist.get_global_rank(group, i) if group else i,
-                        group=group) for i, o in enumerate(outs)]
-    return torch.cat(outs, dim=dim)
+    if len({tuple(o.shape) for o in outs}) == 1:
+        dist.all_gather(outs, t.contiguous(), group=group)
+    else:
+        me = dist.get_rank(group)
+        for i, o in enumerate(outs):
+            if i == me:
+                o.copy_(t)
+            dist.broadcast(o, src=dist.get_global_rank(group, i) if group is not None else i, group=group)
+    return outs
+
+
+def _gather_dim(t, group, dim):
+    return torch.cat(_gather_list(t, group, dim), dim=dim)
 
 
 AUTOTP_TRAINING_MODE = False  # set through ``set_autotp_mode``: training builds autograd-aware TP layers

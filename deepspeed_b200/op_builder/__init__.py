@@ -95,6 +95,23 @@ CPUAdagradBuilder = _mk("CPUAdagradBuilder", "cpu_adagrad", "deepspeed_b200.ops.
 CPULionBuilder = _mk("CPULionBuilder", "cpu_lion", "deepspeed_b200.ops.lion.cpu_lion", CpuRuntimeBuilder)
 QuantizerBuilder = _mk("QuantizerBuilder", "quantizer", "deepspeed_b200.ops.quantizer.quantizer")
 FPQuantizerBuilder = _mk("FPQuantizerBuilder", "fp_quantizer", "deepspeed_b200.ops.fp_quantizer.quantize")
+
+
+def _fpq_default_dtype():
+    """Container dtype of the packed codes (reference op_builder/fp_quantizer.py:106)."""
+    import torch
+    return torch.uint8
+
+
+def _fpq_range(q_bits=None):
+    """Largest representable magnitude of the minifloat format with ``q_bits`` storage bits (reference :111)."""
+    from deepspeed_b200.ops.fp_quantizer.quantize import _MANTISSA, _fmt_max
+    assert q_bits in _MANTISSA, f"Please specify the right quantization range for the selected precision {q_bits}!"
+    return _fmt_max(q_bits, _MANTISSA[q_bits])
+
+
+FPQuantizerBuilder.get_default_quant_dtype = staticmethod(_fpq_default_dtype)
+FPQuantizerBuilder.get_quant_range = staticmethod(_fpq_range)
 TransformerBuilder = _mk("TransformerBuilder", "transformer", "deepspeed_b200.ops.transformer.transformer")
 StochasticTransformerBuilder = _mk("StochasticTransformerBuilder", "stochastic_transformer",
                                    "deepspeed_b200.ops.transformer.transformer")

@@ -68,8 +68,9 @@ class FP_Quantize(Quantizer):
         x = input.contiguous().reshape(-1)
         n = x.numel()
         gs = self.group_size
-        assert n % gs == 0, f"numel {n} must be a multiple of group_size {gs}"
-        groups = n // gs
+        if n % gs:  # a ragged tail is quantized as one zero-padded group (reference quantize.py: num_groups rounds up)
+            x = torch.nn.functional.pad(x, (0, gs - n % gs))
+        groups = x.numel() // gs
         bpg = (gs * q_bits + 7) // 8
         if x.is_cuda:
             q = torch.empty(groups * bpg, dtype=torch.uint8, device=x.device)
@@ -104,16 +105,22 @@ class FP_Quantize(Quantizer):
         gs = self.group_size
         groups = scales.numel()
         dtype = self.orig_dtype or torch.bfloat16
+        want = self.orig_shape.numel() if self.orig_shape is not None else groups * gs
+        padded = want < groups * gs  # the last group carries zero padding
         if input_q.is_cuda:
-            out = fp_out if fp_out is not None else torch.empty(groups * gs, dtype=dtype, device=input_q.device)
+            direct = fp_out is not None and not padded
+            out = fp_out if direct else torch.empty(groups * gs, dtype=dtype, device=input_q.device)
             rc = N.cuda().dsb_fp_dequantize(_p(input_q), _p(scales), _p(out), ctypes.c_int64(groups), gs, q_bits, m,
                                             N.dt(out), ctypes.c_void_p(0), 1, N.stream())
             N.check(rc, "fp_dequantize")
         else:
             out = (input_q.reshape(groups, gs) * scales[:, None]).to(dtype).reshape(-1)
-            if fp_out is not None:
-                fp_out.copy_(out.view_as(fp_out))
-                out = fp_out
+            direct = False
+        if padded:
+            out = out[:want]
+        if fp_out is not None and not direct:
+            fp_out.copy_(out.view_as(fp_out))
+            out = fp_out
         return out.view(self.orig_shape) if self.orig_shape is not None and out.numel() == self.orig_shape.numel() else out
 
     def selective_dequantize(self, input_q, indexes, fp_out=None, q_bits=None, q_mantisa_bits=None, scale=None):

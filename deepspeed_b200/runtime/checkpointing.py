@@ -516,6 +516,40 @@ class CheckpointMixin:
                     sd[alias] = sd[canon]
         return sd if dist.get_rank() == 0 else None
 
+    def autotp_size(self):
+        return int(getattr(self._config.tensor_parallel_config, "autotp_size", 0) or 0)
+
+    def _replace_module_consolidated_state_dict(self):
+        """Tensor-parallel training (reference engine.py:3647): full, un-sharded 16-bit weights on the CPU of rank 0,
+        ``None`` elsewhere. Collective -- every rank must call it; one layer is reassembled at a time."""
+        from deepspeed_b200.module_inject.layers import GatherReplacedLayerParams, TensorParallel_Layer
+        sd = OrderedDict() if dist.get_rank() == 0 else None
+
+        def walk(module, prefix):
+            is_tp = isinstance(module, TensorParallel_Layer)
+            with GatherReplacedLayerParams(list(module.parameters(recurse=False)), module, enabled=is_tp):
+                for name, p in module.named_parameters(recurse=False):
+                    if sd is not None:
+                        sd[prefix + name] = p.detach().cpu().clone()
+            if sd is not None:
+                for name, b in module.named_buffers(recurse=False):
+                    if name not in module._non_persistent_buffers_set:
+                        sd[prefix + name] = b.detach().cpu()
+            for name, child in module.named_children():
+                walk(child, prefix + name + ".")
+
+        walk(self.module, "")
+        return sd
+
+    def _consolidated_16bit_state_dict(self, exclude_frozen_parameters=False):
+        """Full 16-bit state dict of a model whose weights are partitioned (ZeRO-3 or tensor parallelism)."""
+        if self.zero_optimization_partition_weights():
+            return self._zero3_consolidated_16bit_state_dict(exclude_frozen_parameters)
+        if self.autotp_size() > 1:
+            return self._replace_module_consolidated_state_dict()
+        raise ValueError("consolidated_16bit_state_dict is only applicable to cases where weights are partitioned, "
+                         "including Zero Stage 3 and tensor parallelism.")
+
     def save_16bit_model(self, save_dir, save_filename="pytorch_model.bin", exclude_frozen_parameters=False):
         path = os.path.join(save_dir, save_filename)
         if self.zero_optimization_partition_weights():
@@ -523,6 +557,8 @@ class CheckpointMixin:
                 logger.info(f"Did not save the model {path} because `stage3_gather_16bit_weights_on_model_save` is False")
                 return False
             sd = self._zero3_consolidated_16bit_state_dict(exclude_frozen_parameters)
+        elif self.autotp_size() > 1:
+            sd = self._replace_module_consolidated_state_dict()  # re-assembled from the tensor-parallel shards
         else:
             sd = self.module_state_dict(exclude_frozen_parameters=exclude_frozen_parameters)
         if dist.get_rank() == 0:

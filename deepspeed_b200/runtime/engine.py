@@ -151,6 +151,8 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
             groups.initialize(mpu=self.mpu)
         elif self.mesh_device is not None:
             groups.mesh_device = self.mesh_device
+            # ``initialize(mesh_param=(dp, sp))`` without ``sequence_parallel_size`` in the config: the mesh is the authority
+            sp = int(groups._get_sequence_parallel_world_size())
         elif sp * tp > 1 and groups.ranks_of("dp") is None:
             groups.initialize(tp_size=tp, sp_size=sp)
         self.seq_parallel_group = groups._get_sequence_parallel_group() if sp > 1 else None

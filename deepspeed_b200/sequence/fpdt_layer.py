@@ -299,6 +299,35 @@ class _FPDTAttentionCore(torch.autograd.Function):
         return dx, dw.to(w.dtype), (db.to(b.dtype) if db is not None else None), None
 
 
+class _FPDTGPUOffloadingAttentionImpl_:
+    """The reference's internal entry point (``fpdt_layer.py:510``) under its own name and ``apply`` signature, for code
+    that calls it directly: ``x [S_local, B, hidden]`` in the load-balanced chunk order -> context ``[B, S_local, heads,
+    head_dim]``. One implementation serves both variants: ``cpu_offloading`` only decides where idle chunks wait."""
+
+    @staticmethod
+    def apply(layernorm_output, attention_mask, inference_params, rotary_pos_emb, spg, scatter_idx, gather_idx, hidden_size,
+              projection_size, hidden_size_per_attention_head, kv_projection_size, qkv_linear_weight, qkv_linear_bias, dropout,
+              num_chunks_attn=8, cpu_offloading=True):
+        assert not dropout, "attention dropout is not supported on the chunked path"
+        d = int(hidden_size_per_attention_head)
+        hq, hkv = int(projection_size) // d, int(kv_projection_size) // d
+        S, B, _ = layernorm_output.shape
+        rope = tuple(rotary_pos_emb) if isinstance(rotary_pos_emb, (tuple, list)) else None
+        offload = bool(cpu_offloading) and layernorm_output.is_cuda
+        cfg = (spg, hq, hkv, d, int(num_chunks_attn), offload, rope)
+        ctx = _FPDTAttentionCore.apply(layernorm_output, qkv_linear_weight, qkv_linear_bias, cfg)
+        return ctx.view(S, B, hq, d).permute(1, 0, 2, 3)
+
+
+class _FPDTGPUAttentionImpl_(_FPDTGPUOffloadingAttentionImpl_):
+
+    @staticmethod
+    def apply(*a):
+        a = list(a) + [8, False][max(0, len(a) - 14):]
+        a[15] = False
+        return _FPDTGPUOffloadingAttentionImpl_.apply(*a)
+
+
 class SequenceChunk:
     """A K/V (or Q) chunk that may live on the host; ``load_to_gpu`` is asynchronous on a side stream."""
 
@@ -332,18 +361,47 @@ class SequenceChunk:
         self.cpu_chunk.copy_(self.gpu_chunk, non_blocking=True)
 
 
-def FPDT_InputConstruct(tokens, labels, loss_mask, attention_mask, position_ids, args=None, sp_size=1, sp_rank=0,
-                        num_chunks=1):
-    """Load-balanced chunk assignment: the global sequence is cut into ``sp_size * num_chunks`` pieces and rank
-    ``r`` takes pieces ``r, r + sp_size, ...`` so every rank owns early *and* late (cheap and expensive causal)
-    positions (reference :79)."""
-    seq = tokens.shape[1]
-    assert seq % (sp_size * num_chunks) == 0
-    piece = seq // (sp_size * num_chunks)
-    idx = torch.cat([torch.arange((c * sp_size + sp_rank) * piece, (c * sp_size + sp_rank + 1) * piece)
-                     for c in range(num_chunks)]).to(tokens.device)
-    take = lambda t: None if t is None else t.index_select(1, idx)
-    return take(tokens), take(labels), take(loss_mask), attention_mask, take(position_ids)
+class FPDT_InputConstruct(torch.nn.Module):
+    """Load-balanced chunk assignment (reference :79): the global sequence is cut into ``sp_size * chunks_per_rank``
+    pieces and rank ``r`` takes pieces ``r, r + sp_size, ...`` so every rank owns early *and* late (cheap and expensive
+    causal) positions. ``generate()`` returns ``(tokens, labels, loss_mask, attention_mask, position_ids)`` for this rank;
+    like the reference the loss mask comes back re-ordered for ALL ranks (rank-major), the other tensors sliced.
+
+    ``args.ds_sequence_parallel_fpdt_chunk_size`` (global tokens per attention chunk) sets the number of chunks per rank;
+    ``num_chunks`` gives it directly."""
+
+    def __init__(self, tokens, labels, loss_mask, attention_mask, position_ids, args=None, sp_size=1, sp_rank=0,
+                 num_chunks=None):
+        super().__init__()
+        self.tokens, self.labels, self.loss_mask = tokens, labels, loss_mask
+        self.attention_mask, self.position_ids = attention_mask, position_ids
+        seq = tokens.shape[1]
+        assert seq % sp_size == 0
+        if num_chunks is None:
+            cs = int(getattr(args, "ds_sequence_parallel_fpdt_chunk_size", seq))
+            assert seq % cs == 0
+            num_chunks = seq // cs
+        local = seq // sp_size
+        assert local % num_chunks == 0
+        self.num_chunk_per_gpu, self.chunk_size = num_chunks, local // num_chunks
+        self.sp_size, self.sp_rank = sp_size, sp_rank
+        self.global_seq_len, self.local_seq_len, self.batch_size = seq, local, tokens.shape[0]
+        self.device = tokens.device
+
+    def _indices(self, rank):
+        n, sp, cs = self.num_chunk_per_gpu, self.sp_size, self.chunk_size
+        return torch.cat([torch.arange((c * sp + rank) * cs, (c * sp + rank + 1) * cs) for c in range(n)]).to(self.device)
+
+    def generate(self):
+        mine = self._indices(self.sp_rank)
+        take = lambda t: None if t is None else t.index_select(1, mine)
+        lm = self.loss_mask
+        if lm is not None:
+            lm = lm.index_select(1, torch.cat([self._indices(r) for r in range(self.sp_size)]))
+        return take(self.tokens), take(self.labels), lm, self.attention_mask, take(self.position_ids)
+
+    def __iter__(self):  # ``tokens, labels, ... = FPDT_InputConstruct(...)``
+        return iter(self.generate())
 
 
 class FPDT_Attention(torch.nn.Module):

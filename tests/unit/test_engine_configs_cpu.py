@@ -229,3 +229,54 @@ def _init_variants_worker(which):
 @pytest.mark.parametrize("which", ["args_path", "param_groups"])
 def test_initialize_variants(which):
     run_distributed(_init_variants_worker, 2, (which, ), timeout=400)
+
+
+def _tp_consolidate_worker(d):
+    import copy
+    import deepspeed_b200 as ds
+    from deepspeed_b200 import comm as dist
+    from deepspeed_b200.module_inject.layers import LinearAllreduce, LinearLayer, set_autotp_mode
+    from deepspeed_b200.utils import groups
+    set_autotp_mode(training=True)
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(16, 32), torch.nn.Linear(32, 16)
+    cfg = {"train_micro_batch_size_per_gpu": 1, "optimizer": {"type": "SGD", "params": {"lr": 0.0}},
+           "tensor_parallel": {"autotp_size": 2}, "zero_optimization": {"stage": 1}}
+    boot, *_ = ds.initialize(model=torch.nn.Linear(2, 2), config=cfg)  # creates the TP groups
+    g = groups.get_tensor_model_parallel_group()
+
+    class TP(torch.nn.Module):
+
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = LinearLayer(copy.deepcopy(a), g), LinearAllreduce(copy.deepcopy(b), g)
+
+        def forward(self, x):
+            return self.b(torch.relu(self.a(x))).sum()
+
+    model = TP()
+    assert model.a.weight.shape == (16, 16) and model.b.weight.shape == (16, 16)
+    # parameter-level API of the reference: gather in place, then re-partition
+    w = model.a.weight
+    w.gather_params([w, model.a.bias])
+    assert torch.equal(w, a.weight) and torch.equal(model.a.bias, a.bias)
+    w._tp_partition([w, model.a.bias])
+    assert w.shape == (16, 16) and model.a.bias.shape == (16, )
+    eng, *_ = ds.initialize(model=model, config=cfg)
+    eng.backward(eng(torch.randn(1, 16)))
+    eng.step()
+    sd = eng._consolidated_16bit_state_dict()
+    assert eng.save_16bit_model(d, "tp.bin")
+    if dist.get_rank() == 0:
+        ref = {"a.weight": a.weight, "a.bias": a.bias, "b.weight": b.weight, "b.bias": b.bias}
+        on_disk = torch.load(os.path.join(d, "tp.bin"), weights_only=False)
+        for k, v in ref.items():
+            torch.testing.assert_close(sd[k].float(), v.detach())
+            torch.testing.assert_close(on_disk[k].float(), v.detach())
+    else:
+        assert sd is None
+    assert model.a.weight.shape == (16, 16)  # shards restored
+
+
+def test_tensor_parallel_training_consolidated_state_dict(tmp_path):
+    run_distributed(_tp_consolidate_worker, 2, (str(tmp_path), ))
