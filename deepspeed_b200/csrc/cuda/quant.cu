@@ -76,9 +76,9 @@ quantize_kernel(const T* __restrict__ x, int8_t* __restrict__ q, float* __restri
     float scale, offset = 0.f;
     if (SYM) {
         const float amax = fmaxf(fabsf(r.lo), fabsf(r.hi));
-        scale = amax > 0.f ? amax / qmax : 1.f;
+        scale = amax > 0.f ? amax / (qmax + 1.f) : 1.f;  // amax -> 2^(b-1); +side saturates
     } else {
-        scale = (r.hi - r.lo) > 0.f ? (r.hi - r.lo) / qmax_asym : 1.f;
+        scale = (r.hi - r.lo) > 0.f ? (r.hi - r.lo) / (qmax_asym + 1.f) : 1.f;
         offset = r.lo;
     }
     const float inv = 1.f / scale;
@@ -155,7 +155,7 @@ loco_quantize_kernel(const T* __restrict__ x, float* __restrict__ err, int8_t* _
     }
     amax = block_reduce<MaxOp>(amax, scratch);
     constexpr float qmax = static_cast<float>((1 << (BITS - 1)) - 1);
-    const float scale = amax > 0.f ? amax / qmax : 1.f;
+    const float scale = amax > 0.f ? amax / (qmax + 1.f) : 1.f;  // amax -> 2^(b-1); +side saturates
     const float inv = 1.f / scale;
     if (threadIdx.x == 0) params[g] = scale;
     int8_t* qg = q + static_cast<int64_t>(g) * out_group_stride_bytes;
@@ -250,9 +250,9 @@ dequant_reduce_kernel(const int8_t* __restrict__ qin, const float* __restrict__ 
     float scale, offset = 0.f;
     if (SYM) {
         const float amax = fmaxf(fabsf(lo), fabsf(hi));
-        scale = amax > 0.f ? amax / qmax : 1.f;
+        scale = amax > 0.f ? amax / (qmax + 1.f) : 1.f;  // amax -> 2^(b-1); +side saturates
     } else {
-        scale = (hi - lo) > 0.f ? (hi - lo) / qmax_asym : 1.f;
+        scale = (hi - lo) > 0.f ? (hi - lo) / (qmax_asym + 1.f) : 1.f;
         offset = lo;
     }
     if (threadIdx.x == 0) {
@@ -297,11 +297,11 @@ fake_quant_kernel(T* __restrict__ x, int group_size, int bits, int sym, int stoc
     float scale, offset = 0.f, lo_q, hi_q;
     if (sym) {
         const float amax = fmaxf(fabsf(r.lo), fabsf(r.hi));
-        scale = amax > 0.f ? amax / qmax : 1.f;
+        scale = amax > 0.f ? amax / (qmax + 1.f) : 1.f;  // amax -> 2^(b-1); +side saturates
         lo_q = -qmax - 1.f;
         hi_q = qmax;
     } else {
-        scale = (r.hi - r.lo) > 0.f ? (r.hi - r.lo) / levels : 1.f;
+        scale = (r.hi - r.lo) > 0.f ? (r.hi - r.lo) / (levels + 1.f) : 1.f;
         offset = r.lo;
         lo_q = 0.f;
         hi_q = levels;

@@ -50,7 +50,9 @@ class aio_handle:
                                            int(self._overlap_events), self._threads)
         if not self._h:
             raise RuntimeError("failed to create the async I/O context")
-        self._inflight = []   # keep tensors alive until wait()
+        self._inflight = []
+        self._dev_reads = []  # (pinned host, device) pairs of asynchronous reads into device tensors
+        # keep tensors alive until wait()
         self._locked = {}
 
     def __del__(self):
@@ -85,14 +87,29 @@ class aio_handle:
 
     # ---- I/O
     def _io(self, fn, buffer, filename, is_async, file_offset):
-        assert buffer.device.type == "cpu" and buffer.is_contiguous(), "aio buffers must be contiguous host tensors"
+        """Reference return convention (``py_lib/deepspeed_py_io_handle.cpp``): a blocking call returns the number of
+        completed requests (1), an asynchronous one returns 0 and ``wait()`` reports the count."""
+        assert buffer.is_contiguous(), "aio buffers must be contiguous"
+        is_read = fn is self._lib.dsb_aio_pread
+        dev_buffer = None
+        if buffer.device.type != "cpu":
+            # device tensors go through a pinned bounce buffer (the GDS handle in ``ops/gds`` is the direct path)
+            dev_buffer = buffer
+            buffer = torch.empty(dev_buffer.shape, dtype=dev_buffer.dtype, device="cpu", pin_memory=torch.cuda.is_available())
+            if not is_read:
+                buffer.copy_(dev_buffer)
         n = buffer.numel() * buffer.element_size()
         rc = fn(self._h, ctypes.c_void_p(buffer.data_ptr()), n, os.fsencode(filename), int(file_offset), int(is_async))
         if rc < 0:
             raise OSError(-rc, f"aio request on {filename} failed: {os.strerror(-rc)}")
         if is_async:
             self._inflight.append(buffer)
-        return rc
+            if dev_buffer is not None and is_read:
+                self._dev_reads.append((buffer, dev_buffer))
+            return 0
+        if dev_buffer is not None and is_read:
+            dev_buffer.copy_(buffer)
+        return 1
 
     def pread(self, buffer, filename, validate=False, async_op=False, file_offset=0):
         return self._io(self._lib.dsb_aio_pread, buffer, filename, async_op, file_offset)
@@ -124,6 +141,9 @@ class aio_handle:
         self._inflight.clear()
         if rc < 0:
             raise OSError(-rc, f"aio wait failed: {os.strerror(-rc)}")
+        for host, dev in self._dev_reads:
+            dev.copy_(host)
+        self._dev_reads.clear()
         return n
 
     # ---- locked host tensors

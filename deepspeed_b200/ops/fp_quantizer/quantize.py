@@ -93,6 +93,10 @@ class FP_Quantize(Quantizer):
     def get_scales(self):
         return self.scales
 
+    @property
+    def scale(self):  # the reference keeps the group scales under this name
+        return self.scales
+
     def to(self, *args, **kwargs):
         if self.scales is not None:
             self.scales = self.scales.to(*args, **kwargs)

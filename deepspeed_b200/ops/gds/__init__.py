@@ -121,14 +121,14 @@ class gds_handle(aio_handle):
             torch.cuda.current_stream().synchronize()
             rc = self._direct(buffer, filename, False, file_offset)
             if rc is not None:
-                return rc
+                return 0 if async_op else 1  # the reference convention: completed requests of a blocking call
         n = buffer.numel() * buffer.element_size()
         host = self._bounce_buf(n)
         super().pread(host, filename, validate, False, file_offset)
         buffer.view(torch.uint8).reshape(-1).copy_(host, non_blocking=True)
         if not async_op:
             torch.cuda.current_stream().synchronize()
-        return n
+        return 0 if async_op else 1
 
     def pwrite(self, buffer, filename, validate=False, async_op=False, file_offset=0):
         if buffer.device.type != "cuda":
@@ -137,12 +137,13 @@ class gds_handle(aio_handle):
             torch.cuda.current_stream().synchronize()
             rc = self._direct(buffer, filename, True, file_offset)
             if rc is not None:
-                return rc
+                return 0 if async_op else 1
         n = buffer.numel() * buffer.element_size()
         host = self._bounce_buf(n)
         host.copy_(buffer.view(torch.uint8).reshape(-1))
         torch.cuda.current_stream().synchronize()
-        return super().pwrite(host, filename, validate, False, file_offset)
+        super().pwrite(host, filename, validate, False, file_offset)
+        return 0 if async_op else 1
 
 
 class GDSBuilder:

@@ -23,7 +23,7 @@ def _host_quant(x, groups, bits, sym, stochastic=False):
     if sym:
         qmax = 2**(bits - 1) - 1
         amax = g.abs().amax(dim=1, keepdim=True)
-        scale = torch.where(amax > 0, amax / qmax, torch.ones_like(amax))
+        scale = torch.where(amax > 0, amax / (qmax + 1), torch.ones_like(amax))  # reference: q_range / (2 * absmax)
         v = g / scale
         v = torch.floor(v + torch.rand_like(v)) if stochastic else torch.round(v)
         q = v.clamp(-qmax - 1, qmax).to(torch.int32)
@@ -31,7 +31,7 @@ def _host_quant(x, groups, bits, sym, stochastic=False):
     else:
         levels = 2**bits - 1
         lo, hi = g.amin(dim=1, keepdim=True), g.amax(dim=1, keepdim=True)
-        scale = torch.where(hi > lo, (hi - lo) / levels, torch.ones_like(hi))
+        scale = torch.where(hi > lo, (hi - lo) / (levels + 1), torch.ones_like(hi))  # reference: q_range / (max - min)
         v = (g - lo) / scale
         v = torch.floor(v + torch.rand_like(v)) if stochastic else torch.round(v)
         q = v.clamp(0, levels).to(torch.int32)
@@ -74,6 +74,10 @@ def quantize(x, groups, num_bits=8, q_type=Symmetric, group_perm=None, stochasti
     assert n % groups == 0
     gs = n // groups
     sym = q_type == Symmetric
+    if x.dim() > 1 and (num_bits == 8 or x.shape[-1] % 2 == 0):
+        # shaped in -> shaped out (the reference binding keeps the activation's shape; 4 bit halves the last dim)
+        q, params = quantize(x.view(-1), groups, num_bits, q_type, group_perm, stochastic, seed)
+        return q.view(*x.shape[:-1], x.shape[-1] if num_bits == 8 else x.shape[-1] // 2), params
     if not x.is_cuda:
         q, params = _host_quant(x, groups, num_bits, sym, stochastic)
         if group_perm is not None:
@@ -116,8 +120,11 @@ def loco_quantize(x, err, groups, num_bits=4, beta=0.8, reset=False):
     return q, params
 
 
-def dequantize(q, params, groups, num_bits=8, q_type=Symmetric, dtype=torch.bfloat16):
+def dequantize(q, params, groups, num_bits=8, q_type=Symmetric, dtype=torch.float16):
     sym = q_type == Symmetric
+    if q.dim() > 1:
+        out = dequantize(q.contiguous().view(-1), params, groups, num_bits, q_type, dtype)
+        return out.view(*q.shape[:-1], q.shape[-1] if num_bits == 8 else q.shape[-1] * 2)
     n = q.numel() * (1 if num_bits == 8 else 2)
     gs = n // groups
     if not q.is_cuda:
@@ -184,14 +191,14 @@ def fake_quantize(x, groups, num_bits, q_type=Symmetric, stochastic=False, seed=
         if sym:
             qmax = 2**(num_bits - 1) - 1
             amax = g.abs().amax(1, keepdim=True)
-            sc = torch.where(amax > 0, amax / qmax, torch.ones_like(amax))
+            sc = torch.where(amax > 0, amax / (qmax + 1), torch.ones_like(amax))
             v = g / sc
             v = torch.floor(v + torch.rand_like(v)) if stochastic else torch.round(v)
             y = v.clamp(-qmax - 1, qmax) * sc
         else:
             lv = 2**num_bits - 1
             lo, hi = g.amin(1, keepdim=True), g.amax(1, keepdim=True)
-            sc = torch.where(hi > lo, (hi - lo) / lv, torch.ones_like(hi))
+            sc = torch.where(hi > lo, (hi - lo) / (lv + 1), torch.ones_like(hi))
             v = (g - lo) / sc
             v = torch.floor(v + torch.rand_like(v)) if stochastic else torch.round(v)
             y = v.clamp(0, lv) * sc + lo
@@ -207,6 +214,22 @@ def ds_quantizer(input, groups=1, bit_num=8, sr=False, asym=False):
     """Reference-compatible entry point (``ops/quantizer/quantizer.py:18``)."""
     return fake_quantize(input, groups, bit_num, Asymmetric if asym else Symmetric, stochastic=sr,
                          seed=int(torch.randint(0, 2**31 - 1, (1, )).item()) if sr else 0)
+
+
+def _binding(sr, asym):
+
+    def fn(vals, groups, bits):
+        return ds_quantizer(vals, groups, bits, sr=sr, asym=asym)
+
+    return fn
+
+
+# the reference extension's entry points (``csrc/quantization/pt_binding.cpp``): one per dtype / rounding / symmetry,
+# all in-place quantize-dequantize; here the dtype is read from the tensor
+ds_quantize_fp32 = ds_quantize_fp16 = ds_quantize_bf16 = _binding(False, False)
+ds_sr_quantize_fp32 = ds_sr_quantize_fp16 = ds_sr_quantize_bf16 = _binding(True, False)
+ds_quantize_asym_fp32 = ds_quantize_asym_fp16 = ds_quantize_asym_bf16 = _binding(False, True)
+ds_sr_quantize_asym_fp32 = ds_sr_quantize_asym_fp16 = ds_sr_quantize_asym_bf16 = _binding(True, True)
 
 
 class Quantizer:

@@ -4,7 +4,7 @@ from typing import Optional
 
 import torch
 
-from deepspeed_b200.ops.kernels.misc_ops import nhwc_bias_add as _nhwc_bias_add
+from deepspeed_b200.ops.spatial import nhwc_bias_add as _nhwc_bias_add  # handles logical-NCHW channels_last tensors
 
 
 def nhwc_bias_add(activation: torch.Tensor, bias: torch.Tensor, other: Optional[torch.Tensor] = None,

@@ -1,4 +1,4 @@
-"""``BiasGeluOp`` (reference ``ops/transformer/inference/op_binding/bias_gelu.py``): ``gelu(activation + bias)``."""
+"""``BiasGeluOp`` (reference ``ops/transformer/inference/op_binding/bias_gelu.py``): ``gelu(activation + bias)`` (tanh approximation, like the reference kernel)."""
 import torch
 import torch.nn.functional as F
 
@@ -11,4 +11,5 @@ from .base import BaseOp
 class BiasGeluOp(BaseOp):
 
     def forward(self, activation: torch.Tensor, bias: torch.Tensor):
-        return T.bias_gelu(activation, bias)
+        # the reference kernel (csrc/transformer/inference/csrc/gelu.cu) evaluates the tanh form in fp32
+        return T.bias_act(activation, bias, "gelu_tanh")

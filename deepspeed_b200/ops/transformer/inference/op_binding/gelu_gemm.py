@@ -11,5 +11,5 @@ from .base import BaseOp, gemm_linear
 class GELUGemmOp(BaseOp):
 
     def forward(self, input: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, weight_out: torch.Tensor):
-        h = T.bias_gelu(gemm_linear(input, weight), bias)
+        h = T.bias_act(gemm_linear(input, weight), bias, "gelu_tanh")
         return gemm_linear(h, weight_out)

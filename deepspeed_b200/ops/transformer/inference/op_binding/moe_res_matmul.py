@@ -1,9 +1,8 @@
-"""``MoEResMatmulOp`` (reference ``ops/transformer/inference/op_binding/moe_res_matmul.py``): residual-MoE mixing ``mlp * coef[..., 0] + moe * coef[..., 1]``."""
+"""``MoEResMatmulOp`` (reference ``ops/transformer/inference/op_binding/moe_res_matmul.py``): residual-MoE mixing with
+per-channel coefficients. ``coef`` arrives transposed, ``[..., 2 * hidden, 1]``: its first ``hidden`` entries weight the
+residual (dense MLP) branch, the second ``hidden`` entries the expert output -- the layout the reference kernel reads
+(``csrc/transformer/inference/csrc/gelu.cu: moe_res_matmul``)."""
 import torch
-import torch.nn.functional as F
-
-from deepspeed_b200.ops.kernels import misc_ops as M  # noqa: F401
-from deepspeed_b200.ops.kernels import transformer_ops as T  # noqa: F401
 
 from .base import BaseOp
 
@@ -11,4 +10,6 @@ from .base import BaseOp
 class MoEResMatmulOp(BaseOp):
 
     def forward(self, residual: torch.Tensor, coef: torch.Tensor, output: torch.Tensor):
-        return residual * coef[..., 0:1] + output * coef[..., 1:2]
+        c = coef.transpose(-1, -2)
+        h = c.shape[-1] // 2
+        return residual * c[..., :h] + output * c[..., h:]

@@ -57,7 +57,7 @@ def test_hpz_secondary_partition():
 
 def _quantized():
     # int8 weights / int4 gradients are lossy: parameters track the exact run within quantisation noise
-    _run({"zero_quantized_weights": True}, 5e-2)
+    _run({"zero_quantized_weights": True}, 6e-2)
     _run({"zero_quantized_gradients": True}, 9e-2)  # Adam turns int4 sign flips of tiny grads into O(lr) moves
 
 
