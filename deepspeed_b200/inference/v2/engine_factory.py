@@ -93,10 +93,12 @@ def build_hf_engine(path, engine_config=None, debug_level=None, dtype=torch.bflo
     return InferenceEngineV2(model, engine_config, tp_group=group)
 
 
-def build_engine_from_model(module, engine_config=None, dtype=None, device=None) -> InferenceEngineV2:
-    """Serve one of this repo's training models (``deepspeed_b200.models``) directly."""
+def build_engine_from_model(module, engine_config=None, dtype=None, device=None, tp_override=None) -> InferenceEngineV2:
+    """Serve one of this repo's training models (``deepspeed_b200.models``) directly.  ``tp_override`` =
+    ``(group, size, rank)`` shards over an explicit process group (the hybrid engine's generation-time TP group)
+    instead of the global tensor-parallel mesh."""
     engine_config = _as_cfg(engine_config)
-    group, tp, rank = _tp(engine_config)
+    group, tp, rank = tp_override if tp_override is not None else _tp(engine_config)
     cfg = module.cfg
     p = next(module.parameters())
     dtype, device = dtype or p.dtype, device or p.device

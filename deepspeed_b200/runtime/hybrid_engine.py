@@ -83,11 +83,33 @@ class DeepSpeedHybridEngine(DeepSpeedEngine):
             ec.state_manager.memory_config.size = max(64, (256 * max_ctx) // 128)
         dtype = self._model_dtype()
         hf_cfg = getattr(self.module, "config", None)
+        group, tp, tp_rank = self._inference_tp()
         if hf_cfg is not None and hasattr(hf_cfg, "model_type"):
-            model = RaggedTransformer(arch_from_hf_config(hf_cfg), None, 1, 0, dtype, self.device)
+            # every rank holds the gathered full weights here; load_hf_weights keeps this rank's TP slice only
+            model = RaggedTransformer(arch_from_hf_config(hf_cfg), group, tp, tp_rank, dtype, self.device)
             load_hf_weights(model, self.module.state_dict().get)
-            return InferenceEngineV2(model, ec)
-        return build_engine_from_model(self.module, ec, dtype=dtype, device=self.device)
+            return InferenceEngineV2(model, ec, tp_group=group) if tp > 1 else InferenceEngineV2(model, ec)
+        return build_engine_from_model(self.module, ec, dtype=dtype, device=self.device,
+                                       tp_override=(group, tp, tp_rank) if tp > 1 else None)
+
+    def _inference_tp(self):
+        """Generation-time tensor parallelism (reference ``hybrid_engine.py:83`` ``inference_mp_group``): consecutive
+        ranks form one TP group; each keeps ``1 / tp`` of the packed inference weights and KV cache, so a generation
+        batch is served by the whole group (prompts are all-gathered inside :meth:`generate`)."""
+        tp = int(getattr(self._hybrid_cfg, "inference_tp_size", 1) or 1)
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if tp <= 1 or world == 1:
+            return None, 1, 0
+        assert world % tp == 0, f"inference_tp_size {tp} must divide the world size {world}"
+        if DeepSpeedHybridEngine.inference_mp_group is None or getattr(self, "_tp_world", None) != (world, tp):
+            rank = dist.get_rank()
+            for first in range(0, world, tp):      # every rank creates every group (collective)
+                ranks = list(range(first, first + tp))
+                g = dist.new_group(ranks)
+                if rank in ranks:
+                    DeepSpeedHybridEngine.inference_mp_group = g
+            self._tp_world = (world, tp)
+        return DeepSpeedHybridEngine.inference_mp_group, tp, dist.get_rank() % tp
 
     def _gather_ctx(self):
         from deepspeed_b200.runtime.zero.partition_parameters import GatheredParameters
@@ -116,8 +138,25 @@ class DeepSpeedHybridEngine(DeepSpeedEngine):
         t1 = time.time()
         input_ids = kwargs.pop("input_ids", inputs[0] if inputs else None)
         eos_default = getattr(getattr(self.module, "config", None), "eos_token_id", None)
+        group, tp, tp_rank = self._inference_tp()
+        if tp > 1:
+            # the TP group decodes one batch: concatenate the members' prompts (reference generate :174-190), decode,
+            # hand every rank its own rows back
+            assert not kwargs.get("do_sample", False), "inference_tp_size > 1 supports greedy decoding (ranks must agree)"
+            ids = input_ids.contiguous()
+            parts = [torch.empty_like(ids) for _ in range(tp)]
+            dist.all_gather(parts, ids, group=group)
+            mask = kwargs.get("attention_mask")
+            if mask is not None:
+                mparts = [torch.empty_like(mask) for _ in range(tp)]
+                dist.all_gather(mparts, mask.contiguous(), group=group)
+                kwargs["attention_mask"] = torch.cat(mparts, 0)
+            bsz = ids.shape[0]
+            input_ids = torch.cat(parts, 0)
         out, self._uid = ragged_generate(self._ragged, input_ids, self._uid, int(self._hybrid_cfg.max_out_tokens),
                                          eos_default=eos_default, **kwargs)
+        if tp > 1:
+            out = out[tp_rank * bsz:(tp_rank + 1) * bsz]
         self._generate_latency = time.time() - t1
         self._t_generate += self._generate_latency
         self._iters += 1
