@@ -247,6 +247,21 @@ class DeepSpeedEngine(CheckpointMixin, EngineConfigAccessors, nn.Module):
         self.basic_optimizer = client_optimizer
         model_dtype, gad = self.get_data_types()
         stage = self.zero_optimization_stage()
+        if stage == 0:
+            # the reference's wrapper table (engine.py:1301 _do_optimizer_sanity_check): without ZeRO only these
+            # (model dtype, gradient-accumulation dtype) pairs exist -- fp32/fp32, fp16/fp16, bf16/fp32 (bf16/bf16 under
+            # pipeline parallelism), amp on fp32 -- anything else is refused instead of silently losing precision
+            if self._config.amp_enabled:
+                if model_dtype != gad:
+                    raise NotImplementedError("Model data type and gradient accumulation data type must be equal to use Amp")
+                if model_dtype in (torch.bfloat16, torch.float16):
+                    raise NotImplementedError("Cannot enable both amp with (legacy) fp16 or bfloat16 mode")
+            elif model_dtype == gad:
+                if model_dtype == torch.bfloat16 and not getattr(self, "pipeline_parallelism", False):
+                    raise NotImplementedError("Bfloat16 wrapper must use a gradient accumulation type of fp32, enable ZeRO "
+                                              "to use Bfloat16 gradient accumulation")
+            elif not (model_dtype == torch.bfloat16 and gad == torch.float32):
+                raise NotImplementedError("unsupported mix of model dtype and gradient accumulation type")
         if stage > 0 and client_optimizer is not None and not c.zero_allow_untested_optimizer:
             from deepspeed_b200.runtime.zero.utils import is_zero_supported_optimizer
             assert is_zero_supported_optimizer(client_optimizer), (

@@ -77,9 +77,56 @@ def tag_reference_class(opt):
     elif opt.model_dtype == torch.bfloat16:
         from deepspeed_b200.runtime.bf16_optimizer import BF16_Optimizer as cls
     else:
-        return opt
+        return _tag_basic_class(opt)
     if type(opt) is ZeroShardedOptimizer:
         opt.__class__ = cls
+    return opt
+
+
+_BASIC_TAGGED = {}
+
+
+def _tag_basic_class(opt):
+    """Stage 0 + fp32: the reference wraps nothing and hands the *basic* optimizer back from ``initialize`` (engine.py
+    ``_configure_optimizer``: ``FusedAdam`` for a config-named Adam, the client's own object / class otherwise), and user
+    code checks ``isinstance(opt, FusedAdam)`` / ``opt == client_optimizer``.  The flat optimizer here also is that
+    class: a (cached) subclass of both, with this implementation first in the MRO."""
+    client = getattr(opt, "client_optimizer", None)
+    if client is not None:
+        basic = type(client)
+    else:
+        name = (getattr(opt, "optimizer_name", None) or "").lower()
+        if name in ("adam", "adamw"):
+            from deepspeed_b200.ops.adam import FusedAdam as basic
+        elif name == "lamb":
+            from deepspeed_b200.ops.lamb import FusedLamb as basic
+        elif name == "lion":
+            from deepspeed_b200.ops.lion import FusedLion as basic
+        elif name == "adagrad":
+            basic = torch.optim.Adagrad
+        elif name == "sgd":
+            basic = torch.optim.SGD
+        else:
+            return opt
+    base = type(opt)
+    if not isinstance(basic, type) or issubclass(base, basic) or type(opt) is not ZeroShardedOptimizer:
+        return opt
+    key = (base, basic)
+    if key not in _BASIC_TAGGED:
+        def __eq__(self, other):
+            return other is self or (other is not None and other is getattr(self, "client_optimizer", None))
+
+        try:
+            _BASIC_TAGGED[key] = type(basic.__name__, (base, basic), {"__eq__": __eq__, "__hash__": object.__hash__,
+                                                                      "__module__": basic.__module__})
+        except TypeError:  # incompatible layouts (a C-extension optimizer class)
+            _BASIC_TAGGED[key] = None
+    cls = _BASIC_TAGGED[key]
+    if cls is not None:
+        try:
+            opt.__class__ = cls
+        except TypeError:
+            pass
     return opt
 
 
@@ -222,6 +269,7 @@ class ZeroShardedOptimizer(ZeROOptimizer):
 
         # ---- param groups ------------------------------------------------------------------
         self.client_optimizer = client_optimizer
+        self.optimizer_name = optimizer_name
         self.flat_opt: FlatOptimizer = build_flat_optimizer(optimizer_name, optimizer_params, client_optimizer)
         self.param_groups = self._make_param_groups(client_optimizer, param_groups, optimizer_params)
         p2g = {}

@@ -280,3 +280,55 @@ def _tp_consolidate_worker(d):
 
 def test_tensor_parallel_training_consolidated_state_dict(tmp_path):
     run_distributed(_tp_consolidate_worker, 2, (str(tmp_path), ))
+
+
+def _basic_optimizer_worker():
+    """Without ZeRO / mixed precision the reference hands the *basic* optimizer back from ``initialize`` (reference
+    tests/unit/runtime/test_ds_initialize.py TestClientOptimizer / TestConfigOptimizer) and refuses (model dtype,
+    gradient-accumulation dtype) pairs that have no wrapper (TestOptimizerImplementation)."""
+    import deepspeed_b200 as ds
+    from deepspeed_b200.ops.adam import FusedAdam
+    g = torch.Generator().manual_seed(0)
+
+    def step(eng):
+        x, y = make_batch(1, 4, g)
+        l = eng(x[:4], y[:4]); eng.backward(l); eng.step()
+        return l.item()
+
+    # config-named Adam -> FusedAdam; still the engine's flat optimizer (it trains)
+    m = SimpleModel()
+    eng, opt, _, _ = ds.initialize(model=m, model_parameters=list(m.parameters()),
+                                   config={"train_batch_size": 4, "optimizer": {"type": "Adam", "params": {"lr": 1e-2}}})
+    assert isinstance(opt, FusedAdam) and isinstance(opt, torch.optim.Optimizer) and opt is eng.optimizer
+    l0 = step(eng); [step(eng) for _ in range(4)]
+    assert step(eng) < l0 * 1.5
+    # client optimizer object -> compares equal to it, is an instance of its class
+    m = SimpleModel()
+    client = torch.optim.Adam(m.parameters(), lr=1e-2)
+    eng, opt, _, _ = ds.initialize(model=m, optimizer=client, config={"train_batch_size": 4})
+    assert opt == client and isinstance(opt, torch.optim.Adam) and not (opt == torch.optim.Adam(m.parameters()))
+    step(eng)
+    # optimizer factory -> instance of what the factory builds
+    m = SimpleModel()
+    eng, opt, _, _ = ds.initialize(model=m, model_parameters=list(m.parameters()), config={"train_batch_size": 4},
+                                   optimizer=lambda params: torch.optim.AdamW(params, lr=1e-2))
+    assert isinstance(opt, torch.optim.AdamW)
+    step(eng)
+    # unsupported dtype pairs without ZeRO are refused; the same pairs are fine with ZeRO
+    for bf16, gad, ok in ((True, "bf16", False), (False, "bf16", False), (True, "fp32", True), (False, "fp32", True),
+                          (True, None, True)):
+        cfg = {"train_batch_size": 4, "bf16": {"enabled": bf16}, "data_types": {"grad_accum_dtype": gad},
+               "optimizer": {"type": "Adam", "params": {"lr": 1e-3}}}
+        m = SimpleModel()
+        if ok:
+            ds.initialize(model=m, model_parameters=list(m.parameters()), config=cfg)
+        else:
+            with pytest.raises(NotImplementedError):
+                ds.initialize(model=m, model_parameters=list(m.parameters()), config=cfg)
+            cfg["zero_optimization"] = {"stage": 1}
+            m = SimpleModel()
+            ds.initialize(model=m, model_parameters=list(m.parameters()), config=cfg)
+
+
+def test_basic_optimizer_class_and_dtype_pairs():
+    run_distributed(_basic_optimizer_worker, 1, timeout=300)
